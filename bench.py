@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""Benchmark of the DQNFlappyBird hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--envs-per-gpu E]
+
+One "step" = one batched ``frame_step`` (physics + render + cv2-exact preprocess into the device
+frame ring) over every env of the job, with i.i.d. Bernoulli(0.5) actions (BASELINE.json
+configs[1]: "batched frame_step + preprocess only, random actions").  Metric: env frames/s, whole
+job.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BYTES_PER_FRAME = 6400 + 64 + 1 + 4 + 1 + 4          # obs + state r/w + action + reward + terminal + score
+METRIC = "env frames/sec (step+render+preproc)"
+UNIT = "frames/s"
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+
+def cpu_port_frames_per_s(n_envs: int, n_steps: int, threads: int, seed: int = 1234):
+    """The oracle port (oracle/flappy_oracle.c: full-frame blits + cv2-exact resize, as the reference
+    does per frame) on `threads` host threads, one env per reference process, random actions p=0.5."""
+    import numpy as np
+    from oracle import flappy_oracle as fo
+    rng = np.random.default_rng(seed)
+    env = fo.OracleEnvs(n_envs, seed=42)
+    acts = (rng.random((n_steps + 2, n_envs)) < 0.5).astype(np.uint8)
+    env.step(acts[0], want_obs=True, threads=threads)
+    env.step(acts[1], want_obs=True, threads=threads)
+    t0 = time.perf_counter()
+    for t in range(n_steps):
+        env.step(acts[2 + t], want_obs=True, threads=threads)
+    dt = time.perf_counter() - t0
+    return n_envs * n_steps / dt, dt
+
+
+def run_reference(args, rank: int, world: int):
+    """--impl reference: the reference's CPU path for the same metric/config.  pygame and TensorFlow are
+    not installable here and a Python reference cannot travel to the GPU box, so this arm times the
+    oracle PORT of the path (kind "port") on all host threads."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = min(cores, 256)
+    n_envs = threads * 4
+    per_step = []
+    # calibrate so that warmup + steps finish within a couple of minutes
+    fps, _ = cpu_port_frames_per_s(n_envs, 2, threads)
+    steps_per_sample = max(2, int(fps * 1.0 / n_envs))        # ~1 s of CPU work per bench step
+    for k in range(args.warmup):
+        cpu_port_frames_per_s(n_envs, max(2, steps_per_sample // 4), threads)
+    total_frames, total_t = 0, 0.0
+    for k in range(args.steps):
+        f, dt = cpu_port_frames_per_s(n_envs, steps_per_sample, threads, seed=k)
+        total_frames += n_envs * steps_per_sample; total_t += dt
+        per_step.append(dt)
+    value = total_frames / total_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "configs[1]: frame_step + render + preprocess, random actions p=0.5 (CPU port of the reference path)",
+                   "envs": n_envs, "frames_per_bench_step": n_envs * steps_per_sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n_envs} envs x {steps_per_sample} frame_steps per bench step on {threads} threads; "
+                                   "as shipped the reference sleeps to 30 frames/s/process (wrapped_flappy_bird.py:179)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import torch
+    import torch.distributed as dist
+    from dqnflappybird_b200.game import GameState
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    E = args.envs_per_gpu
+    gs = GameState(num_envs=E, device=dev, seed=42, history=4, first_env_id=rank * E)
+    rew = torch.empty(E, dtype=torch.float32, device=dev)
+    term = torch.empty(E, dtype=torch.uint8, device=dev)
+    score = torch.empty(E, dtype=torch.int32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        gs.step_random(1, 0.5, 1234, None, rew, term, score)
+
+    # decorrelate episode phases without drawing, then warm up the real step
+    gs.step_random(min(args.decorrelate, 1000), 0.5, 1234, draw=False)
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        one_step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    gs.check_errors()
+
+    # ---- e2e: the reference-facing call with HOST buffers (actions in, reward/terminal/score out)
+    a_h = (torch.rand(E) < 0.5).to(torch.uint8).pin_memory()
+    r_h = torch.zeros(E, dtype=torch.float32).pin_memory()
+    t_h = torch.zeros(E, dtype=torch.uint8).pin_memory()
+    s_h = torch.zeros(E, dtype=torch.int32).pin_memory()
+    for _ in range(3):
+        gs.frame_step_host(a_h, r_h, t_h, s_h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        gs.frame_step_host(a_h, r_h, t_h, s_h)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+
+    if rank != 0:
+        return
+    total_envs = E * world
+    value = total_envs * args.steps / (ms_max * 1e-3)
+    peak, peak_src = measured_peak_hbm()
+    achieved = BYTES_PER_FRAME * E / (ms_max * 1e-3 / args.steps) / 1e9         # per GPU, per launch
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        threads = min(cores, 256)
+        n_envs = threads * 4
+        fps, _ = cpu_port_frames_per_s(n_envs, 2, threads)
+        n_steps = max(4, int(fps * 12.0 / n_envs))           # ~12 s of CPU work
+        fps, dt = cpu_port_frames_per_s(n_envs, n_steps, threads)
+        cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{n_envs} envs x {n_steps} frame_steps ({dt:.1f} s) of the same workload, oracle/flappy_oracle.c on {threads} threads; "
+                         "as shipped the reference is capped at 30 frames/s/process (wrapped_flappy_bird.py:179)"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "configs[1] op mix (batched frame_step + render + preprocess, random actions p=0.5, Philox gaps) "
+                               "at configs[4] scale: 1,048,576 envs / 8 GPUs",
+                   "envs_per_gpu": E, "envs_total": total_envs, "ring": f"u8[{E}][4][80][80] = {E * 25600 / 1e9:.2f} GB per GPU",
+                   "l2": "inputs larger than L2 (ring >> 126 MB; every frame is written once and not re-read)",
+                   "parallelism": f"env-sharded x{world}, no collective"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "env_step_kernel<128,128>",
+                     "algorithmic_bytes_per_frame": BYTES_PER_FRAME},
+        "cpu_baseline": cpu,
+        "e2e": {"value": total_envs * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": E * 1, "d2h_bytes_per_step": E * 9,
+                "note": "fb_env_step_host: pinned host actions in, reward/terminal/score out every step; the 80x80 observation "
+                        "stays in the device ring by design"},
+        "gpu_launches": args.steps,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=131072)
+    ap.add_argument("--decorrelate", type=int, default=1000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,125 @@
+"""ctypes binding of libflappy_b200.so (the C ABI of include/flappy_b200.h).
+
+The library is built in-tree by ``build()`` (nvcc, sm_100a only).  There is no
+CPU fallback: every product entry point raises if the library is missing or
+the call fails.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import glob
+import os
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_PKG, "csrc")
+SO_PATH = os.path.join(_PKG, "libflappy_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+class FlappyError(RuntimeError):
+    pass
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(_CSRC, "*.cu")))
+
+
+def needs_build() -> bool:
+    if not os.path.exists(SO_PATH):
+        return True
+    t = os.path.getmtime(SO_PATH)
+    deps = sources() + glob.glob(os.path.join(_CSRC, "*.cuh")) + glob.glob(os.path.join(_PKG, "..", "include", "*.h"))
+    return any(os.path.getmtime(p) > t for p in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every .cu under csrc/ into libflappy_b200.so for sm_100a."""
+    if not force and not needs_build():
+        return SO_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH] + sources() + ["-lcuda"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise FlappyError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    return SO_PATH
+
+
+_lib = None
+
+_u8p, _i32p, _f32p, _vp = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
+
+_SIGNATURES = {
+    "fb_last_error": ([], C.c_char_p),
+    "fb_version": ([], C.c_int),
+    "fb_assets_load": ([C.c_char_p, C.c_size_t], C.c_int),
+    "fb_resize_tables": ([_i32p], C.c_int),
+    "fb_env_create": ([C.c_int, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)], C.c_int),
+    "fb_env_destroy": ([_vp], C.c_int),
+    "fb_env_num_envs": ([_vp], C.c_int),
+    "fb_env_set_gap_replay": ([_vp, _u8p, C.c_int], C.c_int),
+    "fb_env_reset": ([_vp, _vp], C.c_int),
+    "fb_env_step": ([_vp, C.c_int, _u8p, _u8p, C.c_int, C.c_int, _f32p, _u8p, _i32p, _vp], C.c_int),
+    "fb_env_draw": ([_vp, _u8p, C.c_int, C.c_int, _vp], C.c_int),
+    "fb_env_step_random": ([_vp, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, _u8p, _u8p, C.c_int, C.c_int,
+                            _f32p, _u8p, _i32p, _vp], C.c_int),
+    "fb_env_step_host": ([_vp, _u8p, _u8p, C.c_int, C.c_int, _f32p, _u8p, _i32p, _vp], C.c_int),
+    "fb_env_check": ([_vp, _vp], C.c_int),
+    "fb_env_export_state": ([_vp, _i32p, _vp], C.c_int),
+    "fb_env_import_state": ([_vp, _i32p, _vp], C.c_int),
+    "fb_env_obs_exact": ([_vp, _u8p, _vp], C.c_int),
+    "fb_render_full": ([_vp, C.c_int, C.c_int, _u8p, _vp], C.c_int),
+    "fb_debug_assets_load_host": ([C.c_char_p, C.c_size_t], C.c_int),
+    "fb_debug_host_reset": ([_i32p, _u8p, C.c_int, C.c_uint64, C.c_uint64], C.c_int),
+    "fb_debug_host_step": ([_i32p, C.c_int, _u8p, C.c_int, C.c_uint64, C.c_uint64, _f32p, _u8p, _i32p], C.c_int),
+    "fb_debug_host_obs": ([_i32p, C.c_int, _u8p], C.c_int),
+    "fb_debug_host_mixed": ([_i32p], C.c_int),
+}
+
+
+def declared_symbols():
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    """The loaded library; builds it if the sources are newer.  Raises when it cannot be had."""
+    global _lib
+    if _lib is None:
+        if needs_build():
+            build()
+        L = C.CDLL(SO_PATH)
+        for name, (argtypes, restype) in _SIGNATURES.items():
+            fn = getattr(L, name)            # AttributeError if the header and the library disagree
+            fn.argtypes = argtypes
+            fn.restype = restype
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().fb_last_error().decode("utf-8", "replace")
+        if rc == -4:
+            raise ValueError(msg or "Multiple input actions!")     # wrapped_flappy_bird.py:99-100
+        raise FlappyError(f"{what} failed ({rc}): {msg}")
+
+
+_assets_device = None
+
+
+def ensure_assets(assets_dir: str | None = None, device_index: int = 0):
+    """fb_assets_load once per process/device (flappy_bird_utils.load())."""
+    global _assets_device
+    key = (assets_dir, device_index)
+    if _assets_device == key:
+        return
+    from .assets import load_blob
+    blob = load_blob(assets_dir)
+    check(lib().fb_assets_load(blob, len(blob)), "fb_assets_load")
+    _assets_device = key

@@ -1,0 +1,141 @@
+/*
+ * flappy_b200.h -- C ABI of libflappy_b200.so, the B200 (sm_100a) implementation of
+ * the data-parallel hot path of angela000/DQNFlappyBird.
+ *
+ * The reference has no FFI of its own: its boundary is two duck-typed Python
+ * objects used by a five-line loop (FlappyBirdDQN.py:60-76).  The entry points
+ * below are what a ctypes binding of that boundary calls; the reference symbol
+ * each one replaces is cited next to it.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative fb_status otherwise;
+ *     fb_last_error() returns a thread-local message for the last failure;
+ *   - pointers named *_dev are CUDA device pointers owned by the caller (the
+ *     Python host code lets PyTorch own them); *_host are host pointers;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     all device work is asynchronous on it, no hidden synchronisation, no
+ *     allocation after the *_create call;
+ *   - a handle is used from one host thread at a time;
+ *   - no C++ exception crosses this boundary.
+ */
+#ifndef FLAPPY_B200_H
+#define FLAPPY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB_OBS 80                 /* preprocess output is 80x80, FlappyBirdDQN.py:32 */
+#define FB_FRAME_BYTES 6400
+#define FB_SCREEN_W 288           /* wrapped_flappy_bird.py:16 */
+#define FB_SCREEN_H 512           /* wrapped_flappy_bird.py:17 */
+#define FB_STATE_INTS 16          /* ints per env in fb_env_export_state */
+
+typedef enum {
+    FB_OK = 0,
+    FB_ERR_INVALID = -1,          /* bad argument */
+    FB_ERR_CUDA = -2,             /* CUDA runtime error, see fb_last_error() */
+    FB_ERR_ASSETS = -3,           /* assets missing or not supported by the fast path */
+    FB_ERR_ACTION = -4,           /* an action was not 0/1 (reference: ValueError, wrapped_flappy_bird.py:99-100) */
+    FB_ERR_STATE = -5
+} fb_status;
+
+const char *fb_last_error(void);
+int fb_version(void);
+
+/* ---- assets: flappy_bird_utils.load() + getHitmask (game/flappy_bird_utils.py:16-124)
+ * `packed` is the FBPK blob of dqnflappybird_b200/assets.py.  Derives the hitmask
+ * bit rows, the cv2 coefficient tables and the observation tables and uploads
+ * them to the current device.  Must be called once per process and device
+ * before fb_env_create. */
+int fb_assets_load(const uint8_t *packed_host, size_t n);
+
+/* ---- environment: game.GameState (game/wrapped_flappy_bird.py:58-183), batched */
+typedef struct fb_env fb_env;
+
+/* GameState() x n_envs (wrapped_flappy_bird.py:59-85).  Env k of this handle is
+ * global env `first_env_id + k`: its gap draws come from the Philox4x32-10 stream
+ * (seed, purpose 0, env id) with CPython's randint(0,7) rule (top 4 bits of a
+ * 32-bit word, rejected while >= 8; wrapped_flappy_bird.py:212). */
+int fb_env_create(int n_envs, uint64_t seed, uint64_t first_env_id, fb_env **out);
+int fb_env_destroy(fb_env *env);
+int fb_env_num_envs(const fb_env *env);
+
+/* Replay mode: gap draws are consumed from a logged script instead of Philox.
+ * gaps_dev: u8[n_envs][per_env_len], values 0..7, read modulo per_env_len.
+ * The buffer must stay alive while the handle uses it.  NULL switches back. */
+int fb_env_set_gap_replay(fb_env *env, const uint8_t *gaps_dev, int per_env_len);
+
+/* (Re)run GameState.__init__ for every env: fresh state, cycle phase 0, RNG
+ * position 0, two gap draws each. */
+int fb_env_reset(fb_env *env, void *stream);
+
+/* n_steps x frame_step (wrapped_flappy_bird.py:87-183) + preprocess
+ * (FlappyBirdDQN.py:31-34) for every env.
+ *   actions_dev  u8[n_steps][n_envs]   0 = [1,0] no-op, 1 = [0,1] flap.  Any other
+ *                                      value sets the handle's error flag
+ *                                      (fb_env_check) and is treated as no-op.
+ *   obs_ring_dev u8[n_envs][ring_len][80][80]  frame of step s is written to slot
+ *                                      (ring_slot + s) % ring_len; obs[i][j]: i ~ game x,
+ *                                      j ~ game y (cv2 rows/cols of array3d)
+ *   reward_dev   f32[n_steps][n_envs]  0.1 / 3 / -3  (wrapped_flappy_bird.py:95,148,162)
+ *   terminal_dev u8 [n_steps][n_envs]
+ *   score_dev    i32[n_steps][n_envs]  score before the reset (:155)
+ * Any output pointer may be NULL. */
+int fb_env_step(fb_env *env, int n_steps, const uint8_t *actions_dev, uint8_t *obs_ring_dev, int ring_len,
+                int ring_slot, float *reward_dev, uint8_t *terminal_dev, int32_t *score_dev, void *stream);
+
+/* Draw the CURRENT state of every env into slot ring_slot without stepping (the fast table
+ * path of fb_env_step; used after fb_env_reset / fb_env_import_state). */
+int fb_env_draw(fb_env *env, uint8_t *obs_ring_dev, int ring_len, int ring_slot, void *stream);
+
+/* Same, with actions drawn on the device: step s of env e flaps iff word
+ * (first_step + s) of Philox stream (action_seed, purpose 1, env id) is below
+ * flap_threshold (2^31 = p 0.5).  actions_out_dev (u8[n_steps][n_envs]) may be NULL. */
+int fb_env_step_random(fb_env *env, int n_steps, uint64_t action_seed, uint32_t first_step, uint32_t flap_threshold,
+                       uint8_t *actions_out_dev, uint8_t *obs_ring_dev, int ring_len, int ring_slot,
+                       float *reward_dev, uint8_t *terminal_dev, int32_t *score_dev, void *stream);
+
+/* The reference-facing call with HOST buffers (one frame_step for every env):
+ * copies actions_host (u8[n]) to the device, steps, and copies reward / terminal /
+ * score back; the observation stays in the device ring.  Synchronises `stream`. */
+int fb_env_step_host(fb_env *env, const uint8_t *actions_host, uint8_t *obs_ring_dev, int ring_len, int ring_slot,
+                     float *reward_host, uint8_t *terminal_host, int32_t *score_host, void *stream);
+
+/* Reads and clears the device error flag (synchronises `stream`): FB_OK or FB_ERR_ACTION. */
+int fb_env_check(fb_env *env, void *stream);
+
+/* Parity-test access to the packed state.  out/in: i32[n_envs][16]:
+ * [0] playery [1] playerVelY [2] playerIndex [3] loopIter [4] cycle phase of PLAYER_INDEX_GEN
+ * [5] basex [6] score [7] number of pipes [8..10] pipe x [11..13] gap index (0..7)
+ * [14] RNG draws consumed [15] reserved */
+int fb_env_export_state(fb_env *env, int32_t *out_dev, void *stream);
+int fb_env_import_state(fb_env *env, const int32_t *in_dev, void *stream);
+
+/* Observation of the CURRENT state computed with per-pixel fixed-point arithmetic
+ * only (no tables): the in-library cross-check of the fast path.  obs_dev u8[n_envs][80][80]. */
+int fb_env_obs_exact(fb_env *env, uint8_t *obs_dev, void *stream);
+
+/* image_data of frame_step (wrapped_flappy_bird.py:165-177): u8[n][288][512][3] for envs
+ * [first, first+n) of the handle. */
+int fb_render_full(fb_env *env, int first, int n, uint8_t *rgb_dev, void *stream);
+
+/* The cv2 coefficient tables the library derived: i32[6][80] = sx,a0,a1,sy,b0,b1. */
+int fb_resize_tables(int32_t *out_host);
+
+/* ---- test hooks (host only, no device needed): the library's own physics / table / exact-pixel
+ * code compiled for the host, so the CPU test-suite can pin it against the oracle. */
+int fb_debug_assets_load_host(const uint8_t *packed_host, size_t n);
+int fb_debug_host_reset(int32_t *state16, const uint8_t *gaps, int gaps_len, uint64_t seed, uint64_t env_id);
+int fb_debug_host_step(int32_t *state16, int action, const uint8_t *gaps, int gaps_len, uint64_t seed,
+                       uint64_t env_id, float *reward, uint8_t *terminal, int32_t *score);
+int fb_debug_host_obs(const int32_t *state16, int mode /* 0 tables, 1 per-pixel */, uint8_t *out6400);
+int fb_debug_host_mixed(const int32_t *state16);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLAPPY_B200_H */

