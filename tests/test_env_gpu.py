@@ -99,7 +99,7 @@ def test_4096_envs_vs_oracle(game):
     np.testing.assert_array_equal(gs.export_state().cpu().numpy(), oracle.export_state())
     np.testing.assert_array_equal(obs[:, :NOBS], o_obs)
     last = fo.OracleEnvs(N, gaps=gaps); last.import_state(oracle.export_state())
-    np.testing.assert_array_equal(obs[-1][::8], last.obs_all()[::8] if False else np.stack([last.obs(k) for k in range(0, N, 8)]))
+    np.testing.assert_array_equal(obs[-1][::8], np.stack([last.obs(k) for k in range(0, N, 8)]))
     # in-library cross-check: table path == per-pixel path for every env
     np.testing.assert_array_equal(gs.obs_exact().cpu().numpy(), obs[-1])
 
