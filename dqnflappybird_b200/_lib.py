@@ -75,6 +75,16 @@ _SIGNATURES = {
     "fb_env_import_state": ([_vp, _i32p, _vp], C.c_int),
     "fb_env_obs_exact": ([_vp, _u8p, _vp], C.c_int),
     "fb_render_full": ([_vp, C.c_int, C.c_int, _u8p, _vp], C.c_int),
+    "fb_qnet_create": ([C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)], C.c_int),
+    "fb_qnet_destroy": ([_vp], C.c_int),
+    "fb_qnet_param_count": ([_vp], C.c_int),
+    "fb_qnet_layout": ([_vp, _i32p], C.c_int),
+    "fb_qnet_forward": ([_vp, _f32p, _u8p, C.c_longlong, _i32p, C.c_int, _f32p, _vp], C.c_int),
+    "fb_qnet_act": ([_vp, _f32p, _u8p, C.c_longlong, _i32p, C.c_int, C.c_double, C.c_uint64, C.c_uint64, _vp, _f32p, _u8p, _vp], C.c_int),
+    "fb_qnet_loss_backward": ([_vp, C.c_int, _f32p, _f32p, _u8p, C.c_longlong, _i32p, _i32p, _u8p, _f32p, _u8p, _f32p,
+                               C.c_int, C.c_int, C.c_double, C.c_int, _f32p, _f32p, _f32p, _f32p, _vp], C.c_int),
+    "fb_qnet_adam": ([_vp, _f32p, _f32p, _f32p, _f32p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp], C.c_int),
+    "fb_qnet_sync_target": ([_vp, _f32p, _f32p, _vp], C.c_int),
     "fb_debug_assets_load_host": ([C.c_char_p, C.c_size_t], C.c_int),
     "fb_debug_host_reset": ([_i32p, _u8p, C.c_int, C.c_uint64, C.c_uint64], C.c_int),
     "fb_debug_host_step": ([_i32p, C.c_int, _u8p, C.c_int, C.c_uint64, C.c_uint64, _f32p, _u8p, _i32p], C.c_int),

@@ -1,0 +1,177 @@
+"""Host-side owner of the Q-network tensors; all math runs in libflappy_b200.so (csrc/fb_qnet*.cu).
+
+Reference: the TensorFlow graph every Brain builds (BrainDQN.py:119-163; target copy
+BrainDQNNature.py:75-111; dueling head BrainDuelingDQN_CC.py:68-77) and
+``tf.train.AdamOptimizer(1e-6)`` (BrainDQN.py:163).  PyTorch owns the flat fp32 vectors
+(parameters, target parameters, gradients, Adam slots); nothing here computes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+VARIANTS = {"vanilla": 0, "nature": 1, "double": 2}
+
+
+def truncated_normal_(t: torch.Tensor, std: float, generator=None):
+    """tf.truncated_normal: N(0, std) resampled beyond two standard deviations (BrainDQN.py:122)."""
+    torch.nn.init.trunc_normal_(t, mean=0.0, std=std, a=-2 * std, b=2 * std, generator=generator)
+    return t
+
+
+class FrameBatch:
+    """A view of u8 frames as network inputs: sample b, channel c = base + b*stride + chan_off[c]."""
+
+    def __init__(self, tensor: torch.Tensor, sample_stride: int, chan_off, batch: int, base_offset: int = 0):
+        self.tensor = tensor                      # keeps the storage alive
+        self.ptr = tensor.data_ptr() + base_offset
+        self.sample_stride = int(sample_stride)
+        self.chan_off = (C.c_int32 * 4)(*[int(o) for o in chan_off])
+        self.batch = int(batch)
+
+    @staticmethod
+    def from_ring(ring: torch.Tensor, newest_slot: int) -> "FrameBatch":
+        """Acting input: the last four frames of every env in a ring u8[N][L][80][80], newest last."""
+        N, L = ring.shape[0], ring.shape[1]
+        off = [((newest_slot - 3 + k) % L) * 6400 for k in range(4)]
+        return FrameBatch(ring, L * 6400, off, N)
+
+    @staticmethod
+    def from_stack(frames: torch.Tensor, first: int = 0) -> "FrameBatch":
+        """frames u8[B][F][80][80] with F >= first+4: channels = frames first..first+3."""
+        B, Fr = frames.shape[0], frames.shape[1]
+        assert frames.is_contiguous() and frames.dtype == torch.uint8 and Fr >= first + 4
+        return FrameBatch(frames, Fr * 6400, [(first + k) * 6400 for k in range(4)], B)
+
+
+class QNetwork:
+    def __init__(self, device="cuda:0", hidden: int = 512, dueling: bool = False, max_batch: int = 256, seed: int = 0,
+                 lr: float = 1e-6, beta1: float = 0.9, beta2: float = 0.999, adam_eps: float = 1e-8,
+                 copy_target_at_init: bool = False):
+        if not torch.cuda.is_available():
+            raise _lib.FlappyError("QNetwork needs a CUDA device (B200); there is no CPU path")
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self._L = _lib.lib()
+        h = C.c_void_p()
+        _lib.check(self._L.fb_qnet_create(hidden, int(dueling), max_batch, C.byref(h)), "fb_qnet_create")
+        self._h = h
+        self.hidden, self.dueling, self.max_batch = hidden, bool(dueling), max_batch
+        lay = (C.c_int32 * 16)()
+        _lib.check(self._L.fb_qnet_layout(self._h, lay), "fb_qnet_layout")
+        names = ["w1", "b1", "w2", "b2", "w3", "b3", "wf1", "bf1", "wf2", "bf2", "wv", "bv", "wa", "ba"]
+        self.offsets = {n: int(lay[i]) for i, n in enumerate(names) if lay[i] >= 0}
+        self.n_params = int(lay[14])
+        z = lambda: torch.zeros(self.n_params, dtype=torch.float32, device=self.device)
+        self.params, self.target, self.grads, self.adam_m, self.adam_v = z(), z(), z(), z(), z()
+        self.loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        # TF variable initialisers: truncated_normal(0.01) weights, constant 0.01 biases (BrainDQN.py:122-123);
+        # the target net is initialised INDEPENDENTLY (BrainDQNNature.py:75-102) unless asked otherwise
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        self.params.copy_(self._init_flat(g))
+        self.target.copy_(self.params if copy_target_at_init else self._init_flat(g))
+        self.lr, self.beta1, self.beta2, self.adam_eps = np.float32(lr), np.float32(beta1), np.float32(beta2), np.float32(adam_eps)
+        self.beta1_power, self.beta2_power = np.float32(beta1), np.float32(beta2)      # TF keeps these as fp32 variables
+        self.adam_steps = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._L.fb_qnet_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _sizes(self):
+        order = sorted(self.offsets.items(), key=lambda kv: kv[1])
+        ends = [o for _, o in order[1:]] + [self.n_params]
+        return [(n, o, e - o) for (n, o), e in zip(order, ends)]
+
+    def _init_flat(self, gen) -> torch.Tensor:
+        flat = torch.empty(self.n_params, dtype=torch.float32)
+        for n, o, sz in self._sizes():
+            if n.startswith("b"):
+                flat[o:o + sz] = 0.01
+            else:
+                truncated_normal_(flat[o:o + sz], 0.01, gen)
+        return flat
+
+    def view(self, name: str, which: str = "params") -> torch.Tensor:
+        """Named slice of a flat vector (which in params/target/grads/adam_m/adam_v), TF shapes."""
+        shapes = {"w1": (8, 8, 4, 32), "b1": (32,), "w2": (4, 4, 32, 64), "b2": (64,), "w3": (3, 3, 64, 64), "b3": (64,),
+                  "wf1": (1600, self.hidden), "bf1": (self.hidden,), "wf2": (self.hidden, 2), "bf2": (2,),
+                  "wv": (self.hidden, 1), "bv": (1,), "wa": (self.hidden, 2), "ba": (2,)}
+        o = self.offsets[name]
+        shp = shapes[name]
+        return getattr(self, which)[o:o + int(np.prod(shp))].view(shp)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ---------------------------------------------------------------- forward / act
+    def forward(self, fb: FrameBatch, target: bool = False, out: torch.Tensor | None = None) -> torch.Tensor:
+        """QValue.eval(feed_dict={stateInput: ...}) (BrainDQN.py:100): f32[B][2]."""
+        q = out if out is not None else torch.empty((fb.batch, 2), dtype=torch.float32, device=self.device)
+        p = self.target if target else self.params
+        _lib.check(self._L.fb_qnet_forward(self._h, p.data_ptr(), fb.ptr, fb.sample_stride, fb.chan_off, fb.batch,
+                                           q.data_ptr(), self._stream()), "fb_qnet_forward")
+        return q
+
+    def act(self, fb: FrameBatch, epsilon: float, seed: int, first_env_id: int, rng_pos: torch.Tensor,
+            actions_out: torch.Tensor, q_out: torch.Tensor):
+        """getAction (BrainDQN.py:99-108) for every env of the batch."""
+        _lib.check(self._L.fb_qnet_act(self._h, self.params.data_ptr(), fb.ptr, fb.sample_stride, fb.chan_off, fb.batch,
+                                       float(epsilon), seed, first_env_id, rng_pos.data_ptr(), q_out.data_ptr(),
+                                       actions_out.data_ptr(), self._stream()), "fb_qnet_act")
+        return actions_out
+
+    # ---------------------------------------------------------------- training
+    def loss_backward(self, variant: str, frames: torch.Tensor, actions: torch.Tensor, rewards: torch.Tensor,
+                      terminals: torch.Tensor, is_weights: torch.Tensor | None = None, gamma: float = 0.99,
+                      loss_sum: bool = False, global_batch: int | None = None, abs_err: torch.Tensor | None = None,
+                      q_target: torch.Tensor | None = None) -> torch.Tensor:
+        """frames u8[B][5][80][80]: s = frames 0..3, s' = frames 1..4 of each sample.  Fills self.grads, self.loss."""
+        B = frames.shape[0]
+        assert frames.shape[1:] == (5, 80, 80) and frames.dtype == torch.uint8 and frames.is_contiguous()
+        off_s = (C.c_int32 * 4)(0, 6400, 12800, 19200)
+        off_n = (C.c_int32 * 4)(6400, 12800, 19200, 25600)
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        _lib.check(self._L.fb_qnet_loss_backward(
+            self._h, VARIANTS[variant], self.params.data_ptr(), self.target.data_ptr(), frames.data_ptr(), 5 * 6400,
+            off_s, off_n, actions.data_ptr(), rewards.data_ptr(), terminals.data_ptr(), ptr(is_weights), B,
+            global_batch or B, float(gamma), int(loss_sum), self.grads.data_ptr(), self.loss.data_ptr(), ptr(abs_err),
+            ptr(q_target), self._stream()), "fb_qnet_loss_backward")
+        return self.loss
+
+    def adam_step(self, grad_scale: float = 1.0):
+        """One tf.train.AdamOptimizer step on self.params with self.grads (TF-1 ApplyAdam)."""
+        one = np.float32(1)
+        alpha = np.float32(self.lr * np.sqrt(one - self.beta2_power) / (one - self.beta1_power))
+        _lib.check(self._L.fb_qnet_adam(self._h, self.params.data_ptr(), self.grads.data_ptr(), self.adam_m.data_ptr(),
+                                        self.adam_v.data_ptr(), float(alpha), float(self.beta1), float(self.beta2),
+                                        float(self.adam_eps), float(grad_scale), self._stream()), "fb_qnet_adam")
+        self.beta1_power = np.float32(self.beta1_power * self.beta1)
+        self.beta2_power = np.float32(self.beta2_power * self.beta2)
+        self.adam_steps += 1
+
+    def sync_target(self):
+        """sess.run(target_replace_op) (BrainDQNNature.py:107-111,151-152)."""
+        _lib.check(self._L.fb_qnet_sync_target(self._h, self.target.data_ptr(), self.params.data_ptr(), self._stream()),
+                   "fb_qnet_sync_target")
+
+    # ---------------------------------------------------------------- checkpoint (row N2, weights + Adam slots + powers)
+    def state_dict(self):
+        return {"params": self.params.clone(), "target": self.target.clone(), "adam_m": self.adam_m.clone(),
+                "adam_v": self.adam_v.clone(), "beta1_power": float(self.beta1_power), "beta2_power": float(self.beta2_power),
+                "adam_steps": self.adam_steps, "hidden": self.hidden, "dueling": self.dueling}
+
+    def load_state_dict(self, sd):
+        assert sd["hidden"] == self.hidden and sd["dueling"] == self.dueling
+        for k in ("params", "target", "adam_m", "adam_v"):
+            getattr(self, k).copy_(sd[k])
+        self.beta1_power, self.beta2_power = np.float32(sd["beta1_power"]), np.float32(sd["beta2_power"])
+        self.adam_steps = int(sd["adam_steps"])

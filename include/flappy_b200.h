@@ -126,6 +126,57 @@ int fb_render_full(fb_env *env, int first, int n, uint8_t *rgb_dev, void *stream
 /* The cv2 coefficient tables the library derived: i32[6][80] = sx,a0,a1,sy,b0,b1. */
 int fb_resize_tables(int32_t *out_host);
 
+/* ---- Q-network: the TensorFlow graph of every Brain (BrainDQN.py:119-163; dueling head
+ * BrainDuelingDQN_CC.py:68-77), getAction (BrainDQN.py:99-116), _trainQNetwork (BrainDQN.py:195-223,
+ * BrainDQNNature.py:149-183, BrainDoubleDQN.py:37-69, BrainPrioritizedReplyDQN.py:277-315) and
+ * tf.train.AdamOptimizer (BrainDQN.py:163).
+ *
+ * Parameters, target parameters, gradients and the Adam slots are flat fp32 vectors owned by the
+ * caller, laid out in TF variable-creation order: W_conv1[8,8,4,32] b_conv1[32] W_conv2[4,4,32,64]
+ * b_conv2[64] W_conv3[3,3,64,64] b_conv3[64] W_fc1[1600,H] b_fc1[H] then W_fc2[H,2] b_fc2[2], or for
+ * the dueling net W_fc2_v[H,1] b_fc2_v[1] W_fc2_a[H,2] b_fc2_a[2].  fb_qnet_layout returns the
+ * offsets: {w1,b1,w2,b2,w3,b3,wf1,bf1,wf2,bf2,wv,bv,wa,ba,total,H} (-1 where absent).
+ *
+ * The input of sample b is never materialised as [80,80,4]: channel c (oldest frame first, newest
+ * last, BrainDQN.py:68) is the u8 frame at frames_dev + b*sample_stride + chan_off[c] -- a view of
+ * the frame ring (acting) or of a gathered replay batch (training). */
+typedef struct fb_qnet fb_qnet;
+int fb_qnet_create(int hidden, int dueling, int max_batch, fb_qnet **out);
+int fb_qnet_destroy(fb_qnet *net);
+int fb_qnet_param_count(const fb_qnet *net);
+int fb_qnet_layout(const fb_qnet *net, int32_t *out16_host);
+
+/* QValue.eval (BrainDQN.py:100): q_out_dev f32[batch][2] */
+int fb_qnet_forward(fb_qnet *net, const float *params_dev, const uint8_t *frames_dev, long long sample_stride,
+                    const int32_t *chan_off_host4, int batch, float *q_out_dev, void *stream);
+
+/* getAction (BrainDQN.py:99-108) for `batch` envs: forward, then random.random() <= epsilon ?
+ * randrange(2) : argmax.  Env e draws from Philox stream (seed, purpose 2, first_env_id + e) at
+ * word position rng_pos_dev[e] (updated).  actions_out_dev u8[batch] (0 no-op / 1 flap). */
+int fb_qnet_act(fb_qnet *net, const float *params_dev, const uint8_t *frames_dev, long long sample_stride,
+                const int32_t *chan_off_host4, int batch, double epsilon, uint64_t seed, uint64_t first_env_id,
+                uint32_t *rng_pos_dev, float *q_out_dev, uint8_t *actions_out_dev, void *stream);
+
+/* TD target + loss + backward into grads_dev (not applied).  variant 0 vanilla / 1 Nature target net /
+ * 2 Double; the dueling head is a property of the net; is_weights_dev != NULL selects the PER loss.
+ * s uses channels chan_off_s, s' uses chan_off_next of the same per-sample block.  loss_sum != 0:
+ * sum of squares (BrainDQN.py:162), else mean over global_batch (BrainDQNNature.py:119) so that a
+ * sum-allreduce of the gradients of `batch`-sized shards is the gradient of the global mean loss.
+ * Outputs (any may be NULL): loss f32[1], abs_err f32[batch] (PER, :247), q_target f32[batch]. */
+int fb_qnet_loss_backward(fb_qnet *net, int variant, const float *params_dev, const float *target_params_dev,
+                          const uint8_t *frames_dev, long long sample_stride, const int32_t *chan_off_s_host4,
+                          const int32_t *chan_off_next_host4, const uint8_t *actions_dev, const float *rewards_dev,
+                          const uint8_t *terminals_dev, const float *is_weights_dev, int batch, int global_batch,
+                          double gamma, int loss_sum, float *grads_dev, float *loss_out_dev, float *abs_err_out_dev,
+                          float *q_target_out_dev, void *stream);
+
+/* One TF-1 ApplyAdam step over the flat vector; alpha = lr*sqrt(1-beta2^t)/(1-beta1^t) from the caller. */
+int fb_qnet_adam(fb_qnet *net, float *params_dev, const float *grads_dev, float *m_dev, float *v_dev, float alpha,
+                 float beta1, float beta2, float eps, float grad_scale, void *stream);
+
+/* target_replace_op (BrainDQNNature.py:107-111) */
+int fb_qnet_sync_target(fb_qnet *net, float *target_dev, const float *params_dev, void *stream);
+
 /* ---- test hooks (host only, no device needed): the library's own physics / table / exact-pixel
  * code compiled for the host, so the CPU test-suite can pin it against the oracle. */
 int fb_debug_assets_load_host(const uint8_t *packed_host, size_t n);
