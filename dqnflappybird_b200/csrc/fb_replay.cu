@@ -1,0 +1,399 @@
+// Device-resident replay memory.
+//
+// Replaces
+//   BrainDQN.py:69-72,197-201           collections.deque of (s, a, r, s', terminal) + random.sample
+//   BrainPrioritizedReplyDQN.py:32-104  SumTree (add / update / get_leaf / get_min_prob / total_p)
+//   BrainPrioritizedReplyDQN.py:107-151 Memory (store / sample / batch_update)
+//
+// Storage.  Frames live once, in the env's own ring u8[N][L][80][80]: frame f_t of env e is slot
+// t % L.  Transition k >= 1 of env e is (s_{k-1}, a_k, r_k, s_k, term_k) with s_k = frames
+// k-3..k (times < 0 clamp to f_0, the setInitState replication of BrainDQN.py:239), i.e. 5
+// consecutive ring slots; a/r/term of step k sit in [L][N] arrays at row k % L and are written there
+// directly by the act / step kernels ("append" moves no frame bytes).  With capacity C <= L-4
+// transitions per env the live set at time t is k in [max(1, t-C+1), t]; the population index of
+// random.sample / the SumTree data index is   j = e * cnt + (k - k_lo)   resp.   e * C + (k-1) % C,
+// which for N = 1 is exactly the reference's deque / data_pointer order.
+#include <new>
+
+#include "fb_common.cuh"
+
+// ------------------------------------------------------------------------------ uniform sampling
+// random.sample(population, k) of CPython (Lib/random.py), driven by the 32-bit word stream
+// Philox(seed, purpose 3, stream 0):  _randbelow(n) = getrandbits(n.bit_length()) with rejection,
+// getrandbits(b) = word >> (32 - b).
+//   n <= setsize : partial shuffle of a pool   (sequential, one thread; only during warm-up sizes)
+//   n >  setsize : draw j = _randbelow(n), retry while j was already selected.  Acceptance of a word
+//                  is "in range and first occurrence", which does not depend on evaluation order, so a
+//                  whole CTA draws candidates in parallel, resolves first occurrences through a shared
+//                  hash table (atomicMin on the candidate index) and compacts in candidate order.
+constexpr int kSampThreads = 256, kCandPerThread = 4, kCandPerRound = kSampThreads * kCandPerThread;
+constexpr int kHashSize = 4096;            // distinct keys ever inserted < max batch 512 + one round (1024)
+constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t sample_word(uint64_t seed, uint32_t pos) { return stream_word(seed, 3u, 0ull, pos); }
+
+__global__ void __launch_bounds__(kSampThreads) sample_uniform_kernel(uint32_t n, int batch, uint32_t setsize, uint64_t seed,
+                                                                      uint32_t *word_pos, int32_t *out) {
+    __shared__ uint32_t hbuf[2 * kHashSize];
+    uint32_t *hkey = hbuf, *hidx = hbuf + kHashSize;
+    __shared__ uint32_t warp_tot[kSampThreads / 32];
+    __shared__ uint32_t s_taken, s_consumed;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t pos0 = *word_pos;
+    if (n <= setsize) {                    // pool branch (Lib/random.py: "An n-length list is smaller than a k-length set")
+        uint32_t *pool = hbuf;             // n <= setsize <= 2 * kHashSize
+        for (uint32_t i = tid; i < n; i += kSampThreads) pool[i] = i;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t pos = pos0;
+            for (int i = 0; i < batch; i++) {
+                uint32_t m = n - (uint32_t)i, bits = 32 - __clz(m), j;
+                do { j = sample_word(seed, pos++) >> (32 - bits); } while (j >= m);
+                out[i] = (int32_t)pool[j];
+                pool[j] = pool[m - 1];
+            }
+            *word_pos = pos;
+        }
+        return;
+    }
+    const uint32_t bits = 32 - __clz(n);
+    for (int i = tid; i < kHashSize; i += kSampThreads) { hkey[i] = kEmpty; hidx[i] = kEmpty; }
+    if (tid == 0) { s_taken = 0; s_consumed = 0; }
+    __syncthreads();
+    for (uint32_t round = 0;; round++) {
+        const uint32_t base = round * kCandPerRound + tid * kCandPerThread;     // candidate index = word offset from pos0
+        uint32_t r[kCandPerThread], slot[kCandPerThread];
+#pragma unroll
+        for (int c = 0; c < kCandPerThread; c++) {
+            r[c] = sample_word(seed, pos0 + base + c) >> (32 - bits);
+            slot[c] = kEmpty;
+            if (r[c] < n) {
+                uint32_t h = (r[c] * 2654435761u) >> 20;                          // 12 bits
+                for (;;) {
+                    uint32_t prev = atomicCAS(&hkey[h], kEmpty, r[c]);
+                    if (prev == kEmpty || prev == r[c]) { atomicMin(&hidx[h], base + c); slot[c] = h; break; }
+                    h = (h + 1) & (kHashSize - 1);
+                }
+            }
+        }
+        __syncthreads();
+        uint32_t acc[kCandPerThread], cnt = 0;
+#pragma unroll
+        for (int c = 0; c < kCandPerThread; c++) { acc[c] = slot[c] != kEmpty && hidx[slot[c]] == base + c; cnt += acc[c]; }
+        uint32_t incl = cnt;                                                     // block-wide exclusive scan of cnt
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(~0u, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        uint32_t before = s_taken;
+        for (int w = 0; w < warp; w++) before += warp_tot[w];
+        uint32_t rank = before + incl - cnt;
+#pragma unroll
+        for (int c = 0; c < kCandPerThread; c++)
+            if (acc[c]) {
+                if (rank < (uint32_t)batch) out[rank] = (int32_t)r[c];
+                if (rank == (uint32_t)batch - 1) s_consumed = base + c + 1;
+                rank++;
+            }
+        __syncthreads();
+        if (tid == 0) { uint32_t tot = 0; for (int w = 0; w < kSampThreads / 32; w++) tot += warp_tot[w]; s_taken += tot; }
+        __syncthreads();
+        if (s_taken >= (uint32_t)batch) break;
+    }
+    if (tid == 0) *word_pos = pos0 + s_consumed;
+}
+
+// ------------------------------------------------------------------------------ gather
+struct GatherArgs {
+    const uint8_t *ring; int N, L;
+    const uint8_t *act; const float *rew; const uint8_t *term;       // [L][N]
+    long long t;                 // time of the newest stored transition
+    int cap;                     // C, transitions kept per env
+    int per;                     // 0: idx is a population index of random.sample; 1: a SumTree data index
+    const int32_t *idx; int batch;
+    uint8_t *frames;             // [batch][5][80][80]
+    uint8_t *a_out; float *r_out; uint8_t *t_out;
+    int32_t *env_out, *k_out;    // optional
+};
+
+__global__ void __launch_bounds__(256) gather_kernel(GatherArgs g) {
+    int b = blockIdx.x;
+    if (b >= g.batch) return;
+    long long k_lo = g.t - g.cap + 1; if (k_lo < 1) k_lo = 1;
+    long long cnt = g.t - k_lo + 1;
+    long long j = g.idx[b], k; int e;
+    if (!g.per) { e = (int)(j / cnt); k = k_lo + j % cnt; }
+    else { e = (int)(j / g.cap); long long p = j % g.cap; long long back = (g.t - 1 - p) % g.cap; k = g.t - back; }
+    const uint4 *ring4 = reinterpret_cast<const uint4 *>(g.ring);
+    uint4 *dst = reinterpret_cast<uint4 *>(g.frames) + (size_t)b * 2000;
+#pragma unroll
+    for (int f = 0; f < 5; f++) {
+        long long tf = k - 4 + f; if (tf < 0) tf = 0;                 // setInitState replication of frame 0
+        const uint4 *src = ring4 + ((size_t)e * g.L + (size_t)(tf % g.L)) * 400;
+        for (int q = threadIdx.x; q < 400; q += 256) dst[f * 400 + q] = __ldg(src + q);
+    }
+    if (threadIdx.x == 0) {
+        size_t m = (size_t)(k % g.L) * g.N + e;
+        g.a_out[b] = g.act[m]; g.r_out[b] = g.rew[m]; g.t_out[b] = g.term[m];
+        if (g.env_out) g.env_out[b] = e;
+        if (g.k_out) g.k_out[b] = (int32_t)k;
+    }
+}
+
+// ------------------------------------------------------------------------------ SumTree
+// tree: f64[2*cap-1], node 0 the root, leaves [cap-1, 2cap-2] (BrainPrioritizedReplyDQN.py:39-47).
+__device__ __forceinline__ int node_depth(int idx) { return 31 - __clz(idx + 1); }
+__device__ __forceinline__ int ancestor_at(int idx, int depth_idx, int d) { return ((idx + 1) >> (depth_idx - d)) - 1; }
+
+__global__ void leaf_minmax_kernel(const double *tree, int cap, unsigned long long *out /* [0]=max bits, [1]=min-positive bits */) {
+    unsigned long long mx = 0ull, mn = ~0ull;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        double v = tree[cap - 1 + i];
+        unsigned long long b = (unsigned long long)__double_as_longlong(v);     // non-negative doubles order like their bits
+        if (b > mx) mx = b;
+        if (v > 0.0 && b < mn) mn = b;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        unsigned long long a = __shfl_xor_sync(~0u, mx, o), c = __shfl_xor_sync(~0u, mn, o);
+        mx = a > mx ? a : mx; mn = c < mn ? c : mn;
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMax(&out[0], mx); atomicMin(&out[1], mn); }
+}
+
+// One CTA applies `count` leaf updates tree[leaf_i] = p_i and repairs the inner nodes.
+//   mode 0 "reference": SumTree.update semantics, item after item: change = p - tree[leaf];
+//          every ancestor += change (BrainPrioritizedReplyDQN.py:62-68).  The additions into one node
+//          happen in item order (thread d owns depth d and walks the items in order, keeping the
+//          running node value in a register), so the float64 rounding history equals the reference's.
+//   mode 1 "rebuild": leaves are set, then every touched ancestor is recomputed as left + right,
+//          deepest level first.  Deterministic, parallel, no drift; used for N > 1 at scale.
+// leaves: tree indices.  prio: f64[count] or nullptr -> use *store_prio_bits (max leaf, 1.0 if 0) for all.
+__global__ void __launch_bounds__(1024) tree_update_kernel(double *tree, int cap, const int32_t *leaves, const double *prio,
+                                                           const unsigned long long *store_prio_bits, int count, int mode,
+                                                           double *change_scratch) {
+    const int tid = threadIdx.x;
+    const int max_depth = node_depth(2 * cap - 2);
+    __shared__ double s_store;
+    if (tid == 0) {
+        double p = 1.0;
+        if (store_prio_bits) { p = __longlong_as_double((long long)store_prio_bits[0]); if (p == 0.0) p = 1.0; }   // Memory.store :121-125
+        s_store = p;
+    }
+    __syncthreads();
+    if (mode == 0) {
+        if (tid == 0)
+            for (int i = 0; i < count; i++) {
+                int leaf = leaves[i];
+                double p = prio ? prio[i] : s_store;
+                change_scratch[i] = p - tree[leaf];
+                tree[leaf] = p;
+            }
+        __syncthreads();
+        if (tid < max_depth) {              // thread d repairs depth d
+            int d = tid, cur = -1; double val = 0.0;
+            for (int i = 0; i < count; i++) {
+                int leaf = leaves[i], dl = node_depth(leaf);
+                if (dl <= d) continue;
+                int node = ancestor_at(leaf, dl, d);
+                if (node != cur) { if (cur >= 0) tree[cur] = val; cur = node; val = tree[node]; }
+                val += change_scratch[i];
+            }
+            if (cur >= 0) tree[cur] = val;
+        }
+        return;
+    }
+    for (int i = tid; i < count; i += blockDim.x) tree[leaves[i]] = prio ? prio[i] : s_store;
+    __syncthreads();
+    for (int d = max_depth - 1; d >= 0; d--) {
+        for (int i = tid; i < count; i += blockDim.x) {
+            int leaf = leaves[i], dl = node_depth(leaf);
+            if (dl > d) { int node = ancestor_at(leaf, dl, d); tree[node] = tree[2 * node + 1] + tree[2 * node + 2]; }
+        }
+        __syncthreads();
+    }
+}
+
+// Memory.sample (BrainPrioritizedReplyDQN.py:127-144): stratified v_i = uniform(i seg, (i+1) seg) with
+// np.random.uniform's 53-bit construction from two stream words (purpose 4), SumTree.get_leaf descent
+// (:73-100, "v <= tree[left]" goes left), ISWeights = (p/total / min_prob)^-beta in float64.
+// The top five levels of the tree are held in lane registers and walked with warp shuffles.
+__global__ void per_sample_kernel(const double *tree, int cap, int batch, double beta, const unsigned long long *minmax,
+                                  uint64_t seed, uint32_t *word_pos, int32_t *tree_idx, int32_t *data_idx, double *isw,
+                                  double *prio_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const int n_nodes = 2 * cap - 1;
+    const double top = lane < 31 && lane < n_nodes ? tree[lane] : 0.0;      // nodes 0..30 = depths 0..4
+    const double total = __shfl_sync(~0u, top, 0);
+    const uint32_t pos0 = *word_pos;
+    const bool live = i < batch;
+    double v = 0.0;
+    if (live) {
+        double seg = total / (double)batch, a = seg * (double)i, b = seg * (double)(i + 1);
+        uint32_t w0 = stream_word(seed, 4u, 0ull, pos0 + 2 * i) >> 5, w1 = stream_word(seed, 4u, 0ull, pos0 + 2 * i + 1) >> 6;
+        double u = ((double)w0 * 67108864.0 + (double)w1) / 9007199254740992.0;
+        v = a + (b - a) * u;
+    }
+    int parent = 0;
+#pragma unroll
+    for (int lvl = 0; lvl < 4; lvl++) {                                      // shuffle-walk while children are in registers
+        int cl = 2 * parent + 1;
+        double left = __shfl_sync(~0u, top, cl < 31 ? cl : 0);
+        if (cl + 1 < n_nodes && cl < 31) { if (v <= left) parent = cl; else { v -= left; parent = cl + 1; } }
+    }
+    if (live) {
+        for (;;) {
+            int cl = 2 * parent + 1;
+            if (cl >= n_nodes) break;
+            double left = tree[cl];
+            if (v <= left) parent = cl; else { v -= left; parent = cl + 1; }
+        }
+        double p = tree[parent];
+        double min_p = __longlong_as_double((long long)minmax[1]);
+        double prob = p / total, min_prob = min_p / total;
+        tree_idx[i] = parent;
+        data_idx[i] = parent - (cap - 1);
+        isw[i] = pow(prob / min_prob, -beta);
+        if (prio_out) prio_out[i] = p;
+    }
+    __syncthreads();
+    if (i == 0) *word_pos = pos0 + 2 * (uint32_t)batch;
+}
+
+// Memory.batch_update's transform (:146-149): float32 like the numpy arrays the reference holds
+__global__ void per_priority_kernel(const float *abs_err, int count, double *prio) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    float e = abs_err[i] + 0.01f;
+    float c = fminf(e, 1.0f);
+    prio[i] = (double)powf(c, 0.6f);
+}
+
+__global__ void store_leaves_kernel(int N, int C, long long k, int32_t *leaves) {   // leaf of transition k for every env
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N) return;
+    leaves[e] = (N * C - 1) + e * C + (int)((k - 1) % C);
+}
+
+// ------------------------------------------------------------------------------ C ABI
+struct fb_replay {
+    int N, L, C, cap;
+    double *tree;                    // PER only
+    unsigned long long *minmax;      // [0] max leaf bits, [1] min positive leaf bits
+    int32_t *leaves; double *prio; double *change;   // scratch, max(N, max_batch)
+    uint32_t *word_pos;              // [0] uniform stream, [1] PER stream
+    int scratch_n;
+};
+
+extern "C" int fb_replay_create(int n_envs, int ring_len, int capacity_per_env, int prioritized, int max_batch, fb_replay **out) {
+    FB_REQUIRE(out && n_envs > 0 && ring_len >= 5 && capacity_per_env >= 1 && capacity_per_env <= ring_len - 4 && max_batch > 0 && max_batch <= 512,
+               "fb_replay_create: need ring_len >= capacity_per_env + 4 and 0 < max_batch <= 512");
+    FB_REQUIRE((long long)n_envs * capacity_per_env < (1ll << 30), "fb_replay_create: capacity too large");
+    fb_replay *r = new (std::nothrow) fb_replay();
+    FB_REQUIRE(r != nullptr, "fb_replay_create: out of host memory");
+    r->N = n_envs; r->L = ring_len; r->C = capacity_per_env; r->cap = n_envs * capacity_per_env; r->tree = nullptr;
+    r->scratch_n = n_envs > max_batch ? n_envs : max_batch;
+    FB_CUDA_OK(cudaMalloc(&r->word_pos, 2 * sizeof(uint32_t)));
+    FB_CUDA_OK(cudaMemset(r->word_pos, 0, 2 * sizeof(uint32_t)));
+    FB_CUDA_OK(cudaMalloc(&r->minmax, 2 * sizeof(unsigned long long)));
+    FB_CUDA_OK(cudaMalloc(&r->leaves, sizeof(int32_t) * r->scratch_n));
+    FB_CUDA_OK(cudaMalloc(&r->prio, sizeof(double) * r->scratch_n));
+    FB_CUDA_OK(cudaMalloc(&r->change, sizeof(double) * r->scratch_n));
+    if (prioritized) {
+        FB_CUDA_OK(cudaMalloc(&r->tree, sizeof(double) * (2 * (size_t)r->cap - 1)));
+        FB_CUDA_OK(cudaMemset(r->tree, 0, sizeof(double) * (2 * (size_t)r->cap - 1)));
+    }
+    *out = r;
+    return FB_OK;
+}
+
+extern "C" int fb_replay_destroy(fb_replay *r) {
+    if (!r) return FB_OK;
+    cudaFree(r->tree); cudaFree(r->minmax); cudaFree(r->leaves); cudaFree(r->prio); cudaFree(r->change); cudaFree(r->word_pos);
+    delete r;
+    return FB_OK;
+}
+
+extern "C" int fb_replay_sample_uniform(fb_replay *r, long long t, int batch, uint32_t setsize, uint64_t seed,
+                                        int32_t *idx_out_dev, void *stream) {
+    FB_REQUIRE(r && idx_out_dev && batch > 0 && batch <= 512, "fb_replay_sample_uniform: bad argument");
+    long long k_lo = t - r->C + 1; if (k_lo < 1) k_lo = 1;
+    long long n = (t - k_lo + 1) * r->N;
+    if (t < 1 || n < batch) { fb_set_error("Sample larger than population or is negative"); return FB_ERR_INVALID; }   // random.sample's ValueError
+    FB_REQUIRE(setsize <= 2u * kHashSize, "fb_replay_sample_uniform: setsize too large");
+    sample_uniform_kernel<<<1, kSampThreads, 0, (cudaStream_t)stream>>>((uint32_t)n, batch, setsize, seed, r->word_pos, idx_out_dev);
+    FB_CUDA_OK(cudaGetLastError());
+    return FB_OK;
+}
+
+extern "C" int fb_replay_gather(fb_replay *r, const uint8_t *ring_dev, const uint8_t *act_dev, const float *rew_dev,
+                                const uint8_t *term_dev, long long t, int prioritized_index, const int32_t *idx_dev, int batch,
+                                uint8_t *frames_out_dev, uint8_t *act_out_dev, float *rew_out_dev, uint8_t *term_out_dev,
+                                int32_t *env_out_dev, int32_t *k_out_dev, void *stream) {
+    FB_REQUIRE(r && ring_dev && act_dev && rew_dev && term_dev && idx_dev && frames_out_dev && act_out_dev && rew_out_dev && term_out_dev && batch > 0,
+               "fb_replay_gather: bad argument");
+    GatherArgs g{ring_dev, r->N, r->L, act_dev, rew_dev, term_dev, t, r->C, prioritized_index, idx_dev, batch,
+                 frames_out_dev, act_out_dev, rew_out_dev, term_out_dev, env_out_dev, k_out_dev};
+    gather_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(g);
+    FB_CUDA_OK(cudaGetLastError());
+    return FB_OK;
+}
+
+static int refresh_minmax(fb_replay *r, cudaStream_t st) {
+    unsigned long long init[2] = {0ull, ~0ull};
+    FB_CUDA_OK(cudaMemcpyAsync(r->minmax, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    int blocks = (r->cap + 255) / 256; if (blocks > 592) blocks = 592;
+    leaf_minmax_kernel<<<blocks, 256, 0, st>>>(r->tree, r->cap, r->minmax);
+    FB_CUDA_OK(cudaGetLastError());
+    return FB_OK;
+}
+
+// Memory.store for transition k of every env (env order): priority = max leaf (1.0 if all zero)
+extern "C" int fb_per_store(fb_replay *r, long long k, int mode, void *stream) {
+    FB_REQUIRE(r && r->tree && k >= 1 && (mode == 0 || mode == 1), "fb_per_store: bad argument (is the replay prioritized?)");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = refresh_minmax(r, st); if (rc) return rc;
+    store_leaves_kernel<<<(r->N + 255) / 256, 256, 0, st>>>(r->N, r->C, k, r->leaves);
+    tree_update_kernel<<<1, 1024, 0, st>>>(r->tree, r->cap, r->leaves, nullptr, r->minmax, r->N, mode, r->change);
+    FB_CUDA_OK(cudaGetLastError());
+    return FB_OK;
+}
+
+extern "C" int fb_per_sample(fb_replay *r, int batch, double beta, uint64_t seed, int32_t *tree_idx_dev, int32_t *data_idx_dev,
+                             double *is_weights_dev, double *prio_out_dev, void *stream) {
+    FB_REQUIRE(r && r->tree && batch > 0 && batch <= 512 && tree_idx_dev && data_idx_dev && is_weights_dev, "fb_per_sample: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = refresh_minmax(r, st); if (rc) return rc;
+    per_sample_kernel<<<1, ((batch + 31) / 32) * 32, 0, st>>>(r->tree, r->cap, batch, beta, r->minmax, seed, r->word_pos + 1,
+                                                            tree_idx_dev, data_idx_dev, is_weights_dev, prio_out_dev);
+    FB_CUDA_OK(cudaGetLastError());
+    return FB_OK;
+}
+
+// Memory.batch_update: either from |TD errors| (abs_err_dev f32, transform on device) or from given priorities
+extern "C" int fb_per_update(fb_replay *r, const int32_t *tree_idx_dev, const float *abs_err_dev, const double *prio_dev, int batch,
+                             int mode, void *stream) {
+    FB_REQUIRE(r && r->tree && tree_idx_dev && (abs_err_dev || prio_dev) && batch > 0 && batch <= r->scratch_n && (mode == 0 || mode == 1),
+               "fb_per_update: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const double *p = prio_dev;
+    if (!p) { per_priority_kernel<<<(batch + 255) / 256, 256, 0, st>>>(abs_err_dev, batch, r->prio); p = r->prio; }
+    tree_update_kernel<<<1, 1024, 0, st>>>(r->tree, r->cap, tree_idx_dev, p, nullptr, batch, mode, r->change);
+    FB_CUDA_OK(cudaGetLastError());
+    return FB_OK;
+}
+
+extern "C" int fb_per_tree_copy(fb_replay *r, double *out_dev, int n_nodes, void *stream) {
+    FB_REQUIRE(r && r->tree && out_dev && n_nodes == 2 * r->cap - 1, "fb_per_tree_copy: bad argument");
+    FB_CUDA_OK(cudaMemcpyAsync(out_dev, r->tree, sizeof(double) * (size_t)n_nodes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return FB_OK;
+}
+
+extern "C" int fb_replay_rng_pos(fb_replay *r, uint32_t *pos_host2, int set, void *stream) {
+    FB_REQUIRE(r && pos_host2, "fb_replay_rng_pos: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (set) FB_CUDA_OK(cudaMemcpyAsync(r->word_pos, pos_host2, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    else FB_CUDA_OK(cudaMemcpyAsync(pos_host2, r->word_pos, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    FB_CUDA_OK(cudaStreamSynchronize(st));
+    return FB_OK;
+}

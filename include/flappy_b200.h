@@ -177,6 +177,44 @@ int fb_qnet_adam(fb_qnet *net, float *params_dev, const float *grads_dev, float 
 /* target_replace_op (BrainDQNNature.py:107-111) */
 int fb_qnet_sync_target(fb_qnet *net, float *target_dev, const float *params_dev, void *stream);
 
+/* ---- replay memory: the deque + random.sample of BrainDQN.py:69-72,197-201 and the SumTree / Memory of
+ * BrainPrioritizedReplyDQN.py:32-151, over the env's own frame ring (no frame is copied on append).
+ * Transition k >= 1 of env e is (s_{k-1}, a_k, r_k, s_k, term_k), s_k = frames k-3..k of the ring
+ * u8[N][ring_len][80][80]; a/r/term of step k live in [ring_len][N] arrays at row k % ring_len (the step /
+ * act kernels write them there).  capacity_per_env C <= ring_len-4 transitions are live per env; the
+ * population of random.sample at time t is j = e*cnt + (k-k_lo), k_lo = max(1,t-C+1), cnt = t-k_lo+1, and
+ * the SumTree data index is e*C + (k-1)%C -- for one env exactly the reference's deque / data_pointer order. */
+typedef struct fb_replay fb_replay;
+int fb_replay_create(int n_envs, int ring_len, int capacity_per_env, int prioritized, int max_batch, fb_replay **out);
+int fb_replay_destroy(fb_replay *r);
+
+/* random.sample(replayMemory, batch) (BrainDQN.py:197) with CPython's algorithm over the word stream
+ * Philox(seed, purpose 3).  setsize is CPython's threshold 21 + 4**ceil(log(3*batch, 4)) (computed by the
+ * caller with the same float expression).  idx_out_dev i32[batch] population indices.  FB_ERR_INVALID with
+ * "Sample larger than population or is negative" when batch exceeds the population (ValueError). */
+int fb_replay_sample_uniform(fb_replay *r, long long t, int batch, uint32_t setsize, uint64_t seed, int32_t *idx_out_dev, void *stream);
+
+/* minibatch assembly: frames_out_dev u8[batch][5][80][80] (s = frames 0..3, s' = frames 1..4), action / reward /
+ * terminal per sample; idx are population indices (prioritized_index 0) or SumTree data indices (1). */
+int fb_replay_gather(fb_replay *r, const uint8_t *ring_dev, const uint8_t *act_dev, const float *rew_dev, const uint8_t *term_dev,
+                     long long t, int prioritized_index, const int32_t *idx_dev, int batch, uint8_t *frames_out_dev,
+                     uint8_t *act_out_dev, float *rew_out_dev, uint8_t *term_out_dev, int32_t *env_out_dev, int32_t *k_out_dev,
+                     void *stream);
+
+/* Memory.store (:121-125) of transition k for every env, in env order.  mode 0 = the reference's
+ * "every ancestor += change" arithmetic in item order (bit-exact rounding history); mode 1 = set leaves
+ * and recompute touched ancestors as left+right (parallel, deterministic). */
+int fb_per_store(fb_replay *r, long long k, int mode, void *stream);
+/* Memory.sample (:127-144); beta is the already-incremented value.  Word stream Philox(seed, purpose 4). */
+int fb_per_sample(fb_replay *r, int batch, double beta, uint64_t seed, int32_t *tree_idx_dev, int32_t *data_idx_dev,
+                  double *is_weights_dev, double *prio_out_dev, void *stream);
+/* Memory.batch_update (:146-151): priorities from |TD error| (abs_err_dev, fp32 like the reference's arrays)
+ * or given directly (prio_dev f64). */
+int fb_per_update(fb_replay *r, const int32_t *tree_idx_dev, const float *abs_err_dev, const double *prio_dev, int batch, int mode, void *stream);
+/* copy of the SumTree array (f64[2*N*C-1]) for inspection / checkpoints */
+int fb_per_tree_copy(fb_replay *r, double *out_dev, int n_nodes, void *stream);
+int fb_replay_rng_pos(fb_replay *r, uint32_t *pos_host2, int set, void *stream);
+
 /* ---- test hooks (host only, no device needed): the library's own physics / table / exact-pixel
  * code compiled for the host, so the CPU test-suite can pin it against the oracle. */
 int fb_debug_assets_load_host(const uint8_t *packed_host, size_t n);

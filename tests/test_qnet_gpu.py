@@ -100,7 +100,7 @@ def test_loss_and_gradients_match_oracle(mods, variant, dueling, loss_sum, per):
     loss, g_ref, ae_ref, y_ref, _ = qo.loss_and_grads(qnet.VARIANTS[variant], p, t, x[:, 0:4], x[:, 1:5], a, r, term, isw, 0.99,
                                                       loss_sum, None, 512, dueling)
     assert abs(net.loss.item() - loss) <= 1e-4 * abs(loss)
-    np.testing.assert_allclose(y.cpu().numpy(), y_ref, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(y.cpu().numpy(), y_ref, rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(abs_err.cpu().numpy(), ae_ref, rtol=1e-4, atol=1e-5)
     g = net.grads.cpu().numpy().astype(np.float64)
     L = qo.layout(512, dueling)

@@ -1,0 +1,150 @@
+"""GPU parity of the replay memory (csrc/fb_replay.cu): sample indices bit-exact against CPython's
+random.sample / the reference SumTree semantics for a fixed word stream; gathered minibatches byte-exact."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import replay_oracle as ro  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def mods():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from dqnflappybird_b200 import game, replay
+    return game, replay
+
+
+@pytest.mark.parametrize("N,L,C,t,batch", [
+    (1, 50004, 50000, 100, 32),       # pool branch (n <= 277)
+    (1, 50004, 50000, 277, 32),       # pool branch boundary
+    (1, 50004, 50000, 278, 32),       # set branch just above the boundary
+    (1, 50004, 50000, 1001, 32),      # the reference's first training step (OBSERVE = 1000)
+    (1, 50004, 50000, 70000, 32),     # full deque: n = 50,000
+    (16, 68, 64, 1000, 256),          # n = 1024 <= 1045: pool branch at minibatch 256
+    (16, 68, 64, 1000, 32),
+    (64, 68, 64, 5000, 256),          # n = 4096, set branch, many duplicates / out-of-range words
+    (3, 40, 36, 17, 5),               # tiny batch: setsize 21
+])
+def test_uniform_sample_indices_match_cpython(mods, N, L, C, t, batch):
+    game, replay = mods
+    ring = torch.zeros((N, L, 80, 80), dtype=torch.uint8, device="cuda")
+    mem = replay.ReplayMemory(ring, C, seed=99, max_batch=256)
+    mem.t = t
+    orc = ro.UniformSampler(99)
+    n = len(mem)
+    assert n == N * min(t, C)
+    for rep in range(12):
+        mb = mem.sample(batch)
+        want = orc.sample(n, batch)
+        np.testing.assert_array_equal(mb.idx.cpu().numpy(), np.array(want, np.int32), err_msg=f"rep {rep}")
+        assert mem.rng_positions()[0] == orc.pos
+        e, k = ro.population_to_transition(np.array(want), t, N, C)
+        np.testing.assert_array_equal(mb.env.cpu().numpy(), e)
+        np.testing.assert_array_equal(mb.k.cpu().numpy(), k)
+
+
+def test_sample_larger_than_population_raises(mods):
+    game, replay = mods
+    ring = torch.zeros((1, 40, 80, 80), dtype=torch.uint8, device="cuda")
+    mem = replay.ReplayMemory(ring, 36, seed=1, max_batch=64)
+    mem.t = 10
+    with pytest.raises(ValueError, match="Sample larger than population"):
+        mem.sample(32)
+
+
+def _rollout_with_memory(game, replay, N, L, C, T, prioritized=False, mode=None):
+    gs = game.GameState(num_envs=N, seed=5, history=L)
+    mem = (replay.PrioritizedMemory(gs.ring, C, seed=7, max_batch=64, mode=mode) if prioritized
+           else replay.ReplayMemory(gs.ring, C, seed=7, max_batch=64))
+    hist_f, hist_a, hist_r, hist_t = [], [None], [None], [None]
+    gs.frame_step(torch.zeros(N, dtype=torch.uint8, device="cuda"))          # f_0: the driver's initial no-op (FlappyBirdDQN.py:65-66)
+    hist_f.append(gs.ring[:, gs.slot].cpu().numpy().copy())
+    for k in range(1, T + 1):
+        a_row, r_row, t_row = mem.rows(k)
+        gs.step_random(1, 0.3, 21, a_row, r_row, t_row, None)
+        assert gs.slot == k % L
+        mem.appended(k)
+        hist_f.append(gs.ring[:, gs.slot].cpu().numpy().copy())
+        hist_a.append(a_row.cpu().numpy().copy()); hist_r.append(r_row.cpu().numpy().copy()); hist_t.append(t_row.cpu().numpy().copy())
+    return gs, mem, hist_f, hist_a, hist_r, hist_t
+
+
+def _check_minibatch(mb, hist_f, hist_a, hist_r, hist_t):
+    env, ks = mb.env.cpu().numpy(), mb.k.cpu().numpy()
+    frames = mb.frames.cpu().numpy()
+    for b, (e, k) in enumerate(zip(env, ks)):
+        for f in range(5):
+            np.testing.assert_array_equal(frames[b, f], hist_f[max(k - 4 + f, 0)][e], err_msg=f"sample {b} env {e} k {k} frame {f}")
+        assert mb.actions[b].item() == hist_a[k][e] and mb.rewards[b].item() == hist_r[k][e] and mb.terminals[b].item() == hist_t[k][e]
+
+
+@pytest.mark.parametrize("T", [3, 30, 90])
+def test_gather_returns_the_right_transitions(mods, T):
+    """s = frames k-4..k-1, s' = k-3..k; early transitions replicate frame 0 (BrainDQN.py:239); ring wrap-around"""
+    game, replay = mods
+    N, L, C = 8, 40, 36
+    gs, mem, hf, ha, hr, ht = _rollout_with_memory(game, replay, N, L, C, T)
+    assert len(mem) == N * min(T, C)
+    for _ in range(4):
+        mb = mem.sample(min(16, len(mem)))
+        ks = mb.k.cpu().numpy()
+        assert ks.min() >= max(1, T - C + 1) and ks.max() <= T
+        _check_minibatch(mb, hf, ha, hr, ht)
+
+
+@pytest.mark.parametrize("N,C,mode", [(1, 50, "reference"), (1, 1000, "reference"), (4, 64, "rebuild"), (4, 64, "reference")])
+def test_sumtree_matches_reference_semantics(mods, N, C, mode):
+    """store / sample / batch_update sequence: tree array bit-identical to the oracle (itself pinned to the
+    reference classes), sampled tree indices identical, IS weights to 1e-12."""
+    game, replay = mods
+    L = C + 4
+    ring = torch.zeros((N, L, 80, 80), dtype=torch.uint8, device="cuda")
+    mem = replay.PrioritizedMemory(ring, C, seed=31, max_batch=64, mode=mode)
+    orc = ro.Memory(N, C, seed=31, mode=mode)
+    rng = np.random.default_rng(3)
+    B = 32 if N * C >= 64 else 8
+    for k in range(1, 3 * C + 7):
+        mem.appended(k); orc.store_step(k)
+        if k >= 12 and k % 2 == 0:
+            mb = mem.sample(B)
+            idx, data, w = orc.sample(B)
+            np.testing.assert_array_equal(mb.tree_idx.cpu().numpy(), idx, err_msg=f"k={k}")
+            np.testing.assert_array_equal(mb.idx.cpu().numpy(), data)
+            np.testing.assert_allclose(mb.is_weights.cpu().numpy(), w, rtol=1e-12)
+            assert mem.beta == orc.beta
+            e, kk = ro.data_index_to_transition(data, k, C)
+            np.testing.assert_array_equal(mb.env.cpu().numpy(), e); np.testing.assert_array_equal(mb.k.cpu().numpy(), kk)
+            ps = ro.Memory.priorities(rng.random(B) * rng.choice([0.02, 0.7, 3.0])).astype(np.float64)
+            mem.batch_update(mb.tree_idx, priorities=torch.from_numpy(ps).cuda())
+            orc.batch_update(idx, ps)
+        if k % 25 == 0:
+            np.testing.assert_array_equal(mem.tree().cpu().numpy(), orc.sum_tree.tree, err_msg=f"tree k={k}")
+    np.testing.assert_array_equal(mem.tree().cpu().numpy(), orc.sum_tree.tree)
+    assert mem.rng_positions()[1] == orc.pos
+
+
+def test_priority_transform_on_device(mods):
+    """Memory.batch_update's (|err|+0.01 clipped to 1)^0.6 in float32: within 4 float32 ulp of numpy"""
+    game, replay = mods
+    ring = torch.zeros((1, 68, 80, 80), dtype=torch.uint8, device="cuda")
+    mem = replay.PrioritizedMemory(ring, 64, seed=1, max_batch=64)
+    for k in range(1, 65):
+        mem.appended(k)
+    err = np.abs(np.random.default_rng(0).standard_normal(64)).astype(np.float32)
+    idx = torch.arange(63, 127, dtype=torch.int32, device="cuda")
+    mem.batch_update(idx, abs_errors=torch.from_numpy(err).cuda())
+    leaves = mem.tree().cpu().numpy()[63:]
+    want = ro.Memory.priorities(err).astype(np.float64)
+    np.testing.assert_allclose(leaves, want, rtol=4 * 1.2e-7)
+    assert abs(mem.total_p - leaves.sum()) < 1e-9
+
+
+def test_prioritized_rollout_gather(mods):
+    game, replay = mods
+    gs, mem, hf, ha, hr, ht = _rollout_with_memory(game, replay, 4, 24, 20, 50, prioritized=True)
+    mb = mem.sample(16)
+    assert mb.tree_idx.min().item() >= 4 * 20 - 1
+    _check_minibatch(mb, hf, ha, hr, ht)
