@@ -203,7 +203,13 @@ __global__ void __launch_bounds__(1024) tree_update_kernel(double *tree, int cap
         }
         return;
     }
-    for (int i = tid; i < count; i += blockDim.x) tree[leaves[i]] = prio ? prio[i] : s_store;
+    for (int i = tid; i < count; i += blockDim.x) {
+        if (!prio) { tree[leaves[i]] = s_store; continue; }      // stores: distinct leaves, one value
+        bool last = true;                                         // duplicates in a minibatch: the last one wins, as in
+        for (int j = i + 1; j < count; j++)                       // the reference's sequential loop (:150-151)
+            if (leaves[j] == leaves[i]) { last = false; break; }
+        if (last) tree[leaves[i]] = prio[i];
+    }
     __syncthreads();
     for (int d = max_depth - 1; d >= 0; d--) {
         for (int i = tid; i < count; i += blockDim.x) {

@@ -1,0 +1,122 @@
+"""End-to-end: the reference's driver loop (FlappyBirdDQN.py:60-76) on the batched GameState + Brain*."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import qnet_oracle as qo  # noqa: E402
+from oracle import replay_oracle as ro  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def mods():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from dqnflappybird_b200 import brains, game
+    return game, brains
+
+
+def test_reference_driver_loop_single_env(mods):
+    """the five-line loop of FlappyBirdDQN.py:60-76, call shapes unchanged (numpy in / numpy out for one env)"""
+    game, brains = mods
+    brain = brains.BrainDQNNature(2, "bird", replay_memory_per_env=200, observe=20., replace_target_iter=7)
+    flappyBird = game.GameState(num_envs=1, seed=3, history=204, ring=brain.ring)
+    action0 = np.array([1, 0])
+    observation0, reward0, terminal, curScore = flappyBird.frame_step(action0)
+    brain.setInitState(observation0[:, :, 0])
+    p0 = brain.net.params.clone(); t0 = brain.net.target.clone()
+    assert not torch.equal(p0, t0)                       # target net is initialised independently
+    eps = 0.03
+    for step in range(60):
+        action = brain.getAction()
+        assert action.shape == (2,) and action.sum() == 1
+        if brain.onlineTimeStep > 20 and eps > 0:        # the decrement happens inside getAction (BrainDQN.py:112-114)
+            eps -= 0.03 / 1000000.
+        assert brain.epsilon == eps
+        nextObserv, reward, terminal, curScore = flappyBird.frame_step(action)
+        assert nextObserv.shape == (80, 80, 1)
+        brain.setPerception(nextObserv, action, reward, terminal, curScore)
+        if step < 21:
+            assert torch.equal(brain.net.params, p0)     # observing: no training until onlineTimeStep > OBSERVE
+    assert brain.timeStep == 60 and brain.onlineTimeStep == 60 and len(brain.replayMemory) == 60
+    assert not torch.equal(brain.net.params, p0) and brain.net.adam_steps == 60 - 21
+    assert torch.isfinite(brain.net.params).all()
+    assert not torch.equal(brain.net.target, t0)         # synced at timeStep % 7 == 0
+    cs = brain.currentState
+    assert cs.shape == (1, 80, 80, 4) and torch.equal(cs[0, :, :, 3], flappyBird.ring[0, flappyBird.slot])
+
+
+def test_training_step_matches_oracle_on_the_sampled_minibatch(mods):
+    """one BrainDQNNature update, batched envs: the minibatch is what CPython's random.sample picks from the same
+    word stream, and the gradient equals the float64 oracle's on exactly those transitions"""
+    game, brains = mods
+    N, C = 16, 28
+    brain = brains.BrainDQNNature(2, "bird", num_envs=N, replay_memory_per_env=C, observe=1e9, batch_size=32, seed=5)
+    gs = game.GameState(num_envs=N, seed=9, history=C + 4, ring=brain.ring)
+    hist = []
+    obs, *_ = gs.frame_step(torch.zeros(N, dtype=torch.uint8, device="cuda"))
+    brain.setInitState(obs)
+    hist.append((obs.cpu().numpy().copy(), None, None, None))
+    rng = np.random.default_rng(0)
+    for k in range(1, 41):
+        a = torch.from_numpy((rng.random(N) < 0.2).astype(np.uint8)).cuda()
+        obs, r, t, s = gs.frame_step(a)
+        brain.setPerception(obs, a, r, t, s)
+        hist.append((obs.cpu().numpy().copy(), a.cpu().numpy(), r.cpu().numpy().copy(), t.cpu().numpy().copy()))
+    mem = brain.replayMemory
+    assert mem.t == 40 and len(mem) == N * C
+    pos = mem.rng_positions()[0]
+    orc = ro.UniformSampler(mem.seed); orc.pos = pos
+    want = orc.sample(N * C, 32)
+    p = brain.net.params.cpu().numpy().copy(); tg = brain.net.target.cpu().numpy().copy()
+    brain.timeStep = 3                                   # not a multiple of 500: no target sync in this step
+    brain._trainQNetwork()
+    env, ks = ro.population_to_transition(np.array(want), 40, N, C)
+    x = np.stack([[hist[max(k - 4 + f, 0)][0][e] for f in range(5)] for e, k in zip(env, ks)])
+    a = np.array([hist[k][1][e] for e, k in zip(env, ks)]); r = np.array([hist[k][2][e] for e, k in zip(env, ks)])
+    t = np.array([hist[k][3][e] for e, k in zip(env, ks)]).astype(np.uint8)
+    loss, g_ref, *_ = qo.loss_and_grads(1, p, tg, x[:, 0:4], x[:, 1:5], a, r, t)
+    g = brain.net.grads.cpu().numpy().astype(np.float64)
+    assert abs(brain.net.loss.item() - loss) <= 1e-4 * abs(loss)
+    assert np.linalg.norm(g - g_ref) <= 3e-4 * np.linalg.norm(g_ref)
+    ref = qo.AdamTF1(len(p)); want_p = ref.step(p.copy(), g_ref.astype(np.float32))
+    np.testing.assert_allclose(brain.net.params.cpu().numpy(), want_p, rtol=0, atol=3e-7)
+
+
+@pytest.mark.parametrize("name", ["dqn", "dqnnature", "ddqn", "duelingdqn", "prioritydqn"])
+def test_every_brain_trains_batched(mods, name):
+    """FlappyBirdDQN.py:41-50 model table: each agent runs the batched loop past OBSERVE and updates its weights"""
+    game, brains = mods
+    N = 64
+    brain = brains.MODELS[name](2, "bird", num_envs=N, replay_memory_per_env=12, observe=6., batch_size=32, seed=1,
+                                replace_target_iter=4)
+    assert brain.net.dueling == (name == "duelingdqn")
+    gs = game.GameState(num_envs=N, seed=2, history=16, ring=brain.ring)
+    obs, *_ = gs.frame_step(torch.zeros(N, dtype=torch.uint8, device="cuda"))
+    brain.setInitState(obs)
+    p0 = brain.net.params.clone()
+    for _ in range(25):
+        a = brain.getAction()
+        obs, r, t, s = gs.frame_step(a)
+        brain.setPerception(obs, a, r, t, s)
+    gs.check_errors()
+    assert brain.net.adam_steps == 25 - 7
+    assert torch.isfinite(brain.net.params).all() and not torch.equal(brain.net.params, p0)
+    assert torch.isfinite(brain.net.loss).all()
+    if name == "prioritydqn":
+        tree = brain.replayMemory.tree()
+        assert tree[0].item() > 0 and abs(tree[0].item() - tree[N * 12 - 1:].sum().item()) < 1e-9
+    sd = brain.state_dict()
+    brain.load_state_dict(sd)
+    assert brain.timeStep == 25
+
+
+def test_quirk_switches(mods):
+    game, brains = mods
+    b = brains.BrainDoubleDQN(2, "bird", num_envs=4, replay_memory_per_env=8, reference_quirks=True)
+    assert b._trainQNetwork.__func__ is not brains.BrainDoubleDQN.trainQNetwork
+    d = brains.BrainDuelingDQN(2, "bird", num_envs=4, replay_memory_per_env=8, reference_quirks=True)
+    assert d.net.dueling is False and d.net.n_params == 898722       # Q2: the shipped code builds the plain net
+    d2 = brains.BrainDuelingDQN(2, "bird", num_envs=4, replay_memory_per_env=8)
+    assert d2.net.dueling is True and d2.net.n_params == 899235
