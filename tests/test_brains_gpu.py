@@ -20,7 +20,7 @@ def mods():
 def test_reference_driver_loop_single_env(mods):
     """the five-line loop of FlappyBirdDQN.py:60-76, call shapes unchanged (numpy in / numpy out for one env)"""
     game, brains = mods
-    brain = brains.BrainDQNNature(2, "bird", replay_memory_per_env=200, observe=20., replace_target_iter=7)
+    brain = brains.BrainDQNNature(2, "bird", replay_memory_per_env=200, observe=40., replace_target_iter=7)
     flappyBird = game.GameState(num_envs=1, seed=3, history=204, ring=brain.ring)
     action0 = np.array([1, 0])
     observation0, reward0, terminal, curScore = flappyBird.frame_step(action0)
@@ -28,19 +28,19 @@ def test_reference_driver_loop_single_env(mods):
     p0 = brain.net.params.clone(); t0 = brain.net.target.clone()
     assert not torch.equal(p0, t0)                       # target net is initialised independently
     eps = 0.03
-    for step in range(60):
+    for step in range(80):
         action = brain.getAction()
         assert action.shape == (2,) and action.sum() == 1
-        if brain.onlineTimeStep > 20 and eps > 0:        # the decrement happens inside getAction (BrainDQN.py:112-114)
+        if brain.onlineTimeStep > 40 and eps > 0:        # the decrement happens inside getAction (BrainDQN.py:112-114)
             eps -= 0.03 / 1000000.
         assert brain.epsilon == eps
         nextObserv, reward, terminal, curScore = flappyBird.frame_step(action)
         assert nextObserv.shape == (80, 80, 1)
         brain.setPerception(nextObserv, action, reward, terminal, curScore)
-        if step < 21:
+        if step < 41:
             assert torch.equal(brain.net.params, p0)     # observing: no training until onlineTimeStep > OBSERVE
-    assert brain.timeStep == 60 and brain.onlineTimeStep == 60 and len(brain.replayMemory) == 60
-    assert not torch.equal(brain.net.params, p0) and brain.net.adam_steps == 60 - 21
+    assert brain.timeStep == 80 and brain.onlineTimeStep == 80 and len(brain.replayMemory) == 80
+    assert not torch.equal(brain.net.params, p0) and brain.net.adam_steps == 80 - 41
     assert torch.isfinite(brain.net.params).all()
     assert not torch.equal(brain.net.target, t0)         # synced at timeStep % 7 == 0
     cs = brain.currentState
