@@ -217,6 +217,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
 
+    learner = None
+    if not args.no_learner:
+        learner = bench_learner(args, rank, world, dev)
     if rank != 0:
         return
     total_envs = E * world
@@ -253,8 +256,77 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                         "stays in the device ring by design"},
         "gpu_launches": args.steps,
         "clocks": clocks,
+        "learner": learner,
     }
     print(json.dumps(line), flush=True)
+
+
+FLOP_FWD, FLOP_BWD = 11675648, 16797696            # SURVEY 2.2 / 8(d), per sample
+
+
+def bench_learner(args, rank, world, dev):
+    """Second half of BASELINE.json's metric: DQN updates/s (configs[2]: BrainDQNNature, 16384 envs, minibatch 256).
+    One update = sample + gather + 2 forwards + backward (+ gradient all-reduce at N > 1) + Adam.  Also times acting
+    (one forward + epsilon-greedy for every env).  Replay is pre-filled from a random-action rollout."""
+    import torch
+    import torch.distributed as dist
+    from dqnflappybird_b200.brains import BrainDQNNature
+    from dqnflappybird_b200.game import GameState
+    N, B, C = args.learner_envs, args.learner_batch, 28
+    brain = BrainDQNNature(2, "bird", num_envs=N, device=dev, replay_memory_per_env=C, batch_size=B, observe=1e18, seed=0,
+                           first_env_id=rank * N, max_act_batch=2048)
+    gs = GameState(num_envs=N, device=dev, seed=42, history=C + 4, first_env_id=rank * N, ring=brain.ring)
+    obs, *_ = gs.frame_step(torch.zeros(N, dtype=torch.uint8, device=dev))
+    brain.setInitState(obs)
+    for k in range(1, C + 9):                       # pre-fill the replay ring with random-action transitions
+        a_row, r_row, t_row = brain.replayMemory.rows(k)
+        gs.step_random(1, 0.5, 1234, a_row, r_row, t_row, None)
+        brain._k = k
+        brain.replayMemory.appended(k)
+    brain.timeStep = 1                              # no target sync inside the timed loop except every 500th update
+    K, W = args.learner_updates, 5
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        brain._trainQNetwork(); brain.timeStep += 1
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        brain._trainQNetwork(); brain.timeStep += 1
+    e1.record()
+    sync()
+    ms_upd = e0.elapsed_time(e1) / K
+    for _ in range(2):
+        brain.getAction()
+    sync()
+    e0.record()
+    for _ in range(5):
+        brain.getAction()
+    e1.record()
+    sync()
+    ms_act = e0.elapsed_time(e1) / 5
+    t = torch.tensor([ms_upd, ms_act], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_upd, ms_act = float(t[0]), float(t[1])
+    flop_upd = (2 * FLOP_FWD + FLOP_BWD) * B
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            tc_peak = float(json.load(f)["bf16_tflops"])
+    except Exception:
+        tc_peak = 1590.0
+    return {"metric": "DQN updates/sec", "model": "BrainDQNNature (target net), fc512, one max-pool (as coded)", "envs_per_gpu": N,
+            "minibatch_global": B, "minibatch_per_gpu": brain.local_batch, "updates_per_s": 1e3 / ms_upd, "ms_per_update": ms_upd,
+            "flop_per_update": flop_upd, "tflops": flop_upd / (ms_upd * 1e-3) / 1e12 / max(world, 1) * 1.0,
+            "frac_of_bf16_tensor_peak": flop_upd / world / (ms_upd * 1e-3) / 1e12 / tc_peak, "tensor_peak_tflops": tc_peak,
+            "compute_path": brain.net.compute_path if hasattr(brain.net, "compute_path") else "fp32 CUDA-core implicit GEMM",
+            "act_envs_per_s": N * world / (ms_act * 1e-3), "ms_per_act": ms_act,
+            "act_tflops_per_gpu": N * FLOP_FWD / (ms_act * 1e-3) / 1e12}
 
 
 def main():
@@ -266,6 +338,10 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=131072)
     ap.add_argument("--decorrelate", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-learner", action="store_true")
+    ap.add_argument("--learner-envs", type=int, default=16384)
+    ap.add_argument("--learner-batch", type=int, default=256)
+    ap.add_argument("--learner-updates", type=int, default=50)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
