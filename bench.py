@@ -274,7 +274,7 @@ def bench_learner(args, rank, world, dev):
     from dqnflappybird_b200.game import GameState
     N, B, C = args.learner_envs, args.learner_batch, 28
     brain = BrainDQNNature(2, "bird", num_envs=N, device=dev, replay_memory_per_env=C, batch_size=B, observe=1e18, seed=0,
-                           first_env_id=rank * N, max_act_batch=2048)
+                           first_env_id=rank * N, max_act_batch=2048, precision=args.learner_precision)
     gs = GameState(num_envs=N, device=dev, seed=42, history=C + 4, first_env_id=rank * N, ring=brain.ring)
     obs, *_ = gs.frame_step(torch.zeros(N, dtype=torch.uint8, device=dev))
     brain.setInitState(obs)
@@ -342,6 +342,7 @@ def main():
     ap.add_argument("--learner-envs", type=int, default=16384)
     ap.add_argument("--learner-batch", type=int, default=256)
     ap.add_argument("--learner-updates", type=int, default=50)
+    ap.add_argument("--learner-precision", default="bf16", choices=["bf16", "fp32"])
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

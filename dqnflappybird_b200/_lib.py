@@ -77,6 +77,9 @@ _SIGNATURES = {
     "fb_render_full": ([_vp, C.c_int, C.c_int, _u8p, _vp], C.c_int),
     "fb_qnet_create": ([C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)], C.c_int),
     "fb_qnet_destroy": ([_vp], C.c_int),
+    "fb_qnet_set_precision": ([_vp, C.c_int], C.c_int),
+    "fb_qnet_get_precision": ([_vp], C.c_int),
+    "fb_qnet_invalidate": ([_vp], C.c_int),
     "fb_qnet_param_count": ([_vp], C.c_int),
     "fb_qnet_layout": ([_vp, _i32p], C.c_int),
     "fb_qnet_forward": ([_vp, _f32p, _u8p, C.c_longlong, _i32p, C.c_int, _f32p, _vp], C.c_int),
@@ -99,6 +102,7 @@ _SIGNATURES = {
     "fb_debug_host_step": ([_i32p, C.c_int, _u8p, C.c_int, C.c_uint64, C.c_uint64, _f32p, _u8p, _i32p], C.c_int),
     "fb_debug_host_obs": ([_i32p, C.c_int, _u8p], C.c_int),
     "fb_debug_host_mixed": ([_i32p], C.c_int),
+    "fb_debug_tc_gemm": ([C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _f32p, _vp, _vp], C.c_int),
 }
 
 

@@ -52,7 +52,8 @@ class BrainDQN:
                  final_epsilon: float = FINAL_EPSILON, initial_epsilon: float = INITIAL_EPSILON,
                  replay_memory_per_env: int | None = None, replace_target_iter: int | None = REPLACE_TARGET_ITER,
                  hidden: int = 512, lr: float = 1e-6, seed: int = 0, first_env_id: int = 0, updates_per_step: int = 1,
-                 reference_quirks: bool = False, copy_target_at_init: bool = False, record: bool = False, max_act_batch: int = 1024):
+                 reference_quirks: bool = False, copy_target_at_init: bool = False, record: bool = False, max_act_batch: int = 1024,
+                 precision: str = "bf16"):
         if actionNum != 2:
             raise ValueError("the Flappy Bird hot path has two actions (FlappyBirdDQN.py:38)")
         self.actionNum, self.gameName = actionNum, gameName
@@ -85,7 +86,7 @@ class BrainDQN:
         # init Q network (BrainDQN.py:60)
         dueling = self.dueling and not (reference_quirks and type(self).__name__ == "BrainDuelingDQN")
         self.net = QNetwork(self.device, hidden=hidden, dueling=dueling, max_batch=max(self.local_batch, min(N, max_act_batch)),
-                            seed=seed, lr=lr, copy_target_at_init=copy_target_at_init)
+                            seed=seed, lr=lr, copy_target_at_init=copy_target_at_init, precision=precision)
         self._k = 0                               # time index of the newest frame in the ring
         self._rng_pos = torch.zeros(N, dtype=torch.int32, device=self.device)
         self._actions = torch.zeros(N, dtype=torch.uint8, device=self.device)

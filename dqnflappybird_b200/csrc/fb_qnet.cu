@@ -279,14 +279,26 @@ __global__ void head_backward_w_kernel(const float *h1, const float *dq, QnetLay
     }
 }
 
-__global__ void head_backward_h_kernel(const float *h1, const float *dq, const float *params, QnetLayout L, int B, float *dh1) {
+__global__ void head_backward_h_kernel(const float *h1, const float *dq, const float *params, QnetLayout L, int B, float *dh1,
+                                       __nv_bfloat16 *dh1_bf16) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)B * L.hidden) return;
     int b = (int)(i / L.hidden), j = (int)(i - (size_t)b * L.hidden);
     float d0 = dq[b * 2], d1 = dq[b * 2 + 1], g;
     if (!L.dueling) g = d0 * params[L.wf2 + j * 2] + d1 * params[L.wf2 + j * 2 + 1];
     else { float m = (d0 + d1) * 0.5f; g = (d0 - m) * params[L.wa + j * 2] + (d1 - m) * params[L.wa + j * 2 + 1] + (d0 + d1) * params[L.wv + j]; }
-    dh1[i] = h1[i] > 0.f ? g : 0.f;
+    g = h1[i] > 0.f ? g : 0.f;
+    if (dh1) dh1[i] = g;
+    if (dh1_bf16) dh1_bf16[i] = __float2bfloat16(g);
+}
+
+void qnet_launch_head_forward(const float *h1, const float *params, const QnetLayout &L, int B, float *q, cudaStream_t st) {
+    head_forward_kernel<<<(B + 3) / 4, 128, 0, st>>>(h1, params, L, B, q);
+}
+void qnet_launch_head_backward(const float *h1, const float *dq, const float *params, const QnetLayout &L, int B, float *grads,
+                               float *dh1_f32, __nv_bfloat16 *dh1_bf16, cudaStream_t st) {
+    head_backward_w_kernel<<<(L.hidden + 1 + 127) / 128, 128, 0, st>>>(h1, dq, L, B, grads);
+    head_backward_h_kernel<<<(B * L.hidden + 255) / 256, 256, 0, st>>>(h1, dq, params, L, B, dh1_f32, dh1_bf16);
 }
 
 __global__ void splitk_reduce_kernel(const float *part, int splits, size_t n, float *out) {
@@ -331,17 +343,7 @@ __global__ void egreedy_kernel(const float *q, int n, double epsilon, uint64_t s
     actions[e] = (uint8_t)act;
 }
 
-// ---------------------------------------------------------------------------------- handle
-struct fb_qnet {
-    QnetLayout L;
-    int max_batch;
-    // activations of the online net on s (kept for backward) and scratch for the other forwards
-    float *z1, *p1, *a2, *a3, *h1, *q;          // [max_batch] x {12800, 3200, 1600, 1600, H, 2}
-    float *q_next, *q_next_online;
-    float *dq, *dh1, *dz3, *dz2, *dp1, *dz1;
-    float *partial; size_t partial_floats;
-    float *loss_dev;
-};
+// ---------------------------------------------------------------------------------- handle (struct fb_qnet: fb_qnet.cuh)
 
 // weight (+ bias, as the extra all-ones row M) gradient: (M+1) x N = A^T dz over K, deterministic split-K
 template <bool A_M_FAST, class AL>
@@ -375,6 +377,8 @@ extern "C" int fb_qnet_create(int hidden, int dueling, int max_batch, fb_qnet **
     FB_REQUIRE(n != nullptr, "fb_qnet_create: out of host memory");
     n->L = qnet_layout(hidden, dueling ? 1 : 0);
     n->max_batch = max_batch;
+    n->precision = FB_PRECISION_FP32;
+    n->tc = nullptr;
     size_t B = (size_t)max_batch;
     auto alloc = [](float **p, size_t floats) { return cudaMalloc(p, floats * sizeof(float)); };
     FB_CUDA_OK(alloc(&n->z1, B * 12800)); FB_CUDA_OK(alloc(&n->p1, B * 3200)); FB_CUDA_OK(alloc(&n->a2, B * 1600));
@@ -396,9 +400,40 @@ extern "C" int fb_qnet_create(int hidden, int dueling, int max_batch, fb_qnet **
 
 extern "C" int fb_qnet_destroy(fb_qnet *n) {
     if (!n) return FB_OK;
+    tc_state_destroy(n);
     float *ps[] = {n->z1, n->p1, n->a2, n->a3, n->h1, n->q, n->q_next, n->q_next_online, n->dq, n->dh1, n->dz3, n->dz2, n->dp1, n->dz1, n->partial, n->loss_dev};
     for (float *p : ps) cudaFree(p);
     delete n;
+    return FB_OK;
+}
+
+extern "C" int fb_qnet_set_precision(fb_qnet *n, int precision) {
+    FB_REQUIRE(n != nullptr && (precision == FB_PRECISION_FP32 || precision == FB_PRECISION_BF16), "fb_qnet_set_precision: bad argument");
+    if (precision == FB_PRECISION_BF16) { int rc = tc_state_create(n); if (rc) return rc; }
+    n->precision = precision;
+    n->packed_src[0] = n->packed_src[1] = nullptr;
+    return FB_OK;
+}
+
+extern "C" int fb_qnet_get_precision(const fb_qnet *n) { return n ? n->precision : -1; }
+
+// The bf16 operand copies of a parameter vector are remade when the vector may have changed: after fb_qnet_adam /
+// fb_qnet_sync_target on it, or when the caller says so (it wrote the tensor itself).
+extern "C" int fb_qnet_invalidate(fb_qnet *n) {
+    FB_REQUIRE(n != nullptr, "fb_qnet_invalidate: NULL argument");
+    n->packed_src[0] = n->packed_src[1] = nullptr;
+    return FB_OK;
+}
+
+static int tc_slot_for(fb_qnet *n, const float *params_dev, int want_slot, cudaStream_t st, int *slot_out) {
+    int slot = want_slot;
+    if (slot < 0) slot = (n->packed_src[1] == params_dev && n->packed_src[0] != params_dev) ? 1 : 0;
+    if (n->packed_src[slot] != params_dev) {
+        int rc = tc_pack_weights(n, params_dev, slot, st);
+        if (rc) return rc;
+        n->packed_src[slot] = params_dev;
+    }
+    *slot_out = slot;
     return FB_OK;
 }
 
@@ -422,10 +457,13 @@ extern "C" int fb_qnet_forward(fb_qnet *n, const float *params_dev, const uint8_
                                const int32_t *chan_off, int batch, float *q_out_dev, void *stream) {
     FB_REQUIRE(n && params_dev && frames_dev && chan_off && q_out_dev && batch > 0, "fb_qnet_forward: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
+    int slot = 0;
+    if (n->precision == FB_PRECISION_BF16) { int rc = tc_slot_for(n, params_dev, -1, st, &slot); if (rc) return rc; }
     for (int b0 = 0; b0 < batch; b0 += n->max_batch) {
         int B = min(n->max_batch, batch - b0);
         FrameView fv = make_view(frames_dev + (size_t)b0 * sample_stride, sample_stride, chan_off);
-        int rc = forward_chunk(n, params_dev, fv, B, q_out_dev + (size_t)b0 * 2, st);
+        int rc = n->precision == FB_PRECISION_BF16 ? tc_forward(n, slot, params_dev, fv, B, q_out_dev + (size_t)b0 * 2, st)
+                                                   : forward_chunk(n, params_dev, fv, B, q_out_dev + (size_t)b0 * 2, st);
         if (rc) return rc;
     }
     return FB_OK;
@@ -459,6 +497,20 @@ extern "C" int fb_qnet_loss_backward(fb_qnet *n, int variant, const float *param
     if (global_batch <= 0) global_batch = batch;
     FrameView fs = make_view(frames_dev, sample_stride, chan_off_s), fn = make_view(frames_dev, sample_stride, chan_off_next);
     int rc;
+    if (n->precision == FB_PRECISION_BF16) {
+        // same order of work on the tcgen05 path; the bf16 operand copies are remade only when stale
+        int s_on = 0, s_tg = 0;
+        const float *next_params = variant == 0 ? params_dev : target_params_dev;
+        rc = tc_slot_for(n, params_dev, 0, st, &s_on); if (rc) return rc;
+        if (variant != 0) { rc = tc_slot_for(n, target_params_dev, 1, st, &s_tg); if (rc) return rc; }
+        if (variant == 2) { rc = tc_forward(n, s_on, params_dev, fn, B, n->q_next_online, st); if (rc) return rc; }
+        rc = tc_forward(n, variant == 0 ? s_on : s_tg, next_params, fn, B, n->q_next, st); if (rc) return rc;
+        rc = tc_forward(n, s_on, params_dev, fs, B, n->q, st); if (rc) return rc;
+        td_loss_kernel<<<1, 256, 0, st>>>(n->q, n->q_next, n->q_next_online, actions_dev, rewards_dev, terminals_dev, is_weights_dev,
+                                           B, global_batch, variant, gamma, loss_sum, n->dq, loss_out_dev ? loss_out_dev : n->loss_dev,
+                                           abs_err_out_dev, q_target_out_dev);
+        return tc_backward(n, params_dev, B, grads_dev, st);
+    }
     // Q(s') with the net the variant names (and the online net too for Double), then Q(s) last so that its
     // activations are the ones left in the workspace for the backward pass.
     if (variant == 2) { rc = forward_chunk(n, params_dev, fn, B, n->q_next_online, st); if (rc) return rc; }
@@ -469,7 +521,7 @@ extern "C" int fb_qnet_loss_backward(fb_qnet *n, int variant, const float *param
                                        abs_err_out_dev, q_target_out_dev);
     // ---- backward
     head_backward_w_kernel<<<(L.hidden + 1 + 127) / 128, 128, 0, st>>>(n->h1, n->dq, L, B, grads_dev);
-    head_backward_h_kernel<<<(B * L.hidden + 255) / 256, 256, 0, st>>>(n->h1, n->dq, params_dev, L, B, n->dh1);
+    head_backward_h_kernel<<<(B * L.hidden + 255) / 256, 256, 0, st>>>(n->h1, n->dq, params_dev, L, B, n->dh1, nullptr);
     // fc1: dW = a3^T dh1 (+ bias row), da3 = dh1 Wf1^T masked by relu(a3)
     wgrad<true>(n, kFlat, L.hidden, B, 64, LoadFc1T{n->a3}, n->dh1, grads_dev + L.wf1, st);
     launch_gemm<64, false, true>(B, kFlat, L.hidden, 1, LoadPlain{n->dh1, L.hidden}, LoadTrans{params_dev + L.wf1, L.hidden},
@@ -493,6 +545,7 @@ extern "C" int fb_qnet_adam(fb_qnet *n, float *params_dev, const float *grads_de
     size_t cnt = (size_t)n->L.total;
     adam_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params_dev, grads_dev, m_dev, v_dev, cnt, alpha, beta1, beta2, eps, grad_scale);
     FB_CUDA_OK(cudaGetLastError());
+    for (int s = 0; s < 2; s++) if (n->packed_src[s] == params_dev) n->packed_src[s] = nullptr;
     return FB_OK;
 }
 
@@ -500,5 +553,6 @@ extern "C" int fb_qnet_adam(fb_qnet *n, float *params_dev, const float *grads_de
 extern "C" int fb_qnet_sync_target(fb_qnet *n, float *target_dev, const float *params_dev, void *stream) {
     FB_REQUIRE(n && target_dev && params_dev, "fb_qnet_sync_target: NULL argument");
     FB_CUDA_OK(cudaMemcpyAsync(target_dev, params_dev, sizeof(float) * (size_t)n->L.total, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    for (int s = 0; s < 2; s++) if (n->packed_src[s] == target_dev) n->packed_src[s] = nullptr;
     return FB_OK;
 }

@@ -9,6 +9,8 @@
 // frames + b * sample_stride + chan_off[c] (a view of the frame ring or of a gathered batch),
 // H = obs axis 0 (game x), W = obs axis 1 (game y), exactly the array the reference feeds.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "fb_common.cuh"
 
 constexpr int kC1 = 32, kC2 = 64, kC3 = 64, kFlat = 1600, kActions = 2;
@@ -41,3 +43,34 @@ struct FrameView {              // where the 4 input channels of each sample liv
     long long sample_stride;    // bytes between consecutive samples
     int chan_off[4];            // byte offset of channel c (oldest frame first, newest last: BrainDQN.py:68)
 };
+
+// ---- handle shared by the strict-fp32 path (fb_qnet.cu) and the tcgen05 path (fb_qnet_tc.cu) ------------
+struct TcState;                 // bf16 workspace, packed weights and TMA plans (fb_qnet_tc.cu)
+struct fb_qnet {
+    QnetLayout L;
+    int max_batch;
+    int precision;              // FB_PRECISION_FP32 (CUDA-core FMA) or FB_PRECISION_BF16 (tcgen05, fp32 accumulate)
+    // fp32 activations of the online net on s (kept for backward) and scratch for the other forwards
+    float *z1, *p1, *a2, *a3, *h1, *q;          // [max_batch] x {12800, 3200, 1600, 1600, H, 2}
+    float *q_next, *q_next_online;
+    float *dq, *dh1, *dz3, *dz2, *dp1, *dz1;
+    float *partial; size_t partial_floats;
+    float *loss_dev;
+    TcState *tc;
+    const float *packed_src[2];   // parameter vectors the bf16 operand copies (slot 0 online, 1 target) were made from
+};
+
+// small CUDA-core stages both paths share (defined in fb_qnet.cu)
+void qnet_launch_head_forward(const float *h1, const float *params, const QnetLayout &L, int B, float *q, cudaStream_t st);
+void qnet_launch_td_loss(const float *q_s, const float *q_next, const float *q_next_online, const uint8_t *actions,
+                         const float *rewards, const uint8_t *terminals, const float *isw, int B, int global_batch, int variant,
+                         double gamma, int loss_sum, float *dq, float *loss_out, float *abs_err, float *q_target, cudaStream_t st);
+void qnet_launch_head_backward(const float *h1, const float *dq, const float *params, const QnetLayout &L, int B, float *grads,
+                               float *dh1_f32, __nv_bfloat16 *dh1_bf16, cudaStream_t st);
+
+// tcgen05 path entry points (fb_qnet_tc.cu); all return FB_OK or an error code with fb_set_error set
+int tc_state_create(fb_qnet *n);
+void tc_state_destroy(fb_qnet *n);
+int tc_pack_weights(fb_qnet *n, const float *params_dev, int slot /* 0 online, 1 target */, cudaStream_t st);
+int tc_forward(fb_qnet *n, int slot, const float *params_dev, FrameView fv, int B, float *q_out, cudaStream_t st);
+int tc_backward(fb_qnet *n, const float *params_dev, int B, float *grads_dev, cudaStream_t st);

@@ -15,6 +15,7 @@ import torch
 from . import _lib
 
 VARIANTS = {"vanilla": 0, "nature": 1, "double": 2}
+PRECISIONS = {"fp32": 0, "bf16": 1}
 
 
 def truncated_normal_(t: torch.Tensor, std: float, generator=None):
@@ -51,7 +52,7 @@ class FrameBatch:
 class QNetwork:
     def __init__(self, device="cuda:0", hidden: int = 512, dueling: bool = False, max_batch: int = 256, seed: int = 0,
                  lr: float = 1e-6, beta1: float = 0.9, beta2: float = 0.999, adam_eps: float = 1e-8,
-                 copy_target_at_init: bool = False):
+                 copy_target_at_init: bool = False, precision: str = "bf16"):
         if not torch.cuda.is_available():
             raise _lib.FlappyError("QNetwork needs a CUDA device (B200); there is no CPU path")
         self.device = torch.device(device)
@@ -61,6 +62,12 @@ class QNetwork:
         _lib.check(self._L.fb_qnet_create(hidden, int(dueling), max_batch, C.byref(h)), "fb_qnet_create")
         self._h = h
         self.hidden, self.dueling, self.max_batch = hidden, bool(dueling), max_batch
+        # "bf16": tcgen05 tensor cores (bf16 operands, fp32 accumulation); "fp32": strict CUDA-core FMA
+        self.precision = precision
+        _lib.check(self._L.fb_qnet_set_precision(self._h, PRECISIONS[precision]), "fb_qnet_set_precision")
+        self._seen_versions = None
+        self.compute_path = ("TMA + tcgen05 implicit GEMM (bf16 operands, fp32 accumulate in TMEM)" if precision == "bf16"
+                             else "fp32 CUDA-core implicit GEMM")
         lay = (C.c_int32 * 16)()
         _lib.check(self._L.fb_qnet_layout(self._h, lay), "fb_qnet_layout")
         names = ["w1", "b1", "w2", "b2", "w3", "b3", "wf1", "bf1", "wf2", "bf2", "wv", "bv", "wa", "ba"]
@@ -112,11 +119,20 @@ class QNetwork:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    def _sync_versions(self):
+        """The library refreshes its bf16 operand copies after its own Adam / target-sync; in-place writes made
+        through torch (tests, load_state_dict, an all-reduce of the parameters) are noticed here."""
+        v = (self.params._version, self.target._version)
+        if v != self._seen_versions:
+            _lib.check(self._L.fb_qnet_invalidate(self._h), "fb_qnet_invalidate")
+            self._seen_versions = v
+
     # ---------------------------------------------------------------- forward / act
     def forward(self, fb: FrameBatch, target: bool = False, out: torch.Tensor | None = None) -> torch.Tensor:
         """QValue.eval(feed_dict={stateInput: ...}) (BrainDQN.py:100): f32[B][2]."""
         q = out if out is not None else torch.empty((fb.batch, 2), dtype=torch.float32, device=self.device)
         p = self.target if target else self.params
+        self._sync_versions()
         _lib.check(self._L.fb_qnet_forward(self._h, p.data_ptr(), fb.ptr, fb.sample_stride, fb.chan_off, fb.batch,
                                            q.data_ptr(), self._stream()), "fb_qnet_forward")
         return q
@@ -124,6 +140,7 @@ class QNetwork:
     def act(self, fb: FrameBatch, epsilon: float, seed: int, first_env_id: int, rng_pos: torch.Tensor,
             actions_out: torch.Tensor, q_out: torch.Tensor):
         """getAction (BrainDQN.py:99-108) for every env of the batch."""
+        self._sync_versions()
         _lib.check(self._L.fb_qnet_act(self._h, self.params.data_ptr(), fb.ptr, fb.sample_stride, fb.chan_off, fb.batch,
                                        float(epsilon), seed, first_env_id, rng_pos.data_ptr(), q_out.data_ptr(),
                                        actions_out.data_ptr(), self._stream()), "fb_qnet_act")
@@ -140,6 +157,7 @@ class QNetwork:
         off_s = (C.c_int32 * 4)(0, 6400, 12800, 19200)
         off_n = (C.c_int32 * 4)(6400, 12800, 19200, 25600)
         ptr = lambda t: t.data_ptr() if t is not None else None
+        self._sync_versions()
         _lib.check(self._L.fb_qnet_loss_backward(
             self._h, VARIANTS[variant], self.params.data_ptr(), self.target.data_ptr(), frames.data_ptr(), 5 * 6400,
             off_s, off_n, actions.data_ptr(), rewards.data_ptr(), terminals.data_ptr(), ptr(is_weights), B,

@@ -143,6 +143,18 @@ int fb_resize_tables(int32_t *out_host);
 typedef struct fb_qnet fb_qnet;
 int fb_qnet_create(int hidden, int dueling, int max_batch, fb_qnet **out);
 int fb_qnet_destroy(fb_qnet *net);
+
+/* Arithmetic of the contractions (the TF ops of BrainDQN.py:123-154 and their gradients):
+ *   FB_PRECISION_FP32  CUDA-core FMA, fp32 everywhere (strict; the tolerance anchor)
+ *   FB_PRECISION_BF16  tcgen05 tensor cores fed by TMA: bf16 operands (the {0,255} inputs are exact), fp32
+ *                      accumulation in TMEM, bf16 activations between layers; head, TD loss and Adam stay fp32.
+ * fb_qnet_invalidate tells the net that the caller rewrote a parameter vector itself (the bf16 operand copies
+ * are otherwise refreshed after fb_qnet_adam / fb_qnet_sync_target). */
+#define FB_PRECISION_FP32 0
+#define FB_PRECISION_BF16 1
+int fb_qnet_set_precision(fb_qnet *net, int precision);
+int fb_qnet_get_precision(const fb_qnet *net);
+int fb_qnet_invalidate(fb_qnet *net);
 int fb_qnet_param_count(const fb_qnet *net);
 int fb_qnet_layout(const fb_qnet *net, int32_t *out16_host);
 
@@ -223,6 +235,10 @@ int fb_debug_host_step(int32_t *state16, int action, const uint8_t *gaps, int ga
                        uint64_t env_id, float *reward, uint8_t *terminal, int32_t *score);
 int fb_debug_host_obs(const int32_t *state16, int mode /* 0 tables, 1 per-pixel */, uint8_t *out6400);
 int fb_debug_host_mixed(const int32_t *state16);
+/* device test hook: one raw bf16 GEMM through the tcgen05 kernel of the Q-network path (descriptor self-test).
+ * mode 0: D[M][N] = A[M][K] Bt[N][K]^T;  mode 1: D[M][N] = A[K][M]^T B[K][N];  bn = N tile (32/64/128). */
+int fb_debug_tc_gemm(int mode, int bn, int M, int N, int K, const void *a_bf16_dev, const void *b_bf16_dev, float *d_dev,
+                     const uint32_t *strides6_host, void *stream);
 
 #ifdef __cplusplus
 }

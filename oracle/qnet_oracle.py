@@ -70,16 +70,51 @@ def _unpack(flat: torch.Tensor, hidden, dueling):
     return {n: flat[v[0]:v[0] + int(np.prod(v[1]))].reshape(v[1]) for n, v in L.items() if n != "total"}
 
 
-def forward(flat: torch.Tensor, x_u8, hidden=512, dueling=False, return_all=False):
-    """x_u8: [B,4,80,80] (channel = frame, oldest first; H = obs axis 0, W = obs axis 1) -> Q [B,2] float64."""
+def _bf16(t):
+    return t.to(torch.float32).to(torch.bfloat16).to(torch.float64)
+
+
+class _RoundFwd(torch.autograd.Function):
+    """value rounded to bf16, gradient passed through (a bf16 operand copy of an fp32 master tensor)"""
+
+    @staticmethod
+    def forward(ctx, t):
+        return _bf16(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _RoundBwd(torch.autograd.Function):
+    """identity whose GRADIENT is rounded to bf16 (a gradient tensor stored as bf16 between kernels)"""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return _bf16(g)
+
+
+def forward(flat: torch.Tensor, x_u8, hidden=512, dueling=False, return_all=False, emulate_bf16=False):
+    """x_u8: [B,4,80,80] (channel = frame, oldest first; H = obs axis 0, W = obs axis 1) -> Q [B,2] float64.
+
+    emulate_bf16: the same graph with the roundings of the tensor-core path (csrc/fb_qnet_tc.cu) put where that
+    path has them -- conv / fc1 weights and the activations z1, a2, a3 rounded to bf16, and (in backward) the
+    gradients dz1, dp1, dz2, dz3, dh1 rounded to bf16; sums stay exact.  Separates implementation errors
+    (must be ~1e-3) from the precision of the format (a few percent)."""
     p = _unpack(flat, hidden, dueling)
+    rw = _RoundFwd.apply if emulate_bf16 else (lambda t: t)
+    rb = _RoundBwd.apply if emulate_bf16 else (lambda t: t)
     x = torch.as_tensor(np.asarray(x_u8)).to(torch.float64)                      # values 0.0 / 255.0, no normalisation
-    z1 = F.relu(F.conv2d(x, p["w1"].permute(3, 2, 0, 1), p["b1"], stride=4, padding=2))        # SAME: pad 2/2
-    p1 = F.max_pool2d(z1, 2, 2)
-    a2 = F.relu(F.conv2d(p1, p["w2"].permute(3, 2, 0, 1), p["b2"], stride=2, padding=1))       # SAME: pad 1/1
-    a3 = F.relu(F.conv2d(a2, p["w3"].permute(3, 2, 0, 1), p["b3"], stride=1, padding=1))
+    z1 = rw(F.relu(rb(F.conv2d(x, rw(p["w1"]).permute(3, 2, 0, 1), p["b1"], stride=4, padding=2))))     # SAME: pad 2/2
+    p1 = rb(F.max_pool2d(z1, 2, 2))
+    a2 = rw(F.relu(rb(F.conv2d(p1, rw(p["w2"]).permute(3, 2, 0, 1), p["b2"], stride=2, padding=1))))    # SAME: pad 1/1
+    a3 = rw(F.relu(rb(F.conv2d(a2, rw(p["w3"]).permute(3, 2, 0, 1), p["b3"], stride=1, padding=1))))
     flat3 = a3.permute(0, 2, 3, 1).reshape(-1, FLAT)                                           # tf.reshape of NHWC
-    h1 = F.relu(flat3 @ p["wf1"] + p["bf1"])
+    h1 = F.relu(rb(flat3 @ rw(p["wf1"]) + p["bf1"]))
     if not dueling:
         q = h1 @ p["wf2"] + p["bf2"]
     else:
@@ -92,7 +127,7 @@ def forward(flat: torch.Tensor, x_u8, hidden=512, dueling=False, return_all=Fals
 
 
 def loss_and_grads(variant, params32, target32, s, s2, actions, rewards, terminals, isw=None, gamma=0.99, loss_sum=False,
-                   global_batch=None, hidden=512, dueling=False):
+                   global_batch=None, hidden=512, dueling=False, emulate_bf16=False):
     """variant 0 vanilla / 1 nature / 2 double.  Returns loss, grads (float64 flat), abs_err, y (fp32 as fed), q(s)."""
     P = torch.tensor(params32.astype(np.float64), requires_grad=True)
     T = torch.tensor((target32 if target32 is not None else params32).astype(np.float64))
@@ -100,18 +135,18 @@ def loss_and_grads(variant, params32, target32, s, s2, actions, rewards, termina
     gb = global_batch or B
     with torch.no_grad():
         if variant == 0:
-            x = forward(P.detach(), s2, hidden, dueling).max(dim=1).values
+            x = forward(P.detach(), s2, hidden, dueling, emulate_bf16=emulate_bf16).max(dim=1).values
         elif variant == 1:
-            x = forward(T, s2, hidden, dueling).max(dim=1).values
+            x = forward(T, s2, hidden, dueling, emulate_bf16=emulate_bf16).max(dim=1).values
         else:
-            qt = forward(T, s2, hidden, dueling)
-            am = forward(P.detach(), s2, hidden, dueling).argmax(dim=1)
+            qt = forward(T, s2, hidden, dueling, emulate_bf16=emulate_bf16)
+            am = forward(P.detach(), s2, hidden, dueling, emulate_bf16=emulate_bf16).argmax(dim=1)
             x = qt[torch.arange(B), am]
         # the reference feeds fp32 Q-values into a Python float64 loop and feeds y back as fp32
         x32 = x.numpy().astype(np.float32).astype(np.float64)
         r = np.array([0.1 if abs(float(v) - 0.1) < 1e-6 else float(v) for v in rewards], np.float64)
         y = np.where(np.asarray(terminals).astype(bool), r, r + gamma * x32).astype(np.float32)
-    q = forward(P, s, hidden, dueling)
+    q = forward(P, s, hidden, dueling, emulate_bf16=emulate_bf16)
     onehot = F.one_hot(torch.as_tensor(np.asarray(actions).astype(np.int64)), 2).to(torch.float64)
     q_eval = (q * onehot).sum(dim=1)
     err = torch.as_tensor(y.astype(np.float64)) - q_eval

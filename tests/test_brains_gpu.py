@@ -52,7 +52,7 @@ def test_training_step_matches_oracle_on_the_sampled_minibatch(mods):
     word stream, and the gradient equals the float64 oracle's on exactly those transitions"""
     game, brains = mods
     N, C = 16, 28
-    brain = brains.BrainDQNNature(2, "bird", num_envs=N, replay_memory_per_env=C, observe=1e9, batch_size=32, seed=5)
+    brain = brains.BrainDQNNature(2, "bird", num_envs=N, replay_memory_per_env=C, observe=1e9, batch_size=32, seed=5, precision="fp32")
     gs = game.GameState(num_envs=N, seed=9, history=C + 4, ring=brain.ring)
     hist = []
     obs, *_ = gs.frame_step(torch.zeros(N, dtype=torch.uint8, device="cuda"))

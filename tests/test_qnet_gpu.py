@@ -44,7 +44,7 @@ def test_forward_matches_oracle(mods, dueling):
     game, qnet = mods
     B = 37
     frames = _env_frames(game, B, 3)
-    net = qnet.QNetwork(hidden=512, dueling=dueling, max_batch=16)          # 37 > 16: exercises chunking
+    net = qnet.QNetwork(precision="fp32", hidden=512, dueling=dueling, max_batch=16)          # 37 > 16: exercises chunking
     flat = qo.init_params(512, dueling, seed=5) * np.float32(4.0)           # larger weights -> non-trivial activations
     _set_params(net, flat)
     q = net.forward(qnet.FrameBatch.from_stack(frames, 0)).cpu().numpy()
@@ -68,7 +68,7 @@ def test_forward_from_ring_view(mods):
     N = 21
     gs = game.GameState(num_envs=N, seed=1, history=7)
     gs.step_random(23, 0.4, 5)
-    net = qnet.QNetwork(max_batch=32)
+    net = qnet.QNetwork(precision="fp32", max_batch=32)
     q = net.forward(qnet.FrameBatch.from_ring(gs.ring, gs.slot)).cpu().numpy()
     st = gs.stacked_state().permute(0, 3, 1, 2).contiguous().cpu().numpy()      # [N,4,80,80], newest last
     ref = qo.forward(torch.tensor(net.params.cpu().numpy().astype(np.float64)), st).numpy()
@@ -84,7 +84,7 @@ def test_loss_and_gradients_match_oracle(mods, variant, dueling, loss_sum, per):
     game, qnet = mods
     B = 32
     frames = _env_frames(game, B, 11)
-    net = qnet.QNetwork(hidden=512, dueling=dueling, max_batch=B)
+    net = qnet.QNetwork(precision="fp32", hidden=512, dueling=dueling, max_batch=B)
     p = qo.init_params(512, dueling, seed=1) * np.float32(3.0)
     t = qo.init_params(512, dueling, seed=2) * np.float32(3.0)
     _set_params(net, p, t)
@@ -119,7 +119,7 @@ def test_sharded_gradients_sum_to_global_gradient(mods):
     game, qnet = mods
     B = 32
     frames = _env_frames(game, B, 5)
-    net = qnet.QNetwork(max_batch=B)
+    net = qnet.QNetwork(precision="fp32", max_batch=B)
     rng = np.random.default_rng(1)
     a = torch.from_numpy(rng.integers(0, 2, B).astype(np.uint8)).cuda()
     r = torch.from_numpy(rng.choice(np.array([0.1, 3.0, -3.0], np.float32), B)).cuda()
@@ -138,7 +138,7 @@ def test_sharded_gradients_sum_to_global_gradient(mods):
 
 def test_adam_matches_tf1_rule(mods):
     game, qnet = mods
-    net = qnet.QNetwork(max_batch=8, seed=3)
+    net = qnet.QNetwork(precision="fp32", max_batch=8, seed=3)
     p = net.params.cpu().numpy().copy()
     ref = qo.AdamTF1(len(p))
     rng = np.random.default_rng(2)
@@ -160,7 +160,7 @@ def test_epsilon_greedy_matches_cpython_random(mods):
     N = 300
     gs = game.GameState(num_envs=N, seed=4)
     gs.step_random(9, 0.5, 1)
-    net = qnet.QNetwork(max_batch=512)
+    net = qnet.QNetwork(precision="fp32", max_batch=512)
     pos = torch.zeros(N, dtype=torch.int32, device="cuda")
     pos_ref = np.zeros(N, np.int64)
     acts = torch.zeros(N, dtype=torch.uint8, device="cuda"); q = torch.zeros((N, 2), device="cuda")

@@ -1,0 +1,194 @@
+"""GPU parity of the tensor-core Q-network path (csrc/fb_qnet_tc.cu: TMA + tcgen05, bf16 operands, fp32 accumulate).
+
+Oracle: oracle/qnet_oracle.py (float64 restatement of the TF-1.12 graph, PARITY UNPINNED -- see its header).
+Two comparisons, two tolerances (operands and stored activations / gradients are bf16: 8 significant bits, unit
+round-off 2^-9 = 0.2 %; sums, head, TD loss and Adam are fp32):
+
+  (A) implementation -- against the oracle run with emulate_bf16=True (the same float64 graph with the bf16
+      roundings placed where this path has them).  What is left is fp32-vs-float64 summation and the rare
+      ReLU / max-pool decision that flips on it:
+        Q-values   |dq| <= 3e-3 * max|q_ref|        loss  relative 3e-3       y  |dy| <= 3e-3 * max|y_ref|
+        gradients  per tensor ||g - g_ref||_2 <= 1.5e-2 ||g_ref||_2
+  (B) precision of the format -- against the exact float64 oracle:
+        Q-values   |dq| <= 2e-2 * max|q_ref|        loss  relative 3e-2
+        gradients  per tensor ||g - g_ref||_2 <= 1.2e-1 ||g_ref||_2 at minibatch 32 (measured 5-7 %: rounded
+                   activations flip ReLU masks of individual samples; the error averages down with the batch,
+                   measured < 4 % at minibatch 256)
+  raw GEMM self-test: exact bf16 inputs, fp32 accumulation: |d - ref| <= 9e-3 * sqrt(K)
+The strict-fp32 path (tests/test_qnet_gpu.py, 2e-4) remains the anchor.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import qnet_oracle as qo  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def mods():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from dqnflappybird_b200 import _lib, game, qnet
+    return _lib, game, qnet
+
+
+def _gemm(_lib, mode, bn, a, b, M, N, K, strides=None):
+    d = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
+    st = (C.c_uint32 * 6)(*strides) if strides is not None else None
+    _lib.check(_lib.lib().fb_debug_tc_gemm(mode, bn, M, N, K, a.data_ptr(), b.data_ptr(), d.data_ptr(), st,
+                                           torch.cuda.current_stream().cuda_stream), "fb_debug_tc_gemm")
+    torch.cuda.synchronize()
+    return d
+
+
+@pytest.mark.parametrize("bn,M,N,K", [(32, 300, 32, 256), (64, 128, 64, 576), (128, 256, 512, 1600), (64, 77, 128, 64)])
+def test_raw_gemm_k_major(mods, bn, M, N, K):
+    """D = A Bt^T through the kernel the forward and data-gradient layers use (both operands K-major, SWIZZLE_128B)"""
+    _lib, _, _ = mods
+    g = torch.Generator(device="cuda").manual_seed(bn + M)
+    a = torch.randn((M, K), device="cuda", generator=g).to(torch.bfloat16)
+    b = torch.randn((N, K), device="cuda", generator=g).to(torch.bfloat16)
+    d = _gemm(_lib, 0, bn, a, b, M, N, K)
+    ref = a.double() @ b.double().T
+    err = (d.double() - ref).abs().max().item()
+    assert err <= 1e-3 * np.sqrt(K) * 9, (err, bn, M, N, K)
+
+
+@pytest.mark.parametrize("bn,M,N,K", [(64, 128, 64, 64), (64, 256, 64, 1000), (32, 256, 32, 1536), (128, 1600, 512, 256), (64, 576, 64, 333)])
+def test_raw_gemm_mn_major(mods, bn, M, N, K):
+    """D = A^T B with the contraction over ROWS of both row-major operands (weight gradients): MN-major descriptors"""
+    _lib, _, _ = mods
+    g = torch.Generator(device="cuda").manual_seed(bn + K)
+    a = torch.randn((K, M), device="cuda", generator=g).to(torch.bfloat16)
+    b = torch.randn((K, N), device="cuda", generator=g).to(torch.bfloat16)
+    d = _gemm(_lib, 1, bn, a, b, M, N, K)
+    ref = a.double().T @ b.double()
+    err = (d.double() - ref).abs().max().item()
+    assert err <= 1e-3 * np.sqrt(K) * 9, (err, bn, M, N, K)
+
+
+def _env_frames(game, B, seed):
+    gs = game.GameState(num_envs=B, seed=seed, history=5)
+    gs.step_random(40 + seed % 7, 0.3, 99 + seed)
+    gs.step_random(5, 0.3, 99 + seed)
+    torch.cuda.synchronize()
+    order = [(gs.slot - 4 + k) % 5 for k in range(5)]
+    return gs.ring[:, order].contiguous()
+
+
+def _set_params(net, flat, target=None):
+    net.params.copy_(torch.from_numpy(flat))
+    net.target.copy_(torch.from_numpy(target if target is not None else flat))
+
+
+@pytest.mark.parametrize("dueling", [False, True])
+def test_forward_matches_oracle_bf16(mods, dueling):
+    _lib, game, qnet = mods
+    B = 37
+    frames = _env_frames(game, B, 3)
+    net = qnet.QNetwork(hidden=512, dueling=dueling, max_batch=16, precision="bf16")     # 37 > 16: chunking
+    flat = qo.init_params(512, dueling, seed=5) * np.float32(4.0)
+    _set_params(net, flat)
+    q = net.forward(qnet.FrameBatch.from_stack(frames, 0)).cpu().numpy()
+    q2 = net.forward(qnet.FrameBatch.from_stack(frames, 1)).cpu().numpy()
+    x = frames.cpu().numpy()
+    ref = qo.forward(torch.tensor(flat.astype(np.float64)), x[:, 0:4], 512, dueling).numpy()
+    ref2 = qo.forward(torch.tensor(flat.astype(np.float64)), x[:, 1:5], 512, dueling).numpy()
+    emu = qo.forward(torch.tensor(flat.astype(np.float64)), x[:, 0:4], 512, dueling, emulate_bf16=True).numpy()
+    assert np.abs(q - emu).max() <= 3e-3 * np.abs(emu).max(), np.abs(q - emu).max() / np.abs(emu).max()          # (A)
+    assert np.abs(q - ref).max() <= 2e-2 * np.abs(ref).max(), np.abs(q - ref).max() / np.abs(ref).max()          # (B)
+    assert np.abs(q2 - ref2).max() <= 2e-2 * np.abs(ref2).max()
+    noise = (torch.rand((9, 5, 80, 80), device="cuda") < 0.3).to(torch.uint8) * 255
+    qn = net.forward(qnet.FrameBatch.from_stack(noise.contiguous(), 0)).cpu().numpy()
+    refn = qo.forward(torch.tensor(flat.astype(np.float64)), noise.cpu().numpy()[:, 0:4], 512, dueling).numpy()
+    assert np.abs(qn - refn).max() <= 2e-2 * np.abs(refn).max()
+    # and the strict path agrees with it to the same bound
+    net32 = qnet.QNetwork(hidden=512, dueling=dueling, max_batch=64, precision="fp32")
+    _set_params(net32, flat)
+    q32 = net32.forward(qnet.FrameBatch.from_stack(frames, 0)).cpu().numpy()
+    assert np.abs(q - q32).max() <= 2e-2 * np.abs(q32).max()
+
+
+def test_forward_from_ring_view_bf16(mods):
+    _lib, game, qnet = mods
+    N = 300
+    gs = game.GameState(num_envs=N, seed=1, history=7)
+    gs.step_random(23, 0.4, 5)
+    net = qnet.QNetwork(max_batch=256, precision="bf16")
+    net.params.mul_(4.0)
+    q = net.forward(qnet.FrameBatch.from_ring(gs.ring, gs.slot)).cpu().numpy()
+    st = gs.stacked_state().permute(0, 3, 1, 2).contiguous().cpu().numpy()
+    ref = qo.forward(torch.tensor(net.params.cpu().numpy().astype(np.float64)), st).numpy()
+    assert np.abs(q - ref).max() <= 2e-2 * np.abs(ref).max()
+
+
+CASES = [("vanilla", False, True, False, 32), ("nature", False, False, False, 32), ("double", False, False, False, 32),
+         ("nature", True, False, False, 32), ("nature", False, False, True, 32), ("double", True, False, True, 32),
+         ("nature", False, False, False, 256), ("nature", False, False, False, 100)]
+
+
+@pytest.mark.parametrize("variant,dueling,loss_sum,per,B", CASES)
+def test_loss_and_gradients_match_oracle_bf16(mods, variant, dueling, loss_sum, per, B):
+    _lib, game, qnet = mods
+    frames = _env_frames(game, B, 11)
+    net = qnet.QNetwork(hidden=512, dueling=dueling, max_batch=256, precision="bf16")
+    p = qo.init_params(512, dueling, seed=1) * np.float32(3.0)
+    t = qo.init_params(512, dueling, seed=2) * np.float32(3.0)
+    _set_params(net, p, t)
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 2, B).astype(np.uint8)
+    r = rng.choice(np.array([0.1, 3.0, -3.0], np.float32), B, p=[0.8, 0.1, 0.1])
+    term = (r == -3.0).astype(np.uint8)
+    isw = rng.random(B).astype(np.float32) if per else None
+    abs_err = torch.zeros(B, device="cuda"); y = torch.zeros(B, device="cuda")
+    net.loss_backward(variant, frames, torch.from_numpy(a).cuda(), torch.from_numpy(r).cuda(), torch.from_numpy(term).cuda(),
+                      torch.from_numpy(isw).cuda() if per else None, 0.99, loss_sum, None, abs_err, y)
+    x = frames.cpu().numpy()
+    g = net.grads.cpu().numpy().astype(np.float64)
+    assert np.isfinite(g).all()
+    L = qo.layout(512, dueling)
+    for emulate, tol_loss, tol_y, tol_g in ((True, 3e-3, 3e-3, 1.5e-2), (False, 3e-2, 2e-2, 1.2e-1)):
+        loss, g_ref, ae_ref, y_ref, _ = qo.loss_and_grads(qnet.VARIANTS[variant], p, t, x[:, 0:4], x[:, 1:5], a, r, term, isw, 0.99,
+                                                          loss_sum, None, 512, dueling, emulate_bf16=emulate)
+        assert abs(net.loss.item() - loss) <= tol_loss * abs(loss), (emulate, net.loss.item(), loss)
+        assert np.abs(y.cpu().numpy() - y_ref).max() <= tol_y * np.abs(y_ref).max(), emulate
+        report = {}
+        for name, v in L.items():
+            if name == "total":
+                continue
+            o, shp = v
+            sz = int(np.prod(shp))
+            num = np.linalg.norm(g[o:o + sz] - g_ref[o:o + sz]); den = np.linalg.norm(g_ref[o:o + sz])
+            assert den > 0, name
+            report[name] = float(num / den)
+        assert all(v <= tol_g for v in report.values()), (emulate, report)
+
+
+def test_training_steps_track_the_strict_path(mods):
+    """ten Nature-DQN updates on the same minibatches: bf16 and fp32 paths stay together (Adam lr 1e-6)"""
+    _lib, game, qnet = mods
+    B = 64
+    frames = _env_frames(game, B, 7)
+    nets = [qnet.QNetwork(max_batch=B, seed=3, precision=pr) for pr in ("bf16", "fp32")]
+    for n in nets:
+        n.params.mul_(3.0); n.target.mul_(3.0)
+    rng = np.random.default_rng(4)
+    p0 = nets[0].params.clone()
+    for step in range(10):
+        a = torch.from_numpy(rng.integers(0, 2, B).astype(np.uint8)).cuda()
+        r = torch.from_numpy(rng.choice(np.array([0.1, 3.0, -3.0], np.float32), B)).cuda()
+        term = (r == -3.0).to(torch.uint8)
+        for n in nets:
+            n.loss_backward("nature", frames, a, r, term)
+            n.adam_step()
+        if step == 4:
+            for n in nets:
+                n.sync_target()
+    u0, u1 = (nets[0].params - p0).double(), (nets[1].params - p0).double()     # Adam normalises: compare directions
+    cos = (u0 @ u1 / (u0.norm() * u1.norm())).item()
+    assert u1.abs().max().item() > 5e-6 and cos > 0.95, cos
+    assert abs(nets[0].loss.item() - nets[1].loss.item()) <= 3e-2 * abs(nets[1].loss.item())
