@@ -27,6 +27,7 @@
 
 #include "fb_qnet.cuh"
 #include "fb_tc.cuh"
+#include "fb_tc_conv.cuh"
 
 using bf16 = __nv_bfloat16;
 
@@ -40,8 +41,9 @@ constexpr int kThreads = 192;             // warp 0 TMA, warp 1 MMA + TMEM owner
 
 // ------------------------------------------------------------------------------------------------ the GEMM
 struct GemmParams {
-    // MODE 0 (K-major A and B):  D[m][n] = sum_kb sum_k A[m + a_rowoff[kb]][a_col[kb] + k] * Bt[n][64 kb + k]
-    int nkb;
+    // MODE 0 (K-major A and B):  D[m][n] = sum_kb sum_k A[m + a_rowoff[kb]][a_col[kb] + k] * Bt[n][64 kb + k];
+    // CTA z takes K-blocks [z kper, min(nkb, (z+1) kper))
+    int nkb, kper;
     int a_rowoff[kMaxKb];
     int a_col[kMaxKb];
     // MODE 1 (MN-major A and B): D[128 mt + 64 i + j][n] = sum_p A[p + a2_rowoff[mt][i]][a2_col[mt][i] + j] * B[p][n]
@@ -64,8 +66,8 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mt = blockIdx.x, n0 = blockIdx.y * BN;
 
-    int nkb, p_begin = 0;
-    if (MODE == 0) nkb = g.nkb;
+    int nkb, p_begin = 0, kb0 = 0;
+    if (MODE == 0) { kb0 = blockIdx.z * g.kper; nkb = min(g.kper, g.nkb - kb0); }
     else {
         p_begin = blockIdx.z * g.klen;
         int len = min(g.klen, g.p_total - p_begin);
@@ -95,8 +97,8 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
                 const uint32_t sa = smem + s * STAGE, sb = sa + A_BYTES;
                 tc::mbar_expect_tx(full, STAGE);
                 if (MODE == 0) {
-                    tc::tma_load_2d(sa, &mapA, g.a_col[kb], mt * 128 + g.a_rowoff[kb], full);
-                    tc::tma_load_2d(sb, &mapB, kb * 64, n0, full);
+                    tc::tma_load_2d(sa, &mapA, g.a_col[kb0 + kb], mt * 128 + g.a_rowoff[kb0 + kb], full);
+                    tc::tma_load_2d(sb, &mapB, (kb0 + kb) * 64, n0, full);
                 } else {
                     const int p = p_begin + kb * 64;
                     tc::tma_load_2d(sa, &mapA, g.a2_col[mt][0], p + g.a2_rowoff[mt][0], full);
@@ -216,17 +218,6 @@ struct EpiConv3 {               // rows on the 7-grid -> dense A3 [B][25][64] (T
 #pragma unroll
         for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i] + __ldg(bias + col + i), 0.f);
         store_bf16x16(a3 + ((size_t)b * 25 + oh * 5 + ow) * 64 + col, v);
-    }
-};
-struct EpiFc1 {                 // H1 fp32 [B][H] = relu(fc + b)
-    float *h1; const float *bias; int B, hidden;
-    __device__ void operator()(int row, int col, float (&v)[16], int) const {
-        if (row >= B) return;
-        float4 *d = reinterpret_cast<float4 *>(h1 + (size_t)row * hidden + col);
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-            d[i] = make_float4(fmaxf(v[4 * i] + __ldg(bias + col + 4 * i), 0.f), fmaxf(v[4 * i + 1] + __ldg(bias + col + 4 * i + 1), 0.f),
-                               fmaxf(v[4 * i + 2] + __ldg(bias + col + 4 * i + 2), 0.f), fmaxf(v[4 * i + 3] + __ldg(bias + col + 4 * i + 3), 0.f));
     }
 };
 struct EpiFc1Dgrad {            // dA3 [B][1600] masked by relu(a3) -> dZ3 on the 7-grid [B*49][64]
@@ -429,24 +420,129 @@ __global__ void pack_weights_kernel(const float *params, QnetLayout L, PackedWei
     }
 }
 
-// column sums of a bf16 matrix [rows][N] in chunks -> part[chunk][N] (bias gradients, summed in order later)
-__global__ void colsum_kernel(const bf16 *x, int rows, int N, int chunk_rows, float *part) {
-    __shared__ float red[256];
-    const int chunk = blockIdx.x, r0 = chunk * chunk_rows, r1 = min(rows, r0 + chunk_rows);
-    for (int c0 = 0; c0 < N; c0 += 256) {
-        const int ncol = min(N - c0, 256), lanes = 256 / ncol;          // N in {32, 64, 512}: lanes in {8, 4, 1}
-        const int col = threadIdx.x % ncol, rl = threadIdx.x / ncol;
-        float s = 0.f;
-        if (rl < lanes)
-            for (int r = r0 + rl; r < r1; r += lanes) s += __bfloat162float(x[(size_t)r * N + c0 + col]);
-        red[threadIdx.x] = s;
+// column sums of bf16 matrices [rows][N] in row chunks -> part[chunk][N] (bias gradients; summed in order by
+// finalize_grads_kernel).  One launch covers all jobs; 16-byte loads, a warp reads whole rows.
+struct ColsumJob { const bf16 *x; float *part; int rows, N, chunk_rows, first_block; };
+struct ColsumJobs { ColsumJob j[3]; int njobs; };
+__global__ void __launch_bounds__(256) colsum_kernel(ColsumJobs jobs) {
+    __shared__ float red[8][64 + 1];
+    int ji = 0;
+#pragma unroll
+    for (int k = 1; k < 3; k++) if (k < jobs.njobs && (int)blockIdx.x >= jobs.j[k].first_block) ji = k;
+    const ColsumJob jb = jobs.j[ji];
+    const int chunk = blockIdx.x - jb.first_block;
+    const int r0 = chunk * jb.chunk_rows, r1 = min(jb.rows, r0 + jb.chunk_rows);
+    const int vec = jb.N >> 3;                       // 16-byte vectors per row: 4 (N = 32) or 8 (N = 64)
+    const int rows_per_pass = 256 / vec;
+    const int v = threadIdx.x % vec, rl = threadIdx.x / vec;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0.f;
+    for (int r = r0 + rl; r < r1; r += rows_per_pass) {
+        uint4 raw = __ldg(reinterpret_cast<const uint4 *>(jb.x + (size_t)r * jb.N) + v);
+        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { float2 f = __bfloat1622float2(h[i]); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
+    }
+    // lanes with equal (lane % vec) hold the same columns: butterfly over the other lane bits, then across warps
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        for (int o = 16; o >= vec; o >>= 1) acc[i] += __shfl_xor_sync(~0u, acc[i], o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < vec)
+#pragma unroll
+        for (int i = 0; i < 8; i++) red[warp][lane * 8 + i] = acc[i];
+    __syncthreads();
+    if ((int)threadIdx.x < jb.N) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) t += red[w][threadIdx.x];
+        jb.part[(size_t)chunk * jb.N + threadIdx.x] = t;
+    }
+}
+
+// Head backward in one pass over h1 (BrainDQN.py:151-154 / dueling BrainDuelingDQN_CC.py:68-77): gradients of the head
+// weights, dh1 = dQ W^T masked by relu (bf16, the operand of the fc1 gradient GEMMs) and the fc1 bias gradient
+// sum_b dh1.  Block = 32 hidden units x 8 row lanes; block gridDim.x-1 does the head bias.
+__global__ void __launch_bounds__(256) head_backward_tc_kernel(const float *h1, const float *dq, const float *params, QnetLayout L, int B,
+                                                               float *grads, bf16 *dh1) {
+    __shared__ float red[8][32][4];
+    const int H = L.hidden;
+    if ((int)blockIdx.x == H / 32) {                 // head bias gradients: sum_b dq (dueling: (d0+d1) for V, d - mean for A)
+        float s0 = 0.f, s1 = 0.f;
+        for (int b = threadIdx.x; b < B; b += 256) { s0 += dq[b * 2]; s1 += dq[b * 2 + 1]; }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { s0 += __shfl_xor_sync(~0u, s0, o); s1 += __shfl_xor_sync(~0u, s1, o); }
+        if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0][0] = s0; red[threadIdx.x >> 5][0][1] = s1; }
         __syncthreads();
-        if (threadIdx.x < ncol) {
-            float tot = 0.f;
-            for (int k = 0; k < lanes; k++) tot += red[k * ncol + threadIdx.x];
-            part[(size_t)chunk * N + c0 + threadIdx.x] = tot;
+        if (threadIdx.x == 0) {
+            float t0 = 0.f, t1 = 0.f;
+            for (int w = 0; w < 8; w++) { t0 += red[w][0][0]; t1 += red[w][0][1]; }
+            if (!L.dueling) { grads[L.bf2] = t0; grads[L.bf2 + 1] = t1; }
+            else { float m = (t0 + t1) * 0.5f; grads[L.ba] = t0 - m; grads[L.ba + 1] = t1 - m; grads[L.bv] = t0 + t1; }
         }
-        __syncthreads();
+        return;
+    }
+    const int jl = threadIdx.x & 31, rl = threadIdx.x >> 5, j = blockIdx.x * 32 + jl;
+    float w0, w1, wv = 0.f;
+    if (!L.dueling) { w0 = params[L.wf2 + j * 2]; w1 = params[L.wf2 + j * 2 + 1]; }
+    else { w0 = params[L.wa + j * 2]; w1 = params[L.wa + j * 2 + 1]; wv = params[L.wv + j]; }
+    float g0 = 0.f, g1 = 0.f, gv = 0.f, gb = 0.f;
+    for (int b = rl; b < B; b += 8) {
+        float x = h1[(size_t)b * H + j];
+        float d0 = dq[b * 2], d1 = dq[b * 2 + 1], g;
+        if (!L.dueling) { g0 = fmaf(x, d0, g0); g1 = fmaf(x, d1, g1); g = d0 * w0 + d1 * w1; }
+        else {
+            float m = (d0 + d1) * 0.5f;
+            g0 = fmaf(x, d0 - m, g0); g1 = fmaf(x, d1 - m, g1); gv = fmaf(x, d0 + d1, gv);
+            g = (d0 - m) * w0 + (d1 - m) * w1 + (d0 + d1) * wv;
+        }
+        g = x > 0.f ? g : 0.f;
+        bf16 gr = __float2bfloat16(g);
+        dh1[(size_t)b * H + j] = gr;
+        gb += __bfloat162float(gr);                  // the bias gradient sums what the weight-gradient GEMM sees
+    }
+    red[rl][jl][0] = g0; red[rl][jl][1] = g1; red[rl][jl][2] = gv; red[rl][jl][3] = gb;
+    __syncthreads();
+    if (rl == 0) {
+        float t0 = 0.f, t1 = 0.f, tv = 0.f, tb = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { t0 += red[w][jl][0]; t1 += red[w][jl][1]; tv += red[w][jl][2]; tb += red[w][jl][3]; }
+        if (!L.dueling) { grads[L.wf2 + j * 2] = t0; grads[L.wf2 + j * 2 + 1] = t1; }
+        else { grads[L.wa + j * 2] = t0; grads[L.wa + j * 2 + 1] = t1; grads[L.wv + j] = tv; }
+        grads[L.bf1 + j] = tb;
+    }
+}
+
+// fc1 split-K finish fused with the Q head (BrainDQN.py:146-154; dueling BrainDuelingDQN_CC.py:68-77): one CTA per
+// sample sums the K-split partials in order, adds the bias, applies ReLU, keeps h1 (fp32) for backward and reduces
+// the two (three) head dot products.
+__global__ void __launch_bounds__(128) fc1_head_kernel(const float *part, int splits, size_t split_stride, const float *params, QnetLayout L,
+                                                      int B, float *h1, float *q) {
+    __shared__ float red[4][3];
+    const int b = blockIdx.x, H = L.hidden;
+    float s0 = 0.f, s1 = 0.f, sv = 0.f;
+    for (int j = threadIdx.x; j < H; j += 128) {
+        float x = params[L.bf1 + j];
+        for (int z = 0; z < splits; z++) x += part[(size_t)z * split_stride + (size_t)b * H + j];
+        x = fmaxf(x, 0.f);
+        h1[(size_t)b * H + j] = x;
+        if (!L.dueling) { s0 = fmaf(x, params[L.wf2 + j * 2], s0); s1 = fmaf(x, params[L.wf2 + j * 2 + 1], s1); }
+        else { s0 = fmaf(x, params[L.wa + j * 2], s0); s1 = fmaf(x, params[L.wa + j * 2 + 1], s1); sv = fmaf(x, params[L.wv + j], sv); }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { s0 += __shfl_xor_sync(~0u, s0, o); s1 += __shfl_xor_sync(~0u, s1, o); sv += __shfl_xor_sync(~0u, sv, o); }
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = s0; red[threadIdx.x >> 5][1] = s1; red[threadIdx.x >> 5][2] = sv; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t0 = 0.f, t1 = 0.f, tv = 0.f;
+        for (int w = 0; w < 4; w++) { t0 += red[w][0]; t1 += red[w][1]; tv += red[w][2]; }
+        if (!L.dueling) { q[b * 2] = t0 + params[L.bf2]; q[b * 2 + 1] = t1 + params[L.bf2 + 1]; }
+        else {
+            float a0 = t0 + params[L.ba], a1 = t1 + params[L.ba + 1], v = tv + params[L.bv];
+            float mean = (a0 + a1) * 0.5f;
+            q[b * 2] = v + (a0 - mean); q[b * 2 + 1] = v + (a1 - mean);
+        }
     }
 }
 
@@ -454,12 +550,11 @@ __global__ void colsum_kernel(const bf16 *x, int rows, int N, int chunk_rows, fl
 struct FinalizeArgs {
     const float *part1, *part2, *part3, *partf;     // [splits][rows][N]
     int s1, s2, s3;                                  // number of splits (fc1 has one)
-    const float *bp1, *bp2, *bp3, *bpf;             // bias partials [chunks][N]
-    int c1, c2, c3, cf;
+    const float *bp1, *bp2, *bp3;                   // bias partials [chunks][N] (the fc1 bias comes from the head kernel)
+    int c1, c2, c3;
 };
 __global__ void finalize_grads_kernel(FinalizeArgs a, QnetLayout L, float *grads) {
-    const int H = L.hidden;
-    const int end = L.bf1 + H;
+    const int end = L.bf1;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x) {
         float s = 0.f;
         if (i < L.b1) {                     // W1 [kh][kw][c][n]
@@ -482,11 +577,8 @@ __global__ void finalize_grads_kernel(FinalizeArgs a, QnetLayout L, float *grads
         } else if (i < L.wf1) {
             int n = i - L.b3;
             for (int k = 0; k < a.c3; k++) s += a.bp3[k * 64 + n];
-        } else if (i < L.bf1) {
-            s = a.partf[i - L.wf1];
         } else {
-            int n = i - L.bf1;
-            for (int k = 0; k < a.cf; k++) s += a.bpf[k * H + n];
+            s = a.partf[i - L.wf1];
         }
         grads[i] = s;
     }
@@ -519,7 +611,7 @@ int make_map(CUtensorMap *m, const bf16 *base, long long rows, long long cols, i
     return FB_OK;
 }
 
-void set_kmajor(GemmParams &g) { g.lbo_a = 16; g.sbo_a = 1024; g.kstep_a = 32; g.lbo_b = 16; g.sbo_b = 1024; g.kstep_b = 32; }
+void set_kmajor(GemmParams &g) { g.kper = kMaxKb; g.lbo_a = 16; g.sbo_a = 1024; g.kstep_a = 32; g.lbo_b = 16; g.sbo_b = 1024; g.kstep_b = 32; }
 void set_mnmajor(GemmParams &g, int bn) {
     g.lbo_a = 8192; g.sbo_a = 1024; g.kstep_a = 2048;
     if (bn == 32) { g.lbo_b = 4096; g.sbo_b = 512; g.kstep_b = 1024; }
@@ -532,30 +624,39 @@ void set_mnmajor(GemmParams &g, int bn) {
 struct TcWeightMaps { CUtensorMap w1p, w2p, w3p, wf1p, wf1n, w3d, w2d; };
 struct TcPlan {                 // everything that depends on the batch size
     int B;
-    CUtensorMap x2_k, p2_k, a2_k, a3_k, dh1_k, dz3_k, dz2_k;        // K-major A operands, box 64 x 128
-    CUtensorMap x2_m, p2_m, a2_m, a3_m;                              // MN-major A operands, box 64 x 64
-    CUtensorMap dz1_b, dz2_b, dz3_b, dh1_b;                          // MN-major B operands
-    GemmParams conv1, conv2, conv3, fc1, fc1_d, conv3_d, conv2_d;
-    GemmParams conv1_w, conv2_w, conv3_w, fc1_w;
-    int s1, s2, s3;                                                  // weight-gradient splits
+    CUtensorMap a3_k, dh1_k;                                         // fc1 K-major A operands, box 64 x 128
+    CUtensorMap a3_m, dh1_b;                                         // fc1 weight gradient (MN-major), boxes 64 x 64
+    CUtensorMap x2_s, p2_s, a2_s, dz3_s, dz2_s;                      // convolution slabs (forward / data gradient)
+    CUtensorMap x2_w, p2_w, a2_w;                                    // weight-gradient slabs (A)
+    CUtensorMap dz1_b, dz2_b, dz3_b;                                 // weight-gradient B operands, 64 rows
+    GemmParams fc1, fc1_d, fc1_w;
+    ConvParams conv1, conv2, conv3, conv3_d, conv2_d;
+    WgradParams conv1_w, conv2_w, conv3_w;
+    int s1, s2, s3, sf;                                              // split-K counts (conv weight gradients, fc1 forward)
 };
 struct TcState {
     // activations / gradients (bf16 unless noted), sized for max_batch
     bf16 *x2, *z1, *p2, *a2, *a3, *dh1, *dz3, *dz2, *dp2, *dz1;
-    float *part1, *part2, *part3, *partf;
+    float *part1, *part2, *part3, *partf, *parth;
     size_t cap1, cap2, cap3;
-    float *bp1, *bp2, *bp3, *bpf;
+    float *bp1, *bp2, *bp3;
     PackedWeights pw[2];
     TcWeightMaps wm[2];
     std::map<int, TcPlan> plans;
+    int n_sms;
 };
 
 namespace {
 
-constexpr int kChunk1 = 768, kChunk23 = 256, kChunkF = 64;
+constexpr int kChunk1 = 1024, kChunk23 = 256;
+constexpr int kFc1Splits = 5;                    // fc1 forward: 25 K-blocks in 5 K-splits of 5
 
-int plan_splits(long long P, int tiles, int *klen_out) {
-    int target = 148 / tiles; if (target < 1) target = 1;
+// slab geometry (rows of 128 bytes): tile or K-block rows + the largest tap offset, rounded up to 8
+constexpr int kSlab1 = 152, kSlab2 = 136, kSlab3 = 144;          // forward / data gradient, 128-position tiles
+constexpr int kSlabW1 = 88, kSlabW2 = 72, kSlabW3 = 88;          // weight gradient, 64-position K-blocks
+
+int plan_splits(long long P, int target, int *klen_out) {
+    if (target < 1) target = 1;
     long long klen = (P + target - 1) / target;
     klen = (klen + 63) / 64 * 64;
     if (klen < 64) klen = 64;
@@ -574,41 +675,44 @@ int make_plan(fb_qnet *n, int B, TcPlan **out) {
     const long long P1 = (long long)B * kP1, P2 = (long long)B * kP2;
     int rc;
 #define MAP(dst, base, rows, cols, bc, br) if ((rc = make_map(&p.dst, base, rows, cols, bc, br))) return rc
-    MAP(x2_k, t->x2, P1, 64, 64, 128); MAP(p2_k, t->p2, P2, 128, 64, 128); MAP(a2_k, t->a2, P2, 64, 64, 128);
-    MAP(a3_k, t->a3, B, kFlat, 64, 128); MAP(dh1_k, t->dh1, B, H, 64, 128); MAP(dz3_k, t->dz3, P2, 64, 64, 128);
-    MAP(dz2_k, t->dz2, P2, 64, 64, 128);
-    MAP(x2_m, t->x2, P1, 64, 64, 64); MAP(p2_m, t->p2, P2, 128, 64, 64); MAP(a2_m, t->a2, P2, 64, 64, 64);
-    MAP(a3_m, t->a3, B, kFlat, 64, 64);
+    MAP(a3_k, t->a3, B, kFlat, 64, 128); MAP(dh1_k, t->dh1, B, H, 64, 128);
+    MAP(a3_m, t->a3, B, kFlat, 64, 64); MAP(dh1_b, t->dh1, B, H, 64, 64);
+    MAP(x2_s, t->x2, P1, 64, 64, kSlab1); MAP(p2_s, t->p2, P2, 128, 64, kSlab2); MAP(a2_s, t->a2, P2, 64, 64, kSlab3);
+    MAP(dz3_s, t->dz3, P2, 64, 64, kSlab3); MAP(dz2_s, t->dz2, P2, 64, 64, kSlab2);
+    MAP(x2_w, t->x2, P1, 64, 64, kSlabW1); MAP(p2_w, t->p2, P2, 128, 64, kSlabW2); MAP(a2_w, t->a2, P2, 64, 64, kSlabW3);
     MAP(dz1_b, t->dz1, P1, 32, 32, 64); MAP(dz2_b, t->dz2, P2, 64, 64, 64); MAP(dz3_b, t->dz3, P2, 64, 64, 64);
-    MAP(dh1_b, t->dh1, B, H, 64, 64);
 #undef MAP
-    // ---- forward
-    set_kmajor(p.conv1); p.conv1.nkb = 4;
-    for (int k = 0; k < 4; k++) { p.conv1.a_rowoff[k] = (k >> 1) * kG1 + (k & 1); p.conv1.a_col[k] = 0; }
-    set_kmajor(p.conv2); p.conv2.nkb = 8;
-    for (int k = 0; k < 8; k++) { int tp = k >> 1; p.conv2.a_rowoff[k] = (tp >> 1) * kG2 + (tp & 1); p.conv2.a_col[k] = (k & 1) * 64; }
-    set_kmajor(p.conv3); p.conv3.nkb = 9;
-    for (int k = 0; k < 9; k++) { p.conv3.a_rowoff[k] = (k / 3) * kG2 + (k % 3) - 8; p.conv3.a_col[k] = 0; }
-    set_kmajor(p.fc1); p.fc1.nkb = 25;
+    // ---- forward: tap (dh,dw) of K-block kb = row offset inside the slab
+    p.conv1.n_tiles = (int)((P1 + 127) / 128); p.conv1.slab_row0 = 0;
+    for (int k = 0; k < 4; k++) { p.conv1.kb_rowoff[k] = (k >> 1) * kG1 + (k & 1); p.conv1.kb_half[k] = 0; }
+    p.conv2.n_tiles = (int)((P2 + 127) / 128); p.conv2.slab_row0 = 0;
+    for (int k = 0; k < 8; k++) { int tp = k >> 1; p.conv2.kb_rowoff[k] = (tp >> 1) * kG2 + (tp & 1); p.conv2.kb_half[k] = k & 1; }
+    p.conv3.n_tiles = p.conv2.n_tiles; p.conv3.slab_row0 = -8;                  // pad ring = the row before / after: offset -8
+    for (int k = 0; k < 9; k++) { p.conv3.kb_rowoff[k] = (k / 3) * kG2 + (k % 3); p.conv3.kb_half[k] = 0; }
+    set_kmajor(p.fc1); p.fc1.nkb = 25; p.fc1.kper = 25 / kFc1Splits; p.sf = kFc1Splits;
     for (int k = 0; k < 25; k++) { p.fc1.a_rowoff[k] = 0; p.fc1.a_col[k] = k * 64; }
     // ---- data gradients
     set_kmajor(p.fc1_d); p.fc1_d.nkb = H / 64;
     FB_REQUIRE(H / 64 <= kMaxKb, "tensor-core path: hidden must be <= 2048");
     for (int k = 0; k < H / 64; k++) { p.fc1_d.a_rowoff[k] = 0; p.fc1_d.a_col[k] = k * 64; }
-    set_kmajor(p.conv3_d); p.conv3_d.nkb = 9;
-    for (int k = 0; k < 9; k++) { p.conv3_d.a_rowoff[k] = (1 - k / 3) * kG2 + (1 - k % 3); p.conv3_d.a_col[k] = 0; }
-    set_kmajor(p.conv2_d); p.conv2_d.nkb = 4;
-    for (int k = 0; k < 4; k++) { p.conv2_d.a_rowoff[k] = -(k >> 1) * kG2 - (k & 1); p.conv2_d.a_col[k] = 0; }
-    // ---- weight gradients (contract over positions)
-    set_mnmajor(p.conv1_w, 32); p.conv1_w.p_total = (int)P1;
-    p.s1 = plan_splits(P1, 2, &p.conv1_w.klen);
-    for (int mt = 0; mt < 2; mt++) for (int i = 0; i < 2; i++) { int tp = 2 * mt + i; p.conv1_w.a2_rowoff[mt][i] = (tp >> 1) * kG1 + (tp & 1); p.conv1_w.a2_col[mt][i] = 0; }
-    set_mnmajor(p.conv2_w, 64); p.conv2_w.p_total = (int)P2;
-    p.s2 = plan_splits(P2, 4, &p.conv2_w.klen);
-    for (int mt = 0; mt < 4; mt++) for (int i = 0; i < 2; i++) { p.conv2_w.a2_rowoff[mt][i] = (mt >> 1) * kG2 + (mt & 1); p.conv2_w.a2_col[mt][i] = i * 64; }
-    set_mnmajor(p.conv3_w, 64); p.conv3_w.p_total = (int)P2;
-    p.s3 = plan_splits(P2, 5, &p.conv3_w.klen);
-    for (int mt = 0; mt < 5; mt++) for (int i = 0; i < 2; i++) { int tp = min(2 * mt + i, 8); p.conv3_w.a2_rowoff[mt][i] = (tp / 3) * kG2 + (tp % 3) - 8; p.conv3_w.a2_col[mt][i] = 0; }
+    p.conv3_d.n_tiles = p.conv2.n_tiles; p.conv3_d.slab_row0 = -8;              // dz3 row p + (1-kh)*7 + (1-kw)
+    for (int k = 0; k < 9; k++) { p.conv3_d.kb_rowoff[k] = (1 - k / 3) * kG2 + (1 - k % 3) + 8; p.conv3_d.kb_half[k] = 0; }
+    p.conv2_d.n_tiles = p.conv2.n_tiles; p.conv2_d.slab_row0 = -8;              // dz2 row p - dh*7 - dw
+    for (int k = 0; k < 4; k++) { p.conv2_d.kb_rowoff[k] = 8 - (k >> 1) * kG2 - (k & 1); p.conv2_d.kb_half[k] = 0; }
+    // ---- weight gradients (contract over positions; accumulator = two taps, or the two column halves of P2)
+    p.conv1_w.p_total = (int)P1; p.conv1_w.slab_row0 = 0;
+    p.s1 = plan_splits(P1, 148, &p.conv1_w.klen);
+    p.conv1_w.acc_rowoff[0] = 0; p.conv1_w.acc_lbo[0] = 128; p.conv1_w.acc_rowoff[1] = kG1; p.conv1_w.acc_lbo[1] = 128;
+    p.conv2_w.p_total = (int)P2; p.conv2_w.slab_row0 = 0;
+    p.s2 = plan_splits(P2, 48, &p.conv2_w.klen);
+    for (int a = 0; a < 4; a++) { p.conv2_w.acc_rowoff[a] = (a >> 1) * kG2 + (a & 1); p.conv2_w.acc_lbo[a] = 0; }
+    p.conv3_w.p_total = (int)P2; p.conv3_w.slab_row0 = -8;
+    p.s3 = plan_splits(P2, 48, &p.conv3_w.klen);
+    {   // taps 0..8 at rows {0,1,2,7,8,9,14,15,16}; pairs (0,1) (2,3) (4,5) (6,7) (8,-): second atom LBO bytes further
+        const int off[5] = {0, 2, 8, 14, 16};
+        const uint32_t lbo[5] = {128, 5 * 128, 128, 128, 128};
+        for (int a = 0; a < 5; a++) { p.conv3_w.acc_rowoff[a] = off[a]; p.conv3_w.acc_lbo[a] = lbo[a]; }
+    }
     set_mnmajor(p.fc1_w, 128); p.fc1_w.p_total = B; p.fc1_w.klen = (B + 63) / 64 * 64;
     for (int mt = 0; mt < 13; mt++) for (int i = 0; i < 2; i++) { p.fc1_w.a2_rowoff[mt][i] = 0; p.fc1_w.a2_col[mt][i] = mt * 128 + i * 64; }
     FB_REQUIRE((size_t)p.s1 <= t->cap1 && (size_t)p.s2 <= t->cap2 && (size_t)p.s3 <= t->cap3, "tensor-core path: split-K workspace too small");
@@ -641,18 +745,12 @@ int tc_state_create(fb_qnet *n) {
     FB_CUDA_OK(alloc_bf(&t->a2, B * kP2 * 64)); FB_CUDA_OK(alloc_bf(&t->a3, B * kFlat)); FB_CUDA_OK(alloc_bf(&t->dh1, B * H));
     FB_CUDA_OK(alloc_bf(&t->dz3, B * kP2 * 64)); FB_CUDA_OK(alloc_bf(&t->dz2, B * kP2 * 64)); FB_CUDA_OK(alloc_bf(&t->dp2, B * kP2 * 128));
     FB_CUDA_OK(alloc_bf(&t->dz1, B * kP1 * 32));
-    int klen;
-    t->cap1 = (size_t)plan_splits((long long)B * kP1, 2, &klen) + 1;
-    t->cap2 = (size_t)plan_splits((long long)B * kP2, 4, &klen) + 1;
-    t->cap3 = (size_t)plan_splits((long long)B * kP2, 5, &klen) + 1;
-    // smaller batches never need more splits than max_batch does, except through rounding: keep generous caps
-    if (t->cap1 < 80) t->cap1 = 80;
-    if (t->cap2 < 40) t->cap2 = 40;
-    if (t->cap3 < 32) t->cap3 = 32;
+    t->cap1 = 150; t->cap2 = 50; t->cap3 = 50;             // plan_splits never exceeds its target
     FB_CUDA_OK(alloc_f(&t->part1, t->cap1 * 256 * 32)); FB_CUDA_OK(alloc_f(&t->part2, t->cap2 * 512 * 64));
     FB_CUDA_OK(alloc_f(&t->part3, t->cap3 * 640 * 64)); FB_CUDA_OK(alloc_f(&t->partf, (size_t)1664 * H));
+    FB_CUDA_OK(alloc_f(&t->parth, (size_t)kFc1Splits * B * H));
     FB_CUDA_OK(alloc_f(&t->bp1, ((B * kP1 + kChunk1 - 1) / kChunk1) * 32)); FB_CUDA_OK(alloc_f(&t->bp2, ((B * kP2 + kChunk23 - 1) / kChunk23) * 64));
-    FB_CUDA_OK(alloc_f(&t->bp3, ((B * kP2 + kChunk23 - 1) / kChunk23) * 64)); FB_CUDA_OK(alloc_f(&t->bpf, ((B + kChunkF - 1) / kChunkF) * H));
+    FB_CUDA_OK(alloc_f(&t->bp3, ((B * kP2 + kChunk23 - 1) / kChunk23) * 64));
     for (int s = 0; s < 2; s++) {
         PackedWeights &w = t->pw[s];
         FB_CUDA_OK(alloc_bf(&w.w1p, kC1 * kK1)); FB_CUDA_OK(alloc_bf(&w.w2p, kC2 * kK2)); FB_CUDA_OK(alloc_bf(&w.w3p, kC3 * kK3));
@@ -667,6 +765,9 @@ int tc_state_create(fb_qnet *n) {
         if ((rc = make_map(&m.w3d, w.w3d, kC3, kK3, 64, 64))) return rc;
         if ((rc = make_map(&m.w2d, w.w2d, 128, 256, 64, 128))) return rc;
     }
+    int dev = 0;
+    FB_CUDA_OK(cudaGetDevice(&dev));
+    FB_CUDA_OK(cudaDeviceGetAttribute(&t->n_sms, cudaDevAttrMultiProcessorCount, dev));
     n->tc = t;
     return FB_OK;
 }
@@ -675,7 +776,7 @@ void tc_state_destroy(fb_qnet *n) {
     TcState *t = n->tc;
     if (!t) return;
     void *ps[] = {t->x2, t->z1, t->p2, t->a2, t->a3, t->dh1, t->dz3, t->dz2, t->dp2, t->dz1, t->part1, t->part2, t->part3, t->partf,
-                  t->bp1, t->bp2, t->bp3, t->bpf};
+                  t->parth, t->bp1, t->bp2, t->bp3};
     for (void *p : ps) cudaFree(p);
     for (int s = 0; s < 2; s++) {
         PackedWeights &w = t->pw[s];
@@ -703,13 +804,13 @@ int tc_forward(fb_qnet *n, int slot, const float *params_dev, FrameView fv, int 
     const TcWeightMaps &wm = t->wm[slot];
     const int P1 = B * kP1, P2 = B * kP2;
     pack_x2_kernel<<<(unsigned)(((size_t)P1 * 8 + 255) / 256), 256, 0, st>>>(fv, B, t->x2);
-    FB_CUDA_OK((launch_tc_gemm<32, 0>(p->x2_k, wm.w1p, p->conv1, dim3((P1 + 127) / 128, 1, 1), EpiConv1{t->z1, params_dev + L.b1, P1}, st)));
+    FB_CUDA_OK((launch_tc_conv<32, kSlab1, 1, 4, 6>(p->x2_s, wm.w1p, p->conv1, t->n_sms, EpiConv1{t->z1, params_dev + L.b1, P1}, st)));
     pool_pack_kernel<<<(unsigned)(((size_t)B * 36 * 16 + 255) / 256), 256, 0, st>>>(t->z1, B, t->p2);
-    FB_CUDA_OK((launch_tc_gemm<64, 0>(p->p2_k, wm.w2p, p->conv2, dim3((P2 + 127) / 128, 1, 1), EpiGrid7{t->a2, params_dev + L.b2, P2}, st)));
-    FB_CUDA_OK((launch_tc_gemm<64, 0>(p->a2_k, wm.w3p, p->conv3, dim3((P2 + 127) / 128, 1, 1), EpiConv3{t->a3, params_dev + L.b3, P2}, st)));
-    FB_CUDA_OK((launch_tc_gemm<128, 0>(p->a3_k, wm.wf1p, p->fc1, dim3((B + 127) / 128, L.hidden / 128, 1),
-                                       EpiFc1{n->h1, params_dev + L.bf1, B, L.hidden}, st)));
-    qnet_launch_head_forward(n->h1, params_dev, L, B, q_out, st);
+    FB_CUDA_OK((launch_tc_conv<64, kSlab2, 2, 8, 3>(p->p2_s, wm.w2p, p->conv2, t->n_sms, EpiGrid7{t->a2, params_dev + L.b2, P2}, st)));
+    FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4>(p->a2_s, wm.w3p, p->conv3, t->n_sms, EpiConv3{t->a3, params_dev + L.b3, P2}, st)));
+    FB_CUDA_OK((launch_tc_gemm<128, 0>(p->a3_k, wm.wf1p, p->fc1, dim3((B + 127) / 128, L.hidden / 128, p->sf),
+                                       EpiStoreF32{t->parth, B, L.hidden, (size_t)n->max_batch * L.hidden}, st)));
+    fc1_head_kernel<<<B, 128, 0, st>>>(t->parth, p->sf, (size_t)n->max_batch * L.hidden, params_dev, L, B, n->h1, q_out);
     FB_CUDA_OK(cudaGetLastError());
     return FB_OK;
 }
@@ -725,27 +826,86 @@ int tc_backward(fb_qnet *n, const float *params_dev, int B, float *grads_dev, cu
     const TcWeightMaps &wm = t->wm[0];
     const int H = L.hidden, P1 = B * kP1, P2 = B * kP2;
     // head: fp32 gradients of the head variables straight into grads, dh1 (masked by relu) as bf16
-    qnet_launch_head_backward(n->h1, n->dq, params_dev, L, B, grads_dev, nullptr, t->dh1, st);
+    head_backward_tc_kernel<<<H / 32 + 1, 256, 0, st>>>(n->h1, n->dq, params_dev, L, B, grads_dev, t->dh1);
     // fc1: dW = a3^T dh1, dz3 = (dh1 Wf1^T) * relu'(a3)
     FB_CUDA_OK((launch_tc_gemm<128, 1>(p->a3_m, p->dh1_b, p->fc1_w, dim3(13, H / 128, 1), EpiStoreF32{t->partf, kFlat, H, 0}, st)));
     FB_CUDA_OK((launch_tc_gemm<64, 0>(p->dh1_k, wm.wf1n, p->fc1_d, dim3((B + 127) / 128, kFlat / 64, 1), EpiFc1Dgrad{t->dz3, t->a3, B}, st)));
     // conv3
-    FB_CUDA_OK((launch_tc_gemm<64, 1>(p->a2_m, p->dz3_b, p->conv3_w, dim3(5, 1, p->s3), EpiStoreF32{t->part3, 640, 64, (size_t)640 * 64}, st)));
-    FB_CUDA_OK((launch_tc_gemm<64, 0>(p->dz3_k, wm.w3d, p->conv3_d, dim3((P2 + 127) / 128, 1, 1), EpiConv3Dgrad{t->dz2, t->a2, P2}, st)));
+    FB_CUDA_OK((launch_tc_wgrad<64, 5, kSlabW3, 1, 6>(p->a2_w, p->dz3_b, p->conv3_w, p->s3, EpiStoreF32{t->part3, 640, 64, (size_t)640 * 64}, st)));
+    FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4>(p->dz3_s, wm.w3d, p->conv3_d, t->n_sms, EpiConv3Dgrad{t->dz2, t->a2, P2}, st)));
     // conv2
-    FB_CUDA_OK((launch_tc_gemm<64, 1>(p->p2_m, p->dz2_b, p->conv2_w, dim3(4, 1, p->s2), EpiStoreF32{t->part2, 512, 64, (size_t)512 * 64}, st)));
-    FB_CUDA_OK((launch_tc_gemm<128, 0>(p->dz2_k, wm.w2d, p->conv2_d, dim3((P2 + 127) / 128, 1, 1), EpiStoreBf16{t->dp2, P2, 128}, st)));
+    FB_CUDA_OK((launch_tc_wgrad<64, 4, kSlabW2, 2, 4>(p->p2_w, p->dz2_b, p->conv2_w, p->s2, EpiStoreF32{t->part2, 512, 64, (size_t)512 * 64}, st)));
+    FB_CUDA_OK((launch_tc_conv<128, kSlab2, 1, 4, 4>(p->dz2_s, wm.w2d, p->conv2_d, t->n_sms, EpiStoreBf16{t->dp2, P2, 128}, st)));
     unpool_relu_kernel_tc<<<(unsigned)(((size_t)B * 400 + 255) / 256), 256, 0, st>>>(t->z1, t->dp2, B, t->dz1);
     // conv1 (no input gradient)
-    FB_CUDA_OK((launch_tc_gemm<32, 1>(p->x2_m, p->dz1_b, p->conv1_w, dim3(2, 1, p->s1), EpiStoreF32{t->part1, 256, 32, (size_t)256 * 32}, st)));
+    FB_CUDA_OK((launch_tc_wgrad<32, 2, kSlabW1, 1, 6>(p->x2_w, p->dz1_b, p->conv1_w, p->s1, EpiStoreF32{t->part1, 256, 32, (size_t)256 * 32}, st)));
     // bias gradients = column sums of the dZ tensors
-    const int c1 = (P1 + kChunk1 - 1) / kChunk1, c23 = (P2 + kChunk23 - 1) / kChunk23, cf = (B + kChunkF - 1) / kChunkF;
-    colsum_kernel<<<c1, 256, 0, st>>>(t->dz1, P1, 32, kChunk1, t->bp1);
-    colsum_kernel<<<c23, 256, 0, st>>>(t->dz2, P2, 64, kChunk23, t->bp2);
-    colsum_kernel<<<c23, 256, 0, st>>>(t->dz3, P2, 64, kChunk23, t->bp3);
-    colsum_kernel<<<cf, 256, 0, st>>>(t->dh1, B, H, kChunkF, t->bpf);
-    FinalizeArgs fa{t->part1, t->part2, t->part3, t->partf, p->s1, p->s2, p->s3, t->bp1, t->bp2, t->bp3, t->bpf, c1, c23, c23, cf};
+    const int c1 = (P1 + kChunk1 - 1) / kChunk1, c23 = (P2 + kChunk23 - 1) / kChunk23;
+    ColsumJobs cj{};
+    cj.njobs = 3;
+    cj.j[0] = ColsumJob{t->dz1, t->bp1, P1, 32, kChunk1, 0};
+    cj.j[1] = ColsumJob{t->dz2, t->bp2, P2, 64, kChunk23, c1};
+    cj.j[2] = ColsumJob{t->dz3, t->bp3, P2, 64, kChunk23, c1 + c23};
+    colsum_kernel<<<c1 + 2 * c23, 256, 0, st>>>(cj);
+    FinalizeArgs fa{t->part1, t->part2, t->part3, t->partf, p->s1, p->s2, p->s3, t->bp1, t->bp2, t->bp3, c1, c23, c23};
     finalize_grads_kernel<<<592, 256, 0, st>>>(fa, L, grads_dev);
+    FB_CUDA_OK(cudaGetLastError());
+    return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ slab probe
+// Experiment behind the "one slab, many taps" plan: A rows [0,256) are loaded ONCE (two 128-row boxes, 128B swizzle)
+// and the MMA reads rows [shift, shift+128) by starting its descriptor shift*128 bytes into the slab.  Valid only if
+// the hardware applies the swizzle to absolute shared-memory address bits (as TMA does when it writes).
+namespace {
+__global__ void __launch_bounds__(128) tc_slab_probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                                                            int shift, uint32_t base_offset, float *d) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full, bar_done;
+    __shared__ uint32_t tmem_slot;
+    const uint32_t smem = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { tc::mbar_init(tc::smem_u32(&bar_full), 1); tc::mbar_init(tc::smem_u32(&bar_done), 1); tc::fence_barrier_init(); }
+    if (warp == 0) tc::tmem_alloc(tc::smem_u32(&tmem_slot), 64);
+    tc::tc_fence_before(); __syncthreads(); tc::tc_fence_after();
+    const uint32_t tmem = tmem_slot, sa = smem, sb = smem + 32768;
+    if (threadIdx.x == 0) {
+        tc::mbar_expect_tx(tc::smem_u32(&bar_full), 32768 + 8192);
+        tc::tma_load_2d(sa, &mapA, 0, 0, tc::smem_u32(&bar_full));
+        tc::tma_load_2d(sa + 16384, &mapA, 0, 128, tc::smem_u32(&bar_full));
+        tc::tma_load_2d(sb, &mapB, 0, 0, tc::smem_u32(&bar_full));
+        tc::mbar_wait(tc::smem_u32(&bar_full), 0);
+        tc::tc_fence_after();
+        constexpr uint32_t idesc = tc::instr_desc_bf16(128, 64, 0, 0);
+        for (int k = 0; k < 4; k++) {
+            uint64_t ad = tc::smem_desc(sa + shift * 128 + k * 32, 16, 1024, tc::kSwizzle128) | ((uint64_t)(base_offset & 7u) << 49);
+            uint64_t bd = tc::smem_desc(sb + k * 32, 16, 1024, tc::kSwizzle128);
+            tc::umma_bf16(tmem, ad, bd, idesc, k != 0);
+        }
+        tc::umma_commit(tc::smem_u32(&bar_done));
+    }
+    tc::mbar_wait(tc::smem_u32(&bar_done), 0);
+    tc::tc_fence_after();
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        for (int i = 0; i < 16; i++) d[(warp * 32 + lane) * 64 + c0 + i] = v[i];
+    }
+    tc::tc_fence_before(); __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 64);
+}
+}  // namespace
+
+// D[128][64] = A[shift .. shift+128)[64] * Bt[64][64]^T with A [256][64] resident as one slab (see above)
+extern "C" int fb_debug_tc_slab(int shift, int base_offset, const void *a_dev, const void *b_dev, float *d_dev, void *stream) {
+    FB_REQUIRE(a_dev && b_dev && d_dev && shift >= 0 && shift <= 128, "fb_debug_tc_slab: bad argument");
+    int rc = ensure_encode();
+    if (rc) return rc;
+    CUtensorMap ma, mb;
+    if ((rc = make_map(&ma, (const bf16 *)a_dev, 256, 64, 64, 128))) return rc;
+    if ((rc = make_map(&mb, (const bf16 *)b_dev, 64, 64, 64, 64))) return rc;
+    FB_CUDA_OK(cudaFuncSetAttribute(tc_slab_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 8192 + 1024));
+    tc_slab_probe_kernel<<<1, 128, 32768 + 8192 + 1024, (cudaStream_t)stream>>>(ma, mb, shift, (uint32_t)base_offset, d_dev);
     FB_CUDA_OK(cudaGetLastError());
     return FB_OK;
 }

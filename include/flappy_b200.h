@@ -239,6 +239,9 @@ int fb_debug_host_mixed(const int32_t *state16);
  * mode 0: D[M][N] = A[M][K] Bt[N][K]^T;  mode 1: D[M][N] = A[K][M]^T B[K][N];  bn = N tile (32/64/128). */
 int fb_debug_tc_gemm(int mode, int bn, int M, int N, int K, const void *a_bf16_dev, const void *b_bf16_dev, float *d_dev,
                      const uint32_t *strides6_host, void *stream);
+/* device test hook: D[128][64] = A[shift..shift+128)[64] Bt[64][64]^T with A [256][64] loaded once as a swizzled slab and
+ * the MMA descriptor started shift rows into it (the property the one-slab-many-taps convolution relies on). */
+int fb_debug_tc_slab(int shift, int base_offset, const void *a_bf16_dev, const void *b_bf16_dev, float *d_dev, void *stream);
 
 #ifdef __cplusplus
 }

@@ -71,6 +71,21 @@ def test_raw_gemm_mn_major(mods, bn, M, N, K):
     assert err <= 1e-3 * np.sqrt(K) * 9, (err, bn, M, N, K)
 
 
+@pytest.mark.parametrize("shift", [0, 1, 7, 8, 21, 22, 100, 128])
+def test_slab_descriptor_shift(mods, shift):
+    """tcgen05 swizzles on absolute shared-memory address bits: a K-major SWIZZLE_128B descriptor started `shift` rows
+    into a TMA-written slab reads rows shift..shift+127 (base_offset 0) -- the property the slab convolutions rely on"""
+    _lib, _, _ = mods
+    g = torch.Generator(device="cuda").manual_seed(shift)
+    a = torch.randn((256, 64), device="cuda", generator=g).to(torch.bfloat16)
+    b = torch.randn((64, 64), device="cuda", generator=g).to(torch.bfloat16)
+    d = torch.full((128, 64), float("nan"), device="cuda")
+    _lib.check(_lib.lib().fb_debug_tc_slab(shift, 0, a.data_ptr(), b.data_ptr(), d.data_ptr(), torch.cuda.current_stream().cuda_stream), "slab")
+    torch.cuda.synchronize()
+    ref = a[shift:shift + 128].double() @ b.double().T
+    assert (d.double() - ref).abs().max().item() <= 1e-4
+
+
 def _env_frames(game, B, seed):
     gs = game.GameState(num_envs=B, seed=seed, history=5)
     gs.step_random(40 + seed % 7, 0.3, 99 + seed)
