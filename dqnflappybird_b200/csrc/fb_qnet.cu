@@ -295,6 +295,12 @@ __global__ void head_backward_h_kernel(const float *h1, const float *dq, const f
 void qnet_launch_head_forward(const float *h1, const float *params, const QnetLayout &L, int B, float *q, cudaStream_t st) {
     head_forward_kernel<<<(B + 3) / 4, 128, 0, st>>>(h1, params, L, B, q);
 }
+void qnet_launch_td_loss(const float *q_s, const float *q_next, const float *q_next_online, const uint8_t *actions,
+                         const float *rewards, const uint8_t *terminals, const float *isw, int B, int global_batch, int variant,
+                         double gamma, int loss_sum, float *dq, float *loss_out, float *abs_err, float *q_target, cudaStream_t st) {
+    td_loss_kernel<<<1, 256, 0, st>>>(q_s, q_next, q_next_online, actions, rewards, terminals, isw, B, global_batch, variant, gamma,
+                                       loss_sum, dq, loss_out, abs_err, q_target);
+}
 void qnet_launch_head_backward(const float *h1, const float *dq, const float *params, const QnetLayout &L, int B, float *grads,
                                float *dh1_f32, __nv_bfloat16 *dh1_bf16, cudaStream_t st) {
     head_backward_w_kernel<<<(L.hidden + 1 + 127) / 128, 128, 0, st>>>(h1, dq, L, B, grads);
@@ -425,18 +431,6 @@ extern "C" int fb_qnet_invalidate(fb_qnet *n) {
     return FB_OK;
 }
 
-static int tc_slot_for(fb_qnet *n, const float *params_dev, int want_slot, cudaStream_t st, int *slot_out) {
-    int slot = want_slot;
-    if (slot < 0) slot = (n->packed_src[1] == params_dev && n->packed_src[0] != params_dev) ? 1 : 0;
-    if (n->packed_src[slot] != params_dev) {
-        int rc = tc_pack_weights(n, params_dev, slot, st);
-        if (rc) return rc;
-        n->packed_src[slot] = params_dev;
-    }
-    *slot_out = slot;
-    return FB_OK;
-}
-
 extern "C" int fb_qnet_param_count(const fb_qnet *n) { return n ? n->L.total : 0; }
 
 extern "C" int fb_qnet_layout(const fb_qnet *n, int32_t *o) {
@@ -462,7 +456,7 @@ extern "C" int fb_qnet_forward(fb_qnet *n, const float *params_dev, const uint8_
     for (int b0 = 0; b0 < batch; b0 += n->max_batch) {
         int B = min(n->max_batch, batch - b0);
         FrameView fv = make_view(frames_dev + (size_t)b0 * sample_stride, sample_stride, chan_off);
-        int rc = n->precision == FB_PRECISION_BF16 ? tc_forward(n, slot, params_dev, fv, B, q_out_dev + (size_t)b0 * 2, st)
+        int rc = n->precision == FB_PRECISION_BF16 ? tc_forward(n, slot, 0, params_dev, fv, B, q_out_dev + (size_t)b0 * 2, st)
                                                    : forward_chunk(n, params_dev, fv, B, q_out_dev + (size_t)b0 * 2, st);
         if (rc) return rc;
     }
@@ -498,18 +492,10 @@ extern "C" int fb_qnet_loss_backward(fb_qnet *n, int variant, const float *param
     FrameView fs = make_view(frames_dev, sample_stride, chan_off_s), fn = make_view(frames_dev, sample_stride, chan_off_next);
     int rc;
     if (n->precision == FB_PRECISION_BF16) {
-        // same order of work on the tcgen05 path; the bf16 operand copies are remade only when stale
-        int s_on = 0, s_tg = 0;
-        const float *next_params = variant == 0 ? params_dev : target_params_dev;
-        rc = tc_slot_for(n, params_dev, 0, st, &s_on); if (rc) return rc;
-        if (variant != 0) { rc = tc_slot_for(n, target_params_dev, 1, st, &s_tg); if (rc) return rc; }
-        if (variant == 2) { rc = tc_forward(n, s_on, params_dev, fn, B, n->q_next_online, st); if (rc) return rc; }
-        rc = tc_forward(n, variant == 0 ? s_on : s_tg, next_params, fn, B, n->q_next, st); if (rc) return rc;
-        rc = tc_forward(n, s_on, params_dev, fs, B, n->q, st); if (rc) return rc;
-        td_loss_kernel<<<1, 256, 0, st>>>(n->q, n->q_next, n->q_next_online, actions_dev, rewards_dev, terminals_dev, is_weights_dev,
-                                           B, global_batch, variant, gamma, loss_sum, n->dq, loss_out_dev ? loss_out_dev : n->loss_dev,
-                                           abs_err_out_dev, q_target_out_dev);
-        return tc_backward(n, params_dev, B, grads_dev, st);
+        TcTrainArgs ta{variant, params_dev, target_params_dev, fs, fn, actions_dev, rewards_dev, terminals_dev, is_weights_dev, B,
+                       global_batch, gamma, loss_sum, grads_dev, loss_out_dev ? loss_out_dev : n->loss_dev, abs_err_out_dev,
+                       q_target_out_dev};
+        return tc_loss_backward(n, ta, st);
     }
     // Q(s') with the net the variant names (and the online net too for Double), then Q(s) last so that its
     // activations are the ones left in the workspace for the backward pass.

@@ -69,8 +69,17 @@ void qnet_launch_head_backward(const float *h1, const float *dq, const float *pa
                                float *dh1_f32, __nv_bfloat16 *dh1_bf16, cudaStream_t st);
 
 // tcgen05 path entry points (fb_qnet_tc.cu); all return FB_OK or an error code with fb_set_error set
+struct TcTrainArgs {
+    int variant;
+    const float *params, *target;
+    FrameView fs, fn;                       // s and s' views of the minibatch frames
+    const uint8_t *actions; const float *rewards; const uint8_t *terminals; const float *isw;
+    int B, global_batch; double gamma; int loss_sum;
+    float *grads, *loss_out, *abs_err, *q_target;
+};
 int tc_state_create(fb_qnet *n);
 void tc_state_destroy(fb_qnet *n);
 int tc_pack_weights(fb_qnet *n, const float *params_dev, int slot /* 0 online, 1 target */, cudaStream_t st);
-int tc_forward(fb_qnet *n, int slot, const float *params_dev, FrameView fv, int B, float *q_out, cudaStream_t st);
-int tc_backward(fb_qnet *n, const float *params_dev, int B, float *grads_dev, cudaStream_t st);
+int tc_slot_for(fb_qnet *n, const float *params_dev, int want_slot, cudaStream_t st, int *slot_out);
+int tc_forward(fb_qnet *n, int slot, int ws, const float *params_dev, FrameView fv, int B, float *q_out, cudaStream_t st);
+int tc_loss_backward(fb_qnet *n, const TcTrainArgs &a, cudaStream_t st);

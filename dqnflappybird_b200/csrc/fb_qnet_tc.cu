@@ -21,6 +21,8 @@
 // head / TD loss / Adam in fp32 (shared with fb_qnet.cu).  Tolerances vs the float64 oracle: tests/test_qnet_tc_gpu.py.
 #include <cudaTypedefs.h>
 
+#include <string.h>
+
 #include <map>
 #include <new>
 #include <vector>
@@ -464,8 +466,9 @@ __global__ void __launch_bounds__(256) colsum_kernel(ColsumJobs jobs) {
 // Head backward in one pass over h1 (BrainDQN.py:151-154 / dueling BrainDuelingDQN_CC.py:68-77): gradients of the head
 // weights, dh1 = dQ W^T masked by relu (bf16, the operand of the fc1 gradient GEMMs) and the fc1 bias gradient
 // sum_b dh1.  Block = 32 hidden units x 8 row lanes; block gridDim.x-1 does the head bias.
-__global__ void __launch_bounds__(256) head_backward_tc_kernel(const float *h1, const float *dq, const float *params, QnetLayout L, int B,
-                                                               float *grads, bf16 *dh1) {
+__global__ void __launch_bounds__(256) head_backward_tc_kernel(const float *__restrict__ h1, const float *__restrict__ dq,
+                                                               const float *__restrict__ params, QnetLayout L, int B,
+                                                               float *__restrict__ grads, bf16 *__restrict__ dh1) {
     __shared__ float red[8][32][4];
     const int H = L.hidden;
     if ((int)blockIdx.x == H / 32) {                 // head bias gradients: sum_b dq (dueling: (d0+d1) for V, d - mean for A)
@@ -488,6 +491,7 @@ __global__ void __launch_bounds__(256) head_backward_tc_kernel(const float *h1, 
     if (!L.dueling) { w0 = params[L.wf2 + j * 2]; w1 = params[L.wf2 + j * 2 + 1]; }
     else { w0 = params[L.wa + j * 2]; w1 = params[L.wa + j * 2 + 1]; wv = params[L.wv + j]; }
     float g0 = 0.f, g1 = 0.f, gv = 0.f, gb = 0.f;
+#pragma unroll 8
     for (int b = rl; b < B; b += 8) {
         float x = h1[(size_t)b * H + j];
         float d0 = dq[b * 2], d1 = dq[b * 2 + 1], g;
@@ -517,13 +521,15 @@ __global__ void __launch_bounds__(256) head_backward_tc_kernel(const float *h1, 
 // fc1 split-K finish fused with the Q head (BrainDQN.py:146-154; dueling BrainDuelingDQN_CC.py:68-77): one CTA per
 // sample sums the K-split partials in order, adds the bias, applies ReLU, keeps h1 (fp32) for backward and reduces
 // the two (three) head dot products.
-__global__ void __launch_bounds__(128) fc1_head_kernel(const float *part, int splits, size_t split_stride, const float *params, QnetLayout L,
-                                                      int B, float *h1, float *q) {
+__global__ void __launch_bounds__(128) fc1_head_kernel(const float *__restrict__ part, int splits, size_t split_stride,
+                                                      const float *__restrict__ params, QnetLayout L, int B, float *__restrict__ h1,
+                                                      float *__restrict__ q) {
     __shared__ float red[4][3];
     const int b = blockIdx.x, H = L.hidden;
     float s0 = 0.f, s1 = 0.f, sv = 0.f;
     for (int j = threadIdx.x; j < H; j += 128) {
         float x = params[L.bf1 + j];
+#pragma unroll 5
         for (int z = 0; z < splits; z++) x += part[(size_t)z * split_stride + (size_t)b * H + j];
         x = fmaxf(x, 0.f);
         h1[(size_t)b * H + j] = x;
@@ -548,18 +554,19 @@ __global__ void __launch_bounds__(128) fc1_head_kernel(const float *part, int sp
 
 // split-K partials + bias partials -> the flat gradient vector in TF variable order (HWIO)
 struct FinalizeArgs {
-    const float *part1, *part2, *part3, *partf;     // [splits][rows][N]
+    const float *part1, *part2, *part3;             // [splits][rows][N]
     int s1, s2, s3;                                  // number of splits (fc1 has one)
     const float *bp1, *bp2, *bp3;                   // bias partials [chunks][N] (the fc1 bias comes from the head kernel)
     int c1, c2, c3;
 };
-__global__ void finalize_grads_kernel(FinalizeArgs a, QnetLayout L, float *grads) {
-    const int end = L.bf1;
+__global__ void finalize_grads_kernel(const FinalizeArgs a, QnetLayout L, float *__restrict__ grads) {
+    const int end = L.wf1;                   // the fc1 weight gradient is written in place by its GEMM, the fc1 bias by the head kernel
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x) {
         float s = 0.f;
         if (i < L.b1) {                     // W1 [kh][kw][c][n]
             int e = i - L.w1, n = e & 31, c = (e >> 5) & 3, kw = (e >> 7) & 7, kh = e >> 10;
             int row = ((kh >> 2) * 2 + (kw >> 2)) * 64 + (kh & 3) * 16 + (kw & 3) * 4 + c;
+#pragma unroll 8
             for (int z = 0; z < a.s1; z++) s += a.part1[((size_t)z * 256 + row) * 32 + n];
         } else if (i < L.w2) {
             int n = i - L.b1;
@@ -567,18 +574,18 @@ __global__ void finalize_grads_kernel(FinalizeArgs a, QnetLayout L, float *grads
         } else if (i < L.b2) {              // W2 [kh][kw][c][n]
             int e = i - L.w2, n = e & 63, c = (e >> 6) & 31, kw = (e >> 11) & 3, kh = e >> 13;
             int row = ((kh >> 1) * 2 + (kw >> 1)) * 128 + (kh & 1) * 64 + (kw & 1) * 32 + c;
+#pragma unroll 8
             for (int z = 0; z < a.s2; z++) s += a.part2[((size_t)z * 512 + row) * 64 + n];
         } else if (i < L.w3) {
             int n = i - L.b2;
             for (int k = 0; k < a.c2; k++) s += a.bp2[k * 64 + n];
         } else if (i < L.b3) {              // W3 [k][n], k natural
             int e = i - L.w3;
+#pragma unroll 8
             for (int z = 0; z < a.s3; z++) s += a.part3[(size_t)z * 640 * 64 + e];
-        } else if (i < L.wf1) {
+        } else {
             int n = i - L.b3;
             for (int k = 0; k < a.c3; k++) s += a.bp3[k * 64 + n];
-        } else {
-            s = a.partf[i - L.wf1];
         }
         grads[i] = s;
     }
@@ -622,28 +629,41 @@ void set_mnmajor(GemmParams &g, int bn) {
 
 // ------------------------------------------------------------------------------------------------ state
 struct TcWeightMaps { CUtensorMap w1p, w2p, w3p, wf1p, wf1n, w3d, w2d; };
+struct FwdWs {                  // forward tensors of one network evaluation (bf16 unless noted), sized for max_batch
+    bf16 *x2, *z1, *p2, *a2, *a3;
+    float *parth, *h1;          // fc1 K-split partials, h1 (fp32, kept for the head backward)
+};
 struct TcPlan {                 // everything that depends on the batch size
     int B;
-    CUtensorMap a3_k, dh1_k;                                         // fc1 K-major A operands, box 64 x 128
-    CUtensorMap a3_m, dh1_b;                                         // fc1 weight gradient (MN-major), boxes 64 x 64
-    CUtensorMap x2_s, p2_s, a2_s, dz3_s, dz2_s;                      // convolution slabs (forward / data gradient)
-    CUtensorMap x2_w, p2_w, a2_w;                                    // weight-gradient slabs (A)
-    CUtensorMap dz1_b, dz2_b, dz3_b;                                 // weight-gradient B operands, 64 rows
+    CUtensorMap x2_s[2], p2_s[2], a2_s[2], a3_k[2];                  // forward operands of workspace 0 / 1
+    CUtensorMap dh1_k, dz3_s, dz2_s;                                 // data-gradient operands
+    CUtensorMap x2_w, p2_w, a2_w, a3_m;                              // weight-gradient A operands (workspace 0)
+    CUtensorMap dz1_b, dz2_b, dz3_b, dh1_b;                          // weight-gradient B operands, 64 rows
     GemmParams fc1, fc1_d, fc1_w;
     ConvParams conv1, conv2, conv3, conv3_d, conv2_d;
     WgradParams conv1_w, conv2_w, conv3_w;
     int s1, s2, s3, sf;                                              // split-K counts (conv weight gradients, fc1 forward)
 };
+struct GraphKey {               // a captured training step is replayed only for byte-identical arguments
+    TcTrainArgs a;
+    int pack_online, pack_target;
+};
+struct GraphEntry { GraphKey key; int seen; cudaGraphExec_t exec; };
 struct TcState {
-    // activations / gradients (bf16 unless noted), sized for max_batch
-    bf16 *x2, *z1, *p2, *a2, *a3, *dh1, *dz3, *dz2, *dp2, *dz1;
-    float *part1, *part2, *part3, *partf, *parth;
+    FwdWs ws[2];                // 0: the online net on s (kept for backward); 1: the other forwards, concurrently
+    bf16 *dh1, *dz3, *dz2, *dp2, *dz1;
+    float *part1, *part2, *part3;
     size_t cap1, cap2, cap3;
     float *bp1, *bp2, *bp3;
     PackedWeights pw[2];
     TcWeightMaps wm[2];
     std::map<int, TcPlan> plans;
     int n_sms;
+    cudaStream_t aux;           // second stream: target forward / weight gradients run beside the critical path
+    cudaStream_t cap;           // capture origin (the caller's stream may be the legacy default stream, which cannot capture)
+    cudaEvent_t ev[8];
+    std::vector<GraphEntry> graphs;
+    int use_graph;
 };
 
 namespace {
@@ -668,19 +688,25 @@ int make_plan(fb_qnet *n, int B, TcPlan **out) {
     TcState *t = n->tc;
     auto it = t->plans.find(B);
     if (it != t->plans.end()) { *out = &it->second; return FB_OK; }
-    if (t->plans.size() > 16) t->plans.clear();
+    if (t->plans.size() > 16) {                  // plans are referenced by captured graphs: drop both together
+        for (auto &g : t->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+        t->graphs.clear();
+        t->plans.clear();
+    }
     TcPlan p{};
     p.B = B;
     const int H = n->L.hidden;
     const long long P1 = (long long)B * kP1, P2 = (long long)B * kP2;
     int rc;
 #define MAP(dst, base, rows, cols, bc, br) if ((rc = make_map(&p.dst, base, rows, cols, bc, br))) return rc
-    MAP(a3_k, t->a3, B, kFlat, 64, 128); MAP(dh1_k, t->dh1, B, H, 64, 128);
-    MAP(a3_m, t->a3, B, kFlat, 64, 64); MAP(dh1_b, t->dh1, B, H, 64, 64);
-    MAP(x2_s, t->x2, P1, 64, 64, kSlab1); MAP(p2_s, t->p2, P2, 128, 64, kSlab2); MAP(a2_s, t->a2, P2, 64, 64, kSlab3);
-    MAP(dz3_s, t->dz3, P2, 64, 64, kSlab3); MAP(dz2_s, t->dz2, P2, 64, 64, kSlab2);
-    MAP(x2_w, t->x2, P1, 64, 64, kSlabW1); MAP(p2_w, t->p2, P2, 128, 64, kSlabW2); MAP(a2_w, t->a2, P2, 64, 64, kSlabW3);
-    MAP(dz1_b, t->dz1, P1, 32, 32, 64); MAP(dz2_b, t->dz2, P2, 64, 64, 64); MAP(dz3_b, t->dz3, P2, 64, 64, 64);
+    for (int w = 0; w < 2; w++) {
+        MAP(x2_s[w], t->ws[w].x2, P1, 64, 64, kSlab1); MAP(p2_s[w], t->ws[w].p2, P2, 128, 64, kSlab2);
+        MAP(a2_s[w], t->ws[w].a2, P2, 64, 64, kSlab3); MAP(a3_k[w], t->ws[w].a3, B, kFlat, 64, 128);
+    }
+    MAP(dh1_k, t->dh1, B, H, 64, 128); MAP(dz3_s, t->dz3, P2, 64, 64, kSlab3); MAP(dz2_s, t->dz2, P2, 64, 64, kSlab2);
+    MAP(x2_w, t->ws[0].x2, P1, 64, 64, kSlabW1); MAP(p2_w, t->ws[0].p2, P2, 128, 64, kSlabW2); MAP(a2_w, t->ws[0].a2, P2, 64, 64, kSlabW3);
+    MAP(a3_m, t->ws[0].a3, B, kFlat, 64, 64);
+    MAP(dz1_b, t->dz1, P1, 32, 32, 64); MAP(dz2_b, t->dz2, P2, 64, 64, 64); MAP(dz3_b, t->dz3, P2, 64, 64, 64); MAP(dh1_b, t->dh1, B, H, 64, 64);
 #undef MAP
     // ---- forward: tap (dh,dw) of K-block kb = row offset inside the slab
     p.conv1.n_tiles = (int)((P1 + 127) / 128); p.conv1.slab_row0 = 0;
@@ -701,13 +727,13 @@ int make_plan(fb_qnet *n, int B, TcPlan **out) {
     for (int k = 0; k < 4; k++) { p.conv2_d.kb_rowoff[k] = 8 - (k >> 1) * kG2 - (k & 1); p.conv2_d.kb_half[k] = 0; }
     // ---- weight gradients (contract over positions; accumulator = two taps, or the two column halves of P2)
     p.conv1_w.p_total = (int)P1; p.conv1_w.slab_row0 = 0;
-    p.s1 = plan_splits(P1, 148, &p.conv1_w.klen);
+    p.s1 = plan_splits(P1, 74, &p.conv1_w.klen);
     p.conv1_w.acc_rowoff[0] = 0; p.conv1_w.acc_lbo[0] = 128; p.conv1_w.acc_rowoff[1] = kG1; p.conv1_w.acc_lbo[1] = 128;
     p.conv2_w.p_total = (int)P2; p.conv2_w.slab_row0 = 0;
-    p.s2 = plan_splits(P2, 48, &p.conv2_w.klen);
+    p.s2 = plan_splits(P2, 28, &p.conv2_w.klen);
     for (int a = 0; a < 4; a++) { p.conv2_w.acc_rowoff[a] = (a >> 1) * kG2 + (a & 1); p.conv2_w.acc_lbo[a] = 0; }
     p.conv3_w.p_total = (int)P2; p.conv3_w.slab_row0 = -8;
-    p.s3 = plan_splits(P2, 48, &p.conv3_w.klen);
+    p.s3 = plan_splits(P2, 28, &p.conv3_w.klen);
     {   // taps 0..8 at rows {0,1,2,7,8,9,14,15,16}; pairs (0,1) (2,3) (4,5) (6,7) (8,-): second atom LBO bytes further
         const int off[5] = {0, 2, 8, 14, 16};
         const uint32_t lbo[5] = {128, 5 * 128, 128, 128, 128};
@@ -741,14 +767,18 @@ int tc_state_create(fb_qnet *n) {
         if (e == cudaSuccess) e = cudaMemset(*p, 0, elems * sizeof(float));
         return e;
     };
-    FB_CUDA_OK(alloc_bf(&t->x2, B * kP1 * 64)); FB_CUDA_OK(alloc_bf(&t->z1, B * kP1 * 32)); FB_CUDA_OK(alloc_bf(&t->p2, B * kP2 * 128));
-    FB_CUDA_OK(alloc_bf(&t->a2, B * kP2 * 64)); FB_CUDA_OK(alloc_bf(&t->a3, B * kFlat)); FB_CUDA_OK(alloc_bf(&t->dh1, B * H));
+    for (int w = 0; w < 2; w++) {
+        FwdWs &f = t->ws[w];
+        FB_CUDA_OK(alloc_bf(&f.x2, B * kP1 * 64)); FB_CUDA_OK(alloc_bf(&f.z1, B * kP1 * 32)); FB_CUDA_OK(alloc_bf(&f.p2, B * kP2 * 128));
+        FB_CUDA_OK(alloc_bf(&f.a2, B * kP2 * 64)); FB_CUDA_OK(alloc_bf(&f.a3, B * kFlat));
+        FB_CUDA_OK(alloc_f(&f.parth, (size_t)kFc1Splits * B * H)); FB_CUDA_OK(alloc_f(&f.h1, B * H));
+    }
+    FB_CUDA_OK(alloc_bf(&t->dh1, B * H));
     FB_CUDA_OK(alloc_bf(&t->dz3, B * kP2 * 64)); FB_CUDA_OK(alloc_bf(&t->dz2, B * kP2 * 64)); FB_CUDA_OK(alloc_bf(&t->dp2, B * kP2 * 128));
     FB_CUDA_OK(alloc_bf(&t->dz1, B * kP1 * 32));
-    t->cap1 = 150; t->cap2 = 50; t->cap3 = 50;             // plan_splits never exceeds its target
+    t->cap1 = 76; t->cap2 = 30; t->cap3 = 30;              // plan_splits never exceeds its target
     FB_CUDA_OK(alloc_f(&t->part1, t->cap1 * 256 * 32)); FB_CUDA_OK(alloc_f(&t->part2, t->cap2 * 512 * 64));
-    FB_CUDA_OK(alloc_f(&t->part3, t->cap3 * 640 * 64)); FB_CUDA_OK(alloc_f(&t->partf, (size_t)1664 * H));
-    FB_CUDA_OK(alloc_f(&t->parth, (size_t)kFc1Splits * B * H));
+    FB_CUDA_OK(alloc_f(&t->part3, t->cap3 * 640 * 64));
     FB_CUDA_OK(alloc_f(&t->bp1, ((B * kP1 + kChunk1 - 1) / kChunk1) * 32)); FB_CUDA_OK(alloc_f(&t->bp2, ((B * kP2 + kChunk23 - 1) / kChunk23) * 64));
     FB_CUDA_OK(alloc_f(&t->bp3, ((B * kP2 + kChunk23 - 1) / kChunk23) * 64));
     for (int s = 0; s < 2; s++) {
@@ -768,6 +798,10 @@ int tc_state_create(fb_qnet *n) {
     int dev = 0;
     FB_CUDA_OK(cudaGetDevice(&dev));
     FB_CUDA_OK(cudaDeviceGetAttribute(&t->n_sms, cudaDevAttrMultiProcessorCount, dev));
+    FB_CUDA_OK(cudaStreamCreateWithFlags(&t->aux, cudaStreamNonBlocking));
+    FB_CUDA_OK(cudaStreamCreateWithFlags(&t->cap, cudaStreamNonBlocking));
+    for (auto &e : t->ev) FB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    t->use_graph = 1;
     n->tc = t;
     return FB_OK;
 }
@@ -775,14 +809,22 @@ int tc_state_create(fb_qnet *n) {
 void tc_state_destroy(fb_qnet *n) {
     TcState *t = n->tc;
     if (!t) return;
-    void *ps[] = {t->x2, t->z1, t->p2, t->a2, t->a3, t->dh1, t->dz3, t->dz2, t->dp2, t->dz1, t->part1, t->part2, t->part3, t->partf,
-                  t->parth, t->bp1, t->bp2, t->bp3};
+    for (auto &g : t->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (int w = 0; w < 2; w++) {
+        FwdWs &f = t->ws[w];
+        void *fs[] = {f.x2, f.z1, f.p2, f.a2, f.a3, f.parth, f.h1};
+        for (void *p : fs) cudaFree(p);
+    }
+    void *ps[] = {t->dh1, t->dz3, t->dz2, t->dp2, t->dz1, t->part1, t->part2, t->part3, t->bp1, t->bp2, t->bp3};
     for (void *p : ps) cudaFree(p);
     for (int s = 0; s < 2; s++) {
         PackedWeights &w = t->pw[s];
         void *ws[] = {w.w1p, w.w2p, w.w3p, w.wf1p, w.wf1n, w.w3d, w.w2d};
         for (void *p : ws) cudaFree(p);
     }
+    for (auto &e : t->ev) if (e) cudaEventDestroy(e);
+    if (t->aux) cudaStreamDestroy(t->aux);
+    if (t->cap) cudaStreamDestroy(t->cap);
     delete t;
     n->tc = nullptr;
 }
@@ -794,62 +836,159 @@ int tc_pack_weights(fb_qnet *n, const float *params_dev, int slot, cudaStream_t 
     return FB_OK;
 }
 
-int tc_forward(fb_qnet *n, int slot, const float *params_dev, FrameView fv, int B, float *q_out, cudaStream_t st) {
+// which bf16 operand copy serves params_dev (want_slot < 0: whichever already holds it, else slot 0), refreshed if stale
+int tc_slot_for(fb_qnet *n, const float *params_dev, int want_slot, cudaStream_t st, int *slot_out) {
+    int slot = want_slot;
+    if (slot < 0) slot = (n->packed_src[1] == params_dev && n->packed_src[0] != params_dev) ? 1 : 0;
+    if (n->packed_src[slot] != params_dev) {
+        int rc = tc_pack_weights(n, params_dev, slot, st);
+        if (rc) return rc;
+        n->packed_src[slot] = params_dev;
+    }
+    *slot_out = slot;
+    return FB_OK;
+}
+
+int tc_forward(fb_qnet *n, int slot, int w, const float *params_dev, FrameView fv, int B, float *q_out, cudaStream_t st) {
     TcState *t = n->tc;
-    FB_REQUIRE(t != nullptr && B > 0 && B <= n->max_batch, "tc_forward: bad argument");
+    FB_REQUIRE(t != nullptr && B > 0 && B <= n->max_batch && (w == 0 || w == 1), "tc_forward: bad argument");
     TcPlan *p;
     int rc = make_plan(n, B, &p);
     if (rc) return rc;
     const QnetLayout &L = n->L;
     const TcWeightMaps &wm = t->wm[slot];
+    const FwdWs &f = t->ws[w];
     const int P1 = B * kP1, P2 = B * kP2;
-    pack_x2_kernel<<<(unsigned)(((size_t)P1 * 8 + 255) / 256), 256, 0, st>>>(fv, B, t->x2);
-    FB_CUDA_OK((launch_tc_conv<32, kSlab1, 1, 4, 6>(p->x2_s, wm.w1p, p->conv1, t->n_sms, EpiConv1{t->z1, params_dev + L.b1, P1}, st)));
-    pool_pack_kernel<<<(unsigned)(((size_t)B * 36 * 16 + 255) / 256), 256, 0, st>>>(t->z1, B, t->p2);
-    FB_CUDA_OK((launch_tc_conv<64, kSlab2, 2, 8, 3>(p->p2_s, wm.w2p, p->conv2, t->n_sms, EpiGrid7{t->a2, params_dev + L.b2, P2}, st)));
-    FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4>(p->a2_s, wm.w3p, p->conv3, t->n_sms, EpiConv3{t->a3, params_dev + L.b3, P2}, st)));
-    FB_CUDA_OK((launch_tc_gemm<128, 0>(p->a3_k, wm.wf1p, p->fc1, dim3((B + 127) / 128, L.hidden / 128, p->sf),
-                                       EpiStoreF32{t->parth, B, L.hidden, (size_t)n->max_batch * L.hidden}, st)));
-    fc1_head_kernel<<<B, 128, 0, st>>>(t->parth, p->sf, (size_t)n->max_batch * L.hidden, params_dev, L, B, n->h1, q_out);
+    pack_x2_kernel<<<(unsigned)(((size_t)P1 * 8 + 255) / 256), 256, 0, st>>>(fv, B, f.x2);
+    FB_CUDA_OK((launch_tc_conv<32, kSlab1, 1, 4, 6>(p->x2_s[w], wm.w1p, p->conv1, t->n_sms, EpiConv1{f.z1, params_dev + L.b1, P1}, st)));
+    pool_pack_kernel<<<(unsigned)(((size_t)B * 36 * 16 + 255) / 256), 256, 0, st>>>(f.z1, B, f.p2);
+    FB_CUDA_OK((launch_tc_conv<64, kSlab2, 2, 8, 3>(p->p2_s[w], wm.w2p, p->conv2, t->n_sms, EpiGrid7{f.a2, params_dev + L.b2, P2}, st)));
+    FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4>(p->a2_s[w], wm.w3p, p->conv3, t->n_sms, EpiConv3{f.a3, params_dev + L.b3, P2}, st)));
+    FB_CUDA_OK((launch_tc_gemm<128, 0>(p->a3_k[w], wm.wf1p, p->fc1, dim3((B + 127) / 128, L.hidden / 128, p->sf),
+                                       EpiStoreF32{f.parth, B, L.hidden, (size_t)n->max_batch * L.hidden}, st)));
+    fc1_head_kernel<<<B, 128, 0, st>>>(f.parth, p->sf, (size_t)n->max_batch * L.hidden, params_dev, L, B, f.h1, q_out);
     FB_CUDA_OK(cudaGetLastError());
     return FB_OK;
 }
 
-// backward of the LAST tc_forward (online net on s); n->dq holds dLoss/dQ.  Fills grads_dev completely.
-int tc_backward(fb_qnet *n, const float *params_dev, int B, float *grads_dev, cudaStream_t st) {
+namespace {
+
+// One training step's device work (BrainDQN.py:195-223 and the variants).  Two streams: the critical path
+// (online forward on s -> TD loss -> data gradients -> conv1 weight gradient -> finalize) stays on `st`; the Q(s')
+// forward(s) and the other weight gradients run beside it on the auxiliary stream.  The same code is what a CUDA
+// graph captures.
+int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pack_target, cudaStream_t st) {
     TcState *t = n->tc;
-    FB_REQUIRE(t != nullptr && B > 0 && B <= n->max_batch, "tc_backward: bad argument");
     TcPlan *p;
-    int rc = make_plan(n, B, &p);
+    int rc = make_plan(n, a.B, &p);
     if (rc) return rc;
     const QnetLayout &L = n->L;
     const TcWeightMaps &wm = t->wm[0];
-    const int H = L.hidden, P1 = B * kP1, P2 = B * kP2;
-    // head: fp32 gradients of the head variables straight into grads, dh1 (masked by relu) as bf16
-    head_backward_tc_kernel<<<H / 32 + 1, 256, 0, st>>>(n->h1, n->dq, params_dev, L, B, grads_dev, t->dh1);
-    // fc1: dW = a3^T dh1, dz3 = (dh1 Wf1^T) * relu'(a3)
-    FB_CUDA_OK((launch_tc_gemm<128, 1>(p->a3_m, p->dh1_b, p->fc1_w, dim3(13, H / 128, 1), EpiStoreF32{t->partf, kFlat, H, 0}, st)));
-    FB_CUDA_OK((launch_tc_gemm<64, 0>(p->dh1_k, wm.wf1n, p->fc1_d, dim3((B + 127) / 128, kFlat / 64, 1), EpiFc1Dgrad{t->dz3, t->a3, B}, st)));
-    // conv3
-    FB_CUDA_OK((launch_tc_wgrad<64, 5, kSlabW3, 1, 6>(p->a2_w, p->dz3_b, p->conv3_w, p->s3, EpiStoreF32{t->part3, 640, 64, (size_t)640 * 64}, st)));
-    FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4>(p->dz3_s, wm.w3d, p->conv3_d, t->n_sms, EpiConv3Dgrad{t->dz2, t->a2, P2}, st)));
-    // conv2
-    FB_CUDA_OK((launch_tc_wgrad<64, 4, kSlabW2, 2, 4>(p->p2_w, p->dz2_b, p->conv2_w, p->s2, EpiStoreF32{t->part2, 512, 64, (size_t)512 * 64}, st)));
+    const FwdWs &f = t->ws[0];
+    const int B = a.B, H = L.hidden, P1 = B * kP1, P2 = B * kP2;
+    cudaStream_t sx = t->aux;
+    int e = 0;
+    auto fork = [&](cudaStream_t from, cudaStream_t to) -> cudaError_t {       // `to` waits for everything issued on `from`
+        cudaError_t r = cudaEventRecord(t->ev[e], from);
+        if (r == cudaSuccess) r = cudaStreamWaitEvent(to, t->ev[e], 0);
+        e++;
+        return r;
+    };
+    if (pack_online) { rc = tc_pack_weights(n, a.params, 0, st); if (rc) return rc; }
+    FB_CUDA_OK(fork(st, sx));
+    // ---- aux: Q(s') with the net the variant names (and the online net too for Double)
+    if (a.variant != 0 && pack_target) { rc = tc_pack_weights(n, a.target, 1, sx); if (rc) return rc; }
+    if (a.variant == 2) { rc = tc_forward(n, 0, 1, a.params, a.fn, B, n->q_next_online, sx); if (rc) return rc; }
+    rc = a.variant == 0 ? tc_forward(n, 0, 1, a.params, a.fn, B, n->q_next, sx) : tc_forward(n, 1, 1, a.target, a.fn, B, n->q_next, sx);
+    if (rc) return rc;
+    // ---- main: Q(s) with the online net; its activations stay in workspace 0 for the backward pass
+    rc = tc_forward(n, 0, 0, a.params, a.fs, B, n->q, st); if (rc) return rc;
+    FB_CUDA_OK(fork(sx, st));
+    qnet_launch_td_loss(n->q, n->q_next, n->q_next_online, a.actions, a.rewards, a.terminals, a.isw, B, a.global_batch, a.variant, a.gamma,
+                        a.loss_sum, n->dq, a.loss_out, a.abs_err, a.q_target, st);
+    // ---- backward.  head: fp32 gradients of the head variables and the fc1 bias straight into grads, dh1 as bf16
+    head_backward_tc_kernel<<<H / 32 + 1, 256, 0, st>>>(f.h1, n->dq, a.params, L, B, a.grads, t->dh1);
+    FB_CUDA_OK(fork(st, sx));
+    // fc1: dW = a3^T dh1 (aux, written in place), dz3 = (dh1 Wf1^T) * relu'(a3)
+    FB_CUDA_OK((launch_tc_gemm<128, 1>(p->a3_m, p->dh1_b, p->fc1_w, dim3(13, H / 128, 1), EpiStoreF32{a.grads + L.wf1, kFlat, H, 0}, sx)));
+    FB_CUDA_OK((launch_tc_gemm<64, 0>(p->dh1_k, wm.wf1n, p->fc1_d, dim3((B + 127) / 128, kFlat / 64, 1), EpiFc1Dgrad{t->dz3, f.a3, B}, st)));
+    FB_CUDA_OK(fork(st, sx));
+    FB_CUDA_OK((launch_tc_wgrad<64, 5, kSlabW3, 1, 6>(p->a2_w, p->dz3_b, p->conv3_w, p->s3, EpiStoreF32{t->part3, 640, 64, (size_t)640 * 64}, sx)));
+    FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4>(p->dz3_s, wm.w3d, p->conv3_d, t->n_sms, EpiConv3Dgrad{t->dz2, f.a2, P2}, st)));
+    FB_CUDA_OK(fork(st, sx));
+    FB_CUDA_OK((launch_tc_wgrad<64, 4, kSlabW2, 2, 4>(p->p2_w, p->dz2_b, p->conv2_w, p->s2, EpiStoreF32{t->part2, 512, 64, (size_t)512 * 64}, sx)));
     FB_CUDA_OK((launch_tc_conv<128, kSlab2, 1, 4, 4>(p->dz2_s, wm.w2d, p->conv2_d, t->n_sms, EpiStoreBf16{t->dp2, P2, 128}, st)));
-    unpool_relu_kernel_tc<<<(unsigned)(((size_t)B * 400 + 255) / 256), 256, 0, st>>>(t->z1, t->dp2, B, t->dz1);
-    // conv1 (no input gradient)
-    FB_CUDA_OK((launch_tc_wgrad<32, 2, kSlabW1, 1, 6>(p->x2_w, p->dz1_b, p->conv1_w, p->s1, EpiStoreF32{t->part1, 256, 32, (size_t)256 * 32}, st)));
-    // bias gradients = column sums of the dZ tensors
+    unpool_relu_kernel_tc<<<(unsigned)(((size_t)B * 400 + 255) / 256), 256, 0, st>>>(f.z1, t->dp2, B, t->dz1);
+    FB_CUDA_OK(fork(st, sx));
+    // bias gradients = column sums of the dZ tensors (aux) beside the conv1 weight gradient (no input gradient there)
     const int c1 = (P1 + kChunk1 - 1) / kChunk1, c23 = (P2 + kChunk23 - 1) / kChunk23;
     ColsumJobs cj{};
     cj.njobs = 3;
     cj.j[0] = ColsumJob{t->dz1, t->bp1, P1, 32, kChunk1, 0};
     cj.j[1] = ColsumJob{t->dz2, t->bp2, P2, 64, kChunk23, c1};
     cj.j[2] = ColsumJob{t->dz3, t->bp3, P2, 64, kChunk23, c1 + c23};
-    colsum_kernel<<<c1 + 2 * c23, 256, 0, st>>>(cj);
-    FinalizeArgs fa{t->part1, t->part2, t->part3, t->partf, p->s1, p->s2, p->s3, t->bp1, t->bp2, t->bp3, c1, c23, c23};
-    finalize_grads_kernel<<<592, 256, 0, st>>>(fa, L, grads_dev);
+    colsum_kernel<<<c1 + 2 * c23, 256, 0, sx>>>(cj);
+    FB_CUDA_OK((launch_tc_wgrad<32, 2, kSlabW1, 1, 6>(p->x2_w, p->dz1_b, p->conv1_w, p->s1, EpiStoreF32{t->part1, 256, 32, (size_t)256 * 32}, st)));
+    FB_CUDA_OK(fork(sx, st));
+    FinalizeArgs fa{t->part1, t->part2, t->part3, p->s1, p->s2, p->s3, t->bp1, t->bp2, t->bp3, c1, c23, c23};
+    finalize_grads_kernel<<<296, 256, 0, st>>>(fa, L, a.grads);
     FB_CUDA_OK(cudaGetLastError());
+    return FB_OK;
+}
+
+bool same_key(const GraphKey &x, const GraphKey &y) { return memcmp(&x, &y, sizeof(GraphKey)) == 0; }
+
+}  // namespace
+
+extern "C" int fb_qnet_use_graphs(fb_qnet *n, int enable) {
+    FB_REQUIRE(n != nullptr, "fb_qnet_use_graphs: NULL argument");
+    if (n->tc) n->tc->use_graph = enable ? 1 : 0;
+    return FB_OK;
+}
+
+int tc_loss_backward(fb_qnet *n, const TcTrainArgs &a, cudaStream_t st) {
+    TcState *t = n->tc;
+    FB_REQUIRE(t != nullptr && a.B > 0 && a.B <= n->max_batch, "tc_loss_backward: bad argument");
+    GraphKey key;
+    memset(&key, 0, sizeof(key));                // padding bytes take part in the comparison
+    key.a.variant = a.variant; key.a.params = a.params; key.a.target = a.target;
+    key.a.fs.base = a.fs.base; key.a.fs.sample_stride = a.fs.sample_stride; key.a.fn.base = a.fn.base; key.a.fn.sample_stride = a.fn.sample_stride;
+    for (int c = 0; c < 4; c++) { key.a.fs.chan_off[c] = a.fs.chan_off[c]; key.a.fn.chan_off[c] = a.fn.chan_off[c]; }
+    key.a.actions = a.actions; key.a.rewards = a.rewards; key.a.terminals = a.terminals; key.a.isw = a.isw;
+    key.a.B = a.B; key.a.global_batch = a.global_batch; key.a.gamma = a.gamma; key.a.loss_sum = a.loss_sum;
+    key.a.grads = a.grads; key.a.loss_out = a.loss_out; key.a.abs_err = a.abs_err; key.a.q_target = a.q_target;
+    key.pack_online = n->packed_src[0] != a.params;
+    key.pack_target = a.variant != 0 && n->packed_src[1] != a.target;
+    int rc = FB_OK;
+    GraphEntry *ge = nullptr;
+    if (t->use_graph) {
+        for (auto &g : t->graphs) if (same_key(g.key, key)) { ge = &g; break; }
+        if (!ge) {
+            if (t->graphs.size() >= 8) { for (auto &g : t->graphs) if (g.exec) cudaGraphExecDestroy(g.exec); t->graphs.clear(); }
+            t->graphs.push_back(GraphEntry{key, 0, nullptr});
+            ge = &t->graphs.back();
+        }
+    }
+    if (ge && ge->exec) {
+        FB_CUDA_OK(cudaGraphLaunch(ge->exec, st));
+    } else if (ge && ge->seen >= 1) {            // second identical call: capture (everything lazy was initialised by the first)
+        cudaGraph_t graph = nullptr;
+        FB_CUDA_OK(cudaStreamBeginCapture(t->cap, cudaStreamCaptureModeRelaxed));
+        rc = train_step_launch(n, a, key.pack_online, key.pack_target, t->cap);
+        cudaError_t ce = cudaStreamEndCapture(t->cap, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        FB_CUDA_OK(ce);
+        cudaError_t ie = cudaGraphInstantiate(&ge->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        FB_CUDA_OK(ie);
+        FB_CUDA_OK(cudaGraphLaunch(ge->exec, st));
+    } else {
+        rc = train_step_launch(n, a, key.pack_online, key.pack_target, st);
+        if (rc) return rc;
+        if (ge) ge->seen++;
+    }
+    n->packed_src[0] = a.params;
+    if (a.variant != 0) n->packed_src[1] = a.target;
     return FB_OK;
 }
 

@@ -155,6 +155,9 @@ int fb_qnet_destroy(fb_qnet *net);
 int fb_qnet_set_precision(fb_qnet *net, int precision);
 int fb_qnet_get_precision(const fb_qnet *net);
 int fb_qnet_invalidate(fb_qnet *net);
+/* FB_PRECISION_BF16 only: replay fb_qnet_loss_backward as a CUDA graph once the same arguments were seen twice
+ * (default on; the eager two-stream path is identical work). */
+int fb_qnet_use_graphs(fb_qnet *net, int enable);
 int fb_qnet_param_count(const fb_qnet *net);
 int fb_qnet_layout(const fb_qnet *net, int32_t *out16_host);
 
