@@ -70,6 +70,8 @@ _SIGNATURES = {
     "fb_env_step_random": ([_vp, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, _u8p, _u8p, C.c_int, C.c_int,
                             _f32p, _u8p, _i32p, _vp], C.c_int),
     "fb_env_step_host": ([_vp, _u8p, _u8p, C.c_int, C.c_int, _f32p, _u8p, _i32p, _vp], C.c_int),
+    "fb_env_step_host_submit": ([_vp, _u8p, _u8p, C.c_int, C.c_int, _f32p, _u8p, _i32p, _vp], C.c_int),
+    "fb_env_step_host_wait": ([_vp], C.c_int),
     "fb_env_check": ([_vp, _vp], C.c_int),
     "fb_env_export_state": ([_vp, _i32p, _vp], C.c_int),
     "fb_env_import_state": ([_vp, _i32p, _vp], C.c_int),

@@ -23,10 +23,14 @@ struct fb_env {
     const uint8_t *gaps;
     int gaps_len;
     int *err_flag;
-    uint8_t *stage_act;      // device staging for fb_env_step_host
-    float *stage_rew;
-    uint8_t *stage_term;
-    int32_t *stage_score;
+    // device staging for the host-buffer calls, two slots so that the copies of one step overlap the kernel of the next
+    uint8_t *stage_act[2];
+    float *stage_rew[2];
+    uint8_t *stage_term[2];
+    int32_t *stage_score[2];
+    cudaStream_t s_in, s_out;               // H2D / D2H copy streams
+    cudaEvent_t ev_in[2], ev_step[2], ev_out[2];
+    unsigned long long submitted, waited;   // host-step tickets
     int num_sms;
 };
 
@@ -239,18 +243,33 @@ extern "C" int fb_env_create(int n_envs, uint64_t seed, uint64_t first_env_id, f
     FB_CUDA_OK(cudaMalloc(&e->state, sizeof(EnvState) * (size_t)n_envs));
     FB_CUDA_OK(cudaMalloc(&e->err_flag, sizeof(int)));
     FB_CUDA_OK(cudaMemset(e->err_flag, 0, sizeof(int)));
-    FB_CUDA_OK(cudaMalloc(&e->stage_act, (size_t)n_envs));
-    FB_CUDA_OK(cudaMalloc(&e->stage_rew, sizeof(float) * (size_t)n_envs));
-    FB_CUDA_OK(cudaMalloc(&e->stage_term, (size_t)n_envs));
-    FB_CUDA_OK(cudaMalloc(&e->stage_score, sizeof(int32_t) * (size_t)n_envs));
+    for (int k = 0; k < 2; k++) {
+        FB_CUDA_OK(cudaMalloc(&e->stage_act[k], (size_t)n_envs));
+        FB_CUDA_OK(cudaMalloc(&e->stage_rew[k], sizeof(float) * (size_t)n_envs));
+        FB_CUDA_OK(cudaMalloc(&e->stage_term[k], (size_t)n_envs));
+        FB_CUDA_OK(cudaMalloc(&e->stage_score[k], sizeof(int32_t) * (size_t)n_envs));
+        FB_CUDA_OK(cudaEventCreateWithFlags(&e->ev_in[k], cudaEventDisableTiming));
+        FB_CUDA_OK(cudaEventCreateWithFlags(&e->ev_step[k], cudaEventDisableTiming));
+        FB_CUDA_OK(cudaEventCreateWithFlags(&e->ev_out[k], cudaEventDisableTiming));
+    }
+    FB_CUDA_OK(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+    FB_CUDA_OK(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+    e->submitted = e->waited = 0;
     *out = e;
     return fb_env_reset(e, nullptr);
 }
 
 extern "C" int fb_env_destroy(fb_env *e) {
     if (!e) return FB_OK;
-    cudaFree(e->state); cudaFree(e->err_flag); cudaFree(e->stage_act); cudaFree(e->stage_rew);
-    cudaFree(e->stage_term); cudaFree(e->stage_score);
+    cudaFree(e->state); cudaFree(e->err_flag);
+    for (int k = 0; k < 2; k++) {
+        cudaFree(e->stage_act[k]); cudaFree(e->stage_rew[k]); cudaFree(e->stage_term[k]); cudaFree(e->stage_score[k]);
+        if (e->ev_in[k]) cudaEventDestroy(e->ev_in[k]);
+        if (e->ev_step[k]) cudaEventDestroy(e->ev_step[k]);
+        if (e->ev_out[k]) cudaEventDestroy(e->ev_out[k]);
+    }
+    if (e->s_in) cudaStreamDestroy(e->s_in);
+    if (e->s_out) cudaStreamDestroy(e->s_out);
     delete e;
     return FB_OK;
 }
@@ -329,26 +348,60 @@ extern "C" int fb_env_step_random(fb_env *e, int n_steps, uint64_t action_seed, 
     return launch_step(e, a, (cudaStream_t)stream);
 }
 
-extern "C" int fb_env_step_host(fb_env *e, const uint8_t *actions_host, uint8_t *obs_ring_dev, int ring_len, int ring_slot,
-                                float *reward_host, uint8_t *terminal_host, int32_t *score_host, void *stream) {
+// frame_step with HOST buffers, split in two so that a caller can keep two steps in flight: the H2D copy of the
+// actions, the step kernel and the D2H copies of reward / terminal / score run on three streams chained by events,
+// and the copies of step t overlap the kernel of step t+1.  The reference raises ValueError for a non one-hot action
+// BEFORE touching the state (wrapped_flappy_bird.py:99-100): the actions are checked on the host first.
+extern "C" int fb_env_step_host_submit(fb_env *e, const uint8_t *actions_host, uint8_t *obs_ring_dev, int ring_len, int ring_slot,
+                                       float *reward_host, uint8_t *terminal_host, int32_t *score_host, void *stream) {
     int rc = check_ring(e, obs_ring_dev, ring_len, ring_slot, 1);
     if (rc) return rc;
     FB_REQUIRE(actions_host != nullptr, "fb_env_step_host: actions_host is NULL");
+    FB_REQUIRE(e->submitted - e->waited < 2, "fb_env_step_host_submit: two steps are already in flight; call fb_env_step_host_wait");
     cudaStream_t st = (cudaStream_t)stream;
-    // the reference raises ValueError before touching the state (wrapped_flappy_bird.py:99-100)
-    for (int k = 0; k < e->n; k++)
-        if (actions_host[k] > 1) { fb_set_error("Multiple input actions!"); return FB_ERR_ACTION; }
-    FB_CUDA_OK(cudaMemcpyAsync(e->stage_act, actions_host, (size_t)e->n, cudaMemcpyHostToDevice, st));
+    {   // every byte must be 0 or 1: eight at a time
+        const int n = e->n;
+        int k = 0;
+        unsigned long long bad = 0;
+        for (; k + 8 <= n; k += 8) { unsigned long long w; memcpy(&w, actions_host + k, 8); bad |= w & 0xFEFEFEFEFEFEFEFEull; }
+        for (; k < n; k++) bad |= (unsigned long long)(actions_host[k] & 0xFE);
+        if (bad) { fb_set_error("Multiple input actions!"); return FB_ERR_ACTION; }
+    }
+    const int sl = (int)(e->submitted & 1);
+    FB_CUDA_OK(cudaMemcpyAsync(e->stage_act[sl], actions_host, (size_t)e->n, cudaMemcpyHostToDevice, e->s_in));
+    FB_CUDA_OK(cudaEventRecord(e->ev_in[sl], e->s_in));
+    FB_CUDA_OK(cudaStreamWaitEvent(st, e->ev_in[sl], 0));
     StepArgs a{};
-    a.actions = e->stage_act; a.ring = obs_ring_dev; a.ring_len = ring_len; a.ring_slot = ring_slot;
-    a.reward = e->stage_rew; a.terminal = e->stage_term; a.score = e->stage_score; a.n_steps = 1;
+    a.actions = e->stage_act[sl]; a.ring = obs_ring_dev; a.ring_len = ring_len; a.ring_slot = ring_slot;
+    a.reward = e->stage_rew[sl]; a.terminal = e->stage_term[sl]; a.score = e->stage_score[sl]; a.n_steps = 1;
     rc = launch_step(e, a, st);
     if (rc) return rc;
-    if (reward_host) FB_CUDA_OK(cudaMemcpyAsync(reward_host, e->stage_rew, sizeof(float) * (size_t)e->n, cudaMemcpyDeviceToHost, st));
-    if (terminal_host) FB_CUDA_OK(cudaMemcpyAsync(terminal_host, e->stage_term, (size_t)e->n, cudaMemcpyDeviceToHost, st));
-    if (score_host) FB_CUDA_OK(cudaMemcpyAsync(score_host, e->stage_score, sizeof(int32_t) * (size_t)e->n, cudaMemcpyDeviceToHost, st));
-    FB_CUDA_OK(cudaStreamSynchronize(st));
+    FB_CUDA_OK(cudaEventRecord(e->ev_step[sl], st));
+    FB_CUDA_OK(cudaStreamWaitEvent(e->s_out, e->ev_step[sl], 0));
+    if (reward_host) FB_CUDA_OK(cudaMemcpyAsync(reward_host, e->stage_rew[sl], sizeof(float) * (size_t)e->n, cudaMemcpyDeviceToHost, e->s_out));
+    if (terminal_host) FB_CUDA_OK(cudaMemcpyAsync(terminal_host, e->stage_term[sl], (size_t)e->n, cudaMemcpyDeviceToHost, e->s_out));
+    if (score_host) FB_CUDA_OK(cudaMemcpyAsync(score_host, e->stage_score[sl], sizeof(int32_t) * (size_t)e->n, cudaMemcpyDeviceToHost, e->s_out));
+    FB_CUDA_OK(cudaEventRecord(e->ev_out[sl], e->s_out));
+    e->submitted++;
     return FB_OK;
+}
+
+// Blocks until the OLDEST submitted step has delivered its reward / terminal / score to the host buffers.
+extern "C" int fb_env_step_host_wait(fb_env *e) {
+    FB_REQUIRE(e != nullptr, "fb_env_step_host_wait: env is NULL");
+    FB_REQUIRE(e->submitted > e->waited, "fb_env_step_host_wait: nothing in flight");
+    FB_CUDA_OK(cudaEventSynchronize(e->ev_out[e->waited & 1]));
+    e->waited++;
+    return FB_OK;
+}
+
+extern "C" int fb_env_step_host(fb_env *e, const uint8_t *actions_host, uint8_t *obs_ring_dev, int ring_len, int ring_slot,
+                                float *reward_host, uint8_t *terminal_host, int32_t *score_host, void *stream) {
+    FB_REQUIRE(e != nullptr, "fb_env_step_host: env is NULL");
+    while (e->submitted > e->waited) { int rc = fb_env_step_host_wait(e); if (rc) return rc; }
+    int rc = fb_env_step_host_submit(e, actions_host, obs_ring_dev, ring_len, ring_slot, reward_host, terminal_host, score_host, stream);
+    if (rc) return rc;
+    return fb_env_step_host_wait(e);
 }
 
 extern "C" int fb_env_check(fb_env *e, void *stream) {

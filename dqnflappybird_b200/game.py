@@ -184,6 +184,22 @@ class GameState:
         self.steps += 1
         return self.ring[:, slot]
 
+    def frame_step_host_submit(self, actions_host: torch.Tensor, reward_host: torch.Tensor, terminal_host: torch.Tensor,
+                               score_host: torch.Tensor):
+        """frame_step_host without the final wait: up to two steps may be in flight, so the copies of one step overlap
+        the kernel of the next.  The host buffers of a step are valid after the matching frame_step_host_wait()."""
+        slot = (self.slot + 1) % self.history
+        _lib.check(self._L.fb_env_step_host_submit(self._h, actions_host.data_ptr(), self.ring.data_ptr(), self.history, slot,
+                                                   reward_host.data_ptr(), terminal_host.data_ptr(), score_host.data_ptr(),
+                                                   _stream_ptr(self.device)), "fb_env_step_host_submit")
+        self.slot = slot
+        self.steps += 1
+        return self.ring[:, slot]
+
+    def frame_step_host_wait(self):
+        """Block until the oldest submitted host step has delivered reward / terminal / score."""
+        _lib.check(self._L.fb_env_step_host_wait(self._h), "fb_env_step_host_wait")
+
     def draw(self) -> torch.Tensor:
         """Draw the current state into the next ring slot without stepping; returns the obs view."""
         slot = (self.slot + 1) % self.history

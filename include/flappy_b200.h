@@ -104,6 +104,12 @@ int fb_env_step_random(fb_env *env, int n_steps, uint64_t action_seed, uint32_t 
  * score back; the observation stays in the device ring.  Synchronises `stream`. */
 int fb_env_step_host(fb_env *env, const uint8_t *actions_host, uint8_t *obs_ring_dev, int ring_len, int ring_slot,
                      float *reward_host, uint8_t *terminal_host, int32_t *score_host, void *stream);
+/* The same call split in two so that two steps can be in flight (copies of step t overlap the kernel of step t+1):
+ * submit returns once everything is queued; wait blocks until the OLDEST submitted step has filled its host buffers.
+ * At most two submits may be outstanding.  fb_env_step_host == submit + wait. */
+int fb_env_step_host_submit(fb_env *env, const uint8_t *actions_host, uint8_t *obs_ring_dev, int ring_len, int ring_slot,
+                            float *reward_host, uint8_t *terminal_host, int32_t *score_host, void *stream);
+int fb_env_step_host_wait(fb_env *env);
 
 /* Reads and clears the device error flag (synchronises `stream`): FB_OK or FB_ERR_ACTION. */
 int fb_env_check(fb_env *env, void *stream);

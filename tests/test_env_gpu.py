@@ -194,3 +194,35 @@ def test_step_host_entry_point(game):
     a[3] = 2
     with pytest.raises(ValueError, match="Multiple input actions"):
         gs.frame_step_host(a, r, t, s)
+
+
+def test_step_host_pipelined_matches_oracle(game):
+    """fb_env_step_host_submit/_wait with two steps in flight: every step's host results equal the oracle's, in order"""
+    N = 777
+    gaps = np.random.default_rng(5).integers(0, 8, (N, 17)).astype(np.uint8)
+    gs = game.GameState(num_envs=N, replay_gaps=gaps)
+    oracle = fo.OracleEnvs(N, gaps=gaps)
+    bufs = [tuple(x.pin_memory() for x in (torch.zeros(N, dtype=torch.uint8), torch.zeros(N, dtype=torch.float32),
+                                           torch.zeros(N, dtype=torch.uint8), torch.zeros(N, dtype=torch.int32))) for _ in range(2)]
+    rng = np.random.default_rng(6)
+    acts = [(rng.random(N) < 0.25).astype(np.uint8) for _ in range(60)]
+    want = [oracle.step(a, want_obs=False)[1:] for a in acts]
+
+    def check(k):
+        _, r, t, s = bufs[k & 1]
+        np.testing.assert_array_equal(r.numpy(), want[k][0]); np.testing.assert_array_equal(t.numpy(), want[k][1])
+        np.testing.assert_array_equal(s.numpy(), want[k][2])
+
+    bufs[0][0].copy_(torch.from_numpy(acts[0]))
+    gs.frame_step_host_submit(*bufs[0])
+    for k in range(1, 60):
+        bufs[k & 1][0].copy_(torch.from_numpy(acts[k]))
+        gs.frame_step_host_submit(*bufs[k & 1])
+        gs.frame_step_host_wait()
+        check(k - 1)
+    gs.frame_step_host_wait()
+    check(59)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(gs.export_state().cpu().numpy(), oracle.export_state())
+    with pytest.raises(Exception, match="nothing in flight"):
+        gs.frame_step_host_wait()
