@@ -329,6 +329,28 @@ def bench_learner(args, rank, world, dev):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_upd, ms_act = float(t[0]), float(t[1])
+    # ---- the dominant GEMM of the update in isolation: conv1 forward (56 % of the forward FLOPs), re-launched on the
+    # workspace contents.  At the update's own batch its operands are L2-resident by construction; at the acting chunk
+    # (2048 samples: 116 MB of operands + 58 MB of output > L2) they stream from HBM.
+    kern = None
+    if args.learner_precision == "bf16":
+        import ctypes as C
+        from dqnflappybird_b200 import _lib
+        L = _lib.lib()
+        st = torch.cuda.current_stream().cuda_stream
+        kern = {}
+        for kb, reps in ((brain.local_batch, 50), (min(2048, brain.net.max_batch), 20)):
+            fbv = brain._act_view()
+            fbv.batch = kb
+            brain.net.forward(fbv)                                   # fills the workspace at this batch
+            _lib.check(L.fb_debug_tc_kernel(brain.net._h, 0, kb, 3, brain.net.params.data_ptr(), st), "probe")
+            sync()
+            e0.record()
+            _lib.check(L.fb_debug_tc_kernel(brain.net._h, 0, kb, reps, brain.net.params.data_ptr(), st), "probe")
+            e1.record(); sync()
+            us = e0.elapsed_time(e1) * 1e3 / reps
+            kern[kb] = {"us": us, "tflops": 6553600 * kb / (us * 1e-6) / 1e12,
+                        "hbm_gbs": kb * 441 * (128 + 64) / (us * 1e-6) / 1e9}
     flop_upd = (2 * FLOP_FWD + FLOP_BWD) * B
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -341,7 +363,18 @@ def bench_learner(args, rank, world, dev):
             "frac_of_bf16_tensor_peak": flop_upd / world / (ms_upd * 1e-3) / 1e12 / tc_peak, "tensor_peak_tflops": tc_peak,
             "compute_path": brain.net.compute_path if hasattr(brain.net, "compute_path") else "fp32 CUDA-core implicit GEMM",
             "act_envs_per_s": N * world / (ms_act * 1e-3), "ms_per_act": ms_act,
-            "act_tflops_per_gpu": N * FLOP_FWD / (ms_act * 1e-3) / 1e12}
+            "act_tflops_per_gpu": N * FLOP_FWD / (ms_act * 1e-3) / 1e12,
+            "transitions_per_s": B * 1e3 / ms_upd,
+            "roofline": None if not kern else {
+                "bound": "tensor", "kernel": "tc_conv_kernel<32,152,1,4,6,EpiConv1> (conv1 forward: TMA slab + tcgen05.mma, N = 32)",
+                "algorithmic_flop_per_sample": 6553600, "unit": "TFLOP/s", "peak": tc_peak,
+                "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, cuBLAS burst)",
+                "achieved": max(v["tflops"] for v in kern.values()),
+                "frac": max(v["tflops"] for v in kern.values()) / tc_peak,
+                "by_batch": {str(k): v for k, v in kern.items()},
+                "note": "per launch, CUDA events over back-to-back launches; at batch 2048 the bf16 operands (X2 read 56 KB + Z1 "
+                        "write 28 KB per sample) exceed L2 and the kernel also runs at hbm_gbs of HBM traffic; traffic and "
+                        "sm__pipe_tensor_cycles_active: profiles/r01_ncu_tc_kernels_summary.json"}}
 
 
 def main():

@@ -88,6 +88,8 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    tc::pdl_wait();
+    tc::pdl_launch();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -113,18 +115,18 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = tc::instr_desc_bf16(128, BN, MODE, MODE);
+            const uint32_t ahi = tc::smem_desc_hi(g.sbo_a, tc::kSwizzle128), bhi = tc::smem_desc_hi(g.sbo_b, B_LAYOUT);
+            const uint32_t a_lo0 = tc::smem_desc_lo(smem, g.lbo_a), b_lo0 = tc::smem_desc_lo(smem + A_BYTES, g.lbo_b);
+            const uint32_t ka = g.kstep_a >> 4, kbs = g.kstep_b >> 4;
             for (int kb = 0; kb < nkb; kb++) {
                 const int s = kb % kStages;
                 const uint32_t ph = (kb / kStages) & 1;
                 tc::mbar_wait(tc::smem_u32(&bar_full[s]), ph);
                 tc::tc_fence_after();
-                const uint32_t sa = smem + s * STAGE, sb = sa + A_BYTES;
+                const uint32_t soff = s * (STAGE >> 4);
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint64_t ad = tc::smem_desc(sa + k * g.kstep_a, g.lbo_a, g.sbo_a, tc::kSwizzle128);
-                    const uint64_t bd = tc::smem_desc(sb + k * g.kstep_b, g.lbo_b, g.sbo_b, B_LAYOUT);
-                    tc::umma_bf16(tmem, ad, bd, idesc, (kb | k) != 0);
-                }
+                for (int k = 0; k < 4; k++)
+                    tc::umma_bf16_lohi(tmem, a_lo0 + soff + k * ka, ahi, b_lo0 + soff + k * kbs, bhi, idesc, (kb | k) != 0);
                 tc::umma_commit(tc::smem_u32(&bar_empty[s]));     // frees the stage once these MMAs have read it
             }
             tc::umma_commit(tc::smem_u32(&bar_accum));
@@ -162,8 +164,7 @@ static cudaError_t launch_tc_gemm(const CUtensorMap &ma, const CUtensorMap &mb, 
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    kern<<<grid, kThreads, gemm_smem_bytes<BN>(), st>>>(ma, mb, g, ep);
-    return cudaGetLastError();
+    return tc::launch_pdl(kern, grid, dim3(kThreads), gemm_smem_bytes<BN>(), st, ma, mb, g, ep);
 }
 
 // ------------------------------------------------------------------------------------------------ epilogues
@@ -267,6 +268,8 @@ struct EpiStoreF32 {            // weight-gradient partials [split][rows][ld] an
 // ------------------------------------------------------------------------------------------------ glue kernels
 // u8 frames (FrameView) -> X2 [B*441][64]: block (bh,bw) of the input padded by 2, channel j = r*16 + s*4 + c
 __global__ void pack_x2_kernel(FrameView fv, int B, bf16 *x2) {
+    tc::pdl_wait();
+    tc::pdl_launch();
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)B * kP1 * 8) return;
     int t8 = (int)(t & 7);
@@ -304,6 +307,8 @@ __device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
 
 // max_pool 2x2 (BrainDQN.py:128) + space-to-depth for conv2: Z1 (21-grid) -> P2 [B*49][128], channel j = r*64 + s*32 + c
 __global__ void pool_pack_kernel(const bf16 *z1, int B, bf16 *p2) {
+    tc::pdl_wait();
+    tc::pdl_launch();
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)B * 36 * 16) return;
     int cg = (int)(t & 3), rs = (int)((t >> 2) & 3);
@@ -321,6 +326,8 @@ __global__ void pool_pack_kernel(const bf16 *z1, int B, bf16 *p2) {
 
 // dZ1 = unpool(dP2) * relu'(z1): the gradient goes to the first maximum of each window (TF MaxPoolGrad)
 __global__ void unpool_relu_kernel_tc(const bf16 *z1, const bf16 *dp2, int B, bf16 *dz1) {
+    tc::pdl_wait();
+    tc::pdl_launch();
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)B * 100 * 4) return;
     int cg = (int)(t & 3);
@@ -375,6 +382,8 @@ struct PackedWeights {
     bf16 *w2d;      // [128][256]  (r, s, c), (tap, o)          conv2 dgrad    Bt
 };
 __global__ void pack_weights_kernel(const float *params, QnetLayout L, PackedWeights pw, int fwd_only) {
+    tc::pdl_wait();
+    tc::pdl_launch();
     const int H = L.hidden;
     const int n1 = kC1 * kK1, n2 = kC2 * kK2, n3 = kC3 * kK3, nf = kFlat * H;
     const int total = fwd_only ? n1 + n2 + n3 + nf : n1 + n2 + n3 + nf + nf + n3 + 128 * 256;
@@ -427,6 +436,8 @@ __global__ void pack_weights_kernel(const float *params, QnetLayout L, PackedWei
 struct ColsumJob { const bf16 *x; float *part; int rows, N, chunk_rows, first_block; };
 struct ColsumJobs { ColsumJob j[3]; int njobs; };
 __global__ void __launch_bounds__(256) colsum_kernel(ColsumJobs jobs) {
+    tc::pdl_wait();
+    tc::pdl_launch();
     __shared__ float red[8][64 + 1];
     int ji = 0;
 #pragma unroll
@@ -469,6 +480,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(ColsumJobs jobs) {
 __global__ void __launch_bounds__(256) head_backward_tc_kernel(const float *__restrict__ h1, const float *__restrict__ dq,
                                                                const float *__restrict__ params, QnetLayout L, int B,
                                                                float *__restrict__ grads, bf16 *__restrict__ dh1) {
+    tc::pdl_wait();
+    tc::pdl_launch();
     __shared__ float red[8][32][4];
     const int H = L.hidden;
     if ((int)blockIdx.x == H / 32) {                 // head bias gradients: sum_b dq (dueling: (d0+d1) for V, d - mean for A)
@@ -524,6 +537,8 @@ __global__ void __launch_bounds__(256) head_backward_tc_kernel(const float *__re
 __global__ void __launch_bounds__(128) fc1_head_kernel(const float *__restrict__ part, int splits, size_t split_stride,
                                                       const float *__restrict__ params, QnetLayout L, int B, float *__restrict__ h1,
                                                       float *__restrict__ q) {
+    tc::pdl_wait();
+    tc::pdl_launch();
     __shared__ float red[4][3];
     const int b = blockIdx.x, H = L.hidden;
     float s0 = 0.f, s1 = 0.f, sv = 0.f;
@@ -560,6 +575,8 @@ struct FinalizeArgs {
     int c1, c2, c3;
 };
 __global__ void finalize_grads_kernel(const FinalizeArgs a, QnetLayout L, float *__restrict__ grads) {
+    tc::pdl_wait();
+    tc::pdl_launch();
     const int end = L.wf1;                   // the fc1 weight gradient is written in place by its GEMM, the fc1 bias by the head kernel
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x) {
         float s = 0.f;
@@ -831,8 +848,7 @@ void tc_state_destroy(fb_qnet *n) {
 
 int tc_pack_weights(fb_qnet *n, const float *params_dev, int slot, cudaStream_t st) {
     FB_REQUIRE(n->tc != nullptr && (slot == 0 || slot == 1), "tc_pack_weights: bad argument");
-    pack_weights_kernel<<<592, 256, 0, st>>>(params_dev, n->L, n->tc->pw[slot], slot == 1 ? 1 : 0);
-    FB_CUDA_OK(cudaGetLastError());
+    FB_CUDA_OK(tc::launch_pdl(pack_weights_kernel, dim3(592), dim3(256), 0, st, params_dev, n->L, n->tc->pw[slot], slot == 1 ? 1 : 0));
     return FB_OK;
 }
 
@@ -859,15 +875,15 @@ int tc_forward(fb_qnet *n, int slot, int w, const float *params_dev, FrameView f
     const TcWeightMaps &wm = t->wm[slot];
     const FwdWs &f = t->ws[w];
     const int P1 = B * kP1, P2 = B * kP2;
-    pack_x2_kernel<<<(unsigned)(((size_t)P1 * 8 + 255) / 256), 256, 0, st>>>(fv, B, f.x2);
+    FB_CUDA_OK(tc::launch_pdl(pack_x2_kernel, dim3((unsigned)(((size_t)P1 * 8 + 255) / 256)), dim3(256), 0, st, fv, B, f.x2));
     FB_CUDA_OK((launch_tc_conv<32, kSlab1, 1, 4, 6>(p->x2_s[w], wm.w1p, p->conv1, t->n_sms, EpiConv1{f.z1, params_dev + L.b1, P1}, st)));
-    pool_pack_kernel<<<(unsigned)(((size_t)B * 36 * 16 + 255) / 256), 256, 0, st>>>(f.z1, B, f.p2);
+    FB_CUDA_OK(tc::launch_pdl(pool_pack_kernel, dim3((unsigned)(((size_t)B * 36 * 16 + 255) / 256)), dim3(256), 0, st, f.z1, B, f.p2));
     FB_CUDA_OK((launch_tc_conv<64, kSlab2, 2, 8, 3>(p->p2_s[w], wm.w2p, p->conv2, t->n_sms, EpiGrid7{f.a2, params_dev + L.b2, P2}, st)));
     FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4>(p->a2_s[w], wm.w3p, p->conv3, t->n_sms, EpiConv3{f.a3, params_dev + L.b3, P2}, st)));
     FB_CUDA_OK((launch_tc_gemm<128, 0>(p->a3_k[w], wm.wf1p, p->fc1, dim3((B + 127) / 128, L.hidden / 128, p->sf),
                                        EpiStoreF32{f.parth, B, L.hidden, (size_t)n->max_batch * L.hidden}, st)));
-    fc1_head_kernel<<<B, 128, 0, st>>>(f.parth, p->sf, (size_t)n->max_batch * L.hidden, params_dev, L, B, f.h1, q_out);
-    FB_CUDA_OK(cudaGetLastError());
+    FB_CUDA_OK(tc::launch_pdl(fc1_head_kernel, dim3(B), dim3(128), 0, st, f.parth, p->sf, (size_t)n->max_batch * L.hidden, params_dev, L, B,
+                              f.h1, q_out));
     return FB_OK;
 }
 
@@ -907,7 +923,7 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     qnet_launch_td_loss(n->q, n->q_next, n->q_next_online, a.actions, a.rewards, a.terminals, a.isw, B, a.global_batch, a.variant, a.gamma,
                         a.loss_sum, n->dq, a.loss_out, a.abs_err, a.q_target, st);
     // ---- backward.  head: fp32 gradients of the head variables and the fc1 bias straight into grads, dh1 as bf16
-    head_backward_tc_kernel<<<H / 32 + 1, 256, 0, st>>>(f.h1, n->dq, a.params, L, B, a.grads, t->dh1);
+    FB_CUDA_OK(tc::launch_pdl(head_backward_tc_kernel, dim3(H / 32 + 1), dim3(256), 0, st, f.h1, n->dq, a.params, L, B, a.grads, t->dh1));
     FB_CUDA_OK(fork(st, sx));
     // fc1: dW = a3^T dh1 (aux, written in place), dz3 = (dh1 Wf1^T) * relu'(a3)
     FB_CUDA_OK((launch_tc_gemm<128, 1>(p->a3_m, p->dh1_b, p->fc1_w, dim3(13, H / 128, 1), EpiStoreF32{a.grads + L.wf1, kFlat, H, 0}, sx)));
@@ -918,7 +934,7 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     FB_CUDA_OK(fork(st, sx));
     FB_CUDA_OK((launch_tc_wgrad<64, 4, kSlabW2, 2, 4>(p->p2_w, p->dz2_b, p->conv2_w, p->s2, EpiStoreF32{t->part2, 512, 64, (size_t)512 * 64}, sx)));
     FB_CUDA_OK((launch_tc_conv<128, kSlab2, 1, 4, 4>(p->dz2_s, wm.w2d, p->conv2_d, t->n_sms, EpiStoreBf16{t->dp2, P2, 128}, st)));
-    unpool_relu_kernel_tc<<<(unsigned)(((size_t)B * 400 + 255) / 256), 256, 0, st>>>(f.z1, t->dp2, B, t->dz1);
+    FB_CUDA_OK(tc::launch_pdl(unpool_relu_kernel_tc, dim3((unsigned)(((size_t)B * 400 + 255) / 256)), dim3(256), 0, st, f.z1, t->dp2, B, t->dz1));
     FB_CUDA_OK(fork(st, sx));
     // bias gradients = column sums of the dZ tensors (aux) beside the conv1 weight gradient (no input gradient there)
     const int c1 = (P1 + kChunk1 - 1) / kChunk1, c23 = (P2 + kChunk23 - 1) / kChunk23;
@@ -927,12 +943,11 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     cj.j[0] = ColsumJob{t->dz1, t->bp1, P1, 32, kChunk1, 0};
     cj.j[1] = ColsumJob{t->dz2, t->bp2, P2, 64, kChunk23, c1};
     cj.j[2] = ColsumJob{t->dz3, t->bp3, P2, 64, kChunk23, c1 + c23};
-    colsum_kernel<<<c1 + 2 * c23, 256, 0, sx>>>(cj);
+    FB_CUDA_OK(tc::launch_pdl(colsum_kernel, dim3(c1 + 2 * c23), dim3(256), 0, sx, cj));
     FB_CUDA_OK((launch_tc_wgrad<32, 2, kSlabW1, 1, 6>(p->x2_w, p->dz1_b, p->conv1_w, p->s1, EpiStoreF32{t->part1, 256, 32, (size_t)256 * 32}, st)));
     FB_CUDA_OK(fork(sx, st));
     FinalizeArgs fa{t->part1, t->part2, t->part3, p->s1, p->s2, p->s3, t->bp1, t->bp2, t->bp3, c1, c23, c23};
-    finalize_grads_kernel<<<296, 256, 0, st>>>(fa, L, a.grads);
-    FB_CUDA_OK(cudaGetLastError());
+    FB_CUDA_OK(tc::launch_pdl(finalize_grads_kernel, dim3(296), dim3(256), 0, st, fa, L, a.grads));
     return FB_OK;
 }
 
@@ -989,6 +1004,37 @@ int tc_loss_backward(fb_qnet *n, const TcTrainArgs &a, cudaStream_t st) {
     }
     n->packed_src[0] = a.params;
     if (a.variant != 0) n->packed_src[1] = a.target;
+    return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel probe
+// Re-launches ONE GEMM kernel of the path `reps` times on whatever the workspaces hold (after a forward / training
+// step at the same batch), so that bench.py and ncu can time it in isolation.  which: 0 conv1 forward, 1 conv2
+// forward, 2 conv3 forward, 3 fc1 forward, 4 conv1 weight gradient, 5 conv3 data gradient, 6 fc1 data gradient.
+extern "C" int fb_debug_tc_kernel(fb_qnet *n, int which, int B, int reps, const float *params_dev, void *stream) {
+    FB_REQUIRE(n && n->tc && params_dev && B > 0 && B <= n->max_batch && reps > 0, "fb_debug_tc_kernel: bad argument");
+    TcState *t = n->tc;
+    TcPlan *p;
+    int rc = make_plan(n, B, &p);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const QnetLayout &L = n->L;
+    const TcWeightMaps &wm = t->wm[0];
+    const FwdWs &f = t->ws[0];
+    const int H = L.hidden, P1 = B * kP1, P2 = B * kP2;
+    for (int r = 0; r < reps; r++) {
+        switch (which) {
+            case 0: FB_CUDA_OK((launch_tc_conv<32, kSlab1, 1, 4, 6>(p->x2_s[0], wm.w1p, p->conv1, t->n_sms, EpiConv1{f.z1, params_dev + L.b1, P1}, st))); break;
+            case 1: FB_CUDA_OK((launch_tc_conv<64, kSlab2, 2, 8, 3>(p->p2_s[0], wm.w2p, p->conv2, t->n_sms, EpiGrid7{f.a2, params_dev + L.b2, P2}, st))); break;
+            case 2: FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4>(p->a2_s[0], wm.w3p, p->conv3, t->n_sms, EpiConv3{f.a3, params_dev + L.b3, P2}, st))); break;
+            case 3: FB_CUDA_OK((launch_tc_gemm<128, 0>(p->a3_k[0], wm.wf1p, p->fc1, dim3((B + 127) / 128, H / 128, p->sf),
+                                                       EpiStoreF32{f.parth, B, H, (size_t)n->max_batch * H}, st))); break;
+            case 4: FB_CUDA_OK((launch_tc_wgrad<32, 2, kSlabW1, 1, 6>(p->x2_w, p->dz1_b, p->conv1_w, p->s1, EpiStoreF32{t->part1, 256, 32, (size_t)256 * 32}, st))); break;
+            case 5: FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4>(p->dz3_s, wm.w3d, p->conv3_d, t->n_sms, EpiConv3Dgrad{t->dz2, f.a2, P2}, st))); break;
+            case 6: FB_CUDA_OK((launch_tc_gemm<64, 0>(p->dh1_k, wm.wf1n, p->fc1_d, dim3((B + 127) / 128, kFlat / 64, 1), EpiFc1Dgrad{t->dz3, f.a3, B}, st))); break;
+            default: FB_REQUIRE(false, "fb_debug_tc_kernel: which must be 0..6");
+        }
+    }
     return FB_OK;
 }
 

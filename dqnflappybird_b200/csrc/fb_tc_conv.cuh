@@ -52,10 +52,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
     tc::tc_fence_after();
     const uint32_t tmem = tmem_slot;
 
+    if (threadIdx.x == 0) {                          // the weights do not depend on the previous kernel: fetch them first
+        tc::mbar_expect_tx(tc::smem_u32(&bar_b), B_BYTES);
+        for (int kb = 0; kb < NKB; kb++) tc::tma_load_2d(smem_b + kb * BBLK, &mapB, kb * 64, 0, tc::smem_u32(&bar_b));
+    }
+    tc::pdl_wait();
+    tc::pdl_launch();
+
     if (warp == 0) {
         if (lane == 0) {
-            tc::mbar_expect_tx(tc::smem_u32(&bar_b), B_BYTES);
-            for (int kb = 0; kb < NKB; kb++) tc::tma_load_2d(smem_b + kb * BBLK, &mapB, kb * 64, 0, tc::smem_u32(&bar_b));
             int i = 0;
             for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, i++) {
                 const int s = i % S;
@@ -70,6 +75,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = tc::instr_desc_bf16(128, BN, 0, 0);
+            constexpr uint32_t dhi = tc::smem_desc_hi(1024, tc::kSwizzle128);
+            // descriptor start fields, in 16-byte units: per K-block for A (tap row offset, column half), constant for B
+            uint32_t a_rel[NKB];
+#pragma unroll
+            for (int kb = 0; kb < NKB; kb++) a_rel[kb] = (uint32_t)(g.kb_half[kb] * (int)HALF_BYTES + g.kb_rowoff[kb] * 128) >> 4;
+            const uint32_t a_lo0 = tc::smem_desc_lo(smem_a, 16), b_lo0 = tc::smem_desc_lo(smem_b, 16);
             tc::mbar_wait(tc::smem_u32(&bar_b), 0);
             int i = 0;
             for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, i++) {
@@ -77,15 +88,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
                 tc::mbar_wait(tc::smem_u32(&bar_acc_empty[as]), ((i >> 1) & 1) ^ 1u);
                 tc::mbar_wait(tc::smem_u32(&bar_full[s]), (i / S) & 1);
                 tc::tc_fence_after();
-                const uint32_t slab = smem_a + s * STAGE, d = tmem + as * BN;
+                const uint32_t a_lo = a_lo0 + s * (STAGE >> 4), d = tmem + as * BN;
 #pragma unroll
-                for (int kb = 0; kb < NKB; kb++) {
-                    const uint32_t a0 = slab + g.kb_half[kb] * HALF_BYTES + g.kb_rowoff[kb] * 128, b0 = smem_b + kb * BBLK;
+                for (int kb = 0; kb < NKB; kb++)
 #pragma unroll
                     for (int k = 0; k < 4; k++)
-                        tc::umma_bf16(d, tc::smem_desc(a0 + k * 32, 16, 1024, tc::kSwizzle128), tc::smem_desc(b0 + k * 32, 16, 1024, tc::kSwizzle128),
-                                      idesc, (kb | k) != 0);
-                }
+                        tc::umma_bf16_lohi(d, a_lo + a_rel[kb] + 2 * k, dhi, b_lo0 + ((kb * BBLK + k * 32) >> 4), dhi, idesc, (kb | k) != 0);
                 tc::umma_commit(tc::smem_u32(&bar_empty[s]));
                 tc::umma_commit(tc::smem_u32(&bar_acc_full[as]));
             }
@@ -131,8 +139,7 @@ static cudaError_t launch_tc_conv(const CUtensorMap &ma, const CUtensorMap &mb, 
         configured = true;
     }
     int grid = g.n_tiles < max_ctas ? g.n_tiles : max_ctas;
-    kern<<<grid, kConvThreads, smem, st>>>(ma, mb, g, ep);
-    return cudaGetLastError();
+    return tc::launch_pdl(kern, dim3(grid), dim3(kConvThreads), smem, st, ma, mb, g, ep);
 }
 
 // ---- weight gradient: D[128 a + 64 i + j][n] = sum_p A[p + off(a, i)][j] * B[p][n] over this CTA's rows p ---------
@@ -171,6 +178,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_wgrad_kernel(const __grid_
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    tc::pdl_wait();
+    tc::pdl_launch();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -188,20 +197,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_wgrad_kernel(const __grid_
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = tc::instr_desc_bf16(128, BN, 1, 1);
+            constexpr uint32_t ahi = tc::smem_desc_hi(1024, tc::kSwizzle128), bhi = tc::smem_desc_hi(B_SBO, B_LAYOUT);
+            uint32_t a_lo0[NACC];                 // start (16-byte units) + LBO of each accumulator's A descriptor, stage 0
+#pragma unroll
+            for (int a = 0; a < NACC; a++)
+                a_lo0[a] = tc::smem_desc_lo(smem + g.acc_rowoff[a] * 128, NHALF == 2 ? HALF_BYTES : g.acc_lbo[a]);
+            const uint32_t b_lo0 = tc::smem_desc_lo(smem + A_BYTES, 8192);
             for (int kb = 0; kb < nkb; kb++) {
                 const int s = kb % S;
                 tc::mbar_wait(tc::smem_u32(&bar_full[s]), (kb / S) & 1);
                 tc::tc_fence_after();
-                const uint32_t sa = smem + s * STAGE, sb = sa + A_BYTES;
+                const uint32_t soff = s * (STAGE >> 4);
 #pragma unroll
-                for (int a = 0; a < NACC; a++) {
-                    const uint32_t a0 = sa + g.acc_rowoff[a] * 128;
-                    const uint32_t lbo = NHALF == 2 ? HALF_BYTES : g.acc_lbo[a];
+                for (int a = 0; a < NACC; a++)
 #pragma unroll
                     for (int k = 0; k < 4; k++)
-                        tc::umma_bf16(tmem + a * BN, tc::smem_desc(a0 + k * 2048, lbo, 1024, tc::kSwizzle128),
-                                      tc::smem_desc(sb + k * B_KSTEP, 8192, B_SBO, B_LAYOUT), idesc, (kb | k) != 0);
-                }
+                        tc::umma_bf16_lohi(tmem + a * BN, a_lo0[a] + soff + k * 128, ahi, b_lo0 + soff + k * (B_KSTEP >> 4), bhi, idesc,
+                                           (kb | k) != 0);
                 tc::umma_commit(tc::smem_u32(&bar_empty[s]));
             }
             tc::umma_commit(tc::smem_u32(&bar_acc));
@@ -239,8 +251,7 @@ static cudaError_t launch_tc_wgrad(const CUtensorMap &ma, const CUtensorMap &mb,
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    kern<<<splits, kConvThreads, smem, st>>>(ma, mb, g, ep);
-    return cudaGetLastError();
+    return tc::launch_pdl(kern, dim3(splits), dim3(kConvThreads), smem, st, ma, mb, g, ep);
 }
 
 }  // namespace

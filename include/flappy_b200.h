@@ -248,6 +248,9 @@ int fb_debug_host_mixed(const int32_t *state16);
  * mode 0: D[M][N] = A[M][K] Bt[N][K]^T;  mode 1: D[M][N] = A[K][M]^T B[K][N];  bn = N tile (32/64/128). */
 int fb_debug_tc_gemm(int mode, int bn, int M, int N, int K, const void *a_bf16_dev, const void *b_bf16_dev, float *d_dev,
                      const uint32_t *strides6_host, void *stream);
+/* measurement hook: re-launch one GEMM kernel of the tensor-core path `reps` times on the current workspace contents
+ * (which: 0 conv1 fwd, 1 conv2 fwd, 2 conv3 fwd, 3 fc1 fwd, 4 conv1 wgrad, 5 conv3 dgrad, 6 fc1 dgrad) */
+int fb_debug_tc_kernel(fb_qnet *net, int which, int batch, int reps, const float *params_dev, void *stream);
 /* device test hook: D[128][64] = A[shift..shift+128)[64] Bt[64][64]^T with A [256][64] loaded once as a swizzled slab and
  * the MMA descriptor started shift rows into it (the property the one-slab-many-taps convolution relies on). */
 int fb_debug_tc_slab(int shift, int base_offset, const void *a_bf16_dev, const void *b_bf16_dev, float *d_dev, void *stream);
