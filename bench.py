@@ -287,7 +287,10 @@ def bench_learner(args, rank, world, dev):
     import torch.distributed as dist
     from dqnflappybird_b200.brains import BrainDQNNature
     from dqnflappybird_b200.game import GameState
-    N, B, C = args.learner_envs, args.learner_batch, 28
+    # weak scaling like the env leg: every GPU keeps configs[2]'s minibatch of 256, the global minibatch is 256 x world
+    # (--learner-scaling strong splits ONE minibatch of 256 over the ranks instead)
+    N, C = args.learner_envs, 28
+    B = args.learner_batch * (world if args.learner_scaling == "weak" else 1)
     brain = BrainDQNNature(2, "bird", num_envs=N, device=dev, replay_memory_per_env=C, batch_size=B, observe=1e18, seed=0,
                            first_env_id=rank * N, max_act_batch=2048, precision=args.learner_precision)
     gs = GameState(num_envs=N, device=dev, seed=42, history=C + 4, first_env_id=rank * N, ring=brain.ring)
@@ -364,7 +367,9 @@ def bench_learner(args, rank, world, dev):
             "compute_path": brain.net.compute_path if hasattr(brain.net, "compute_path") else "fp32 CUDA-core implicit GEMM",
             "act_envs_per_s": N * world / (ms_act * 1e-3), "ms_per_act": ms_act,
             "act_tflops_per_gpu": N * FLOP_FWD / (ms_act * 1e-3) / 1e12,
-            "transitions_per_s": B * 1e3 / ms_upd,
+            "transitions_per_s": B * 1e3 / ms_upd, "scaling": args.learner_scaling,
+            "gradient_exchange": ("none (1 GPU)" if world == 1 else
+                                  "fused into Adam over NVLink peer memory (fb_dist_adam)" if brain.net.exchange is not None else "NCCL all-reduce"),
             "roofline": None if not kern else {
                 "bound": "tensor", "kernel": "tc_conv_kernel<32,152,1,4,6,EpiConv1> (conv1 forward: TMA slab + tcgen05.mma, N = 32)",
                 "algorithmic_flop_per_sample": 6553600, "unit": "TFLOP/s", "peak": tc_peak,
@@ -391,6 +396,7 @@ def main():
     ap.add_argument("--learner-batch", type=int, default=256)
     ap.add_argument("--learner-updates", type=int, default=50)
     ap.add_argument("--learner-precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--learner-scaling", default="weak", choices=["weak", "strong"])
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -91,6 +91,15 @@ _SIGNATURES = {
                                C.c_int, C.c_int, C.c_double, C.c_int, _f32p, _f32p, _f32p, _f32p, _vp], C.c_int),
     "fb_qnet_adam": ([_vp, _f32p, _f32p, _f32p, _f32p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp], C.c_int),
     "fb_qnet_sync_target": ([_vp, _f32p, _f32p, _vp], C.c_int),
+    "fb_dist_create": ([C.c_int, C.c_int, C.c_longlong, C.POINTER(C.c_void_p)], C.c_int),
+    "fb_dist_destroy": ([_vp], C.c_int),
+    "fb_dist_handle_bytes": ([], C.c_int),
+    "fb_dist_handles": ([_vp, C.c_char_p], C.c_int),
+    "fb_dist_connect": ([_vp, C.c_char_p], C.c_int),
+    "fb_dist_connect_local": ([_vp, C.c_int, _vp], C.c_int),
+    "fb_dist_grads": ([_vp, C.c_int, C.POINTER(C.c_void_p)], C.c_int),
+    "fb_dist_parity": ([_vp], C.c_int),
+    "fb_dist_adam": ([_vp, _vp, _f32p, _f32p, _f32p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _f32p, C.c_int, _vp], C.c_int),
     "fb_replay_create": ([C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)], C.c_int),
     "fb_replay_destroy": ([_vp], C.c_int),
     "fb_replay_sample_uniform": ([_vp, C.c_longlong, C.c_int, C.c_uint32, C.c_uint64, _i32p, _vp], C.c_int),

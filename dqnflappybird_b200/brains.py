@@ -53,7 +53,7 @@ class BrainDQN:
                  replay_memory_per_env: int | None = None, replace_target_iter: int | None = REPLACE_TARGET_ITER,
                  hidden: int = 512, lr: float = 1e-6, seed: int = 0, first_env_id: int = 0, updates_per_step: int = 1,
                  reference_quirks: bool = False, copy_target_at_init: bool = False, record: bool = False, max_act_batch: int = 1024,
-                 precision: str = "bf16"):
+                 precision: str = "bf16", peer_exchange: bool | None = None):
         if actionNum != 2:
             raise ValueError("the Flappy Bird hot path has two actions (FlappyBirdDQN.py:38)")
         self.actionNum, self.gameName = actionNum, gameName
@@ -87,6 +87,11 @@ class BrainDQN:
         dueling = self.dueling and not (reference_quirks and type(self).__name__ == "BrainDuelingDQN")
         self.net = QNetwork(self.device, hidden=hidden, dueling=dueling, max_batch=max(self.local_batch, min(N, max_act_batch)),
                             seed=seed, lr=lr, copy_target_at_init=copy_target_at_init, precision=precision)
+        # one process per GPU under NCCL: sum the gradients from NVLink peer memory inside the Adam kernel (fb_dist.cu)
+        if peer_exchange is None:
+            peer_exchange = self.world > 1 and torch.distributed.get_backend() == "nccl"
+        if peer_exchange and self.world > 1:
+            self.net.enable_peer_exchange()
         self._k = 0                               # time index of the newest frame in the ring
         self._rng_pos = torch.zeros(N, dtype=torch.int32, device=self.device)
         self._actions = torch.zeros(N, dtype=torch.uint8, device=self.device)
@@ -182,9 +187,9 @@ class BrainDQN:
             isw.copy_(mb.is_weights)                 # the placeholder is tf.float32 (BrainPrioritizedReplyDQN.py:243)
         self.net.loss_backward(variant, mb.frames, mb.actions, mb.rewards, mb.terminals, isw, self.gamma, self.loss_sum,
                                self.local_batch * self.world, self._abs_err[:self.local_batch], self._q_target[:self.local_batch])
-        if self.world > 1:
+        if self.world > 1 and self.net.exchange is None:
             torch.distributed.all_reduce(self.net.grads)          # sum of per-shard gradients of the global loss
-        self.net.adam_step()
+        self.net.adam_step()                                      # with a peer exchange the sum happens inside the Adam kernel
         if mb.tree_idx is not None:
             mem.batch_update(mb.tree_idx, abs_errors=self._abs_err[:self.local_batch])   # :316
         if self.record:

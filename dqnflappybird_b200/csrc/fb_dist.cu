@@ -1,0 +1,192 @@
+// Multi-GPU gradient exchange fused with the optimizer (the learner is replicated, the ONE exchange step of
+// the path is the sum of the per-shard gradients before tf.train.AdamOptimizer, BrainDQN.py:163).
+//
+// One process per GPU.  Every rank keeps its gradient vector in a cudaMalloc'd exchange buffer that the other ranks
+// map through CUDA IPC (NVLink peer access).  One kernel per step, on every rank:
+//   1. publish: write this step's number into every peer's flag array (system-scope release; the gradients were
+//      produced by earlier kernels of the same stream);
+//   2. wait until every rank's flag shows the step (polling LOCAL memory);
+//   3. for each parameter: sum the gradients of ranks 0..G-1 in rank order straight from peer memory (identical
+//      order on every rank => bitwise identical parameters everywhere, no broadcast ever needed) and apply TF-1 Adam.
+// No separate all-reduce, no reduced-gradient round trip through HBM.  Exchange buffers are double-buffered by step
+// parity: a rank may already write step s+1's gradients while a slow peer still reads step s's; it cannot reach s+2
+// before every peer has published s+1, i.e. has finished reading s.  Waits are bounded and end in a trap, not a hang.
+#include <string.h>
+
+#include <new>
+
+#include "fb_qnet.cuh"
+
+constexpr int kMaxRanks = 8;
+
+struct fb_dist {
+    int rank, world;
+    size_t n;
+    float *xgrads[2];
+    uint32_t *flags;                         // local; flags[q] = newest step rank q has published
+    const float *peer_grads[2][kMaxRanks];
+    uint32_t *peer_flags[kMaxRanks];
+    void *opened[3 * kMaxRanks];
+    int n_opened;
+    uint32_t step;
+};
+
+namespace {
+
+struct XArgs {
+    const float *g[kMaxRanks];
+    uint32_t *peer_flags[kMaxRanks];
+    const uint32_t *my_flags;
+    int rank, world, wait;
+    uint32_t step;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float4 ld_peer(const float *p) {          // never served from a stale L1 line
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ float adam_one(float &p, float g, float &m, float &v, float alpha, float beta1, float beta2, float eps) {
+    m += (g - m) * (1.f - beta1);            // TF 1.12 ApplyAdam functor, as adam_kernel in fb_qnet.cu
+    v += (g * g - v) * (1.f - beta2);
+    p -= (m * alpha) / (sqrtf(v) + eps);
+    return p;
+}
+
+__global__ void __launch_bounds__(256) adam_xreduce_kernel(float *__restrict__ params, float *__restrict__ am, float *__restrict__ av, size_t n,
+                                                           const XArgs x, float alpha, float beta1, float beta2, float eps, float grad_scale,
+                                                           float *__restrict__ reduced_out) {
+    if (x.wait) {
+        if (blockIdx.x == 0 && (int)threadIdx.x < x.world) {
+            __threadfence_system();
+            st_release_sys(x.peer_flags[threadIdx.x] + x.rank, x.step);
+        }
+        if ((int)threadIdx.x < x.world) {
+            uint32_t spins = 0;
+            while ((int32_t)(ld_acquire_sys(x.my_flags + threadIdx.x) - x.step) < 0)
+                if (++spins > (1u << 26)) __trap();
+        }
+        __syncthreads();
+    }
+    const size_t n4 = n >> 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 g = ld_peer(x.g[0] + 4 * i);
+        for (int q = 1; q < x.world; q++) {
+            float4 h = ld_peer(x.g[q] + 4 * i);
+            g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
+        }
+        g.x *= grad_scale; g.y *= grad_scale; g.z *= grad_scale; g.w *= grad_scale;
+        float4 p = reinterpret_cast<float4 *>(params)[i], m = reinterpret_cast<float4 *>(am)[i], v = reinterpret_cast<float4 *>(av)[i];
+        adam_one(p.x, g.x, m.x, v.x, alpha, beta1, beta2, eps); adam_one(p.y, g.y, m.y, v.y, alpha, beta1, beta2, eps);
+        adam_one(p.z, g.z, m.z, v.z, alpha, beta1, beta2, eps); adam_one(p.w, g.w, m.w, v.w, alpha, beta1, beta2, eps);
+        reinterpret_cast<float4 *>(params)[i] = p; reinterpret_cast<float4 *>(am)[i] = m; reinterpret_cast<float4 *>(av)[i] = v;
+        if (reduced_out) reinterpret_cast<float4 *>(reduced_out)[i] = g;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (size_t i = n4 * 4; i < n; i++) {                        // tail (n % 4 parameters)
+            float g = 0.f;
+            for (int q = 0; q < x.world; q++) g += __ldcv(x.g[q] + i);
+            g *= grad_scale;
+            adam_one(params[i], g, am[i], av[i], alpha, beta1, beta2, eps);
+            if (reduced_out) reduced_out[i] = g;
+        }
+}
+
+}  // namespace
+
+extern "C" int fb_dist_create(int rank, int world, long long n_floats, fb_dist **out) {
+    FB_REQUIRE(out != nullptr && world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world && n_floats > 0, "fb_dist_create: bad argument");
+    fb_dist *d = new (std::nothrow) fb_dist();
+    FB_REQUIRE(d != nullptr, "fb_dist_create: out of host memory");
+    d->rank = rank; d->world = world; d->n = (size_t)n_floats; d->n_opened = 0; d->step = 0;
+    const size_t bytes = ((size_t)n_floats * sizeof(float) + 255) / 256 * 256;
+    for (int k = 0; k < 2; k++) { FB_CUDA_OK(cudaMalloc(&d->xgrads[k], bytes)); FB_CUDA_OK(cudaMemset(d->xgrads[k], 0, bytes)); }
+    FB_CUDA_OK(cudaMalloc(&d->flags, 256));
+    FB_CUDA_OK(cudaMemset(d->flags, 0, 256));
+    for (int q = 0; q < kMaxRanks; q++) { d->peer_grads[0][q] = d->peer_grads[1][q] = nullptr; d->peer_flags[q] = nullptr; }
+    d->peer_grads[0][rank] = d->xgrads[0]; d->peer_grads[1][rank] = d->xgrads[1]; d->peer_flags[rank] = d->flags;
+    *out = d;
+    return FB_OK;
+}
+
+extern "C" int fb_dist_destroy(fb_dist *d) {
+    if (!d) return FB_OK;
+    for (int k = 0; k < d->n_opened; k++) cudaIpcCloseMemHandle(d->opened[k]);
+    cudaFree(d->xgrads[0]); cudaFree(d->xgrads[1]); cudaFree(d->flags);
+    delete d;
+    return FB_OK;
+}
+
+extern "C" int fb_dist_handle_bytes(void) { return 3 * (int)sizeof(cudaIpcMemHandle_t); }
+
+// this rank's three IPC handles (exchange buffer 0, exchange buffer 1, flags), fb_dist_handle_bytes() bytes
+extern "C" int fb_dist_handles(fb_dist *d, uint8_t *out_host) {
+    FB_REQUIRE(d != nullptr && out_host != nullptr, "fb_dist_handles: NULL argument");
+    cudaIpcMemHandle_t h[3];
+    FB_CUDA_OK(cudaIpcGetMemHandle(&h[0], d->xgrads[0]));
+    FB_CUDA_OK(cudaIpcGetMemHandle(&h[1], d->xgrads[1]));
+    FB_CUDA_OK(cudaIpcGetMemHandle(&h[2], d->flags));
+    memcpy(out_host, h, sizeof(h));
+    return FB_OK;
+}
+
+// all ranks' handles, rank-major (world x fb_dist_handle_bytes()); maps every peer's buffers into this process
+extern "C" int fb_dist_connect(fb_dist *d, const uint8_t *all_handles_host) {
+    FB_REQUIRE(d != nullptr && all_handles_host != nullptr, "fb_dist_connect: NULL argument");
+    for (int q = 0; q < d->world; q++) {
+        if (q == d->rank) continue;
+        cudaIpcMemHandle_t h[3];
+        memcpy(h, all_handles_host + (size_t)q * sizeof(h), sizeof(h));
+        void *p[3];
+        for (int k = 0; k < 3; k++) {
+            FB_CUDA_OK(cudaIpcOpenMemHandle(&p[k], h[k], cudaIpcMemLazyEnablePeerAccess));
+            d->opened[d->n_opened++] = p[k];
+        }
+        d->peer_grads[0][q] = (const float *)p[0]; d->peer_grads[1][q] = (const float *)p[1]; d->peer_flags[q] = (uint32_t *)p[2];
+    }
+    return FB_OK;
+}
+
+// test hook: several "ranks" living in one process (no IPC): rank q's buffers are given directly
+extern "C" int fb_dist_connect_local(fb_dist *d, int q, fb_dist *peer) {
+    FB_REQUIRE(d && peer && q >= 0 && q < d->world && peer->rank == q && peer->n == d->n, "fb_dist_connect_local: bad argument");
+    d->peer_grads[0][q] = peer->xgrads[0]; d->peer_grads[1][q] = peer->xgrads[1]; d->peer_flags[q] = peer->flags;
+    return FB_OK;
+}
+
+// device pointer of the exchange buffer the NEXT fb_dist_adam will read (write this step's gradients there)
+extern "C" int fb_dist_grads(fb_dist *d, int parity, float **out) {
+    FB_REQUIRE(d != nullptr && out != nullptr && (parity == 0 || parity == 1), "fb_dist_grads: bad argument");
+    *out = d->xgrads[parity];
+    return FB_OK;
+}
+extern "C" int fb_dist_parity(const fb_dist *d) { return d ? (int)(d->step & 1) : -1; }
+
+// One optimizer step over the SUM of all ranks' gradients (exchange buffer of the current parity).  wait = 0 skips the
+// publish / wait handshake (single-process tests whose "ranks" run one after the other on one GPU).
+extern "C" int fb_dist_adam(fb_dist *d, fb_qnet *net, float *params_dev, float *m_dev, float *v_dev, float alpha, float beta1, float beta2,
+                            float eps, float grad_scale, float *reduced_out_dev, int wait, void *stream) {
+    FB_REQUIRE(d && net && params_dev && m_dev && v_dev, "fb_dist_adam: NULL argument");
+    FB_REQUIRE((size_t)net->L.total == d->n, "fb_dist_adam: the exchange buffers were sized for another network");
+    const int par = (int)(d->step & 1);
+    XArgs x{};
+    for (int q = 0; q < d->world; q++) {
+        FB_REQUIRE(d->peer_grads[par][q] != nullptr && d->peer_flags[q] != nullptr, "fb_dist_adam: call fb_dist_connect first");
+        x.g[q] = d->peer_grads[par][q]; x.peer_flags[q] = d->peer_flags[q];
+    }
+    x.my_flags = d->flags; x.rank = d->rank; x.world = d->world; x.wait = wait; x.step = d->step + 1;
+    adam_xreduce_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(params_dev, m_dev, v_dev, d->n, x, alpha, beta1, beta2, eps, grad_scale, reduced_out_dev);
+    FB_CUDA_OK(cudaGetLastError());
+    d->step++;
+    for (int s = 0; s < 2; s++) if (net->packed_src[s] == params_dev) net->packed_src[s] = nullptr;
+    return FB_OK;
+}

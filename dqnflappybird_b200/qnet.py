@@ -84,6 +84,15 @@ class QNetwork:
         self.lr, self.beta1, self.beta2, self.adam_eps = np.float32(lr), np.float32(beta1), np.float32(beta2), np.float32(adam_eps)
         self.beta1_power, self.beta2_power = np.float32(beta1), np.float32(beta2)      # TF keeps these as fp32 variables
         self.adam_steps = 0
+        self.exchange = None                    # dist.PeerGradExchange once enable_peer_exchange() was called
+
+    def enable_peer_exchange(self, exchange=None):
+        """Multi-GPU: keep the gradient vector in an NVLink-mapped exchange buffer and let adam_step() sum every rank's
+        gradients from peer memory inside the Adam kernel (csrc/fb_dist.cu) instead of a separate all-reduce."""
+        from .dist import PeerGradExchange
+        self.exchange = exchange if exchange is not None else PeerGradExchange(self.n_params, self.device)
+        self.grads = self.exchange.grads
+        return self.exchange
 
     def __del__(self):
         try:
@@ -169,9 +178,13 @@ class QNetwork:
         """One tf.train.AdamOptimizer step on self.params with self.grads (TF-1 ApplyAdam)."""
         one = np.float32(1)
         alpha = np.float32(self.lr * np.sqrt(one - self.beta2_power) / (one - self.beta1_power))
-        _lib.check(self._L.fb_qnet_adam(self._h, self.params.data_ptr(), self.grads.data_ptr(), self.adam_m.data_ptr(),
-                                        self.adam_v.data_ptr(), float(alpha), float(self.beta1), float(self.beta2),
-                                        float(self.adam_eps), float(grad_scale), self._stream()), "fb_qnet_adam")
+        if self.exchange is not None:           # sum over ranks + Adam in one kernel; then switch to the other buffer
+            self.exchange.adam(self, alpha, grad_scale, wait=self.exchange.world > 1 and not getattr(self.exchange, "no_wait", False))
+            self.grads = self.exchange.grads
+        else:
+            _lib.check(self._L.fb_qnet_adam(self._h, self.params.data_ptr(), self.grads.data_ptr(), self.adam_m.data_ptr(),
+                                            self.adam_v.data_ptr(), float(alpha), float(self.beta1), float(self.beta2),
+                                            float(self.adam_eps), float(grad_scale), self._stream()), "fb_qnet_adam")
         self.beta1_power = np.float32(self.beta1_power * self.beta1)
         self.beta2_power = np.float32(self.beta2_power * self.beta2)
         self.adam_steps += 1

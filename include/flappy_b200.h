@@ -198,6 +198,24 @@ int fb_qnet_adam(fb_qnet *net, float *params_dev, const float *grads_dev, float 
 /* target_replace_op (BrainDQNNature.py:107-111) */
 int fb_qnet_sync_target(fb_qnet *net, float *target_dev, const float *params_dev, void *stream);
 
+/* ---- multi-GPU gradient exchange fused with Adam (the one exchange step of the path: the sum of the per-shard
+ * gradients of the replicated learner).  One process per GPU; each rank's gradient vector lives in an exchange
+ * buffer the peers map through CUDA IPC; fb_dist_adam publishes this rank's step, waits for every rank's, sums the
+ * gradients of ranks 0..G-1 in rank order straight from peer memory over NVLink and applies TF-1 Adam in the same kernel
+ * (bitwise identical parameters on every rank).  Buffers alternate by step parity: write the gradients of the next step to
+ * fb_dist_grads(d, fb_dist_parity(d)). */
+typedef struct fb_dist fb_dist;
+int fb_dist_create(int rank, int world, long long n_floats, fb_dist **out);
+int fb_dist_destroy(fb_dist *d);
+int fb_dist_handle_bytes(void);
+int fb_dist_handles(fb_dist *d, uint8_t *out_host);                 /* this rank's IPC handles */
+int fb_dist_connect(fb_dist *d, const uint8_t *all_handles_host);   /* world x fb_dist_handle_bytes(), rank-major */
+int fb_dist_connect_local(fb_dist *d, int q, fb_dist *peer);        /* test hook: "ranks" inside one process */
+int fb_dist_grads(fb_dist *d, int parity, float **out_dev_ptr);
+int fb_dist_parity(const fb_dist *d);
+int fb_dist_adam(fb_dist *d, fb_qnet *net, float *params_dev, float *m_dev, float *v_dev, float alpha, float beta1, float beta2,
+                 float eps, float grad_scale, float *reduced_out_dev /* may be NULL */, int wait, void *stream);
+
 /* ---- replay memory: the deque + random.sample of BrainDQN.py:69-72,197-201 and the SumTree / Memory of
  * BrainPrioritizedReplyDQN.py:32-151, over the env's own frame ring (no frame is copied on append).
  * Transition k >= 1 of env e is (s_{k-1}, a_k, r_k, s_k, term_k), s_k = frames k-3..k of the ring
