@@ -528,6 +528,8 @@ extern "C" int fb_qnet_loss_backward(fb_qnet *n, int variant, const float *param
 extern "C" int fb_qnet_adam(fb_qnet *n, float *params_dev, const float *grads_dev, float *m_dev, float *v_dev, float alpha,
                             float beta1, float beta2, float eps, float grad_scale, void *stream) {
     FB_REQUIRE(n && params_dev && grads_dev && m_dev && v_dev, "fb_qnet_adam: NULL argument");
+    if (n->precision == FB_PRECISION_BF16)    // the same update, plus the bf16 operand copies of what it writes
+        return tc_adam(n, params_dev, grads_dev, m_dev, v_dev, alpha, beta1, beta2, eps, grad_scale, (cudaStream_t)stream);
     size_t cnt = (size_t)n->L.total;
     adam_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params_dev, grads_dev, m_dev, v_dev, cnt, alpha, beta1, beta2, eps, grad_scale);
     FB_CUDA_OK(cudaGetLastError());

@@ -60,6 +60,8 @@ template <int BN, int MODE, class EP>
 __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
                                                            const __grid_constant__ CUtensorMap mapB, const GemmParams g, const EP ep) {
     constexpr uint32_t A_BYTES = 128 * 64 * 2, B_BYTES = BN * 64 * 2, STAGE = A_BYTES + B_BYTES;
+    // MODE 0: A and B K-major.  MODE 1: A and B MN-major (contraction over rows).  MODE 2: A K-major, B MN-major
+    // (B = a row-major [K][N] matrix used as stored: fc1 forward reads W_fc1 [1600][H] without a transposed copy).
     constexpr uint32_t B_LAYOUT = (MODE == 1 && BN == 32) ? tc::kSwizzle64 : tc::kSwizzle128;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[kStages], bar_empty[kStages], bar_accum;
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
     const int mt = blockIdx.x, n0 = blockIdx.y * BN;
 
     int nkb, p_begin = 0, kb0 = 0;
-    if (MODE == 0) { kb0 = blockIdx.z * g.kper; nkb = min(g.kper, g.nkb - kb0); }
+    if (MODE != 1) { kb0 = blockIdx.z * g.kper; nkb = min(g.kper, g.nkb - kb0); }
     else {
         p_begin = blockIdx.z * g.klen;
         int len = min(g.klen, g.p_total - p_begin);
@@ -103,6 +105,10 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
                 if (MODE == 0) {
                     tc::tma_load_2d(sa, &mapA, g.a_col[kb0 + kb], mt * 128 + g.a_rowoff[kb0 + kb], full);
                     tc::tma_load_2d(sb, &mapB, (kb0 + kb) * 64, n0, full);
+                } else if (MODE == 2) {
+                    tc::tma_load_2d(sa, &mapA, g.a_col[kb0 + kb], mt * 128 + g.a_rowoff[kb0 + kb], full);
+                    tc::tma_load_2d(sb, &mapB, n0, (kb0 + kb) * 64, full);
+                    if (BN == 128) tc::tma_load_2d(sb + 8192, &mapB, n0 + 64, (kb0 + kb) * 64, full);
                 } else {
                     const int p = p_begin + kb * 64;
                     tc::tma_load_2d(sa, &mapA, g.a2_col[mt][0], p + g.a2_rowoff[mt][0], full);
@@ -114,7 +120,7 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = tc::instr_desc_bf16(128, BN, MODE, MODE);
+            constexpr uint32_t idesc = tc::instr_desc_bf16(128, BN, MODE == 1, MODE != 0);
             const uint32_t ahi = tc::smem_desc_hi(g.sbo_a, tc::kSwizzle128), bhi = tc::smem_desc_hi(g.sbo_b, B_LAYOUT);
             const uint32_t a_lo0 = tc::smem_desc_lo(smem, g.lbo_a), b_lo0 = tc::smem_desc_lo(smem + A_BYTES, g.lbo_b);
             const uint32_t ka = g.kstep_a >> 4, kbs = g.kstep_b >> 4;
@@ -144,7 +150,7 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
 #pragma unroll
                 for (int i = 0; i < 16; i++) v[i] = 0.f;
             }
-            ep(row, n0 + c0, v, (int)blockIdx.z);
+            ep(row, n0 + c0, v, (int)blockIdx.z, nullptr);
         }
     }
     tc::tc_fence_before();
@@ -190,42 +196,45 @@ __device__ __forceinline__ void load_bf16x16(const bf16 *src, float (&v)[16]) {
     }
 }
 
+// An epilogue sees 16 consecutive fp32 columns of one output row; `bs` is the layer bias staged in shared memory by the
+// kernel when the functor asks for it (bias != nullptr) -- a global load per column per tile was what bounded the tiles.
 struct EpiConv1 {               // rows on the 21-grid -> Z1 [B*441][32] = relu(conv + b), zeros at invalid positions
     bf16 *z1; const float *bias; int rows;
-    __device__ void operator()(int row, int col, float (&v)[16], int) const {
+    __device__ void operator()(int row, int col, float (&v)[16], int, const float *bs) const {
         if (row >= rows) return;
         int p = row % kP1;
         bool ok = (p / kG1) < 20 && (p % kG1) < 20;
 #pragma unroll
-        for (int i = 0; i < 16; i++) v[i] = ok ? fmaxf(v[i] + __ldg(bias + col + i), 0.f) : 0.f;
+        for (int i = 0; i < 16; i++) v[i] = ok ? fmaxf(v[i] + bs[col + i], 0.f) : 0.f;
         store_bf16x16(z1 + (size_t)row * kC1 + col, v);
     }
 };
 struct EpiGrid7 {               // conv2: rows on the 7-grid -> A2 [B*49][64], zeros at invalid positions
     bf16 *out; const float *bias; int rows;
-    __device__ void operator()(int row, int col, float (&v)[16], int) const {
+    __device__ void operator()(int row, int col, float (&v)[16], int, const float *bs) const {
         if (row >= rows) return;
         int p = row % kP2;
         bool ok = (p / kG2) < 5 && (p % kG2) < 5;
 #pragma unroll
-        for (int i = 0; i < 16; i++) v[i] = ok ? fmaxf(v[i] + __ldg(bias + col + i), 0.f) : 0.f;
+        for (int i = 0; i < 16; i++) v[i] = ok ? fmaxf(v[i] + bs[col + i], 0.f) : 0.f;
         store_bf16x16(out + (size_t)row * 64 + col, v);
     }
 };
 struct EpiConv3 {               // rows on the 7-grid -> dense A3 [B][25][64] (TF flatten order h,w,c)
     bf16 *a3; const float *bias; int rows;
-    __device__ void operator()(int row, int col, float (&v)[16], int) const {
+    __device__ void operator()(int row, int col, float (&v)[16], int, const float *bs) const {
         if (row >= rows) return;
         int b = row / kP2, p = row - b * kP2, oh = p / kG2, ow = p - oh * kG2;
         if (oh >= 5 || ow >= 5) return;
 #pragma unroll
-        for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i] + __ldg(bias + col + i), 0.f);
+        for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i] + bs[col + i], 0.f);
         store_bf16x16(a3 + ((size_t)b * 25 + oh * 5 + ow) * 64 + col, v);
     }
 };
 struct EpiFc1Dgrad {            // dA3 [B][1600] masked by relu(a3) -> dZ3 on the 7-grid [B*49][64]
     bf16 *dz3; const bf16 *a3; int B;
-    __device__ void operator()(int row, int col, float (&v)[16], int) const {
+    static constexpr const float *bias = nullptr;
+    __device__ void operator()(int row, int col, float (&v)[16], int, const float *) const {
         if (row >= B) return;
         float a[16];
         load_bf16x16(a3 + (size_t)row * kFlat + col, a);
@@ -237,7 +246,8 @@ struct EpiFc1Dgrad {            // dA3 [B][1600] masked by relu(a3) -> dZ3 on th
 };
 struct EpiConv3Dgrad {          // dA2 on the 7-grid masked by relu(a2) -> dZ2 [B*49][64], zeros at invalid positions
     bf16 *dz2; const bf16 *a2; int rows;
-    __device__ void operator()(int row, int col, float (&v)[16], int) const {
+    static constexpr const float *bias = nullptr;
+    __device__ void operator()(int row, int col, float (&v)[16], int, const float *) const {
         if (row >= rows) return;
         int p = row % kP2;
         bool ok = (p / kG2) < 5 && (p % kG2) < 5;
@@ -250,14 +260,16 @@ struct EpiConv3Dgrad {          // dA2 on the 7-grid masked by relu(a2) -> dZ2 [
 };
 struct EpiStoreBf16 {           // conv2 dgrad: dP2 [B*49][128]
     bf16 *out; int rows, ld;
-    __device__ void operator()(int row, int col, float (&v)[16], int) const {
+    static constexpr const float *bias = nullptr;
+    __device__ void operator()(int row, int col, float (&v)[16], int, const float *) const {
         if (row >= rows) return;
         store_bf16x16(out + (size_t)row * ld + col, v);
     }
 };
 struct EpiStoreF32 {            // weight-gradient partials [split][rows][ld] and the self-test
     float *out; int rows, ld; size_t split_stride;
-    __device__ void operator()(int row, int col, float (&v)[16], int split) const {
+    static constexpr const float *bias = nullptr;
+    __device__ void operator()(int row, int col, float (&v)[16], int split, const float *) const {
         if (row >= rows) return;
         float4 *d = reinterpret_cast<float4 *>(out + (size_t)split * split_stride + (size_t)row * ld + col);
 #pragma unroll
@@ -376,59 +388,50 @@ struct PackedWeights {
     bf16 *w1p;      // [32][256]   n, (tap, r, s, c)            conv1 forward  Bt
     bf16 *w2p;      // [64][512]   n, (tap, r, s, c)            conv2 forward  Bt
     bf16 *w3p;      // [64][576]   n, (kh, kw, c)               conv3 forward  Bt
-    bf16 *wf1p;     // [H][1600]   n, k                         fc1 forward    Bt
-    bf16 *wf1n;     // [1600][H]   k, n   (as stored)           fc1 dgrad      Bt
+    bf16 *wf1n;     // [1600][H]   k, n   (as stored)           fc1 forward B (MN-major) and fc1 dgrad Bt
     bf16 *w3d;      // [64][576]   c, (kh, kw, o)               conv3 dgrad    Bt
     bf16 *w2d;      // [128][256]  (r, s, c), (tap, o)          conv2 dgrad    Bt
 };
+// parameter i (TF variable order) -> its bf16 operand copies
+__device__ __forceinline__ void scatter_packed(int i, float val, const QnetLayout &L, const PackedWeights &pw, int fwd_only) {
+    const bf16 v = __float2bfloat16(val);
+    if (i < L.b1) {                         // W1 [kh][kw][c][n]
+        int e = i - L.w1, n = e & 31, c = (e >> 5) & 3, kw = (e >> 7) & 7, kh = e >> 10;
+        int k = ((kh >> 2) * 2 + (kw >> 2)) * 64 + (kh & 3) * 16 + (kw & 3) * 4 + c;
+        pw.w1p[n * kK1 + k] = v;
+    } else if (i >= L.w2 && i < L.b2) {     // W2 [kh][kw][c][o]
+        int e = i - L.w2, o = e & 63, c = (e >> 6) & 31, kw = (e >> 11) & 3, kh = e >> 13;
+        int t = (kh >> 1) * 2 + (kw >> 1), j = (kh & 1) * 64 + (kw & 1) * 32 + c;
+        pw.w2p[o * kK2 + t * 128 + j] = v;
+        if (!fwd_only) pw.w2d[j * 256 + t * 64 + o] = v;
+    } else if (i >= L.w3 && i < L.b3) {     // W3 [t][c][o]
+        int e = i - L.w3, o = e & 63, c = (e >> 6) & 63, t = e >> 12;
+        pw.w3p[o * kK3 + t * 64 + c] = v;
+        if (!fwd_only) pw.w3d[c * kK3 + t * 64 + o] = v;
+    } else if (i >= L.wf1 && i < L.bf1) {   // W_fc1 [k][n]: same index
+        pw.wf1n[i - L.wf1] = v;
+    }
+}
 __global__ void pack_weights_kernel(const float *params, QnetLayout L, PackedWeights pw, int fwd_only) {
     tc::pdl_wait();
     tc::pdl_launch();
-    const int H = L.hidden;
-    const int n1 = kC1 * kK1, n2 = kC2 * kK2, n3 = kC3 * kK3, nf = kFlat * H;
-    const int total = fwd_only ? n1 + n2 + n3 + nf : n1 + n2 + n3 + nf + nf + n3 + 128 * 256;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        int e = i;
-        if (e < n1) {
-            int n = e >> 8, k = e & 255, t = k >> 6, j = k & 63, r = j >> 4, s = (j >> 2) & 3, c = j & 3;
-            int kh = 4 * (t >> 1) + r, kw = 4 * (t & 1) + s;
-            pw.w1p[e] = __float2bfloat16(params[L.w1 + ((kh * 8 + kw) * 4 + c) * kC1 + n]);
-            continue;
-        }
-        e -= n1;
-        if (e < n2) {
-            int n = e >> 9, k = e & 511, t = k >> 7, j = k & 127, r = j >> 6, s = (j >> 5) & 1, c = j & 31;
-            int kh = 2 * (t >> 1) + r, kw = 2 * (t & 1) + s;
-            pw.w2p[e] = __float2bfloat16(params[L.w2 + ((kh * 4 + kw) * 32 + c) * kC2 + n]);
-            continue;
-        }
-        e -= n2;
-        if (e < n3) {
-            int n = e / kK3, k = e - n * kK3;
-            pw.w3p[e] = __float2bfloat16(params[L.w3 + k * kC3 + n]);
-            continue;
-        }
-        e -= n3;
-        if (e < nf) {
-            int n = e / kFlat, k = e - n * kFlat;
-            pw.wf1p[e] = __float2bfloat16(params[L.wf1 + (size_t)k * H + n]);
-            continue;
-        }
-        e -= nf;
-        if (e < nf) { pw.wf1n[e] = __float2bfloat16(params[L.wf1 + e]); continue; }
-        e -= nf;
-        if (e < n3) {
-            int c = e / kK3, k = e - c * kK3, t = k >> 6, o = k & 63;
-            pw.w3d[e] = __float2bfloat16(params[L.w3 + (t * 64 + c) * kC3 + o]);
-            continue;
-        }
-        e -= n3;
-        {
-            int nn = e >> 8, k = e & 255, t = k >> 6, o = k & 63, r = nn >> 6, s = (nn >> 5) & 1, c = nn & 31;
-            int kh = 2 * (t >> 1) + r, kw = 2 * (t & 1) + s;
-            pw.w2d[e] = __float2bfloat16(params[L.w2 + ((kh * 4 + kw) * 32 + c) * kC2 + o]);
-        }
-    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.bf1; i += gridDim.x * blockDim.x) scatter_packed(i, params[i], L, pw, fwd_only);
+}
+
+// tf.train.AdamOptimizer step (TF 1.12 ApplyAdam, as adam_kernel in fb_qnet.cu) that also refreshes the bf16 operand
+// copies of the parameters it has just written, so the next training step starts without a pack kernel
+__global__ void adam_pack_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, int n,
+                                 float alpha, float beta1, float beta2, float eps, float grad_scale, QnetLayout L, PackedWeights pw) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float gi = g[i] * grad_scale;
+    float mi = m[i], vi = v[i];
+    mi += (gi - mi) * (1.f - beta1);
+    vi += (gi * gi - vi) * (1.f - beta2);
+    m[i] = mi; v[i] = vi;
+    float pi = p[i] - (mi * alpha) / (sqrtf(vi) + eps);
+    p[i] = pi;
+    scatter_packed(i, pi, L, pw, 0);
 }
 
 // column sums of bf16 matrices [rows][N] in row chunks -> part[chunk][N] (bias gradients; summed in order by
@@ -645,7 +648,7 @@ void set_mnmajor(GemmParams &g, int bn) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ state
-struct TcWeightMaps { CUtensorMap w1p, w2p, w3p, wf1p, wf1n, w3d, w2d; };
+struct TcWeightMaps { CUtensorMap w1p, w2p, w3p, wf1n, w3d, w2d; };
 struct FwdWs {                  // forward tensors of one network evaluation (bf16 unless noted), sized for max_batch
     bf16 *x2, *z1, *p2, *a2, *a3;
     float *parth, *h1;          // fc1 K-split partials, h1 (fp32, kept for the head backward)
@@ -732,7 +735,8 @@ int make_plan(fb_qnet *n, int B, TcPlan **out) {
     for (int k = 0; k < 8; k++) { int tp = k >> 1; p.conv2.kb_rowoff[k] = (tp >> 1) * kG2 + (tp & 1); p.conv2.kb_half[k] = k & 1; }
     p.conv3.n_tiles = p.conv2.n_tiles; p.conv3.slab_row0 = -8;                  // pad ring = the row before / after: offset -8
     for (int k = 0; k < 9; k++) { p.conv3.kb_rowoff[k] = (k / 3) * kG2 + (k % 3); p.conv3.kb_half[k] = 0; }
-    set_kmajor(p.fc1); p.fc1.nkb = 25; p.fc1.kper = 25 / kFc1Splits; p.sf = kFc1Splits;
+    set_kmajor(p.fc1); p.fc1.lbo_b = 8192; p.fc1.sbo_b = 1024; p.fc1.kstep_b = 2048;     // B = W_fc1 as stored (MN-major)
+    p.fc1.nkb = 25; p.fc1.kper = 25 / kFc1Splits; p.sf = kFc1Splits;
     for (int k = 0; k < 25; k++) { p.fc1.a_rowoff[k] = 0; p.fc1.a_col[k] = k * 64; }
     // ---- data gradients
     set_kmajor(p.fc1_d); p.fc1_d.nkb = H / 64;
@@ -747,10 +751,10 @@ int make_plan(fb_qnet *n, int B, TcPlan **out) {
     p.s1 = plan_splits(P1, 74, &p.conv1_w.klen);
     p.conv1_w.acc_rowoff[0] = 0; p.conv1_w.acc_lbo[0] = 128; p.conv1_w.acc_rowoff[1] = kG1; p.conv1_w.acc_lbo[1] = 128;
     p.conv2_w.p_total = (int)P2; p.conv2_w.slab_row0 = 0;
-    p.s2 = plan_splits(P2, 28, &p.conv2_w.klen);
+    p.s2 = plan_splits(P2, 49, &p.conv2_w.klen);
     for (int a = 0; a < 4; a++) { p.conv2_w.acc_rowoff[a] = (a >> 1) * kG2 + (a & 1); p.conv2_w.acc_lbo[a] = 0; }
     p.conv3_w.p_total = (int)P2; p.conv3_w.slab_row0 = -8;
-    p.s3 = plan_splits(P2, 28, &p.conv3_w.klen);
+    p.s3 = plan_splits(P2, 49, &p.conv3_w.klen);
     {   // taps 0..8 at rows {0,1,2,7,8,9,14,15,16}; pairs (0,1) (2,3) (4,5) (6,7) (8,-): second atom LBO bytes further
         const int off[5] = {0, 2, 8, 14, 16};
         const uint32_t lbo[5] = {128, 5 * 128, 128, 128, 128};
@@ -793,7 +797,7 @@ int tc_state_create(fb_qnet *n) {
     FB_CUDA_OK(alloc_bf(&t->dh1, B * H));
     FB_CUDA_OK(alloc_bf(&t->dz3, B * kP2 * 64)); FB_CUDA_OK(alloc_bf(&t->dz2, B * kP2 * 64)); FB_CUDA_OK(alloc_bf(&t->dp2, B * kP2 * 128));
     FB_CUDA_OK(alloc_bf(&t->dz1, B * kP1 * 32));
-    t->cap1 = 76; t->cap2 = 30; t->cap3 = 30;              // plan_splits never exceeds its target
+    t->cap1 = 76; t->cap2 = 50; t->cap3 = 50;              // plan_splits never exceeds its target
     FB_CUDA_OK(alloc_f(&t->part1, t->cap1 * 256 * 32)); FB_CUDA_OK(alloc_f(&t->part2, t->cap2 * 512 * 64));
     FB_CUDA_OK(alloc_f(&t->part3, t->cap3 * 640 * 64));
     FB_CUDA_OK(alloc_f(&t->bp1, ((B * kP1 + kChunk1 - 1) / kChunk1) * 32)); FB_CUDA_OK(alloc_f(&t->bp2, ((B * kP2 + kChunk23 - 1) / kChunk23) * 64));
@@ -801,13 +805,12 @@ int tc_state_create(fb_qnet *n) {
     for (int s = 0; s < 2; s++) {
         PackedWeights &w = t->pw[s];
         FB_CUDA_OK(alloc_bf(&w.w1p, kC1 * kK1)); FB_CUDA_OK(alloc_bf(&w.w2p, kC2 * kK2)); FB_CUDA_OK(alloc_bf(&w.w3p, kC3 * kK3));
-        FB_CUDA_OK(alloc_bf(&w.wf1p, kFlat * H)); FB_CUDA_OK(alloc_bf(&w.wf1n, kFlat * H)); FB_CUDA_OK(alloc_bf(&w.w3d, kC3 * kK3));
+        FB_CUDA_OK(alloc_bf(&w.wf1n, kFlat * H)); FB_CUDA_OK(alloc_bf(&w.w3d, kC3 * kK3));
         FB_CUDA_OK(alloc_bf(&w.w2d, 128 * 256));
         TcWeightMaps &m = t->wm[s];
         if ((rc = make_map(&m.w1p, w.w1p, kC1, kK1, 64, 32))) return rc;
         if ((rc = make_map(&m.w2p, w.w2p, kC2, kK2, 64, 64))) return rc;
         if ((rc = make_map(&m.w3p, w.w3p, kC3, kK3, 64, 64))) return rc;
-        if ((rc = make_map(&m.wf1p, w.wf1p, (long long)H, kFlat, 64, 128))) return rc;
         if ((rc = make_map(&m.wf1n, w.wf1n, kFlat, (long long)H, 64, 64))) return rc;
         if ((rc = make_map(&m.w3d, w.w3d, kC3, kK3, 64, 64))) return rc;
         if ((rc = make_map(&m.w2d, w.w2d, 128, 256, 64, 128))) return rc;
@@ -836,7 +839,7 @@ void tc_state_destroy(fb_qnet *n) {
     for (void *p : ps) cudaFree(p);
     for (int s = 0; s < 2; s++) {
         PackedWeights &w = t->pw[s];
-        void *ws[] = {w.w1p, w.w2p, w.w3p, w.wf1p, w.wf1n, w.w3d, w.w2d};
+        void *ws[] = {w.w1p, w.w2p, w.w3p, w.wf1n, w.w3d, w.w2d};
         for (void *p : ws) cudaFree(p);
     }
     for (auto &e : t->ev) if (e) cudaEventDestroy(e);
@@ -849,6 +852,18 @@ void tc_state_destroy(fb_qnet *n) {
 int tc_pack_weights(fb_qnet *n, const float *params_dev, int slot, cudaStream_t st) {
     FB_REQUIRE(n->tc != nullptr && (slot == 0 || slot == 1), "tc_pack_weights: bad argument");
     FB_CUDA_OK(tc::launch_pdl(pack_weights_kernel, dim3(592), dim3(256), 0, st, params_dev, n->L, n->tc->pw[slot], slot == 1 ? 1 : 0));
+    return FB_OK;
+}
+
+int tc_adam(fb_qnet *n, float *params_dev, const float *grads_dev, float *m_dev, float *v_dev, float alpha, float beta1, float beta2,
+            float eps, float grad_scale, cudaStream_t st) {
+    FB_REQUIRE(n->tc != nullptr, "tc_adam: no tensor-core state");
+    const int cnt = n->L.total;
+    adam_pack_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(params_dev, grads_dev, m_dev, v_dev, cnt, alpha, beta1, beta2, eps, grad_scale, n->L,
+                                                        n->tc->pw[0]);
+    FB_CUDA_OK(cudaGetLastError());
+    if (n->packed_src[1] == params_dev) n->packed_src[1] = nullptr;
+    n->packed_src[0] = params_dev;          // slot 0 now mirrors the updated vector
     return FB_OK;
 }
 
@@ -876,11 +891,11 @@ int tc_forward(fb_qnet *n, int slot, int w, const float *params_dev, FrameView f
     const FwdWs &f = t->ws[w];
     const int P1 = B * kP1, P2 = B * kP2;
     FB_CUDA_OK(tc::launch_pdl(pack_x2_kernel, dim3((unsigned)(((size_t)P1 * 8 + 255) / 256)), dim3(256), 0, st, fv, B, f.x2));
-    FB_CUDA_OK((launch_tc_conv<32, kSlab1, 1, 4, 6>(p->x2_s[w], wm.w1p, p->conv1, t->n_sms, EpiConv1{f.z1, params_dev + L.b1, P1}, st)));
+    FB_CUDA_OK((launch_tc_conv<32, kSlab1, 1, 4, 6, 1>(p->x2_s[w], wm.w1p, p->conv1, t->n_sms, EpiConv1{f.z1, params_dev + L.b1, P1}, st)));
     FB_CUDA_OK(tc::launch_pdl(pool_pack_kernel, dim3((unsigned)(((size_t)B * 36 * 16 + 255) / 256)), dim3(256), 0, st, f.z1, B, f.p2));
-    FB_CUDA_OK((launch_tc_conv<64, kSlab2, 2, 8, 3>(p->p2_s[w], wm.w2p, p->conv2, t->n_sms, EpiGrid7{f.a2, params_dev + L.b2, P2}, st)));
-    FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4>(p->a2_s[w], wm.w3p, p->conv3, t->n_sms, EpiConv3{f.a3, params_dev + L.b3, P2}, st)));
-    FB_CUDA_OK((launch_tc_gemm<128, 0>(p->a3_k[w], wm.wf1p, p->fc1, dim3((B + 127) / 128, L.hidden / 128, p->sf),
+    FB_CUDA_OK((launch_tc_conv<64, kSlab2, 2, 8, 3, 1>(p->p2_s[w], wm.w2p, p->conv2, t->n_sms, EpiGrid7{f.a2, params_dev + L.b2, P2}, st)));
+    FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4, 1>(p->a2_s[w], wm.w3p, p->conv3, t->n_sms, EpiConv3{f.a3, params_dev + L.b3, P2}, st)));
+    FB_CUDA_OK((launch_tc_gemm<128, 2>(p->a3_k[w], wm.wf1n, p->fc1, dim3((B + 127) / 128, L.hidden / 128, p->sf),
                                        EpiStoreF32{f.parth, B, L.hidden, (size_t)n->max_batch * L.hidden}, st)));
     FB_CUDA_OK(tc::launch_pdl(fc1_head_kernel, dim3(B), dim3(128), 0, st, f.parth, p->sf, (size_t)n->max_batch * L.hidden, params_dev, L, B,
                               f.h1, q_out));
@@ -930,21 +945,20 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     FB_CUDA_OK((launch_tc_gemm<64, 0>(p->dh1_k, wm.wf1n, p->fc1_d, dim3((B + 127) / 128, kFlat / 64, 1), EpiFc1Dgrad{t->dz3, f.a3, B}, st)));
     FB_CUDA_OK(fork(st, sx));
     FB_CUDA_OK((launch_tc_wgrad<64, 5, kSlabW3, 1, 6>(p->a2_w, p->dz3_b, p->conv3_w, p->s3, EpiStoreF32{t->part3, 640, 64, (size_t)640 * 64}, sx)));
-    FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4>(p->dz3_s, wm.w3d, p->conv3_d, t->n_sms, EpiConv3Dgrad{t->dz2, f.a2, P2}, st)));
+    FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4, 1>(p->dz3_s, wm.w3d, p->conv3_d, t->n_sms, EpiConv3Dgrad{t->dz2, f.a2, P2}, st)));
     FB_CUDA_OK(fork(st, sx));
     FB_CUDA_OK((launch_tc_wgrad<64, 4, kSlabW2, 2, 4>(p->p2_w, p->dz2_b, p->conv2_w, p->s2, EpiStoreF32{t->part2, 512, 64, (size_t)512 * 64}, sx)));
-    FB_CUDA_OK((launch_tc_conv<128, kSlab2, 1, 4, 4>(p->dz2_s, wm.w2d, p->conv2_d, t->n_sms, EpiStoreBf16{t->dp2, P2, 128}, st)));
+    FB_CUDA_OK((launch_tc_conv<128, kSlab2, 1, 4, 4, 1>(p->dz2_s, wm.w2d, p->conv2_d, t->n_sms, EpiStoreBf16{t->dp2, P2, 128}, st)));
     FB_CUDA_OK(tc::launch_pdl(unpool_relu_kernel_tc, dim3((unsigned)(((size_t)B * 400 + 255) / 256)), dim3(256), 0, st, f.z1, t->dp2, B, t->dz1));
-    FB_CUDA_OK(fork(st, sx));
-    // bias gradients = column sums of the dZ tensors (aux) beside the conv1 weight gradient (no input gradient there)
+    // conv1 weight gradient (no input gradient there), then the bias gradients = column sums of the dZ tensors
+    FB_CUDA_OK((launch_tc_wgrad<32, 2, kSlabW1, 1, 6>(p->x2_w, p->dz1_b, p->conv1_w, p->s1, EpiStoreF32{t->part1, 256, 32, (size_t)256 * 32}, st)));
     const int c1 = (P1 + kChunk1 - 1) / kChunk1, c23 = (P2 + kChunk23 - 1) / kChunk23;
     ColsumJobs cj{};
     cj.njobs = 3;
     cj.j[0] = ColsumJob{t->dz1, t->bp1, P1, 32, kChunk1, 0};
     cj.j[1] = ColsumJob{t->dz2, t->bp2, P2, 64, kChunk23, c1};
     cj.j[2] = ColsumJob{t->dz3, t->bp3, P2, 64, kChunk23, c1 + c23};
-    FB_CUDA_OK(tc::launch_pdl(colsum_kernel, dim3(c1 + 2 * c23), dim3(256), 0, sx, cj));
-    FB_CUDA_OK((launch_tc_wgrad<32, 2, kSlabW1, 1, 6>(p->x2_w, p->dz1_b, p->conv1_w, p->s1, EpiStoreF32{t->part1, 256, 32, (size_t)256 * 32}, st)));
+    FB_CUDA_OK(tc::launch_pdl(colsum_kernel, dim3(c1 + 2 * c23), dim3(256), 0, st, cj));
     FB_CUDA_OK(fork(sx, st));
     FinalizeArgs fa{t->part1, t->part2, t->part3, p->s1, p->s2, p->s3, t->bp1, t->bp2, t->bp3, c1, c23, c23};
     FB_CUDA_OK(tc::launch_pdl(finalize_grads_kernel, dim3(296), dim3(256), 0, st, fa, L, a.grads));
@@ -1024,13 +1038,13 @@ extern "C" int fb_debug_tc_kernel(fb_qnet *n, int which, int B, int reps, const 
     const int H = L.hidden, P1 = B * kP1, P2 = B * kP2;
     for (int r = 0; r < reps; r++) {
         switch (which) {
-            case 0: FB_CUDA_OK((launch_tc_conv<32, kSlab1, 1, 4, 6>(p->x2_s[0], wm.w1p, p->conv1, t->n_sms, EpiConv1{f.z1, params_dev + L.b1, P1}, st))); break;
-            case 1: FB_CUDA_OK((launch_tc_conv<64, kSlab2, 2, 8, 3>(p->p2_s[0], wm.w2p, p->conv2, t->n_sms, EpiGrid7{f.a2, params_dev + L.b2, P2}, st))); break;
-            case 2: FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4>(p->a2_s[0], wm.w3p, p->conv3, t->n_sms, EpiConv3{f.a3, params_dev + L.b3, P2}, st))); break;
-            case 3: FB_CUDA_OK((launch_tc_gemm<128, 0>(p->a3_k[0], wm.wf1p, p->fc1, dim3((B + 127) / 128, H / 128, p->sf),
+            case 0: FB_CUDA_OK((launch_tc_conv<32, kSlab1, 1, 4, 6, 1>(p->x2_s[0], wm.w1p, p->conv1, t->n_sms, EpiConv1{f.z1, params_dev + L.b1, P1}, st))); break;
+            case 1: FB_CUDA_OK((launch_tc_conv<64, kSlab2, 2, 8, 3, 1>(p->p2_s[0], wm.w2p, p->conv2, t->n_sms, EpiGrid7{f.a2, params_dev + L.b2, P2}, st))); break;
+            case 2: FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4, 1>(p->a2_s[0], wm.w3p, p->conv3, t->n_sms, EpiConv3{f.a3, params_dev + L.b3, P2}, st))); break;
+            case 3: FB_CUDA_OK((launch_tc_gemm<128, 2>(p->a3_k[0], wm.wf1n, p->fc1, dim3((B + 127) / 128, H / 128, p->sf),
                                                        EpiStoreF32{f.parth, B, H, (size_t)n->max_batch * H}, st))); break;
             case 4: FB_CUDA_OK((launch_tc_wgrad<32, 2, kSlabW1, 1, 6>(p->x2_w, p->dz1_b, p->conv1_w, p->s1, EpiStoreF32{t->part1, 256, 32, (size_t)256 * 32}, st))); break;
-            case 5: FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4>(p->dz3_s, wm.w3d, p->conv3_d, t->n_sms, EpiConv3Dgrad{t->dz2, f.a2, P2}, st))); break;
+            case 5: FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4, 1>(p->dz3_s, wm.w3d, p->conv3_d, t->n_sms, EpiConv3Dgrad{t->dz2, f.a2, P2}, st))); break;
             case 6: FB_CUDA_OK((launch_tc_gemm<64, 0>(p->dh1_k, wm.wf1n, p->fc1_d, dim3((B + 127) / 128, kFlat / 64, 1), EpiFc1Dgrad{t->dz3, f.a3, B}, st))); break;
             default: FB_REQUIRE(false, "fb_debug_tc_kernel: which must be 0..6");
         }

@@ -26,17 +26,19 @@ struct ConvParams {
 // D[p][n] = sum_kb sum_c A[p + tap(kb)][64 half(kb) + c] * Bt[n][64 kb + c], persistent over tiles of 128 positions.
 // The whole Bt (NKB x BN x 64) stays resident in shared memory; slabs stream through S stages; two TMEM accumulators
 // let the epilogue of tile i overlap the MMAs of tile i+1.
-template <int BN, int SLAB_ROWS, int NHALF, int NKB, int S, class EP>
+template <int BN, int SLAB_ROWS, int NHALF, int NKB, int S, int T, class EP>
 __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                    const __grid_constant__ CUtensorMap mapB, const ConvParams g, const EP ep) {
     constexpr uint32_t HALF_BYTES = SLAB_ROWS * 128, STAGE = NHALF * HALF_BYTES, BBLK = BN * 128, B_BYTES = NKB * BBLK;
     static_assert(SLAB_ROWS % 8 == 0 && SLAB_ROWS <= 256, "slab rows: multiple of 8 (1024-byte stage alignment), one TMA box");
+    static_assert(S % T == 0 && 2 * T * BN <= 512, "a group of T tiles occupies T consecutive stages and T accumulators of a set");
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[S], bar_empty[S], bar_b, bar_acc_full[2], bar_acc_empty[2];
     __shared__ uint32_t tmem_slot;
+    __shared__ float bias_s[BN];
     const uint32_t smem_b = (tc::smem_u32(smem_raw) + 1023u) & ~1023u, smem_a = smem_b + B_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    constexpr uint32_t TMEM_COLS = 2 * T * BN <= 32 ? 32 : 2 * T * BN <= 64 ? 64 : 2 * T * BN <= 128 ? 128 : 2 * T * BN <= 256 ? 256 : 512;
 
     if (threadIdx.x == 0) {
         tc::tma_prefetch_desc(&mapA);
@@ -56,8 +58,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
         tc::mbar_expect_tx(tc::smem_u32(&bar_b), B_BYTES);
         for (int kb = 0; kb < NKB; kb++) tc::tma_load_2d(smem_b + kb * BBLK, &mapB, kb * 64, 0, tc::smem_u32(&bar_b));
     }
+    if (ep.bias != nullptr && threadIdx.x >= 64 && (int)threadIdx.x - 64 < BN) bias_s[threadIdx.x - 64] = ep.bias[threadIdx.x - 64];
     tc::pdl_wait();
     tc::pdl_launch();
+    __syncthreads();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -82,40 +86,62 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
             for (int kb = 0; kb < NKB; kb++) a_rel[kb] = (uint32_t)(g.kb_half[kb] * (int)HALF_BYTES + g.kb_rowoff[kb] * 128) >> 4;
             const uint32_t a_lo0 = tc::smem_desc_lo(smem_a, 16), b_lo0 = tc::smem_desc_lo(smem_b, 16);
             tc::mbar_wait(tc::smem_u32(&bar_b), 0);
-            int i = 0;
-            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, i++) {
-                const int s = i % S, as = i & 1;
-                tc::mbar_wait(tc::smem_u32(&bar_acc_empty[as]), ((i >> 1) & 1) ^ 1u);
-                tc::mbar_wait(tc::smem_u32(&bar_full[s]), (i / S) & 1);
+            // Tiles are taken T at a time, their MMAs issued round-robin over T accumulators.  Measured on the B200: T > 1
+            // does NOT help (conv1 forward 45 -> 50 us at 2048 samples) -- the per-MMA cost at N = 32 is the 4 KB A-operand
+            // read from shared memory (sm__pipe_tc_cycles_active 54 % vs tensor math 14 %), not an accumulator dependency --
+            // so every launch uses T = 1; the grouping is kept for wider-N layers.
+            int grp = 0;
+            for (int tile0 = blockIdx.x; tile0 < g.n_tiles; tile0 += T * gridDim.x, grp++) {
+                const int as = grp & 1;
+                int nt = 0;
+#pragma unroll
+                for (int t = 0; t < T; t++) nt += (tile0 + t * (int)gridDim.x < g.n_tiles) ? 1 : 0;
+                tc::mbar_wait(tc::smem_u32(&bar_acc_empty[as]), ((grp >> 1) & 1) ^ 1u);
+                for (int t = 0; t < nt; t++) {
+                    const int it = grp * T + t;
+                    tc::mbar_wait(tc::smem_u32(&bar_full[it % S]), (it / S) & 1);
+                }
                 tc::tc_fence_after();
-                const uint32_t a_lo = a_lo0 + s * (STAGE >> 4), d = tmem + as * BN;
+                const uint32_t s0 = (uint32_t)((grp * T) % S);
 #pragma unroll
                 for (int kb = 0; kb < NKB; kb++)
 #pragma unroll
                     for (int k = 0; k < 4; k++)
-                        tc::umma_bf16_lohi(d, a_lo + a_rel[kb] + 2 * k, dhi, b_lo0 + ((kb * BBLK + k * 32) >> 4), dhi, idesc, (kb | k) != 0);
-                tc::umma_commit(tc::smem_u32(&bar_empty[s]));
+#pragma unroll
+                        for (int t = 0; t < T; t++)
+                            if (t < nt)
+                                tc::umma_bf16_lohi(tmem + (as * T + t) * BN, a_lo0 + (s0 + t) * (STAGE >> 4) + a_rel[kb] + 2 * k, dhi,
+                                                   b_lo0 + ((kb * BBLK + k * 32) >> 4), dhi, idesc, (kb | k) != 0);
+                for (int t = 0; t < nt; t++) tc::umma_commit(tc::smem_u32(&bar_empty[(s0 + t) % S]));
                 tc::umma_commit(tc::smem_u32(&bar_acc_full[as]));
             }
         }
     } else {
         const int q = warp & 3;
-        int i = 0;
-        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, i++) {
-            const int as = i & 1;
-            tc::mbar_wait(tc::smem_u32(&bar_acc_full[as]), (i >> 1) & 1);
+        int grp = 0;
+        for (int tile0 = blockIdx.x; tile0 < g.n_tiles; tile0 += T * gridDim.x, grp++) {
+            const int as = grp & 1;
+            tc::mbar_wait(tc::smem_u32(&bar_acc_full[as]), (grp >> 1) & 1);
             tc::tc_fence_after();
-            const int row = tile * 128 + q * 32 + lane;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                float v[16];
-                tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), v);
-                if (c0 + 16 >= BN) {                 // accumulator drained: hand it back before the stores
-                    tc::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_acc_empty[as]));
+            for (int t = 0; t < T; t++) {
+                const int tile = tile0 + t * (int)gridDim.x;
+                const bool last = t == T - 1 || tile + (int)gridDim.x >= g.n_tiles;
+                if (tile < g.n_tiles) {
+                    const int row = tile * 128 + q * 32 + lane;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < BN; c0 += 32) {
+                        float v[32];
+                        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * T + t) * BN + c0), v);
+                        if (last && c0 + 32 >= BN) {         // accumulator set drained: hand it back before the stores
+                            tc::tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_acc_empty[as]));
+                        }
+                        ep(row, c0, *reinterpret_cast<float(*)[16]>(&v[0]), 0, bias_s);
+                        ep(row, c0 + 16, *reinterpret_cast<float(*)[16]>(&v[16]), 0, bias_s);
+                    }
                 }
-                ep(row, c0, v, 0);
             }
         }
     }
@@ -127,10 +153,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
 template <int BN, int SLAB_ROWS, int NHALF, int NKB, int S>
 constexpr size_t conv_smem_bytes() { return (size_t)NKB * BN * 128 + (size_t)S * NHALF * SLAB_ROWS * 128 + 1024; }
 
-template <int BN, int SLAB_ROWS, int NHALF, int NKB, int S, class EP>
+template <int BN, int SLAB_ROWS, int NHALF, int NKB, int S, int T, class EP>
 static cudaError_t launch_tc_conv(const CUtensorMap &ma, const CUtensorMap &mb, const ConvParams &g, int max_ctas, EP ep, cudaStream_t st) {
     static bool configured = false;
-    auto kern = tc_conv_kernel<BN, SLAB_ROWS, NHALF, NKB, S, EP>;
+    auto kern = tc_conv_kernel<BN, SLAB_ROWS, NHALF, NKB, S, T, EP>;
     constexpr size_t smem = conv_smem_bytes<BN, SLAB_ROWS, NHALF, NKB, S>();
     static_assert(smem <= 227 * 1024, "shared memory budget");
     if (!configured) {
@@ -208,10 +234,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_wgrad_kernel(const __grid_
                 tc::mbar_wait(tc::smem_u32(&bar_full[s]), (kb / S) & 1);
                 tc::tc_fence_after();
                 const uint32_t soff = s * (STAGE >> 4);
+                // k outer, accumulators inner (neutral on the B200: the MMA rate here is set by operand reads, see tc_conv_kernel)
 #pragma unroll
-                for (int a = 0; a < NACC; a++)
+                for (int k = 0; k < 4; k++)
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
+                    for (int a = 0; a < NACC; a++)
                         tc::umma_bf16_lohi(tmem + a * BN, a_lo0[a] + soff + k * 128, ahi, b_lo0 + soff + k * (B_KSTEP >> 4), bhi, idesc,
                                            (kb | k) != 0);
                 tc::umma_commit(tc::smem_u32(&bar_empty[s]));
@@ -232,7 +259,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_wgrad_kernel(const __grid_
 #pragma unroll
                     for (int i = 0; i < 16; i++) v[i] = 0.f;
                 }
-                ep(a * 128 + q * 32 + lane, c0, v, (int)blockIdx.x);
+                ep(a * 128 + q * 32 + lane, c0, v, (int)blockIdx.x, nullptr);
             }
     }
     tc::tc_fence_before();
