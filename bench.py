@@ -117,6 +117,29 @@ def cpu_port_frames_per_s(n_envs: int, n_steps: int, threads: int, seed: int = 1
     return n_envs * n_steps / dt, dt
 
 
+def cpu_port_updates_per_s(budget_s: float = 6.0):
+    """The reference's learner on the host cores: BrainDQNNature's update at ITS OWN minibatch of 32 (BrainDQN.py:22) as the
+    torch-CPU restatement of the TF-1.12 graph (oracle/qnet_oracle.py, float64 like the oracle; TensorFlow 1.12 is not
+    installable) -- target forward, online forward, backward, Adam, all host threads."""
+    import numpy as np
+    from oracle import qnet_oracle as qo
+    B = 32
+    rng = np.random.default_rng(0)
+    p = qo.init_params(512, False, seed=1); t = qo.init_params(512, False, seed=2)
+    x = (rng.random((B, 5, 80, 80)) < 0.2).astype(np.uint8) * 255
+    a = rng.integers(0, 2, B).astype(np.uint8)
+    r = rng.choice(np.array([0.1, 3.0, -3.0], np.float32), B); term = (r == -3.0).astype(np.uint8)
+    adam = qo.AdamTF1(len(p))
+    qo.loss_and_grads(1, p, t, x[:, 0:4], x[:, 1:5], a, r, term)
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        _, g, *_ = qo.loss_and_grads(1, p, t, x[:, 0:4], x[:, 1:5], a, r, term)
+        p = adam.step(p, g.astype(np.float32))
+        n += 1
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt
+
+
 def run_reference(args, rank: int, world: int):
     """--impl reference: the reference's CPU path for the same metric/config.  pygame and TensorFlow are
     not installable here and a Python reference cannot travel to the GPU box, so this arm times the
@@ -354,6 +377,12 @@ def bench_learner(args, rank, world, dev):
             us = e0.elapsed_time(e1) * 1e3 / reps
             kern[kb] = {"us": us, "tflops": 6553600 * kb / (us * 1e-6) / 1e12,
                         "hbm_gbs": kb * 441 * (128 + 64) / (us * 1e-6) / 1e9}
+    cpu_upd = None
+    if world == 1 and not args.no_cpu_baseline:
+        ups, n_done, dt = cpu_port_updates_per_s()
+        cpu_upd = {"value": ups, "unit": "updates/s", "minibatch": 32, "cores": os.cpu_count() or 1, "kind": "port",
+                   "sample": f"{n_done} BrainDQNNature updates of minibatch 32 in {dt:.1f} s: oracle/qnet_oracle.py (torch CPU float64 "
+                             "restatement of the TF-1.12 graph; TensorFlow 1.12 is not installable), all host threads"}
     flop_upd = (2 * FLOP_FWD + FLOP_BWD) * B
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -367,7 +396,7 @@ def bench_learner(args, rank, world, dev):
             "compute_path": brain.net.compute_path if hasattr(brain.net, "compute_path") else "fp32 CUDA-core implicit GEMM",
             "act_envs_per_s": N * world / (ms_act * 1e-3), "ms_per_act": ms_act,
             "act_tflops_per_gpu": N * FLOP_FWD / (ms_act * 1e-3) / 1e12,
-            "transitions_per_s": B * 1e3 / ms_upd, "scaling": args.learner_scaling,
+            "transitions_per_s": B * 1e3 / ms_upd, "scaling": args.learner_scaling, "cpu_baseline": cpu_upd,
             "gradient_exchange": ("none (1 GPU)" if world == 1 else
                                   "fused into Adam over NVLink peer memory (fb_dist_adam)" if brain.net.exchange is not None else "NCCL all-reduce"),
             "roofline": None if not kern else {

@@ -114,6 +114,7 @@ _SIGNATURES = {
     "fb_debug_host_step": ([_i32p, C.c_int, _u8p, C.c_int, C.c_uint64, C.c_uint64, _f32p, _u8p, _i32p], C.c_int),
     "fb_debug_host_obs": ([_i32p, C.c_int, _u8p], C.c_int),
     "fb_debug_host_mixed": ([_i32p], C.c_int),
+    "fb_debug_tc_mma_rate": ([C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp], C.c_int),
     "fb_debug_tc_kernel": ([_vp, C.c_int, C.c_int, C.c_int, _f32p, _vp], C.c_int),
     "fb_debug_tc_slab": ([C.c_int, C.c_int, _vp, _vp, _f32p, _vp], C.c_int),
     "fb_debug_tc_gemm": ([C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _f32p, _vp, _vp], C.c_int),

@@ -94,11 +94,12 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
     tc::pdl_launch();
 
     if (warp == 0) {
-        if (lane == 0) {
-            for (int kb = 0; kb < nkb; kb++) {
-                const int s = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
-                tc::mbar_wait(tc::smem_u32(&bar_empty[s]), ph ^ 1u);
+        const bool leader = tc::elect_one();
+        for (int kb = 0; kb < nkb; kb++) {
+            const int s = kb % kStages;
+            const uint32_t ph = (kb / kStages) & 1;
+            tc::mbar_wait(tc::smem_u32(&bar_empty[s]), ph ^ 1u);
+            if (leader) {
                 const uint32_t full = tc::smem_u32(&bar_full[s]);
                 const uint32_t sa = smem + s * STAGE, sb = sa + A_BYTES;
                 tc::mbar_expect_tx(full, STAGE);
@@ -117,9 +118,11 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
                     if (BN == 128) tc::tma_load_2d(sb + 8192, &mapB, n0 + 64, p, full);
                 }
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
+            const bool leader = tc::elect_one();
             constexpr uint32_t idesc = tc::instr_desc_bf16(128, BN, MODE == 1, MODE != 0);
             const uint32_t ahi = tc::smem_desc_hi(g.sbo_a, tc::kSwizzle128), bhi = tc::smem_desc_hi(g.sbo_b, B_LAYOUT);
             const uint32_t a_lo0 = tc::smem_desc_lo(smem, g.lbo_a), b_lo0 = tc::smem_desc_lo(smem + A_BYTES, g.lbo_b);
@@ -130,12 +133,16 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
                 tc::mbar_wait(tc::smem_u32(&bar_full[s]), ph);
                 tc::tc_fence_after();
                 const uint32_t soff = s * (STAGE >> 4);
+                if (leader) {
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    tc::umma_bf16_lohi(tmem, a_lo0 + soff + k * ka, ahi, b_lo0 + soff + k * kbs, bhi, idesc, (kb | k) != 0);
-                tc::umma_commit(tc::smem_u32(&bar_empty[s]));     // frees the stage once these MMAs have read it
+                    for (int k = 0; k < 4; k++)
+                        tc::umma_bf16_lohi(tmem, a_lo0 + soff + k * ka, ahi, b_lo0 + soff + k * kbs, bhi, idesc, (kb | k) != 0);
+                    tc::umma_commit(tc::smem_u32(&bar_empty[s]));     // frees the stage once these MMAs have read it
+                }
+                __syncwarp();
             }
-            tc::umma_commit(tc::smem_u32(&bar_accum));
+            if (leader) tc::umma_commit(tc::smem_u32(&bar_accum));
+            __syncwarp();
         }
     } else {
         const int q = warp & 3;                                    // TMEM lane quadrant this warp may read
@@ -1105,6 +1112,64 @@ extern "C" int fb_debug_tc_slab(int shift, int base_offset, const void *a_dev, c
     if ((rc = make_map(&mb, (const bf16 *)b_dev, 64, 64, 64, 64))) return rc;
     FB_CUDA_OK(cudaFuncSetAttribute(tc_slab_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 8192 + 1024));
     tc_slab_probe_kernel<<<1, 128, 32768 + 8192 + 1024, (cudaStream_t)stream>>>(ma, mb, shift, (uint32_t)base_offset, d_dev);
+    FB_CUDA_OK(cudaGetLastError());
+    return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ MMA rate probe
+// cycles per tcgen05.mma (M = 128, K = 16, bf16) as a function of N, operand major-ness and the number of independent
+// accumulators, on whatever bytes shared memory holds: `iters` back-to-back MMAs by one thread, one commit, clock64.
+namespace {
+__global__ void __launch_bounds__(128) tc_mma_rate_kernel(int n, int mn_major, int naccs, int iters, int same_operands, long long *cycles) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const uint32_t smem = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 48 * 1024 / 4; i += 128) reinterpret_cast<uint32_t *>(smem_raw)[i] = 0x3c003c00u;   // finite bf16s
+    if (threadIdx.x == 0) { tc::mbar_init(tc::smem_u32(&bar), 1); tc::fence_barrier_init(); }
+    if (warp == 0) tc::tmem_alloc(tc::smem_u32(&tmem_slot), 512);
+    tc::fence_proxy_async();
+    tc::tc_fence_before(); __syncthreads(); tc::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (warp == 1) {                                  // whole warp converged; one elected lane issues (CUTLASS style)
+        const uint32_t idesc = tc::instr_desc_bf16(128, n, mn_major, mn_major);
+        const uint32_t hi = tc::smem_desc_hi(1024, tc::kSwizzle128);
+        const uint32_t a0 = tc::smem_desc_lo(smem, mn_major ? 8192 : 16), b0 = tc::smem_desc_lo(smem + 16384, mn_major ? 8192 : 16);
+        const uint32_t step = same_operands ? 0 : (mn_major ? 128 : 2);      // K advance of one MMA, 16-byte units
+        const uint32_t d1 = naccs > 1 ? (uint32_t)n : 0, d2 = naccs > 2 ? 2u * n : 0, d3 = naccs > 3 ? 3u * n : d1;
+        uint32_t elected;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(elected));
+        long long t0 = clock64();
+        for (int i = 0; i < iters; i += 8) {
+            if (elected) {
+                tc::umma_bf16_lohi(tmem, a0, hi, b0, hi, idesc, 1);
+                tc::umma_bf16_lohi(tmem + d1, a0 + step, hi, b0 + step, hi, idesc, 1);
+                tc::umma_bf16_lohi(tmem + d2, a0 + 2 * step, hi, b0 + 2 * step, hi, idesc, 1);
+                tc::umma_bf16_lohi(tmem + d3, a0 + 3 * step, hi, b0 + 3 * step, hi, idesc, 1);
+                tc::umma_bf16_lohi(tmem, a0, hi, b0, hi, idesc, 1);
+                tc::umma_bf16_lohi(tmem + d1, a0 + step, hi, b0 + step, hi, idesc, 1);
+                tc::umma_bf16_lohi(tmem + d2, a0 + 2 * step, hi, b0 + 2 * step, hi, idesc, 1);
+                tc::umma_bf16_lohi(tmem + d3, a0 + 3 * step, hi, b0 + 3 * step, hi, idesc, 1);
+            }
+            __syncwarp();
+        }
+        long long t_issue = clock64();
+        if (elected) tc::umma_commit(tc::smem_u32(&bar));
+        __syncwarp();
+        tc::mbar_wait(tc::smem_u32(&bar), 0);
+        long long t1 = clock64();
+        if (elected) { cycles[0] = t1 - t0; cycles[1] = t_issue - t0; }
+    }
+    tc::tc_fence_before(); __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+}  // namespace
+
+extern "C" int fb_debug_tc_mma_rate(int n, int mn_major, int naccs, int iters, int same_operands, long long *cycles_dev, void *stream) {
+    FB_REQUIRE(cycles_dev && n >= 16 && n <= 256 && n % 16 == 0 && naccs >= 1 && naccs * n <= 512 && iters > 0, "fb_debug_tc_mma_rate: bad argument");
+    FB_CUDA_OK(cudaFuncSetAttribute(tc_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    tc_mma_rate_kernel<<<1, 128, 64 * 1024, (cudaStream_t)stream>>>(n, mn_major, naccs, iters, same_operands, cycles_dev);
     FB_CUDA_OK(cudaGetLastError());
     return FB_OK;
 }

@@ -11,6 +11,15 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a CONVERGED warp (the whole warp executes the surrounding loop and its waits; only the issue of
+// TMA / tcgen05.mma / commit is predicated).  Measured on the B200: an MMA issue loop run by a lone lane inside a
+// divergent branch sustains ~70-150 cycles per tcgen05.mma, the same sequence under elect.sync 40 (N = 32).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t e;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(e));
+    return e != 0;
+}
+
 // ---- mbarrier -------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));

@@ -64,20 +64,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
     __syncthreads();
 
     if (warp == 0) {
-        if (lane == 0) {
-            int i = 0;
-            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, i++) {
-                const int s = i % S;
-                tc::mbar_wait(tc::smem_u32(&bar_empty[s]), ((i / S) & 1) ^ 1u);
+        const bool leader = tc::elect_one();
+        int i = 0;
+        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, i++) {
+            const int s = i % S;
+            tc::mbar_wait(tc::smem_u32(&bar_empty[s]), ((i / S) & 1) ^ 1u);
+            if (leader) {
                 const uint32_t full = tc::smem_u32(&bar_full[s]);
                 tc::mbar_expect_tx(full, STAGE);
 #pragma unroll
                 for (int h = 0; h < NHALF; h++)
                     tc::tma_load_2d(smem_a + s * STAGE + h * HALF_BYTES, &mapA, h * 64, tile * 128 + g.slab_row0, full);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
+            const bool leader = tc::elect_one();
             constexpr uint32_t idesc = tc::instr_desc_bf16(128, BN, 0, 0);
             constexpr uint32_t dhi = tc::smem_desc_hi(1024, tc::kSwizzle128);
             // descriptor start fields, in 16-byte units: per K-block for A (tap row offset, column half), constant for B
@@ -103,17 +106,20 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
                 }
                 tc::tc_fence_after();
                 const uint32_t s0 = (uint32_t)((grp * T) % S);
+                if (leader) {
 #pragma unroll
-                for (int kb = 0; kb < NKB; kb++)
+                    for (int kb = 0; kb < NKB; kb++)
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
+                        for (int k = 0; k < 4; k++)
 #pragma unroll
-                        for (int t = 0; t < T; t++)
-                            if (t < nt)
-                                tc::umma_bf16_lohi(tmem + (as * T + t) * BN, a_lo0 + (s0 + t) * (STAGE >> 4) + a_rel[kb] + 2 * k, dhi,
-                                                   b_lo0 + ((kb * BBLK + k * 32) >> 4), dhi, idesc, (kb | k) != 0);
-                for (int t = 0; t < nt; t++) tc::umma_commit(tc::smem_u32(&bar_empty[(s0 + t) % S]));
-                tc::umma_commit(tc::smem_u32(&bar_acc_full[as]));
+                            for (int t = 0; t < T; t++)
+                                if (t < nt)
+                                    tc::umma_bf16_lohi(tmem + (as * T + t) * BN, a_lo0 + (s0 + t) * (STAGE >> 4) + a_rel[kb] + 2 * k, dhi,
+                                                       b_lo0 + ((kb * BBLK + k * 32) >> 4), dhi, idesc, (kb | k) != 0);
+                    for (int t = 0; t < nt; t++) tc::umma_commit(tc::smem_u32(&bar_empty[(s0 + t) % S]));
+                    tc::umma_commit(tc::smem_u32(&bar_acc_full[as]));
+                }
+                __syncwarp();
             }
         }
     } else {
@@ -208,10 +214,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_wgrad_kernel(const __grid_
     tc::pdl_launch();
 
     if (warp == 0) {
-        if (lane == 0) {
-            for (int kb = 0; kb < nkb; kb++) {
-                const int s = kb % S;
-                tc::mbar_wait(tc::smem_u32(&bar_empty[s]), ((kb / S) & 1) ^ 1u);
+        const bool leader = tc::elect_one();
+        for (int kb = 0; kb < nkb; kb++) {
+            const int s = kb % S;
+            tc::mbar_wait(tc::smem_u32(&bar_empty[s]), ((kb / S) & 1) ^ 1u);
+            if (leader) {
                 const uint32_t full = tc::smem_u32(&bar_full[s]), sa = smem + s * STAGE;
                 const int p = p_begin + kb * 64;
                 tc::mbar_expect_tx(full, STAGE);
@@ -219,9 +226,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_wgrad_kernel(const __grid_
                 for (int h = 0; h < NHALF; h++) tc::tma_load_2d(sa + h * HALF_BYTES, &mapA, h * 64, p + g.slab_row0, full);
                 tc::tma_load_2d(sa + A_BYTES, &mapB, 0, p, full);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
+            const bool leader = tc::elect_one();
             constexpr uint32_t idesc = tc::instr_desc_bf16(128, BN, 1, 1);
             constexpr uint32_t ahi = tc::smem_desc_hi(1024, tc::kSwizzle128), bhi = tc::smem_desc_hi(B_SBO, B_LAYOUT);
             uint32_t a_lo0[NACC];                 // start (16-byte units) + LBO of each accumulator's A descriptor, stage 0
@@ -234,16 +243,20 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_wgrad_kernel(const __grid_
                 tc::mbar_wait(tc::smem_u32(&bar_full[s]), (kb / S) & 1);
                 tc::tc_fence_after();
                 const uint32_t soff = s * (STAGE >> 4);
-                // k outer, accumulators inner (neutral on the B200: the MMA rate here is set by operand reads, see tc_conv_kernel)
+                if (leader) {
+                    // k outer, accumulators inner (neutral on the B200: the MMA rate is set by operand reads, see tc_conv_kernel)
 #pragma unroll
-                for (int k = 0; k < 4; k++)
+                    for (int k = 0; k < 4; k++)
 #pragma unroll
-                    for (int a = 0; a < NACC; a++)
-                        tc::umma_bf16_lohi(tmem + a * BN, a_lo0[a] + soff + k * 128, ahi, b_lo0 + soff + k * (B_KSTEP >> 4), bhi, idesc,
-                                           (kb | k) != 0);
-                tc::umma_commit(tc::smem_u32(&bar_empty[s]));
+                        for (int a = 0; a < NACC; a++)
+                            tc::umma_bf16_lohi(tmem + a * BN, a_lo0[a] + soff + k * 128, ahi, b_lo0 + soff + k * (B_KSTEP >> 4), bhi, idesc,
+                                               (kb | k) != 0);
+                    tc::umma_commit(tc::smem_u32(&bar_empty[s]));
+                }
+                __syncwarp();
             }
-            tc::umma_commit(tc::smem_u32(&bar_acc));
+            if (leader) tc::umma_commit(tc::smem_u32(&bar_acc));
+            __syncwarp();
         }
     } else {
         const int q = warp & 3;

@@ -266,6 +266,8 @@ int fb_debug_host_mixed(const int32_t *state16);
  * mode 0: D[M][N] = A[M][K] Bt[N][K]^T;  mode 1: D[M][N] = A[K][M]^T B[K][N];  bn = N tile (32/64/128). */
 int fb_debug_tc_gemm(int mode, int bn, int M, int N, int K, const void *a_bf16_dev, const void *b_bf16_dev, float *d_dev,
                      const uint32_t *strides6_host, void *stream);
+/* measurement hook: SM cycles for `iters` back-to-back tcgen05.mma (M 128, K 16, bf16) of width n from one thread */
+int fb_debug_tc_mma_rate(int n, int mn_major, int naccs, int iters, int same_operands, long long *cycles_dev, void *stream);
 /* measurement hook: re-launch one GEMM kernel of the tensor-core path `reps` times on the current workspace contents
  * (which: 0 conv1 fwd, 1 conv2 fwd, 2 conv3 fwd, 3 fc1 fwd, 4 conv1 wgrad, 5 conv3 dgrad, 6 fc1 dgrad) */
 int fb_debug_tc_kernel(fb_qnet *net, int which, int batch, int reps, const float *params_dev, void *stream);
