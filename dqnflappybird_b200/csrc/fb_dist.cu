@@ -8,6 +8,9 @@
 //   2. wait until every rank's flag shows the step (polling LOCAL memory);
 //   3. for each parameter: sum the gradients of ranks 0..G-1 in rank order straight from peer memory (identical
 //      order on every rank => bitwise identical parameters everywhere, no broadcast ever needed) and apply TF-1 Adam.
+// With four or more ranks step 3 is split (two-shot): each rank first reduces only ITS 1/G slice of the vector from all
+// peers into a `red` buffer, a grid barrier + second flag publishes it, and every rank then reads the G reduced slices
+// (its own locally) while applying Adam: 2 (G-1)/G vector reads per rank over NVLink instead of G-1.
 // No separate all-reduce, no reduced-gradient round trip through HBM.  Exchange buffers are double-buffered by step
 // parity: a rank may already write step s+1's gradients while a slow peer still reads step s's; it cannot reach s+2
 // before every peer has published s+1, i.e. has finished reading s.  Waits are bounded and end in a trap, not a hang.
@@ -23,10 +26,15 @@ struct fb_dist {
     int rank, world;
     size_t n;
     float *xgrads[2];
-    uint32_t *flags;                         // local; flags[q] = newest step rank q has published
+    uint32_t *flags;                         // local; flags[q] = newest step rank q has published, flags[32 + q] = its reduced slice
+    float *red;                              // this rank's reduced slice (two-shot)
+    unsigned int *grid_count;                // grid barrier counter (two-shot)
+    int two_shot;
+    uint32_t ts_steps;                       // two-shot exchanges done (the grid barrier counter is monotonic)
     const float *peer_grads[2][kMaxRanks];
     uint32_t *peer_flags[kMaxRanks];
-    void *opened[3 * kMaxRanks];
+    const float *peer_red[kMaxRanks];
+    void *opened[4 * kMaxRanks];
     int n_opened;
     uint32_t step;
 };
@@ -36,9 +44,13 @@ namespace {
 struct XArgs {
     const float *g[kMaxRanks];
     uint32_t *peer_flags[kMaxRanks];
+    const float *red[kMaxRanks];             // two-shot: every rank's reduced slice
+    float *my_red;
+    unsigned int *grid_count;
     const uint32_t *my_flags;
-    int rank, world, wait;
-    uint32_t step;
+    int rank, world, wait, two_shot;
+    size_t slice4;                           // float4s per slice (two-shot)
+    uint32_t step, ts_step;                  // exchange number; number of two-shot exchanges including this one
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
@@ -78,11 +90,42 @@ __global__ void __launch_bounds__(256) adam_xreduce_kernel(float *__restrict__ p
         __syncthreads();
     }
     const size_t n4 = n >> 2;
+    if (x.two_shot) {
+        // shot 1: this rank's slice, summed over the ranks in rank order
+        const size_t lo = x.slice4 * (size_t)x.rank, hi = min(n4, lo + x.slice4);
+        for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) {
+            float4 g = ld_peer(x.g[0] + 4 * i);
+            for (int q = 1; q < x.world; q++) {
+                float4 h = ld_peer(x.g[q] + 4 * i);
+                g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
+            }
+            reinterpret_cast<float4 *>(x.my_red)[i - lo] = g;
+        }
+        // grid barrier (every CTA of this grid is resident: 2 per SM), then publish the slice and wait for everyone's
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (atomicAdd(x.grid_count, 1u) + 1u == gridDim.x * x.ts_step)       // the last CTA of this grid
+                for (int q = 0; q < x.world; q++) st_release_sys(x.peer_flags[q] + 32 + x.rank, x.step);
+        }
+        if ((int)threadIdx.x < x.world) {
+            uint32_t spins = 0;
+            while ((int32_t)(ld_acquire_sys(x.my_flags + 32 + threadIdx.x) - x.step) < 0)
+                if (++spins > (1u << 26)) __trap();
+        }
+        __syncthreads();
+    }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-        float4 g = ld_peer(x.g[0] + 4 * i);
-        for (int q = 1; q < x.world; q++) {
-            float4 h = ld_peer(x.g[q] + 4 * i);
-            g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
+        float4 g;
+        if (x.two_shot) {
+            const int q = (int)(i / x.slice4);
+            g = ld_peer(x.red[q] + 4 * (i - (size_t)q * x.slice4));
+        } else {
+            g = ld_peer(x.g[0] + 4 * i);
+            for (int q = 1; q < x.world; q++) {
+                float4 h = ld_peer(x.g[q] + 4 * i);
+                g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
+            }
         }
         g.x *= grad_scale; g.y *= grad_scale; g.z *= grad_scale; g.w *= grad_scale;
         float4 p = reinterpret_cast<float4 *>(params)[i], m = reinterpret_cast<float4 *>(am)[i], v = reinterpret_cast<float4 *>(av)[i];
@@ -110,10 +153,15 @@ extern "C" int fb_dist_create(int rank, int world, long long n_floats, fb_dist *
     d->rank = rank; d->world = world; d->n = (size_t)n_floats; d->n_opened = 0; d->step = 0;
     const size_t bytes = ((size_t)n_floats * sizeof(float) + 255) / 256 * 256;
     for (int k = 0; k < 2; k++) { FB_CUDA_OK(cudaMalloc(&d->xgrads[k], bytes)); FB_CUDA_OK(cudaMemset(d->xgrads[k], 0, bytes)); }
-    FB_CUDA_OK(cudaMalloc(&d->flags, 256));
-    FB_CUDA_OK(cudaMemset(d->flags, 0, 256));
-    for (int q = 0; q < kMaxRanks; q++) { d->peer_grads[0][q] = d->peer_grads[1][q] = nullptr; d->peer_flags[q] = nullptr; }
-    d->peer_grads[0][rank] = d->xgrads[0]; d->peer_grads[1][rank] = d->xgrads[1]; d->peer_flags[rank] = d->flags;
+    FB_CUDA_OK(cudaMalloc(&d->flags, 512));
+    FB_CUDA_OK(cudaMemset(d->flags, 0, 512));
+    FB_CUDA_OK(cudaMalloc(&d->red, bytes));
+    FB_CUDA_OK(cudaMemset(d->red, 0, bytes));
+    FB_CUDA_OK(cudaMalloc(&d->grid_count, 256));
+    FB_CUDA_OK(cudaMemset(d->grid_count, 0, 256));
+    d->two_shot = world >= 4; d->ts_steps = 0;
+    for (int q = 0; q < kMaxRanks; q++) { d->peer_grads[0][q] = d->peer_grads[1][q] = nullptr; d->peer_flags[q] = nullptr; d->peer_red[q] = nullptr; }
+    d->peer_grads[0][rank] = d->xgrads[0]; d->peer_grads[1][rank] = d->xgrads[1]; d->peer_flags[rank] = d->flags; d->peer_red[rank] = d->red;
     *out = d;
     return FB_OK;
 }
@@ -121,20 +169,28 @@ extern "C" int fb_dist_create(int rank, int world, long long n_floats, fb_dist *
 extern "C" int fb_dist_destroy(fb_dist *d) {
     if (!d) return FB_OK;
     for (int k = 0; k < d->n_opened; k++) cudaIpcCloseMemHandle(d->opened[k]);
-    cudaFree(d->xgrads[0]); cudaFree(d->xgrads[1]); cudaFree(d->flags);
+    cudaFree(d->xgrads[0]); cudaFree(d->xgrads[1]); cudaFree(d->flags); cudaFree(d->red); cudaFree(d->grid_count);
     delete d;
     return FB_OK;
 }
 
-extern "C" int fb_dist_handle_bytes(void) { return 3 * (int)sizeof(cudaIpcMemHandle_t); }
+extern "C" int fb_dist_handle_bytes(void) { return 4 * (int)sizeof(cudaIpcMemHandle_t); }
 
-// this rank's three IPC handles (exchange buffer 0, exchange buffer 1, flags), fb_dist_handle_bytes() bytes
+// force the one-shot (0) or two-shot (1) exchange (default: two-shot from four ranks up)
+extern "C" int fb_dist_set_two_shot(fb_dist *d, int on) {
+    FB_REQUIRE(d != nullptr, "fb_dist_set_two_shot: NULL argument");
+    d->two_shot = on ? 1 : 0;
+    return FB_OK;
+}
+
+// this rank's IPC handles (exchange buffer 0, exchange buffer 1, flags, reduced slice), fb_dist_handle_bytes() bytes
 extern "C" int fb_dist_handles(fb_dist *d, uint8_t *out_host) {
     FB_REQUIRE(d != nullptr && out_host != nullptr, "fb_dist_handles: NULL argument");
-    cudaIpcMemHandle_t h[3];
+    cudaIpcMemHandle_t h[4];
     FB_CUDA_OK(cudaIpcGetMemHandle(&h[0], d->xgrads[0]));
     FB_CUDA_OK(cudaIpcGetMemHandle(&h[1], d->xgrads[1]));
     FB_CUDA_OK(cudaIpcGetMemHandle(&h[2], d->flags));
+    FB_CUDA_OK(cudaIpcGetMemHandle(&h[3], d->red));
     memcpy(out_host, h, sizeof(h));
     return FB_OK;
 }
@@ -144,14 +200,15 @@ extern "C" int fb_dist_connect(fb_dist *d, const uint8_t *all_handles_host) {
     FB_REQUIRE(d != nullptr && all_handles_host != nullptr, "fb_dist_connect: NULL argument");
     for (int q = 0; q < d->world; q++) {
         if (q == d->rank) continue;
-        cudaIpcMemHandle_t h[3];
+        cudaIpcMemHandle_t h[4];
         memcpy(h, all_handles_host + (size_t)q * sizeof(h), sizeof(h));
-        void *p[3];
-        for (int k = 0; k < 3; k++) {
+        void *p[4];
+        for (int k = 0; k < 4; k++) {
             FB_CUDA_OK(cudaIpcOpenMemHandle(&p[k], h[k], cudaIpcMemLazyEnablePeerAccess));
             d->opened[d->n_opened++] = p[k];
         }
         d->peer_grads[0][q] = (const float *)p[0]; d->peer_grads[1][q] = (const float *)p[1]; d->peer_flags[q] = (uint32_t *)p[2];
+        d->peer_red[q] = (const float *)p[3];
     }
     return FB_OK;
 }
@@ -159,7 +216,7 @@ extern "C" int fb_dist_connect(fb_dist *d, const uint8_t *all_handles_host) {
 // test hook: several "ranks" living in one process (no IPC): rank q's buffers are given directly
 extern "C" int fb_dist_connect_local(fb_dist *d, int q, fb_dist *peer) {
     FB_REQUIRE(d && peer && q >= 0 && q < d->world && peer->rank == q && peer->n == d->n, "fb_dist_connect_local: bad argument");
-    d->peer_grads[0][q] = peer->xgrads[0]; d->peer_grads[1][q] = peer->xgrads[1]; d->peer_flags[q] = peer->flags;
+    d->peer_grads[0][q] = peer->xgrads[0]; d->peer_grads[1][q] = peer->xgrads[1]; d->peer_flags[q] = peer->flags; d->peer_red[q] = peer->red;
     return FB_OK;
 }
 
@@ -181,9 +238,15 @@ extern "C" int fb_dist_adam(fb_dist *d, fb_qnet *net, float *params_dev, float *
     XArgs x{};
     for (int q = 0; q < d->world; q++) {
         FB_REQUIRE(d->peer_grads[par][q] != nullptr && d->peer_flags[q] != nullptr, "fb_dist_adam: call fb_dist_connect first");
-        x.g[q] = d->peer_grads[par][q]; x.peer_flags[q] = d->peer_flags[q];
+        x.g[q] = d->peer_grads[par][q]; x.peer_flags[q] = d->peer_flags[q]; x.red[q] = d->peer_red[q];
     }
     x.my_flags = d->flags; x.rank = d->rank; x.world = d->world; x.wait = wait; x.step = d->step + 1;
+    x.my_red = d->red; x.grid_count = d->grid_count;
+    // two-shot needs every rank's slice before anyone reads it: without the cross-rank handshake (single-process test,
+    // ranks run one after the other) only the one-shot form is meaningful
+    x.two_shot = d->two_shot && d->world > 1 && wait;
+    x.slice4 = ((d->n >> 2) + d->world - 1) / d->world;
+    if (x.two_shot) x.ts_step = ++d->ts_steps;
     adam_xreduce_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(params_dev, m_dev, v_dev, d->n, x, alpha, beta1, beta2, eps, grad_scale, reduced_out_dev);
     FB_CUDA_OK(cudaGetLastError());
     d->step++;

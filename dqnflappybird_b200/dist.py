@@ -93,6 +93,10 @@ class PeerGradExchange:
             _lib.check(self._L.fb_dist_connect(self._h, allh), "fb_dist_connect")
             dist.barrier()
 
+    def set_two_shot(self, on: bool):
+        """force the one-shot / two-shot form of the exchange (default: two-shot from four ranks up)"""
+        self._lib.check(self._L.fb_dist_set_two_shot(self._h, int(on)), "fb_dist_set_two_shot")
+
     def connect_local(self, q: int, peer: "PeerGradExchange"):
         """test hook: several ranks inside one process"""
         self._lib.check(self._L.fb_dist_connect_local(self._h, q, peer._h), "fb_dist_connect_local")

@@ -208,6 +208,7 @@ typedef struct fb_dist fb_dist;
 int fb_dist_create(int rank, int world, long long n_floats, fb_dist **out);
 int fb_dist_destroy(fb_dist *d);
 int fb_dist_handle_bytes(void);
+int fb_dist_set_two_shot(fb_dist *d, int on);                       /* default: two-shot (reduce own slice, then gather) from 4 ranks up */
 int fb_dist_handles(fb_dist *d, uint8_t *out_host);                 /* this rank's IPC handles */
 int fb_dist_connect(fb_dist *d, const uint8_t *all_handles_host);   /* world x fb_dist_handle_bytes(), rank-major */
 int fb_dist_connect_local(fb_dist *d, int q, fb_dist *peer);        /* test hook: "ranks" inside one process */

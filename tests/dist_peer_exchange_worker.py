@@ -18,9 +18,10 @@ def main():
     dev = torch.device("cuda", local)
     net = qnet.QNetwork(device=dev, max_batch=8, seed=3, precision="fp32")
     ref = qnet.QNetwork(device=dev, max_batch=8, seed=3, precision="fp32")
-    net.enable_peer_exchange()
+    x = net.enable_peer_exchange()
     g = torch.Generator(device=dev).manual_seed(100 + rank)
-    for step in range(6):
+    for step in range(8):
+        x.set_two_shot(step >= 4)                   # both forms of the exchange, whatever the world size
         mine = torch.randn(net.n_params, device=dev, generator=g) * 0.01
         net.grads.copy_(mine)
         net.adam_step()
