@@ -21,6 +21,7 @@
 // head / TD loss / Adam in fp32 (shared with fb_qnet.cu).  Tolerances vs the float64 oracle: tests/test_qnet_tc_gpu.py.
 #include <cudaTypedefs.h>
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -691,6 +692,7 @@ struct TcState {
     cudaEvent_t ev[8];
     std::vector<GraphEntry> graphs;
     int use_graph;
+    int fused_conv1;            // opt-in: tc_conv1_fused_kernel instead of pack_x2 + conv1 + pool_pack
 };
 
 namespace {
@@ -829,6 +831,7 @@ int tc_state_create(fb_qnet *n) {
     FB_CUDA_OK(cudaStreamCreateWithFlags(&t->cap, cudaStreamNonBlocking));
     for (auto &e : t->ev) FB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     t->use_graph = 1;
+    { const char *e = getenv("FB_TC_FUSED_CONV1"); t->fused_conv1 = (e && e[0] == '1') ? 1 : 0; }
     n->tc = t;
     return FB_OK;
 }
@@ -887,7 +890,13 @@ int tc_slot_for(fb_qnet *n, const float *params_dev, int want_slot, cudaStream_t
     return FB_OK;
 }
 
+static FrameView g_probe_view;                    // frames of the last forward (the fused conv1 probe re-reads them)
+// keep != 0: this forward's activations feed a backward pass (Z1 and, for the conv1 weight gradient, X2 are written)
+static int tc_forward_impl(fb_qnet *n, int slot, int w, const float *params_dev, FrameView fv, int B, float *q_out, int keep, cudaStream_t st);
 int tc_forward(fb_qnet *n, int slot, int w, const float *params_dev, FrameView fv, int B, float *q_out, cudaStream_t st) {
+    return tc_forward_impl(n, slot, w, params_dev, fv, B, q_out, 0, st);
+}
+static int tc_forward_impl(fb_qnet *n, int slot, int w, const float *params_dev, FrameView fv, int B, float *q_out, int keep, cudaStream_t st) {
     TcState *t = n->tc;
     FB_REQUIRE(t != nullptr && B > 0 && B <= n->max_batch && (w == 0 || w == 1), "tc_forward: bad argument");
     TcPlan *p;
@@ -897,9 +906,18 @@ int tc_forward(fb_qnet *n, int slot, int w, const float *params_dev, FrameView f
     const TcWeightMaps &wm = t->wm[slot];
     const FwdWs &f = t->ws[w];
     const int P1 = B * kP1, P2 = B * kP2;
-    FB_CUDA_OK(tc::launch_pdl(pack_x2_kernel, dim3((unsigned)(((size_t)P1 * 8 + 255) / 256)), dim3(256), 0, st, fv, B, f.x2));
-    FB_CUDA_OK((launch_tc_conv<32, kSlab1, 1, 4, 6, 1>(p->x2_s[w], wm.w1p, p->conv1, t->n_sms, EpiConv1{f.z1, params_dev + L.b1, P1}, st)));
-    FB_CUDA_OK(tc::launch_pdl(pool_pack_kernel, dim3((unsigned)(((size_t)B * 36 * 16 + 255) / 256)), dim3(256), 0, st, f.z1, B, f.p2));
+    g_probe_view = fv;
+    if (t->fused_conv1) {
+        // conv1 fused with the u8 -> space-to-depth conversion in front of it and the max-pool behind it: a fifth of the
+        // HBM bytes, but its slab builders are issue-latency bound (92 us vs 80 us for the three kernels at 2048 samples),
+        // so it is opt-in (FB_TC_FUSED_CONV1=1) until they are faster
+        if (keep) FB_CUDA_OK(tc::launch_pdl(pack_x2_kernel, dim3((unsigned)(((size_t)P1 * 8 + 255) / 256)), dim3(256), 0, st, fv, B, f.x2));
+        FB_CUDA_OK((launch_tc_conv1_fused<4>(wm.w1p, Conv1FusedParams{fv, B, params_dev + L.b1, keep ? f.z1 : nullptr, f.p2}, t->n_sms, st)));
+    } else {
+        FB_CUDA_OK(tc::launch_pdl(pack_x2_kernel, dim3((unsigned)(((size_t)P1 * 8 + 255) / 256)), dim3(256), 0, st, fv, B, f.x2));
+        FB_CUDA_OK((launch_tc_conv<32, kSlab1, 1, 4, 6, 1>(p->x2_s[w], wm.w1p, p->conv1, t->n_sms, EpiConv1{f.z1, params_dev + L.b1, P1}, st)));
+        FB_CUDA_OK(tc::launch_pdl(pool_pack_kernel, dim3((unsigned)(((size_t)B * 36 * 16 + 255) / 256)), dim3(256), 0, st, f.z1, B, f.p2));
+    }
     FB_CUDA_OK((launch_tc_conv<64, kSlab2, 2, 8, 3, 1>(p->p2_s[w], wm.w2p, p->conv2, t->n_sms, EpiGrid7{f.a2, params_dev + L.b2, P2}, st)));
     FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4, 1>(p->a2_s[w], wm.w3p, p->conv3, t->n_sms, EpiConv3{f.a3, params_dev + L.b3, P2}, st)));
     FB_CUDA_OK((launch_tc_gemm<128, 2>(p->a3_k[w], wm.wf1n, p->fc1, dim3((B + 127) / 128, L.hidden / 128, p->sf),
@@ -940,7 +958,7 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     rc = a.variant == 0 ? tc_forward(n, 0, 1, a.params, a.fn, B, n->q_next, sx) : tc_forward(n, 1, 1, a.target, a.fn, B, n->q_next, sx);
     if (rc) return rc;
     // ---- main: Q(s) with the online net; its activations stay in workspace 0 for the backward pass
-    rc = tc_forward(n, 0, 0, a.params, a.fs, B, n->q, st); if (rc) return rc;
+    rc = tc_forward_impl(n, 0, 0, a.params, a.fs, B, n->q, 1, st); if (rc) return rc;
     FB_CUDA_OK(fork(sx, st));
     qnet_launch_td_loss(n->q, n->q_next, n->q_next_online, a.actions, a.rewards, a.terminals, a.isw, B, a.global_batch, a.variant, a.gamma,
                         a.loss_sum, n->dq, a.loss_out, a.abs_err, a.q_target, st);
@@ -975,6 +993,14 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
 bool same_key(const GraphKey &x, const GraphKey &y) { return memcmp(&x, &y, sizeof(GraphKey)) == 0; }
 
 }  // namespace
+
+extern "C" int fb_qnet_use_fused_conv1(fb_qnet *n, int enable) {
+    FB_REQUIRE(n != nullptr && n->tc != nullptr, "fb_qnet_use_fused_conv1: needs FB_PRECISION_BF16");
+    n->tc->fused_conv1 = enable ? 1 : 0;
+    for (auto &g : n->tc->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    n->tc->graphs.clear();
+    return FB_OK;
+}
 
 extern "C" int fb_qnet_use_graphs(fb_qnet *n, int enable) {
     FB_REQUIRE(n != nullptr, "fb_qnet_use_graphs: NULL argument");
@@ -1053,7 +1079,9 @@ extern "C" int fb_debug_tc_kernel(fb_qnet *n, int which, int B, int reps, const 
             case 4: FB_CUDA_OK((launch_tc_wgrad<32, 2, kSlabW1, 1, 6>(p->x2_w, p->dz1_b, p->conv1_w, p->s1, EpiStoreF32{t->part1, 256, 32, (size_t)256 * 32}, st))); break;
             case 5: FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4, 1>(p->dz3_s, wm.w3d, p->conv3_d, t->n_sms, EpiConv3Dgrad{t->dz2, f.a2, P2}, st))); break;
             case 6: FB_CUDA_OK((launch_tc_gemm<64, 0>(p->dh1_k, wm.wf1n, p->fc1_d, dim3((B + 127) / 128, kFlat / 64, 1), EpiFc1Dgrad{t->dz3, f.a3, B}, st))); break;
-            default: FB_REQUIRE(false, "fb_debug_tc_kernel: which must be 0..6");
+            case 7: FB_CUDA_OK((launch_tc_conv1_fused<4>(wm.w1p, Conv1FusedParams{g_probe_view, B, params_dev + L.b1, nullptr, f.p2}, t->n_sms, st))); break;
+            case 8: FB_CUDA_OK((launch_tc_conv1_fused<4>(wm.w1p, Conv1FusedParams{g_probe_view, B, params_dev + L.b1, f.z1, f.p2}, t->n_sms, st))); break;
+            default: FB_REQUIRE(false, "fb_debug_tc_kernel: which must be 0..8");
         }
     }
     return FB_OK;

@@ -295,3 +295,237 @@ static cudaError_t launch_tc_wgrad(const CUtensorMap &ma, const CUtensorMap &mb,
 }
 
 }  // namespace
+
+// ---- conv1 fused with its neighbours ---------------------------------------------------------------------------------
+// frames (u8, FrameView) -> [space-to-depth slab built in shared memory] -> conv 8x8 s4 + bias + ReLU -> Z1 (optional,
+// kept for backward) -> 2x2 max-pool -> P2 in conv2's space-to-depth layout.  Neither the bf16 input matrix X2
+// (56 KB/sample) nor, when acting, Z1 (28 KB/sample) ever exists in HBM: 25.6 KB of u8 in, 12.5 KB of P2 out per sample.
+//
+// Tile = 6 rows of one sample's 21-wide block grid (126 positions, M = 128), so that every 2x2 pooling window is inside
+// one tile; 4 tiles per sample.  Warps: 0 weights (TMA), 1 MMA issue, 2-5 epilogue (+ pooling through shared memory),
+// 6-13 slab builders, one tile each in flight (u8 -> bf16, written with the 128-byte swizzle TMA would have used, fence.proxy.async, mbarrier).
+namespace {
+
+constexpr int kFusedThreads = 448;                              // 6 role warps + 8 slab builders
+constexpr int kBuilders = 256;
+constexpr int kTileRows1 = 6, kTilePos1 = kTileRows1 * 21;      // 126 positions per tile
+constexpr int kSlabF = 152;                                     // 126 + 22 halo, rounded up to 8
+
+// rows [row0, row0 + nrows) of the virtual matrix X2 [B*441][64] (block (bh,bw) of the input padded by 2, channel
+// j = r*16 + s*4 + c) into a swizzled slab: 16-byte chunk c16 of slab row r lands at r*128 + ((c16 ^ (r & 7)) << 4)
+// Slab building, two steps, by the 256 builder threads of the fused conv1 kernel:
+//   (A) the tile's raw pixels -- 4 frames x 32 pixel rows x 80 bytes, this sample only; 32 rows of a frame are one
+//       contiguous 2,560-byte run -- arrive as four cp.async.bulk copies per tile into a ring of raw stages, issued
+//       several tiles ahead by warp 0 (one tile in flight at a time is bound by the HBM latency, ~3,400 cycles a tile);
+//   (B) every thread gathers 2 pixels x 4 frames per 16-byte chunk from there, converts u8 -> bf16 and stores the chunk
+//       where TMA's 128-byte swizzle would have put it (row r, chunk c16 -> r*128 + ((c16 ^ (r & 7)) << 4)).
+// Gathering straight from global memory with 2-byte loads asks L1 for 7x the sectors the tile holds and was the bound.
+constexpr int kRawRows = 32, kRawBytes = 4 * kRawRows * 80;     // raw pixels per tile (10,240 bytes)
+constexpr int kRawStages = 4;
+
+// thread (bw, c16) walks down the 8 block rows of the tile: no division, every address is an increment
+__device__ __forceinline__ void slab_from_raw(uint8_t *slab, const uint8_t *raw, int tq, int tid) {
+    if (tid >= 21 * 8) return;
+    const int bw = tid >> 3, c16 = tid & 7, dr = c16 >> 1, iw = 4 * bw - 2 + 2 * (c16 & 1);
+    const bool col_ok = (unsigned)iw < 80u;
+#pragma unroll
+    for (int bh_l = 0; bh_l < 8; bh_l++) {
+        const int r = bh_l * 21 + bw;
+        if (r < kSlabF) {
+            const int rr = 4 * bh_l + dr, ih = 24 * tq - 2 + rr;
+            uint4 out = make_uint4(0u, 0u, 0u, 0u);
+            if (col_ok && kTileRows1 * tq + bh_l < 21 && (unsigned)ih < 80u) {
+                const uint8_t *src = raw + rr * 80 + iw;
+                uint32_t t[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) t[c] = *reinterpret_cast<const unsigned short *>(src + c * (kRawRows * 80));
+                uint32_t w[4];
+#pragma unroll
+                for (int s2 = 0; s2 < 2; s2++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const float lo = (float)((t[2 * h] >> (8 * s2)) & 255), hi = (float)((t[2 * h + 1] >> (8 * s2)) & 255);
+                        __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+                        w[s2 * 2 + h] = *reinterpret_cast<uint32_t *>(&v);
+                    }
+                out = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            *reinterpret_cast<uint4 *>(slab + r * 128 + ((c16 ^ (r & 7)) << 4)) = out;
+        }
+    }
+}
+
+struct Conv1FusedParams {
+    FrameView fv;
+    int B;
+    const float *bias;
+    __nv_bfloat16 *z1;          // [B*441][32] or nullptr (acting / target forward: not needed)
+    __nv_bfloat16 *p2;          // [B*49][128]
+};
+
+template <int S>
+__global__ void __launch_bounds__(kFusedThreads, 1) tc_conv1_fused_kernel(const __grid_constant__ CUtensorMap mapB, const Conv1FusedParams g) {
+    constexpr int BN = 32, NKB = 4;
+    constexpr uint32_t STAGE = kSlabF * 128, BBLK = BN * 128, B_BYTES = NKB * BBLK, ZS_BYTES = 128 * BN * 2;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[S], bar_empty[S], bar_b, bar_acc_full[2], bar_acc_empty[2], bar_raw_full[kRawStages],
+        bar_raw_empty[kRawStages];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float bias_s[BN];
+    uint8_t *smem_gen = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-aligned, generic pointer
+    const uint32_t smem_b = tc::smem_u32(smem_gen), smem_a = smem_b + B_BYTES;
+    uint8_t *slab_gen = smem_gen + B_BYTES, *zs_gen = slab_gen + S * STAGE, *raw_gen = zs_gen + 2 * ZS_BYTES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = 4 * g.B;
+    const long long total_rows = (long long)g.B * 441;
+
+    if (threadIdx.x == 0) {
+        tc::tma_prefetch_desc(&mapB);
+        for (int s = 0; s < S; s++) { tc::mbar_init(tc::smem_u32(&bar_full[s]), 1); tc::mbar_init(tc::smem_u32(&bar_empty[s]), 1); }
+        tc::mbar_init(tc::smem_u32(&bar_b), 1);
+        for (int a = 0; a < 2; a++) { tc::mbar_init(tc::smem_u32(&bar_acc_full[a]), 1); tc::mbar_init(tc::smem_u32(&bar_acc_empty[a]), 4); }
+        for (int k = 0; k < kRawStages; k++) { tc::mbar_init(tc::smem_u32(&bar_raw_full[k]), 1); tc::mbar_init(tc::smem_u32(&bar_raw_empty[k]), 1); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tc::smem_u32(&tmem_slot), 64);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (threadIdx.x == 0) {
+        tc::mbar_expect_tx(tc::smem_u32(&bar_b), B_BYTES);
+        for (int kb = 0; kb < NKB; kb++) tc::tma_load_2d(smem_b + kb * BBLK, &mapB, kb * 64, 0, tc::smem_u32(&bar_b));
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + BN) bias_s[threadIdx.x - 64] = g.bias[threadIdx.x - 64];
+    tc::pdl_wait();
+    tc::pdl_launch();
+    __syncthreads();
+
+    if (warp == 0) {
+        // ===== raw pixel loader: four bulk copies per tile (one contiguous run of rows per frame), kRawStages tiles ahead
+        const bool leader = tc::elect_one();
+        int i = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, i++) {
+            const int rs = i % kRawStages, b = tile >> 2, tq = tile & 3;
+            tc::mbar_wait(tc::smem_u32(&bar_raw_empty[rs]), ((i / kRawStages) & 1) ^ 1u);
+            if (leader) {
+                const int ih0 = 24 * tq - 2, lo = ih0 < 0 ? 0 : ih0, hi = ih0 + kRawRows > 80 ? 80 : ih0 + kRawRows;       // valid rows [lo, hi)
+                const uint32_t bytes = (uint32_t)(hi - lo) * 80u, full = tc::smem_u32(&bar_raw_full[rs]);
+                const uint32_t dst = tc::smem_u32(raw_gen) + rs * kRawBytes + (uint32_t)(lo - ih0) * 80u;
+                const uint8_t *src = g.fv.base + (size_t)b * g.fv.sample_stride + lo * 80;
+                tc::mbar_expect_tx(full, 4 * bytes);
+#pragma unroll
+                for (int c = 0; c < 4; c++) tc::bulk_load_1d(dst + c * (kRawRows * 80), src + g.fv.chan_off[c], bytes, full);
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 6) {
+        // ===== slab builders (256 threads, named barrier 2)
+        const int tid = threadIdx.x - 192;
+        int i = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, i++) {
+            const int s = i % S, rs = i % kRawStages;
+            tc::mbar_wait(tc::smem_u32(&bar_raw_full[rs]), (i / kRawStages) & 1);
+            tc::mbar_wait(tc::smem_u32(&bar_empty[s]), ((i / S) & 1) ^ 1u);
+            slab_from_raw(slab_gen + s * STAGE, raw_gen + rs * kRawBytes, tile & 3, tid);
+            tc::fence_proxy_async();                      // generic-proxy writes -> visible to the tensor core's async proxy
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (tid == 0) { tc::mbar_arrive(tc::smem_u32(&bar_full[s])); tc::mbar_arrive(tc::smem_u32(&bar_raw_empty[rs])); }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issue
+        const bool leader = tc::elect_one();
+        constexpr uint32_t idesc = tc::instr_desc_bf16(128, BN, 0, 0);
+        constexpr uint32_t dhi = tc::smem_desc_hi(1024, tc::kSwizzle128);
+        const uint32_t a_lo0 = tc::smem_desc_lo(smem_a, 16), b_lo0 = tc::smem_desc_lo(smem_b, 16);
+        tc::mbar_wait(tc::smem_u32(&bar_b), 0);
+        int i = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, i++) {
+            const int s = i % S, as = i & 1;
+            tc::mbar_wait(tc::smem_u32(&bar_acc_empty[as]), ((i >> 1) & 1) ^ 1u);
+            tc::mbar_wait(tc::smem_u32(&bar_full[s]), (i / S) & 1);
+            tc::tc_fence_after();
+            if (leader) {
+                const uint32_t a_lo = a_lo0 + s * (STAGE >> 4);
+#pragma unroll
+                for (int kb = 0; kb < NKB; kb++) {
+                    const uint32_t tap = (uint32_t)(((kb >> 1) * 21 + (kb & 1)) * 128) >> 4;       // taps at rows 0, 1, 21, 22
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        tc::umma_bf16_lohi(tmem + as * BN, a_lo + tap + 2 * k, dhi, b_lo0 + ((kb * BBLK + k * 32) >> 4), dhi, idesc, (kb | k) != 0);
+                }
+                tc::umma_commit(tc::smem_u32(&bar_empty[s]));
+                tc::umma_commit(tc::smem_u32(&bar_acc_full[as]));
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 2 && warp < 6) {
+        // ===== epilogue: bias + ReLU, Z1, max-pool through shared memory, P2
+        const int q = warp & 3, r = q * 32 + lane;          // accumulator row = position r of the tile
+        const int et = threadIdx.x - 64;                    // 0..127 among the epilogue threads
+        int i = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, i++) {
+            const int as = i & 1, b = tile >> 2, tq = tile & 3;
+            tc::mbar_wait(tc::smem_u32(&bar_acc_full[as]), (i >> 1) & 1);
+            tc::tc_fence_after();
+            float v[32];
+            tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN), v);
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_acc_empty[as]));
+            const int oh_l = r / 21, ow = r - oh_l * 21, oh = kTileRows1 * tq + oh_l;
+            const bool ok = r < kTilePos1 && oh < 20 && ow < 20;
+            uint32_t w[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const float x0 = ok ? fmaxf(v[2 * k] + bias_s[2 * k], 0.f) : 0.f, x1 = ok ? fmaxf(v[2 * k + 1] + bias_s[2 * k + 1], 0.f) : 0.f;
+                __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+                w[k] = *reinterpret_cast<uint32_t *>(&h);
+            }
+            uint4 *zs = reinterpret_cast<uint4 *>(zs_gen + (i & 1) * ZS_BYTES + r * 64);
+#pragma unroll
+            for (int k = 0; k < 4; k++) zs[(k + (r >> 1)) & 3] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);   // rotate: fewer bank conflicts
+            if (ok && g.z1 != nullptr) {
+                uint4 *d = reinterpret_cast<uint4 *>(g.z1 + ((size_t)b * 441 + oh * 21 + ow) * BN);
+#pragma unroll
+                for (int k = 0; k < 4; k++) d[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et < 120) {
+                const int ph_l = et / 40, rem = et - ph_l * 40, pw = rem >> 2, cg = rem & 3, ph = 3 * tq + ph_l;
+                if (ph < 10) {
+                    const uint8_t *zb = zs_gen + (i & 1) * ZS_BYTES;
+                    auto ld = [&](int row) { return *reinterpret_cast<const uint4 *>(zb + row * 64 + (((cg + (row >> 1)) & 3) << 4)); };
+                    const int r0 = (2 * ph_l) * 21 + 2 * pw;
+                    uint4 m = ld(r0), o1 = ld(r0 + 1), o2 = ld(r0 + 21), o3 = ld(r0 + 22);
+                    __nv_bfloat162 *pm = reinterpret_cast<__nv_bfloat162 *>(&m);
+                    const __nv_bfloat162 *p1 = reinterpret_cast<const __nv_bfloat162 *>(&o1), *p2 = reinterpret_cast<const __nv_bfloat162 *>(&o2),
+                                         *p3 = reinterpret_cast<const __nv_bfloat162 *>(&o3);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) pm[k] = __hmax2(__hmax2(pm[k], p1[k]), __hmax2(p2[k], p3[k]));
+                    const int bh = (ph + 1) >> 1, rr = (ph + 1) & 1, bw = (pw + 1) >> 1, ss = (pw + 1) & 1;
+                    *reinterpret_cast<uint4 *>(g.p2 + ((size_t)b * 49 + bh * 7 + bw) * 128 + rr * 64 + ss * 32 + cg * 8) = m;
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem, 64);
+}
+
+template <int S>
+static cudaError_t launch_tc_conv1_fused(const CUtensorMap &mb, const Conv1FusedParams &g, int max_ctas, cudaStream_t st) {
+    static bool configured = false;
+    auto kern = tc_conv1_fused_kernel<S>;
+    constexpr size_t smem = 4 * 32 * 128 + (size_t)S * kSlabF * 128 + 2 * 128 * 32 * 2 + kRawStages * kRawBytes + 1024;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    int grid = 4 * g.B < max_ctas ? 4 * g.B : max_ctas;
+    return tc::launch_pdl(kern, dim3(grid), dim3(kFusedThreads), smem, st, mb, g);
+}
+
+}  // namespace

@@ -164,6 +164,9 @@ int fb_qnet_invalidate(fb_qnet *net);
 /* FB_PRECISION_BF16 only: replay fb_qnet_loss_backward as a CUDA graph once the same arguments were seen twice
  * (default on; the eager two-stream path is identical work). */
 int fb_qnet_use_graphs(fb_qnet *net, int enable);
+/* FB_PRECISION_BF16 only, opt-in (also FB_TC_FUSED_CONV1=1): conv1 built straight from the u8 frames with the max-pool in its
+ * epilogue (no bf16 input matrix, no separate pooling pass; a fifth of the HBM bytes, not yet faster). */
+int fb_qnet_use_fused_conv1(fb_qnet *net, int enable);
 int fb_qnet_param_count(const fb_qnet *net);
 int fb_qnet_layout(const fb_qnet *net, int32_t *out16_host);
 
