@@ -24,6 +24,8 @@ if ROOT not in sys.path:
 
 BYTES_PER_FRAME = 6400 + 64 + 1 + 4 + 1 + 4          # obs + state r/w + action + reward + terminal + score
 METRIC = "env frames/sec (step+render+preproc)"
+WORKLOAD = ("configs[1] op mix (batched frame_step + render + preprocess, random actions p=0.5, Philox gaps) "
+            "at configs[4] scale: 1,048,576 envs / 8 GPUs")
 UNIT = "frames/s"
 
 
@@ -165,8 +167,9 @@ def run_reference(args, rank: int, world: int):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "configs[1]: frame_step + render + preprocess, random actions p=0.5 (CPU port of the reference path)",
-                   "envs": n_envs, "frames_per_bench_step": n_envs * steps_per_sample},
+        "config": {"workload": WORKLOAD, "envs_per_gpu": args.envs_per_gpu, "envs_total": args.envs_per_gpu * max(args.gpus, 1),
+                   "cpu_sample": f"bounded sample of the same per-env workload: {n_envs} envs x {steps_per_sample} frame_steps per bench step "
+                                 "(CPU port of the reference path: full 288x512 blits + cv2-exact resize / gray / threshold per frame)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{n_envs} envs x {steps_per_sample} frame_steps per bench step on {threads} threads; "
                                    "as shipped the reference sleeps to 30 frames/s/process (wrapped_flappy_bird.py:179)"},
@@ -277,8 +280,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "configs[1] op mix (batched frame_step + render + preprocess, random actions p=0.5, Philox gaps) "
-                               "at configs[4] scale: 1,048,576 envs / 8 GPUs",
+        "config": {"workload": WORKLOAD,
                    "envs_per_gpu": E, "envs_total": total_envs, "ring": f"u8[{E}][4][80][80] = {E * 25600 / 1e9:.2f} GB per GPU",
                    "l2": "inputs larger than L2 (ring >> 126 MB; every frame is written once and not re-read)",
                    "parallelism": f"env-sharded x{world}, no collective"},
