@@ -362,7 +362,6 @@ def bench_learner(args, rank, world, dev):
     # (2048 samples: 116 MB of operands + 58 MB of output > L2) they stream from HBM.
     kern = None
     if args.learner_precision == "bf16":
-        import ctypes as C
         from dqnflappybird_b200 import _lib
         L = _lib.lib()
         st = torch.cuda.current_stream().cuda_stream
@@ -379,6 +378,34 @@ def bench_learner(args, rank, world, dev):
             us = e0.elapsed_time(e1) * 1e3 / reps
             kern[kb] = {"us": us, "tflops": 6553600 * kb / (us * 1e-6) / 1e12,
                         "hbm_gbs": kb * 441 * (128 + 64) / (us * 1e-6) / 1e9}
+    # ---- the other DQN-family agents of BASELINE.json's configs on the same workload (same envs, replay and minibatch):
+    # Double (configs[4]), Dueling (configs[4]), prioritized replay with the device sum-tree (configs[3])
+    variants = {"dqnnature": {"updates_per_s": 1e3 / ms_upd, "ms_per_update": ms_upd}}
+    if not args.no_learner_variants:
+        from dqnflappybird_b200.brains import BrainDoubleDQN, BrainDuelingDQN, BrainPrioritizedReplyDQN
+        ring_shared = brain.ring
+        for name, cls in (("ddqn", BrainDoubleDQN), ("duelingdqn", BrainDuelingDQN), ("prioritydqn", BrainPrioritizedReplyDQN)):
+            vb = cls(2, "bird", num_envs=N, device=dev, ring=ring_shared, replay_memory_per_env=C, batch_size=B, observe=1e18, seed=0,
+                     first_env_id=rank * N, max_act_batch=2048, precision=args.learner_precision)
+            vb._k = brain._k
+            for k in range(max(1, brain._k - C + 1), brain._k + 1):      # the ring already holds the rollout: register its steps
+                a_row, r_row, t_row = vb.replayMemory.rows(k)
+                a0, r0, t0 = brain.replayMemory.rows(k)
+                a_row.copy_(a0); r_row.copy_(r0); t_row.copy_(t0)
+                vb.replayMemory.appended(k)
+            vb.timeStep = 1
+            for _ in range(W):
+                vb._trainQNetwork(); vb.timeStep += 1
+            sync()
+            e0.record()
+            for _ in range(K):
+                vb._trainQNetwork(); vb.timeStep += 1
+            e1.record(); sync()
+            tv = torch.tensor([e0.elapsed_time(e1) / K], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+            variants[name] = {"updates_per_s": 1e3 / float(tv[0]), "ms_per_update": float(tv[0])}
+            del vb
     cpu_upd = None
     if world == 1 and not args.no_cpu_baseline:
         ups, n_done, dt = cpu_port_updates_per_s()
@@ -398,7 +425,7 @@ def bench_learner(args, rank, world, dev):
             "compute_path": brain.net.compute_path if hasattr(brain.net, "compute_path") else "fp32 CUDA-core implicit GEMM",
             "act_envs_per_s": N * world / (ms_act * 1e-3), "ms_per_act": ms_act,
             "act_tflops_per_gpu": N * FLOP_FWD / (ms_act * 1e-3) / 1e12,
-            "transitions_per_s": B * 1e3 / ms_upd, "scaling": args.learner_scaling, "cpu_baseline": cpu_upd,
+            "transitions_per_s": B * 1e3 / ms_upd, "scaling": args.learner_scaling, "cpu_baseline": cpu_upd, "variants": variants,
             "gradient_exchange": ("none (1 GPU)" if world == 1 else
                                   "fused into Adam over NVLink peer memory (fb_dist_adam)" if brain.net.exchange is not None else "NCCL all-reduce"),
             "roofline": None if not kern else {
@@ -428,6 +455,7 @@ def main():
     ap.add_argument("--learner-updates", type=int, default=50)
     ap.add_argument("--learner-precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--learner-scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-learner-variants", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
