@@ -154,13 +154,24 @@ __global__ void __launch_bounds__(THREADS) env_step_kernel(const StepArgs a) {
                 if (a.ring) dl[tid] = make_draw_list(s);
             }
             if (a.ring) {
-                __syncthreads();
                 const int slot = (a.ring_slot + step) % a.ring_len;
-                for (int e = warp; e < n_here; e += WARPS) {
-                    uint8_t *out = a.ring + ((size_t)(env0 + e) * a.ring_len + slot) * (size_t)FB_FRAME_BYTES;
-                    render_env(T, a.ex, dl[e], rowmask[warp], out, lane);
+                if (EPC == THREADS) {
+                    // each warp draws the 32 envs its own lanes have just stepped: only warp-level synchronisation, so the
+                    // warps of a CTA drift apart and one warp's physics overlaps another's stores
+                    __syncwarp();
+                    for (int e = warp * 32; e < min(n_here, warp * 32 + 32); e++) {
+                        uint8_t *out = a.ring + ((size_t)(env0 + e) * a.ring_len + slot) * (size_t)FB_FRAME_BYTES;
+                        render_env(T, a.ex, dl[e], rowmask[warp], out, lane);
+                    }
+                    __syncwarp();
+                } else {
+                    __syncthreads();
+                    for (int e = warp; e < n_here; e += WARPS) {
+                        uint8_t *out = a.ring + ((size_t)(env0 + e) * a.ring_len + slot) * (size_t)FB_FRAME_BYTES;
+                        render_env(T, a.ex, dl[e], rowmask[warp], out, lane);
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
             }
         }
         if (have) {
