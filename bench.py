@@ -406,6 +406,32 @@ def bench_learner(args, rank, world, dev):
                 dist.all_reduce(tv, op=dist.ReduceOp.MAX)
             variants[name] = {"updates_per_s": 1e3 / float(tv[0]), "ms_per_update": float(tv[0])}
             del vb
+    # ---- minibatch sweep (BrainDQNNature): the 256 of configs[2] is launch/latency-bound on a B200; the same step at
+    # larger minibatches shows what the kernels sustain
+    sweep = {str(B): {"updates_per_s": 1e3 / ms_upd, "transitions_per_s": B * 1e3 / ms_upd, "includes": "sample + gather + update"}}
+    if not args.no_learner_variants and world == 1:
+        from dqnflappybird_b200.qnet import QNetwork
+        for mb_size in (1024, 4096):
+            parts = [brain.replayMemory.sample(brain.local_batch) for _ in range(1)]
+            fr, ac, rw, tm = [], [], [], []
+            for _ in range(mb_size // brain.local_batch):
+                mbp = brain.replayMemory.sample(brain.local_batch)
+                fr.append(mbp.frames.clone()); ac.append(mbp.actions.clone()); rw.append(mbp.rewards.clone()); tm.append(mbp.terminals.clone())
+            fr, ac, rw, tm = torch.cat(fr), torch.cat(ac), torch.cat(rw), torch.cat(tm)
+            netv = QNetwork(device=dev, max_batch=mb_size, precision=args.learner_precision, seed=0)
+            for _ in range(3):
+                netv.loss_backward("nature", fr, ac, rw, tm); netv.adam_step()
+            sync()
+            Kv = max(10, K // 4)
+            e0.record()
+            for _ in range(Kv):
+                netv.loss_backward("nature", fr, ac, rw, tm); netv.adam_step()
+            e1.record(); sync()
+            msv = e0.elapsed_time(e1) / Kv
+            sweep[str(mb_size)] = {"updates_per_s": 1e3 / msv, "transitions_per_s": mb_size * 1e3 / msv,
+                                   "tflops": (2 * FLOP_FWD + FLOP_BWD) * mb_size / (msv * 1e-3) / 1e12,
+                                   "includes": "update only on a fixed minibatch (the CPython-exact sampler is one CTA, <= 512 draws)"}
+            del netv, fr
     cpu_upd = None
     if world == 1 and not args.no_cpu_baseline:
         ups, n_done, dt = cpu_port_updates_per_s()
@@ -425,7 +451,7 @@ def bench_learner(args, rank, world, dev):
             "compute_path": brain.net.compute_path if hasattr(brain.net, "compute_path") else "fp32 CUDA-core implicit GEMM",
             "act_envs_per_s": N * world / (ms_act * 1e-3), "ms_per_act": ms_act,
             "act_tflops_per_gpu": N * FLOP_FWD / (ms_act * 1e-3) / 1e12,
-            "transitions_per_s": B * 1e3 / ms_upd, "scaling": args.learner_scaling, "cpu_baseline": cpu_upd, "variants": variants,
+            "transitions_per_s": B * 1e3 / ms_upd, "scaling": args.learner_scaling, "cpu_baseline": cpu_upd, "variants": variants, "minibatch_sweep": sweep,
             "gradient_exchange": ("none (1 GPU)" if world == 1 else
                                   "fused into Adam over NVLink peer memory (fb_dist_adam)" if brain.net.exchange is not None else "NCCL all-reduce"),
             "roofline": None if not kern else {

@@ -488,16 +488,18 @@ __global__ void __launch_bounds__(256) colsum_kernel(ColsumJobs jobs) {
 // Head backward in one pass over h1 (BrainDQN.py:151-154 / dueling BrainDuelingDQN_CC.py:68-77): gradients of the head
 // weights, dh1 = dQ W^T masked by relu (bf16, the operand of the fc1 gradient GEMMs) and the fc1 bias gradient
 // sum_b dh1.  Block = 32 hidden units x 8 row lanes; block gridDim.x-1 does the head bias.
+constexpr int kHeadRows = 256;                      // rows of the minibatch per head-backward CTA row group
 __global__ void __launch_bounds__(256) head_backward_tc_kernel(const float *__restrict__ h1, const float *__restrict__ dq,
                                                                const float *__restrict__ params, QnetLayout L, int B,
-                                                               float *__restrict__ grads, bf16 *__restrict__ dh1) {
+                                                               float *__restrict__ hp /* [G][H][4] */, float *__restrict__ hb /* [G][2] */,
+                                                               bf16 *__restrict__ dh1) {
     tc::pdl_wait();
     tc::pdl_launch();
     __shared__ float red[8][32][4];
-    const int H = L.hidden;
-    if ((int)blockIdx.x == H / 32) {                 // head bias gradients: sum_b dq (dueling: (d0+d1) for V, d - mean for A)
+    const int H = L.hidden, grp = blockIdx.y, b0 = grp * kHeadRows, b1 = min(B, b0 + kHeadRows);
+    if ((int)blockIdx.x == H / 32) {                 // head bias partials: sum_b dq over this row group
         float s0 = 0.f, s1 = 0.f;
-        for (int b = threadIdx.x; b < B; b += 256) { s0 += dq[b * 2]; s1 += dq[b * 2 + 1]; }
+        for (int b = b0 + threadIdx.x; b < b1; b += 256) { s0 += dq[b * 2]; s1 += dq[b * 2 + 1]; }
 #pragma unroll
         for (int o = 16; o; o >>= 1) { s0 += __shfl_xor_sync(~0u, s0, o); s1 += __shfl_xor_sync(~0u, s1, o); }
         if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0][0] = s0; red[threadIdx.x >> 5][0][1] = s1; }
@@ -505,8 +507,7 @@ __global__ void __launch_bounds__(256) head_backward_tc_kernel(const float *__re
         if (threadIdx.x == 0) {
             float t0 = 0.f, t1 = 0.f;
             for (int w = 0; w < 8; w++) { t0 += red[w][0][0]; t1 += red[w][0][1]; }
-            if (!L.dueling) { grads[L.bf2] = t0; grads[L.bf2 + 1] = t1; }
-            else { float m = (t0 + t1) * 0.5f; grads[L.ba] = t0 - m; grads[L.ba + 1] = t1 - m; grads[L.bv] = t0 + t1; }
+            hb[grp * 2] = t0; hb[grp * 2 + 1] = t1;
         }
         return;
     }
@@ -516,7 +517,7 @@ __global__ void __launch_bounds__(256) head_backward_tc_kernel(const float *__re
     else { w0 = params[L.wa + j * 2]; w1 = params[L.wa + j * 2 + 1]; wv = params[L.wv + j]; }
     float g0 = 0.f, g1 = 0.f, gv = 0.f, gb = 0.f;
 #pragma unroll 8
-    for (int b = rl; b < B; b += 8) {
+    for (int b = b0 + rl; b < b1; b += 8) {
         float x = h1[(size_t)b * H + j];
         float d0 = dq[b * 2], d1 = dq[b * 2 + 1], g;
         if (!L.dueling) { g0 = fmaf(x, d0, g0); g1 = fmaf(x, d1, g1); g = d0 * w0 + d1 * w1; }
@@ -536,9 +537,7 @@ __global__ void __launch_bounds__(256) head_backward_tc_kernel(const float *__re
         float t0 = 0.f, t1 = 0.f, tv = 0.f, tb = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; w++) { t0 += red[w][jl][0]; t1 += red[w][jl][1]; tv += red[w][jl][2]; tb += red[w][jl][3]; }
-        if (!L.dueling) { grads[L.wf2 + j * 2] = t0; grads[L.wf2 + j * 2 + 1] = t1; }
-        else { grads[L.wa + j * 2] = t0; grads[L.wa + j * 2 + 1] = t1; grads[L.wv + j] = tv; }
-        grads[L.bf1 + j] = tb;
+        *reinterpret_cast<float4 *>(hp + ((size_t)grp * H + j) * 4) = make_float4(t0, t1, tv, tb);
     }
 }
 
@@ -578,44 +577,67 @@ __global__ void __launch_bounds__(128) fc1_head_kernel(const float *__restrict__
     }
 }
 
-// split-K partials + bias partials -> the flat gradient vector in TF variable order (HWIO)
+// split-K partials, bias partials and head partials -> the flat gradient vector in TF variable order (HWIO).  One CTA
+// sums 32 consecutive gradient elements: lane = element (coalesced across the partial buffers), the 8 warps take every
+// 8th term, and the 8 sub-sums are added in a fixed order (deterministic for a given batch size).
 struct FinalizeArgs {
     const float *part1, *part2, *part3;             // [splits][rows][N]
-    int s1, s2, s3;                                  // number of splits (fc1 has one)
-    const float *bp1, *bp2, *bp3;                   // bias partials [chunks][N] (the fc1 bias comes from the head kernel)
+    int s1, s2, s3;                                  // number of splits (fc1's weight gradient is written in place)
+    const float *bp1, *bp2, *bp3;                   // bias partials [chunks][N]
     int c1, c2, c3;
+    const float *hp, *hb;                           // head partials [G][H][4], [G][2]
+    int G;
 };
-__global__ void finalize_grads_kernel(const FinalizeArgs a, QnetLayout L, float *__restrict__ grads) {
+__global__ void __launch_bounds__(256) finalize_grads_kernel(const FinalizeArgs a, QnetLayout L, float *__restrict__ grads) {
     tc::pdl_wait();
     tc::pdl_launch();
-    const int end = L.wf1;                   // the fc1 weight gradient is written in place by its GEMM, the fc1 bias by the head kernel
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x) {
-        float s = 0.f;
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5, H = L.hidden;
+    const int k = blockIdx.x * 32 + lane;            // compact index: [0, wf1) then [bf1, total)
+    const int n_compact = L.wf1 + (L.total - L.bf1);
+    const int i = k < L.wf1 ? k : k - L.wf1 + L.bf1;
+    float s = 0.f;
+    if (k < n_compact) {
         if (i < L.b1) {                     // W1 [kh][kw][c][n]
             int e = i - L.w1, n = e & 31, c = (e >> 5) & 3, kw = (e >> 7) & 7, kh = e >> 10;
             int row = ((kh >> 2) * 2 + (kw >> 2)) * 64 + (kh & 3) * 16 + (kw & 3) * 4 + c;
-#pragma unroll 8
-            for (int z = 0; z < a.s1; z++) s += a.part1[((size_t)z * 256 + row) * 32 + n];
+            for (int z = g; z < a.s1; z += 8) s += a.part1[((size_t)z * 256 + row) * 32 + n];
         } else if (i < L.w2) {
             int n = i - L.b1;
-            for (int k = 0; k < a.c1; k++) s += a.bp1[k * 32 + n];
+            for (int z = g; z < a.c1; z += 8) s += a.bp1[z * 32 + n];
         } else if (i < L.b2) {              // W2 [kh][kw][c][n]
             int e = i - L.w2, n = e & 63, c = (e >> 6) & 31, kw = (e >> 11) & 3, kh = e >> 13;
             int row = ((kh >> 1) * 2 + (kw >> 1)) * 128 + (kh & 1) * 64 + (kw & 1) * 32 + c;
-#pragma unroll 8
-            for (int z = 0; z < a.s2; z++) s += a.part2[((size_t)z * 512 + row) * 64 + n];
+            for (int z = g; z < a.s2; z += 8) s += a.part2[((size_t)z * 512 + row) * 64 + n];
         } else if (i < L.w3) {
             int n = i - L.b2;
-            for (int k = 0; k < a.c2; k++) s += a.bp2[k * 64 + n];
+            for (int z = g; z < a.c2; z += 8) s += a.bp2[z * 64 + n];
         } else if (i < L.b3) {              // W3 [k][n], k natural
             int e = i - L.w3;
-#pragma unroll 8
-            for (int z = 0; z < a.s3; z++) s += a.part3[(size_t)z * 640 * 64 + e];
-        } else {
+            for (int z = g; z < a.s3; z += 8) s += a.part3[(size_t)z * 640 * 64 + e];
+        } else if (i < L.wf1) {
             int n = i - L.b3;
-            for (int k = 0; k < a.c3; k++) s += a.bp3[k * 64 + n];
+            for (int z = g; z < a.c3; z += 8) s += a.bp3[z * 64 + n];
+        } else if (i < L.bf1 + H) {         // fc1 bias
+            int j = i - L.bf1;
+            for (int z = g; z < a.G; z += 8) s += a.hp[((size_t)z * H + j) * 4 + 3];
+        } else if (!L.dueling) {
+            if (i < L.bf2) { int e = i - L.wf2; for (int z = g; z < a.G; z += 8) s += a.hp[((size_t)z * H + (e >> 1)) * 4 + (e & 1)]; }
+            else { int e = i - L.bf2; for (int z = g; z < a.G; z += 8) s += a.hb[z * 2 + e]; }
+        } else {
+            if (i < L.bv) { int j = i - L.wv; for (int z = g; z < a.G; z += 8) s += a.hp[((size_t)z * H + j) * 4 + 2]; }
+            else if (i < L.wa) { for (int z = g; z < a.G; z += 8) s += a.hb[z * 2] + a.hb[z * 2 + 1]; }
+            else if (i < L.ba) { int e = i - L.wa; for (int z = g; z < a.G; z += 8) s += a.hp[((size_t)z * H + (e >> 1)) * 4 + (e & 1)]; }
+            else { int e = i - L.ba; for (int z = g; z < a.G; z += 8) s += (e == 0 ? 0.5f : -0.5f) * (a.hb[z * 2] - a.hb[z * 2 + 1]); }
         }
-        grads[i] = s;
+    }
+    red[g][lane] = s;
+    __syncthreads();
+    if (g == 0 && k < n_compact) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) t += red[w][lane];
+        grads[i] = t;
     }
 }
 
@@ -683,6 +705,7 @@ struct TcState {
     float *part1, *part2, *part3;
     size_t cap1, cap2, cap3;
     float *bp1, *bp2, *bp3;
+    float *hp, *hb;             // head-backward partials per row group
     PackedWeights pw[2];
     TcWeightMaps wm[2];
     std::map<int, TcPlan> plans;
@@ -757,13 +780,15 @@ int make_plan(fb_qnet *n, int B, TcPlan **out) {
     for (int k = 0; k < 4; k++) { p.conv2_d.kb_rowoff[k] = 8 - (k >> 1) * kG2 - (k & 1); p.conv2_d.kb_half[k] = 0; }
     // ---- weight gradients (contract over positions; accumulator = two taps, or the two column halves of P2)
     p.conv1_w.p_total = (int)P1; p.conv1_w.slab_row0 = 0;
-    p.s1 = plan_splits(P1, 74, &p.conv1_w.klen);
+    // split-K: about 24 (conv1) / 4 (conv2, conv3) K-blocks of 64 positions per CTA, one wave of CTAs at most
+    auto splits_for = [](long long P, int kb_per_cta) { long long s = (P / 64 + kb_per_cta - 1) / kb_per_cta; return (int)(s < 1 ? 1 : s > 148 ? 148 : s); };
+    p.s1 = plan_splits(P1, splits_for(P1, 24), &p.conv1_w.klen);
     p.conv1_w.acc_rowoff[0] = 0; p.conv1_w.acc_lbo[0] = 128; p.conv1_w.acc_rowoff[1] = kG1; p.conv1_w.acc_lbo[1] = 128;
     p.conv2_w.p_total = (int)P2; p.conv2_w.slab_row0 = 0;
-    p.s2 = plan_splits(P2, 49, &p.conv2_w.klen);
+    p.s2 = plan_splits(P2, splits_for(P2, 4), &p.conv2_w.klen);
     for (int a = 0; a < 4; a++) { p.conv2_w.acc_rowoff[a] = (a >> 1) * kG2 + (a & 1); p.conv2_w.acc_lbo[a] = 0; }
     p.conv3_w.p_total = (int)P2; p.conv3_w.slab_row0 = -8;
-    p.s3 = plan_splits(P2, 49, &p.conv3_w.klen);
+    p.s3 = plan_splits(P2, splits_for(P2, 4), &p.conv3_w.klen);
     {   // taps 0..8 at rows {0,1,2,7,8,9,14,15,16}; pairs (0,1) (2,3) (4,5) (6,7) (8,-): second atom LBO bytes further
         const int off[5] = {0, 2, 8, 14, 16};
         const uint32_t lbo[5] = {128, 5 * 128, 128, 128, 128};
@@ -806,11 +831,12 @@ int tc_state_create(fb_qnet *n) {
     FB_CUDA_OK(alloc_bf(&t->dh1, B * H));
     FB_CUDA_OK(alloc_bf(&t->dz3, B * kP2 * 64)); FB_CUDA_OK(alloc_bf(&t->dz2, B * kP2 * 64)); FB_CUDA_OK(alloc_bf(&t->dp2, B * kP2 * 128));
     FB_CUDA_OK(alloc_bf(&t->dz1, B * kP1 * 32));
-    t->cap1 = 76; t->cap2 = 50; t->cap3 = 50;              // plan_splits never exceeds its target
+    t->cap1 = 150; t->cap2 = 150; t->cap3 = 150;              // plan_splits never exceeds its target
     FB_CUDA_OK(alloc_f(&t->part1, t->cap1 * 256 * 32)); FB_CUDA_OK(alloc_f(&t->part2, t->cap2 * 512 * 64));
     FB_CUDA_OK(alloc_f(&t->part3, t->cap3 * 640 * 64));
     FB_CUDA_OK(alloc_f(&t->bp1, ((B * kP1 + kChunk1 - 1) / kChunk1) * 32)); FB_CUDA_OK(alloc_f(&t->bp2, ((B * kP2 + kChunk23 - 1) / kChunk23) * 64));
     FB_CUDA_OK(alloc_f(&t->bp3, ((B * kP2 + kChunk23 - 1) / kChunk23) * 64));
+    FB_CUDA_OK(alloc_f(&t->hp, ((B + kHeadRows - 1) / kHeadRows) * H * 4)); FB_CUDA_OK(alloc_f(&t->hb, ((B + kHeadRows - 1) / kHeadRows) * 2 + 2));
     for (int s = 0; s < 2; s++) {
         PackedWeights &w = t->pw[s];
         FB_CUDA_OK(alloc_bf(&w.w1p, kC1 * kK1)); FB_CUDA_OK(alloc_bf(&w.w2p, kC2 * kK2)); FB_CUDA_OK(alloc_bf(&w.w3p, kC3 * kK3));
@@ -845,7 +871,7 @@ void tc_state_destroy(fb_qnet *n) {
         void *fs[] = {f.x2, f.z1, f.p2, f.a2, f.a3, f.parth, f.h1};
         for (void *p : fs) cudaFree(p);
     }
-    void *ps[] = {t->dh1, t->dz3, t->dz2, t->dp2, t->dz1, t->part1, t->part2, t->part3, t->bp1, t->bp2, t->bp3};
+    void *ps[] = {t->dh1, t->dz3, t->dz2, t->dp2, t->dz1, t->part1, t->part2, t->part3, t->bp1, t->bp2, t->bp3, t->hp, t->hb};
     for (void *p : ps) cudaFree(p);
     for (int s = 0; s < 2; s++) {
         PackedWeights &w = t->pw[s];
@@ -963,7 +989,8 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     qnet_launch_td_loss(n->q, n->q_next, n->q_next_online, a.actions, a.rewards, a.terminals, a.isw, B, a.global_batch, a.variant, a.gamma,
                         a.loss_sum, n->dq, a.loss_out, a.abs_err, a.q_target, st);
     // ---- backward.  head: fp32 gradients of the head variables and the fc1 bias straight into grads, dh1 as bf16
-    FB_CUDA_OK(tc::launch_pdl(head_backward_tc_kernel, dim3(H / 32 + 1), dim3(256), 0, st, f.h1, n->dq, a.params, L, B, a.grads, t->dh1));
+    const int G = (B + kHeadRows - 1) / kHeadRows;
+    FB_CUDA_OK(tc::launch_pdl(head_backward_tc_kernel, dim3(H / 32 + 1, G), dim3(256), 0, st, f.h1, n->dq, a.params, L, B, t->hp, t->hb, t->dh1));
     FB_CUDA_OK(fork(st, sx));
     // fc1: dW = a3^T dh1 (aux, written in place), dz3 = (dh1 Wf1^T) * relu'(a3)
     FB_CUDA_OK((launch_tc_gemm<128, 1>(p->a3_m, p->dh1_b, p->fc1_w, dim3(13, H / 128, 1), EpiStoreF32{a.grads + L.wf1, kFlat, H, 0}, sx)));
@@ -985,8 +1012,9 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     cj.j[2] = ColsumJob{t->dz3, t->bp3, P2, 64, kChunk23, c1 + c23};
     FB_CUDA_OK(tc::launch_pdl(colsum_kernel, dim3(c1 + 2 * c23), dim3(256), 0, st, cj));
     FB_CUDA_OK(fork(sx, st));
-    FinalizeArgs fa{t->part1, t->part2, t->part3, p->s1, p->s2, p->s3, t->bp1, t->bp2, t->bp3, c1, c23, c23};
-    FB_CUDA_OK(tc::launch_pdl(finalize_grads_kernel, dim3(296), dim3(256), 0, st, fa, L, a.grads));
+    FinalizeArgs fa{t->part1, t->part2, t->part3, p->s1, p->s2, p->s3, t->bp1, t->bp2, t->bp3, c1, c23, c23, t->hp, t->hb, G};
+    const int n_compact = L.wf1 + (L.total - L.bf1);
+    FB_CUDA_OK(tc::launch_pdl(finalize_grads_kernel, dim3((n_compact + 31) / 32), dim3(256), 0, st, fa, L, a.grads));
     return FB_OK;
 }
 
