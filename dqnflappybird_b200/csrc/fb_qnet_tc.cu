@@ -491,23 +491,23 @@ __global__ void __launch_bounds__(256) colsum_kernel(ColsumJobs jobs) {
 constexpr int kHeadRows = 256;                      // rows of the minibatch per head-backward CTA row group
 __global__ void __launch_bounds__(256) head_backward_tc_kernel(const float *__restrict__ h1, const float *__restrict__ dq,
                                                                const float *__restrict__ params, QnetLayout L, int B,
-                                                               float *__restrict__ hp /* [G][H][4] */, float *__restrict__ hb /* [G][2] */,
-                                                               bf16 *__restrict__ dh1) {
+                                                               float *__restrict__ hp /* [G][H][4] */, float *__restrict__ hb /* [G][4] */,
+                                                               const float *__restrict__ loss_terms, bf16 *__restrict__ dh1) {
     tc::pdl_wait();
     tc::pdl_launch();
     __shared__ float red[8][32][4];
     const int H = L.hidden, grp = blockIdx.y, b0 = grp * kHeadRows, b1 = min(B, b0 + kHeadRows);
     if ((int)blockIdx.x == H / 32) {                 // head bias partials: sum_b dq over this row group
-        float s0 = 0.f, s1 = 0.f;
-        for (int b = b0 + threadIdx.x; b < b1; b += 256) { s0 += dq[b * 2]; s1 += dq[b * 2 + 1]; }
+        float s0 = 0.f, s1 = 0.f, sl = 0.f;
+        for (int b = b0 + threadIdx.x; b < b1; b += 256) { s0 += dq[b * 2]; s1 += dq[b * 2 + 1]; sl += loss_terms[b]; }
 #pragma unroll
-        for (int o = 16; o; o >>= 1) { s0 += __shfl_xor_sync(~0u, s0, o); s1 += __shfl_xor_sync(~0u, s1, o); }
-        if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0][0] = s0; red[threadIdx.x >> 5][0][1] = s1; }
+        for (int o = 16; o; o >>= 1) { s0 += __shfl_xor_sync(~0u, s0, o); s1 += __shfl_xor_sync(~0u, s1, o); sl += __shfl_xor_sync(~0u, sl, o); }
+        if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0][0] = s0; red[threadIdx.x >> 5][0][1] = s1; red[threadIdx.x >> 5][0][2] = sl; }
         __syncthreads();
         if (threadIdx.x == 0) {
-            float t0 = 0.f, t1 = 0.f;
-            for (int w = 0; w < 8; w++) { t0 += red[w][0][0]; t1 += red[w][0][1]; }
-            hb[grp * 2] = t0; hb[grp * 2 + 1] = t1;
+            float t0 = 0.f, t1 = 0.f, tl = 0.f;
+            for (int w = 0; w < 8; w++) { t0 += red[w][0][0]; t1 += red[w][0][1]; tl += red[w][0][2]; }
+            hb[grp * 4] = t0; hb[grp * 4 + 1] = t1; hb[grp * 4 + 2] = tl;
         }
         return;
     }
@@ -544,9 +544,18 @@ __global__ void __launch_bounds__(256) head_backward_tc_kernel(const float *__re
 // fc1 split-K finish fused with the Q head (BrainDQN.py:146-154; dueling BrainDuelingDQN_CC.py:68-77): one CTA per
 // sample sums the K-split partials in order, adds the bias, applies ReLU, keeps h1 (fp32) for backward and reduces
 // the two (three) head dot products.
+// The TD target / loss of sample b needs only Q(s)[b] and Q(s')[b] (td_loss_kernel in fb_qnet.cu): when `td.on` the CTA that has
+// just produced Q(s)[b] also writes dLoss/dQ[b], |error|, y and the sample's loss term (summed later in a fixed order).
+struct TdFuse {
+    int on, variant, loss_sum, global_batch;
+    double gamma;
+    const float *q_next, *q_next_online, *rewards, *isw;
+    const uint8_t *actions, *terminals;
+    float *dq, *abs_err, *q_target, *loss_terms;
+};
 __global__ void __launch_bounds__(128) fc1_head_kernel(const float *__restrict__ part, int splits, size_t split_stride,
                                                       const float *__restrict__ params, QnetLayout L, int B, float *__restrict__ h1,
-                                                      float *__restrict__ q) {
+                                                      float *__restrict__ q, const TdFuse td) {
     tc::pdl_wait();
     tc::pdl_launch();
     __shared__ float red[4][3];
@@ -574,6 +583,22 @@ __global__ void __launch_bounds__(128) fc1_head_kernel(const float *__restrict__
             float mean = (a0 + a1) * 0.5f;
             q[b * 2] = v + (a0 - mean); q[b * 2 + 1] = v + (a1 - mean);
         }
+        if (td.on) {                                  // exactly td_loss_kernel's arithmetic for this sample
+            float x;
+            if (td.variant == 2) { int am = td.q_next_online[b * 2 + 1] > td.q_next_online[b * 2] ? 1 : 0; x = td.q_next[b * 2 + am]; }
+            else x = fmaxf(td.q_next[b * 2], td.q_next[b * 2 + 1]);
+            const float rf = td.rewards[b];
+            const double r = rf == 0.1f ? 0.1 : (double)rf;
+            const float y = (float)(td.terminals[b] ? r : r + td.gamma * (double)x);
+            const int a = td.actions[b] ? 1 : 0;
+            const float err = y - q[b * 2 + a];
+            const float w = td.isw ? td.isw[b] : 1.f;
+            const float scale = td.loss_sum ? 1.f : 1.f / (float)td.global_batch;
+            td.dq[b * 2 + a] = -2.f * w * err * scale; td.dq[b * 2 + (1 - a)] = 0.f;
+            td.loss_terms[b] = w * err * err * scale;
+            if (td.abs_err) td.abs_err[b] = fabsf(err);
+            if (td.q_target) td.q_target[b] = y;
+        }
     }
 }
 
@@ -585,8 +610,9 @@ struct FinalizeArgs {
     int s1, s2, s3;                                  // number of splits (fc1's weight gradient is written in place)
     const float *bp1, *bp2, *bp3;                   // bias partials [chunks][N]
     int c1, c2, c3;
-    const float *hp, *hb;                           // head partials [G][H][4], [G][2]
+    const float *hp, *hb;                           // head partials [G][H][4], [G][4] (dq sums, loss)
     int G;
+    float *loss_out;
 };
 __global__ void __launch_bounds__(256) finalize_grads_kernel(const FinalizeArgs a, QnetLayout L, float *__restrict__ grads) {
     tc::pdl_wait();
@@ -623,12 +649,12 @@ __global__ void __launch_bounds__(256) finalize_grads_kernel(const FinalizeArgs 
             for (int z = g; z < a.G; z += 8) s += a.hp[((size_t)z * H + j) * 4 + 3];
         } else if (!L.dueling) {
             if (i < L.bf2) { int e = i - L.wf2; for (int z = g; z < a.G; z += 8) s += a.hp[((size_t)z * H + (e >> 1)) * 4 + (e & 1)]; }
-            else { int e = i - L.bf2; for (int z = g; z < a.G; z += 8) s += a.hb[z * 2 + e]; }
+            else { int e = i - L.bf2; for (int z = g; z < a.G; z += 8) s += a.hb[z * 4 + e]; }
         } else {
             if (i < L.bv) { int j = i - L.wv; for (int z = g; z < a.G; z += 8) s += a.hp[((size_t)z * H + j) * 4 + 2]; }
-            else if (i < L.wa) { for (int z = g; z < a.G; z += 8) s += a.hb[z * 2] + a.hb[z * 2 + 1]; }
+            else if (i < L.wa) { for (int z = g; z < a.G; z += 8) s += a.hb[z * 4] + a.hb[z * 4 + 1]; }
             else if (i < L.ba) { int e = i - L.wa; for (int z = g; z < a.G; z += 8) s += a.hp[((size_t)z * H + (e >> 1)) * 4 + (e & 1)]; }
-            else { int e = i - L.ba; for (int z = g; z < a.G; z += 8) s += (e == 0 ? 0.5f : -0.5f) * (a.hb[z * 2] - a.hb[z * 2 + 1]); }
+            else { int e = i - L.ba; for (int z = g; z < a.G; z += 8) s += (e == 0 ? 0.5f : -0.5f) * (a.hb[z * 4] - a.hb[z * 4 + 1]); }
         }
     }
     red[g][lane] = s;
@@ -638,6 +664,11 @@ __global__ void __launch_bounds__(256) finalize_grads_kernel(const FinalizeArgs 
 #pragma unroll
         for (int w = 0; w < 8; w++) t += red[w][lane];
         grads[i] = t;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.loss_out) {       // the loss: row-group sums in order
+        float t = 0.f;
+        for (int z = 0; z < a.G; z++) t += a.hb[z * 4 + 2];
+        *a.loss_out = t;
     }
 }
 
@@ -706,6 +737,7 @@ struct TcState {
     size_t cap1, cap2, cap3;
     float *bp1, *bp2, *bp3;
     float *hp, *hb;             // head-backward partials per row group
+    float *loss_terms;          // per-sample loss terms
     PackedWeights pw[2];
     TcWeightMaps wm[2];
     std::map<int, TcPlan> plans;
@@ -836,7 +868,8 @@ int tc_state_create(fb_qnet *n) {
     FB_CUDA_OK(alloc_f(&t->part3, t->cap3 * 640 * 64));
     FB_CUDA_OK(alloc_f(&t->bp1, ((B * kP1 + kChunk1 - 1) / kChunk1) * 32)); FB_CUDA_OK(alloc_f(&t->bp2, ((B * kP2 + kChunk23 - 1) / kChunk23) * 64));
     FB_CUDA_OK(alloc_f(&t->bp3, ((B * kP2 + kChunk23 - 1) / kChunk23) * 64));
-    FB_CUDA_OK(alloc_f(&t->hp, ((B + kHeadRows - 1) / kHeadRows) * H * 4)); FB_CUDA_OK(alloc_f(&t->hb, ((B + kHeadRows - 1) / kHeadRows) * 2 + 2));
+    FB_CUDA_OK(alloc_f(&t->hp, ((B + kHeadRows - 1) / kHeadRows) * H * 4)); FB_CUDA_OK(alloc_f(&t->hb, ((B + kHeadRows - 1) / kHeadRows) * 4 + 4));
+    FB_CUDA_OK(alloc_f(&t->loss_terms, B));
     for (int s = 0; s < 2; s++) {
         PackedWeights &w = t->pw[s];
         FB_CUDA_OK(alloc_bf(&w.w1p, kC1 * kK1)); FB_CUDA_OK(alloc_bf(&w.w2p, kC2 * kK2)); FB_CUDA_OK(alloc_bf(&w.w3p, kC3 * kK3));
@@ -871,7 +904,7 @@ void tc_state_destroy(fb_qnet *n) {
         void *fs[] = {f.x2, f.z1, f.p2, f.a2, f.a3, f.parth, f.h1};
         for (void *p : fs) cudaFree(p);
     }
-    void *ps[] = {t->dh1, t->dz3, t->dz2, t->dp2, t->dz1, t->part1, t->part2, t->part3, t->bp1, t->bp2, t->bp3, t->hp, t->hb};
+    void *ps[] = {t->dh1, t->dz3, t->dz2, t->dp2, t->dz1, t->part1, t->part2, t->part3, t->bp1, t->bp2, t->bp3, t->hp, t->hb, t->loss_terms};
     for (void *p : ps) cudaFree(p);
     for (int s = 0; s < 2; s++) {
         PackedWeights &w = t->pw[s];
@@ -918,11 +951,15 @@ int tc_slot_for(fb_qnet *n, const float *params_dev, int want_slot, cudaStream_t
 
 static FrameView g_probe_view;                    // frames of the last forward (the fused conv1 probe re-reads them)
 // keep != 0: this forward's activations feed a backward pass (Z1 and, for the conv1 weight gradient, X2 are written)
-static int tc_forward_impl(fb_qnet *n, int slot, int w, const float *params_dev, FrameView fv, int B, float *q_out, int keep, cudaStream_t st);
+// td != nullptr: the TD target / loss is fused into the head kernel; `join` (if any) is waited for first -- it marks the end
+// of the Q(s') forward on the other stream
+static int tc_forward_impl(fb_qnet *n, int slot, int w, const float *params_dev, FrameView fv, int B, float *q_out, int keep, cudaStream_t st,
+                           const TdFuse *td = nullptr, cudaEvent_t join = nullptr);
 int tc_forward(fb_qnet *n, int slot, int w, const float *params_dev, FrameView fv, int B, float *q_out, cudaStream_t st) {
     return tc_forward_impl(n, slot, w, params_dev, fv, B, q_out, 0, st);
 }
-static int tc_forward_impl(fb_qnet *n, int slot, int w, const float *params_dev, FrameView fv, int B, float *q_out, int keep, cudaStream_t st) {
+static int tc_forward_impl(fb_qnet *n, int slot, int w, const float *params_dev, FrameView fv, int B, float *q_out, int keep, cudaStream_t st,
+                           const TdFuse *td, cudaEvent_t join) {
     TcState *t = n->tc;
     FB_REQUIRE(t != nullptr && B > 0 && B <= n->max_batch && (w == 0 || w == 1), "tc_forward: bad argument");
     TcPlan *p;
@@ -948,8 +985,10 @@ static int tc_forward_impl(fb_qnet *n, int slot, int w, const float *params_dev,
     FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4, 1>(p->a2_s[w], wm.w3p, p->conv3, t->n_sms, EpiConv3{f.a3, params_dev + L.b3, P2}, st)));
     FB_CUDA_OK((launch_tc_gemm<128, 2>(p->a3_k[w], wm.wf1n, p->fc1, dim3((B + 127) / 128, L.hidden / 128, p->sf),
                                        EpiStoreF32{f.parth, B, L.hidden, (size_t)n->max_batch * L.hidden}, st)));
+    if (join) FB_CUDA_OK(cudaStreamWaitEvent(st, join, 0));
+    TdFuse none{};
     FB_CUDA_OK(tc::launch_pdl(fc1_head_kernel, dim3(B), dim3(128), 0, st, f.parth, p->sf, (size_t)n->max_batch * L.hidden, params_dev, L, B,
-                              f.h1, q_out));
+                              f.h1, q_out, td ? *td : none));
     return FB_OK;
 }
 
@@ -984,13 +1023,16 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     rc = a.variant == 0 ? tc_forward(n, 0, 1, a.params, a.fn, B, n->q_next, sx) : tc_forward(n, 1, 1, a.target, a.fn, B, n->q_next, sx);
     if (rc) return rc;
     // ---- main: Q(s) with the online net; its activations stay in workspace 0 for the backward pass
-    rc = tc_forward_impl(n, 0, 0, a.params, a.fs, B, n->q, 1, st); if (rc) return rc;
-    FB_CUDA_OK(fork(sx, st));
-    qnet_launch_td_loss(n->q, n->q_next, n->q_next_online, a.actions, a.rewards, a.terminals, a.isw, B, a.global_batch, a.variant, a.gamma,
-                        a.loss_sum, n->dq, a.loss_out, a.abs_err, a.q_target, st);
+    // the TD target, loss and dLoss/dQ come out of its head kernel, which first waits for Q(s') from the other stream
+    FB_CUDA_OK(cudaEventRecord(t->ev[e], sx));
+    TdFuse td{1, a.variant, a.loss_sum, a.global_batch, a.gamma, n->q_next, n->q_next_online, a.rewards, a.isw, a.actions, a.terminals,
+              n->dq, a.abs_err, a.q_target, t->loss_terms};
+    rc = tc_forward_impl(n, 0, 0, a.params, a.fs, B, n->q, 1, st, &td, t->ev[e]); if (rc) return rc;
+    e++;
     // ---- backward.  head: fp32 gradients of the head variables and the fc1 bias straight into grads, dh1 as bf16
     const int G = (B + kHeadRows - 1) / kHeadRows;
-    FB_CUDA_OK(tc::launch_pdl(head_backward_tc_kernel, dim3(H / 32 + 1, G), dim3(256), 0, st, f.h1, n->dq, a.params, L, B, t->hp, t->hb, t->dh1));
+    FB_CUDA_OK(tc::launch_pdl(head_backward_tc_kernel, dim3(H / 32 + 1, G), dim3(256), 0, st, f.h1, n->dq, a.params, L, B, t->hp, t->hb,
+                              t->loss_terms, t->dh1));
     FB_CUDA_OK(fork(st, sx));
     // fc1: dW = a3^T dh1 (aux, written in place), dz3 = (dh1 Wf1^T) * relu'(a3)
     FB_CUDA_OK((launch_tc_gemm<128, 1>(p->a3_m, p->dh1_b, p->fc1_w, dim3(13, H / 128, 1), EpiStoreF32{a.grads + L.wf1, kFlat, H, 0}, sx)));
@@ -1012,7 +1054,7 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     cj.j[2] = ColsumJob{t->dz3, t->bp3, P2, 64, kChunk23, c1 + c23};
     FB_CUDA_OK(tc::launch_pdl(colsum_kernel, dim3(c1 + 2 * c23), dim3(256), 0, st, cj));
     FB_CUDA_OK(fork(sx, st));
-    FinalizeArgs fa{t->part1, t->part2, t->part3, p->s1, p->s2, p->s3, t->bp1, t->bp2, t->bp3, c1, c23, c23, t->hp, t->hb, G};
+    FinalizeArgs fa{t->part1, t->part2, t->part3, p->s1, p->s2, p->s3, t->bp1, t->bp2, t->bp3, c1, c23, c23, t->hp, t->hb, G, a.loss_out};
     const int n_compact = L.wf1 + (L.total - L.bf1);
     FB_CUDA_OK(tc::launch_pdl(finalize_grads_kernel, dim3((n_compact + 31) / 32), dim3(256), 0, st, fa, L, a.grads));
     return FB_OK;

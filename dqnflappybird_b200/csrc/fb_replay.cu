@@ -116,23 +116,24 @@ struct GatherArgs {
     int32_t *env_out, *k_out;    // optional
 };
 
-__global__ void __launch_bounds__(256) gather_kernel(GatherArgs g) {
-    int b = blockIdx.x;
+// one CTA per (sample, frame): 6,400 bytes, every thread's loads issued together (the ring is HBM-cold)
+__global__ void __launch_bounds__(128) gather_kernel(GatherArgs g) {
+    const int b = blockIdx.x, f = blockIdx.y;
     if (b >= g.batch) return;
     long long k_lo = g.t - g.cap + 1; if (k_lo < 1) k_lo = 1;
     long long cnt = g.t - k_lo + 1;
     long long j = g.idx[b], k; int e;
     if (!g.per) { e = (int)(j / cnt); k = k_lo + j % cnt; }
     else { e = (int)(j / g.cap); long long p = j % g.cap; long long back = (g.t - 1 - p) % g.cap; k = g.t - back; }
-    const uint4 *ring4 = reinterpret_cast<const uint4 *>(g.ring);
-    uint4 *dst = reinterpret_cast<uint4 *>(g.frames) + (size_t)b * 2000;
+    long long tf = k - 4 + f; if (tf < 0) tf = 0;                     // setInitState replication of frame 0
+    const uint4 *src = reinterpret_cast<const uint4 *>(g.ring) + ((size_t)e * g.L + (size_t)(tf % g.L)) * 400;
+    uint4 *dst = reinterpret_cast<uint4 *>(g.frames) + (size_t)b * 2000 + f * 400;
+    uint4 v[4];
 #pragma unroll
-    for (int f = 0; f < 5; f++) {
-        long long tf = k - 4 + f; if (tf < 0) tf = 0;                 // setInitState replication of frame 0
-        const uint4 *src = ring4 + ((size_t)e * g.L + (size_t)(tf % g.L)) * 400;
-        for (int q = threadIdx.x; q < 400; q += 256) dst[f * 400 + q] = __ldg(src + q);
-    }
-    if (threadIdx.x == 0) {
+    for (int q = 0; q < 4; q++) { int i = threadIdx.x + q * 128; v[q] = i < 400 ? __ldg(src + i) : make_uint4(0u, 0u, 0u, 0u); }
+#pragma unroll
+    for (int q = 0; q < 4; q++) { int i = threadIdx.x + q * 128; if (i < 400) dst[i] = v[q]; }
+    if (f == 0 && threadIdx.x == 0) {
         size_t m = (size_t)(k % g.L) * g.N + e;
         g.a_out[b] = g.act[m]; g.r_out[b] = g.rew[m]; g.t_out[b] = g.term[m];
         if (g.env_out) g.env_out[b] = e;
@@ -340,7 +341,7 @@ extern "C" int fb_replay_gather(fb_replay *r, const uint8_t *ring_dev, const uin
                "fb_replay_gather: bad argument");
     GatherArgs g{ring_dev, r->N, r->L, act_dev, rew_dev, term_dev, t, r->C, prioritized_index, idx_dev, batch,
                  frames_out_dev, act_out_dev, rew_out_dev, term_out_dev, env_out_dev, k_out_dev};
-    gather_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(g);
+    gather_kernel<<<dim3(batch, 5), 128, 0, (cudaStream_t)stream>>>(g);
     FB_CUDA_OK(cudaGetLastError());
     return FB_OK;
 }
