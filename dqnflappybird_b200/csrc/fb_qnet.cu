@@ -452,7 +452,10 @@ extern "C" int fb_qnet_forward(fb_qnet *n, const float *params_dev, const uint8_
     FB_REQUIRE(n && params_dev && frames_dev && chan_off && q_out_dev && batch > 0, "fb_qnet_forward: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     int slot = 0;
-    if (n->precision == FB_PRECISION_BF16) { int rc = tc_slot_for(n, params_dev, -1, st, &slot); if (rc) return rc; }
+    if (n->precision == FB_PRECISION_BF16) {
+        int rc = tc_slot_for(n, params_dev, -1, st, &slot); if (rc) return rc;
+        return tc_forward_chunks(n, slot, params_dev, frames_dev, sample_stride, chan_off, batch, q_out_dev, st);
+    }
     for (int b0 = 0; b0 < batch; b0 += n->max_batch) {
         int B = min(n->max_batch, batch - b0);
         FrameView fv = make_view(frames_dev + (size_t)b0 * sample_stride, sample_stride, chan_off);

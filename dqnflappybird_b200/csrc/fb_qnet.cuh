@@ -82,6 +82,8 @@ void tc_state_destroy(fb_qnet *n);
 int tc_pack_weights(fb_qnet *n, const float *params_dev, int slot /* 0 online, 1 target */, cudaStream_t st);
 int tc_slot_for(fb_qnet *n, const float *params_dev, int want_slot, cudaStream_t st, int *slot_out);
 int tc_forward(fb_qnet *n, int slot, int ws, const float *params_dev, FrameView fv, int B, float *q_out, cudaStream_t st);
+int tc_forward_chunks(fb_qnet *n, int slot, const float *params_dev, const uint8_t *frames_dev, long long sample_stride,
+                      const int32_t *chan_off, int batch, float *q_out_dev, cudaStream_t st);
 int tc_loss_backward(fb_qnet *n, const TcTrainArgs &a, cudaStream_t st);
 int tc_adam(fb_qnet *n, float *params_dev, const float *grads_dev, float *m_dev, float *v_dev, float alpha, float beta1, float beta2,
             float eps, float grad_scale, cudaStream_t st);

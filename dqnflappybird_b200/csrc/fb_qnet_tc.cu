@@ -992,6 +992,28 @@ static int tc_forward_impl(fb_qnet *n, int slot, int w, const float *params_dev,
     return FB_OK;
 }
 
+// Acting over more samples than one workspace holds: chunks alternate between the two forward workspaces and the two
+// streams, so one chunk's latency chain (seven kernels) overlaps the other's.
+int tc_forward_chunks(fb_qnet *n, int slot, const float *params_dev, const uint8_t *frames_dev, long long sample_stride,
+                      const int32_t *chan_off, int batch, float *q_out_dev, cudaStream_t st) {
+    TcState *t = n->tc;
+    FB_REQUIRE(t != nullptr, "tc_forward_chunks: no tensor-core state");
+    const int nchunks = (batch + n->max_batch - 1) / n->max_batch;
+    const bool two = nchunks > 1;
+    if (two) { FB_CUDA_OK(cudaEventRecord(t->ev[6], st)); FB_CUDA_OK(cudaStreamWaitEvent(t->aux, t->ev[6], 0)); }
+    int c = 0;
+    for (int b0 = 0; b0 < batch; b0 += n->max_batch, c++) {
+        const int B = min(n->max_batch, batch - b0), w = two ? (c & 1) : 0;
+        FrameView fv;
+        fv.base = frames_dev + (size_t)b0 * sample_stride; fv.sample_stride = sample_stride;
+        for (int k = 0; k < 4; k++) fv.chan_off[k] = chan_off[k];
+        int rc = tc_forward(n, slot, w, params_dev, fv, B, q_out_dev + (size_t)b0 * 2, w ? t->aux : st);
+        if (rc) return rc;
+    }
+    if (two) { FB_CUDA_OK(cudaEventRecord(t->ev[7], t->aux)); FB_CUDA_OK(cudaStreamWaitEvent(st, t->ev[7], 0)); }
+    return FB_OK;
+}
+
 namespace {
 
 // One training step's device work (BrainDQN.py:195-223 and the variants).  Two streams: the critical path
