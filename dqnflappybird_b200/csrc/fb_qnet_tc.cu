@@ -748,6 +748,7 @@ struct TcState {
     std::vector<GraphEntry> graphs;
     int use_graph;
     int fused_conv1;            // opt-in: tc_conv1_fused_kernel instead of pack_x2 + conv1 + pool_pack
+    int pooled_conv1;           // conv1 with the max-pool in its epilogue (slab by TMA from X2)
 };
 
 namespace {
@@ -891,6 +892,7 @@ int tc_state_create(fb_qnet *n) {
     for (auto &e : t->ev) FB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     t->use_graph = 1;
     { const char *e = getenv("FB_TC_FUSED_CONV1"); t->fused_conv1 = (e && e[0] == '1') ? 1 : 0; }
+    { const char *e = getenv("FB_TC_POOLED_CONV1"); t->pooled_conv1 = (e && e[0] == '1') ? 1 : 0; }
     n->tc = t;
     return FB_OK;
 }
@@ -975,7 +977,15 @@ static int tc_forward_impl(fb_qnet *n, int slot, int w, const float *params_dev,
         // HBM bytes, but its slab builders are issue-latency bound (92 us vs 80 us for the three kernels at 2048 samples),
         // so it is opt-in (FB_TC_FUSED_CONV1=1) until they are faster
         if (keep) FB_CUDA_OK(tc::launch_pdl(pack_x2_kernel, dim3((unsigned)(((size_t)P1 * 8 + 255) / 256)), dim3(256), 0, st, fv, B, f.x2));
-        FB_CUDA_OK((launch_tc_conv1_fused<4>(wm.w1p, Conv1FusedParams{fv, B, params_dev + L.b1, keep ? f.z1 : nullptr, f.p2}, t->n_sms, st)));
+        FB_CUDA_OK((launch_tc_conv1_fused<4, false>(p->x2_s[w], wm.w1p, Conv1FusedParams{fv, B, params_dev + L.b1, keep ? f.z1 : nullptr, f.p2},
+                                                   t->n_sms, st)));
+    } else if (t->pooled_conv1) {
+        // opt-in (FB_TC_POOLED_CONV1=1): X2 by pack_x2, then conv1 with the max-pool in its epilogue.  Measured 89 us vs
+        // 35 + 15 us (conv1 + pool) at 2048 samples: the pooled epilogue, not the slab source, is what is slow in the
+        // fused kernels (the same epilogue without the pooling section: 83 us); to be understood before it is a default
+        FB_CUDA_OK(tc::launch_pdl(pack_x2_kernel, dim3((unsigned)(((size_t)P1 * 8 + 255) / 256)), dim3(256), 0, st, fv, B, f.x2));
+        FB_CUDA_OK((launch_tc_conv1_fused<6, true>(p->x2_s[w], wm.w1p, Conv1FusedParams{fv, B, params_dev + L.b1, keep ? f.z1 : nullptr, f.p2},
+                                                  t->n_sms, st)));
     } else {
         FB_CUDA_OK(tc::launch_pdl(pack_x2_kernel, dim3((unsigned)(((size_t)P1 * 8 + 255) / 256)), dim3(256), 0, st, fv, B, f.x2));
         FB_CUDA_OK((launch_tc_conv<32, kSlab1, 1, 4, 6, 1>(p->x2_s[w], wm.w1p, p->conv1, t->n_sms, EpiConv1{f.z1, params_dev + L.b1, P1}, st)));
@@ -1171,9 +1181,12 @@ extern "C" int fb_debug_tc_kernel(fb_qnet *n, int which, int B, int reps, const 
             case 4: FB_CUDA_OK((launch_tc_wgrad<32, 2, kSlabW1, 1, 6>(p->x2_w, p->dz1_b, p->conv1_w, p->s1, EpiStoreF32{t->part1, 256, 32, (size_t)256 * 32}, st))); break;
             case 5: FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4, 1>(p->dz3_s, wm.w3d, p->conv3_d, t->n_sms, EpiConv3Dgrad{t->dz2, f.a2, P2}, st))); break;
             case 6: FB_CUDA_OK((launch_tc_gemm<64, 0>(p->dh1_k, wm.wf1n, p->fc1_d, dim3((B + 127) / 128, kFlat / 64, 1), EpiFc1Dgrad{t->dz3, f.a3, B}, st))); break;
-            case 7: FB_CUDA_OK((launch_tc_conv1_fused<4>(wm.w1p, Conv1FusedParams{g_probe_view, B, params_dev + L.b1, nullptr, f.p2}, t->n_sms, st))); break;
-            case 8: FB_CUDA_OK((launch_tc_conv1_fused<4>(wm.w1p, Conv1FusedParams{g_probe_view, B, params_dev + L.b1, f.z1, f.p2}, t->n_sms, st))); break;
-            default: FB_REQUIRE(false, "fb_debug_tc_kernel: which must be 0..8");
+            case 7: FB_CUDA_OK((launch_tc_conv1_fused<4, false>(p->x2_s[0], wm.w1p, Conv1FusedParams{g_probe_view, B, params_dev + L.b1, nullptr, f.p2}, t->n_sms, st))); break;
+            case 8: FB_CUDA_OK((launch_tc_conv1_fused<4, false>(p->x2_s[0], wm.w1p, Conv1FusedParams{g_probe_view, B, params_dev + L.b1, f.z1, f.p2}, t->n_sms, st))); break;
+            case 9: FB_CUDA_OK((launch_tc_conv1_fused<6, true>(p->x2_s[0], wm.w1p, Conv1FusedParams{g_probe_view, B, params_dev + L.b1, nullptr, f.p2}, t->n_sms, st))); break;
+            case 10: FB_CUDA_OK((launch_tc_conv1_fused<6, true>(p->x2_s[0], wm.w1p, Conv1FusedParams{g_probe_view, B, params_dev + L.b1, f.z1, f.p2}, t->n_sms, st))); break;
+            case 11: FB_CUDA_OK((launch_tc_conv1_fused<6, true>(p->x2_s[0], wm.w1p, Conv1FusedParams{g_probe_view, B, params_dev + L.b1, nullptr, nullptr}, t->n_sms, st))); break;
+            default: FB_REQUIRE(false, "fb_debug_tc_kernel: which must be 0..11");
         }
     }
     return FB_OK;

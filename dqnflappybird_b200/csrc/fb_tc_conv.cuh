@@ -363,8 +363,12 @@ struct Conv1FusedParams {
     __nv_bfloat16 *p2;          // [B*49][128]
 };
 
-template <int S>
-__global__ void __launch_bounds__(kFusedThreads, 1) tc_conv1_fused_kernel(const __grid_constant__ CUtensorMap mapB, const Conv1FusedParams g) {
+// FROM_X2: the slab comes by TMA from a materialised X2 (pack_x2_kernel) instead of the in-kernel builders -- conv1 with
+// only the pooling fused (no Z1 round trip, no pool kernel); 192 threads.
+template <int S, bool FROM_X2>
+__global__ void __launch_bounds__(FROM_X2 ? 192 : kFusedThreads, 1) tc_conv1_fused_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                                          const __grid_constant__ CUtensorMap mapB,
+                                                                                          const Conv1FusedParams g) {
     constexpr int BN = 32, NKB = 4;
     constexpr uint32_t STAGE = kSlabF * 128, BBLK = BN * 128, B_BYTES = NKB * BBLK, ZS_BYTES = 128 * BN * 2;
     extern __shared__ uint8_t smem_raw[];
@@ -401,7 +405,21 @@ __global__ void __launch_bounds__(kFusedThreads, 1) tc_conv1_fused_kernel(const 
     tc::pdl_launch();
     __syncthreads();
 
-    if (warp == 0) {
+    if (warp == 0 && FROM_X2) {
+        // ===== slab loader: one TMA box of 152 rows of X2 per tile
+        const bool leader = tc::elect_one();
+        int i = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, i++) {
+            const int s = i % S;
+            tc::mbar_wait(tc::smem_u32(&bar_empty[s]), ((i / S) & 1) ^ 1u);
+            if (leader) {
+                const uint32_t full = tc::smem_u32(&bar_full[s]);
+                tc::mbar_expect_tx(full, STAGE);
+                tc::tma_load_2d(smem_a + s * STAGE, &mapA, 0, (tile >> 2) * 441 + (tile & 3) * kTilePos1, full);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 0) {
         // ===== raw pixel loader: four bulk copies per tile (one contiguous run of rows per frame), kRawStages tiles ahead
         const bool leader = tc::elect_one();
         int i = 0;
@@ -490,6 +508,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) tc_conv1_fused_kernel(const 
 #pragma unroll
                 for (int k = 0; k < 4; k++) d[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
             }
+            if (g.p2 == nullptr) continue;               // (measurement only: no pooling, no output)
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (et < 120) {
                 const int ph_l = et / 40, rem = et - ph_l * 40, pw = rem >> 2, cg = rem & 3, ph = 3 * tq + ph_l;
@@ -514,18 +533,18 @@ __global__ void __launch_bounds__(kFusedThreads, 1) tc_conv1_fused_kernel(const 
     if (warp == 1) tc::tmem_dealloc(tmem, 64);
 }
 
-template <int S>
-static cudaError_t launch_tc_conv1_fused(const CUtensorMap &mb, const Conv1FusedParams &g, int max_ctas, cudaStream_t st) {
+template <int S, bool FROM_X2>
+static cudaError_t launch_tc_conv1_fused(const CUtensorMap &ma, const CUtensorMap &mb, const Conv1FusedParams &g, int max_ctas, cudaStream_t st) {
     static bool configured = false;
-    auto kern = tc_conv1_fused_kernel<S>;
-    constexpr size_t smem = 4 * 32 * 128 + (size_t)S * kSlabF * 128 + 2 * 128 * 32 * 2 + kRawStages * kRawBytes + 1024;
+    auto kern = tc_conv1_fused_kernel<S, FROM_X2>;
+    constexpr size_t smem = 4 * 32 * 128 + (size_t)S * kSlabF * 128 + 2 * 128 * 32 * 2 + (FROM_X2 ? 0 : kRawStages * kRawBytes) + 1024;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     int grid = 4 * g.B < max_ctas ? 4 * g.B : max_ctas;
-    return tc::launch_pdl(kern, dim3(grid), dim3(kFusedThreads), smem, st, mb, g);
+    return tc::launch_pdl(kern, dim3(grid), dim3(FROM_X2 ? 192 : kFusedThreads), smem, st, ma, mb, g);
 }
 
 }  // namespace

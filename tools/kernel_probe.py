@@ -14,9 +14,9 @@ import torch  # noqa: E402
 from dqnflappybird_b200 import _lib, qnet  # noqa: E402
 from dqnflappybird_b200.game import GameState  # noqa: E402
 
-NAMES = ["conv1_fwd", "conv2_fwd", "conv3_fwd", "fc1_fwd", "conv1_wgrad", "conv3_dgrad", "fc1_dgrad", "conv1_fused_act", "conv1_fused_train"]
+NAMES = ["conv1_fwd", "conv2_fwd", "conv3_fwd", "fc1_fwd", "conv1_wgrad", "conv3_dgrad", "fc1_dgrad", "conv1_fused_act", "conv1_fused_train", "conv1_pooled_act", "conv1_pooled_train", "conv1_pooled_nopool"]
 # algorithmic FLOP per sample: 2 * M * N * K of the reference's own GEMM view
-FLOP = [6553600, 1638400, 1843200, 1638400, 6553600, 1843200, 1638400, 6553600, 6553600]
+FLOP = [6553600, 1638400, 1843200, 1638400, 6553600, 1843200, 1638400, 6553600, 6553600, 6553600, 6553600, 6553600]
 
 
 def main():
