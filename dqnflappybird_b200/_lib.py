@@ -83,7 +83,7 @@ _SIGNATURES = {
     "fb_qnet_get_precision": ([_vp], C.c_int),
     "fb_qnet_invalidate": ([_vp], C.c_int),
     "fb_qnet_use_graphs": ([_vp, C.c_int], C.c_int),
-    "fb_qnet_use_fused_conv1": ([_vp, C.c_int], C.c_int),
+    "fb_qnet_set_conv1_mode": ([_vp, C.c_int], C.c_int),
     "fb_qnet_param_count": ([_vp], C.c_int),
     "fb_qnet_layout": ([_vp, _i32p], C.c_int),
     "fb_qnet_forward": ([_vp, _f32p, _u8p, C.c_longlong, _i32p, C.c_int, _f32p, _vp], C.c_int),

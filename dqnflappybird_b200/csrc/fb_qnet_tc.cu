@@ -206,36 +206,51 @@ __device__ __forceinline__ void load_bf16x16(const bf16 *src, float (&v)[16]) {
 
 // An epilogue sees 16 consecutive fp32 columns of one output row; `bs` is the layer bias staged in shared memory by the
 // kernel when the functor asks for it (bias != nullptr) -- a global load per column per tile was what bounded the tiles.
+// sixteen bias values of the staged layer bias, loaded unconditionally and vectorised BEFORE any per-row predicate: with
+// the shared-memory loads inside `ok ? ... : 0` the compiler emits one divergent block per pair of columns
+__device__ __forceinline__ void load_bias16(const float *bs, int col, float (&b)[16]) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float4 t4 = reinterpret_cast<const float4 *>(bs + col)[k];
+        b[4 * k] = t4.x; b[4 * k + 1] = t4.y; b[4 * k + 2] = t4.z; b[4 * k + 3] = t4.w;
+    }
+}
 struct EpiConv1 {               // rows on the 21-grid -> Z1 [B*441][32] = relu(conv + b), zeros at invalid positions
     bf16 *z1; const float *bias; int rows;
     __device__ void operator()(int row, int col, float (&v)[16], int, const float *bs) const {
+        float b[16];
+        load_bias16(bs, col, b);
         if (row >= rows) return;
         int p = row % kP1;
-        bool ok = (p / kG1) < 20 && (p % kG1) < 20;
+        const float keep = ((p / kG1) < 20 && (p % kG1) < 20) ? 1.f : 0.f;
 #pragma unroll
-        for (int i = 0; i < 16; i++) v[i] = ok ? fmaxf(v[i] + bs[col + i], 0.f) : 0.f;
+        for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i] + b[i], 0.f) * keep;
         store_bf16x16(z1 + (size_t)row * kC1 + col, v);
     }
 };
 struct EpiGrid7 {               // conv2: rows on the 7-grid -> A2 [B*49][64], zeros at invalid positions
     bf16 *out; const float *bias; int rows;
     __device__ void operator()(int row, int col, float (&v)[16], int, const float *bs) const {
+        float b[16];
+        load_bias16(bs, col, b);
         if (row >= rows) return;
         int p = row % kP2;
-        bool ok = (p / kG2) < 5 && (p % kG2) < 5;
+        const float keep = ((p / kG2) < 5 && (p % kG2) < 5) ? 1.f : 0.f;
 #pragma unroll
-        for (int i = 0; i < 16; i++) v[i] = ok ? fmaxf(v[i] + bs[col + i], 0.f) : 0.f;
+        for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i] + b[i], 0.f) * keep;
         store_bf16x16(out + (size_t)row * 64 + col, v);
     }
 };
 struct EpiConv3 {               // rows on the 7-grid -> dense A3 [B][25][64] (TF flatten order h,w,c)
     bf16 *a3; const float *bias; int rows;
     __device__ void operator()(int row, int col, float (&v)[16], int, const float *bs) const {
+        float bi[16];
+        load_bias16(bs, col, bi);
         if (row >= rows) return;
         int b = row / kP2, p = row - b * kP2, oh = p / kG2, ow = p - oh * kG2;
         if (oh >= 5 || ow >= 5) return;
 #pragma unroll
-        for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i] + bs[col + i], 0.f);
+        for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i] + bi[i], 0.f);
         store_bf16x16(a3 + ((size_t)b * 25 + oh * 5 + ow) * 64 + col, v);
     }
 };
@@ -747,8 +762,8 @@ struct TcState {
     cudaEvent_t ev[8];
     std::vector<GraphEntry> graphs;
     int use_graph;
-    int fused_conv1;            // opt-in: tc_conv1_fused_kernel instead of pack_x2 + conv1 + pool_pack
-    int pooled_conv1;           // conv1 with the max-pool in its epilogue (slab by TMA from X2)
+    int conv1_mode;             // 2 (default): pooled epilogue, slab from u8 when no backward follows; 1: slab always from X2;
+                                // 0: separate pack_x2 / conv1 / pool_pack kernels
 };
 
 namespace {
@@ -891,8 +906,7 @@ int tc_state_create(fb_qnet *n) {
     FB_CUDA_OK(cudaStreamCreateWithFlags(&t->cap, cudaStreamNonBlocking));
     for (auto &e : t->ev) FB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     t->use_graph = 1;
-    { const char *e = getenv("FB_TC_FUSED_CONV1"); t->fused_conv1 = (e && e[0] == '1') ? 1 : 0; }
-    { const char *e = getenv("FB_TC_POOLED_CONV1"); t->pooled_conv1 = (e && e[0] == '1') ? 1 : 0; }
+    { const char *e = getenv("FB_TC_CONV1_MODE"); t->conv1_mode = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }
     n->tc = t;
     return FB_OK;
 }
@@ -972,24 +986,20 @@ static int tc_forward_impl(fb_qnet *n, int slot, int w, const float *params_dev,
     const FwdWs &f = t->ws[w];
     const int P1 = B * kP1, P2 = B * kP2;
     g_probe_view = fv;
-    if (t->fused_conv1) {
-        // conv1 fused with the u8 -> space-to-depth conversion in front of it and the max-pool behind it: a fifth of the
-        // HBM bytes, but its slab builders are issue-latency bound (92 us vs 80 us for the three kernels at 2048 samples),
-        // so it is opt-in (FB_TC_FUSED_CONV1=1) until they are faster
-        if (keep) FB_CUDA_OK(tc::launch_pdl(pack_x2_kernel, dim3((unsigned)(((size_t)P1 * 8 + 255) / 256)), dim3(256), 0, st, fv, B, f.x2));
-        FB_CUDA_OK((launch_tc_conv1_fused<4, false>(p->x2_s[w], wm.w1p, Conv1FusedParams{fv, B, params_dev + L.b1, keep ? f.z1 : nullptr, f.p2},
-                                                   t->n_sms, st)));
-    } else if (t->pooled_conv1) {
-        // opt-in (FB_TC_POOLED_CONV1=1): X2 by pack_x2, then conv1 with the max-pool in its epilogue.  Measured 89 us vs
-        // 35 + 15 us (conv1 + pool) at 2048 samples: the pooled epilogue, not the slab source, is what is slow in the
-        // fused kernels (the same epilogue without the pooling section: 83 us); to be understood before it is a default
+    // conv1 with the 2x2 max-pool in its epilogue (Z1 is written only when a backward pass needs it; no pooling pass):
+    //   keep == 0 (acting, Q(s') forwards): slab built in the kernel straight from the u8 frames -- no X2 either;
+    //   keep != 0: X2 is materialised once (the conv1 weight gradient contracts over it by TMA) and feeds the slab.
+    // conv1_mode 0 restores the three separate kernels (pack_x2, conv1, pool_pack).
+    if (t->conv1_mode == 0) {
+        FB_CUDA_OK(tc::launch_pdl(pack_x2_kernel, dim3((unsigned)(((size_t)P1 * 8 + 255) / 256)), dim3(256), 0, st, fv, B, f.x2));
+        FB_CUDA_OK((launch_tc_conv<32, kSlab1, 1, 4, 6, 1>(p->x2_s[w], wm.w1p, p->conv1, t->n_sms, EpiConv1{f.z1, params_dev + L.b1, P1}, st)));
+        FB_CUDA_OK(tc::launch_pdl(pool_pack_kernel, dim3((unsigned)(((size_t)B * 36 * 16 + 255) / 256)), dim3(256), 0, st, f.z1, B, f.p2));
+    } else if (keep || t->conv1_mode == 1) {
         FB_CUDA_OK(tc::launch_pdl(pack_x2_kernel, dim3((unsigned)(((size_t)P1 * 8 + 255) / 256)), dim3(256), 0, st, fv, B, f.x2));
         FB_CUDA_OK((launch_tc_conv1_fused<6, true>(p->x2_s[w], wm.w1p, Conv1FusedParams{fv, B, params_dev + L.b1, keep ? f.z1 : nullptr, f.p2},
                                                   t->n_sms, st)));
     } else {
-        FB_CUDA_OK(tc::launch_pdl(pack_x2_kernel, dim3((unsigned)(((size_t)P1 * 8 + 255) / 256)), dim3(256), 0, st, fv, B, f.x2));
-        FB_CUDA_OK((launch_tc_conv<32, kSlab1, 1, 4, 6, 1>(p->x2_s[w], wm.w1p, p->conv1, t->n_sms, EpiConv1{f.z1, params_dev + L.b1, P1}, st)));
-        FB_CUDA_OK(tc::launch_pdl(pool_pack_kernel, dim3((unsigned)(((size_t)B * 36 * 16 + 255) / 256)), dim3(256), 0, st, f.z1, B, f.p2));
+        FB_CUDA_OK((launch_tc_conv1_fused<4, false>(p->x2_s[w], wm.w1p, Conv1FusedParams{fv, B, params_dev + L.b1, nullptr, f.p2}, t->n_sms, st)));
     }
     FB_CUDA_OK((launch_tc_conv<64, kSlab2, 2, 8, 3, 1>(p->p2_s[w], wm.w2p, p->conv2, t->n_sms, EpiGrid7{f.a2, params_dev + L.b2, P2}, st)));
     FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4, 1>(p->a2_s[w], wm.w3p, p->conv3, t->n_sms, EpiConv3{f.a3, params_dev + L.b3, P2}, st)));
@@ -1096,9 +1106,9 @@ bool same_key(const GraphKey &x, const GraphKey &y) { return memcmp(&x, &y, size
 
 }  // namespace
 
-extern "C" int fb_qnet_use_fused_conv1(fb_qnet *n, int enable) {
-    FB_REQUIRE(n != nullptr && n->tc != nullptr, "fb_qnet_use_fused_conv1: needs FB_PRECISION_BF16");
-    n->tc->fused_conv1 = enable ? 1 : 0;
+extern "C" int fb_qnet_set_conv1_mode(fb_qnet *n, int mode) {
+    FB_REQUIRE(n != nullptr && n->tc != nullptr && mode >= 0 && mode <= 2, "fb_qnet_set_conv1_mode: needs FB_PRECISION_BF16 and mode 0..2");
+    n->tc->conv1_mode = mode;
     for (auto &g : n->tc->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     n->tc->graphs.clear();
     return FB_OK;

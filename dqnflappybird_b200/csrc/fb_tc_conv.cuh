@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[S], bar_empty[S], bar_b, bar_acc_full[2], bar_acc_empty[2];
     __shared__ uint32_t tmem_slot;
-    __shared__ float bias_s[BN];
+    __shared__ __align__(16) float bias_s[BN];
     const uint32_t smem_b = (tc::smem_u32(smem_raw) + 1023u) & ~1023u, smem_a = smem_b + B_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t TMEM_COLS = 2 * T * BN <= 32 ? 32 : 2 * T * BN <= 64 ? 64 : 2 * T * BN <= 128 ? 128 : 2 * T * BN <= 256 ? 256 : 512;
@@ -333,23 +333,22 @@ __device__ __forceinline__ void slab_from_raw(uint8_t *slab, const uint8_t *raw,
         const int r = bh_l * 21 + bw;
         if (r < kSlabF) {
             const int rr = 4 * bh_l + dr, ih = 24 * tq - 2 + rr;
-            uint4 out = make_uint4(0u, 0u, 0u, 0u);
-            if (col_ok && kTileRows1 * tq + bh_l < 21 && (unsigned)ih < 80u) {
-                const uint8_t *src = raw + rr * 80 + iw;
-                uint32_t t[4];
+            // loads unconditional (clamped address), zeroing by a select afterwards: no divergent blocks around the LDS
+            const bool valid = col_ok && kTileRows1 * tq + bh_l < 21 && (unsigned)ih < 80u;
+            const uint8_t *src = raw + rr * 80 + (col_ok ? iw : 0);
+            uint32_t t[4];
 #pragma unroll
-                for (int c = 0; c < 4; c++) t[c] = *reinterpret_cast<const unsigned short *>(src + c * (kRawRows * 80));
-                uint32_t w[4];
+            for (int c = 0; c < 4; c++) t[c] = *reinterpret_cast<const unsigned short *>(src + c * (kRawRows * 80));
+            uint32_t w[4];
 #pragma unroll
-                for (int s2 = 0; s2 < 2; s2++)
+            for (int s2 = 0; s2 < 2; s2++)
 #pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const float lo = (float)((t[2 * h] >> (8 * s2)) & 255), hi = (float)((t[2 * h + 1] >> (8 * s2)) & 255);
-                        __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-                        w[s2 * 2 + h] = *reinterpret_cast<uint32_t *>(&v);
-                    }
-                out = make_uint4(w[0], w[1], w[2], w[3]);
-            }
+                for (int h = 0; h < 2; h++) {
+                    const float lo = (float)((t[2 * h] >> (8 * s2)) & 255), hi = (float)((t[2 * h + 1] >> (8 * s2)) & 255);
+                    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+                    w[s2 * 2 + h] = valid ? *reinterpret_cast<uint32_t *>(&v) : 0u;
+                }
+            const uint4 out = make_uint4(w[0], w[1], w[2], w[3]);
             *reinterpret_cast<uint4 *>(slab + r * 128 + ((c16 ^ (r & 7)) << 4)) = out;
         }
     }
@@ -375,7 +374,7 @@ __global__ void __launch_bounds__(FROM_X2 ? 192 : kFusedThreads, 1) tc_conv1_fus
     __shared__ __align__(8) uint64_t bar_full[S], bar_empty[S], bar_b, bar_acc_full[2], bar_acc_empty[2], bar_raw_full[kRawStages],
         bar_raw_empty[kRawStages];
     __shared__ uint32_t tmem_slot;
-    __shared__ float bias_s[BN];
+    __shared__ __align__(16) float bias_s[BN];
     uint8_t *smem_gen = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-aligned, generic pointer
     const uint32_t smem_b = tc::smem_u32(smem_gen), smem_a = smem_b + B_BYTES;
     uint8_t *slab_gen = smem_gen + B_BYTES, *zs_gen = slab_gen + S * STAGE, *raw_gen = zs_gen + 2 * ZS_BYTES;
@@ -493,14 +492,24 @@ __global__ void __launch_bounds__(FROM_X2 ? 192 : kFusedThreads, 1) tc_conv1_fus
             if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_acc_empty[as]));
             const int oh_l = r / 21, ow = r - oh_l * 21, oh = kTileRows1 * tq + oh_l;
             const bool ok = r < kTilePos1 && oh < 20 && ow < 20;
+            // bias first, unconditionally and vectorised: with the loads inside the `ok ? :` the compiler emitted sixteen
+            // divergent blocks per tile, each re-deriving the shared window (S2UR) before two dependent LDS (3,000 cycles a tile)
+            float bia[32];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float4 t4 = reinterpret_cast<const float4 *>(bias_s)[k];
+                bia[4 * k] = t4.x; bia[4 * k + 1] = t4.y; bia[4 * k + 2] = t4.z; bia[4 * k + 3] = t4.w;
+            }
+            const float keep = ok ? 1.f : 0.f;
             uint32_t w[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) {
-                const float x0 = ok ? fmaxf(v[2 * k] + bias_s[2 * k], 0.f) : 0.f, x1 = ok ? fmaxf(v[2 * k + 1] + bias_s[2 * k + 1], 0.f) : 0.f;
+                const float x0 = fmaxf(v[2 * k] + bia[2 * k], 0.f) * keep, x1 = fmaxf(v[2 * k + 1] + bia[2 * k + 1], 0.f) * keep;
                 __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
                 w[k] = *reinterpret_cast<uint32_t *>(&h);
             }
             uint4 *zs = reinterpret_cast<uint4 *>(zs_gen + (i & 1) * ZS_BYTES + r * 64);
+            if (g.p2 != nullptr)
 #pragma unroll
             for (int k = 0; k < 4; k++) zs[(k + (r >> 1)) & 3] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);   // rotate: fewer bank conflicts
             if (ok && g.z1 != nullptr) {

@@ -164,9 +164,11 @@ int fb_qnet_invalidate(fb_qnet *net);
 /* FB_PRECISION_BF16 only: replay fb_qnet_loss_backward as a CUDA graph once the same arguments were seen twice
  * (default on; the eager two-stream path is identical work). */
 int fb_qnet_use_graphs(fb_qnet *net, int enable);
-/* FB_PRECISION_BF16 only, opt-in (also FB_TC_FUSED_CONV1=1): conv1 built straight from the u8 frames with the max-pool in its
- * epilogue (no bf16 input matrix, no separate pooling pass; a fifth of the HBM bytes, not yet faster). */
-int fb_qnet_use_fused_conv1(fb_qnet *net, int enable);
+/* FB_PRECISION_BF16 only: how conv1 is run (also FB_TC_CONV1_MODE).  2 (default): the 2x2 max-pool is fused into conv1's
+ * epilogue, and when no backward pass follows (acting, Q(s')) its input tile is built in the kernel straight from the u8
+ * frames -- neither the bf16 input matrix nor the conv1 activations go through HBM; 1: pooled epilogue, input always via the
+ * materialised matrix; 0: three separate kernels (conversion, conv1, pooling).  Results are bit-identical in all modes. */
+int fb_qnet_set_conv1_mode(fb_qnet *net, int mode);
 int fb_qnet_param_count(const fb_qnet *net);
 int fb_qnet_layout(const fb_qnet *net, int32_t *out16_host);
 

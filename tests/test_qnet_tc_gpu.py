@@ -128,24 +128,26 @@ def test_forward_matches_oracle_bf16(mods, dueling):
     assert np.abs(q - q32).max() <= 2e-2 * np.abs(q32).max()
 
 
-def test_fused_conv1_matches_the_three_kernel_path(mods):
-    """opt-in conv1 fused with the u8 -> space-to-depth conversion and the max-pool: same Q-values, same gradients"""
+def test_conv1_modes_are_bit_identical(mods):
+    """conv1 as three kernels (mode 0), with the max-pool in its epilogue (1), and built straight from the u8 frames when
+    no backward follows (2, default): the same arithmetic on different data paths -- identical Q-values and gradients"""
     _lib, game, qnet = mods
     B = 70
     frames = _env_frames(game, B, 9)
-    nets = [qnet.QNetwork(max_batch=128, seed=2, precision="bf16") for _ in range(2)]
-    for n in nets:
+    nets = [qnet.QNetwork(max_batch=128, seed=2, precision="bf16") for _ in range(3)]
+    for mode, n in enumerate(nets):
         n.params.mul_(4.0); n.target.mul_(4.0)
-    _lib.check(_lib.lib().fb_qnet_use_fused_conv1(nets[1]._h, 1), "fb_qnet_use_fused_conv1")
+        _lib.check(_lib.lib().fb_qnet_set_conv1_mode(n._h, mode), "fb_qnet_set_conv1_mode")
     q = [n.forward(qnet.FrameBatch.from_stack(frames, 1)) for n in nets]
-    assert torch.equal(q[0], q[1])                        # identical arithmetic, only the data path differs
+    assert torch.equal(q[0], q[1]) and torch.equal(q[0], q[2])
     rng = np.random.default_rng(3)
     a = torch.from_numpy(rng.integers(0, 2, B).astype(np.uint8)).cuda()
     r = torch.from_numpy(rng.choice(np.array([0.1, 3.0, -3.0], np.float32), B)).cuda()
     term = (r == -3.0).to(torch.uint8)
     for n in nets:
         n.loss_backward("double", frames, a, r, term)
-    assert torch.equal(nets[0].grads, nets[1].grads) and nets[0].loss.item() == nets[1].loss.item()
+    for n in nets[1:]:
+        assert torch.equal(nets[0].grads, n.grads) and nets[0].loss.item() == n.loss.item()
 
 
 def test_forward_from_ring_view_bf16(mods):
