@@ -370,14 +370,14 @@ def bench_learner(args, rank, world, dev):
             fbv = brain._act_view()
             fbv.batch = kb
             brain.net.forward(fbv)                                   # fills the workspace at this batch
-            _lib.check(L.fb_debug_tc_kernel(brain.net._h, 0, kb, 3, brain.net.params.data_ptr(), st), "probe")
+            _lib.check(L.fb_debug_tc_kernel(brain.net._h, 10, kb, 3, brain.net.params.data_ptr(), st), "probe")
             sync()
             e0.record()
-            _lib.check(L.fb_debug_tc_kernel(brain.net._h, 0, kb, reps, brain.net.params.data_ptr(), st), "probe")
+            _lib.check(L.fb_debug_tc_kernel(brain.net._h, 10, kb, reps, brain.net.params.data_ptr(), st), "probe")
             e1.record(); sync()
             us = e0.elapsed_time(e1) * 1e3 / reps
             kern[kb] = {"us": us, "tflops": 6553600 * kb / (us * 1e-6) / 1e12,
-                        "hbm_gbs": kb * 441 * (128 + 64) / (us * 1e-6) / 1e9}
+                        "hbm_gbs": kb * (441 * (128 + 64) + 49 * 256) / (us * 1e-6) / 1e9}
     # ---- the other DQN-family agents of BASELINE.json's configs on the same workload (same envs, replay and minibatch):
     # Double (configs[4]), Dueling (configs[4]), prioritized replay with the device sum-tree (configs[3])
     variants = {"dqnnature": {"updates_per_s": 1e3 / ms_upd, "ms_per_update": ms_upd}}
@@ -455,15 +455,17 @@ def bench_learner(args, rank, world, dev):
             "gradient_exchange": ("none (1 GPU)" if world == 1 else
                                   "fused into Adam over NVLink peer memory (fb_dist_adam)" if brain.net.exchange is not None else "NCCL all-reduce"),
             "roofline": None if not kern else {
-                "bound": "tensor", "kernel": "tc_conv_kernel<32,152,1,4,6,EpiConv1> (conv1 forward: TMA slab + tcgen05.mma, N = 32)",
+                "bound": "tensor", "kernel": "tc_conv1_fused_kernel<6,true> (conv1 forward of the training step: TMA slab + tcgen05.mma, N = 32, "
+                                             "bias + ReLU + 2x2 max-pool in the epilogue, Z1 and P2 out)",
                 "algorithmic_flop_per_sample": 6553600, "unit": "TFLOP/s", "peak": tc_peak,
                 "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, cuBLAS burst)",
                 "achieved": max(v["tflops"] for v in kern.values()),
                 "frac": max(v["tflops"] for v in kern.values()) / tc_peak,
                 "by_batch": {str(k): v for k, v in kern.items()},
-                "note": "per launch, CUDA events over back-to-back launches; at batch 2048 the bf16 operands (X2 read 56 KB + Z1 "
-                        "write 28 KB per sample) exceed L2 and the kernel also runs at hbm_gbs of HBM traffic; traffic and "
-                        "sm__pipe_tensor_cycles_active: profiles/r01_ncu_tc_kernels_summary.json"}}
+                "note": "per launch, CUDA events over back-to-back launches; a tcgen05.mma of N = 32 is bound by its operand reads from "
+                        "shared memory at 16/40 of the math rate (profiles/r01_tcgen05_mma_rate_b200.txt), so 0.40 is this layer's ceiling; "
+                        "at batch 2048 the operands (X2 read 56 KB + Z1 write 28 KB + P2 6 KB per sample) exceed L2 and stream at "
+                        "hbm_gbs; ncu traffic and pipe utilisation: profiles/r01_ncu_tc_kernels_summary.json"}}
 
 
 def main():
