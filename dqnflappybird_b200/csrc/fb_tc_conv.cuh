@@ -306,8 +306,8 @@ static cudaError_t launch_tc_wgrad(const CUtensorMap &ma, const CUtensorMap &mb,
 // 6-13 slab builders, one tile each in flight (u8 -> bf16, written with the 128-byte swizzle TMA would have used, fence.proxy.async, mbarrier).
 namespace {
 
-constexpr int kFusedThreads = 448;                              // 6 role warps + 8 slab builders
-constexpr int kBuilders = 256;
+constexpr int kBuilders = 256;                                   // 8 slab-builder warps in two groups
+constexpr int kFusedThreads = 192 + kBuilders;                  // + 6 role warps
 constexpr int kTileRows1 = 6, kTilePos1 = kTileRows1 * 21;      // 126 positions per tile
 constexpr int kSlabF = 152;                                     // 126 + 22 halo, rounded up to 8
 
@@ -323,17 +323,18 @@ constexpr int kSlabF = 152;                                     // 126 + 22 halo
 constexpr int kRawRows = 32, kRawBytes = 4 * kRawRows * 80;     // raw pixels per tile (10,240 bytes)
 constexpr int kRawStages = 4;
 
-// thread (bw, c16) walks down the 8 block rows of the tile: no division, every address is an increment
+// 1,216 chunks of 16 bytes per slab over the builder threads (every warp equally loaded); r / 21 by multiply-shift;
+// loads unconditional (clamped address) and zeroing by a select, so that no divergent block surrounds the LDS
+template <int NT>
 __device__ __forceinline__ void slab_from_raw(uint8_t *slab, const uint8_t *raw, int tq, int tid) {
-    if (tid >= 21 * 8) return;
-    const int bw = tid >> 3, c16 = tid & 7, dr = c16 >> 1, iw = 4 * bw - 2 + 2 * (c16 & 1);
-    const bool col_ok = (unsigned)iw < 80u;
 #pragma unroll
-    for (int bh_l = 0; bh_l < 8; bh_l++) {
-        const int r = bh_l * 21 + bw;
-        if (r < kSlabF) {
-            const int rr = 4 * bh_l + dr, ih = 24 * tq - 2 + rr;
-            // loads unconditional (clamped address), zeroing by a select afterwards: no divergent blocks around the LDS
+    for (int k = 0; k < (kSlabF * 8 + NT - 1) / NT; k++) {
+        const int item = tid + k * NT;
+        if (item < kSlabF * 8) {
+            const int r = item >> 3, c16 = item & 7;
+            const int bh_l = (r * 3121) >> 16, bw = r - bh_l * 21;              // r / 21, r % 21 for r < 400
+            const int rr = 4 * bh_l + (c16 >> 1), ih = 24 * tq - 2 + rr, iw = 4 * bw - 2 + 2 * (c16 & 1);
+            const bool col_ok = (unsigned)iw < 80u;
             const bool valid = col_ok && kTileRows1 * tq + bh_l < 21 && (unsigned)ih < 80u;
             const uint8_t *src = raw + rr * 80 + (col_ok ? iw : 0);
             uint32_t t[4];
@@ -348,8 +349,7 @@ __device__ __forceinline__ void slab_from_raw(uint8_t *slab, const uint8_t *raw,
                     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
                     w[s2 * 2 + h] = valid ? *reinterpret_cast<uint32_t *>(&v) : 0u;
                 }
-            const uint4 out = make_uint4(w[0], w[1], w[2], w[3]);
-            *reinterpret_cast<uint4 *>(slab + r * 128 + ((c16 ^ (r & 7)) << 4)) = out;
+            *reinterpret_cast<uint4 *>(slab + r * 128 + ((c16 ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
     }
 }
@@ -437,16 +437,19 @@ __global__ void __launch_bounds__(FROM_X2 ? 192 : kFusedThreads, 1) tc_conv1_fus
             __syncwarp();
         }
     } else if (warp >= 6) {
-        // ===== slab builders (256 threads, named barrier 2)
-        const int tid = threadIdx.x - 192;
-        int i = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, i++) {
+        // ===== slab builders: two groups of kBuilders / 2 threads take alternate tiles (named barriers 2 and 3), so that one
+        // group's fence / barrier / hand-over latency overlaps the other's conversion
+        constexpr int GT = kBuilders / 2;
+        const int grp = (threadIdx.x - 192) / GT, tid = (threadIdx.x - 192) - grp * GT;
+        int i = grp;
+        for (int tile = blockIdx.x + grp * (int)gridDim.x; tile < n_tiles; tile += 2 * (int)gridDim.x, i += 2) {
             const int s = i % S, rs = i % kRawStages;
             tc::mbar_wait(tc::smem_u32(&bar_raw_full[rs]), (i / kRawStages) & 1);
             tc::mbar_wait(tc::smem_u32(&bar_empty[s]), ((i / S) & 1) ^ 1u);
-            slab_from_raw(slab_gen + s * STAGE, raw_gen + rs * kRawBytes, tile & 3, tid);
+            slab_from_raw<GT>(slab_gen + s * STAGE, raw_gen + rs * kRawBytes, tile & 3, tid);
             tc::fence_proxy_async();                      // generic-proxy writes -> visible to the tensor core's async proxy
-            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (grp == 0) asm volatile("bar.sync 2, %0;" ::"n"(GT) : "memory");
+            else asm volatile("bar.sync 3, %0;" ::"n"(GT) : "memory");
             if (tid == 0) { tc::mbar_arrive(tc::smem_u32(&bar_full[s])); tc::mbar_arrive(tc::smem_u32(&bar_raw_empty[rs])); }
         }
     } else if (warp == 1) {
