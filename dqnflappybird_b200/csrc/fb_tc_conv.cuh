@@ -302,12 +302,14 @@ static cudaError_t launch_tc_wgrad(const CUtensorMap &ma, const CUtensorMap &mb,
 // (56 KB/sample) nor, when acting, Z1 (28 KB/sample) ever exists in HBM: 25.6 KB of u8 in, 12.5 KB of P2 out per sample.
 //
 // Tile = 6 rows of one sample's 21-wide block grid (126 positions, M = 128), so that every 2x2 pooling window is inside
-// one tile; 4 tiles per sample.  Warps: 0 weights (TMA), 1 MMA issue, 2-5 epilogue (+ pooling through shared memory),
-// 6-13 slab builders, one tile each in flight (u8 -> bf16, written with the 128-byte swizzle TMA would have used, fence.proxy.async, mbarrier).
+// one tile; 4 tiles per sample.  Warps: 0 weights (TMA), 1 MMA issue, 2-9 epilogue (+ pooling through shared memory; two groups
+// on alternate tiles, staging buffer i & 3 so that a group's next tile never overwrites rows still being pooled),
+// 10-17 slab builders, one tile per group in flight (u8 -> bf16, written with the 128-byte swizzle TMA would have used, fence.proxy.async, mbarrier).
 namespace {
 
 constexpr int kBuilders = 256;                                   // 8 slab-builder warps in two groups
-constexpr int kFusedThreads = 192 + kBuilders;                  // + 6 role warps
+constexpr int kRoleThreads1 = 64 + 256;                          // TMA warp, MMA warp, two epilogue groups of 4 warps
+constexpr int kFusedThreads = kRoleThreads1 + kBuilders;
 constexpr int kTileRows1 = 6, kTilePos1 = kTileRows1 * 21;      // 126 positions per tile
 constexpr int kSlabF = 152;                                     // 126 + 22 halo, rounded up to 8
 
@@ -327,30 +329,38 @@ constexpr int kRawStages = 4;
 // loads unconditional (clamped address) and zeroing by a select, so that no divergent block surrounds the LDS
 template <int NT>
 __device__ __forceinline__ void slab_from_raw(uint8_t *slab, const uint8_t *raw, int tq, int tid) {
+    constexpr int K = (kSlabF * 8 + NT - 1) / NT, LAST = kSlabF * 8 - 1;
+    // all of a thread's loads first (one warp per scheduler: the conversions of chunk k would otherwise wait out the
+    // shared-memory latency of chunk k's own loads, ~350 cycles a chunk), then convert and store
+    uint32_t t[K][4];
+    uint32_t dst[K];
 #pragma unroll
-    for (int k = 0; k < (kSlabF * 8 + NT - 1) / NT; k++) {
-        const int item = tid + k * NT;
-        if (item < kSlabF * 8) {
-            const int r = item >> 3, c16 = item & 7;
-            const int bh_l = (r * 3121) >> 16, bw = r - bh_l * 21;              // r / 21, r % 21 for r < 400
-            const int rr = 4 * bh_l + (c16 >> 1), ih = 24 * tq - 2 + rr, iw = 4 * bw - 2 + 2 * (c16 & 1);
-            const bool col_ok = (unsigned)iw < 80u;
-            const bool valid = col_ok && kTileRows1 * tq + bh_l < 21 && (unsigned)ih < 80u;
-            const uint8_t *src = raw + rr * 80 + (col_ok ? iw : 0);
-            uint32_t t[4];
+    for (int k = 0; k < K; k++) {
+        int item = tid + k * NT;
+        item = item < LAST ? item : LAST;
+        const int r = item >> 3, c16 = item & 7;
+        const int bh_l = (r * 3121) >> 16, bw = r - bh_l * 21;              // r / 21, r % 21 for r < 400
+        const int rr = 4 * bh_l + (c16 >> 1), ih = 24 * tq - 2 + rr, iw = 4 * bw - 2 + 2 * (c16 & 1);
+        const bool col_ok = (unsigned)iw < 80u;
+        const bool valid = col_ok && kTileRows1 * tq + bh_l < 21 && (unsigned)ih < 80u;
+        const uint8_t *src = raw + rr * 80 + (col_ok ? iw : 0);
 #pragma unroll
-            for (int c = 0; c < 4; c++) t[c] = *reinterpret_cast<const unsigned short *>(src + c * (kRawRows * 80));
-            uint32_t w[4];
+        for (int c = 0; c < 4; c++) t[k][c] = *reinterpret_cast<const unsigned short *>(src + c * (kRawRows * 80));
+        dst[k] = (uint32_t)(r * 128 + ((c16 ^ (r & 7)) << 4)) | (valid ? 0x80000000u : 0u);
+    }
 #pragma unroll
-            for (int s2 = 0; s2 < 2; s2++)
+    for (int k = 0; k < K; k++) {
+        const bool valid = (dst[k] & 0x80000000u) != 0;
+        uint32_t w[4];
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const float lo = (float)((t[2 * h] >> (8 * s2)) & 255), hi = (float)((t[2 * h + 1] >> (8 * s2)) & 255);
-                    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-                    w[s2 * 2 + h] = valid ? *reinterpret_cast<uint32_t *>(&v) : 0u;
-                }
-            *reinterpret_cast<uint4 *>(slab + r * 128 + ((c16 ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
+        for (int s2 = 0; s2 < 2; s2++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const float lo = (float)((t[k][2 * h] >> (8 * s2)) & 255), hi = (float)((t[k][2 * h + 1] >> (8 * s2)) & 255);
+                __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+                w[s2 * 2 + h] = valid ? *reinterpret_cast<uint32_t *>(&v) : 0u;
+            }
+        if (tid + k * NT <= LAST) *reinterpret_cast<uint4 *>(slab + (dst[k] & 0x7fffffffu)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
@@ -365,7 +375,7 @@ struct Conv1FusedParams {
 // FROM_X2: the slab comes by TMA from a materialised X2 (pack_x2_kernel) instead of the in-kernel builders -- conv1 with
 // only the pooling fused (no Z1 round trip, no pool kernel); 192 threads.
 template <int S, bool FROM_X2>
-__global__ void __launch_bounds__(FROM_X2 ? 192 : kFusedThreads, 1) tc_conv1_fused_kernel(const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(FROM_X2 ? kRoleThreads1 : kFusedThreads, 1) tc_conv1_fused_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                                           const __grid_constant__ CUtensorMap mapB,
                                                                                           const Conv1FusedParams g) {
     constexpr int BN = 32, NKB = 4;
@@ -377,7 +387,7 @@ __global__ void __launch_bounds__(FROM_X2 ? 192 : kFusedThreads, 1) tc_conv1_fus
     __shared__ __align__(16) float bias_s[BN];
     uint8_t *smem_gen = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-aligned, generic pointer
     const uint32_t smem_b = tc::smem_u32(smem_gen), smem_a = smem_b + B_BYTES;
-    uint8_t *slab_gen = smem_gen + B_BYTES, *zs_gen = slab_gen + S * STAGE, *raw_gen = zs_gen + 2 * ZS_BYTES;
+    uint8_t *slab_gen = smem_gen + B_BYTES, *zs_gen = slab_gen + S * STAGE, *raw_gen = zs_gen + 4 * ZS_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = 4 * g.B;
     const long long total_rows = (long long)g.B * 441;
@@ -436,11 +446,11 @@ __global__ void __launch_bounds__(FROM_X2 ? 192 : kFusedThreads, 1) tc_conv1_fus
             }
             __syncwarp();
         }
-    } else if (warp >= 6) {
+    } else if (warp >= kRoleThreads1 / 32) {
         // ===== slab builders: two groups of kBuilders / 2 threads take alternate tiles (named barriers 2 and 3), so that one
         // group's fence / barrier / hand-over latency overlaps the other's conversion
         constexpr int GT = kBuilders / 2;
-        const int grp = (threadIdx.x - 192) / GT, tid = (threadIdx.x - 192) - grp * GT;
+        const int grp = (threadIdx.x - kRoleThreads1) / GT, tid = (threadIdx.x - kRoleThreads1) - grp * GT;
         int i = grp;
         for (int tile = blockIdx.x + grp * (int)gridDim.x; tile < n_tiles; tile += 2 * (int)gridDim.x, i += 2) {
             const int s = i % S, rs = i % kRawStages;
@@ -479,12 +489,15 @@ __global__ void __launch_bounds__(FROM_X2 ? 192 : kFusedThreads, 1) tc_conv1_fus
             }
             __syncwarp();
         }
-    } else if (warp >= 2 && warp < 6) {
-        // ===== epilogue: bias + ReLU, Z1, max-pool through shared memory, P2
-        const int q = warp & 3, r = q * 32 + lane;          // accumulator row = position r of the tile
-        const int et = threadIdx.x - 64;                    // 0..127 among the epilogue threads
-        int i = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, i++) {
+    } else if (warp >= 2 && warp < kRoleThreads1 / 32) {
+        // ===== epilogue: bias + ReLU, Z1, max-pool through shared memory, P2.  Two groups of four warps on alternate tiles
+        // (group e owns accumulator e and staging buffer e): at N = 32 a tile's MMAs take ~640 cycles, one group's
+        // epilogue about twice that
+        const int eg = (warp - 2) >> 2;
+        const int q = warp & 3, r = q * 32 + lane;          // accumulator row = position r of the tile (TMEM lanes of warp % 4)
+        const int et = threadIdx.x - 64 - 128 * eg;         // 0..127 within the group
+        int i = eg;
+        for (int tile = blockIdx.x + eg * (int)gridDim.x; tile < n_tiles; tile += 2 * (int)gridDim.x, i += 2) {
             const int as = i & 1, b = tile >> 2, tq = tile & 3;
             tc::mbar_wait(tc::smem_u32(&bar_acc_full[as]), (i >> 1) & 1);
             tc::tc_fence_after();
@@ -511,7 +524,7 @@ __global__ void __launch_bounds__(FROM_X2 ? 192 : kFusedThreads, 1) tc_conv1_fus
                 __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
                 w[k] = *reinterpret_cast<uint32_t *>(&h);
             }
-            uint4 *zs = reinterpret_cast<uint4 *>(zs_gen + (i & 1) * ZS_BYTES + r * 64);
+            uint4 *zs = reinterpret_cast<uint4 *>(zs_gen + (i & 3) * ZS_BYTES + r * 64);
             if (g.p2 != nullptr)
 #pragma unroll
             for (int k = 0; k < 4; k++) zs[(k + (r >> 1)) & 3] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);   // rotate: fewer bank conflicts
@@ -521,11 +534,12 @@ __global__ void __launch_bounds__(FROM_X2 ? 192 : kFusedThreads, 1) tc_conv1_fus
                 for (int k = 0; k < 4; k++) d[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
             }
             if (g.p2 == nullptr) continue;               // (measurement only: no pooling, no output)
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+            else asm volatile("bar.sync 4, 128;" ::: "memory");
             if (et < 120) {
                 const int ph_l = et / 40, rem = et - ph_l * 40, pw = rem >> 2, cg = rem & 3, ph = 3 * tq + ph_l;
                 if (ph < 10) {
-                    const uint8_t *zb = zs_gen + (i & 1) * ZS_BYTES;
+                    const uint8_t *zb = zs_gen + (i & 3) * ZS_BYTES;
                     auto ld = [&](int row) { return *reinterpret_cast<const uint4 *>(zb + row * 64 + (((cg + (row >> 1)) & 3) << 4)); };
                     const int r0 = (2 * ph_l) * 21 + 2 * pw;
                     uint4 m = ld(r0), o1 = ld(r0 + 1), o2 = ld(r0 + 21), o3 = ld(r0 + 22);
@@ -549,14 +563,14 @@ template <int S, bool FROM_X2>
 static cudaError_t launch_tc_conv1_fused(const CUtensorMap &ma, const CUtensorMap &mb, const Conv1FusedParams &g, int max_ctas, cudaStream_t st) {
     static bool configured = false;
     auto kern = tc_conv1_fused_kernel<S, FROM_X2>;
-    constexpr size_t smem = 4 * 32 * 128 + (size_t)S * kSlabF * 128 + 2 * 128 * 32 * 2 + (FROM_X2 ? 0 : kRawStages * kRawBytes) + 1024;
+    constexpr size_t smem = 4 * 32 * 128 + (size_t)S * kSlabF * 128 + 4 * 128 * 32 * 2 + (FROM_X2 ? 0 : kRawStages * kRawBytes) + 1024;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     int grid = 4 * g.B < max_ctas ? 4 * g.B : max_ctas;
-    return tc::launch_pdl(kern, dim3(grid), dim3(FROM_X2 ? 192 : kFusedThreads), smem, st, ma, mb, g);
+    return tc::launch_pdl(kern, dim3(grid), dim3(FROM_X2 ? kRoleThreads1 : kFusedThreads), smem, st, ma, mb, g);
 }
 
 }  // namespace
