@@ -77,6 +77,7 @@ _SIGNATURES = {
     "fb_env_import_state": ([_vp, _i32p, _vp], C.c_int),
     "fb_env_obs_exact": ([_vp, _u8p, _vp], C.c_int),
     "fb_render_full": ([_vp, C.c_int, C.c_int, _u8p, _vp], C.c_int),
+    "fb_log_episodes": ([_u8p, _i32p, C.c_int, C.c_int, C.c_int, _i32p, _i32p, C.c_int, _vp], C.c_int),
     "fb_qnet_create": ([C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)], C.c_int),
     "fb_qnet_destroy": ([_vp], C.c_int),
     "fb_qnet_set_precision": ([_vp, C.c_int], C.c_int),

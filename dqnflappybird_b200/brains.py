@@ -22,9 +22,13 @@ its flat gradient vector (NCCL) before the Adam step, every rank training on its
 """
 from __future__ import annotations
 
+import os
+import pickle
+
 import numpy as np
 import torch
 
+from . import _lib
 from .qnet import FrameBatch, QNetwork
 from .replay import PrioritizedMemory, ReplayMemory
 
@@ -38,6 +42,7 @@ FINAL_EPSILON = 0
 INITIAL_EPSILON = 0.03
 REPLAY_MEMORY = 50000
 REPLACE_TARGET_ITER = 500
+SAVE_EVERY = 100000                 # BrainDQN.py:227: weights, (gameTimes, timeStep, epsilon) and the logs every 100,000 steps
 
 
 class BrainDQN:
@@ -46,6 +51,7 @@ class BrainDQN:
     loss_sum = True                 # BrainDQN.py:162 reduce_sum; every subclass uses reduce_mean
     prioritized = False
     uses_target = False
+    dir_name = "/dqn/"              # BrainDQN.py:62-63 _setDirName
 
     def __init__(self, actionNum: int = 2, gameName: str = "bird", num_envs: int = 1, device="cuda:0", ring: torch.Tensor | None = None,
                  batch_size: int = BATCH_SIZE, observe: float = OBSERVE, explore: float = EXPLORE, gamma: float = GAMMA,
@@ -53,7 +59,8 @@ class BrainDQN:
                  replay_memory_per_env: int | None = None, replace_target_iter: int | None = REPLACE_TARGET_ITER,
                  hidden: int = 512, lr: float = 1e-6, seed: int = 0, first_env_id: int = 0, updates_per_step: int = 1,
                  reference_quirks: bool = False, copy_target_at_init: bool = False, record: bool = False, max_act_batch: int = 1024,
-                 precision: str = "bf16", peer_exchange: bool | None = None):
+                 precision: str = "bf16", peer_exchange: bool | None = None, root_dir: str | None = None, save_every: int = SAVE_EVERY,
+                 log_capacity: int = 1 << 20):
         if actionNum != 2:
             raise ValueError("the Flappy Bird hot path has two actions (FlappyBirdDQN.py:38)")
         self.actionNum, self.gameName = actionNum, gameName
@@ -80,7 +87,6 @@ class BrainDQN:
         self.replayMemory = mem_cls(ring, C, seed=seed + 1, max_batch=max(self.local_batch, 8))
         # init other parameters (BrainDQN.py:37-41)
         self.onlineTimeStep = 0
-        self.gameTimes = 0
         self.timeStep = 0
         self.epsilon = initial_epsilon
         # init Q network (BrainDQN.py:60)
@@ -100,7 +106,33 @@ class BrainDQN:
         self._q_target = torch.zeros(max(self.local_batch, 8), dtype=torch.float32, device=self.device)
         self._isw32 = torch.zeros(max(self.local_batch, 8), dtype=torch.float32, device=self.device)
         self._game_times = torch.zeros((), dtype=torch.int64, device=self.device)
+        # logs (BrainDQN.py:44-58).  With record=True they are fed from device-side accumulators (no host sync on the
+        # step path) and reach these lists / the reference's five text files when flushed.
+        self.gameName = gameName
         self.lost_hist, self.q_target_list = [], []
+        self.score_every_episode, self.time_steps_when_episode_end, self.reward_every_time_step = [], [], []
+        self.episode_envs = []                     # which env ended each logged episode (no reference equivalent: one env there)
+        self.save_every = int(save_every)
+        self.save_path = self.logs_path = self.saved_parameters_file_path = None
+        if root_dir is not None:
+            self.save_path = os.path.join(root_dir, "saved_parameters" + self.dir_name)
+            self.saved_parameters_file_path = self.save_path + self.gameName + "-saved-parameters.txt"
+            self.logs_path = os.path.join(root_dir, "logs_" + self.gameName + self.dir_name)      # "logs_bird/dqn/"
+            os.makedirs(self.save_path, exist_ok=True)
+            os.makedirs(self.logs_path, exist_ok=True)
+        if record:
+            cap = int(log_capacity)
+            self._log_cap = cap
+            self._ep_log = torch.zeros((cap, 3), dtype=torch.int32, device=self.device)
+            self._ep_count = torch.zeros((), dtype=torch.int32, device=self.device)
+            self._rew_log = torch.zeros(cap, dtype=torch.float32, device=self.device)
+            self._rew_n = 0
+            self._upd_cap = ucap = max(1, min(cap, (1 << 24) // max(1, self.local_batch)))
+            self._loss_log = torch.zeros(ucap, dtype=torch.float32, device=self.device)
+            self._qt_log = torch.zeros((ucap, self.local_batch), dtype=torch.float32, device=self.device)
+            self._upd_n = 0
+        if self.save_path is not None:
+            self._load_saved_parameters()
 
     # ------------------------------------------------------------------ state
     @property
@@ -166,12 +198,17 @@ class BrainDQN:
             for _ in range(self.updates_per_step):
                 self._trainQNetwork()
         self._game_times += t_row.sum()              # gameTimes += 1 per terminal (BrainDQN.py:88-90), kept on the device
+        if self.record:
+            self._log_step(r_row, t_row, curScore)
         self.timeStep += 1
         self.onlineTimeStep += 1
 
     @property
-    def gameTimesTotal(self) -> int:
+    def gameTimes(self) -> int:
+        """episodes finished so far over all envs (BrainDQN.py:88-90); counted on the device, reading it synchronises"""
         return int(self._game_times.item())
+
+    gameTimesTotal = gameTimes
 
     # ------------------------------------------------------------------ training
     def _maybe_sync_target(self):
@@ -192,15 +229,118 @@ class BrainDQN:
         self.net.adam_step()                                      # with a peer exchange the sum happens inside the Adam kernel
         if mb.tree_idx is not None:
             mem.batch_update(mb.tree_idx, abs_errors=self._abs_err[:self.local_batch])   # :316
-        if self.record:
-            self.lost_hist.append(float(self.net.loss.item()))
-            self.q_target_list.append(self._q_target[:self.local_batch].cpu().tolist())
+        if self.record:                                              # BrainDQN.py:222-225, kept on the device until flushed
+            if self._upd_n == self._upd_cap:
+                self.flush_logs()
+            self._loss_log[self._upd_n].copy_(self.net.loss.reshape(()))
+            self._qt_log[self._upd_n].copy_(self._q_target[:self.local_batch])
+            self._upd_n += 1
+        # save network and other data every 100,000 iterations (BrainDQN.py:226-233)
+        if self.save_path is not None and self.save_every and self.timeStep % self.save_every == 0:
+            self.save()
 
     def _trainQNetwork(self):
         """BrainDQN.py:195-223"""
         self._update("vanilla")
 
+    # ------------------------------------------------------------------ logging surface (row N3)
+    def _log_step(self, r_row, t_row, curScore):
+        """reward_every_time_step / score_every_episode / time_steps_when_episode_end (BrainDQN.py:87-93) without a host sync:
+        the step's mean reward (the reward itself for one env) and one (timeStep, env, score) record per finished episode"""
+        if self._rew_n == self._log_cap:
+            self.flush_logs()
+        self._rew_log[self._rew_n].copy_(r_row.mean() if self.num_envs > 1 else r_row[0])
+        self._rew_n += 1
+        if curScore is None:
+            return
+        sc = torch.as_tensor(curScore).reshape(-1).to(self.device, torch.int32)
+        _lib.check(_lib.lib().fb_log_episodes(t_row.data_ptr(), sc.data_ptr(), self.num_envs, self.first_env_id, int(self.timeStep),
+                                              self._ep_log.data_ptr(), self._ep_count.data_ptr(), self._log_cap,
+                                              torch.cuda.current_stream(self.device).cuda_stream), "fb_log_episodes")
+
+    def flush_logs(self):
+        """move the device-side accumulators into the reference's lists (one host sync); episodes sorted by (timeStep, env)"""
+        if not self.record:
+            return
+        n = int(self._ep_count.item())
+        if n > self._log_cap:
+            raise RuntimeError(f"episode log overflow: {n} episodes since the last flush, capacity {self._log_cap} (raise log_capacity)")
+        if n:
+            ep = self._ep_log[:n].cpu().numpy()
+            ep = ep[np.lexsort((ep[:, 1], ep[:, 0]))]
+            self.time_steps_when_episode_end += ep[:, 0].tolist()
+            self.episode_envs += ep[:, 1].tolist()
+            self.score_every_episode += ep[:, 2].tolist()
+            self._ep_count.zero_()
+        if self._rew_n:
+            self.reward_every_time_step += [float(np.float32(x)) for x in self._rew_log[:self._rew_n].cpu().numpy()]
+            self._rew_n = 0
+        if self._upd_n:
+            self.lost_hist += [float(x) for x in self._loss_log[:self._upd_n].cpu().numpy()]
+            self.q_target_list += self._qt_log[:self._upd_n].cpu().numpy().tolist()
+            self._upd_n = 0
+
+    def _save_loss_score_timestep_reward_qtarget_to_file(self):
+        """BrainDQN.py:270-294: append every list to its text file as ``str(x) + ' '`` and clear it"""
+        self.flush_logs()
+        if self.logs_path is None:
+            raise RuntimeError("no root_dir: the brain was built without a place to put logs_<game>/<model>/")
+        for name, values in (("lost_hist.txt", self.lost_hist), ("score_every_episode.txt", self.score_every_episode),
+                             ("time_steps_when_episode_end.txt", self.time_steps_when_episode_end),
+                             ("reward_every_time_step.txt", self.reward_every_time_step), ("q_targets.txt", self.q_target_list)):
+            with open(self.logs_path + name, "a") as f:
+                for v in values:
+                    f.write(str(v) + " ")
+            del values[:]
+        del self.episode_envs[:]
+
+    def _get_loss_score_timestep_reward_qtarget_from_file(self):
+        """BrainDQN.py:297-330: the five files back as lists of floats (q_targets is a list of per-update lists there too:
+        the reference parses it with the same whitespace split, which only works for its other four files -- here it is
+        parsed properly)"""
+        def floats(name):
+            with open(self.logs_path + name) as f:
+                return [float(t) for t in f.readline().split(" ")[:-1]]
+        with open(self.logs_path + "q_targets.txt") as f:
+            txt = f.readline()
+        q = [float(t) for t in txt.replace("[", " ").replace("]", " ").replace(",", " ").split()]
+        return (floats("lost_hist.txt"), floats("score_every_episode.txt"), floats("time_steps_when_episode_end.txt"),
+                floats("reward_every_time_step.txt"), q)
+
     # ------------------------------------------------------------------ checkpoint (row N2)
+    def save(self):
+        """BrainDQN.py:226-233: the network (weights, target, Adam slots) under save_path + gameName + '-' + timeStep, a
+        ``checkpoint`` file naming the newest one, (gameTimes, timeStep, epsilon) as three pickles in
+        <game>-saved-parameters.txt exactly like the reference writes them, then the logs"""
+        if self.save_path is None:
+            raise RuntimeError("no root_dir: the brain was built without a place to put saved_parameters/<model>/")
+        name = f"{self.gameName}-{self.timeStep}"
+        torch.save(self.net.state_dict(), self.save_path + name + ".pt")
+        with open(self.save_path + "checkpoint", "w") as f:
+            f.write(f'model_checkpoint_path: "{name}"\n')
+        with open(self.saved_parameters_file_path, "wb") as f:
+            pickle.dump(self.gameTimesTotal, f)
+            pickle.dump(self.timeStep, f)
+            pickle.dump(self.epsilon, f)
+        if self.record:
+            self._save_loss_score_timestep_reward_qtarget_to_file()
+
+    def _load_saved_parameters(self) -> bool:
+        """BrainDQN.py:176-192: restore the newest checkpoint if there is one; timeStep and epsilon come back,
+        onlineTimeStep does not (so a resumed run observes for OBSERVE steps again, as in the reference)"""
+        ck = self.save_path + "checkpoint"
+        if not os.path.exists(ck):
+            return False                            # "Could not find old network weights"
+        with open(ck) as f:
+            name = f.readline().split('"')[1]
+        self.net.load_state_dict(torch.load(self.save_path + name + ".pt", map_location=self.device))
+        if os.path.exists(self.saved_parameters_file_path) and os.path.getsize(self.saved_parameters_file_path) > 0:
+            with open(self.saved_parameters_file_path, "rb") as f:
+                self._game_times.fill_(int(pickle.load(f)))
+                self.timeStep = int(pickle.load(f))
+                self.epsilon = float(pickle.load(f))
+        return True
+
     def state_dict(self):
         return {"net": self.net.state_dict(), "gameTimes": self.gameTimesTotal, "timeStep": self.timeStep, "epsilon": self.epsilon}
 
@@ -213,6 +353,7 @@ class BrainDQN:
 
 class BrainDQNNature(BrainDQN):
     variant = "nature"
+    dir_name = '/dqn_nature/'              # BrainDQNNature.py:126
     loss_sum = False
     uses_target = True
 
@@ -224,6 +365,7 @@ class BrainDQNNature(BrainDQN):
 
 class BrainDoubleDQN(BrainDQNNature):
     variant = "double"
+    dir_name = '/double_dqn/'              # BrainDoubleDQN.py:35
 
     def trainQNetwork(self):
         """BrainDoubleDQN.py:37-69 -- the Double target the file defines but the shipped loop never calls (Q1)"""
@@ -238,6 +380,7 @@ class BrainDoubleDQN(BrainDQNNature):
 
 class BrainDuelingDQN(BrainDQNNature):
     dueling = True
+    dir_name = '/dueling_dqn/'             # BrainDuelingDQN_CC.py:35
 
     def trainQNetwork(self):
         """BrainDuelingDQN_CC.py:171-202 (Nature target on the dueling net)"""
@@ -246,6 +389,7 @@ class BrainDuelingDQN(BrainDQNNature):
 
 class BrainPrioritizedReplyDQN(BrainDQNNature):
     prioritized = True
+    dir_name = '/prioritized_reply_dqn/'   # BrainPrioritizedReplyDQN.py:162
 
     def _trainQNetwork(self):
         """BrainPrioritizedReplyDQN.py:277-315; the reference never runs target_replace_op here (Q3)"""

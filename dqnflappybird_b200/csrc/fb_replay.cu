@@ -404,3 +404,33 @@ extern "C" int fb_replay_rng_pos(fb_replay *r, uint32_t *pos_host2, int set, voi
     FB_CUDA_OK(cudaStreamSynchronize(st));
     return FB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Logging surface (BrainDQN.py:88-93): on a terminal the reference appends curScore to score_every_episode and
+// timeStep to time_steps_when_episode_end.  Batched: every env that ended an episode this step appends (time_step, env,
+// score) to a device log through one warp-aggregated atomic; the host sorts by (time_step, env) when it flushes, so the
+// order is deterministic.  *count_dev keeps counting past the capacity (the host reports the overflow); no host sync.
+__global__ void log_episodes_kernel(const uint8_t *__restrict__ terminal, const int32_t *__restrict__ score, int n, int first_env,
+                                    int time_step, int32_t *__restrict__ log, int *__restrict__ count, int cap) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool hit = e < n && terminal[e] != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (hit) {
+        const int at = base + __popc(m & ((1u << lane) - 1u));
+        if (at < cap) { log[3 * at] = time_step; log[3 * at + 1] = first_env + e; log[3 * at + 2] = score[e]; }
+    }
+}
+
+extern "C" int fb_log_episodes(const uint8_t *terminal_dev, const int32_t *score_dev, int n_envs, int first_env_id, int time_step,
+                               int32_t *log_dev, int *count_dev, int capacity, void *stream) {
+    FB_REQUIRE(terminal_dev && score_dev && log_dev && count_dev && n_envs > 0 && capacity > 0, "fb_log_episodes: bad argument");
+    log_episodes_kernel<<<(n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(terminal_dev, score_dev, n_envs, first_env_id, time_step,
+                                                                                log_dev, count_dev, capacity);
+    FB_CUDA_OK(cudaGetLastError());
+    return FB_OK;
+}

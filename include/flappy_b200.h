@@ -246,6 +246,13 @@ int fb_replay_gather(fb_replay *r, const uint8_t *ring_dev, const uint8_t *act_d
                      uint8_t *act_out_dev, float *rew_out_dev, uint8_t *term_out_dev, int32_t *env_out_dev, int32_t *k_out_dev,
                      void *stream);
 
+/* Logging surface (BrainDQN.py:88-93: score_every_episode.append(curScore), time_steps_when_episode_end.append(timeStep)):
+ * every env whose terminal flag is set appends (time_step, first_env_id + env, score) to log_dev i32[capacity][3] and
+ * bumps *count_dev (which keeps counting past capacity so the host can see an overflow).  Entries of one step arrive in
+ * no fixed order; the host sorts by (time_step, env) when it flushes. */
+int fb_log_episodes(const uint8_t *terminal_dev, const int32_t *score_dev, int n_envs, int first_env_id, int time_step,
+                    int32_t *log_dev, int *count_dev, int capacity, void *stream);
+
 /* Memory.store (:121-125) of transition k for every env, in env order.  mode 0 = the reference's
  * "every ancestor += change" arithmetic in item order (bit-exact rounding history); mode 1 = set leaves
  * and recompute touched ancestors as left+right (parallel, deterministic). */

@@ -120,3 +120,51 @@ def test_quirk_switches(mods):
     assert d.net.dueling is False and d.net.n_params == 898722       # Q2: the shipped code builds the plain net
     d2 = brains.BrainDuelingDQN(2, "bird", num_envs=4, replay_memory_per_env=8)
     assert d2.net.dueling is True and d2.net.n_params == 899235
+
+
+def test_logging_surface_and_disk_checkpoint(mods, tmp_path):
+    """Rows N2/N3 of SURVEY 8(f): the five log lists / text files of BrainDQN.py:49-58,270-294 fed from device-side
+    accumulators, and save/restore in the layout of BrainDQN.py:176-192,226-233 (weights + the three pickles)."""
+    import pickle
+    game, brains = mods
+    N = 64
+    kw = dict(num_envs=N, replay_memory_per_env=12, batch_size=32, observe=5, record=True, root_dir=str(tmp_path), save_every=10, seed=4)
+    brain = brains.BrainDQNNature(2, "bird", **kw)
+    assert brain.logs_path.endswith("logs_bird/dqn_nature/") and brain.save_path.endswith("saved_parameters/dqn_nature/")
+    gs = game.GameState(num_envs=N, seed=2, history=16, ring=brain.ring)
+    obs, *_ = gs.frame_step(torch.zeros(N, dtype=torch.uint8, device="cuda"))
+    brain.setInitState(obs)
+    want_steps, want_envs, want_scores, want_rewards = [], [], [], []
+    for step in range(60):
+        a = torch.zeros(N, dtype=torch.uint8, device="cuda") if step % 3 else brain.getAction()
+        obs, r, t, s = gs.frame_step(a)
+        tt, ss = t.cpu().numpy(), s.cpu().numpy()
+        for e in np.nonzero(tt)[0]:
+            want_steps.append(brain.timeStep); want_envs.append(int(e)); want_scores.append(int(ss[e]))
+        want_rewards.append(float(r.mean().item()))
+        brain.setPerception(obs, a, r, t, s)
+    assert len(want_steps) > 0                        # all-no-op episodes hit the ground on their 19th step
+    # saved at timeStep 10, 20, ... 50 (inside _trainQNetwork, BrainDQN.py:227): the lists were emptied into the files then
+    brain.flush_logs()
+    n_file = len(brain._get_loss_score_timestep_reward_qtarget_from_file()[1])
+    brain._save_loss_score_timestep_reward_qtarget_to_file()
+    loss, scores, steps, rewards, q = brain._get_loss_score_timestep_reward_qtarget_from_file()
+    assert n_file <= len(scores)
+    assert [int(x) for x in steps] == want_steps and [int(x) for x in scores] == want_scores
+    np.testing.assert_allclose(rewards, want_rewards, rtol=1e-6)
+    assert len(loss) == brain.net.adam_steps == 60 - 6 and len(q) == 32 * len(loss)
+    assert np.isfinite(loss).all() and brain.gameTimes == len(want_steps)
+    # the three pickles, readable the way BrainDQN.py:186-189 reads them
+    with open(brain.saved_parameters_file_path, "rb") as f:
+        g, ts, eps = pickle.load(f), pickle.load(f), pickle.load(f)
+    assert ts == 50 and isinstance(eps, float) and g <= brain.gameTimes
+    # a new brain on the same directory resumes from the newest checkpoint: timeStep and epsilon restored, onlineTimeStep not (Q12)
+    ref_params = torch.load(brain.save_path + "bird-50.pt")["params"]
+    b2 = brains.BrainDQNNature(2, "bird", **kw)
+    assert b2.timeStep == 50 and b2.onlineTimeStep == 0 and b2.epsilon == eps and b2.gameTimes == g
+    assert torch.equal(b2.net.params.cpu(), ref_params.cpu())
+    # without a checkpoint directory nothing is restored and save() says why it cannot run
+    b3 = brains.BrainDQN(2, "bird", num_envs=4, replay_memory_per_env=8)
+    assert b3.timeStep == 0
+    with pytest.raises(RuntimeError):
+        b3.save()
