@@ -168,3 +168,22 @@ def test_logging_surface_and_disk_checkpoint(mods, tmp_path):
     assert b3.timeStep == 0
     with pytest.raises(RuntimeError):
         b3.save()
+
+
+@pytest.mark.parametrize("model", ["dqn", "ddqn", "dqnnature", "duelingdqn", "prioritydqn"])
+def test_driver_loop_every_model(mods, model):
+    """FlappyBirdDQN.py:36-79, batched (row N4): --model picks the Brain, the env draws into its ring, the loop trains."""
+    from dqnflappybird_b200 import play
+    brain, gs, stats = play.playFlappyBird(model, num_envs=32, steps=20, replay_memory_per_env=12, batch_size=32, observe=3)
+    assert stats == {"steps": 20, "envs": 32, "updates": 20 - 4}
+    assert brain.timeStep == 20 and gs.steps == 21                  # one no-op step for the initial state (:63-69)
+    assert gs.ring.data_ptr() == brain.ring.data_ptr()
+    assert torch.isfinite(brain.net.params).all()
+
+
+def test_driver_loop_single_env_and_bad_model(mods):
+    from dqnflappybird_b200 import play
+    brain, gs, stats = play.playFlappyBird("dqnnature", num_envs=1, steps=12, replay_memory_per_env=40, batch_size=4, observe=5)
+    assert stats["updates"] == 12 - 6 and brain.timeStep == 12
+    with pytest.raises(SystemExit):
+        play.playFlappyBird("actorcritic")                         # outside the DQN hot path, like an unknown model (:51-54)
