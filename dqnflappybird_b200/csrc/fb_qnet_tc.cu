@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(128) fc1_head_kernel(const float *__restrict__
 #pragma unroll 5
         for (int z = 0; z < splits; z++) x += part[(size_t)z * split_stride + (size_t)b * H + j];
         x = fmaxf(x, 0.f);
-        h1[(size_t)b * H + j] = x;
+        if (h1 != nullptr) h1[(size_t)b * H + j] = x;          // kept for the head backward; acting / target forwards pass nullptr
         if (!L.dueling) { s0 = fmaf(x, params[L.wf2 + j * 2], s0); s1 = fmaf(x, params[L.wf2 + j * 2 + 1], s1); }
         else { s0 = fmaf(x, params[L.wa + j * 2], s0); s1 = fmaf(x, params[L.wa + j * 2 + 1], s1); sv = fmaf(x, params[L.wv + j], sv); }
     }
@@ -816,7 +816,14 @@ int make_plan(fb_qnet *n, int B, TcPlan **out) {
     p.conv3.n_tiles = p.conv2.n_tiles; p.conv3.slab_row0 = -8;                  // pad ring = the row before / after: offset -8
     for (int k = 0; k < 9; k++) { p.conv3.kb_rowoff[k] = (k / 3) * kG2 + (k % 3); p.conv3.kb_half[k] = 0; }
     set_kmajor(p.fc1); p.fc1.lbo_b = 8192; p.fc1.sbo_b = 1024; p.fc1.kstep_b = 2048;     // B = W_fc1 as stored (MN-major)
-    p.fc1.nkb = 25; p.fc1.kper = 25 / kFc1Splits; p.sf = kFc1Splits;
+    // K-splits of fc1 forward: 5 of 5 K-blocks fill the GPU at minibatch sizes (2 row tiles x 4 column tiles); from 8 row tiles
+    // up fewer, longer splits do (2 at 2,048 samples: 128 CTAs of 13 K-blocks, 2/5 of the partial-sum traffic)
+    {
+        const int mt = (B + 127) / 128, ct = H / 128;
+        int sf = kFc1Splits;
+        while (sf > 1 && mt * ct * (sf - 1) >= 128) sf--;
+        p.sf = sf; p.fc1.nkb = 25; p.fc1.kper = (25 + sf - 1) / sf;
+    }
     for (int k = 0; k < 25; k++) { p.fc1.a_rowoff[k] = 0; p.fc1.a_col[k] = k * 64; }
     // ---- data gradients
     set_kmajor(p.fc1_d); p.fc1_d.nkb = H / 64;
@@ -1008,7 +1015,7 @@ static int tc_forward_impl(fb_qnet *n, int slot, int w, const float *params_dev,
     if (join) FB_CUDA_OK(cudaStreamWaitEvent(st, join, 0));
     TdFuse none{};
     FB_CUDA_OK(tc::launch_pdl(fc1_head_kernel, dim3(B), dim3(128), 0, st, f.parth, p->sf, (size_t)n->max_batch * L.hidden, params_dev, L, B,
-                              f.h1, q_out, td ? *td : none));
+                              keep ? f.h1 : nullptr, q_out, td ? *td : none));
     return FB_OK;
 }
 
