@@ -420,12 +420,12 @@ def bench_learner(args, rank, world, dev):
             fr, ac, rw, tm = torch.cat(fr), torch.cat(ac), torch.cat(rw), torch.cat(tm)
             netv = QNetwork(device=dev, max_batch=mb_size, precision=args.learner_precision, seed=0)
             for _ in range(3):
-                netv.loss_backward("nature", fr, ac, rw, tm); netv.adam_step()
+                netv.train_step("nature", fr, ac, rw, tm)
             sync()
             Kv = max(10, K // 4)
             e0.record()
             for _ in range(Kv):
-                netv.loss_backward("nature", fr, ac, rw, tm); netv.adam_step()
+                netv.train_step("nature", fr, ac, rw, tm)
             e1.record(); sync()
             msv = e0.elapsed_time(e1) / Kv
             sweep[str(mb_size)] = {"updates_per_s": 1e3 / msv, "transitions_per_s": mb_size * 1e3 / msv,

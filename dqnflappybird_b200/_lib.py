@@ -91,6 +91,9 @@ _SIGNATURES = {
     "fb_qnet_act": ([_vp, _f32p, _u8p, C.c_longlong, _i32p, C.c_int, C.c_double, C.c_uint64, C.c_uint64, _vp, _f32p, _u8p, _vp], C.c_int),
     "fb_qnet_loss_backward": ([_vp, C.c_int, _f32p, _f32p, _u8p, C.c_longlong, _i32p, _i32p, _u8p, _f32p, _u8p, _f32p,
                                C.c_int, C.c_int, C.c_double, C.c_int, _f32p, _f32p, _f32p, _f32p, _vp], C.c_int),
+    "fb_qnet_train_step": ([_vp, C.c_int, _f32p, _f32p, _u8p, C.c_longlong, _i32p, _i32p, _u8p, _f32p, _u8p, _f32p,
+                            C.c_int, C.c_int, C.c_double, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float, C.c_float,
+                            C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp], C.c_int),
     "fb_qnet_adam": ([_vp, _f32p, _f32p, _f32p, _f32p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp], C.c_int),
     "fb_qnet_sync_target": ([_vp, _f32p, _f32p, _vp], C.c_int),
     "fb_dist_create": ([C.c_int, C.c_int, C.c_longlong, C.POINTER(C.c_void_p)], C.c_int),

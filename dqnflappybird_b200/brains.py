@@ -222,11 +222,15 @@ class BrainDQN:
         if mb.is_weights is not None:
             isw = self._isw32[:self.local_batch]
             isw.copy_(mb.is_weights)                 # the placeholder is tf.float32 (BrainPrioritizedReplyDQN.py:243)
-        self.net.loss_backward(variant, mb.frames, mb.actions, mb.rewards, mb.terminals, isw, self.gamma, self.loss_sum,
-                               self.local_batch * self.world, self._abs_err[:self.local_batch], self._q_target[:self.local_batch])
-        if self.world > 1 and self.net.exchange is None:
-            torch.distributed.all_reduce(self.net.grads)          # sum of per-shard gradients of the global loss
-        self.net.adam_step()                                      # with a peer exchange the sum happens inside the Adam kernel
+        args = (variant, mb.frames, mb.actions, mb.rewards, mb.terminals, isw, self.gamma, self.loss_sum, self.local_batch * self.world,
+                self._abs_err[:self.local_batch], self._q_target[:self.local_batch])
+        if self.world == 1:
+            self.net.train_step(*args)                            # one call: on the tensor-core path one CUDA graph, Adam included
+        else:
+            self.net.loss_backward(*args)
+            if self.net.exchange is None:
+                torch.distributed.all_reduce(self.net.grads)      # sum of per-shard gradients of the global loss
+            self.net.adam_step()                                  # with a peer exchange the sum happens inside the Adam kernel
         if mb.tree_idx is not None:
             mem.batch_update(mb.tree_idx, abs_errors=self._abs_err[:self.local_batch])   # :316
         if self.record:                                              # BrainDQN.py:222-225, kept on the device until flushed

@@ -540,6 +540,36 @@ extern "C" int fb_qnet_adam(fb_qnet *n, float *params_dev, const float *grads_de
     return FB_OK;
 }
 
+// session.run(trainStep) in one call (BrainDQN.py:204-207): fb_qnet_loss_backward followed by fb_qnet_adam with
+// alpha = lr sqrt(1 - beta2_power) / (1 - beta1_power).  On the tensor-core path the Adam update rides in the step's last
+// kernel and the whole step is one CUDA graph launch.
+extern "C" int fb_qnet_train_step(fb_qnet *n, int variant, float *params_dev, const float *target_params_dev, const uint8_t *frames_dev,
+                                  long long sample_stride, const int32_t *chan_off_s, const int32_t *chan_off_next,
+                                  const uint8_t *actions_dev, const float *rewards_dev, const uint8_t *terminals_dev,
+                                  const float *is_weights_dev, int batch, int global_batch, double gamma, int loss_sum, float *grads_dev,
+                                  float *loss_out_dev, float *abs_err_out_dev, float *q_target_out_dev, float *m_dev, float *v_dev, float lr,
+                                  float beta1, float beta2, float eps, float grad_scale, float beta1_power, float beta2_power, void *stream) {
+    FB_REQUIRE(n && params_dev && m_dev && v_dev && grads_dev, "fb_qnet_train_step: NULL argument");
+    if (n->precision == FB_PRECISION_BF16 && n->tc != nullptr) {
+        FB_REQUIRE(frames_dev && chan_off_s && chan_off_next && actions_dev && rewards_dev && terminals_dev, "fb_qnet_train_step: NULL argument");
+        FB_REQUIRE(batch > 0 && batch <= n->max_batch, "fb_qnet_train_step: batch exceeds max_batch");
+        FB_REQUIRE(variant >= 0 && variant <= 2, "fb_qnet_train_step: variant must be 0 (vanilla), 1 (nature) or 2 (double)");
+        FB_REQUIRE(variant == 0 || target_params_dev != nullptr, "fb_qnet_train_step: target parameters required");
+        if (global_batch <= 0) global_batch = batch;
+        FrameView fs = make_view(frames_dev, sample_stride, chan_off_s), fn = make_view(frames_dev, sample_stride, chan_off_next);
+        TcTrainArgs ta{variant, params_dev, target_params_dev, fs, fn, actions_dev, rewards_dev, terminals_dev, is_weights_dev, batch,
+                       global_batch, gamma, loss_sum, grads_dev, loss_out_dev ? loss_out_dev : n->loss_dev, abs_err_out_dev,
+                       q_target_out_dev, AdamFuse{1, m_dev, v_dev, lr, beta1, beta2, eps, grad_scale}};
+        return tc_train_step(n, ta, beta1_power, beta2_power, (cudaStream_t)stream);
+    }
+    int rc = fb_qnet_loss_backward(n, variant, params_dev, target_params_dev, frames_dev, sample_stride, chan_off_s, chan_off_next, actions_dev,
+                                   rewards_dev, terminals_dev, is_weights_dev, batch, global_batch, gamma, loss_sum, grads_dev, loss_out_dev,
+                                   abs_err_out_dev, q_target_out_dev, stream);
+    if (rc) return rc;
+    const float alpha = lr * sqrtf(1.f - beta2_power) / (1.f - beta1_power);
+    return fb_qnet_adam(n, params_dev, grads_dev, m_dev, v_dev, alpha, beta1, beta2, eps, grad_scale, stream);
+}
+
 // target_replace_op (BrainDQNNature.py:107-111): hard copy of all variables
 extern "C" int fb_qnet_sync_target(fb_qnet *n, float *target_dev, const float *params_dev, void *stream) {
     FB_REQUIRE(n && target_dev && params_dev, "fb_qnet_sync_target: NULL argument");

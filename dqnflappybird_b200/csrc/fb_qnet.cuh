@@ -69,6 +69,9 @@ void qnet_launch_head_backward(const float *h1, const float *dq, const float *pa
                                float *dh1_f32, __nv_bfloat16 *dh1_bf16, cudaStream_t st);
 
 // tcgen05 path entry points (fb_qnet_tc.cu); all return FB_OK or an error code with fb_set_error set
+// Adam fused into the last kernel of the training step (fb_qnet_train_step): alpha comes from the beta powers kept in
+// device memory, so a captured step replays without any per-step argument
+struct AdamFuse { int on; float *m, *v; float lr, beta1, beta2, eps, grad_scale; };
 struct TcTrainArgs {
     int variant;
     const float *params, *target;
@@ -76,6 +79,7 @@ struct TcTrainArgs {
     const uint8_t *actions; const float *rewards; const uint8_t *terminals; const float *isw;
     int B, global_batch; double gamma; int loss_sum;
     float *grads, *loss_out, *abs_err, *q_target;
+    AdamFuse ad;                            // ad.on: params is updated in place at the end of the step
 };
 int tc_state_create(fb_qnet *n);
 void tc_state_destroy(fb_qnet *n);
@@ -85,5 +89,6 @@ int tc_forward(fb_qnet *n, int slot, int ws, const float *params_dev, FrameView 
 int tc_forward_chunks(fb_qnet *n, int slot, const float *params_dev, const uint8_t *frames_dev, long long sample_stride,
                       const int32_t *chan_off, int batch, float *q_out_dev, cudaStream_t st);
 int tc_loss_backward(fb_qnet *n, const TcTrainArgs &a, cudaStream_t st);
+int tc_train_step(fb_qnet *n, const TcTrainArgs &a, float beta1_power, float beta2_power, cudaStream_t st);
 int tc_adam(fb_qnet *n, float *params_dev, const float *grads_dev, float *m_dev, float *v_dev, float alpha, float beta1, float beta2,
             float eps, float grad_scale, cudaStream_t st);

@@ -443,11 +443,9 @@ __global__ void pack_weights_kernel(const float *params, QnetLayout L, PackedWei
 
 // tf.train.AdamOptimizer step (TF 1.12 ApplyAdam, as adam_kernel in fb_qnet.cu) that also refreshes the bf16 operand
 // copies of the parameters it has just written, so the next training step starts without a pack kernel
-__global__ void adam_pack_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, int n,
-                                 float alpha, float beta1, float beta2, float eps, float grad_scale, QnetLayout L, PackedWeights pw) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float gi = g[i] * grad_scale;
+__device__ __forceinline__ void adam_one(int i, float g, float *__restrict__ p, float *__restrict__ m, float *__restrict__ v, float alpha,
+                                         float beta1, float beta2, float eps, float grad_scale, const QnetLayout &L, const PackedWeights &pw) {
+    float gi = g * grad_scale;
     float mi = m[i], vi = v[i];
     mi += (gi - mi) * (1.f - beta1);
     vi += (gi * gi - vi) * (1.f - beta2);
@@ -455,6 +453,12 @@ __global__ void adam_pack_kernel(float *__restrict__ p, const float *__restrict_
     float pi = p[i] - (mi * alpha) / (sqrtf(vi) + eps);
     p[i] = pi;
     scatter_packed(i, pi, L, pw, 0);
+}
+__global__ void adam_pack_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, int n,
+                                 float alpha, float beta1, float beta2, float eps, float grad_scale, QnetLayout L, PackedWeights pw) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    adam_one(i, g[i], p, m, v, alpha, beta1, beta2, eps, grad_scale, L, pw);
 }
 
 // column sums of bf16 matrices [rows][N] in row chunks -> part[chunk][N] (bias gradients; summed in order by
@@ -504,12 +508,21 @@ __global__ void __launch_bounds__(256) colsum_kernel(ColsumJobs jobs) {
 // weights, dh1 = dQ W^T masked by relu (bf16, the operand of the fc1 gradient GEMMs) and the fc1 bias gradient
 // sum_b dh1.  Block = 32 hidden units x 8 row lanes; block gridDim.x-1 does the head bias.
 constexpr int kHeadRows = 256;                      // rows of the minibatch per head-backward CTA row group
+// Fused Adam (fb_qnet_train_step): one thread of this kernel -- early on the step's critical path, exactly once per step --
+// turns the beta powers kept in device memory into this step's alpha = lr sqrt(1 - beta2^t) / (1 - beta1^t) (fp32, the
+// host formula) and advances them; the step's last kernel reads alpha.  Nothing about a step is a launch argument.
+struct AdamPow { int on; float *pow /* beta1^t, beta2^t */, *alpha; float lr, beta1, beta2; };
 __global__ void __launch_bounds__(256) head_backward_tc_kernel(const float *__restrict__ h1, const float *__restrict__ dq,
                                                                const float *__restrict__ params, QnetLayout L, int B,
                                                                float *__restrict__ hp /* [G][H][4] */, float *__restrict__ hb /* [G][4] */,
-                                                               const float *__restrict__ loss_terms, bf16 *__restrict__ dh1) {
+                                                               const float *__restrict__ loss_terms, bf16 *__restrict__ dh1, const AdamPow ap) {
     tc::pdl_wait();
     tc::pdl_launch();
+    if (ap.on && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        const float b1p = ap.pow[0], b2p = ap.pow[1];
+        *ap.alpha = ap.lr * sqrtf(1.f - b2p) / (1.f - b1p);
+        ap.pow[0] = b1p * ap.beta1; ap.pow[1] = b2p * ap.beta2;
+    }
     __shared__ float red[8][32][4];
     const int H = L.hidden, grp = blockIdx.y, b0 = grp * kHeadRows, b1 = min(B, b0 + kHeadRows);
     if ((int)blockIdx.x == H / 32) {                 // head bias partials: sum_b dq over this row group
@@ -629,10 +642,25 @@ struct FinalizeArgs {
     int G;
     float *loss_out;
 };
-__global__ void __launch_bounds__(256) finalize_grads_kernel(const FinalizeArgs a, QnetLayout L, float *__restrict__ grads) {
+// With `ad.on` the same launch also applies Adam (fb_qnet_train_step): the CTA that has just summed 32 gradient elements
+// updates those parameters, and CTAs [nb_fin, gridDim.x) update W_fc1 (four elements a thread), whose gradient the fc1 GEMM
+// wrote in place.  alpha was left in device memory by head_backward_tc_kernel, so the whole update replays as one CUDA graph.
+struct AdamDev { int on; float *p, *m, *v; float beta1, beta2, eps, grad_scale; const float *alpha; int nb_fin; };
+__global__ void __launch_bounds__(256) finalize_grads_kernel(const FinalizeArgs a, QnetLayout L, float *__restrict__ grads, const AdamDev ad,
+                                                            const PackedWeights pw) {
     tc::pdl_wait();
     tc::pdl_launch();
     __shared__ float red[8][32];
+    const float alpha = ad.on ? *ad.alpha : 0.f;
+    if (ad.on && (int)blockIdx.x >= ad.nb_fin) {                    // Adam on W_fc1
+        const int i0 = L.wf1 + ((int)blockIdx.x - ad.nb_fin) * 1024 + (int)threadIdx.x;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * 256;
+            if (i < L.bf1) adam_one(i, grads[i], ad.p, ad.m, ad.v, alpha, ad.beta1, ad.beta2, ad.eps, ad.grad_scale, L, pw);
+        }
+        return;
+    }
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5, H = L.hidden;
     const int k = blockIdx.x * 32 + lane;            // compact index: [0, wf1) then [bf1, total)
     const int n_compact = L.wf1 + (L.total - L.bf1);
@@ -679,6 +707,7 @@ __global__ void __launch_bounds__(256) finalize_grads_kernel(const FinalizeArgs 
 #pragma unroll
         for (int w = 0; w < 8; w++) t += red[w][lane];
         grads[i] = t;
+        if (ad.on) adam_one(i, t, ad.p, ad.m, ad.v, alpha, ad.beta1, ad.beta2, ad.eps, ad.grad_scale, L, pw);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.loss_out) {       // the loss: row-group sums in order
         float t = 0.f;
@@ -753,6 +782,10 @@ struct TcState {
     float *bp1, *bp2, *bp3;
     float *hp, *hb;             // head-backward partials per row group
     float *loss_terms;          // per-sample loss terms
+    float *adam_pow;            // device: beta1^t, beta2^t of the fused Adam (fb_qnet_train_step), then this step's alpha
+    float pow_host[2];          // what adam_pow will hold once everything enqueued so far has run
+    float *pow_pinned;          // 16 x 2 staging slots for re-seeding adam_pow
+    int pow_slot;
     PackedWeights pw[2];
     TcWeightMaps wm[2];
     std::map<int, TcPlan> plans;
@@ -893,6 +926,9 @@ int tc_state_create(fb_qnet *n) {
     FB_CUDA_OK(alloc_f(&t->bp3, ((B * kP2 + kChunk23 - 1) / kChunk23) * 64));
     FB_CUDA_OK(alloc_f(&t->hp, ((B + kHeadRows - 1) / kHeadRows) * H * 4)); FB_CUDA_OK(alloc_f(&t->hb, ((B + kHeadRows - 1) / kHeadRows) * 4 + 4));
     FB_CUDA_OK(alloc_f(&t->loss_terms, B));
+    FB_CUDA_OK(alloc_f(&t->adam_pow, 4));
+    FB_CUDA_OK(cudaMallocHost(&t->pow_pinned, 32 * sizeof(float)));
+    t->pow_host[0] = t->pow_host[1] = -1.f; t->pow_slot = 0;
     for (int s = 0; s < 2; s++) {
         PackedWeights &w = t->pw[s];
         FB_CUDA_OK(alloc_bf(&w.w1p, kC1 * kK1)); FB_CUDA_OK(alloc_bf(&w.w2p, kC2 * kK2)); FB_CUDA_OK(alloc_bf(&w.w3p, kC3 * kK3));
@@ -927,8 +963,10 @@ void tc_state_destroy(fb_qnet *n) {
         void *fs[] = {f.x2, f.z1, f.p2, f.a2, f.a3, f.parth, f.h1};
         for (void *p : fs) cudaFree(p);
     }
-    void *ps[] = {t->dh1, t->dz3, t->dz2, t->dp2, t->dz1, t->part1, t->part2, t->part3, t->bp1, t->bp2, t->bp3, t->hp, t->hb, t->loss_terms};
+    void *ps[] = {t->dh1, t->dz3, t->dz2, t->dp2, t->dz1, t->part1, t->part2, t->part3, t->bp1, t->bp2, t->bp3, t->hp, t->hb, t->loss_terms,
+                  t->adam_pow};
     for (void *p : ps) cudaFree(p);
+    if (t->pow_pinned) cudaFreeHost(t->pow_pinned);
     for (int s = 0; s < 2; s++) {
         PackedWeights &w = t->pw[s];
         void *ws[] = {w.w1p, w.w2p, w.w3p, w.wf1n, w.w3d, w.w2d};
@@ -1081,7 +1119,7 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     // ---- backward.  head: fp32 gradients of the head variables and the fc1 bias straight into grads, dh1 as bf16
     const int G = (B + kHeadRows - 1) / kHeadRows;
     FB_CUDA_OK(tc::launch_pdl(head_backward_tc_kernel, dim3(H / 32 + 1, G), dim3(256), 0, st, f.h1, n->dq, a.params, L, B, t->hp, t->hb,
-                              t->loss_terms, t->dh1));
+                              t->loss_terms, t->dh1, AdamPow{a.ad.on, t->adam_pow, t->adam_pow + 2, a.ad.lr, a.ad.beta1, a.ad.beta2}));
     FB_CUDA_OK(fork(st, sx));
     // fc1: dW = a3^T dh1 (aux, written in place), dz3 = (dh1 Wf1^T) * relu'(a3)
     FB_CUDA_OK((launch_tc_gemm<128, 1>(p->a3_m, p->dh1_b, p->fc1_w, dim3(13, H / 128, 1), EpiStoreF32{a.grads + L.wf1, kFlat, H, 0}, sx)));
@@ -1105,7 +1143,9 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     FB_CUDA_OK(fork(sx, st));
     FinalizeArgs fa{t->part1, t->part2, t->part3, p->s1, p->s2, p->s3, t->bp1, t->bp2, t->bp3, c1, c23, c23, t->hp, t->hb, G, a.loss_out};
     const int n_compact = L.wf1 + (L.total - L.bf1);
-    FB_CUDA_OK(tc::launch_pdl(finalize_grads_kernel, dim3((n_compact + 31) / 32), dim3(256), 0, st, fa, L, a.grads));
+    const int nb_fin = (n_compact + 31) / 32, nb_wf1 = a.ad.on ? (L.bf1 - L.wf1 + 1023) / 1024 : 0;
+    AdamDev ad{a.ad.on, const_cast<float *>(a.params), a.ad.m, a.ad.v, a.ad.beta1, a.ad.beta2, a.ad.eps, a.ad.grad_scale, t->adam_pow + 2, nb_fin};
+    FB_CUDA_OK(tc::launch_pdl(finalize_grads_kernel, dim3(nb_fin + nb_wf1), dim3(256), 0, st, fa, L, a.grads, ad, t->pw[0]));
     return FB_OK;
 }
 
@@ -1138,6 +1178,8 @@ int tc_loss_backward(fb_qnet *n, const TcTrainArgs &a, cudaStream_t st) {
     key.a.actions = a.actions; key.a.rewards = a.rewards; key.a.terminals = a.terminals; key.a.isw = a.isw;
     key.a.B = a.B; key.a.global_batch = a.global_batch; key.a.gamma = a.gamma; key.a.loss_sum = a.loss_sum;
     key.a.grads = a.grads; key.a.loss_out = a.loss_out; key.a.abs_err = a.abs_err; key.a.q_target = a.q_target;
+    key.a.ad.on = a.ad.on; key.a.ad.m = a.ad.m; key.a.ad.v = a.ad.v; key.a.ad.lr = a.ad.lr; key.a.ad.beta1 = a.ad.beta1; key.a.ad.beta2 = a.ad.beta2;
+    key.a.ad.eps = a.ad.eps; key.a.ad.grad_scale = a.ad.grad_scale;
     key.pack_online = n->packed_src[0] != a.params;
     key.pack_target = a.variant != 0 && n->packed_src[1] != a.target;
     int rc = FB_OK;
@@ -1168,8 +1210,26 @@ int tc_loss_backward(fb_qnet *n, const TcTrainArgs &a, cudaStream_t st) {
         if (rc) return rc;
         if (ge) ge->seen++;
     }
-    n->packed_src[0] = a.params;
+    n->packed_src[0] = a.params;            // (with a fused Adam the kernel has re-packed what it updated)
     if (a.variant != 0) n->packed_src[1] = a.target;
+    if (a.ad.on && n->packed_src[1] == a.params) n->packed_src[1] = nullptr;
+    return FB_OK;
+}
+
+// loss_backward + Adam as one step.  beta*_power are the caller's (QNetwork keeps them like TF's beta1_power / beta2_power
+// variables); the device copy is re-seeded only when it does not already hold them (first step, load_state_dict, a separate
+// fb_qnet_adam in between).
+int tc_train_step(fb_qnet *n, const TcTrainArgs &a, float beta1_power, float beta2_power, cudaStream_t st) {
+    TcState *t = n->tc;
+    FB_REQUIRE(t != nullptr && a.ad.on && a.ad.m && a.ad.v, "tc_train_step: bad argument");
+    if (t->pow_host[0] != beta1_power || t->pow_host[1] != beta2_power) {
+        float *slot = t->pow_pinned + 2 * (t->pow_slot++ & 15);
+        slot[0] = beta1_power; slot[1] = beta2_power;
+        FB_CUDA_OK(cudaMemcpyAsync(t->adam_pow, slot, 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    int rc = tc_loss_backward(n, a, st);
+    if (rc) { t->pow_host[0] = t->pow_host[1] = -1.f; return rc; }
+    t->pow_host[0] = beta1_power * a.ad.beta1; t->pow_host[1] = beta2_power * a.ad.beta2;
     return FB_OK;
 }
 

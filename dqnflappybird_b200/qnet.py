@@ -174,6 +174,34 @@ class QNetwork:
             ptr(q_target), self._stream()), "fb_qnet_loss_backward")
         return self.loss
 
+    def train_step(self, variant: str, frames: torch.Tensor, actions: torch.Tensor, rewards: torch.Tensor, terminals: torch.Tensor,
+                   is_weights: torch.Tensor | None = None, gamma: float = 0.99, loss_sum: bool = False, global_batch: int | None = None,
+                   abs_err: torch.Tensor | None = None, q_target: torch.Tensor | None = None, grad_scale: float = 1.0) -> torch.Tensor:
+        """session.run(trainStep) (BrainDQN.py:204-207): loss_backward + adam_step as one library call, bit-identical to the
+        two; on the tensor-core path one CUDA graph launch with Adam inside the step's last kernel.  With a peer exchange
+        (several GPUs) the sum over ranks lives in the Adam kernel, so the two calls are made separately."""
+        if self.exchange is not None:
+            self.loss_backward(variant, frames, actions, rewards, terminals, is_weights, gamma, loss_sum, global_batch, abs_err, q_target)
+            self.adam_step(grad_scale)
+            return self.loss
+        B = frames.shape[0]
+        assert frames.shape[1:] == (5, 80, 80) and frames.dtype == torch.uint8 and frames.is_contiguous()
+        off_s = (C.c_int32 * 4)(0, 6400, 12800, 19200)
+        off_n = (C.c_int32 * 4)(6400, 12800, 19200, 25600)
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        self._sync_versions()
+        _lib.check(self._L.fb_qnet_train_step(
+            self._h, VARIANTS[variant], self.params.data_ptr(), self.target.data_ptr(), frames.data_ptr(), 5 * 6400,
+            off_s, off_n, actions.data_ptr(), rewards.data_ptr(), terminals.data_ptr(), ptr(is_weights), B,
+            global_batch or B, float(gamma), int(loss_sum), self.grads.data_ptr(), self.loss.data_ptr(), ptr(abs_err),
+            ptr(q_target), self.adam_m.data_ptr(), self.adam_v.data_ptr(), float(self.lr), float(self.beta1), float(self.beta2),
+            float(self.adam_eps), float(grad_scale), float(self.beta1_power), float(self.beta2_power), self._stream()),
+            "fb_qnet_train_step")
+        self.beta1_power = np.float32(self.beta1_power * self.beta1)
+        self.beta2_power = np.float32(self.beta2_power * self.beta2)
+        self.adam_steps += 1
+        return self.loss
+
     def adam_step(self, grad_scale: float = 1.0):
         """One tf.train.AdamOptimizer step on self.params with self.grads (TF-1 ApplyAdam)."""
         one = np.float32(1)

@@ -200,6 +200,18 @@ int fb_qnet_loss_backward(fb_qnet *net, int variant, const float *params_dev, co
 int fb_qnet_adam(fb_qnet *net, float *params_dev, const float *grads_dev, float *m_dev, float *v_dev, float alpha,
                  float beta1, float beta2, float eps, float grad_scale, void *stream);
 
+/* session.run(trainStep) (BrainDQN.py:204-207) as ONE call: fb_qnet_loss_backward + fb_qnet_adam, bit-identical to the two
+ * calls.  beta1_power / beta2_power are the caller's beta^t (TF's beta1_power / beta2_power variables, before this step);
+ * alpha = lr*sqrt(1-beta2_power)/(1-beta1_power) in fp32.  With FB_PRECISION_BF16 Adam runs inside the step's last kernel
+ * from powers kept in device memory (re-seeded only when they differ from the caller's), so the whole update replays as one
+ * CUDA graph launch; params_dev is updated in place, grads_dev / loss_out_dev are still written. */
+int fb_qnet_train_step(fb_qnet *net, int variant, float *params_dev, const float *target_params_dev, const uint8_t *frames_dev,
+                       long long sample_stride, const int32_t *chan_off_s_host4, const int32_t *chan_off_next_host4,
+                       const uint8_t *actions_dev, const float *rewards_dev, const uint8_t *terminals_dev,
+                       const float *is_weights_dev, int batch, int global_batch, double gamma, int loss_sum, float *grads_dev,
+                       float *loss_out_dev, float *abs_err_out_dev, float *q_target_out_dev, float *m_dev, float *v_dev, float lr,
+                       float beta1, float beta2, float eps, float grad_scale, float beta1_power, float beta2_power, void *stream);
+
 /* target_replace_op (BrainDQNNature.py:107-111) */
 int fb_qnet_sync_target(fb_qnet *net, float *target_dev, const float *params_dev, void *stream);
 

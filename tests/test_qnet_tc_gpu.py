@@ -255,3 +255,44 @@ def test_training_steps_track_the_strict_path(mods):
     cos = (u0 @ u1 / (u0.norm() * u1.norm())).item()
     assert u1.abs().max().item() > 5e-6 and cos > 0.95, cos
     assert abs(nets[0].loss.item() - nets[1].loss.item()) <= 3e-2 * abs(nets[1].loss.item())
+
+
+@pytest.mark.parametrize("precision,variant,dueling", [("bf16", "nature", False), ("bf16", "double", True), ("bf16", "vanilla", False),
+                                                       ("fp32", "nature", False)])
+def test_train_step_is_loss_backward_plus_adam(mods, precision, variant, dueling):
+    """fb_qnet_train_step (Adam inside the step's last kernel, alpha from beta powers in device memory, one CUDA graph) is
+    bit-identical to fb_qnet_loss_backward + fb_qnet_adam, over graph capture / replay and when the two forms are mixed"""
+    _lib, game, qnet = mods
+    B = 64
+    frames = _env_frames(game, B, 21)
+    rng = np.random.default_rng(5)
+    a = torch.from_numpy(rng.integers(0, 2, B).astype(np.uint8)).cuda()
+    r = torch.from_numpy(rng.choice(np.array([0.1, 3.0, -3.0], np.float32), B)).cuda()
+    term = (r == -3.0).to(torch.uint8)
+    fused, split = [qnet.QNetwork(max_batch=B, seed=3, dueling=dueling, precision=precision, lr=1e-3) for _ in range(2)]
+    for n in (fused, split):
+        n.params.mul_(4.0); n.target.mul_(4.0)
+    plan = ["f", "f", "f", "f", "s", "f", "f", "s", "s", "f"]          # what `fused` does; `split` always takes the two calls
+    for k, how in enumerate(plan):
+        if how == "f":
+            lf = fused.train_step(variant, frames, a, r, term, loss_sum=(variant == "vanilla")).clone()
+        else:
+            lf = fused.loss_backward(variant, frames, a, r, term, loss_sum=(variant == "vanilla")).clone(); fused.adam_step()
+        ls = split.loss_backward(variant, frames, a, r, term, loss_sum=(variant == "vanilla")).clone(); split.adam_step()
+        assert torch.equal(lf, ls), (k, how)
+        assert torch.equal(fused.grads, split.grads), (k, how)
+        for name in ("params", "adam_m", "adam_v"):
+            assert torch.equal(getattr(fused, name), getattr(split, name)), (k, how, name)
+        assert fused.beta1_power == split.beta1_power and fused.beta2_power == split.beta2_power and fused.adam_steps == k + 1
+        if k == 5:
+            fused.sync_target(); split.sync_target()
+    # the updated parameters are what the next forward uses (the bf16 operand copies were refreshed by the fused Adam)
+    qf = fused.forward(qnet.FrameBatch.from_stack(frames, 0)); qs = split.forward(qnet.FrameBatch.from_stack(frames, 0))
+    assert torch.equal(qf, qs)
+    # resume: the powers come back from a checkpoint and re-seed the device copy
+    sd = split.state_dict()
+    fresh = qnet.QNetwork(max_batch=B, seed=9, dueling=dueling, precision=precision, lr=1e-3)
+    fresh.load_state_dict(sd)
+    fresh.train_step(variant, frames, a, r, term, loss_sum=(variant == "vanilla"))
+    split.loss_backward(variant, frames, a, r, term, loss_sum=(variant == "vanilla")); split.adam_step()
+    assert torch.equal(fresh.params, split.params)

@@ -53,18 +53,33 @@ def main():
     mb = brain.replayMemory.sample(B)
     net = brain.net
     torch.cuda.synchronize()
+    import time
     e0.record()
+    t0 = time.perf_counter()
     for _ in range(a.updates):
         net.loss_backward(brain.variant, mb.frames, mb.actions, mb.rewards, mb.terminals)
         net.adam_step()
+    host_issue_ms = (time.perf_counter() - t0) * 1e3 / a.updates      # host time to ISSUE an update (no sync): CPU-bound if ~ ms_net
     e1.record(); torch.cuda.synchronize()
     ms_net = e0.elapsed_time(e1) / a.updates
+    e0.record()
+    for _ in range(a.updates):
+        net.loss_backward(brain.variant, mb.frames, mb.actions, mb.rewards, mb.terminals)
+    e1.record(); torch.cuda.synchronize()
+    ms_lb = e0.elapsed_time(e1) / a.updates
+    for _ in range(3):
+        net.train_step(brain.variant, mb.frames, mb.actions, mb.rewards, mb.terminals)
+    e0.record()
+    for _ in range(a.updates):
+        net.train_step(brain.variant, mb.frames, mb.actions, mb.rewards, mb.terminals)
+    e1.record(); torch.cuda.synchronize()
+    ms_fused = e0.elapsed_time(e1) / a.updates
     e0.record()
     for _ in range(a.updates):
         brain.getAction()
     e1.record(); torch.cuda.synchronize()
     ms_act = e0.elapsed_time(e1) / a.updates
-    print(json.dumps({"ms_per_update_full": ms_full, "ms_per_update_net_only": ms_net, "updates_per_s": 1e3 / ms_full,
+    print(json.dumps({"ms_per_update_full": ms_full, "ms_per_update_net_only": ms_net, "ms_loss_backward_only": ms_lb, "ms_train_step_fused": ms_fused, "host_issue_ms_per_update": host_issue_ms, "updates_per_s": 1e3 / ms_full,
                       "ms_per_act": ms_act, "act_envs_per_s": N / (ms_act * 1e-3), "envs": N, "batch": B,
                       "precision": a.precision, "variant": brain.variant}))
 
