@@ -164,10 +164,18 @@ class BrainDQN:
         off = [(max(self._k - 3 + c, 0) % L) * 6400 for c in range(4)]
         return FrameBatch(self.ring, L * 6400, off, self.num_envs)
 
+    def next_rows(self):
+        """(actions u8[N], rewards f32[N], terminals u8[N]): the replay rows of the transition the next setPerception will
+        store.  getAction already writes its actions there; hand the other two to ``GameState.frame_step(..., out=...)`` and
+        pass everything back to setPerception, which then has nothing to copy (the observation is in the shared ring too)."""
+        return self.replayMemory.rows(self._k + 1)
+
     # ------------------------------------------------------------------ acting
     def getAction(self):
-        """BrainDQN.py:99-116.  Returns u8[N] action indices on the device (0 = [1,0] no-op, 1 = [0,1] flap); for a
-        single env the reference's one-hot float array."""
+        """BrainDQN.py:99-116.  Returns u8[N] action indices on the device (0 = [1,0] no-op, 1 = [0,1] flap), written
+        straight into the replay row of the coming transition; for a single env the reference's one-hot float array."""
+        if self.num_envs > 1:
+            self._actions = self.replayMemory.rows(self._k + 1)[0]
         self.net.act(self._act_view(), self.epsilon, self.seed + 2, self.first_env_id, self._rng_pos, self._actions, self._q)
         # change epsilon (BrainDQN.py:112-114), float64 like the reference
         if self.epsilon > self.final_epsilon and self.onlineTimeStep > self.observe:
@@ -186,12 +194,16 @@ class BrainDQN:
         self._to_ring(nextObserv, k % L)
         a_row, r_row, t_row = self.replayMemory.rows(k)
         dev = self.device
-        a = torch.as_tensor(np.asarray(action) if not torch.is_tensor(action) else action)
-        if a.dim() >= 1 and a.shape[-1] == 2 and (a.dim() == 2 or self.num_envs == 1):
-            a = a.reshape(-1, 2)[:, 1]               # one-hot -> index
-        a_row.copy_(a.reshape(-1).to(dev).to(torch.uint8))
-        r_row.copy_(torch.as_tensor(reward, dtype=torch.float32).reshape(-1).to(dev))
-        t_row.copy_(torch.as_tensor(terminal).reshape(-1).to(dev).to(torch.uint8))
+        same = lambda x, row: torch.is_tensor(x) and x.is_cuda and x.data_ptr() == row.data_ptr() and x.dtype == row.dtype
+        if not same(action, a_row):                  # (rows handed out by next_rows() / getAction are already in place)
+            a = torch.as_tensor(np.asarray(action) if not torch.is_tensor(action) else action)
+            if a.dim() >= 1 and a.shape[-1] == 2 and (a.dim() == 2 or self.num_envs == 1):
+                a = a.reshape(-1, 2)[:, 1]           # one-hot -> index
+            a_row.copy_(a.reshape(-1).to(dev).to(torch.uint8))
+        if not same(reward, r_row):
+            r_row.copy_(torch.as_tensor(reward, dtype=torch.float32).reshape(-1).to(dev))
+        if not same(terminal, t_row):
+            t_row.copy_(torch.as_tensor(terminal).reshape(-1).to(dev).to(torch.uint8))
         self._k = k
         self.replayMemory.appended(k)               # deque.append / Memory.store
         if self.onlineTimeStep > self.observe:

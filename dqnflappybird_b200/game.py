@@ -128,7 +128,7 @@ class GameState:
             raise ValueError("actions must be [N] indices, [N,2] one-hot, or one one-hot pair when num_envs == 1")
         return torch.from_numpy(np.ascontiguousarray(a)).to(self.device, non_blocking=True)
 
-    def frame_step(self, input_actions, render_full: bool = False):
+    def frame_step(self, input_actions, render_full: bool = False, out=None):
         """``GameState.frame_step`` (wrapped_flappy_bird.py:87-183) for every env.
 
         Returns ``(obs, reward, terminal, score)`` -- the reference's 4-tuple (:183) with the
@@ -140,12 +140,21 @@ class GameState:
         * ``num_envs == 1`` with a single one-hot pair: numpy ``u8[80,80,1]`` (what
           ``preprocess`` returns, FlappyBirdDQN.py:34), ``float``, ``bool``, ``int`` -- or the raw
           ``u8[288,512,3]`` ``image_data`` when ``render_full=True``.
+
+        ``out=(reward f32[N], terminal u8[N])`` makes the step kernel write those two straight into the caller's device
+        tensors -- e.g. the replay rows ``Brain.next_rows()`` hands out, so that no transition field is ever copied;
+        ``terminal`` is then returned as that u8 tensor.
         """
         single = (not torch.is_tensor(input_actions)) and np.asarray(input_actions).shape == (2,) and self.num_envs == 1
         a = self._to_action_index(input_actions)
         slot = (self.slot + 1) % self.history
+        reward, terminal = (self.reward, self.terminal) if out is None else out
+        if out is not None:
+            N = self.num_envs
+            assert reward.shape == (N,) and reward.dtype == torch.float32 and reward.is_cuda and reward.is_contiguous()
+            assert terminal.shape == (N,) and terminal.dtype == torch.uint8 and terminal.is_cuda and terminal.is_contiguous()
         _lib.check(self._L.fb_env_step(self._h, 1, a.data_ptr(), self.ring.data_ptr(), self.history, slot,
-                                       self.reward.data_ptr(), self.terminal.data_ptr(), self.score.data_ptr(),
+                                       reward.data_ptr(), terminal.data_ptr(), self.score.data_ptr(),
                                        _stream_ptr(self.device)), "fb_env_step")
         self.slot = slot
         self.steps += 1
@@ -155,8 +164,8 @@ class GameState:
                 img = self.render_full(0, 1)[0].cpu().numpy()
             else:
                 img = obs[0].cpu().numpy().reshape(80, 80, 1)
-            return img, float(self.reward[0].item()), bool(self.terminal[0].item()), int(self.score[0].item())
-        return obs, self.reward, self.terminal.bool(), self.score
+            return img, float(reward[0].item()), bool(terminal[0].item()), int(self.score[0].item())
+        return obs, reward, (terminal.bool() if out is None else terminal), self.score
 
     def step_random(self, n_steps: int = 1, p_flap: float = 0.5, action_seed: int = 1234, actions_out: torch.Tensor | None = None,
                     reward: torch.Tensor | None = None, terminal: torch.Tensor | None = None, score: torch.Tensor | None = None,

@@ -45,7 +45,8 @@ def playFlappyBird(model: str, num_envs: int = 1, steps: int | None = None, devi
     t0, done, last = time.perf_counter(), 0, 0
     while steps is None or done < steps:
         action = brain.getAction()
-        nextObserv, reward, terminal, curScore = flappyBird.frame_step(action)
+        out = brain.next_rows()[1:] if n_local > 1 else None          # reward / terminal land in the replay rows: nothing is copied
+        nextObserv, reward, terminal, curScore = flappyBird.frame_step(action, out=out)
         brain.setPerception(nextObserv, action, reward, terminal, curScore)
         done += 1
         if report_every and done % report_every == 0 and rank == 0:
