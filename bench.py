@@ -148,20 +148,33 @@ def run_reference(args, rank: int, world: int):
     oracle PORT of the path (kind "port") on all host threads."""
     if rank != 0:
         return
+    import numpy as np
+    from oracle import flappy_oracle as fo
     cores = os.cpu_count() or 1
     threads = min(cores, 256)
     n_envs = threads * 4
-    per_step = []
-    # calibrate so that warmup + steps finish within a couple of minutes
-    fps, _ = cpu_port_frames_per_s(n_envs, 2, threads)
-    steps_per_sample = max(2, int(fps * 1.0 / n_envs))        # ~1 s of CPU work per bench step
+    env = fo.OracleEnvs(n_envs, seed=42)
+    rng = np.random.default_rng(1234)
+
+    def run(n_steps):
+        acts = (rng.random((n_steps, n_envs)) < 0.5).astype(np.uint8)
+        t0 = time.perf_counter()
+        for t in range(n_steps):
+            env.step(acts[t], want_obs=True, threads=threads)
+        return time.perf_counter() - t0
+
+    # one bench step = a bounded sample of the workload, sized so that warm-up + K steps end within about two minutes
+    # whatever K is (at most ~1 s of CPU work per step)
+    run(2)
+    fps = n_envs * 8 / run(8)
+    budget_s = min(1.0, args.reference_budget_s / (args.steps + 0.25 * args.warmup))
+    steps_per_sample = max(1, int(fps * budget_s / n_envs))
     for k in range(args.warmup):
-        cpu_port_frames_per_s(n_envs, max(2, steps_per_sample // 4), threads)
+        run(max(1, steps_per_sample // 4))
     total_frames, total_t = 0, 0.0
     for k in range(args.steps):
-        f, dt = cpu_port_frames_per_s(n_envs, steps_per_sample, threads, seed=k)
-        total_frames += n_envs * steps_per_sample; total_t += dt
-        per_step.append(dt)
+        total_t += run(steps_per_sample)
+        total_frames += n_envs * steps_per_sample
     value = total_frames / total_t
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -484,6 +497,7 @@ def main():
     ap.add_argument("--learner-precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--learner-scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-learner-variants", action="store_true")
+    ap.add_argument("--reference-budget-s", type=float, default=120.0, help="--impl reference: CPU seconds for warm-up + all steps")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -23,6 +23,20 @@ def test_reference_arm_prints_the_contract_line():
     assert line["metric"] == bench.METRIC and line["config"]["workload"] == bench.WORKLOAD
 
 
+def test_reference_arm_is_bounded_for_any_step_count():
+    """each bench step is a bounded sample sized from K, so the driver's K (ours defaults to 2000) never makes the arm run long"""
+    import time
+    t0 = time.perf_counter()
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2000", "--warmup", "20",
+                        "--reference-budget-s", "8"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    dt = time.perf_counter() - t0
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["steps"] == 2000 and line["value"] > 0
+    assert dt < 120, dt                     # 8 s of samples + interpreter / library start-up
+
+
 def test_learner_cpu_baseline_runs():
     import bench
     ups, n, dt = bench.cpu_port_updates_per_s(0.5)
