@@ -29,6 +29,15 @@ WORKLOAD = ("configs[1] op mix (batched frame_step + render + preprocess, random
 UNIT = "frames/s"
 
 
+_RESULT_OUT = None
+
+
+def emit(line: dict):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def recorded_traffic(envs_per_gpu: int):
     """dram read+write bytes per launch of the step kernel from the committed ncu --set full capture."""
     try:
@@ -189,7 +198,7 @@ def run_reference(args, rank: int, world: int):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -311,7 +320,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "clocks": clocks,
         "learner": learner,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 FLOP_FWD, FLOP_BWD = 11675648, 16797696            # SURVEY 2.2 / 8(d), per sample
@@ -503,8 +512,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    # stdout carries the one JSON line and nothing else: NCCL's own log ("NCCL version ..." when NCCL_DEBUG is set) goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries the one JSON line and nothing else: file descriptor 1 is pointed at stderr for everything libraries
+    # print on their own (NCCL writes "NCCL version ..." to stdout), and the line goes out through the saved descriptor
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
