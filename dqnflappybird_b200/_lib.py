@@ -111,7 +111,7 @@ _SIGNATURES = {
     "fb_replay_sample_uniform": ([_vp, C.c_longlong, C.c_int, C.c_uint32, C.c_uint64, _i32p, _vp], C.c_int),
     "fb_replay_gather": ([_vp, _u8p, _u8p, _f32p, _u8p, C.c_longlong, C.c_int, _i32p, C.c_int, _u8p, _u8p, _f32p, _u8p, _i32p, _i32p, _vp], C.c_int),
     "fb_per_store": ([_vp, C.c_longlong, C.c_int, _vp], C.c_int),
-    "fb_per_sample": ([_vp, C.c_int, C.c_double, C.c_uint64, _i32p, _i32p, _vp, _vp, _vp], C.c_int),
+    "fb_per_sample": ([_vp, C.c_int, C.c_double, C.c_uint64, _i32p, _i32p, _vp, _vp, _f32p, _vp], C.c_int),
     "fb_per_update": ([_vp, _i32p, _f32p, _vp, C.c_int, C.c_int, _vp], C.c_int),
     "fb_per_tree_copy": ([_vp, _vp, C.c_int, _vp], C.c_int),
     "fb_replay_rng_pos": ([_vp, _vp, C.c_int, _vp], C.c_int),

@@ -230,10 +230,7 @@ class BrainDQN:
     def _update(self, variant: str):
         mem = self.replayMemory
         mb = mem.sample(self.local_batch)
-        isw = None
-        if mb.is_weights is not None:
-            isw = self._isw32[:self.local_batch]
-            isw.copy_(mb.is_weights)                 # the placeholder is tf.float32 (BrainPrioritizedReplyDQN.py:243)
+        isw = mb.is_weights_f32 if mb.is_weights is not None else None   # the placeholder is tf.float32 (BrainPrioritizedReplyDQN.py:243)
         args = (variant, mb.frames, mb.actions, mb.rewards, mb.terminals, isw, self.gamma, self.loss_sum, self.local_batch * self.world,
                 self._abs_err[:self.local_batch], self._q_target[:self.local_batch])
         if self.world == 1:

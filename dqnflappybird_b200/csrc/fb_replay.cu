@@ -170,16 +170,29 @@ __global__ void leaf_minmax_kernel(const double *tree, int cap, unsigned long lo
 //   mode 1 "rebuild": leaves are set, then every touched ancestor is recomputed as left + right,
 //          deepest level first.  Deterministic, parallel, no drift; used for N > 1 at scale.
 // leaves: tree indices.  prio: f64[count] or nullptr -> use *store_prio_bits (max leaf, 1.0 if 0) for all.
+// abs_err (f32, optional): Memory.batch_update's transform (:146-149) p = min(|err| + 0.01, 1)^0.6 in float32, computed
+// here into prio_scratch instead of by a kernel of its own.  store_prio_bits is the leaf scan's result; this kernel, its one
+// consumer on the store path, re-arms it for the next scan.
+constexpr int kMaxDupScan = 512;
+constexpr int kTopDepth = 11, kTopNodes = (1 << kTopDepth) - 1;          // depths 0..10 of the tree: 2,047 nodes, 16 KB
 __global__ void __launch_bounds__(1024) tree_update_kernel(double *tree, int cap, const int32_t *leaves, const double *prio,
-                                                           const unsigned long long *store_prio_bits, int count, int mode,
-                                                           double *change_scratch) {
+                                                           unsigned long long *store_prio_bits, int count, int mode,
+                                                           double *change_scratch, const float *abs_err, double *prio_scratch) {
     const int tid = threadIdx.x;
     const int max_depth = node_depth(2 * cap - 2);
     __shared__ double s_store;
+    __shared__ double s_top[kTopNodes];
     if (tid == 0) {
         double p = 1.0;
-        if (store_prio_bits) { p = __longlong_as_double((long long)store_prio_bits[0]); if (p == 0.0) p = 1.0; }   // Memory.store :121-125
+        if (store_prio_bits) {
+            p = __longlong_as_double((long long)store_prio_bits[0]); if (p == 0.0) p = 1.0;     // Memory.store :121-125
+            store_prio_bits[0] = 0ull; store_prio_bits[1] = ~0ull;
+        }
         s_store = p;
+    }
+    if (abs_err != nullptr) {
+        for (int i = tid; i < count; i += blockDim.x) prio_scratch[i] = (double)powf(fminf(abs_err[i] + 0.01f, 1.0f), 0.6f);
+        prio = prio_scratch;
     }
     __syncthreads();
     if (mode == 0) {
@@ -204,18 +217,38 @@ __global__ void __launch_bounds__(1024) tree_update_kernel(double *tree, int cap
         }
         return;
     }
+    __shared__ int s_leaf[kMaxDupScan];
+    const bool in_smem = prio != nullptr && count <= kMaxDupScan;     // a minibatch: scan for duplicates from shared memory
+    if (in_smem) { for (int i = tid; i < count; i += blockDim.x) s_leaf[i] = leaves[i]; __syncthreads(); }
     for (int i = tid; i < count; i += blockDim.x) {
         if (!prio) { tree[leaves[i]] = s_store; continue; }      // stores: distinct leaves, one value
-        bool last = true;                                         // duplicates in a minibatch: the last one wins, as in
-        for (int j = i + 1; j < count; j++)                       // the reference's sequential loop (:150-151)
-            if (leaves[j] == leaves[i]) { last = false; break; }
-        if (last) tree[leaves[i]] = prio[i];
+        const int mine = leaves[i];
+        int later = 0;                                            // duplicates in a minibatch: the last one wins, as in
+        if (in_smem) { for (int j = i + 1; j < count; j++) later += (s_leaf[j] == mine); }     // the reference's sequential loop (:150-151)
+        else { for (int j = i + 1; j < count; j++) if (leaves[j] == mine) { later = 1; break; } }
+        if (later == 0) tree[mine] = prio[i];
     }
     __syncthreads();
-    for (int d = max_depth - 1; d >= 0; d--) {
+    // deep levels in global memory (one dependent L2 round trip per level), then depths <= 10 from a shared-memory copy
+    const int top = max_depth - 1 < kTopDepth ? max_depth - 1 : kTopDepth - 1;      // deepest level handled in shared memory
+    for (int d = max_depth - 1; d > top; d--) {
         for (int i = tid; i < count; i += blockDim.x) {
             int leaf = leaves[i], dl = node_depth(leaf);
             if (dl > d) { int node = ancestor_at(leaf, dl, d); tree[node] = tree[2 * node + 1] + tree[2 * node + 2]; }
+        }
+        __syncthreads();
+    }
+    const int n_top = (2 << top) - 1, n_all = 2 * cap - 1;                         // nodes of depths 0..top
+    for (int j = tid; j < n_top && j < n_all; j += blockDim.x) s_top[j] = tree[j];
+    __syncthreads();
+    for (int d = top; d >= 0; d--) {
+        for (int i = tid; i < count; i += blockDim.x) {
+            int leaf = leaves[i], dl = node_depth(leaf);
+            if (dl > d) {
+                int node = ancestor_at(leaf, dl, d), cl = 2 * node + 1;
+                double v = (cl < n_top ? s_top[cl] : tree[cl]) + (cl + 1 < n_top ? s_top[cl + 1] : tree[cl + 1]);
+                s_top[node] = v; tree[node] = v;
+            }
         }
         __syncthreads();
     }
@@ -224,14 +257,17 @@ __global__ void __launch_bounds__(1024) tree_update_kernel(double *tree, int cap
 // Memory.sample (BrainPrioritizedReplyDQN.py:127-144): stratified v_i = uniform(i seg, (i+1) seg) with
 // np.random.uniform's 53-bit construction from two stream words (purpose 4), SumTree.get_leaf descent
 // (:73-100, "v <= tree[left]" goes left), ISWeights = (p/total / min_prob)^-beta in float64.
-// The top five levels of the tree are held in lane registers and walked with warp shuffles.
-__global__ void per_sample_kernel(const double *tree, int cap, int batch, double beta, const unsigned long long *minmax,
+// The top eleven levels of the tree are read once into shared memory; only the deeper ones cost a round trip each.
+__global__ void per_sample_kernel(const double *tree, int cap, int batch, double beta, unsigned long long *minmax,
                                   uint64_t seed, uint32_t *word_pos, int32_t *tree_idx, int32_t *data_idx, double *isw,
-                                  double *prio_out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+                                  double *prio_out, float *isw_f32) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_nodes = 2 * cap - 1;
-    const double top = lane < 31 && lane < n_nodes ? tree[lane] : 0.0;      // nodes 0..30 = depths 0..4
-    const double total = __shfl_sync(~0u, top, 0);
+    __shared__ double s_top[kTopNodes];                                      // depths 0..10: one round trip instead of eleven
+    const int n_top = n_nodes < kTopNodes ? n_nodes : kTopNodes;
+    for (int j = threadIdx.x; j < n_top; j += blockDim.x) s_top[j] = tree[j];
+    __syncthreads();
+    const double total = s_top[0];
     const uint32_t pos0 = *word_pos;
     const bool live = i < batch;
     double v = 0.0;
@@ -242,11 +278,13 @@ __global__ void per_sample_kernel(const double *tree, int cap, int batch, double
         v = a + (b - a) * u;
     }
     int parent = 0;
-#pragma unroll
-    for (int lvl = 0; lvl < 4; lvl++) {                                      // shuffle-walk while children are in registers
-        int cl = 2 * parent + 1;
-        double left = __shfl_sync(~0u, top, cl < 31 ? cl : 0);
-        if (cl + 1 < n_nodes && cl < 31) { if (v <= left) parent = cl; else { v -= left; parent = cl + 1; } }
+    if (live) {
+        for (;;) {                                                           // SumTree.get_leaf (:73-100) through the cached levels
+            int cl = 2 * parent + 1;
+            if (cl + 1 >= n_top) break;
+            double left = s_top[cl];
+            if (v <= left) parent = cl; else { v -= left; parent = cl + 1; }
+        }
     }
     if (live) {
         for (;;) {
@@ -260,20 +298,13 @@ __global__ void per_sample_kernel(const double *tree, int cap, int batch, double
         double prob = p / total, min_prob = min_p / total;
         tree_idx[i] = parent;
         data_idx[i] = parent - (cap - 1);
-        isw[i] = pow(prob / min_prob, -beta);
+        const double w = pow(prob / min_prob, -beta);
+        isw[i] = w;
+        if (isw_f32) isw_f32[i] = (float)w;             // the ISWeights placeholder is tf.float32 (BrainPrioritizedReplyDQN.py:243)
         if (prio_out) prio_out[i] = p;
     }
     __syncthreads();
-    if (i == 0) *word_pos = pos0 + 2 * (uint32_t)batch;
-}
-
-// Memory.batch_update's transform (:146-149): float32 like the numpy arrays the reference holds
-__global__ void per_priority_kernel(const float *abs_err, int count, double *prio) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    float e = abs_err[i] + 0.01f;
-    float c = fminf(e, 1.0f);
-    prio[i] = (double)powf(c, 0.6f);
+    if (i == 0) { *word_pos = pos0 + 2 * (uint32_t)batch; minmax[0] = 0ull; minmax[1] = ~0ull; }     // re-arm the leaf scan
 }
 
 __global__ void store_leaves_kernel(int N, int C, long long k, int32_t *leaves) {   // leaf of transition k for every env
@@ -303,6 +334,7 @@ extern "C" int fb_replay_create(int n_envs, int ring_len, int capacity_per_env, 
     FB_CUDA_OK(cudaMalloc(&r->word_pos, 2 * sizeof(uint32_t)));
     FB_CUDA_OK(cudaMemset(r->word_pos, 0, 2 * sizeof(uint32_t)));
     FB_CUDA_OK(cudaMalloc(&r->minmax, 2 * sizeof(unsigned long long)));
+    { const unsigned long long armed[2] = {0ull, ~0ull}; FB_CUDA_OK(cudaMemcpy(r->minmax, armed, sizeof(armed), cudaMemcpyHostToDevice)); }
     FB_CUDA_OK(cudaMalloc(&r->leaves, sizeof(int32_t) * r->scratch_n));
     FB_CUDA_OK(cudaMalloc(&r->prio, sizeof(double) * r->scratch_n));
     FB_CUDA_OK(cudaMalloc(&r->change, sizeof(double) * r->scratch_n));
@@ -346,9 +378,9 @@ extern "C" int fb_replay_gather(fb_replay *r, const uint8_t *ring_dev, const uin
     return FB_OK;
 }
 
+// leaf scan into r->minmax, which is armed ({0, ~0}) at create and re-armed by the scan's one consumer
+// (tree_update_kernel on the store path, per_sample_kernel on the sample path)
 static int refresh_minmax(fb_replay *r, cudaStream_t st) {
-    unsigned long long init[2] = {0ull, ~0ull};
-    FB_CUDA_OK(cudaMemcpyAsync(r->minmax, init, sizeof(init), cudaMemcpyHostToDevice, st));
     int blocks = (r->cap + 255) / 256; if (blocks > 592) blocks = 592;
     leaf_minmax_kernel<<<blocks, 256, 0, st>>>(r->tree, r->cap, r->minmax);
     FB_CUDA_OK(cudaGetLastError());
@@ -361,18 +393,18 @@ extern "C" int fb_per_store(fb_replay *r, long long k, int mode, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     int rc = refresh_minmax(r, st); if (rc) return rc;
     store_leaves_kernel<<<(r->N + 255) / 256, 256, 0, st>>>(r->N, r->C, k, r->leaves);
-    tree_update_kernel<<<1, 1024, 0, st>>>(r->tree, r->cap, r->leaves, nullptr, r->minmax, r->N, mode, r->change);
+    tree_update_kernel<<<1, 1024, 0, st>>>(r->tree, r->cap, r->leaves, nullptr, r->minmax, r->N, mode, r->change, nullptr, nullptr);
     FB_CUDA_OK(cudaGetLastError());
     return FB_OK;
 }
 
 extern "C" int fb_per_sample(fb_replay *r, int batch, double beta, uint64_t seed, int32_t *tree_idx_dev, int32_t *data_idx_dev,
-                             double *is_weights_dev, double *prio_out_dev, void *stream) {
+                             double *is_weights_dev, double *prio_out_dev, float *is_weights_f32_dev, void *stream) {
     FB_REQUIRE(r && r->tree && batch > 0 && batch <= 512 && tree_idx_dev && data_idx_dev && is_weights_dev, "fb_per_sample: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = refresh_minmax(r, st); if (rc) return rc;
     per_sample_kernel<<<1, ((batch + 31) / 32) * 32, 0, st>>>(r->tree, r->cap, batch, beta, r->minmax, seed, r->word_pos + 1,
-                                                            tree_idx_dev, data_idx_dev, is_weights_dev, prio_out_dev);
+                                                            tree_idx_dev, data_idx_dev, is_weights_dev, prio_out_dev, is_weights_f32_dev);
     FB_CUDA_OK(cudaGetLastError());
     return FB_OK;
 }
@@ -383,9 +415,8 @@ extern "C" int fb_per_update(fb_replay *r, const int32_t *tree_idx_dev, const fl
     FB_REQUIRE(r && r->tree && tree_idx_dev && (abs_err_dev || prio_dev) && batch > 0 && batch <= r->scratch_n && (mode == 0 || mode == 1),
                "fb_per_update: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    const double *p = prio_dev;
-    if (!p) { per_priority_kernel<<<(batch + 255) / 256, 256, 0, st>>>(abs_err_dev, batch, r->prio); p = r->prio; }
-    tree_update_kernel<<<1, 1024, 0, st>>>(r->tree, r->cap, tree_idx_dev, p, nullptr, batch, mode, r->change);
+    tree_update_kernel<<<1, 1024, 0, st>>>(r->tree, r->cap, tree_idx_dev, prio_dev, nullptr, batch, mode, r->change,
+                                           prio_dev ? nullptr : abs_err_dev, r->prio);
     FB_CUDA_OK(cudaGetLastError());
     return FB_OK;
 }

@@ -24,7 +24,7 @@ def cpython_setsize(k: int) -> int:
 
 
 class Minibatch:
-    __slots__ = ("frames", "actions", "rewards", "terminals", "idx", "tree_idx", "is_weights", "env", "k")
+    __slots__ = ("frames", "actions", "rewards", "terminals", "idx", "tree_idx", "is_weights", "is_weights_f32", "env", "k")
 
 
 class ReplayMemory:
@@ -94,7 +94,7 @@ class ReplayMemory:
         mb = Minibatch()
         mb.frames, mb.actions, mb.rewards, mb.terminals = self._frames[:batch], self._a[:batch], self._r[:batch], self._t[:batch]
         mb.idx, mb.env, mb.k = idx[:batch], self._env[:batch], self._k[:batch]
-        mb.tree_idx = mb.is_weights = None
+        mb.tree_idx = mb.is_weights = mb.is_weights_f32 = None
         return mb
 
     def sample(self, batch: int) -> Minibatch:
@@ -130,6 +130,7 @@ class PrioritizedMemory(ReplayMemory):
         dev = self.device
         self._tree_idx = torch.empty(max_batch, dtype=torch.int32, device=dev)
         self._isw = torch.empty(max_batch, dtype=torch.float64, device=dev)
+        self._isw32 = torch.empty(max_batch, dtype=torch.float32, device=dev)     # what the tf.float32 placeholder receives (:243)
         self._prio = torch.empty(max_batch, dtype=torch.float64, device=dev)
 
     def appended(self, k: int):
@@ -141,10 +142,12 @@ class PrioritizedMemory(ReplayMemory):
         """Memory.sample(n) (:127-144) -> tree_idx, minibatch, ISWeights"""
         self.beta = min(1.0, self.beta + self.beta_increment_per_sampling)
         _lib.check(self._L.fb_per_sample(self._h, batch, self.beta, self.seed, self._tree_idx.data_ptr(), self._idx.data_ptr(),
-                                         self._isw.data_ptr(), self._prio.data_ptr(), self._stream()), "fb_per_sample")
+                                         self._isw.data_ptr(), self._prio.data_ptr(), self._isw32.data_ptr(), self._stream()),
+                   "fb_per_sample")
         mb = self._gather(self._idx, batch, per=True)
         mb.tree_idx = self._tree_idx[:batch]
         mb.is_weights = self._isw[:batch]
+        mb.is_weights_f32 = self._isw32[:batch]
         return mb
 
     def batch_update(self, tree_idx: torch.Tensor, abs_errors: torch.Tensor | None = None, priorities: torch.Tensor | None = None):

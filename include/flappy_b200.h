@@ -269,9 +269,10 @@ int fb_log_episodes(const uint8_t *terminal_dev, const int32_t *score_dev, int n
  * "every ancestor += change" arithmetic in item order (bit-exact rounding history); mode 1 = set leaves
  * and recompute touched ancestors as left+right (parallel, deterministic). */
 int fb_per_store(fb_replay *r, long long k, int mode, void *stream);
-/* Memory.sample (:127-144); beta is the already-incremented value.  Word stream Philox(seed, purpose 4). */
+/* Memory.sample (:127-144); beta is the already-incremented value.  Word stream Philox(seed, purpose 4).
+ * is_weights_f32_dev (optional): the same weights rounded to fp32, what the tf.float32 ISWeights placeholder receives (:243). */
 int fb_per_sample(fb_replay *r, int batch, double beta, uint64_t seed, int32_t *tree_idx_dev, int32_t *data_idx_dev,
-                  double *is_weights_dev, double *prio_out_dev, void *stream);
+                  double *is_weights_dev, double *prio_out_dev, float *is_weights_f32_dev, void *stream);
 /* Memory.batch_update (:146-151): priorities from |TD error| (abs_err_dev, fp32 like the reference's arrays)
  * or given directly (prio_dev f64). */
 int fb_per_update(fb_replay *r, const int32_t *tree_idx_dev, const float *abs_err_dev, const double *prio_dev, int batch, int mode, void *stream);

@@ -7,14 +7,14 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 import torch  # noqa: E402
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
-from dqnflappybird_b200.brains import BrainDQNNature  # noqa: E402
+from dqnflappybird_b200.brains import MODELS  # noqa: E402
 from dqnflappybird_b200.game import GameState  # noqa: E402
 
 
 def main():
     dev = "cuda:0"
     N, B, C = 4096, 256, 28
-    brain = BrainDQNNature(2, "bird", num_envs=N, device=dev, replay_memory_per_env=C, batch_size=B, observe=1e18, seed=0, max_act_batch=2048)
+    brain = MODELS[sys.argv[1] if len(sys.argv) > 1 else "dqnnature"](2, "bird", num_envs=N, device=dev, replay_memory_per_env=C, batch_size=B, observe=1e18, seed=0, max_act_batch=2048)
     gs = GameState(num_envs=N, device=dev, seed=42, history=C + 4, ring=brain.ring)
     obs, *_ = gs.frame_step(torch.zeros(N, dtype=torch.uint8, device=dev))
     brain.setInitState(obs)
