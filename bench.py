@@ -339,7 +339,7 @@ def bench_learner(args, rank, world, dev):
     N, C = args.learner_envs, 28
     B = args.learner_batch * (world if args.learner_scaling == "weak" else 1)
     brain = BrainDQNNature(2, "bird", num_envs=N, device=dev, replay_memory_per_env=C, batch_size=B, observe=1e18, seed=0,
-                           first_env_id=rank * N, max_act_batch=2048, precision=args.learner_precision)
+                           first_env_id=rank * N, max_act_batch=4096, precision=args.learner_precision)
     gs = GameState(num_envs=N, device=dev, seed=42, history=C + 4, first_env_id=rank * N, ring=brain.ring)
     obs, *_ = gs.frame_step(torch.zeros(N, dtype=torch.uint8, device=dev))
     brain.setInitState(obs)
@@ -408,7 +408,7 @@ def bench_learner(args, rank, world, dev):
         ring_shared = brain.ring
         for name, cls in (("ddqn", BrainDoubleDQN), ("duelingdqn", BrainDuelingDQN), ("prioritydqn", BrainPrioritizedReplyDQN)):
             vb = cls(2, "bird", num_envs=N, device=dev, ring=ring_shared, replay_memory_per_env=C, batch_size=B, observe=1e18, seed=0,
-                     first_env_id=rank * N, max_act_batch=2048, precision=args.learner_precision)
+                     first_env_id=rank * N, max_act_batch=4096, precision=args.learner_precision)
             vb._k = brain._k
             for k in range(max(1, brain._k - C + 1), brain._k + 1):      # the ring already holds the rollout: register its steps
                 a_row, r_row, t_row = vb.replayMemory.rows(k)

@@ -58,7 +58,7 @@ class BrainDQN:
                  final_epsilon: float = FINAL_EPSILON, initial_epsilon: float = INITIAL_EPSILON,
                  replay_memory_per_env: int | None = None, replace_target_iter: int | None = REPLACE_TARGET_ITER,
                  hidden: int = 512, lr: float = 1e-6, seed: int = 0, first_env_id: int = 0, updates_per_step: int = 1,
-                 reference_quirks: bool = False, copy_target_at_init: bool = False, record: bool = False, max_act_batch: int = 1024,
+                 reference_quirks: bool = False, copy_target_at_init: bool = False, record: bool = False, max_act_batch: int = 4096,
                  precision: str = "bf16", peer_exchange: bool | None = None, root_dir: str | None = None, save_every: int = SAVE_EVERY,
                  log_capacity: int = 1 << 20):
         if actionNum != 2:

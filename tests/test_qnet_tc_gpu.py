@@ -163,15 +163,16 @@ def test_forward_from_ring_view_bf16(mods):
     assert np.abs(q - ref).max() <= 2e-2 * np.abs(ref).max()
 
 
-def test_forward_large_chunks_and_single_sample_bf16(mods):
-    """acting-sized batches: 2,500 envs through workspaces of 2,048 (fc1 forward then runs 2 K-splits instead of 5, the
-    conv1 slab is built from the u8 ring in the kernel, chunks alternate between two streams) and a batch of one"""
+@pytest.mark.parametrize("N,chunk", [(2500, 2048), (4500, 4096)])
+def test_forward_large_chunks_and_single_sample_bf16(mods, N, chunk):
+    """acting-sized batches: 2,500 envs through workspaces of 2,048 / 4,500 through 4,096 (fc1 forward then runs 2 / 1
+    K-splits instead of 5, the conv1 slab is built from the u8 ring in the kernel, chunks alternate between two streams)
+    and a batch of one"""
     _lib, game, qnet = mods
-    N = 2500
     gs = game.GameState(num_envs=N, seed=8, history=6)
     gs.step_random(31, 0.45, 11)
     fb = qnet.FrameBatch.from_ring(gs.ring, gs.slot)
-    net = qnet.QNetwork(max_batch=2048, precision="bf16")
+    net = qnet.QNetwork(max_batch=chunk, precision="bf16")
     net.params.mul_(4.0)
     q = net.forward(fb)
     small = qnet.QNetwork(max_batch=128, precision="bf16")           # same weights, 20 chunks of 128 (5 K-splits)
@@ -180,7 +181,7 @@ def test_forward_large_chunks_and_single_sample_bf16(mods):
     scale = q.abs().max().item()
     assert (q - qs).abs().max().item() <= 2e-5 * scale               # only the fp32 summation order of fc1 differs
     st = gs.stacked_state().permute(0, 3, 1, 2).contiguous().cpu().numpy()
-    pick = np.r_[0:24, 2040:2056, N - 24:N]                          # both chunks and their seam
+    pick = np.r_[0:24, chunk - 8:chunk + 8, N - 24:N]                # both chunks and their seam
     ref = qo.forward(torch.tensor(net.params.cpu().numpy().astype(np.float64)), st[pick]).numpy()
     assert np.abs(q.cpu().numpy()[pick] - ref).max() <= 2e-2 * np.abs(ref).max()
     one = game.GameState(num_envs=1, seed=8, history=6)

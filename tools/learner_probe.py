@@ -26,12 +26,13 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--double", action="store_true")
+    ap.add_argument("--max-act-batch", type=int, default=2048)
     a = ap.parse_args()
     dev = "cuda:0"
     N, B, C = a.envs, a.batch, 28
     cls = BrainDoubleDQN if a.double else BrainDQNNature
     brain = cls(2, "bird", num_envs=N, device=dev, replay_memory_per_env=C, batch_size=B, observe=1e18, seed=0,
-                max_act_batch=2048, precision=a.precision)
+                max_act_batch=a.max_act_batch, precision=a.precision)
     gs = GameState(num_envs=N, device=dev, seed=42, history=C + 4, ring=brain.ring)
     obs, *_ = gs.frame_step(torch.zeros(N, dtype=torch.uint8, device=dev))
     brain.setInitState(obs)
