@@ -55,6 +55,14 @@ _lib = None
 
 _u8p, _i32p, _f32p, _vp = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
 
+
+class StepSampling(C.Structure):
+    """fb_step_sampling (include/flappy_b200.h): the minibatch draw that rides at the head of fb_qnet_train_step_sampled"""
+    _fields_ = [("replay", C.c_void_p), ("ring_dev", C.c_void_p), ("act_dev", C.c_void_p), ("rew_dev", C.c_void_p), ("term_dev", C.c_void_p),
+                ("t", C.c_longlong), ("batch", C.c_int), ("setsize", C.c_uint32), ("seed", C.c_uint64), ("idx_out_dev", C.c_void_p),
+                ("frames_out_dev", C.c_void_p), ("act_out_dev", C.c_void_p), ("rew_out_dev", C.c_void_p), ("term_out_dev", C.c_void_p),
+                ("env_out_dev", C.c_void_p), ("k_out_dev", C.c_void_p)]
+
 _SIGNATURES = {
     "fb_last_error": ([], C.c_char_p),
     "fb_version": ([], C.c_int),
@@ -94,6 +102,8 @@ _SIGNATURES = {
     "fb_qnet_train_step": ([_vp, C.c_int, _f32p, _f32p, _u8p, C.c_longlong, _i32p, _i32p, _u8p, _f32p, _u8p, _f32p,
                             C.c_int, C.c_int, C.c_double, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float, C.c_float,
                             C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp], C.c_int),
+    "fb_qnet_train_step_sampled": ([_vp, _vp, C.c_int, _f32p, _f32p, _i32p, _i32p, C.c_int, C.c_double, C.c_int, _f32p, _f32p, _f32p, _f32p,
+                                    _f32p, _f32p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp], C.c_int),
     "fb_qnet_adam": ([_vp, _f32p, _f32p, _f32p, _f32p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp], C.c_int),
     "fb_qnet_sync_target": ([_vp, _f32p, _f32p, _vp], C.c_int),
     "fb_dist_create": ([C.c_int, C.c_int, C.c_longlong, C.POINTER(C.c_void_p)], C.c_int),

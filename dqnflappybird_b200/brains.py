@@ -72,6 +72,7 @@ class BrainDQN:
         self.updates_per_step = updates_per_step
         self.reference_quirks = reference_quirks
         self.record = record
+        self.fuse_sampling = True                  # uniform replay on one GPU: draw the minibatch inside the update's graph
         self.seed, self.first_env_id = seed, first_env_id
         # distributed: one process per GPU, replicated learner
         self.world = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
@@ -229,12 +230,16 @@ class BrainDQN:
 
     def _update(self, variant: str):
         mem = self.replayMemory
-        mb = mem.sample(self.local_batch)
+        sampling = None
+        if self.world == 1 and not self.prioritized and self.fuse_sampling:
+            sampling, mb = mem.step_sampling(self.local_batch)    # random.sample + gather ride at the head of the step's graph
+        else:
+            mb = mem.sample(self.local_batch)
         isw = mb.is_weights_f32 if mb.is_weights is not None else None   # the placeholder is tf.float32 (BrainPrioritizedReplyDQN.py:243)
         args = (variant, mb.frames, mb.actions, mb.rewards, mb.terminals, isw, self.gamma, self.loss_sum, self.local_batch * self.world,
                 self._abs_err[:self.local_batch], self._q_target[:self.local_batch])
         if self.world == 1:
-            self.net.train_step(*args)                            # one call: on the tensor-core path one CUDA graph, Adam included
+            self.net.train_step(*args, sampling=sampling)         # one call: on the tensor-core path one CUDA graph, Adam included
         else:
             self.net.loss_backward(*args)
             if self.net.exchange is None:

@@ -570,6 +570,35 @@ extern "C" int fb_qnet_train_step(fb_qnet *n, int variant, float *params_dev, co
     return fb_qnet_adam(n, params_dev, grads_dev, m_dev, v_dev, alpha, beta1, beta2, eps, grad_scale, stream);
 }
 
+// The same with the minibatch drawn by the step's first two kernels (uniform replay): on the tensor-core path sampling,
+// gather, forward, backward and Adam are one CUDA graph launch.
+extern "C" int fb_qnet_train_step_sampled(fb_qnet *n, const fb_step_sampling *sp, int variant, float *params_dev,
+                                          const float *target_params_dev, const int32_t *chan_off_s, const int32_t *chan_off_next,
+                                          int global_batch, double gamma, int loss_sum, float *grads_dev, float *loss_out_dev,
+                                          float *abs_err_out_dev, float *q_target_out_dev, float *m_dev, float *v_dev, float lr, float beta1,
+                                          float beta2, float eps, float grad_scale, float beta1_power, float beta2_power, void *stream) {
+    FB_REQUIRE(n && sp && sp->replay && params_dev && m_dev && v_dev && grads_dev && chan_off_s && chan_off_next,
+               "fb_qnet_train_step_sampled: NULL argument");
+    const int batch = sp->batch;
+    if (n->precision == FB_PRECISION_BF16 && n->tc != nullptr) {
+        FB_REQUIRE(batch > 0 && batch <= n->max_batch, "fb_qnet_train_step_sampled: batch exceeds max_batch");
+        FB_REQUIRE(variant >= 0 && variant <= 2, "fb_qnet_train_step_sampled: variant must be 0 (vanilla), 1 (nature) or 2 (double)");
+        FB_REQUIRE(variant == 0 || target_params_dev != nullptr, "fb_qnet_train_step_sampled: target parameters required");
+        if (global_batch <= 0) global_batch = batch;
+        FrameView fs = make_view(sp->frames_out_dev, 5 * 6400, chan_off_s), fn = make_view(sp->frames_out_dev, 5 * 6400, chan_off_next);
+        TcTrainArgs ta{variant, params_dev, target_params_dev, fs, fn, sp->act_out_dev, sp->rew_out_dev, sp->term_out_dev, nullptr, batch,
+                       global_batch, gamma, loss_sum, grads_dev, loss_out_dev ? loss_out_dev : n->loss_dev, abs_err_out_dev,
+                       q_target_out_dev, AdamFuse{1, m_dev, v_dev, lr, beta1, beta2, eps, grad_scale}, *sp};
+        return tc_train_step(n, ta, beta1_power, beta2_power, (cudaStream_t)stream);
+    }
+    int rc = replay_launch_sample_gather(*sp, (cudaStream_t)stream);
+    if (rc) return rc;
+    return fb_qnet_train_step(n, variant, params_dev, target_params_dev, sp->frames_out_dev, 5 * 6400, chan_off_s, chan_off_next,
+                              sp->act_out_dev, sp->rew_out_dev, sp->term_out_dev, nullptr, batch, global_batch, gamma, loss_sum, grads_dev,
+                              loss_out_dev, abs_err_out_dev, q_target_out_dev, m_dev, v_dev, lr, beta1, beta2, eps, grad_scale, beta1_power,
+                              beta2_power, stream);
+}
+
 // target_replace_op (BrainDQNNature.py:107-111): hard copy of all variables
 extern "C" int fb_qnet_sync_target(fb_qnet *n, float *target_dev, const float *params_dev, void *stream) {
     FB_REQUIRE(n && target_dev && params_dev, "fb_qnet_sync_target: NULL argument");

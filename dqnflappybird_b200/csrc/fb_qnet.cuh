@@ -80,7 +80,14 @@ struct TcTrainArgs {
     int B, global_batch; double gamma; int loss_sum;
     float *grads, *loss_out, *abs_err, *q_target;
     AdamFuse ad;                            // ad.on: params is updated in place at the end of the step
+    fb_step_sampling pro;                   // pro.replay != nullptr: the minibatch is drawn by the step's first two kernels
 };
+// fb_replay.cu: the two kernels of fb_replay_sample_uniform + fb_replay_gather on `st`; and the per-step patch of their
+// nodes in an instantiated graph (`t` is the only argument that changes)
+int replay_launch_sample_gather(const fb_step_sampling &p, cudaStream_t st);
+bool replay_is_sampler(const void *func);
+bool replay_is_gather(const void *func);
+int replay_patch_nodes(cudaGraphExec_t exec, cudaGraphNode_t sampler, cudaGraphNode_t gather, const fb_step_sampling &p);
 int tc_state_create(fb_qnet *n);
 void tc_state_destroy(fb_qnet *n);
 int tc_pack_weights(fb_qnet *n, const float *params_dev, int slot /* 0 online, 1 target */, cudaStream_t st);

@@ -773,7 +773,16 @@ struct GraphKey {               // a captured training step is replayed only for
     TcTrainArgs a;
     int pack_online, pack_target;
 };
-struct GraphEntry { GraphKey key; int seen; cudaGraphExec_t exec; };
+struct GraphEntry {
+    GraphKey key; int seen; cudaGraphExec_t exec;
+    cudaGraph_t graph;                      // kept only while its node handles are needed (the sampling head is patched every step)
+    cudaGraphNode_t n_sampler, n_gather;
+};
+static void destroy_entry(GraphEntry &g) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.graph) cudaGraphDestroy(g.graph);
+    g.exec = nullptr; g.graph = nullptr;
+}
 struct TcState {
     FwdWs ws[2];                // 0: the online net on s (kept for backward); 1: the other forwards, concurrently
     bf16 *dh1, *dz3, *dz2, *dp2, *dz1;
@@ -822,7 +831,7 @@ int make_plan(fb_qnet *n, int B, TcPlan **out) {
     auto it = t->plans.find(B);
     if (it != t->plans.end()) { *out = &it->second; return FB_OK; }
     if (t->plans.size() > 16) {                  // plans are referenced by captured graphs: drop both together
-        for (auto &g : t->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+        for (auto &g : t->graphs) destroy_entry(g);
         t->graphs.clear();
         t->plans.clear();
     }
@@ -957,7 +966,7 @@ int tc_state_create(fb_qnet *n) {
 void tc_state_destroy(fb_qnet *n) {
     TcState *t = n->tc;
     if (!t) return;
-    for (auto &g : t->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (auto &g : t->graphs) destroy_entry(g);
     for (int w = 0; w < 2; w++) {
         FwdWs &f = t->ws[w];
         void *fs[] = {f.x2, f.z1, f.p2, f.a2, f.a3, f.parth, f.h1};
@@ -1102,6 +1111,7 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
         e++;
         return r;
     };
+    if (a.pro.replay != nullptr) { rc = replay_launch_sample_gather(a.pro, st); if (rc) return rc; }     // the minibatch itself
     if (pack_online) { rc = tc_pack_weights(n, a.params, 0, st); if (rc) return rc; }
     FB_CUDA_OK(fork(st, sx));
     // ---- aux: Q(s') with the net the variant names (and the online net too for Double)
@@ -1156,7 +1166,7 @@ bool same_key(const GraphKey &x, const GraphKey &y) { return memcmp(&x, &y, size
 extern "C" int fb_qnet_set_conv1_mode(fb_qnet *n, int mode) {
     FB_REQUIRE(n != nullptr && n->tc != nullptr && mode >= 0 && mode <= 2, "fb_qnet_set_conv1_mode: needs FB_PRECISION_BF16 and mode 0..2");
     n->tc->conv1_mode = mode;
-    for (auto &g : n->tc->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (auto &g : n->tc->graphs) destroy_entry(g);
     n->tc->graphs.clear();
     return FB_OK;
 }
@@ -1180,6 +1190,13 @@ int tc_loss_backward(fb_qnet *n, const TcTrainArgs &a, cudaStream_t st) {
     key.a.grads = a.grads; key.a.loss_out = a.loss_out; key.a.abs_err = a.abs_err; key.a.q_target = a.q_target;
     key.a.ad.on = a.ad.on; key.a.ad.m = a.ad.m; key.a.ad.v = a.ad.v; key.a.ad.lr = a.ad.lr; key.a.ad.beta1 = a.ad.beta1; key.a.ad.beta2 = a.ad.beta2;
     key.a.ad.eps = a.ad.eps; key.a.ad.grad_scale = a.ad.grad_scale;
+    {   // the sampling head: everything but `t`, which is patched into the two nodes before every launch
+        const fb_step_sampling &q = a.pro; fb_step_sampling &k = key.a.pro;
+        k.replay = q.replay; k.ring_dev = q.ring_dev; k.act_dev = q.act_dev; k.rew_dev = q.rew_dev; k.term_dev = q.term_dev;
+        k.batch = q.batch; k.setsize = q.setsize; k.seed = q.seed; k.idx_out_dev = q.idx_out_dev; k.frames_out_dev = q.frames_out_dev;
+        k.act_out_dev = q.act_out_dev; k.rew_out_dev = q.rew_out_dev; k.term_out_dev = q.term_out_dev; k.env_out_dev = q.env_out_dev;
+        k.k_out_dev = q.k_out_dev;
+    }
     key.pack_online = n->packed_src[0] != a.params;
     key.pack_target = a.variant != 0 && n->packed_src[1] != a.target;
     int rc = FB_OK;
@@ -1187,12 +1204,13 @@ int tc_loss_backward(fb_qnet *n, const TcTrainArgs &a, cudaStream_t st) {
     if (t->use_graph) {
         for (auto &g : t->graphs) if (same_key(g.key, key)) { ge = &g; break; }
         if (!ge) {
-            if (t->graphs.size() >= 8) { for (auto &g : t->graphs) if (g.exec) cudaGraphExecDestroy(g.exec); t->graphs.clear(); }
-            t->graphs.push_back(GraphEntry{key, 0, nullptr});
+            if (t->graphs.size() >= 8) { for (auto &g : t->graphs) destroy_entry(g); t->graphs.clear(); }
+            t->graphs.push_back(GraphEntry{key, 0, nullptr, nullptr, nullptr, nullptr});
             ge = &t->graphs.back();
         }
     }
     if (ge && ge->exec) {
+        if (a.pro.replay != nullptr) { rc = replay_patch_nodes(ge->exec, ge->n_sampler, ge->n_gather, a.pro); if (rc) return rc; }
         FB_CUDA_OK(cudaGraphLaunch(ge->exec, st));
     } else if (ge && ge->seen >= 1) {            // second identical call: capture (everything lazy was initialised by the first)
         cudaGraph_t graph = nullptr;
@@ -1202,7 +1220,23 @@ int tc_loss_backward(fb_qnet *n, const TcTrainArgs &a, cudaStream_t st) {
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
         FB_CUDA_OK(ce);
         cudaError_t ie = cudaGraphInstantiate(&ge->exec, graph, 0);
-        cudaGraphDestroy(graph);
+        if (ie == cudaSuccess && a.pro.replay != nullptr) {       // remember the two replay nodes: their `t` changes every step
+            size_t nn = 0;
+            cudaGraphGetNodes(graph, nullptr, &nn);
+            std::vector<cudaGraphNode_t> nodes(nn);
+            if (nn) cudaGraphGetNodes(graph, nodes.data(), &nn);
+            for (size_t i = 0; i < nn; i++) {
+                cudaGraphNodeType ty;
+                if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+                cudaKernelNodeParams kp{};
+                if (cudaGraphKernelNodeGetParams(nodes[i], &kp) != cudaSuccess) continue;
+                if (replay_is_sampler(kp.func)) ge->n_sampler = nodes[i];
+                else if (replay_is_gather(kp.func)) ge->n_gather = nodes[i];
+            }
+            if (!ge->n_sampler || !ge->n_gather) { cudaGraphExecDestroy(ge->exec); ge->exec = nullptr; ie = cudaErrorUnknown; }
+        }
+        if (ie == cudaSuccess && a.pro.replay != nullptr) ge->graph = graph;      // its node handles stay in use
+        else cudaGraphDestroy(graph);
         FB_CUDA_OK(ie);
         FB_CUDA_OK(cudaGraphLaunch(ge->exec, st));
     } else {

@@ -378,6 +378,45 @@ extern "C" int fb_replay_gather(fb_replay *r, const uint8_t *ring_dev, const uin
     return FB_OK;
 }
 
+// ---- sampling + gather as the head of a captured training step (fb_qnet_train_step_sampled) -------------------------
+static bool sampling_population(const fb_step_sampling &p, uint32_t *n_out) {
+    long long k_lo = p.t - p.replay->C + 1; if (k_lo < 1) k_lo = 1;
+    long long n = (p.t - k_lo + 1) * p.replay->N;
+    *n_out = (uint32_t)n;
+    return p.t >= 1 && n >= p.batch;
+}
+static GatherArgs sampling_gather_args(const fb_step_sampling &p) {
+    const fb_replay *r = p.replay;
+    return GatherArgs{p.ring_dev, r->N, r->L, p.act_dev, p.rew_dev, p.term_dev, p.t, r->C, 0, p.idx_out_dev, p.batch,
+                      p.frames_out_dev, p.act_out_dev, p.rew_out_dev, p.term_out_dev, p.env_out_dev, p.k_out_dev};
+}
+int replay_launch_sample_gather(const fb_step_sampling &p, cudaStream_t st) {
+    FB_REQUIRE(p.replay && p.ring_dev && p.act_dev && p.rew_dev && p.term_dev && p.idx_out_dev && p.frames_out_dev && p.act_out_dev &&
+               p.rew_out_dev && p.term_out_dev && p.batch > 0 && p.batch <= 512 && p.setsize <= 2u * kHashSize, "step sampling: bad argument");
+    uint32_t n;
+    if (!sampling_population(p, &n)) { fb_set_error("Sample larger than population or is negative"); return FB_ERR_INVALID; }
+    sample_uniform_kernel<<<1, kSampThreads, 0, st>>>(n, p.batch, p.setsize, p.seed, p.replay->word_pos, p.idx_out_dev);
+    gather_kernel<<<dim3(p.batch, 5), 128, 0, st>>>(sampling_gather_args(p));
+    FB_CUDA_OK(cudaGetLastError());
+    return FB_OK;
+}
+bool replay_is_sampler(const void *func) { return func == (const void *)sample_uniform_kernel; }
+bool replay_is_gather(const void *func) { return func == (const void *)gather_kernel; }
+int replay_patch_nodes(cudaGraphExec_t exec, cudaGraphNode_t sampler, cudaGraphNode_t gather, const fb_step_sampling &p) {
+    uint32_t n;
+    if (!sampling_population(p, &n)) { fb_set_error("Sample larger than population or is negative"); return FB_ERR_INVALID; }
+    int batch = p.batch; uint32_t setsize = p.setsize; uint64_t seed = p.seed; uint32_t *word_pos = p.replay->word_pos; int32_t *idx = p.idx_out_dev;
+    void *sargs[] = {&n, &batch, &setsize, &seed, &word_pos, &idx};
+    cudaKernelNodeParams kp{};
+    kp.func = (void *)sample_uniform_kernel; kp.gridDim = dim3(1); kp.blockDim = dim3(kSampThreads); kp.sharedMemBytes = 0; kp.kernelParams = sargs;
+    FB_CUDA_OK(cudaGraphExecKernelNodeSetParams(exec, sampler, &kp));
+    GatherArgs g = sampling_gather_args(p);
+    void *gargs[] = {&g};
+    kp.func = (void *)gather_kernel; kp.gridDim = dim3(p.batch, 5); kp.blockDim = dim3(128); kp.kernelParams = gargs;
+    FB_CUDA_OK(cudaGraphExecKernelNodeSetParams(exec, gather, &kp));
+    return FB_OK;
+}
+
 // leaf scan into r->minmax, which is armed ({0, ~0}) at create and re-armed by the scan's one consumer
 // (tree_update_kernel on the store path, per_sample_kernel on the sample path)
 static int refresh_minmax(fb_replay *r, cudaStream_t st) {

@@ -176,10 +176,38 @@ class QNetwork:
 
     def train_step(self, variant: str, frames: torch.Tensor, actions: torch.Tensor, rewards: torch.Tensor, terminals: torch.Tensor,
                    is_weights: torch.Tensor | None = None, gamma: float = 0.99, loss_sum: bool = False, global_batch: int | None = None,
-                   abs_err: torch.Tensor | None = None, q_target: torch.Tensor | None = None, grad_scale: float = 1.0) -> torch.Tensor:
+                   abs_err: torch.Tensor | None = None, q_target: torch.Tensor | None = None, grad_scale: float = 1.0,
+                   sampling=None) -> torch.Tensor:
         """session.run(trainStep) (BrainDQN.py:204-207): loss_backward + adam_step as one library call, bit-identical to the
         two; on the tensor-core path one CUDA graph launch with Adam inside the step's last kernel.  With a peer exchange
-        (several GPUs) the sum over ranks lives in the Adam kernel, so the two calls are made separately."""
+        (several GPUs) the sum over ranks lives in the Adam kernel, so the two calls are made separately.
+
+        ``sampling`` (``ReplayMemory.step_sampling(batch)[0]``): the minibatch is drawn and gathered by the step's first two
+        kernels -- ``random.sample`` and the list comprehensions of BrainDQN.py:197-201 ride in the same graph; ``frames`` /
+        ``actions`` / ``rewards`` / ``terminals`` must then be the replay's own minibatch buffers."""
+        if sampling is not None and self.exchange is None and is_weights is None:
+            assert frames.data_ptr() == sampling.frames_out_dev and frames.shape[0] == sampling.batch
+            off_s = (C.c_int32 * 4)(0, 6400, 12800, 19200)
+            off_n = (C.c_int32 * 4)(6400, 12800, 19200, 25600)
+            ptr = lambda t: t.data_ptr() if t is not None else None
+            self._sync_versions()
+            _lib.check(self._L.fb_qnet_train_step_sampled(
+                self._h, C.addressof(sampling), VARIANTS[variant], self.params.data_ptr(), self.target.data_ptr(), off_s, off_n,
+                global_batch or sampling.batch, float(gamma), int(loss_sum), self.grads.data_ptr(), self.loss.data_ptr(), ptr(abs_err),
+                ptr(q_target), self.adam_m.data_ptr(), self.adam_v.data_ptr(), float(self.lr), float(self.beta1), float(self.beta2),
+                float(self.adam_eps), float(grad_scale), float(self.beta1_power), float(self.beta2_power), self._stream()),
+                "fb_qnet_train_step_sampled")
+            self.beta1_power = np.float32(self.beta1_power * self.beta1)
+            self.beta2_power = np.float32(self.beta2_power * self.beta2)
+            self.adam_steps += 1
+            return self.loss
+        if sampling is not None:                 # not fusable here: draw the minibatch with its own two launches
+            _lib.check(self._L.fb_replay_sample_uniform(sampling.replay, sampling.t, sampling.batch, sampling.setsize, sampling.seed,
+                                                        sampling.idx_out_dev, self._stream()), "fb_replay_sample_uniform")
+            _lib.check(self._L.fb_replay_gather(sampling.replay, sampling.ring_dev, sampling.act_dev, sampling.rew_dev, sampling.term_dev,
+                                                sampling.t, 0, sampling.idx_out_dev, sampling.batch, sampling.frames_out_dev,
+                                                sampling.act_out_dev, sampling.rew_out_dev, sampling.term_out_dev, sampling.env_out_dev,
+                                                sampling.k_out_dev, self._stream()), "fb_replay_gather")
         if self.exchange is not None:
             self.loss_backward(variant, frames, actions, rewards, terminals, is_weights, gamma, loss_sum, global_batch, abs_err, q_target)
             self.adam_step(grad_scale)

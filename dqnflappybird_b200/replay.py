@@ -91,11 +91,24 @@ class ReplayMemory:
                                             self.term.data_ptr(), self.t, int(per), idx.data_ptr(), batch,
                                             self._frames.data_ptr(), self._a.data_ptr(), self._r.data_ptr(), self._t.data_ptr(),
                                             self._env.data_ptr(), self._k.data_ptr(), self._stream()), "fb_replay_gather")
+        return self._minibatch(idx, batch)
+
+    def _minibatch(self, idx: torch.Tensor, batch: int) -> Minibatch:
         mb = Minibatch()
         mb.frames, mb.actions, mb.rewards, mb.terminals = self._frames[:batch], self._a[:batch], self._r[:batch], self._t[:batch]
         mb.idx, mb.env, mb.k = idx[:batch], self._env[:batch], self._k[:batch]
         mb.tree_idx = mb.is_weights = mb.is_weights_f32 = None
         return mb
+
+    def step_sampling(self, batch: int):
+        """``sample(batch)`` as a descriptor instead of two launches: (fb_step_sampling, Minibatch of the buffers it fills).
+        ``QNetwork.train_step(..., sampling=...)`` runs the draw and the gather as the first two kernels of the update."""
+        if self.t < 1 or len(self) < batch:
+            raise ValueError("Sample larger than population or is negative")
+        sp = _lib.StepSampling(self._h.value, self.ring.data_ptr(), self.act.data_ptr(), self.rew.data_ptr(), self.term.data_ptr(), self.t,
+                               batch, cpython_setsize(batch), self.seed, self._idx.data_ptr(), self._frames.data_ptr(), self._a.data_ptr(),
+                               self._r.data_ptr(), self._t.data_ptr(), self._env.data_ptr(), self._k.data_ptr())
+        return sp, self._minibatch(self._idx, batch)
 
     def sample(self, batch: int) -> Minibatch:
         """random.sample(self.replayMemory, BATCH_SIZE) (BrainDQN.py:197) + the four list comprehensions (:198-201)"""

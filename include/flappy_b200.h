@@ -280,6 +280,29 @@ int fb_per_update(fb_replay *r, const int32_t *tree_idx_dev, const float *abs_er
 int fb_per_tree_copy(fb_replay *r, double *out_dev, int n_nodes, void *stream);
 int fb_replay_rng_pos(fb_replay *r, uint32_t *pos_host2, int set, void *stream);
 
+/* The minibatch of fb_qnet_train_step drawn INSIDE the step: random.sample + the list comprehensions of BrainDQN.py:197-201
+ * (fb_replay_sample_uniform + fb_replay_gather with these arguments) run as the first two kernels of the step, so that on
+ * the tensor-core path sampling, gather, forward, backward and Adam are ONE CUDA graph launch; `t` is the only field that
+ * changes from step to step and is patched into the two kernel nodes.  frames_out_dev etc. are the minibatch buffers the
+ * step then reads (pass the same frames pointer as frames_dev of the step, sample_stride 5*6400, chan_off 0.. / 6400..). */
+typedef struct fb_step_sampling {
+    fb_replay *replay;
+    const uint8_t *ring_dev, *act_dev; const float *rew_dev; const uint8_t *term_dev;
+    long long t;                        /* time of the newest stored transition */
+    int batch; uint32_t setsize; uint64_t seed;
+    int32_t *idx_out_dev;
+    uint8_t *frames_out_dev, *act_out_dev; float *rew_out_dev; uint8_t *term_out_dev;
+    int32_t *env_out_dev, *k_out_dev;   /* optional */
+} fb_step_sampling;
+/* fb_qnet_train_step with the minibatch drawn first (uniform replay).  FB_ERR_INVALID with "Sample larger than population
+ * or is negative" when the replay holds fewer than `batch` transitions (random.sample's ValueError). */
+int fb_qnet_train_step_sampled(fb_qnet *net, const fb_step_sampling *sampling, int variant, float *params_dev,
+                               const float *target_params_dev, const int32_t *chan_off_s_host4, const int32_t *chan_off_next_host4,
+                               int global_batch, double gamma, int loss_sum, float *grads_dev, float *loss_out_dev,
+                               float *abs_err_out_dev, float *q_target_out_dev, float *m_dev, float *v_dev, float lr, float beta1,
+                               float beta2, float eps, float grad_scale, float beta1_power, float beta2_power, void *stream);
+
+
 /* ---- test hooks (host only, no device needed): the library's own physics / table / exact-pixel
  * code compiled for the host, so the CPU test-suite can pin it against the oracle. */
 int fb_debug_assets_load_host(const uint8_t *packed_host, size_t n);

@@ -187,3 +187,48 @@ def test_driver_loop_single_env_and_bad_model(mods):
     assert stats["updates"] == 12 - 6 and brain.timeStep == 12
     with pytest.raises(SystemExit):
         play.playFlappyBird("actorcritic")                         # outside the DQN hot path, like an unknown model (:51-54)
+
+
+@pytest.mark.parametrize("model", ["dqn", "ddqn", "duelingdqn"])
+def test_sampling_inside_the_step_is_identical_to_separate_launches(mods, model):
+    """fb_qnet_train_step_sampled: random.sample + gather as the first two kernels of the update's CUDA graph (their `t`
+    patched into the graph nodes every step) -- same minibatches, same parameters, same stream positions as
+    fb_replay_sample_uniform + fb_replay_gather + fb_qnet_train_step, while the replay fills, wraps and the graph replays"""
+    game, brains = mods
+    N = 48
+    runs = []
+    for fuse in (True, False):
+        brain = brains.MODELS[model](2, "bird", num_envs=N, replay_memory_per_env=10, batch_size=32, observe=3, seed=6, lr=1e-4)
+        brain.fuse_sampling = fuse
+        gs = game.GameState(num_envs=N, seed=2, history=14, ring=brain.ring)
+        obs, *_ = gs.frame_step(torch.zeros(N, dtype=torch.uint8, device="cuda"))
+        brain.setInitState(obs)
+        picked = []
+        for _ in range(30):
+            a = brain.getAction()
+            obs, r, t, s = gs.frame_step(a, out=brain.next_rows()[1:])
+            brain.setPerception(obs, a, r, t, s)
+            picked.append(brain.replayMemory._idx[:32].clone())
+        runs.append((brain, picked))
+    (b1, p1), (b0, p0) = runs
+    assert b1.net.adam_steps == b0.net.adam_steps == 30 - 4
+    for x, y in zip(p1[4:], p0[4:]):              # (no minibatch is drawn during the first OBSERVE + 1 steps)
+        assert torch.equal(x, y)
+    assert torch.equal(b1.net.params, b0.net.params) and torch.equal(b1.net.adam_v, b0.net.adam_v)
+    assert b1.replayMemory.rng_positions() == b0.replayMemory.rng_positions()
+    assert torch.equal(b1.net.loss, b0.net.loss)
+
+
+def test_sampling_inside_the_step_raises_like_random_sample(mods):
+    game, brains = mods
+    brain = brains.BrainDQNNature(2, "bird", num_envs=2, replay_memory_per_env=8, batch_size=32, observe=0)
+    gs = game.GameState(num_envs=2, seed=2, history=12, ring=brain.ring)
+    obs, *_ = gs.frame_step(torch.zeros(2, dtype=torch.uint8, device="cuda"))
+    brain.setInitState(obs)
+    a = brain.getAction()
+    obs, r, t, s = gs.frame_step(a)
+    brain.setPerception(obs, a, r, t, s)          # onlineTimeStep 0: no training yet
+    a = brain.getAction()
+    obs, r, t, s = gs.frame_step(a)
+    with pytest.raises(ValueError):               # 2 envs x 2 transitions < 32 (random.sample's ValueError, BrainDQN.py:197)
+        brain.setPerception(obs, a, r, t, s)
