@@ -61,7 +61,9 @@ class StepSampling(C.Structure):
     _fields_ = [("replay", C.c_void_p), ("ring_dev", C.c_void_p), ("act_dev", C.c_void_p), ("rew_dev", C.c_void_p), ("term_dev", C.c_void_p),
                 ("t", C.c_longlong), ("batch", C.c_int), ("setsize", C.c_uint32), ("seed", C.c_uint64), ("idx_out_dev", C.c_void_p),
                 ("frames_out_dev", C.c_void_p), ("act_out_dev", C.c_void_p), ("rew_out_dev", C.c_void_p), ("term_out_dev", C.c_void_p),
-                ("env_out_dev", C.c_void_p), ("k_out_dev", C.c_void_p)]
+                ("env_out_dev", C.c_void_p), ("k_out_dev", C.c_void_p),
+                ("prioritized", C.c_int), ("per_mode", C.c_int), ("beta", C.c_double), ("tree_idx_out_dev", C.c_void_p),
+                ("is_weights_out_dev", C.c_void_p), ("prio_out_dev", C.c_void_p), ("is_weights_f32_out_dev", C.c_void_p)]
 
 _SIGNATURES = {
     "fb_last_error": ([], C.c_char_p),

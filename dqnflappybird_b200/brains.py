@@ -231,7 +231,7 @@ class BrainDQN:
     def _update(self, variant: str):
         mem = self.replayMemory
         sampling = None
-        if self.world == 1 and not self.prioritized and self.fuse_sampling:
+        if self.world == 1 and self.fuse_sampling:
             sampling, mb = mem.step_sampling(self.local_batch)    # random.sample + gather ride at the head of the step's graph
         else:
             mb = mem.sample(self.local_batch)
@@ -245,8 +245,8 @@ class BrainDQN:
             if self.net.exchange is None:
                 torch.distributed.all_reduce(self.net.grads)      # sum of per-shard gradients of the global loss
             self.net.adam_step()                                  # with a peer exchange the sum happens inside the Adam kernel
-        if mb.tree_idx is not None:
-            mem.batch_update(mb.tree_idx, abs_errors=self._abs_err[:self.local_batch])   # :316
+        if mb.tree_idx is not None and sampling is None:
+            mem.batch_update(mb.tree_idx, abs_errors=self._abs_err[:self.local_batch])   # :316 (else: the last kernel of the step's graph)
         if self.record:                                              # BrainDQN.py:222-225, kept on the device until flushed
             if self._upd_n == self._upd_cap:
                 self.flush_logs()

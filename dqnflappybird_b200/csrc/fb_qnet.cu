@@ -586,17 +586,22 @@ extern "C" int fb_qnet_train_step_sampled(fb_qnet *n, const fb_step_sampling *sp
         FB_REQUIRE(variant == 0 || target_params_dev != nullptr, "fb_qnet_train_step_sampled: target parameters required");
         if (global_batch <= 0) global_batch = batch;
         FrameView fs = make_view(sp->frames_out_dev, 5 * 6400, chan_off_s), fn = make_view(sp->frames_out_dev, 5 * 6400, chan_off_next);
-        TcTrainArgs ta{variant, params_dev, target_params_dev, fs, fn, sp->act_out_dev, sp->rew_out_dev, sp->term_out_dev, nullptr, batch,
+        FB_REQUIRE(!sp->prioritized || abs_err_out_dev != nullptr, "fb_qnet_train_step_sampled: prioritized replay needs abs_err_out_dev");
+        TcTrainArgs ta{variant, params_dev, target_params_dev, fs, fn, sp->act_out_dev, sp->rew_out_dev, sp->term_out_dev,
+                       sp->prioritized ? sp->is_weights_f32_out_dev : nullptr, batch,
                        global_batch, gamma, loss_sum, grads_dev, loss_out_dev ? loss_out_dev : n->loss_dev, abs_err_out_dev,
                        q_target_out_dev, AdamFuse{1, m_dev, v_dev, lr, beta1, beta2, eps, grad_scale}, *sp};
         return tc_train_step(n, ta, beta1_power, beta2_power, (cudaStream_t)stream);
     }
+    FB_REQUIRE(!sp->prioritized || abs_err_out_dev != nullptr, "fb_qnet_train_step_sampled: prioritized replay needs abs_err_out_dev");
     int rc = replay_launch_sample_gather(*sp, (cudaStream_t)stream);
     if (rc) return rc;
-    return fb_qnet_train_step(n, variant, params_dev, target_params_dev, sp->frames_out_dev, 5 * 6400, chan_off_s, chan_off_next,
-                              sp->act_out_dev, sp->rew_out_dev, sp->term_out_dev, nullptr, batch, global_batch, gamma, loss_sum, grads_dev,
-                              loss_out_dev, abs_err_out_dev, q_target_out_dev, m_dev, v_dev, lr, beta1, beta2, eps, grad_scale, beta1_power,
-                              beta2_power, stream);
+    rc = fb_qnet_train_step(n, variant, params_dev, target_params_dev, sp->frames_out_dev, 5 * 6400, chan_off_s, chan_off_next,
+                            sp->act_out_dev, sp->rew_out_dev, sp->term_out_dev, sp->prioritized ? sp->is_weights_f32_out_dev : nullptr, batch,
+                            global_batch, gamma, loss_sum, grads_dev, loss_out_dev, abs_err_out_dev, q_target_out_dev, m_dev, v_dev, lr, beta1,
+                            beta2, eps, grad_scale, beta1_power, beta2_power, stream);
+    if (rc) return rc;
+    return sp->prioritized ? replay_launch_per_update(*sp, abs_err_out_dev, (cudaStream_t)stream) : FB_OK;
 }
 
 // target_replace_op (BrainDQNNature.py:107-111): hard copy of all variables

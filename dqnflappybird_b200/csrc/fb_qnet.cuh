@@ -85,7 +85,8 @@ struct TcTrainArgs {
 // fb_replay.cu: the two kernels of fb_replay_sample_uniform + fb_replay_gather on `st`; and the per-step patch of their
 // nodes in an instantiated graph (`t` is the only argument that changes)
 int replay_launch_sample_gather(const fb_step_sampling &p, cudaStream_t st);
-bool replay_is_sampler(const void *func);
+int replay_launch_per_update(const fb_step_sampling &p, const float *abs_err_dev, cudaStream_t st);     // Memory.batch_update, prioritized only
+bool replay_is_sampler(const void *func);        // sample_uniform_kernel or per_sample_kernel
 bool replay_is_gather(const void *func);
 int replay_patch_nodes(cudaGraphExec_t exec, cudaGraphNode_t sampler, cudaGraphNode_t gather, const fb_step_sampling &p);
 int tc_state_create(fb_qnet *n);

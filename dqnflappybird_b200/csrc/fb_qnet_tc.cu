@@ -1156,6 +1156,7 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     const int nb_fin = (n_compact + 31) / 32, nb_wf1 = a.ad.on ? (L.bf1 - L.wf1 + 1023) / 1024 : 0;
     AdamDev ad{a.ad.on, const_cast<float *>(a.params), a.ad.m, a.ad.v, a.ad.beta1, a.ad.beta2, a.ad.eps, a.ad.grad_scale, t->adam_pow + 2, nb_fin};
     FB_CUDA_OK(tc::launch_pdl(finalize_grads_kernel, dim3(nb_fin + nb_wf1), dim3(256), 0, st, fa, L, a.grads, ad, t->pw[0]));
+    if (a.pro.replay != nullptr && a.pro.prioritized) { rc = replay_launch_per_update(a.pro, a.abs_err, st); if (rc) return rc; }   // Memory.batch_update
     return FB_OK;
 }
 
@@ -1196,6 +1197,8 @@ int tc_loss_backward(fb_qnet *n, const TcTrainArgs &a, cudaStream_t st) {
         k.batch = q.batch; k.setsize = q.setsize; k.seed = q.seed; k.idx_out_dev = q.idx_out_dev; k.frames_out_dev = q.frames_out_dev;
         k.act_out_dev = q.act_out_dev; k.rew_out_dev = q.rew_out_dev; k.term_out_dev = q.term_out_dev; k.env_out_dev = q.env_out_dev;
         k.k_out_dev = q.k_out_dev;
+        k.prioritized = q.prioritized; k.per_mode = q.per_mode; k.tree_idx_out_dev = q.tree_idx_out_dev;       // (beta is patched like t)
+        k.is_weights_out_dev = q.is_weights_out_dev; k.prio_out_dev = q.prio_out_dev; k.is_weights_f32_out_dev = q.is_weights_f32_out_dev;
     }
     key.pack_online = n->packed_src[0] != a.params;
     key.pack_target = a.variant != 0 && n->packed_src[1] != a.target;

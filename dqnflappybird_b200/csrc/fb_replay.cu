@@ -378,6 +378,15 @@ extern "C" int fb_replay_gather(fb_replay *r, const uint8_t *ring_dev, const uin
     return FB_OK;
 }
 
+// leaf scan into r->minmax, which is armed ({0, ~0}) at create and re-armed by the scan's one consumer
+// (tree_update_kernel on the store path, per_sample_kernel on the sample path)
+static int refresh_minmax(fb_replay *r, cudaStream_t st) {
+    int blocks = (r->cap + 255) / 256; if (blocks > 592) blocks = 592;
+    leaf_minmax_kernel<<<blocks, 256, 0, st>>>(r->tree, r->cap, r->minmax);
+    FB_CUDA_OK(cudaGetLastError());
+    return FB_OK;
+}
+
 // ---- sampling + gather as the head of a captured training step (fb_qnet_train_step_sampled) -------------------------
 static bool sampling_population(const fb_step_sampling &p, uint32_t *n_out) {
     long long k_lo = p.t - p.replay->C + 1; if (k_lo < 1) k_lo = 1;
@@ -387,29 +396,57 @@ static bool sampling_population(const fb_step_sampling &p, uint32_t *n_out) {
 }
 static GatherArgs sampling_gather_args(const fb_step_sampling &p) {
     const fb_replay *r = p.replay;
-    return GatherArgs{p.ring_dev, r->N, r->L, p.act_dev, p.rew_dev, p.term_dev, p.t, r->C, 0, p.idx_out_dev, p.batch,
+    return GatherArgs{p.ring_dev, r->N, r->L, p.act_dev, p.rew_dev, p.term_dev, p.t, r->C, p.prioritized ? 1 : 0, p.idx_out_dev, p.batch,
                       p.frames_out_dev, p.act_out_dev, p.rew_out_dev, p.term_out_dev, p.env_out_dev, p.k_out_dev};
 }
 int replay_launch_sample_gather(const fb_step_sampling &p, cudaStream_t st) {
     FB_REQUIRE(p.replay && p.ring_dev && p.act_dev && p.rew_dev && p.term_dev && p.idx_out_dev && p.frames_out_dev && p.act_out_dev &&
-               p.rew_out_dev && p.term_out_dev && p.batch > 0 && p.batch <= 512 && p.setsize <= 2u * kHashSize, "step sampling: bad argument");
-    uint32_t n;
-    if (!sampling_population(p, &n)) { fb_set_error("Sample larger than population or is negative"); return FB_ERR_INVALID; }
-    sample_uniform_kernel<<<1, kSampThreads, 0, st>>>(n, p.batch, p.setsize, p.seed, p.replay->word_pos, p.idx_out_dev);
+               p.rew_out_dev && p.term_out_dev && p.batch > 0 && p.batch <= 512, "step sampling: bad argument");
+    fb_replay *r = p.replay;
+    if (p.prioritized) {
+        FB_REQUIRE(r->tree && p.tree_idx_out_dev && p.is_weights_out_dev && p.is_weights_f32_out_dev && (p.per_mode == 0 || p.per_mode == 1) &&
+                   p.batch <= r->scratch_n, "step sampling: prioritized replay arguments");
+        int rc = refresh_minmax(r, st); if (rc) return rc;
+        per_sample_kernel<<<1, ((p.batch + 31) / 32) * 32, 0, st>>>(r->tree, r->cap, p.batch, p.beta, r->minmax, p.seed, r->word_pos + 1,
+                                                                    p.tree_idx_out_dev, p.idx_out_dev, p.is_weights_out_dev, p.prio_out_dev,
+                                                                    p.is_weights_f32_out_dev);
+    } else {
+        FB_REQUIRE(p.setsize <= 2u * kHashSize, "step sampling: setsize too large");
+        uint32_t n;
+        if (!sampling_population(p, &n)) { fb_set_error("Sample larger than population or is negative"); return FB_ERR_INVALID; }
+        sample_uniform_kernel<<<1, kSampThreads, 0, st>>>(n, p.batch, p.setsize, p.seed, r->word_pos, p.idx_out_dev);
+    }
     gather_kernel<<<dim3(p.batch, 5), 128, 0, st>>>(sampling_gather_args(p));
     FB_CUDA_OK(cudaGetLastError());
     return FB_OK;
 }
-bool replay_is_sampler(const void *func) { return func == (const void *)sample_uniform_kernel; }
+int replay_launch_per_update(const fb_step_sampling &p, const float *abs_err_dev, cudaStream_t st) {
+    FB_REQUIRE(p.prioritized && abs_err_dev, "step sampling: Memory.batch_update needs the step's |TD errors| (abs_err_out_dev)");
+    fb_replay *r = p.replay;
+    tree_update_kernel<<<1, 1024, 0, st>>>(r->tree, r->cap, p.tree_idx_out_dev, nullptr, nullptr, p.batch, p.per_mode, r->change, abs_err_dev, r->prio);
+    FB_CUDA_OK(cudaGetLastError());
+    return FB_OK;
+}
+bool replay_is_sampler(const void *func) { return func == (const void *)sample_uniform_kernel || func == (const void *)per_sample_kernel; }
 bool replay_is_gather(const void *func) { return func == (const void *)gather_kernel; }
 int replay_patch_nodes(cudaGraphExec_t exec, cudaGraphNode_t sampler, cudaGraphNode_t gather, const fb_step_sampling &p) {
-    uint32_t n;
-    if (!sampling_population(p, &n)) { fb_set_error("Sample larger than population or is negative"); return FB_ERR_INVALID; }
-    int batch = p.batch; uint32_t setsize = p.setsize; uint64_t seed = p.seed; uint32_t *word_pos = p.replay->word_pos; int32_t *idx = p.idx_out_dev;
-    void *sargs[] = {&n, &batch, &setsize, &seed, &word_pos, &idx};
+    fb_replay *r = p.replay;
     cudaKernelNodeParams kp{};
-    kp.func = (void *)sample_uniform_kernel; kp.gridDim = dim3(1); kp.blockDim = dim3(kSampThreads); kp.sharedMemBytes = 0; kp.kernelParams = sargs;
-    FB_CUDA_OK(cudaGraphExecKernelNodeSetParams(exec, sampler, &kp));
+    int batch = p.batch; uint64_t seed = p.seed; int32_t *idx = p.idx_out_dev;
+    if (p.prioritized) {
+        const double *tree = r->tree; int cap = r->cap; double beta = p.beta; unsigned long long *minmax = r->minmax; uint32_t *word_pos = r->word_pos + 1;
+        int32_t *tree_idx = p.tree_idx_out_dev; double *isw = p.is_weights_out_dev, *prio = p.prio_out_dev; float *isw32 = p.is_weights_f32_out_dev;
+        void *sargs[] = {&tree, &cap, &batch, &beta, &minmax, &seed, &word_pos, &tree_idx, &idx, &isw, &prio, &isw32};
+        kp.func = (void *)per_sample_kernel; kp.gridDim = dim3(1); kp.blockDim = dim3(((p.batch + 31) / 32) * 32); kp.kernelParams = sargs;
+        FB_CUDA_OK(cudaGraphExecKernelNodeSetParams(exec, sampler, &kp));
+    } else {
+        uint32_t n;
+        if (!sampling_population(p, &n)) { fb_set_error("Sample larger than population or is negative"); return FB_ERR_INVALID; }
+        uint32_t setsize = p.setsize; uint32_t *word_pos = r->word_pos;
+        void *sargs[] = {&n, &batch, &setsize, &seed, &word_pos, &idx};
+        kp.func = (void *)sample_uniform_kernel; kp.gridDim = dim3(1); kp.blockDim = dim3(kSampThreads); kp.kernelParams = sargs;
+        FB_CUDA_OK(cudaGraphExecKernelNodeSetParams(exec, sampler, &kp));
+    }
     GatherArgs g = sampling_gather_args(p);
     void *gargs[] = {&g};
     kp.func = (void *)gather_kernel; kp.gridDim = dim3(p.batch, 5); kp.blockDim = dim3(128); kp.kernelParams = gargs;
@@ -417,14 +454,6 @@ int replay_patch_nodes(cudaGraphExec_t exec, cudaGraphNode_t sampler, cudaGraphN
     return FB_OK;
 }
 
-// leaf scan into r->minmax, which is armed ({0, ~0}) at create and re-armed by the scan's one consumer
-// (tree_update_kernel on the store path, per_sample_kernel on the sample path)
-static int refresh_minmax(fb_replay *r, cudaStream_t st) {
-    int blocks = (r->cap + 255) / 256; if (blocks > 592) blocks = 592;
-    leaf_minmax_kernel<<<blocks, 256, 0, st>>>(r->tree, r->cap, r->minmax);
-    FB_CUDA_OK(cudaGetLastError());
-    return FB_OK;
-}
 
 // Memory.store for transition k of every env (env order): priority = max leaf (1.0 if all zero)
 extern "C" int fb_per_store(fb_replay *r, long long k, int mode, void *stream) {

@@ -185,8 +185,9 @@ class QNetwork:
         ``sampling`` (``ReplayMemory.step_sampling(batch)[0]``): the minibatch is drawn and gathered by the step's first two
         kernels -- ``random.sample`` and the list comprehensions of BrainDQN.py:197-201 ride in the same graph; ``frames`` /
         ``actions`` / ``rewards`` / ``terminals`` must then be the replay's own minibatch buffers."""
-        if sampling is not None and self.exchange is None and is_weights is None:
+        if sampling is not None and self.exchange is None:
             assert frames.data_ptr() == sampling.frames_out_dev and frames.shape[0] == sampling.batch
+            assert (is_weights is None) == (not sampling.prioritized)
             off_s = (C.c_int32 * 4)(0, 6400, 12800, 19200)
             off_n = (C.c_int32 * 4)(6400, 12800, 19200, 25600)
             ptr = lambda t: t.data_ptr() if t is not None else None
@@ -202,6 +203,7 @@ class QNetwork:
             self.adam_steps += 1
             return self.loss
         if sampling is not None:                 # not fusable here: draw the minibatch with its own two launches
+            assert not sampling.prioritized, "with a peer exchange call PrioritizedMemory.sample / batch_update yourself"
             _lib.check(self._L.fb_replay_sample_uniform(sampling.replay, sampling.t, sampling.batch, sampling.setsize, sampling.seed,
                                                         sampling.idx_out_dev, self._stream()), "fb_replay_sample_uniform")
             _lib.check(self._L.fb_replay_gather(sampling.replay, sampling.ring_dev, sampling.act_dev, sampling.rew_dev, sampling.term_dev,

@@ -163,6 +163,19 @@ class PrioritizedMemory(ReplayMemory):
         mb.is_weights_f32 = self._isw32[:batch]
         return mb
 
+    def step_sampling(self, batch: int):
+        """``sample(batch)`` (and the ``batch_update`` that follows the update) as a descriptor: Memory.sample rides at the head
+        of ``QNetwork.train_step(..., sampling=...)``'s graph, Memory.batch_update at its tail"""
+        self.beta = min(1.0, self.beta + self.beta_increment_per_sampling)
+        sp = _lib.StepSampling(self._h.value, self.ring.data_ptr(), self.act.data_ptr(), self.rew.data_ptr(), self.term.data_ptr(), self.t,
+                               batch, 0, self.seed, self._idx.data_ptr(), self._frames.data_ptr(), self._a.data_ptr(),
+                               self._r.data_ptr(), self._t.data_ptr(), self._env.data_ptr(), self._k.data_ptr(),
+                               1, self._mode, self.beta, self._tree_idx.data_ptr(), self._isw.data_ptr(), self._prio.data_ptr(),
+                               self._isw32.data_ptr())
+        mb = self._minibatch(self._idx, batch)
+        mb.tree_idx, mb.is_weights, mb.is_weights_f32 = self._tree_idx[:batch], self._isw[:batch], self._isw32[:batch]
+        return sp, mb
+
     def batch_update(self, tree_idx: torch.Tensor, abs_errors: torch.Tensor | None = None, priorities: torch.Tensor | None = None):
         """Memory.batch_update(tree_idx, abs_errors) (:146-151)"""
         n = tree_idx.shape[0]

@@ -293,8 +293,16 @@ typedef struct fb_step_sampling {
     int32_t *idx_out_dev;
     uint8_t *frames_out_dev, *act_out_dev; float *rew_out_dev; uint8_t *term_out_dev;
     int32_t *env_out_dev, *k_out_dev;   /* optional */
+    /* prioritized != 0: Memory.sample (fb_per_sample with `beta`, which like `t` is patched per step) instead of
+     * random.sample, the loss weighted by is_weights_f32_out_dev, and Memory.batch_update (fb_per_update from the step's
+     * |TD errors|, abs_err_out_dev of the call is then required) as the graph's last kernel */
+    int prioritized, per_mode;
+    double beta;
+    int32_t *tree_idx_out_dev;
+    double *is_weights_out_dev, *prio_out_dev;
+    float *is_weights_f32_out_dev;
 } fb_step_sampling;
-/* fb_qnet_train_step with the minibatch drawn first (uniform replay).  FB_ERR_INVALID with "Sample larger than population
+/* fb_qnet_train_step with the minibatch drawn first (uniform or prioritized replay).  FB_ERR_INVALID with "Sample larger than population
  * or is negative" when the replay holds fewer than `batch` transitions (random.sample's ValueError). */
 int fb_qnet_train_step_sampled(fb_qnet *net, const fb_step_sampling *sampling, int variant, float *params_dev,
                                const float *target_params_dev, const int32_t *chan_off_s_host4, const int32_t *chan_off_next_host4,

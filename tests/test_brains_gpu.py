@@ -189,7 +189,7 @@ def test_driver_loop_single_env_and_bad_model(mods):
         play.playFlappyBird("actorcritic")                         # outside the DQN hot path, like an unknown model (:51-54)
 
 
-@pytest.mark.parametrize("model", ["dqn", "ddqn", "duelingdqn"])
+@pytest.mark.parametrize("model", ["dqn", "ddqn", "duelingdqn", "prioritydqn"])
 def test_sampling_inside_the_step_is_identical_to_separate_launches(mods, model):
     """fb_qnet_train_step_sampled: random.sample + gather as the first two kernels of the update's CUDA graph (their `t`
     patched into the graph nodes every step) -- same minibatches, same parameters, same stream positions as
@@ -217,6 +217,9 @@ def test_sampling_inside_the_step_is_identical_to_separate_launches(mods, model)
     assert torch.equal(b1.net.params, b0.net.params) and torch.equal(b1.net.adam_v, b0.net.adam_v)
     assert b1.replayMemory.rng_positions() == b0.replayMemory.rng_positions()
     assert torch.equal(b1.net.loss, b0.net.loss)
+    if model == "prioritydqn":                    # Memory.sample at the head, Memory.batch_update at the tail of the same graph
+        assert torch.equal(b1.replayMemory.tree(), b0.replayMemory.tree()) and b1.replayMemory.beta == b0.replayMemory.beta
+        assert torch.equal(b1.replayMemory._isw[:32], b0.replayMemory._isw[:32])
 
 
 def test_sampling_inside_the_step_raises_like_random_sample(mods):
