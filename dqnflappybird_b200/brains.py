@@ -231,7 +231,7 @@ class BrainDQN:
     def _update(self, variant: str):
         mem = self.replayMemory
         sampling = None
-        if self.world == 1 and self.fuse_sampling:
+        if self.fuse_sampling and (self.world == 1 or not self.prioritized):
             sampling, mb = mem.step_sampling(self.local_batch)    # random.sample + gather ride at the head of the step's graph
         else:
             mb = mem.sample(self.local_batch)
@@ -241,7 +241,7 @@ class BrainDQN:
         if self.world == 1:
             self.net.train_step(*args, sampling=sampling)         # one call: on the tensor-core path one CUDA graph, Adam included
         else:
-            self.net.loss_backward(*args)
+            self.net.loss_backward(*args, sampling=sampling)
             if self.net.exchange is None:
                 torch.distributed.all_reduce(self.net.grads)      # sum of per-shard gradients of the global loss
             self.net.adam_step()                                  # with a peer exchange the sum happens inside the Adam kernel

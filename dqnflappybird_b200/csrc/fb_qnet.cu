@@ -577,8 +577,9 @@ extern "C" int fb_qnet_train_step_sampled(fb_qnet *n, const fb_step_sampling *sp
                                           int global_batch, double gamma, int loss_sum, float *grads_dev, float *loss_out_dev,
                                           float *abs_err_out_dev, float *q_target_out_dev, float *m_dev, float *v_dev, float lr, float beta1,
                                           float beta2, float eps, float grad_scale, float beta1_power, float beta2_power, void *stream) {
-    FB_REQUIRE(n && sp && sp->replay && params_dev && m_dev && v_dev && grads_dev && chan_off_s && chan_off_next,
+    FB_REQUIRE(n && sp && sp->replay && params_dev && grads_dev && chan_off_s && chan_off_next && (m_dev != nullptr) == (v_dev != nullptr),
                "fb_qnet_train_step_sampled: NULL argument");
+    const bool adam = m_dev != nullptr;            // without Adam slots: gradients only (the caller applies Adam, e.g. fb_dist_adam)
     const int batch = sp->batch;
     if (n->precision == FB_PRECISION_BF16 && n->tc != nullptr) {
         FB_REQUIRE(batch > 0 && batch <= n->max_batch, "fb_qnet_train_step_sampled: batch exceeds max_batch");
@@ -590,12 +591,17 @@ extern "C" int fb_qnet_train_step_sampled(fb_qnet *n, const fb_step_sampling *sp
         TcTrainArgs ta{variant, params_dev, target_params_dev, fs, fn, sp->act_out_dev, sp->rew_out_dev, sp->term_out_dev,
                        sp->prioritized ? sp->is_weights_f32_out_dev : nullptr, batch,
                        global_batch, gamma, loss_sum, grads_dev, loss_out_dev ? loss_out_dev : n->loss_dev, abs_err_out_dev,
-                       q_target_out_dev, AdamFuse{1, m_dev, v_dev, lr, beta1, beta2, eps, grad_scale}, *sp};
-        return tc_train_step(n, ta, beta1_power, beta2_power, (cudaStream_t)stream);
+                       q_target_out_dev, AdamFuse{adam ? 1 : 0, m_dev, v_dev, lr, beta1, beta2, eps, grad_scale}, *sp};
+        return adam ? tc_train_step(n, ta, beta1_power, beta2_power, (cudaStream_t)stream) : tc_loss_backward(n, ta, (cudaStream_t)stream);
     }
     FB_REQUIRE(!sp->prioritized || abs_err_out_dev != nullptr, "fb_qnet_train_step_sampled: prioritized replay needs abs_err_out_dev");
     int rc = replay_launch_sample_gather(*sp, (cudaStream_t)stream);
     if (rc) return rc;
+    if (!adam)
+        rc = fb_qnet_loss_backward(n, variant, params_dev, target_params_dev, sp->frames_out_dev, 5 * 6400, chan_off_s, chan_off_next,
+                                   sp->act_out_dev, sp->rew_out_dev, sp->term_out_dev, sp->prioritized ? sp->is_weights_f32_out_dev : nullptr,
+                                   batch, global_batch, gamma, loss_sum, grads_dev, loss_out_dev, abs_err_out_dev, q_target_out_dev, stream);
+    else
     rc = fb_qnet_train_step(n, variant, params_dev, target_params_dev, sp->frames_out_dev, 5 * 6400, chan_off_s, chan_off_next,
                             sp->act_out_dev, sp->rew_out_dev, sp->term_out_dev, sp->prioritized ? sp->is_weights_f32_out_dev : nullptr, batch,
                             global_batch, gamma, loss_sum, grads_dev, loss_out_dev, abs_err_out_dev, q_target_out_dev, m_dev, v_dev, lr, beta1,

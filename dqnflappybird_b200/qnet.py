@@ -159,14 +159,22 @@ class QNetwork:
     def loss_backward(self, variant: str, frames: torch.Tensor, actions: torch.Tensor, rewards: torch.Tensor,
                       terminals: torch.Tensor, is_weights: torch.Tensor | None = None, gamma: float = 0.99,
                       loss_sum: bool = False, global_batch: int | None = None, abs_err: torch.Tensor | None = None,
-                      q_target: torch.Tensor | None = None) -> torch.Tensor:
-        """frames u8[B][5][80][80]: s = frames 0..3, s' = frames 1..4 of each sample.  Fills self.grads, self.loss."""
+                      q_target: torch.Tensor | None = None, sampling=None) -> torch.Tensor:
+        """frames u8[B][5][80][80]: s = frames 0..3, s' = frames 1..4 of each sample.  Fills self.grads, self.loss.
+        ``sampling``: as in train_step -- the minibatch is drawn by the first two kernels of the same graph."""
         B = frames.shape[0]
         assert frames.shape[1:] == (5, 80, 80) and frames.dtype == torch.uint8 and frames.is_contiguous()
         off_s = (C.c_int32 * 4)(0, 6400, 12800, 19200)
         off_n = (C.c_int32 * 4)(6400, 12800, 19200, 25600)
         ptr = lambda t: t.data_ptr() if t is not None else None
         self._sync_versions()
+        if sampling is not None:
+            assert frames.data_ptr() == sampling.frames_out_dev and B == sampling.batch and (is_weights is None) == (not sampling.prioritized)
+            _lib.check(self._L.fb_qnet_train_step_sampled(
+                self._h, C.addressof(sampling), VARIANTS[variant], self.params.data_ptr(), self.target.data_ptr(), off_s, off_n,
+                global_batch or B, float(gamma), int(loss_sum), self.grads.data_ptr(), self.loss.data_ptr(), ptr(abs_err), ptr(q_target),
+                None, None, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, self._stream()), "fb_qnet_train_step_sampled")
+            return self.loss
         _lib.check(self._L.fb_qnet_loss_backward(
             self._h, VARIANTS[variant], self.params.data_ptr(), self.target.data_ptr(), frames.data_ptr(), 5 * 6400,
             off_s, off_n, actions.data_ptr(), rewards.data_ptr(), terminals.data_ptr(), ptr(is_weights), B,

@@ -302,7 +302,8 @@ typedef struct fb_step_sampling {
     double *is_weights_out_dev, *prio_out_dev;
     float *is_weights_f32_out_dev;
 } fb_step_sampling;
-/* fb_qnet_train_step with the minibatch drawn first (uniform or prioritized replay).  FB_ERR_INVALID with "Sample larger than population
+/* fb_qnet_train_step with the minibatch drawn first (uniform or prioritized replay).  m_dev == v_dev == NULL: gradients only
+ * (fb_qnet_loss_backward with the minibatch drawn first; the caller applies Adam, e.g. through fb_dist_adam).  FB_ERR_INVALID with "Sample larger than population
  * or is negative" when the replay holds fewer than `batch` transitions (random.sample's ValueError). */
 int fb_qnet_train_step_sampled(fb_qnet *net, const fb_step_sampling *sampling, int variant, float *params_dev,
                                const float *target_params_dev, const int32_t *chan_off_s_host4, const int32_t *chan_off_next_host4,
