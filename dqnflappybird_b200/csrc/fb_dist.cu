@@ -19,6 +19,7 @@
 #include <new>
 
 #include "fb_qnet.cuh"
+#include "fb_pack.cuh"
 
 constexpr int kMaxRanks = 8;
 
@@ -67,7 +68,7 @@ __device__ __forceinline__ float4 ld_peer(const float *p) {          // never se
     return v;
 }
 
-__device__ __forceinline__ float adam_one(float &p, float g, float &m, float &v, float alpha, float beta1, float beta2, float eps) {
+__device__ __forceinline__ float adam_x(float &p, float g, float &m, float &v, float alpha, float beta1, float beta2, float eps) {
     m += (g - m) * (1.f - beta1);            // TF 1.12 ApplyAdam functor, as adam_kernel in fb_qnet.cu
     v += (g * g - v) * (1.f - beta2);
     p -= (m * alpha) / (sqrtf(v) + eps);
@@ -76,7 +77,8 @@ __device__ __forceinline__ float adam_one(float &p, float g, float &m, float &v,
 
 __global__ void __launch_bounds__(256) adam_xreduce_kernel(float *__restrict__ params, float *__restrict__ am, float *__restrict__ av, size_t n,
                                                            const XArgs x, float alpha, float beta1, float beta2, float eps, float grad_scale,
-                                                           float *__restrict__ reduced_out) {
+                                                           float *__restrict__ reduced_out, int repack, const QnetLayout L,
+                                                           const PackedWeights pw) {
     if (x.wait) {
         if (blockIdx.x == 0 && (int)threadIdx.x < x.world) {
             __threadfence_system();
@@ -129,9 +131,13 @@ __global__ void __launch_bounds__(256) adam_xreduce_kernel(float *__restrict__ p
         }
         g.x *= grad_scale; g.y *= grad_scale; g.z *= grad_scale; g.w *= grad_scale;
         float4 p = reinterpret_cast<float4 *>(params)[i], m = reinterpret_cast<float4 *>(am)[i], v = reinterpret_cast<float4 *>(av)[i];
-        adam_one(p.x, g.x, m.x, v.x, alpha, beta1, beta2, eps); adam_one(p.y, g.y, m.y, v.y, alpha, beta1, beta2, eps);
-        adam_one(p.z, g.z, m.z, v.z, alpha, beta1, beta2, eps); adam_one(p.w, g.w, m.w, v.w, alpha, beta1, beta2, eps);
+        adam_x(p.x, g.x, m.x, v.x, alpha, beta1, beta2, eps); adam_x(p.y, g.y, m.y, v.y, alpha, beta1, beta2, eps);
+        adam_x(p.z, g.z, m.z, v.z, alpha, beta1, beta2, eps); adam_x(p.w, g.w, m.w, v.w, alpha, beta1, beta2, eps);
         reinterpret_cast<float4 *>(params)[i] = p; reinterpret_cast<float4 *>(am)[i] = m; reinterpret_cast<float4 *>(av)[i] = v;
+        if (repack) {                         // tensor-core path: the bf16 operand copies of what was just updated
+            const int e = (int)(4 * i);
+            scatter_packed(e, p.x, L, pw, 0); scatter_packed(e + 1, p.y, L, pw, 0); scatter_packed(e + 2, p.z, L, pw, 0); scatter_packed(e + 3, p.w, L, pw, 0);
+        }
         if (reduced_out) reinterpret_cast<float4 *>(reduced_out)[i] = g;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
@@ -139,7 +145,8 @@ __global__ void __launch_bounds__(256) adam_xreduce_kernel(float *__restrict__ p
             float g = 0.f;
             for (int q = 0; q < x.world; q++) g += __ldcv(x.g[q] + i);
             g *= grad_scale;
-            adam_one(params[i], g, am[i], av[i], alpha, beta1, beta2, eps);
+            adam_x(params[i], g, am[i], av[i], alpha, beta1, beta2, eps);
+            if (repack) scatter_packed((int)i, params[i], L, pw, 0);
             if (reduced_out) reduced_out[i] = g;
         }
 }
@@ -247,9 +254,13 @@ extern "C" int fb_dist_adam(fb_dist *d, fb_qnet *net, float *params_dev, float *
     x.two_shot = d->two_shot && d->world > 1 && wait;
     x.slice4 = ((d->n >> 2) + d->world - 1) / d->world;
     if (x.two_shot) x.ts_step = ++d->ts_steps;
-    adam_xreduce_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(params_dev, m_dev, v_dev, d->n, x, alpha, beta1, beta2, eps, grad_scale, reduced_out_dev);
+    PackedWeights pw{};
+    const int repack = tc_online_operands(net, &pw) ? 1 : 0;
+    adam_xreduce_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(params_dev, m_dev, v_dev, d->n, x, alpha, beta1, beta2, eps, grad_scale, reduced_out_dev,
+                                                               repack, net->L, pw);
     FB_CUDA_OK(cudaGetLastError());
     d->step++;
     for (int s = 0; s < 2; s++) if (net->packed_src[s] == params_dev) net->packed_src[s] = nullptr;
+    if (repack) net->packed_src[0] = params_dev;          // slot 0 mirrors the updated vector: the next step needs no pack kernel
     return FB_OK;
 }

@@ -29,10 +29,10 @@
 #include <vector>
 
 #include "fb_qnet.cuh"
+#include "fb_pack.cuh"
 #include "fb_tc.cuh"
 #include "fb_tc_conv.cuh"
 
-using bf16 = __nv_bfloat16;
 
 namespace {
 
@@ -406,35 +406,6 @@ __global__ void unpool_relu_kernel_tc(const bf16 *z1, const bf16 *dp2, int B, bf
     }
 }
 
-// fp32 parameters -> bf16 operand matrices in the K orders the GEMMs use (see the tables in make_plan)
-struct PackedWeights {
-    bf16 *w1p;      // [32][256]   n, (tap, r, s, c)            conv1 forward  Bt
-    bf16 *w2p;      // [64][512]   n, (tap, r, s, c)            conv2 forward  Bt
-    bf16 *w3p;      // [64][576]   n, (kh, kw, c)               conv3 forward  Bt
-    bf16 *wf1n;     // [1600][H]   k, n   (as stored)           fc1 forward B (MN-major) and fc1 dgrad Bt
-    bf16 *w3d;      // [64][576]   c, (kh, kw, o)               conv3 dgrad    Bt
-    bf16 *w2d;      // [128][256]  (r, s, c), (tap, o)          conv2 dgrad    Bt
-};
-// parameter i (TF variable order) -> its bf16 operand copies
-__device__ __forceinline__ void scatter_packed(int i, float val, const QnetLayout &L, const PackedWeights &pw, int fwd_only) {
-    const bf16 v = __float2bfloat16(val);
-    if (i < L.b1) {                         // W1 [kh][kw][c][n]
-        int e = i - L.w1, n = e & 31, c = (e >> 5) & 3, kw = (e >> 7) & 7, kh = e >> 10;
-        int k = ((kh >> 2) * 2 + (kw >> 2)) * 64 + (kh & 3) * 16 + (kw & 3) * 4 + c;
-        pw.w1p[n * kK1 + k] = v;
-    } else if (i >= L.w2 && i < L.b2) {     // W2 [kh][kw][c][o]
-        int e = i - L.w2, o = e & 63, c = (e >> 6) & 31, kw = (e >> 11) & 3, kh = e >> 13;
-        int t = (kh >> 1) * 2 + (kw >> 1), j = (kh & 1) * 64 + (kw & 1) * 32 + c;
-        pw.w2p[o * kK2 + t * 128 + j] = v;
-        if (!fwd_only) pw.w2d[j * 256 + t * 64 + o] = v;
-    } else if (i >= L.w3 && i < L.b3) {     // W3 [t][c][o]
-        int e = i - L.w3, o = e & 63, c = (e >> 6) & 63, t = e >> 12;
-        pw.w3p[o * kK3 + t * 64 + c] = v;
-        if (!fwd_only) pw.w3d[c * kK3 + t * 64 + o] = v;
-    } else if (i >= L.wf1 && i < L.bf1) {   // W_fc1 [k][n]: same index
-        pw.wf1n[i - L.wf1] = v;
-    }
-}
 __global__ void pack_weights_kernel(const float *params, QnetLayout L, PackedWeights pw, int fwd_only) {
     tc::pdl_wait();
     tc::pdl_launch();
@@ -992,6 +963,12 @@ int tc_pack_weights(fb_qnet *n, const float *params_dev, int slot, cudaStream_t 
     FB_REQUIRE(n->tc != nullptr && (slot == 0 || slot == 1), "tc_pack_weights: bad argument");
     FB_CUDA_OK(tc::launch_pdl(pack_weights_kernel, dim3(592), dim3(256), 0, st, params_dev, n->L, n->tc->pw[slot], slot == 1 ? 1 : 0));
     return FB_OK;
+}
+
+bool tc_online_operands(fb_qnet *n, PackedWeights *out) {
+    if (!n || n->precision != FB_PRECISION_BF16 || !n->tc) return false;
+    *out = n->tc->pw[0];
+    return true;
 }
 
 int tc_adam(fb_qnet *n, float *params_dev, const float *grads_dev, float *m_dev, float *v_dev, float alpha, float beta1, float beta2,

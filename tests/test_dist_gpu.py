@@ -60,3 +60,32 @@ def test_peer_exchange_across_processes():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "PEER_EXCHANGE_OK" in r.stdout
+
+
+def test_exchange_adam_refreshes_the_bf16_operand_copies(mods):
+    """tensor-core path: the exchange + Adam kernel rewrites the bf16 copies of every parameter it updates, so the next step
+    starts without a pack kernel -- Q-values after it equal those of a net whose copies were rebuilt from the same weights"""
+    dist, qnet = mods
+    from dqnflappybird_b200 import game
+    nets = [qnet.QNetwork(max_batch=16, seed=3, precision="bf16") for _ in range(2)]
+    xs = [dist.PeerGradExchange(nets[0].n_params, "cuda:0", rank=r, world=2, connect=False) for r in range(2)]
+    xs[0].connect_local(1, xs[1]); xs[1].connect_local(0, xs[0])
+    for r in range(2):
+        xs[r].no_wait = True
+        nets[r].enable_peer_exchange(xs[r])
+        nets[r].lr = np.float32(1e-3)
+    gs = game.GameState(num_envs=16, seed=5, history=6)
+    gs.step_random(20, 0.4, 3)
+    fb = qnet.FrameBatch.from_ring(gs.ring, gs.slot)
+    q0 = nets[0].forward(fb).clone()                               # packs the operand copies of the initial weights
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for step in range(3):
+        for r in range(2):
+            nets[r].grads.copy_(torch.randn(nets[r].n_params, device="cuda", generator=g))
+        for r in range(2):
+            nets[r].adam_step()
+    q1 = nets[0].forward(fb)
+    fresh = qnet.QNetwork(max_batch=16, seed=9, precision="bf16")
+    fresh.params.copy_(nets[0].params)
+    assert not torch.equal(q1, q0)
+    assert torch.equal(q1, fresh.forward(fb))
