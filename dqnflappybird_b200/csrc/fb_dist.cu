@@ -117,28 +117,46 @@ __global__ void __launch_bounds__(256) adam_xreduce_kernel(float *__restrict__ p
         }
         __syncthreads();
     }
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-        float4 g;
-        if (x.two_shot) {
-            const int q = (int)(i / x.slice4);
-            g = ld_peer(x.red[q] + 4 * (i - (size_t)q * x.slice4));
-        } else {
-            g = ld_peer(x.g[0] + 4 * i);
-            for (int q = 1; q < x.world; q++) {
-                float4 h = ld_peer(x.g[q] + 4 * i);
-                g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
+    // every remote load of a thread is issued before the first Adam update (the vector is ~3 float4 per thread: three
+    // dependent NVLink round trips otherwise)
+    constexpr int U = 4;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t base = (size_t)blockIdx.x * blockDim.x + threadIdx.x; base < n4; base += U * stride) {
+        float4 gs[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const size_t i = base + u * stride;
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < n4) {
+                if (x.two_shot) {
+                    const int q = (int)(i / x.slice4);
+                    g = ld_peer(x.red[q] + 4 * (i - (size_t)q * x.slice4));
+                } else {
+                    g = ld_peer(x.g[0] + 4 * i);
+                    for (int q = 1; q < x.world; q++) {
+                        float4 h = ld_peer(x.g[q] + 4 * i);
+                        g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
+                    }
+                }
             }
+            gs[u] = g;
         }
-        g.x *= grad_scale; g.y *= grad_scale; g.z *= grad_scale; g.w *= grad_scale;
-        float4 p = reinterpret_cast<float4 *>(params)[i], m = reinterpret_cast<float4 *>(am)[i], v = reinterpret_cast<float4 *>(av)[i];
-        adam_x(p.x, g.x, m.x, v.x, alpha, beta1, beta2, eps); adam_x(p.y, g.y, m.y, v.y, alpha, beta1, beta2, eps);
-        adam_x(p.z, g.z, m.z, v.z, alpha, beta1, beta2, eps); adam_x(p.w, g.w, m.w, v.w, alpha, beta1, beta2, eps);
-        reinterpret_cast<float4 *>(params)[i] = p; reinterpret_cast<float4 *>(am)[i] = m; reinterpret_cast<float4 *>(av)[i] = v;
-        if (repack) {                         // tensor-core path: the bf16 operand copies of what was just updated
-            const int e = (int)(4 * i);
-            scatter_packed(e, p.x, L, pw, 0); scatter_packed(e + 1, p.y, L, pw, 0); scatter_packed(e + 2, p.z, L, pw, 0); scatter_packed(e + 3, p.w, L, pw, 0);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const size_t i = base + u * stride;
+            if (i >= n4) break;
+            float4 g = gs[u];
+            g.x *= grad_scale; g.y *= grad_scale; g.z *= grad_scale; g.w *= grad_scale;
+            float4 p = reinterpret_cast<float4 *>(params)[i], m = reinterpret_cast<float4 *>(am)[i], v = reinterpret_cast<float4 *>(av)[i];
+            adam_x(p.x, g.x, m.x, v.x, alpha, beta1, beta2, eps); adam_x(p.y, g.y, m.y, v.y, alpha, beta1, beta2, eps);
+            adam_x(p.z, g.z, m.z, v.z, alpha, beta1, beta2, eps); adam_x(p.w, g.w, m.w, v.w, alpha, beta1, beta2, eps);
+            reinterpret_cast<float4 *>(params)[i] = p; reinterpret_cast<float4 *>(am)[i] = m; reinterpret_cast<float4 *>(av)[i] = v;
+            if (repack) {                         // tensor-core path: the bf16 operand copies of what was just updated
+                const int e = (int)(4 * i);
+                scatter_packed(e, p.x, L, pw, 0); scatter_packed(e + 1, p.y, L, pw, 0); scatter_packed(e + 2, p.z, L, pw, 0); scatter_packed(e + 3, p.w, L, pw, 0);
+            }
+            if (reduced_out) reinterpret_cast<float4 *>(reduced_out)[i] = g;
         }
-        if (reduced_out) reinterpret_cast<float4 *>(reduced_out)[i] = g;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
         for (size_t i = n4 * 4; i < n; i++) {                        // tail (n % 4 parameters)
