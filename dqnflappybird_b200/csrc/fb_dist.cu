@@ -38,6 +38,7 @@ struct fb_dist {
     void *opened[4 * kMaxRanks];
     int n_opened;
     uint32_t step;
+    unsigned long long *stamps;              // debug: %globaltimer at the phase boundaries of the last exchange (block 0)
 };
 
 namespace {
@@ -52,6 +53,7 @@ struct XArgs {
     int rank, world, wait, two_shot;
     size_t slice4;                           // float4s per slice (two-shot)
     uint32_t step, ts_step;                  // exchange number; number of two-shot exchanges including this one
+    unsigned long long *stamps;              // optional phase time stamps
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
@@ -68,6 +70,13 @@ __device__ __forceinline__ float4 ld_peer(const float *p) {          // never se
     return v;
 }
 
+__device__ __forceinline__ void stamp(const XArgs &x, int k) {
+    if (x.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        x.stamps[k] = t;
+    }
+}
 __device__ __forceinline__ float adam_x(float &p, float g, float &m, float &v, float alpha, float beta1, float beta2, float eps) {
     m += (g - m) * (1.f - beta1);            // TF 1.12 ApplyAdam functor, as adam_kernel in fb_qnet.cu
     v += (g * g - v) * (1.f - beta2);
@@ -79,6 +88,7 @@ __global__ void __launch_bounds__(256) adam_xreduce_kernel(float *__restrict__ p
                                                            const XArgs x, float alpha, float beta1, float beta2, float eps, float grad_scale,
                                                            float *__restrict__ reduced_out, int repack, const QnetLayout L,
                                                            const PackedWeights pw) {
+    stamp(x, 0);
     if (x.wait) {
         if (blockIdx.x == 0 && (int)threadIdx.x < x.world) {
             __threadfence_system();
@@ -91,6 +101,7 @@ __global__ void __launch_bounds__(256) adam_xreduce_kernel(float *__restrict__ p
         }
         __syncthreads();
     }
+    stamp(x, 1);
     const size_t n4 = n >> 2;
     if (x.two_shot) {
         // shot 1: this rank's slice, summed over the ranks in rank order
@@ -103,13 +114,21 @@ __global__ void __launch_bounds__(256) adam_xreduce_kernel(float *__restrict__ p
             }
             reinterpret_cast<float4 *>(x.my_red)[i - lo] = g;
         }
+        stamp(x, 2);
         // grid barrier (every CTA of this grid is resident: 2 per SM), then publish the slice and wait for everyone's
-        __threadfence_system();
+        // Measured on 8 GPUs: one thread publishing to the eight peers in a loop cost ~4 us per system-scope release store, so the
+        // last peer saw the slice ~30 us after the first and the skew carried into the next step; now one thread per peer.
+        // One system-scope fence per CTA, by the thread that then arrives at the grid barrier: it follows the CTA barrier, so it
+        // is cumulative over the slice stores of the CTA's other threads (a fence in every thread cost ~10 us here).
+        __shared__ int s_last;
         __syncthreads();
         if (threadIdx.x == 0) {
-            if (atomicAdd(x.grid_count, 1u) + 1u == gridDim.x * x.ts_step)       // the last CTA of this grid
-                for (int q = 0; q < x.world; q++) st_release_sys(x.peer_flags[q] + 32 + x.rank, x.step);
+            __threadfence_system();
+            s_last = atomicAdd(x.grid_count, 1u) + 1u == gridDim.x * x.ts_step;  // the last CTA of this grid
+            __threadfence_system();
         }
+        __syncthreads();
+        if (s_last && (int)threadIdx.x < x.world) st_release_sys(x.peer_flags[threadIdx.x] + 32 + x.rank, x.step);
         if ((int)threadIdx.x < x.world) {
             uint32_t spins = 0;
             while ((int32_t)(ld_acquire_sys(x.my_flags + 32 + threadIdx.x) - x.step) < 0)
@@ -117,6 +136,7 @@ __global__ void __launch_bounds__(256) adam_xreduce_kernel(float *__restrict__ p
         }
         __syncthreads();
     }
+    stamp(x, 3);
     // every remote load of a thread is issued before the first Adam update (the vector is ~3 float4 per thread: three
     // dependent NVLink round trips otherwise)
     constexpr int U = 4;
@@ -158,6 +178,7 @@ __global__ void __launch_bounds__(256) adam_xreduce_kernel(float *__restrict__ p
             if (reduced_out) reinterpret_cast<float4 *>(reduced_out)[i] = g;
         }
     }
+    stamp(x, 4);
     if (blockIdx.x == 0 && threadIdx.x == 0)
         for (size_t i = n4 * 4; i < n; i++) {                        // tail (n % 4 parameters)
             float g = 0.f;
@@ -184,6 +205,7 @@ extern "C" int fb_dist_create(int rank, int world, long long n_floats, fb_dist *
     FB_CUDA_OK(cudaMemset(d->red, 0, bytes));
     FB_CUDA_OK(cudaMalloc(&d->grid_count, 256));
     FB_CUDA_OK(cudaMemset(d->grid_count, 0, 256));
+    d->stamps = nullptr;
     d->two_shot = world >= 4; d->ts_steps = 0;
     for (int q = 0; q < kMaxRanks; q++) { d->peer_grads[0][q] = d->peer_grads[1][q] = nullptr; d->peer_flags[q] = nullptr; d->peer_red[q] = nullptr; }
     d->peer_grads[0][rank] = d->xgrads[0]; d->peer_grads[1][rank] = d->xgrads[1]; d->peer_flags[rank] = d->flags; d->peer_red[rank] = d->red;
@@ -194,7 +216,7 @@ extern "C" int fb_dist_create(int rank, int world, long long n_floats, fb_dist *
 extern "C" int fb_dist_destroy(fb_dist *d) {
     if (!d) return FB_OK;
     for (int k = 0; k < d->n_opened; k++) cudaIpcCloseMemHandle(d->opened[k]);
-    cudaFree(d->xgrads[0]); cudaFree(d->xgrads[1]); cudaFree(d->flags); cudaFree(d->red); cudaFree(d->grid_count);
+    cudaFree(d->xgrads[0]); cudaFree(d->xgrads[1]); cudaFree(d->flags); cudaFree(d->red); cudaFree(d->grid_count); cudaFree(d->stamps);
     delete d;
     return FB_OK;
 }
@@ -253,6 +275,19 @@ extern "C" int fb_dist_grads(fb_dist *d, int parity, float **out) {
 }
 extern "C" int fb_dist_parity(const fb_dist *d) { return d ? (int)(d->step & 1) : -1; }
 
+// debug: nanosecond %globaltimer stamps of block 0 at the phase boundaries of the most recent exchange (start, peers'
+// gradients published, own slice reduced, slices published, Adam done); the first call switches the stamping on
+extern "C" int fb_dist_debug_stamps(fb_dist *d, unsigned long long *out_host5) {
+    FB_REQUIRE(d != nullptr && out_host5 != nullptr, "fb_dist_debug_stamps: NULL argument");
+    if (!d->stamps) {
+        FB_CUDA_OK(cudaMalloc(&d->stamps, 8 * sizeof(unsigned long long)));
+        FB_CUDA_OK(cudaMemset(d->stamps, 0, 8 * sizeof(unsigned long long)));
+    }
+    FB_CUDA_OK(cudaDeviceSynchronize());
+    FB_CUDA_OK(cudaMemcpy(out_host5, d->stamps, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return FB_OK;
+}
+
 // One optimizer step over the SUM of all ranks' gradients (exchange buffer of the current parity).  wait = 0 skips the
 // publish / wait handshake (single-process tests whose "ranks" run one after the other on one GPU).
 extern "C" int fb_dist_adam(fb_dist *d, fb_qnet *net, float *params_dev, float *m_dev, float *v_dev, float alpha, float beta1, float beta2,
@@ -266,7 +301,7 @@ extern "C" int fb_dist_adam(fb_dist *d, fb_qnet *net, float *params_dev, float *
         x.g[q] = d->peer_grads[par][q]; x.peer_flags[q] = d->peer_flags[q]; x.red[q] = d->peer_red[q];
     }
     x.my_flags = d->flags; x.rank = d->rank; x.world = d->world; x.wait = wait; x.step = d->step + 1;
-    x.my_red = d->red; x.grid_count = d->grid_count;
+    x.my_red = d->red; x.grid_count = d->grid_count; x.stamps = d->stamps;
     // two-shot needs every rank's slice before anyone reads it: without the cross-rank handshake (single-process test,
     // ranks run one after the other) only the one-shot form is meaningful
     x.two_shot = d->two_shot && d->world > 1 && wait;

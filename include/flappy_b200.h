@@ -233,6 +233,9 @@ int fb_dist_grads(fb_dist *d, int parity, float **out_dev_ptr);
 int fb_dist_parity(const fb_dist *d);
 int fb_dist_adam(fb_dist *d, fb_qnet *net, float *params_dev, float *m_dev, float *v_dev, float alpha, float beta1, float beta2,
                  float eps, float grad_scale, float *reduced_out_dev /* may be NULL */, int wait, void *stream);
+/* debug: %globaltimer (ns) of the last exchange's phase boundaries on this rank: start, all gradients published, own slice
+ * reduced, all slices published, Adam done.  The first call switches the stamping on. */
+int fb_dist_debug_stamps(fb_dist *d, unsigned long long *out_host5);
 
 /* ---- replay memory: the deque + random.sample of BrainDQN.py:69-72,197-201 and the SumTree / Memory of
  * BrainPrioritizedReplyDQN.py:32-151, over the env's own frame ring (no frame is copied on append).
