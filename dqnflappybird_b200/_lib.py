@@ -108,6 +108,7 @@ _SIGNATURES = {
                                     _f32p, _f32p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp], C.c_int),
     "fb_qnet_adam": ([_vp, _f32p, _f32p, _f32p, _f32p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp], C.c_int),
     "fb_qnet_sync_target": ([_vp, _f32p, _f32p, _vp], C.c_int),
+    "fb_debug_step_sampling_layout": ([_i32p, C.c_int], C.c_int),
     "fb_dist_debug_stamps": ([_vp, _vp], C.c_int),
     "fb_dist_create": ([C.c_int, C.c_int, C.c_longlong, C.POINTER(C.c_void_p)], C.c_int),
     "fb_dist_destroy": ([_vp], C.c_int),

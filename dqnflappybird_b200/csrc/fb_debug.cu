@@ -2,6 +2,7 @@
 // (fb_env_logic.cuh is __host__ __device__) on the CPU, so the CPU-only test-suite can check
 // the derived tables and the step logic against the oracle without a GPU.  Not used by the
 // product path.
+#include <stddef.h>
 #include <string.h>
 
 #include "fb_env_logic.cuh"
@@ -66,4 +67,26 @@ extern "C" int fb_debug_host_mixed(const int32_t *state16) {
     memset(&s, 0, sizeof(s));
     if (!ints_to_state(state16, s)) return -1;
     return (make_draw_list(s).np_mixed & 16) ? 1 : 0;
+}
+
+// layout of fb_step_sampling as this library was compiled: sizeof, then the byte offset of every field in declaration
+// order -- the CPU test-suite checks the ctypes mirror (dqnflappybird_b200/_lib.py StepSampling) against it
+extern "C" int fb_debug_step_sampling_layout(int32_t *out, int capacity) {
+    const int32_t v[] = {(int32_t)sizeof(fb_step_sampling),
+                         (int32_t)offsetof(fb_step_sampling, replay), (int32_t)offsetof(fb_step_sampling, ring_dev),
+                         (int32_t)offsetof(fb_step_sampling, act_dev), (int32_t)offsetof(fb_step_sampling, rew_dev),
+                         (int32_t)offsetof(fb_step_sampling, term_dev), (int32_t)offsetof(fb_step_sampling, t),
+                         (int32_t)offsetof(fb_step_sampling, batch), (int32_t)offsetof(fb_step_sampling, setsize),
+                         (int32_t)offsetof(fb_step_sampling, seed), (int32_t)offsetof(fb_step_sampling, idx_out_dev),
+                         (int32_t)offsetof(fb_step_sampling, frames_out_dev), (int32_t)offsetof(fb_step_sampling, act_out_dev),
+                         (int32_t)offsetof(fb_step_sampling, rew_out_dev), (int32_t)offsetof(fb_step_sampling, term_out_dev),
+                         (int32_t)offsetof(fb_step_sampling, env_out_dev), (int32_t)offsetof(fb_step_sampling, k_out_dev),
+                         (int32_t)offsetof(fb_step_sampling, prioritized), (int32_t)offsetof(fb_step_sampling, per_mode),
+                         (int32_t)offsetof(fb_step_sampling, beta), (int32_t)offsetof(fb_step_sampling, tree_idx_out_dev),
+                         (int32_t)offsetof(fb_step_sampling, is_weights_out_dev), (int32_t)offsetof(fb_step_sampling, prio_out_dev),
+                         (int32_t)offsetof(fb_step_sampling, is_weights_f32_out_dev)};
+    const int n = (int)(sizeof(v) / sizeof(v[0]));
+    FB_REQUIRE(out != nullptr && capacity >= n, "fb_debug_step_sampling_layout: buffer too small");
+    for (int i = 0; i < n; i++) out[i] = v[i];
+    return n;
 }

@@ -318,6 +318,8 @@ int fb_qnet_train_step_sampled(fb_qnet *net, const fb_step_sampling *sampling, i
 /* ---- test hooks (host only, no device needed): the library's own physics / table / exact-pixel
  * code compiled for the host, so the CPU test-suite can pin it against the oracle. */
 int fb_debug_assets_load_host(const uint8_t *packed_host, size_t n);
+/* sizeof(fb_step_sampling) followed by the byte offset of each field, in declaration order; returns the count written */
+int fb_debug_step_sampling_layout(int32_t *out, int capacity);
 int fb_debug_host_reset(int32_t *state16, const uint8_t *gaps, int gaps_len, uint64_t seed, uint64_t env_id);
 int fb_debug_host_step(int32_t *state16, int action, const uint8_t *gaps, int gaps_len, uint64_t seed,
                        uint64_t env_id, float *reward, uint8_t *terminal, int32_t *score);

@@ -156,3 +156,16 @@ def test_invalid_action_is_rejected(L):
     r, t, s = C.c_float(), C.c_uint8(), C.c_int32()
     assert L.fb_debug_host_step(st.ctypes.data, 2, None, 0, 0, 0, C.byref(r), C.byref(t), C.byref(s)) == -4
     assert b"Multiple input actions" in L.fb_last_error()
+
+
+def test_step_sampling_struct_matches_the_c_layout():
+    """the ctypes mirror of fb_step_sampling (the descriptor handed to fb_qnet_train_step_sampled) against the compiled struct"""
+    import ctypes as C
+    from dqnflappybird_b200 import _lib
+    out = (C.c_int32 * 32)()
+    n = _lib.lib().fb_debug_step_sampling_layout(out, 32)
+    fields = _lib.StepSampling._fields_
+    assert n == 1 + len(fields)
+    assert out[0] == C.sizeof(_lib.StepSampling)
+    for k, (name, _) in enumerate(fields):
+        assert out[1 + k] == getattr(_lib.StepSampling, name).offset, name
