@@ -105,7 +105,6 @@ class BrainDQN:
         self._q = torch.zeros((N, 2), dtype=torch.float32, device=self.device)
         self._abs_err = torch.zeros(max(self.local_batch, 8), dtype=torch.float32, device=self.device)
         self._q_target = torch.zeros(max(self.local_batch, 8), dtype=torch.float32, device=self.device)
-        self._isw32 = torch.zeros(max(self.local_batch, 8), dtype=torch.float32, device=self.device)
         self._game_times = torch.zeros((), dtype=torch.int64, device=self.device)
         # logs (BrainDQN.py:44-58).  With record=True they are fed from device-side accumulators (no host sync on the
         # step path) and reach these lists / the reference's five text files when flushed.
