@@ -67,3 +67,13 @@ def test_word_stream_random_is_cpython_random():
         assert R.random() == ref.random()
         assert R.randrange(2) == ref.randrange(2)
     assert ro.cpython_setsize(32) == 277 and ro.cpython_setsize(256) == 1045 and ro.cpython_setsize(512) == 4117
+
+
+def test_product_setsize_equals_cpythons_expression():
+    """random.sample's set / list switch (21 + 4**ceil(log(3k, 4)) for k > 5, CPython's float expression): the product's
+    host helper, the oracle's and the interpreter's own must agree for every minibatch size the library accepts"""
+    from math import ceil, log
+    from dqnflappybird_b200 import replay
+    for k in range(1, 513):
+        want = 21 + (4 ** ceil(log(k * 3, 4)) if k > 5 else 0)
+        assert replay.cpython_setsize(k) == ro.cpython_setsize(k) == want, k
