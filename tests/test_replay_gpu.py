@@ -27,6 +27,7 @@ def mods():
     (16, 68, 64, 1000, 32),
     (64, 68, 64, 5000, 256),          # n = 4096, set branch, many duplicates / out-of-range words
     (3, 40, 36, 17, 5),               # tiny batch: setsize 21
+    (16384, 64, 60, 5000, 256),       # BASELINE configs[2]: 16,384 envs x 60 transitions = 983,040, minibatch 256
 ])
 def test_uniform_sample_indices_match_cpython(mods, N, L, C, t, batch):
     game, replay = mods
@@ -148,3 +149,49 @@ def test_prioritized_rollout_gather(mods):
     mb = mem.sample(16)
     assert mb.tree_idx.min().item() >= 4 * 20 - 1
     _check_minibatch(mb, hf, ha, hr, ht)
+
+
+def test_full_size_sumtree_properties(mods):
+    """BASELINE configs[2] size -- 16,384 envs x 60 transitions = 983,040 leaves -- through size-independent properties:
+    after stores that fill and wrap the memory and prioritized updates, every inner node is exactly left + right (rebuild
+    mode), the root is the sum of the leaves, sampled leaves lie in their strata, and the IS weights follow
+    (p / min_p)^-beta (BrainPrioritizedReplyDQN.py:127-144) to 1e-12."""
+    game, replay = mods
+    N, C, B = 16384, 60, 256
+    ring = torch.zeros((N, C + 4, 80, 80), dtype=torch.uint8, device="cuda")
+    mem = replay.PrioritizedMemory(ring, C, seed=5, max_batch=B)
+    cap = N * C
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for k in range(1, C + 25):
+        mem.appended(k)
+        if k % 3 == 0:
+            mb = mem.sample(B)
+            tree = mem.tree()
+            total, leaves = tree[0].item(), tree[cap - 1:]
+            li = mb.tree_idx.long()
+            assert int(li.min()) >= cap - 1 and int(li.max()) <= 2 * cap - 2
+            # stratified: the prefix sum just before leaf i is <= (i + 1) * total / B and the one after it >= i * total / B
+            # leaves from left to right: the deepest level first (tree indices 2^D - 1 .. 2 cap - 2), then the rest of the
+            # level above it (cap - 1 .. 2^D - 2) -- the capacity is not a power of two (BrainPrioritizedReplyDQN.py:39-47)
+            D = (2 * cap - 1).bit_length() - 1
+            order = torch.cat([torch.arange(2 ** D - 1, 2 * cap - 1, device="cuda"), torch.arange(cap - 1, 2 ** D - 1, device="cuda")])
+            csum = torch.cumsum(tree[order], 0)
+            pos = torch.empty(2 * cap - 1, dtype=torch.long, device="cuda")
+            pos[order] = torch.arange(cap, device="cuda")
+            d = li - (cap - 1)
+            hi = csum[pos[li]]
+            lo = hi - tree[li]
+            seg = total / B
+            i = torch.arange(B, device="cuda", dtype=torch.float64)
+            assert bool((lo <= (i + 1) * seg * (1 + 1e-9)).all()) and bool((hi >= i * seg * (1 - 1e-9)).all())
+            min_p = leaves[leaves > 0].min()
+            want_w = (leaves[d] / min_p) ** (-mem.beta)
+            torch.testing.assert_close(mb.is_weights, want_w, rtol=1e-12, atol=0)
+            assert float(mb.is_weights.max()) <= 1.0 + 1e-12
+            err = torch.rand(B, device="cuda", generator=g) * 2.0
+            mem.batch_update(mb.tree_idx, abs_errors=err)
+    tree = mem.tree()
+    inner = torch.arange(cap - 1, device="cuda")
+    assert torch.equal(tree[inner], tree[2 * inner + 1] + tree[2 * inner + 2])       # exact: parents are recomputed, never drifted
+    torch.testing.assert_close(tree[0], tree[cap - 1:].sum(), rtol=1e-9, atol=0)
+    assert int((tree[cap - 1:] > 0).sum()) == cap                                     # the memory wrapped: every leaf was stored
