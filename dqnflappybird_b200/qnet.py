@@ -15,6 +15,9 @@ import torch
 from . import _lib
 
 VARIANTS = {"vanilla": 0, "nature": 1, "double": 2}
+# byte offsets of the four frames of s and of s' inside one minibatch sample u8[5][80][80]
+_OFF_S = (C.c_int32 * 4)(0, 6400, 12800, 19200)
+_OFF_N = (C.c_int32 * 4)(6400, 12800, 19200, 25600)
 PRECISIONS = {"fp32": 0, "bf16": 1}
 
 
@@ -164,8 +167,7 @@ class QNetwork:
         ``sampling``: as in train_step -- the minibatch is drawn by the first two kernels of the same graph."""
         B = frames.shape[0]
         assert frames.shape[1:] == (5, 80, 80) and frames.dtype == torch.uint8 and frames.is_contiguous()
-        off_s = (C.c_int32 * 4)(0, 6400, 12800, 19200)
-        off_n = (C.c_int32 * 4)(6400, 12800, 19200, 25600)
+        off_s, off_n = _OFF_S, _OFF_N
         ptr = lambda t: t.data_ptr() if t is not None else None
         self._sync_versions()
         if sampling is not None:
@@ -196,8 +198,7 @@ class QNetwork:
         if sampling is not None and self.exchange is None:
             assert frames.data_ptr() == sampling.frames_out_dev and frames.shape[0] == sampling.batch
             assert (is_weights is None) == (not sampling.prioritized)
-            off_s = (C.c_int32 * 4)(0, 6400, 12800, 19200)
-            off_n = (C.c_int32 * 4)(6400, 12800, 19200, 25600)
+            off_s, off_n = _OFF_S, _OFF_N
             ptr = lambda t: t.data_ptr() if t is not None else None
             self._sync_versions()
             _lib.check(self._L.fb_qnet_train_step_sampled(
@@ -206,9 +207,7 @@ class QNetwork:
                 ptr(q_target), self.adam_m.data_ptr(), self.adam_v.data_ptr(), float(self.lr), float(self.beta1), float(self.beta2),
                 float(self.adam_eps), float(grad_scale), float(self.beta1_power), float(self.beta2_power), self._stream()),
                 "fb_qnet_train_step_sampled")
-            self.beta1_power = np.float32(self.beta1_power * self.beta1)
-            self.beta2_power = np.float32(self.beta2_power * self.beta2)
-            self.adam_steps += 1
+            self._advance_powers()
             return self.loss
         if sampling is not None:                 # not fusable here: draw the minibatch with its own two launches
             assert not sampling.prioritized, "with a peer exchange call PrioritizedMemory.sample / batch_update yourself"
@@ -224,8 +223,7 @@ class QNetwork:
             return self.loss
         B = frames.shape[0]
         assert frames.shape[1:] == (5, 80, 80) and frames.dtype == torch.uint8 and frames.is_contiguous()
-        off_s = (C.c_int32 * 4)(0, 6400, 12800, 19200)
-        off_n = (C.c_int32 * 4)(6400, 12800, 19200, 25600)
+        off_s, off_n = _OFF_S, _OFF_N
         ptr = lambda t: t.data_ptr() if t is not None else None
         self._sync_versions()
         _lib.check(self._L.fb_qnet_train_step(
@@ -235,10 +233,14 @@ class QNetwork:
             ptr(q_target), self.adam_m.data_ptr(), self.adam_v.data_ptr(), float(self.lr), float(self.beta1), float(self.beta2),
             float(self.adam_eps), float(grad_scale), float(self.beta1_power), float(self.beta2_power), self._stream()),
             "fb_qnet_train_step")
+        self._advance_powers()
+        return self.loss
+
+    def _advance_powers(self):
+        """beta1_power *= beta1, beta2_power *= beta2 in fp32, like the update ops TF-1's Adam runs after every step"""
         self.beta1_power = np.float32(self.beta1_power * self.beta1)
         self.beta2_power = np.float32(self.beta2_power * self.beta2)
         self.adam_steps += 1
-        return self.loss
 
     def adam_step(self, grad_scale: float = 1.0):
         """One tf.train.AdamOptimizer step on self.params with self.grads (TF-1 ApplyAdam)."""
@@ -251,9 +253,7 @@ class QNetwork:
             _lib.check(self._L.fb_qnet_adam(self._h, self.params.data_ptr(), self.grads.data_ptr(), self.adam_m.data_ptr(),
                                             self.adam_v.data_ptr(), float(alpha), float(self.beta1), float(self.beta2),
                                             float(self.adam_eps), float(grad_scale), self._stream()), "fb_qnet_adam")
-        self.beta1_power = np.float32(self.beta1_power * self.beta1)
-        self.beta2_power = np.float32(self.beta2_power * self.beta2)
-        self.adam_steps += 1
+        self._advance_powers()
 
     def sync_target(self):
         """sess.run(target_replace_op) (BrainDQNNature.py:107-111,151-152)."""
