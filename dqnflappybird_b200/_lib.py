@@ -38,16 +38,35 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu under csrc/ into libflappy_b200.so for sm_100a."""
+    """Compile every .cu under csrc/ for sm_100a (one nvcc per file, in parallel; objects under csrc/build/, rebuilt only
+    when the source or a header is newer) and link them into libflappy_b200.so."""
     if not force and not needs_build():
         return SO_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH] + sources() + ["-lcuda"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise FlappyError("nvcc failed:\n" + r.stdout + r.stderr)
+    objdir = os.path.join(_CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+    headers = glob.glob(os.path.join(_CSRC, "*.cuh")) + glob.glob(os.path.join(_PKG, "..", "include", "*.h"))
+    hdr_t = max(os.path.getmtime(h) for h in headers)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
+            return obj, ""
+        cmd = [nvcc] + compile_flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise FlappyError(f"nvcc failed on {os.path.basename(src)}:\n" + r.stdout + r.stderr)
+        return obj, r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        results = list(ex.map(one, sources()))
     if verbose:
-        print(r.stderr)
+        print("".join(log for _, log in results))
+    r = subprocess.run([nvcc, "-shared", "-o", SO_PATH] + [o for o, _ in results] + ["-lcuda"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise FlappyError("link failed:\n" + r.stdout + r.stderr)
     return SO_PATH
 
 
@@ -93,6 +112,8 @@ _SIGNATURES = {
     "fb_qnet_set_precision": ([_vp, C.c_int], C.c_int),
     "fb_qnet_get_precision": ([_vp], C.c_int),
     "fb_qnet_invalidate": ([_vp], C.c_int),
+    "fb_qnet_set_per_broadcast": ([_vp, C.c_int], C.c_int),
+    "fb_debug_poison_packed": ([_vp, C.c_int, _vp], C.c_int),
     "fb_qnet_use_graphs": ([_vp, C.c_int], C.c_int),
     "fb_qnet_set_conv1_mode": ([_vp, C.c_int], C.c_int),
     "fb_qnet_param_count": ([_vp], C.c_int),

@@ -76,7 +76,9 @@ class BrainDQN:
         self.seed, self.first_env_id = seed, first_env_id
         # distributed: one process per GPU, replicated learner
         self.world = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
-        self.local_batch = max(1, batch_size // self.world)
+        from .dist import local_batch as _local_batch
+        self.local_batch = _local_batch(batch_size, self.world)     # raises unless the minibatch divides evenly over the ranks
+        self.rank = torch.distributed.get_rank() if self.world > 1 else 0
         # init replay memory (BrainDQN.py:35): REPLAY_MEMORY transitions per env, frames shared with the env's ring
         C = replay_memory_per_env if replay_memory_per_env is not None else (REPLAY_MEMORY if N == 1 else 60)
         L = C + 4
@@ -94,6 +96,10 @@ class BrainDQN:
         dueling = self.dueling and not (reference_quirks and type(self).__name__ == "BrainDuelingDQN")
         self.net = QNetwork(self.device, hidden=hidden, dueling=dueling, max_batch=max(self.local_batch, min(N, max_act_batch)),
                             seed=seed, lr=lr, copy_target_at_init=copy_target_at_init, precision=precision)
+        if self.prioritized and reference_quirks:
+            # what the shipped graph really minimises: ISWeights [B,1] x square(...) [B] broadcasts to [B,B], so every sample is
+            # weighted by mean(ISWeights) (BrainPrioritizedReplyDQN.py:243-251); the default is the intended per-sample weight
+            self.net.set_per_broadcast(True)
         # one process per GPU under NCCL: sum the gradients from NVLink peer memory inside the Adam kernel (fb_dist.cu)
         if peer_exchange is None:
             peer_exchange = self.world > 1 and torch.distributed.get_backend() == "nccl"
@@ -331,6 +337,16 @@ class BrainDQN:
         <game>-saved-parameters.txt exactly like the reference writes them, then the logs"""
         if self.save_path is None:
             raise RuntimeError("no root_dir: the brain was built without a place to put saved_parameters/<model>/")
+        if self.world > 1:
+            # replicas are bit-identical: rank 0 alone writes (concurrent writers would corrupt the files); the others
+            # only flush their device-side logs and meet rank 0 at the barrier
+            if self.rank != 0:
+                self.flush_logs()
+                for lst in (self.lost_hist, self.q_target_list, self.score_every_episode, self.time_steps_when_episode_end,
+                            self.reward_every_time_step, self.episode_envs):
+                    del lst[:]
+                torch.distributed.barrier()
+                return
         name = f"{self.gameName}-{self.timeStep}"
         torch.save(self.net.state_dict(), self.save_path + name + ".pt")
         with open(self.save_path + "checkpoint", "w") as f:
@@ -341,6 +357,8 @@ class BrainDQN:
             pickle.dump(self.epsilon, f)
         if self.record:
             self._save_loss_score_timestep_reward_qtarget_to_file()
+        if self.world > 1:
+            torch.distributed.barrier()
 
     def _load_saved_parameters(self) -> bool:
         """BrainDQN.py:176-192: restore the newest checkpoint if there is one; timeStep and epsilon come back,

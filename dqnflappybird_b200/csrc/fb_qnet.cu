@@ -227,9 +227,16 @@ __global__ void head_forward_kernel(const float *h1, const float *params, QnetLa
 __global__ void td_loss_kernel(const float *q_s, const float *q_next, const float *q_next_online, const uint8_t *actions,
                                const float *rewards, const uint8_t *terminals, const float *isw, int B, int global_batch,
                                int variant, double gamma, int loss_sum, float *dq, float *loss_out, float *abs_err,
-                               float *q_target) {
+                               float *q_target, int isw_mean) {
     __shared__ float red[32];
+    __shared__ float wmean_s;
     float local = 0.f;
+    // isw_mean: ISWeights is a [B,1] placeholder multiplied with a [B] vector (BrainPrioritizedReplyDQN.py:243-251): TensorFlow
+    // broadcasts to [B,B], so the cost the reference minimises is mean(w) * mean(err^2) -- every sample weighted by mean(w)
+    if (isw && isw_mean) {
+        if (threadIdx.x == 0) { float s = 0.f; for (int b = 0; b < B; b++) s += isw[b]; wmean_s = s / (float)B; }
+        __syncthreads();
+    }
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         float x;
         if (variant == 2) { int am = q_next_online[b * 2 + 1] > q_next_online[b * 2] ? 1 : 0; x = q_next[b * 2 + am]; }
@@ -240,7 +247,7 @@ __global__ void td_loss_kernel(const float *q_s, const float *q_next, const floa
         int a = actions[b] ? 1 : 0;
         float qa = q_s[b * 2 + a];
         float err = y - qa;
-        float w = isw ? isw[b] : 1.f;
+        float w = isw ? (isw_mean ? wmean_s : isw[b]) : 1.f;
         float scale = loss_sum ? 1.f : 1.f / (float)global_batch;
         local += w * err * err * scale;
         float g = -2.f * w * err * scale;
@@ -299,7 +306,7 @@ void qnet_launch_td_loss(const float *q_s, const float *q_next, const float *q_n
                          const float *rewards, const uint8_t *terminals, const float *isw, int B, int global_batch, int variant,
                          double gamma, int loss_sum, float *dq, float *loss_out, float *abs_err, float *q_target, cudaStream_t st) {
     td_loss_kernel<<<1, 256, 0, st>>>(q_s, q_next, q_next_online, actions, rewards, terminals, isw, B, global_batch, variant, gamma,
-                                       loss_sum, dq, loss_out, abs_err, q_target);
+                                       loss_sum, dq, loss_out, abs_err, q_target, 0);
 }
 void qnet_launch_head_backward(const float *h1, const float *dq, const float *params, const QnetLayout &L, int B, float *grads,
                                float *dh1_f32, __nv_bfloat16 *dh1_bf16, cudaStream_t st) {
@@ -385,6 +392,7 @@ extern "C" int fb_qnet_create(int hidden, int dueling, int max_batch, fb_qnet **
     n->max_batch = max_batch;
     n->precision = FB_PRECISION_FP32;
     n->tc = nullptr;
+    n->per_broadcast = 0;
     size_t B = (size_t)max_batch;
     auto alloc = [](float **p, size_t floats) { return cudaMalloc(p, floats * sizeof(float)); };
     FB_CUDA_OK(alloc(&n->z1, B * 12800)); FB_CUDA_OK(alloc(&n->p1, B * 3200)); FB_CUDA_OK(alloc(&n->a2, B * 1600));
@@ -422,6 +430,15 @@ extern "C" int fb_qnet_set_precision(fb_qnet *n, int precision) {
 }
 
 extern "C" int fb_qnet_get_precision(const fb_qnet *n) { return n ? n->precision : -1; }
+
+// PER loss as the reference's graph computes it (BrainPrioritizedReplyDQN.py:243-251): ISWeights [B,1] * square(...) [B] is
+// broadcast to [B,B] by TensorFlow, so reduce_mean gives mean(w) * mean(err^2) and every sample's gradient is scaled by
+// mean(w) instead of its own w.  Off (default): the intended mean(w_i err_i^2).
+extern "C" int fb_qnet_set_per_broadcast(fb_qnet *n, int on) {
+    FB_REQUIRE(n != nullptr, "fb_qnet_set_per_broadcast: NULL argument");
+    n->per_broadcast = on ? 1 : 0;
+    return tc_drop_graphs(n);
+}
 
 // The bf16 operand copies of a parameter vector are remade when the vector may have changed: after fb_qnet_adam /
 // fb_qnet_sync_target on it, or when the caller says so (it wrote the tensor itself).
@@ -507,7 +524,7 @@ extern "C" int fb_qnet_loss_backward(fb_qnet *n, int variant, const float *param
     rc = forward_chunk(n, params_dev, fs, B, n->q, st); if (rc) return rc;
     td_loss_kernel<<<1, 256, 0, st>>>(n->q, n->q_next, n->q_next_online, actions_dev, rewards_dev, terminals_dev, is_weights_dev,
                                        B, global_batch, variant, gamma, loss_sum, n->dq, loss_out_dev ? loss_out_dev : n->loss_dev,
-                                       abs_err_out_dev, q_target_out_dev);
+                                       abs_err_out_dev, q_target_out_dev, n->per_broadcast);
     // ---- backward
     head_backward_w_kernel<<<(L.hidden + 1 + 127) / 128, 128, 0, st>>>(n->h1, n->dq, L, B, grads_dev);
     head_backward_h_kernel<<<(B * L.hidden + 255) / 256, 256, 0, st>>>(n->h1, n->dq, params_dev, L, B, n->dh1, nullptr);

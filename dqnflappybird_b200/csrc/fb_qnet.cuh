@@ -57,6 +57,7 @@ struct fb_qnet {
     float *partial; size_t partial_floats;
     float *loss_dev;
     TcState *tc;
+    int per_broadcast;            // PER loss as the reference's graph really computes it: every sample weighted by mean(ISWeights)
     const float *packed_src[2];   // parameter vectors the bf16 operand copies (slot 0 online, 1 target) were made from
 };
 
@@ -90,6 +91,7 @@ bool replay_is_sampler(const void *func);        // sample_uniform_kernel or per
 bool replay_is_gather(const void *func);
 int replay_patch_nodes(cudaGraphExec_t exec, cudaGraphNode_t sampler, cudaGraphNode_t gather, const fb_step_sampling &p);
 int tc_state_create(fb_qnet *n);
+int tc_drop_graphs(fb_qnet *n);                 // captured steps embed the net's settings: drop them when one changes
 void tc_state_destroy(fb_qnet *n);
 int tc_pack_weights(fb_qnet *n, const float *params_dev, int slot /* 0 online, 1 target */, cudaStream_t st);
 int tc_slot_for(fb_qnet *n, const float *params_dev, int want_slot, cudaStream_t st, int *slot_out);

@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
 }
 
 template <int BN>
-constexpr size_t gemm_smem_bytes() { return (size_t)kStages * (128 * 64 * 2 + BN * 64 * 2) + 1024; }
+constexpr size_t gemm_smem_bytes() { return exclusive_smem((size_t)kStages * (128 * 64 * 2 + BN * 64 * 2) + 1024); }
 
 template <int BN, int MODE, class EP>
 static cudaError_t launch_tc_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const GemmParams &g, dim3 grid, EP ep, cudaStream_t st) {
@@ -406,22 +406,29 @@ __global__ void unpool_relu_kernel_tc(const bf16 *z1, const bf16 *dp2, int B, bf
     }
 }
 
+// This kernel WRITES the operand copies that its stream successor (a conv kernel) fetches by TMA in its prologue, i.e.
+// BEFORE that kernel's griddepcontrol.wait: it must not release its dependents early.  No launch_dependents here -- the
+// implicit trigger at grid completion applies, so the successor starts only when every packed weight is in memory
+// (tests/test_qnet_tc_gpu.py::test_pack_then_forward_never_reads_stale_operands).
 __global__ void pack_weights_kernel(const float *params, QnetLayout L, PackedWeights pw, int fwd_only) {
     tc::pdl_wait();
-    tc::pdl_launch();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.bf1; i += gridDim.x * blockDim.x) scatter_packed(i, params[i], L, pw, fwd_only);
 }
 
 // tf.train.AdamOptimizer step (TF 1.12 ApplyAdam, as adam_kernel in fb_qnet.cu) that also refreshes the bf16 operand
 // copies of the parameters it has just written, so the next training step starts without a pack kernel
-__device__ __forceinline__ void adam_one(int i, float g, float *__restrict__ p, float *__restrict__ m, float *__restrict__ v, float alpha,
-                                         float beta1, float beta2, float eps, float grad_scale, const QnetLayout &L, const PackedWeights &pw) {
+__device__ __forceinline__ float adam_math(float g, float pi, float &mi, float &vi, float alpha, float beta1, float beta2, float eps,
+                                           float grad_scale) {
     float gi = g * grad_scale;
-    float mi = m[i], vi = v[i];
     mi += (gi - mi) * (1.f - beta1);
     vi += (gi * gi - vi) * (1.f - beta2);
+    return pi - (mi * alpha) / (sqrtf(vi) + eps);
+}
+__device__ __forceinline__ void adam_one(int i, float g, float *__restrict__ p, float *__restrict__ m, float *__restrict__ v, float alpha,
+                                         float beta1, float beta2, float eps, float grad_scale, const QnetLayout &L, const PackedWeights &pw) {
+    float mi = m[i], vi = v[i];
+    float pi = adam_math(g, p[i], mi, vi, alpha, beta1, beta2, eps, grad_scale);
     m[i] = mi; v[i] = vi;
-    float pi = p[i] - (mi * alpha) / (sqrtf(vi) + eps);
     p[i] = pi;
     scatter_packed(i, pi, L, pw, 0);
 }
@@ -479,6 +486,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(ColsumJobs jobs) {
 // weights, dh1 = dQ W^T masked by relu (bf16, the operand of the fc1 gradient GEMMs) and the fc1 bias gradient
 // sum_b dh1.  Block = 32 hidden units x 8 row lanes; block gridDim.x-1 does the head bias.
 constexpr int kHeadRows = 256;                      // rows of the minibatch per head-backward CTA row group
+constexpr int kMaxHeadCtas = 160;                   // fused head kernel: at most one CTA (four samples at a time) per SM
 // Fused Adam (fb_qnet_train_step): one thread of this kernel -- early on the step's critical path, exactly once per step --
 // turns the beta powers kept in device memory into this step's alpha = lr sqrt(1 - beta2^t) / (1 - beta1^t) (fp32, the
 // host formula) and advances them; the step's last kernel reads alpha.  Nothing about a step is a launch argument.
@@ -546,7 +554,7 @@ __global__ void __launch_bounds__(256) head_backward_tc_kernel(const float *__re
 // The TD target / loss of sample b needs only Q(s)[b] and Q(s')[b] (td_loss_kernel in fb_qnet.cu): when `td.on` the CTA that has
 // just produced Q(s)[b] also writes dLoss/dQ[b], |error|, y and the sample's loss term (summed later in a fixed order).
 struct TdFuse {
-    int on, variant, loss_sum, global_batch;
+    int on, variant, loss_sum, global_batch, isw_mean;
     double gamma;
     const float *q_next, *q_next_online, *rewards, *isw;
     const uint8_t *actions, *terminals;
@@ -591,7 +599,8 @@ __global__ void __launch_bounds__(128) fc1_head_kernel(const float *__restrict__
             const float y = (float)(td.terminals[b] ? r : r + td.gamma * (double)x);
             const int a = td.actions[b] ? 1 : 0;
             const float err = y - q[b * 2 + a];
-            const float w = td.isw ? td.isw[b] : 1.f;
+            float w = td.isw ? td.isw[b] : 1.f;
+            if (td.isw && td.isw_mean) { w = 0.f; for (int k = 0; k < B; k++) w += td.isw[k]; w /= (float)B; }    // [B,1] x [B] broadcast (see TdFuse)
             const float scale = td.loss_sum ? 1.f : 1.f / (float)td.global_batch;
             td.dq[b * 2 + a] = -2.f * w * err * scale; td.dq[b * 2 + (1 - a)] = 0.f;
             td.loss_terms[b] = w * err * err * scale;
@@ -599,6 +608,166 @@ __global__ void __launch_bounds__(128) fc1_head_kernel(const float *__restrict__
             if (td.q_target) td.q_target[b] = y;
         }
     }
+}
+
+// The plain head (acting, Q(s')) in the same warp-per-sample form: fc1 split-K finish + bias + ReLU + the head dot products,
+// reductions by shuffles.  Measured at minibatch 256: 5 us against 10 us for the CTA-per-sample fc1_head_kernel.
+template <int JPL>
+__global__ void __launch_bounds__(128) fc1_head_warp_kernel(const float *__restrict__ part, int splits, size_t split_stride,
+                                                           const float *__restrict__ params, QnetLayout L, int B, float *__restrict__ h1,
+                                                           float *__restrict__ q) {
+    tc::pdl_wait();
+    tc::pdl_launch();
+    constexpr int H = 32 * JPL;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float w0[JPL], w1[JPL], wv[JPL], bias[JPL];
+#pragma unroll
+    for (int u = 0; u < JPL; u++) {
+        const int j = lane + 32 * u;
+        bias[u] = params[L.bf1 + j];
+        if (!L.dueling) { w0[u] = params[L.wf2 + j * 2]; w1[u] = params[L.wf2 + j * 2 + 1]; wv[u] = 0.f; }
+        else { w0[u] = params[L.wa + j * 2]; w1[u] = params[L.wa + j * 2 + 1]; wv[u] = params[L.wv + j]; }
+    }
+    const float b_q0 = L.dueling ? params[L.ba] : params[L.bf2], b_q1 = L.dueling ? params[L.ba + 1] : params[L.bf2 + 1];
+    const float b_v = L.dueling ? params[L.bv] : 0.f;
+    const int nwarps = gridDim.x * 4;
+    for (int b = blockIdx.x * 4 + warp; b < B; b += nwarps) {
+        float x[JPL];
+        float s0 = 0.f, s1 = 0.f, sv = 0.f;
+#pragma unroll
+        for (int u = 0; u < JPL; u++) x[u] = bias[u];
+        for (int z = 0; z < splits; z++) {
+            const float *pz = part + (size_t)z * split_stride + (size_t)b * H + lane;
+#pragma unroll
+            for (int u = 0; u < JPL; u++) x[u] += pz[32 * u];
+        }
+#pragma unroll
+        for (int u = 0; u < JPL; u++) {
+            x[u] = fmaxf(x[u], 0.f);
+            if (h1 != nullptr) h1[(size_t)b * H + lane + 32 * u] = x[u];
+            s0 = fmaf(x[u], w0[u], s0); s1 = fmaf(x[u], w1[u], s1); sv = fmaf(x[u], wv[u], sv);
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) { s0 += __shfl_xor_sync(~0u, s0, off); s1 += __shfl_xor_sync(~0u, s1, off); sv += __shfl_xor_sync(~0u, sv, off); }
+        if (lane == 0) {
+            if (!L.dueling) { q[b * 2] = s0 + b_q0; q[b * 2 + 1] = s1 + b_q1; }
+            else { const float a0 = s0 + b_q0, a1 = s1 + b_q1, v = sv + b_v, mean = (a0 + a1) * 0.5f; q[b * 2] = v + (a0 - mean); q[b * 2 + 1] = v + (a1 - mean); }
+        }
+    }
+}
+
+// The training step's head in ONE kernel (hidden = 32 JPL): fc1 split-K finish + bias + ReLU, the Q head, the TD target /
+// loss / dLoss/dQ, and the head's backward pass -- dh1 = dQ W^T masked by relu (bf16, the operand of the fc1 gradient GEMMs),
+// the head weight gradients and the fc1 bias gradient -- for which h1 never leaves the registers.  One WARP per sample
+// (lane = hidden units lane + 32 u): the sample's reductions are shuffles, no block barrier sits between Q(s) and its
+// gradient; the per-CTA partial sums [G][H][4], [G][4] are what finalize_grads_kernel adds in a fixed order.  Also carries the
+// fused-Adam alpha (AdamPow, as head_backward_tc_kernel did).  Replaces fc1_head_kernel + head_backward_tc_kernel on the
+// step's critical path.
+struct HeadBwd { bf16 *dh1; float *hp /* [G][H][4] */, *hb /* [G][4]: sum dq0, sum dq1, loss */; };
+template <int JPL>
+__global__ void __launch_bounds__(128) fc1_head_train_kernel(const float *__restrict__ part, int splits, size_t split_stride,
+                                                            const float *__restrict__ params, QnetLayout L, int B, float *__restrict__ q,
+                                                            const TdFuse td, const HeadBwd o, const AdamPow ap) {
+    tc::pdl_wait();
+    tc::pdl_launch();
+    constexpr int H = 32 * JPL;
+    __shared__ float4 red[4][H];
+    __shared__ float red_b[4][4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (ap.on && blockIdx.x == 0 && threadIdx.x == 0) {
+        const float b1p = ap.pow[0], b2p = ap.pow[1];
+        *ap.alpha = ap.lr * sqrtf(1.f - b2p) / (1.f - b1p);
+        ap.pow[0] = b1p * ap.beta1; ap.pow[1] = b2p * ap.beta2;
+    }
+    float w0[JPL], w1[JPL], wv[JPL], bias[JPL], g0[JPL], g1[JPL], gv[JPL], gb[JPL];
+#pragma unroll
+    for (int u = 0; u < JPL; u++) {
+        const int j = lane + 32 * u;
+        bias[u] = params[L.bf1 + j];
+        if (!L.dueling) { w0[u] = params[L.wf2 + j * 2]; w1[u] = params[L.wf2 + j * 2 + 1]; wv[u] = 0.f; }
+        else { w0[u] = params[L.wa + j * 2]; w1[u] = params[L.wa + j * 2 + 1]; wv[u] = params[L.wv + j]; }
+        g0[u] = g1[u] = gv[u] = gb[u] = 0.f;
+    }
+    float wmean = 1.f;
+    if (td.isw && td.isw_mean) {                     // ISWeights [B,1] * square(...) [B] broadcasts to [B,B] in the reference
+        float s = 0.f;                               // (BrainPrioritizedReplyDQN.py:243-251): every sample is weighted by mean(w)
+        for (int b = lane; b < B; b += 32) s += td.isw[b];
+#pragma unroll
+        for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(~0u, s, off);
+        wmean = s / (float)B;
+    }
+    const float b_q0 = L.dueling ? params[L.ba] : params[L.bf2], b_q1 = L.dueling ? params[L.ba + 1] : params[L.bf2 + 1];
+    const float b_v = L.dueling ? params[L.bv] : 0.f;
+    float sd0 = 0.f, sd1 = 0.f, sloss = 0.f;
+    const int nwarps = gridDim.x * 4;
+    for (int b = blockIdx.x * 4 + warp; b < B; b += nwarps) {
+        float x[JPL];
+        float s0 = 0.f, s1 = 0.f, sv = 0.f;
+#pragma unroll
+        for (int u = 0; u < JPL; u++) x[u] = bias[u];
+        for (int z = 0; z < splits; z++) {
+            const float *pz = part + (size_t)z * split_stride + (size_t)b * H + lane;
+#pragma unroll
+            for (int u = 0; u < JPL; u++) x[u] += pz[32 * u];
+        }
+#pragma unroll
+        for (int u = 0; u < JPL; u++) {
+            x[u] = fmaxf(x[u], 0.f);
+            s0 = fmaf(x[u], w0[u], s0); s1 = fmaf(x[u], w1[u], s1); sv = fmaf(x[u], wv[u], sv);
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) { s0 += __shfl_xor_sync(~0u, s0, off); s1 += __shfl_xor_sync(~0u, s1, off); sv += __shfl_xor_sync(~0u, sv, off); }
+        float q0, q1;
+        if (!L.dueling) { q0 = s0 + b_q0; q1 = s1 + b_q1; }
+        else { const float a0 = s0 + b_q0, a1 = s1 + b_q1, v = sv + b_v, mean = (a0 + a1) * 0.5f; q0 = v + (a0 - mean); q1 = v + (a1 - mean); }
+        // td_loss_kernel's arithmetic (fb_qnet.cu), the same in every lane
+        float xn;
+        if (td.variant == 2) { const int am = td.q_next_online[b * 2 + 1] > td.q_next_online[b * 2] ? 1 : 0; xn = td.q_next[b * 2 + am]; }
+        else xn = fmaxf(td.q_next[b * 2], td.q_next[b * 2 + 1]);
+        const float rf = td.rewards[b];
+        const double r = rf == 0.1f ? 0.1 : (double)rf;
+        const float y = (float)(td.terminals[b] ? r : r + td.gamma * (double)xn);
+        const int a = td.actions[b] ? 1 : 0;
+        const float err = y - (a ? q1 : q0);
+        const float w = td.isw ? (td.isw_mean ? wmean : td.isw[b]) : 1.f;
+        const float scale = td.loss_sum ? 1.f : 1.f / (float)td.global_batch;
+        const float g = -2.f * w * err * scale;
+        const float d0 = a ? 0.f : g, d1 = a ? g : 0.f;
+        sd0 += d0; sd1 += d1; sloss += w * err * err * scale;
+        if (lane == 0) {
+            q[b * 2] = q0; q[b * 2 + 1] = q1;
+            td.dq[b * 2] = d0; td.dq[b * 2 + 1] = d1;
+            td.loss_terms[b] = w * err * err * scale;
+            if (td.abs_err) td.abs_err[b] = fabsf(err);
+            if (td.q_target) td.q_target[b] = y;
+        }
+        // head backward for this sample (head_backward_tc_kernel's arithmetic)
+        const float m = (d0 + d1) * 0.5f;
+#pragma unroll
+        for (int u = 0; u < JPL; u++) {
+            float gh;
+            if (!L.dueling) { g0[u] = fmaf(x[u], d0, g0[u]); g1[u] = fmaf(x[u], d1, g1[u]); gh = d0 * w0[u] + d1 * w1[u]; }
+            else {
+                g0[u] = fmaf(x[u], d0 - m, g0[u]); g1[u] = fmaf(x[u], d1 - m, g1[u]); gv[u] = fmaf(x[u], d0 + d1, gv[u]);
+                gh = (d0 - m) * w0[u] + (d1 - m) * w1[u] + (d0 + d1) * wv[u];
+            }
+            gh = x[u] > 0.f ? gh : 0.f;
+            const bf16 gr = __float2bfloat16(gh);
+            o.dh1[(size_t)b * H + lane + 32 * u] = gr;
+            gb[u] += __bfloat162float(gr);            // the bias gradient sums what the weight-gradient GEMM sees
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < JPL; u++) red[warp][lane + 32 * u] = make_float4(g0[u], g1[u], gv[u], gb[u]);
+    if (lane == 0) { red_b[warp][0] = sd0; red_b[warp][1] = sd1; red_b[warp][2] = sloss; }
+    __syncthreads();
+    for (int j = threadIdx.x; j < H; j += 128) {
+        float4 t = red[0][j];
+#pragma unroll
+        for (int k = 1; k < 4; k++) { const float4 v = red[k][j]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+        *reinterpret_cast<float4 *>(o.hp + ((size_t)blockIdx.x * H + j) * 4) = t;
+    }
+    if (threadIdx.x < 3) o.hb[blockIdx.x * 4 + threadIdx.x] = red_b[0][threadIdx.x] + red_b[1][threadIdx.x] + red_b[2][threadIdx.x] + red_b[3][threadIdx.x];
 }
 
 // split-K partials, bias partials and head partials -> the flat gradient vector in TF variable order (HWIO).  One CTA
@@ -614,24 +783,39 @@ struct FinalizeArgs {
     float *loss_out;
 };
 // With `ad.on` the same launch also applies Adam (fb_qnet_train_step): the CTA that has just summed 32 gradient elements
-// updates those parameters, and CTAs [nb_fin, gridDim.x) update W_fc1 (four elements a thread), whose gradient the fc1 GEMM
-// wrote in place.  alpha was left in device memory by head_backward_tc_kernel, so the whole update replays as one CUDA graph.
-struct AdamDev { int on; float *p, *m, *v; float beta1, beta2, eps, grad_scale; const float *alpha; int nb_fin; };
+// updates those parameters (W_fc1, whose gradient the fc1 GEMM wrote in place, is updated earlier by adam_wf1_kernel).
+// alpha was left in device memory by the head kernel, so the whole update replays as one CUDA graph.
+// These kernels WRITE the bf16 operand copies: no early launch_dependents (see pack_weights_kernel).
+struct AdamDev { int on; float *p, *m, *v; float beta1, beta2, eps, grad_scale; const float *alpha; };
+// Adam on W_fc1: its gradient exists early in the backward pass, so these 819,200 of the 898,722 parameters are updated beside
+// the convolution gradients instead of after them (the caller orders it after the fc1 data-gradient GEMM, the last reader of
+// the bf16 copy it rewrites).
+__global__ void __launch_bounds__(256) adam_wf1_kernel(QnetLayout L, const float *__restrict__ grads, const AdamDev ad, const PackedWeights pw) {
+    const float alpha = *ad.alpha;
+    const int n4 = (L.bf1 - L.wf1) >> 2;            // hidden % 128 == 0: a multiple of four, 16-byte aligned (L.wf1 = 77,984)
+    for (int i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += gridDim.x * blockDim.x) {
+        const int i = L.wf1 + 4 * i4;
+        const float4 g = *reinterpret_cast<const float4 *>(grads + i);
+        float4 p = *reinterpret_cast<float4 *>(ad.p + i), m = *reinterpret_cast<float4 *>(ad.m + i), v = *reinterpret_cast<float4 *>(ad.v + i);
+        const float gg[4] = {g.x, g.y, g.z, g.w};
+        float pp[4] = {p.x, p.y, p.z, p.w}, mm[4] = {m.x, m.y, m.z, m.w}, vv[4] = {v.x, v.y, v.z, v.w};
+        uint32_t pk[2];
+#pragma unroll
+        for (int k = 0; k < 4; k++) pp[k] = adam_math(gg[k], pp[k], mm[k], vv[k], alpha, ad.beta1, ad.beta2, ad.eps, ad.grad_scale);
+        *reinterpret_cast<float4 *>(ad.p + i) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+        *reinterpret_cast<float4 *>(ad.m + i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+        *reinterpret_cast<float4 *>(ad.v + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+#pragma unroll
+        for (int k = 0; k < 2; k++) { __nv_bfloat162 h = __floats2bfloat162_rn(pp[2 * k], pp[2 * k + 1]); pk[k] = *reinterpret_cast<uint32_t *>(&h); }
+        *reinterpret_cast<uint2 *>(pw.wf1n + 4 * i4) = make_uint2(pk[0], pk[1]);
+    }
+}
 __global__ void __launch_bounds__(256) finalize_grads_kernel(const FinalizeArgs a, QnetLayout L, float *__restrict__ grads, const AdamDev ad,
                                                             const PackedWeights pw) {
     tc::pdl_wait();
-    tc::pdl_launch();
+    if (!ad.on) tc::pdl_launch();
     __shared__ float red[8][32];
     const float alpha = ad.on ? *ad.alpha : 0.f;
-    if (ad.on && (int)blockIdx.x >= ad.nb_fin) {                    // Adam on W_fc1
-        const int i0 = L.wf1 + ((int)blockIdx.x - ad.nb_fin) * 1024 + (int)threadIdx.x;
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int i = i0 + u * 256;
-            if (i < L.bf1) adam_one(i, grads[i], ad.p, ad.m, ad.v, alpha, ad.beta1, ad.beta2, ad.eps, ad.grad_scale, L, pw);
-        }
-        return;
-    }
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5, H = L.hidden;
     const int k = blockIdx.x * 32 + lane;            // compact index: [0, wf1) then [bf1, total)
     const int n_compact = L.wf1 + (L.total - L.bf1);
@@ -771,8 +955,9 @@ struct TcState {
     std::map<int, TcPlan> plans;
     int n_sms;
     cudaStream_t aux;           // second stream: target forward / weight gradients run beside the critical path
+    cudaStream_t aux2;          // third stream: bias column sums and the early Adam on W_fc1
     cudaStream_t cap;           // capture origin (the caller's stream may be the legacy default stream, which cannot capture)
-    cudaEvent_t ev[8];
+    cudaEvent_t ev[16];
     std::vector<GraphEntry> graphs;
     int use_graph;
     int conv1_mode;             // 2 (default): pooled epilogue, slab from u8 when no backward follows; 1: slab always from X2;
@@ -783,6 +968,9 @@ namespace {
 
 constexpr int kChunk1 = 1024, kChunk23 = 256;
 constexpr int kFc1Splits = 5;                    // fc1 forward: 25 K-blocks in 5 K-splits of 5
+// the fused head kernel (fc1_head_train_kernel<16>) serves the reference's hidden width; other widths keep the two-kernel form
+bool fused_head_ok(const QnetLayout &L) { return L.hidden == 512; }
+int head_ctas(const TcState *t, int B) { const int c = (B + 3) / 4, m = t->n_sms < kMaxHeadCtas ? t->n_sms : kMaxHeadCtas; return c < m ? c : m; }
 
 // slab geometry (rows of 128 bytes): tile or K-block rows + the largest tap offset, rounded up to 8
 constexpr int kSlab1 = 152, kSlab2 = 136, kSlab3 = 144;          // forward / data gradient, 128-position tiles
@@ -850,7 +1038,7 @@ int make_plan(fb_qnet *n, int B, TcPlan **out) {
     p.conv1_w.p_total = (int)P1; p.conv1_w.slab_row0 = 0;
     // split-K: about 24 (conv1) / 4 (conv2, conv3) K-blocks of 64 positions per CTA, one wave of CTAs at most
     auto splits_for = [](long long P, int kb_per_cta) { long long s = (P / 64 + kb_per_cta - 1) / kb_per_cta; return (int)(s < 1 ? 1 : s > 148 ? 148 : s); };
-    p.s1 = plan_splits(P1, splits_for(P1, 24), &p.conv1_w.klen);
+    p.s1 = plan_splits(P1, splits_for(P1, 8), &p.conv1_w.klen);            // at minibatch sizes: every SM takes <= 12 K-blocks
     p.conv1_w.acc_rowoff[0] = 0; p.conv1_w.acc_lbo[0] = 128; p.conv1_w.acc_rowoff[1] = kG1; p.conv1_w.acc_lbo[1] = 128;
     p.conv2_w.p_total = (int)P2; p.conv2_w.slab_row0 = 0;
     p.s2 = plan_splits(P2, splits_for(P2, 4), &p.conv2_w.klen);
@@ -904,7 +1092,10 @@ int tc_state_create(fb_qnet *n) {
     FB_CUDA_OK(alloc_f(&t->part3, t->cap3 * 640 * 64));
     FB_CUDA_OK(alloc_f(&t->bp1, ((B * kP1 + kChunk1 - 1) / kChunk1) * 32)); FB_CUDA_OK(alloc_f(&t->bp2, ((B * kP2 + kChunk23 - 1) / kChunk23) * 64));
     FB_CUDA_OK(alloc_f(&t->bp3, ((B * kP2 + kChunk23 - 1) / kChunk23) * 64));
-    FB_CUDA_OK(alloc_f(&t->hp, ((B + kHeadRows - 1) / kHeadRows) * H * 4)); FB_CUDA_OK(alloc_f(&t->hb, ((B + kHeadRows - 1) / kHeadRows) * 4 + 4));
+    {   // head partials: one per row group (head_backward_tc_kernel) or per CTA of the fused head kernel (at most kMaxHeadCtas)
+        const size_t G = (B + kHeadRows - 1) / kHeadRows > (size_t)kMaxHeadCtas ? (B + kHeadRows - 1) / kHeadRows : (size_t)kMaxHeadCtas;
+        FB_CUDA_OK(alloc_f(&t->hp, G * H * 4)); FB_CUDA_OK(alloc_f(&t->hb, G * 4 + 4));
+    }
     FB_CUDA_OK(alloc_f(&t->loss_terms, B));
     FB_CUDA_OK(alloc_f(&t->adam_pow, 4));
     FB_CUDA_OK(cudaMallocHost(&t->pow_pinned, 32 * sizeof(float)));
@@ -925,8 +1116,15 @@ int tc_state_create(fb_qnet *n) {
     int dev = 0;
     FB_CUDA_OK(cudaGetDevice(&dev));
     FB_CUDA_OK(cudaDeviceGetAttribute(&t->n_sms, cudaDevAttrMultiProcessorCount, dev));
-    FB_CUDA_OK(cudaStreamCreateWithFlags(&t->aux, cudaStreamNonBlocking));
-    FB_CUDA_OK(cudaStreamCreateWithFlags(&t->cap, cudaStreamNonBlocking));
+    {   // the side streams run at the LOWEST priority, the capture origin at the highest: when a critical-path kernel and a side
+        // kernel are ready together the block scheduler places the critical one first (measured: the Q(s') conv1, 576 threads
+        // and the whole register file per SM, held up the 256-thread X2 conversion of the Q(s) path by 7.6 us)
+        int lo = 0, hi = 0;
+        FB_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        FB_CUDA_OK(cudaStreamCreateWithPriority(&t->aux, cudaStreamNonBlocking, lo));
+        FB_CUDA_OK(cudaStreamCreateWithPriority(&t->aux2, cudaStreamNonBlocking, hi));     // short kernels finalize waits for
+        FB_CUDA_OK(cudaStreamCreateWithPriority(&t->cap, cudaStreamNonBlocking, hi));
+    }
     for (auto &e : t->ev) FB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     t->use_graph = 1;
     { const char *e = getenv("FB_TC_CONV1_MODE"); t->conv1_mode = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }
@@ -954,6 +1152,7 @@ void tc_state_destroy(fb_qnet *n) {
     }
     for (auto &e : t->ev) if (e) cudaEventDestroy(e);
     if (t->aux) cudaStreamDestroy(t->aux);
+    if (t->aux2) cudaStreamDestroy(t->aux2);
     if (t->cap) cudaStreamDestroy(t->cap);
     delete t;
     n->tc = nullptr;
@@ -962,6 +1161,17 @@ void tc_state_destroy(fb_qnet *n) {
 int tc_pack_weights(fb_qnet *n, const float *params_dev, int slot, cudaStream_t st) {
     FB_REQUIRE(n->tc != nullptr && (slot == 0 || slot == 1), "tc_pack_weights: bad argument");
     FB_CUDA_OK(tc::launch_pdl(pack_weights_kernel, dim3(592), dim3(256), 0, st, params_dev, n->L, n->tc->pw[slot], slot == 1 ? 1 : 0));
+    return FB_OK;
+}
+
+extern "C" int fb_debug_poison_packed(fb_qnet *n, int slot, void *stream) {
+    FB_REQUIRE(n != nullptr && n->tc != nullptr && (slot == 0 || slot == 1), "fb_debug_poison_packed: needs the tensor-core path and slot 0 / 1");
+    const PackedWeights &w = n->tc->pw[slot];
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t H = (size_t)n->L.hidden;
+    FB_CUDA_OK(cudaMemsetAsync(w.w1p, 0xFF, sizeof(bf16) * kC1 * kK1, st)); FB_CUDA_OK(cudaMemsetAsync(w.w2p, 0xFF, sizeof(bf16) * kC2 * kK2, st));
+    FB_CUDA_OK(cudaMemsetAsync(w.w3p, 0xFF, sizeof(bf16) * kC3 * kK3, st)); FB_CUDA_OK(cudaMemsetAsync(w.wf1n, 0xFF, sizeof(bf16) * kFlat * H, st));
+    FB_CUDA_OK(cudaMemsetAsync(w.w3d, 0xFF, sizeof(bf16) * kC3 * kK3, st)); FB_CUDA_OK(cudaMemsetAsync(w.w2d, 0xFF, sizeof(bf16) * 128 * 256, st));
     return FB_OK;
 }
 
@@ -1001,12 +1211,12 @@ static FrameView g_probe_view;                    // frames of the last forward 
 // td != nullptr: the TD target / loss is fused into the head kernel; `join` (if any) is waited for first -- it marks the end
 // of the Q(s') forward on the other stream
 static int tc_forward_impl(fb_qnet *n, int slot, int w, const float *params_dev, FrameView fv, int B, float *q_out, int keep, cudaStream_t st,
-                           const TdFuse *td = nullptr, cudaEvent_t join = nullptr);
+                           const TdFuse *td = nullptr, cudaEvent_t join = nullptr, const AdamPow *ap = nullptr);
 int tc_forward(fb_qnet *n, int slot, int w, const float *params_dev, FrameView fv, int B, float *q_out, cudaStream_t st) {
     return tc_forward_impl(n, slot, w, params_dev, fv, B, q_out, 0, st);
 }
 static int tc_forward_impl(fb_qnet *n, int slot, int w, const float *params_dev, FrameView fv, int B, float *q_out, int keep, cudaStream_t st,
-                           const TdFuse *td, cudaEvent_t join) {
+                           const TdFuse *td, cudaEvent_t join, const AdamPow *ap) {
     TcState *t = n->tc;
     FB_REQUIRE(t != nullptr && B > 0 && B <= n->max_batch && (w == 0 || w == 1), "tc_forward: bad argument");
     TcPlan *p;
@@ -1038,8 +1248,16 @@ static int tc_forward_impl(fb_qnet *n, int slot, int w, const float *params_dev,
                                        EpiStoreF32{f.parth, B, L.hidden, (size_t)n->max_batch * L.hidden}, st)));
     if (join) FB_CUDA_OK(cudaStreamWaitEvent(st, join, 0));
     TdFuse none{};
-    FB_CUDA_OK(tc::launch_pdl(fc1_head_kernel, dim3(B), dim3(128), 0, st, f.parth, p->sf, (size_t)n->max_batch * L.hidden, params_dev, L, B,
-                              keep ? f.h1 : nullptr, q_out, td ? *td : none));
+    if (td != nullptr && ap != nullptr && fused_head_ok(L))      // training step: head forward + TD loss + head backward in one kernel
+        FB_CUDA_OK(tc::launch_pdl(fc1_head_train_kernel<16>, dim3(head_ctas(t, B)), dim3(128), 0, st, f.parth, p->sf,
+                                  (size_t)n->max_batch * L.hidden, params_dev, L, B, q_out, *td, HeadBwd{t->dh1, t->hp, t->hb}, *ap));
+    else if (td == nullptr && fused_head_ok(L)) {
+        const int ctas = (B + 3) / 4 < 4 * t->n_sms ? (B + 3) / 4 : 4 * t->n_sms;
+        FB_CUDA_OK(tc::launch_pdl(fc1_head_warp_kernel<16>, dim3(ctas), dim3(128), 0, st, f.parth, p->sf, (size_t)n->max_batch * L.hidden,
+                                  params_dev, L, B, keep ? f.h1 : nullptr, q_out));
+    } else
+        FB_CUDA_OK(tc::launch_pdl(fc1_head_kernel, dim3(B), dim3(128), 0, st, f.parth, p->sf, (size_t)n->max_batch * L.hidden, params_dev, L, B,
+                                  keep ? f.h1 : nullptr, q_out, td ? *td : none));
     return FB_OK;
 }
 
@@ -1051,7 +1269,7 @@ int tc_forward_chunks(fb_qnet *n, int slot, const float *params_dev, const uint8
     FB_REQUIRE(t != nullptr, "tc_forward_chunks: no tensor-core state");
     const int nchunks = (batch + n->max_batch - 1) / n->max_batch;
     const bool two = nchunks > 1;
-    if (two) { FB_CUDA_OK(cudaEventRecord(t->ev[6], st)); FB_CUDA_OK(cudaStreamWaitEvent(t->aux, t->ev[6], 0)); }
+    if (two) { FB_CUDA_OK(cudaEventRecord(t->ev[14], st)); FB_CUDA_OK(cudaStreamWaitEvent(t->aux, t->ev[14], 0)); }
     int c = 0;
     for (int b0 = 0; b0 < batch; b0 += n->max_batch, c++) {
         const int B = min(n->max_batch, batch - b0), w = two ? (c & 1) : 0;
@@ -1061,7 +1279,7 @@ int tc_forward_chunks(fb_qnet *n, int slot, const float *params_dev, const uint8
         int rc = tc_forward(n, slot, w, params_dev, fv, B, q_out_dev + (size_t)b0 * 2, w ? t->aux : st);
         if (rc) return rc;
     }
-    if (two) { FB_CUDA_OK(cudaEventRecord(t->ev[7], t->aux)); FB_CUDA_OK(cudaStreamWaitEvent(st, t->ev[7], 0)); }
+    if (two) { FB_CUDA_OK(cudaEventRecord(t->ev[15], t->aux)); FB_CUDA_OK(cudaStreamWaitEvent(st, t->ev[15], 0)); }
     return FB_OK;
 }
 
@@ -1099,40 +1317,60 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     // ---- main: Q(s) with the online net; its activations stay in workspace 0 for the backward pass
     // the TD target, loss and dLoss/dQ come out of its head kernel, which first waits for Q(s') from the other stream
     FB_CUDA_OK(cudaEventRecord(t->ev[e], sx));
-    TdFuse td{1, a.variant, a.loss_sum, a.global_batch, a.gamma, n->q_next, n->q_next_online, a.rewards, a.isw, a.actions, a.terminals,
-              n->dq, a.abs_err, a.q_target, t->loss_terms};
-    rc = tc_forward_impl(n, 0, 0, a.params, a.fs, B, n->q, 1, st, &td, t->ev[e]); if (rc) return rc;
+    TdFuse td{1, a.variant, a.loss_sum, a.global_batch, n->per_broadcast, a.gamma, n->q_next, n->q_next_online, a.rewards, a.isw, a.actions,
+              a.terminals, n->dq, a.abs_err, a.q_target, t->loss_terms};
+    const AdamPow apow{a.ad.on, t->adam_pow, t->adam_pow + 2, a.ad.lr, a.ad.beta1, a.ad.beta2};
+    rc = tc_forward_impl(n, 0, 0, a.params, a.fs, B, n->q, 1, st, &td, t->ev[e], &apow); if (rc) return rc;
     e++;
-    // ---- backward.  head: fp32 gradients of the head variables and the fc1 bias straight into grads, dh1 as bf16
-    const int G = (B + kHeadRows - 1) / kHeadRows;
-    FB_CUDA_OK(tc::launch_pdl(head_backward_tc_kernel, dim3(H / 32 + 1, G), dim3(256), 0, st, f.h1, n->dq, a.params, L, B, t->hp, t->hb,
-                              t->loss_terms, t->dh1, AdamPow{a.ad.on, t->adam_pow, t->adam_pow + 2, a.ad.lr, a.ad.beta1, a.ad.beta2}));
+    // ---- backward.  The head's backward pass rode in the forward's last kernel when hidden = 512 (fc1_head_train_kernel);
+    // otherwise: fp32 gradients of the head variables and the fc1 bias straight into partials, dh1 as bf16
+    const bool fused_head = fused_head_ok(L);
+    const int G = fused_head ? head_ctas(t, B) : (B + kHeadRows - 1) / kHeadRows;
+    if (!fused_head)
+        FB_CUDA_OK(tc::launch_pdl(head_backward_tc_kernel, dim3(H / 32 + 1, G), dim3(256), 0, st, f.h1, n->dq, a.params, L, B, t->hp, t->hb,
+                                  t->loss_terms, t->dh1, apow));
+    cudaStream_t sy = t->aux2;                  // third stream: bias column sums and the early Adam on W_fc1, all off the critical path
     FB_CUDA_OK(fork(st, sx));
     // fc1: dW = a3^T dh1 (aux, written in place), dz3 = (dh1 Wf1^T) * relu'(a3)
     FB_CUDA_OK((launch_tc_gemm<128, 1>(p->a3_m, p->dh1_b, p->fc1_w, dim3(13, H / 128, 1), EpiStoreF32{a.grads + L.wf1, kFlat, H, 0}, sx)));
+    const int e_fc1w = e++;
+    FB_CUDA_OK(cudaEventRecord(t->ev[e_fc1w], sx));                    // W_fc1's gradient is final
     FB_CUDA_OK((launch_tc_gemm<64, 0>(p->dh1_k, wm.wf1n, p->fc1_d, dim3((B + 127) / 128, kFlat / 64, 1), EpiFc1Dgrad{t->dz3, f.a3, B}, st)));
     FB_CUDA_OK(fork(st, sx));
+    FB_CUDA_OK(cudaStreamWaitEvent(sy, t->ev[e - 1], 0));              // sy: after the fc1 data gradient (dz3 complete, wf1n no longer read)
+    const int c1 = (P1 + kChunk1 - 1) / kChunk1, c23 = (P2 + kChunk23 - 1) / kChunk23;
+    auto colsum_on = [&](const bf16 *x, float *part, int rows, int N, int chunk_rows, int chunks) -> cudaError_t {
+        ColsumJobs cj{};
+        cj.njobs = 1;
+        cj.j[0] = ColsumJob{x, part, rows, N, chunk_rows, 0};
+        colsum_kernel<<<chunks, 256, 0, sy>>>(cj);
+        return cudaGetLastError();
+    };
+    FB_CUDA_OK(colsum_on(t->dz3, t->bp3, P2, 64, kChunk23, c23));
+    AdamDev ad{a.ad.on, const_cast<float *>(a.params), a.ad.m, a.ad.v, a.ad.beta1, a.ad.beta2, a.ad.eps, a.ad.grad_scale, t->adam_pow + 2};
     FB_CUDA_OK((launch_tc_wgrad<64, 5, kSlabW3, 1, 6>(p->a2_w, p->dz3_b, p->conv3_w, p->s3, EpiStoreF32{t->part3, 640, 64, (size_t)640 * 64}, sx)));
     FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4, 1>(p->dz3_s, wm.w3d, p->conv3_d, t->n_sms, EpiConv3Dgrad{t->dz2, f.a2, P2}, st)));
     FB_CUDA_OK(fork(st, sx));
+    FB_CUDA_OK(cudaStreamWaitEvent(sy, t->ev[e - 1], 0));              // sy: after the conv3 data gradient (dz2 complete)
+    FB_CUDA_OK(colsum_on(t->dz2, t->bp2, P2, 64, kChunk23, c23));
     FB_CUDA_OK((launch_tc_wgrad<64, 4, kSlabW2, 2, 4>(p->p2_w, p->dz2_b, p->conv2_w, p->s2, EpiStoreF32{t->part2, 512, 64, (size_t)512 * 64}, sx)));
     FB_CUDA_OK((launch_tc_conv<128, kSlab2, 1, 4, 4, 1>(p->dz2_s, wm.w2d, p->conv2_d, t->n_sms, EpiStoreBf16{t->dp2, P2, 128}, st)));
     FB_CUDA_OK(tc::launch_pdl(unpool_relu_kernel_tc, dim3((unsigned)(((size_t)B * 400 + 255) / 256)), dim3(256), 0, st, f.z1, t->dp2, B, t->dz1));
-    // conv1 weight gradient (no input gradient there), then the bias gradients = column sums of the dZ tensors
+    FB_CUDA_OK(fork(st, sy));                                           // sy: after the un-pool (dz1 complete)
+    FB_CUDA_OK(colsum_on(t->dz1, t->bp1, P1, 32, kChunk1, c1));
+    if (a.ad.on) {                                                      // last on sy: after the fc1 weight gradient (sx) and the fc1 data gradient
+        FB_CUDA_OK(cudaStreamWaitEvent(sy, t->ev[e_fc1w], 0));
+        adam_wf1_kernel<<<4 * t->n_sms, 256, 0, sy>>>(L, a.grads, ad, t->pw[0]);
+        FB_CUDA_OK(cudaGetLastError());
+    }
+    // conv1 weight gradient (no input gradient there); the bias gradients = column sums of the dZ tensors ran beside it
     FB_CUDA_OK((launch_tc_wgrad<32, 2, kSlabW1, 1, 6>(p->x2_w, p->dz1_b, p->conv1_w, p->s1, EpiStoreF32{t->part1, 256, 32, (size_t)256 * 32}, st)));
-    const int c1 = (P1 + kChunk1 - 1) / kChunk1, c23 = (P2 + kChunk23 - 1) / kChunk23;
-    ColsumJobs cj{};
-    cj.njobs = 3;
-    cj.j[0] = ColsumJob{t->dz1, t->bp1, P1, 32, kChunk1, 0};
-    cj.j[1] = ColsumJob{t->dz2, t->bp2, P2, 64, kChunk23, c1};
-    cj.j[2] = ColsumJob{t->dz3, t->bp3, P2, 64, kChunk23, c1 + c23};
-    FB_CUDA_OK(tc::launch_pdl(colsum_kernel, dim3(c1 + 2 * c23), dim3(256), 0, st, cj));
     FB_CUDA_OK(fork(sx, st));
+    FB_CUDA_OK(fork(sy, st));
     FinalizeArgs fa{t->part1, t->part2, t->part3, p->s1, p->s2, p->s3, t->bp1, t->bp2, t->bp3, c1, c23, c23, t->hp, t->hb, G, a.loss_out};
     const int n_compact = L.wf1 + (L.total - L.bf1);
-    const int nb_fin = (n_compact + 31) / 32, nb_wf1 = a.ad.on ? (L.bf1 - L.wf1 + 1023) / 1024 : 0;
-    AdamDev ad{a.ad.on, const_cast<float *>(a.params), a.ad.m, a.ad.v, a.ad.beta1, a.ad.beta2, a.ad.eps, a.ad.grad_scale, t->adam_pow + 2, nb_fin};
-    FB_CUDA_OK(tc::launch_pdl(finalize_grads_kernel, dim3(nb_fin + nb_wf1), dim3(256), 0, st, fa, L, a.grads, ad, t->pw[0]));
+    const int nb_fin = (n_compact + 31) / 32;
+    FB_CUDA_OK(tc::launch_pdl(finalize_grads_kernel, dim3(nb_fin), dim3(256), 0, st, fa, L, a.grads, ad, t->pw[0]));
     if (a.pro.replay != nullptr && a.pro.prioritized) { rc = replay_launch_per_update(a.pro, a.abs_err, st); if (rc) return rc; }   // Memory.batch_update
     return FB_OK;
 }
@@ -1140,6 +1378,11 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
 bool same_key(const GraphKey &x, const GraphKey &y) { return memcmp(&x, &y, sizeof(GraphKey)) == 0; }
 
 }  // namespace
+
+int tc_drop_graphs(fb_qnet *n) {
+    if (n->tc) { for (auto &g : n->tc->graphs) destroy_entry(g); n->tc->graphs.clear(); }
+    return FB_OK;
+}
 
 extern "C" int fb_qnet_set_conv1_mode(fb_qnet *n, int mode) {
     FB_REQUIRE(n != nullptr && n->tc != nullptr && mode >= 0 && mode <= 2, "fb_qnet_set_conv1_mode: needs FB_PRECISION_BF16 and mode 0..2");

@@ -16,6 +16,14 @@ namespace {
 
 constexpr int kConvThreads = 192;          // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2..5 epilogue
 
+// Every tcgen05 kernel asks for more than half of an SM's shared memory, so that two tensor-core CTAs (of the same or of
+// different, concurrently running kernels) never share an SM.  The block scheduler knows nothing about TMEM: a CTA placed
+// beside one that holds the columns it needs spins in tcgen05.alloc with its shared memory and registers taken -- measured in
+// the training step's backward pass, where three weight-gradient kernels and two data-gradient kernels overlap: the conv2
+// weight gradient took 24-29 us for 2 us of tensor work.  With exclusive SMs the scheduler queues CTAs instead.
+constexpr size_t kExclusiveSmem = 116 * 1024;
+constexpr size_t exclusive_smem(size_t need) { return need > kExclusiveSmem ? need : kExclusiveSmem; }
+
 struct ConvParams {
     int n_tiles;                           // tiles of 128 output positions
     int slab_row0;                         // the slab of tile t starts at row 128 t + slab_row0 (<= 0)
@@ -163,7 +171,7 @@ template <int BN, int SLAB_ROWS, int NHALF, int NKB, int S, int T, class EP>
 static cudaError_t launch_tc_conv(const CUtensorMap &ma, const CUtensorMap &mb, const ConvParams &g, int max_ctas, EP ep, cudaStream_t st) {
     static bool configured = false;
     auto kern = tc_conv_kernel<BN, SLAB_ROWS, NHALF, NKB, S, T, EP>;
-    constexpr size_t smem = conv_smem_bytes<BN, SLAB_ROWS, NHALF, NKB, S>();
+    constexpr size_t smem = exclusive_smem(conv_smem_bytes<BN, SLAB_ROWS, NHALF, NKB, S>());
     static_assert(smem <= 227 * 1024, "shared memory budget");
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -284,7 +292,7 @@ template <int BN, int NACC, int SLAB_ROWS, int NHALF, int S, class EP>
 static cudaError_t launch_tc_wgrad(const CUtensorMap &ma, const CUtensorMap &mb, const WgradParams &g, int splits, EP ep, cudaStream_t st) {
     static bool configured = false;
     auto kern = tc_wgrad_kernel<BN, NACC, SLAB_ROWS, NHALF, S, EP>;
-    constexpr size_t smem = (size_t)S * (NHALF * SLAB_ROWS * 128 + 64 * BN * 2) + 1024;
+    constexpr size_t smem = exclusive_smem((size_t)S * (NHALF * SLAB_ROWS * 128 + 64 * BN * 2) + 1024);
     static_assert(smem <= 227 * 1024, "shared memory budget");
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -563,7 +571,7 @@ template <int S, bool FROM_X2>
 static cudaError_t launch_tc_conv1_fused(const CUtensorMap &ma, const CUtensorMap &mb, const Conv1FusedParams &g, int max_ctas, cudaStream_t st) {
     static bool configured = false;
     auto kern = tc_conv1_fused_kernel<S, FROM_X2>;
-    constexpr size_t smem = 4 * 32 * 128 + (size_t)S * kSlabF * 128 + 4 * 128 * 32 * 2 + (FROM_X2 ? 0 : kRawStages * kRawBytes) + 1024;
+    constexpr size_t smem = exclusive_smem(4 * 32 * 128 + (size_t)S * kSlabF * 128 + 4 * 128 * 32 * 2 + (FROM_X2 ? 0 : kRawStages * kRawBytes) + 1024);
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -89,6 +89,11 @@ class QNetwork:
         self.adam_steps = 0
         self.exchange = None                    # dist.PeerGradExchange once enable_peer_exchange() was called
 
+    def set_per_broadcast(self, on: bool):
+        """PER loss exactly as the reference's graph evaluates it (BrainPrioritizedReplyDQN.py:243-251): the [B,1] ISWeights
+        placeholder times the [B] squared error broadcasts to [B,B], i.e. every sample is weighted by mean(ISWeights)."""
+        _lib.check(self._L.fb_qnet_set_per_broadcast(self._h, int(bool(on))), "fb_qnet_set_per_broadcast")
+
     def enable_peer_exchange(self, exchange=None):
         """Multi-GPU: keep the gradient vector in an NVLink-mapped exchange buffer and let adam_step() sum every rank's
         gradients from peer memory inside the Adam kernel (csrc/fb_dist.cu) instead of a separate all-reduce."""

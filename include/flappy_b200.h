@@ -161,6 +161,13 @@ int fb_qnet_destroy(fb_qnet *net);
 int fb_qnet_set_precision(fb_qnet *net, int precision);
 int fb_qnet_get_precision(const fb_qnet *net);
 int fb_qnet_invalidate(fb_qnet *net);
+/* PER loss exactly as the reference's graph evaluates it (BrainPrioritizedReplyDQN.py:243-251): the [B,1] ISWeights
+ * placeholder times the [B] squared error is broadcast to [B,B], so the cost is mean(w) * mean(err^2) and every sample's
+ * gradient is scaled by mean(w).  on = 0 (default): the intended mean(w_i * err_i^2). */
+int fb_qnet_set_per_broadcast(fb_qnet *net, int on);
+/* test hook: overwrite the bf16 operand copies of slot 0 (online) / 1 (target) with NaNs WITHOUT marking them stale --
+ * whoever reads them before the next pack kernel has finished shows up as NaN Q-values */
+int fb_debug_poison_packed(fb_qnet *net, int slot, void *stream);
 /* FB_PRECISION_BF16 only: replay fb_qnet_loss_backward as a CUDA graph once the same arguments were seen twice
  * (default on; the eager two-stream path is identical work). */
 int fb_qnet_use_graphs(fb_qnet *net, int enable);

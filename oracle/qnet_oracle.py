@@ -127,8 +127,12 @@ def forward(flat: torch.Tensor, x_u8, hidden=512, dueling=False, return_all=Fals
 
 
 def loss_and_grads(variant, params32, target32, s, s2, actions, rewards, terminals, isw=None, gamma=0.99, loss_sum=False,
-                   global_batch=None, hidden=512, dueling=False, emulate_bf16=False):
-    """variant 0 vanilla / 1 nature / 2 double.  Returns loss, grads (float64 flat), abs_err, y (fp32 as fed), q(s)."""
+                   global_batch=None, hidden=512, dueling=False, emulate_bf16=False, isw_broadcast=False):
+    """variant 0 vanilla / 1 nature / 2 double.  Returns loss, grads (float64 flat), abs_err, y (fp32 as fed), q(s).
+
+    ``isw_broadcast``: the PER cost exactly as the reference's graph evaluates it -- ``ISWeights`` is a [B,1] placeholder and
+    ``tf.square(q_target - q_eval)`` a [B] vector (BrainPrioritizedReplyDQN.py:243-251), so TensorFlow broadcasts the product
+    to [B,B] and ``reduce_mean`` returns mean(w) * mean(err^2).  Default: the intended mean(w_i * err_i^2)."""
     P = torch.tensor(params32.astype(np.float64), requires_grad=True)
     T = torch.tensor((target32 if target32 is not None else params32).astype(np.float64))
     B = len(actions)
@@ -151,7 +155,11 @@ def loss_and_grads(variant, params32, target32, s, s2, actions, rewards, termina
     q_eval = (q * onehot).sum(dim=1)
     err = torch.as_tensor(y.astype(np.float64)) - q_eval
     w = torch.ones(B, dtype=torch.float64) if isw is None else torch.as_tensor(np.asarray(isw, np.float64))
-    loss = (w * err ** 2).sum() if loss_sum else (w * err ** 2).sum() / gb
+    if isw is not None and isw_broadcast:
+        prod = w.reshape(B, 1) * (err ** 2).reshape(1, B)          # [B,1] * [B] -> [B,B], what tf.multiply does
+        loss = prod.sum() if loss_sum else prod.sum() / (B * gb)   # reduce_mean over B*B elements (gb = B on one GPU)
+    else:
+        loss = (w * err ** 2).sum() if loss_sum else (w * err ** 2).sum() / gb
     loss.backward()
     return float(loss.detach()), P.grad.numpy().copy(), err.detach().abs().numpy(), y, q.detach().numpy()
 

@@ -237,8 +237,26 @@ def gen_cv2():
                         cv2_version=np.array(cv2.__version__))
 
 
+def gen_graphs():
+    """The reference's own TensorFlow graphs: MetaGraphDef files of its checkpoints (weights are absent, the graphs are not),
+    parsed by oracle/tf_graph.py into JSON: vanilla DQN (BrainDQN.py:119-172, reduce_sum loss) and Nature DQN
+    (BrainDQNNature.py:35-123, eval_net + target_net, reduce_mean loss; --model ddqn saved the same graph)."""
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    from oracle import tf_graph
+    for out, rel in (("ref_graph_dqn.json", "train_history/dqn/4/bird-2500000.meta"),
+                     ("ref_graph_dqn_nature.json", "train_history/dqn_nature/bird-2000000.meta"),
+                     ("ref_graph_double_dqn.json", "train_history/double_dqn/bird-1500000.meta")):
+        g = tf_graph.parse_meta(os.path.join(REF, rel))
+        g["source"] = rel
+        # initialisers, Saver and summary nodes are not on the path: keep what the forward / loss / gradient / Adam ops reach
+        tf_graph.dump_json(g, os.path.join(HERE, out))
+        print(out, len(g["nodes"]), "nodes, TensorFlow", g["tf_version"])
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["env", "logs", "per", "cv2"]
+    which = sys.argv[1:] or ["env", "logs", "per", "cv2", "graphs"]
+    if "graphs" in which: gen_graphs()
     if "env" in which: gen_env_trajectories()
     if "logs" in which: gen_logs()
     if "per" in which: gen_per()

@@ -297,3 +297,104 @@ def test_train_step_is_loss_backward_plus_adam(mods, precision, variant, dueling
     fresh.train_step(variant, frames, a, r, term, loss_sum=(variant == "vanilla"))
     split.loss_backward(variant, frames, a, r, term, loss_sum=(variant == "vanilla")); split.adam_step()
     assert torch.equal(fresh.params, split.params)
+
+
+def test_pack_then_forward_never_reads_stale_operands(mods):
+    """The pack kernel writes the bf16 operand copies that its stream successor (a conv kernel launched with programmatic
+    dependent launch) TMA-loads in its prologue, before its own griddepcontrol.wait: the pack kernel must therefore not
+    release its dependents early.  Poison the copies (NaN bit patterns, NOT marked stale), mark them stale, run
+    pack + forward back to back many times: a conv kernel that fetched weights before the pack finished shows as NaN /
+    different Q-values.  Both operand slots: the online net (acting) and the target net (first update after a sync)."""
+    _lib, game, qnet = mods
+    L = _lib.lib()
+    B = 48
+    frames = _env_frames(game, B, 13)
+    net = qnet.QNetwork(max_batch=64, seed=4, precision="bf16")
+    net.params.mul_(4.0); net.target.mul_(3.0)
+    fb = qnet.FrameBatch.from_stack(frames, 0)
+    st = torch.cuda.current_stream().cuda_stream
+    for use_target in (False, True):
+        good = net.forward(fb, target=use_target).clone()
+        assert torch.isfinite(good).all()
+        for rep in range(40):
+            for slot in (0, 1):
+                _lib.check(L.fb_debug_poison_packed(net._h, slot, st), "fb_debug_poison_packed")
+            _lib.check(L.fb_qnet_invalidate(net._h), "fb_qnet_invalidate")
+            q = net.forward(fb, target=use_target)
+            assert torch.equal(q, good), (use_target, rep)
+    # the training step: Q(s') on the second stream right after the target operands were re-packed
+    rng = np.random.default_rng(6)
+    a = torch.from_numpy(rng.integers(0, 2, B).astype(np.uint8)).cuda()
+    r = torch.from_numpy(rng.choice(np.array([0.1, 3.0, -3.0], np.float32), B)).cuda()
+    term = (r == -3.0).to(torch.uint8)
+    ref_loss = net.loss_backward("nature", frames, a, r, term).clone()
+    ref_grads = net.grads.clone()
+    for rep in range(20):
+        for slot in (0, 1):
+            _lib.check(L.fb_debug_poison_packed(net._h, slot, st), "fb_debug_poison_packed")
+        _lib.check(L.fb_qnet_invalidate(net._h), "fb_qnet_invalidate")
+        loss = net.loss_backward("nature", frames, a, r, term)
+        assert torch.equal(loss, ref_loss) and torch.equal(net.grads, ref_grads), rep
+
+
+@pytest.mark.parametrize("precision,tol_g", [("fp32", 2e-4), ("bf16", 1.5e-2)])
+def test_per_broadcast_loss_is_what_the_reference_graph_computes(mods, precision, tol_g):
+    """BrainPrioritizedReplyDQN.py:243-251: ISWeights is a [B,1] placeholder, tf.square(q_target - q_eval) a [B] vector; their
+    product broadcasts to [B,B] and reduce_mean gives mean(w) * mean(err^2).  fb_qnet_set_per_broadcast(1) (what
+    reference_quirks=True selects) reproduces that; the default is the intended mean(w_i err_i^2).  Both against the oracle."""
+    _lib, game, qnet = mods
+    B = 32
+    frames = _env_frames(game, B, 17)
+    net = qnet.QNetwork(max_batch=B, precision=precision)
+    p = qo.init_params(512, False, seed=1) * np.float32(3.0)
+    t = qo.init_params(512, False, seed=2) * np.float32(3.0)
+    _set_params(net, p, t)
+    rng = np.random.default_rng(2)
+    a = rng.integers(0, 2, B).astype(np.uint8)
+    r = rng.choice(np.array([0.1, 3.0, -3.0], np.float32), B, p=[0.8, 0.1, 0.1])
+    term = (r == -3.0).astype(np.uint8)
+    isw = (0.05 + rng.random(B)).astype(np.float32)
+    x = frames.cpu().numpy()
+    emulate = precision == "bf16"
+    got = {}
+    for on in (False, True):
+        net.set_per_broadcast(on)
+        abs_err = torch.zeros(B, device="cuda")
+        net.loss_backward("nature", frames, torch.from_numpy(a).cuda(), torch.from_numpy(r).cuda(), torch.from_numpy(term).cuda(),
+                          torch.from_numpy(isw).cuda(), 0.99, False, None, abs_err, None)
+        loss, g_ref, ae_ref, _, _ = qo.loss_and_grads(1, p, t, x[:, 0:4], x[:, 1:5], a, r, term, isw, emulate_bf16=emulate, isw_broadcast=on)
+        g = net.grads.cpu().numpy().astype(np.float64)
+        assert abs(net.loss.item() - loss) <= (3e-3 if emulate else 1e-4) * abs(loss), (on, net.loss.item(), loss)
+        assert np.linalg.norm(g - g_ref) <= tol_g * np.linalg.norm(g_ref), (on, np.linalg.norm(g - g_ref) / np.linalg.norm(g_ref))
+        assert np.abs(abs_err.cpu().numpy() - ae_ref).max() <= (2e-2 if emulate else 1e-4) * np.abs(ae_ref).max()      # |delta| is not weighted
+        got[on] = (net.loss.item(), g)
+    # the two forms really differ on this minibatch (so the switch is observable), and relate as the algebra says
+    assert abs(got[True][0] - got[False][0]) > 1e-3 * abs(got[False][0])
+
+
+def test_loss_and_gradients_other_hidden_width_bf16(mods):
+    """hidden = 256 (north_star's "fc256" as a configuration): the head runs as the two-kernel form instead of the fused
+    fc1_head_train_kernel<16> (hidden = 512); same tolerances against the oracle with the bf16 roundings emulated"""
+    _lib, game, qnet = mods
+    B, H = 48, 256
+    frames = _env_frames(game, B, 19)
+    net = qnet.QNetwork(hidden=H, max_batch=64, precision="bf16")
+    p = qo.init_params(H, False, seed=1) * np.float32(3.0)
+    t = qo.init_params(H, False, seed=2) * np.float32(3.0)
+    _set_params(net, p, t)
+    rng = np.random.default_rng(8)
+    a = rng.integers(0, 2, B).astype(np.uint8)
+    r = rng.choice(np.array([0.1, 3.0, -3.0], np.float32), B, p=[0.8, 0.1, 0.1])
+    term = (r == -3.0).astype(np.uint8)
+    net.loss_backward("nature", frames, torch.from_numpy(a).cuda(), torch.from_numpy(r).cuda(), torch.from_numpy(term).cuda())
+    x = frames.cpu().numpy()
+    loss, g_ref, *_ = qo.loss_and_grads(1, p, t, x[:, 0:4], x[:, 1:5], a, r, term, hidden=H, emulate_bf16=True)
+    g = net.grads.cpu().numpy().astype(np.float64)
+    assert abs(net.loss.item() - loss) <= 3e-3 * abs(loss)
+    Lo = qo.layout(H, False)
+    for name, v in Lo.items():
+        if name == "total":
+            continue
+        o, shp = v
+        sz = int(np.prod(shp))
+        assert np.linalg.norm(g[o:o + sz] - g_ref[o:o + sz]) <= 1.5e-2 * np.linalg.norm(g_ref[o:o + sz]), name
