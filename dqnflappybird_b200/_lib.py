@@ -116,6 +116,7 @@ _SIGNATURES = {
     "fb_debug_poison_packed": ([_vp, C.c_int, _vp], C.c_int),
     "fb_qnet_use_graphs": ([_vp, C.c_int], C.c_int),
     "fb_qnet_set_conv1_mode": ([_vp, C.c_int], C.c_int),
+    "fb_qnet_set_fused_backward": ([_vp, C.c_int], C.c_int),
     "fb_qnet_param_count": ([_vp], C.c_int),
     "fb_qnet_layout": ([_vp, _i32p], C.c_int),
     "fb_qnet_forward": ([_vp, _f32p, _u8p, C.c_longlong, _i32p, C.c_int, _f32p, _vp], C.c_int),

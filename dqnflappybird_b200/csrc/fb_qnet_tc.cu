@@ -359,6 +359,30 @@ __global__ void pool_pack_kernel(const bf16 *z1, int B, bf16 *p2) {
     *reinterpret_cast<uint4 *>(p2 + ((size_t)b * kP2 + bh * kG2 + bw) * 128 + r * 64 + s * 32 + cg * 8) = m;
 }
 
+// eight channels of one pooling window: g = gradient of the pooled value, z[k] = the window's four activations (k = row-major
+// position); the gradient goes to the FIRST maximum (TF MaxPoolGrad) if it is positive (ReluGrad); bf16 out, 16 bytes a position
+__device__ __forceinline__ void unpool_route8(const float (&g)[8], const float (&z)[4][8], bf16 *dst, const size_t (&off)[4]) {
+    float o[4][8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        float m = fmaxf(fmaxf(z[0][i], z[1][i]), fmaxf(z[2][i], z[3][i]));
+        bool done = false;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            bool hit = !done && z[k][i] == m;
+            o[k][i] = (hit && z[k][i] > 0.f) ? g[i] : 0.f;
+            done |= hit;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { __nv_bfloat162 h = __floats2bfloat162_rn(o[k][2 * i], o[k][2 * i + 1]); w[i] = *reinterpret_cast<uint32_t *>(&h); }
+        *reinterpret_cast<uint4 *>(dst + off[k]) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 // dZ1 = unpool(dP2) * relu'(z1): the gradient goes to the first maximum of each window (TF MaxPoolGrad)
 __global__ void unpool_relu_kernel_tc(const bf16 *z1, const bf16 *dp2, int B, bf16 *dz1) {
     tc::pdl_wait();
@@ -385,25 +409,7 @@ __global__ void unpool_relu_kernel_tc(const bf16 *z1, const bf16 *dp2, int B, bf
 #pragma unroll
         for (int i = 0; i < 4; i++) { float2 f = __bfloat1622float2(h[i]); z[k][2 * i] = f.x; z[k][2 * i + 1] = f.y; }
     }
-    float o[4][8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        float m = fmaxf(fmaxf(z[0][i], z[1][i]), fmaxf(z[2][i], z[3][i]));
-        bool done = false;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            bool hit = !done && z[k][i] == m;
-            o[k][i] = (hit && z[k][i] > 0.f) ? g[i] : 0.f;
-            done |= hit;
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) { __nv_bfloat162 h = __floats2bfloat162_rn(o[k][2 * i], o[k][2 * i + 1]); w[i] = *reinterpret_cast<uint32_t *>(&h); }
-        *reinterpret_cast<uint4 *>(dz1 + base + off[k]) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
+    unpool_route8(g, z, dz1 + base, off);
 }
 
 // This kernel WRITES the operand copies that its stream successor (a conv kernel) fetches by TMA in its prologue, i.e.
@@ -871,6 +877,435 @@ __global__ void __launch_bounds__(256) finalize_grads_kernel(const FinalizeArgs 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ fused conv backward
+// conv3 data gradient -> ReLU mask -> conv2 data gradient -> un-pool + ReLU mask in ONE kernel: three dependent stages of the
+// step's critical path (three launches, two HBM/L2 round trips of dZ2 / dP2) become one.  A tile is TWO SAMPLES of the
+// 7-wide grid (98 rows of an M = 128 accumulator), so that everything a tile needs from its neighbours is rows that are zero
+// by construction (the pad ring of the grid): dZ2 of the tile never leaves the SM between the two GEMMs -- the epilogue of the
+// first writes it (bf16, masked) where TMA's 128-byte swizzle would have put it, fence.proxy.async, and the second GEMM reads
+// it through shifted descriptors like any slab.  dZ2 also goes to HBM once (the conv2 weight gradient and the conv2 bias
+// gradient contract over it); dP2 exists only in TMEM / registers.  Arithmetic and roundings are those of the three separate
+// kernels (bit-identical results: tests/test_qnet_tc_gpu.py::test_fused_backward_is_bit_identical).
+struct Bwd23Params {
+    int n_tiles, B;
+    const bf16 *a2;             // [B*49][64]   conv2 activations: ReLU mask of dZ2
+    bf16 *dz2;                  // [B*49][64]   out
+    const bf16 *z1;             // [B*441][32]  conv1 activations: pooling argmax + ReLU mask
+    bf16 *dz1;                  // [B*441][32]  out (invalid grid positions stay zero)
+};
+constexpr int kBwdRows = 2 * kP2;           // 98 rows of the 7-grid per tile
+
+template <int S>
+__global__ void __launch_bounds__(kConvThreads, 1) tc_bwd23_kernel(const __grid_constant__ CUtensorMap mapDz3, const __grid_constant__ CUtensorMap mapW3d,
+                                                                    const __grid_constant__ CUtensorMap mapW2d, const Bwd23Params g) {
+    constexpr uint32_t W3_BYTES = 9 * 64 * 128, W2_BYTES = 4 * 128 * 128, SLAB1 = 144 * 128, SLAB2 = 136 * 128;
+    static_assert(SLAB1 % 1024 == 0 && SLAB2 % 1024 == 0, "swizzle atoms are 1024-byte aligned");   // slab 2: taps reach 8 rows back, 128 + 8 rows
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[S], bar_empty[S], bar_b, bar_acc1_full, bar_acc1_empty, bar_acc2_full, bar_acc2_empty, bar_slab2;
+    __shared__ uint32_t tmem_slot;
+    uint8_t *smem_gen = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t smem_w3 = tc::smem_u32(smem_gen), smem_w2 = smem_w3 + W3_BYTES, smem_s1 = smem_w2 + W2_BYTES, smem_s2 = smem_s1 + S * SLAB1;
+    uint8_t *slab2_gen = smem_gen + W3_BYTES + W2_BYTES + S * SLAB1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        tc::tma_prefetch_desc(&mapDz3); tc::tma_prefetch_desc(&mapW3d); tc::tma_prefetch_desc(&mapW2d);
+        for (int s = 0; s < S; s++) { tc::mbar_init(tc::smem_u32(&bar_full[s]), 1); tc::mbar_init(tc::smem_u32(&bar_empty[s]), 1); }
+        tc::mbar_init(tc::smem_u32(&bar_b), 1);
+        tc::mbar_init(tc::smem_u32(&bar_acc1_full), 1); tc::mbar_init(tc::smem_u32(&bar_acc1_empty), 4);
+        tc::mbar_init(tc::smem_u32(&bar_acc2_full), 1); tc::mbar_init(tc::smem_u32(&bar_acc2_empty), 4);
+        tc::mbar_init(tc::smem_u32(&bar_slab2), 4);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tc::smem_u32(&tmem_slot), 256);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_slot, acc1 = tmem, acc2 = tmem + 64;
+    if (threadIdx.x == 0) {                          // the weights do not depend on the previous kernel: fetch them first
+        tc::mbar_expect_tx(tc::smem_u32(&bar_b), W3_BYTES + W2_BYTES);
+        for (int kb = 0; kb < 9; kb++) tc::tma_load_2d(smem_w3 + kb * (64 * 128), &mapW3d, kb * 64, 0, tc::smem_u32(&bar_b));
+        for (int kb = 0; kb < 4; kb++) tc::tma_load_2d(smem_w2 + kb * (128 * 128), &mapW2d, kb * 64, 0, tc::smem_u32(&bar_b));
+    }
+    tc::pdl_wait();
+    tc::pdl_launch();
+
+    if (warp == 0) {
+        const bool leader = tc::elect_one();
+        int i = 0;
+        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, i++) {
+            const int s = i % S;
+            tc::mbar_wait(tc::smem_u32(&bar_empty[s]), ((i / S) & 1) ^ 1u);
+            if (leader) {
+                const uint32_t full = tc::smem_u32(&bar_full[s]);
+                tc::mbar_expect_tx(full, SLAB1);
+                tc::tma_load_2d(smem_s1 + s * SLAB1, &mapDz3, 0, tile * kBwdRows - 8, full);    // rows before / after the tensor: zeros
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        const bool leader = tc::elect_one();
+        constexpr uint32_t idesc1 = tc::instr_desc_bf16(128, 64, 0, 0), idesc2 = tc::instr_desc_bf16(128, 128, 0, 0);
+        constexpr uint32_t dhi = tc::smem_desc_hi(1024, tc::kSwizzle128);
+        const uint32_t w3_lo = tc::smem_desc_lo(smem_w3, 16), w2_lo = tc::smem_desc_lo(smem_w2, 16);
+        const uint32_t s1_lo = tc::smem_desc_lo(smem_s1, 16), s2_lo = tc::smem_desc_lo(smem_s2, 16);
+        tc::mbar_wait(tc::smem_u32(&bar_b), 0);
+        int i = 0;
+        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, i++) {
+            const int s = i % S;
+            // ---- GEMM 1: dA2[p][c] = sum_{kh,kw,o} dZ3[p + (1-kh) 7 + (1-kw)][o] W3[kh][kw][c][o]   (slab row 0 = position -8)
+            tc::mbar_wait(tc::smem_u32(&bar_acc1_empty), (i & 1) ^ 1u);
+            tc::mbar_wait(tc::smem_u32(&bar_full[s]), (i / S) & 1);
+            tc::tc_fence_after();
+            if (leader) {
+#pragma unroll
+                for (int kb = 0; kb < 9; kb++) {
+                    const uint32_t tap = (uint32_t)(((1 - kb / 3) * kG2 + (1 - kb % 3) + 8) * 128) >> 4;
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        tc::umma_bf16_lohi(acc1, s1_lo + s * (SLAB1 >> 4) + tap + 2 * k, dhi, w3_lo + ((kb * 64 * 128 + k * 32) >> 4), dhi, idesc1, (kb | k) != 0);
+                }
+                tc::umma_commit(tc::smem_u32(&bar_empty[s]));
+                tc::umma_commit(tc::smem_u32(&bar_acc1_full));
+            }
+            __syncwarp();
+            // ---- GEMM 2: dP2[p][(r,s,c)] = sum_{dh,dw,o} dZ2[p - 7 dh - dw][o] W2d[(r,s,c)][(dh,dw),o]   (slab-2 row 8 = the tile's row 0)
+            tc::mbar_wait(tc::smem_u32(&bar_slab2), i & 1);
+            tc::mbar_wait(tc::smem_u32(&bar_acc2_empty), (i & 1) ^ 1u);
+            tc::tc_fence_after();
+            if (leader) {
+#pragma unroll
+                for (int kb = 0; kb < 4; kb++) {
+                    const uint32_t tap = (uint32_t)((8 - (kb >> 1) * kG2 - (kb & 1)) * 128) >> 4;
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        tc::umma_bf16_lohi(acc2, s2_lo + tap + 2 * k, dhi, w2_lo + ((kb * 128 * 128 + k * 32) >> 4), dhi, idesc2, (kb | k) != 0);
+                }
+                tc::umma_commit(tc::smem_u32(&bar_acc2_full));
+            }
+            __syncwarp();
+        }
+    } else {
+        const int q = warp & 3, r = q * 32 + lane;            // accumulator row = row r of the tile (TMEM lanes of warp % 4)
+        // zero rows of the second slab that no tile ever writes: the 8 rows before the tile (the previous sample's pad ring)
+        if (r < 8) {
+#pragma unroll
+            for (int c = 0; c < 8; c++) *reinterpret_cast<uint4 *>(slab2_gen + r * 128 + c * 16) = make_uint4(0, 0, 0, 0);
+        }
+        int i = 0;
+        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, i++) {
+            const long long grow = (long long)tile * kBwdRows + r;               // row of the [B*49] grid tensors
+            const bool in_tile = r < kBwdRows && grow < (long long)g.B * kP2;
+            const int p = r % kP2, bh = p / kG2, bw = p - bh * kG2;
+            const int b = (int)(tile * 2 + (r >= kP2 ? 1 : 0));
+            // ---- epilogue 1: dZ2 = dA2 * relu'(a2), zeros at invalid positions -> HBM and the second slab
+            tc::mbar_wait(tc::smem_u32(&bar_acc1_full), i & 1);
+            tc::tc_fence_after();
+            float v[64];
+            tc::tmem_ld32(acc1 + ((uint32_t)(q * 32) << 16), *reinterpret_cast<float(*)[32]>(&v[0]));
+            tc::tmem_ld32(acc1 + ((uint32_t)(q * 32) << 16) + 32, *reinterpret_cast<float(*)[32]>(&v[32]));
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_acc1_empty));
+            const bool ok = in_tile && bh < 5 && bw < 5;
+            uint4 outw[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) outw[c] = make_uint4(0, 0, 0, 0);
+            if (ok) {
+                const uint4 *am = reinterpret_cast<const uint4 *>(g.a2 + grow * 64);
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const uint4 raw = __ldg(am + c);
+                    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+                    uint32_t w[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const float2 a = __bfloat1622float2(h[k]);
+                        __nv_bfloat162 o = __floats2bfloat162_rn(a.x > 0.f ? v[c * 8 + 2 * k] : 0.f, a.y > 0.f ? v[c * 8 + 2 * k + 1] : 0.f);
+                        w[k] = *reinterpret_cast<uint32_t *>(&o);
+                    }
+                    outw[c] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            if (in_tile) {
+                uint4 *d = reinterpret_cast<uint4 *>(g.dz2 + grow * 64);
+#pragma unroll
+                for (int c = 0; c < 8; c++) d[c] = outw[c];
+            }
+            {   // slab-2 row r + 8, 16-byte chunk c at ((c ^ (row & 7)) << 4): the layout a TMA SWIZZLE_128B load would have produced
+                const int R = r + 8;
+                uint8_t *rowp = slab2_gen + R * 128;
+#pragma unroll
+                for (int c = 0; c < 8; c++) *reinterpret_cast<uint4 *>(rowp + ((c ^ (R & 7)) << 4)) = outw[c];
+            }
+            tc::fence_proxy_async();                      // generic-proxy writes -> visible to the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_slab2));
+            // ---- epilogue 2: dZ1 = unpool(dP2) * relu'(z1); row (b, bh, bw) holds the 2x2 block of pooled positions (2bh-1+rr, 2bw-1+ss)
+            tc::mbar_wait(tc::smem_u32(&bar_acc2_full), i & 1);
+            tc::tc_fence_after();
+#pragma unroll 1
+            for (int rs = 0; rs < 4; rs++) {
+                float gq[32];
+                tc::tmem_ld32(acc2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(rs * 32), gq);
+                if (rs == 3) {                             // accumulator drained: hand it back before the stores
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_acc2_empty));
+                }
+                const int ph = 2 * bh - 1 + (rs >> 1), pw = 2 * bw - 1 + (rs & 1);
+                if (in_tile && (unsigned)ph < 10u && (unsigned)pw < 10u) {
+                    const size_t base = ((size_t)b * kP1 + (2 * ph) * kG1 + 2 * pw) * kC1;
+                    const size_t off[4] = {0, (size_t)kC1, (size_t)kG1 * kC1, (size_t)kG1 * kC1 + kC1};
+#pragma unroll
+                    for (int cg = 0; cg < 4; cg++) {
+                        float gg[8], z[4][8];
+#pragma unroll
+                        for (int k = 0; k < 8; k++) gg[k] = __bfloat162float(__float2bfloat16(gq[cg * 8 + k]));      // dP2 was a bf16 tensor
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(g.z1 + base + off[k] + cg * 8));
+                            const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+#pragma unroll
+                            for (int e = 0; e < 4; e++) { const float2 f = __bfloat1622float2(h[e]); z[k][2 * e] = f.x; z[k][2 * e + 1] = f.y; }
+                        }
+                        unpool_route8(gg, z, g.dz1 + base + cg * 8, off);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem, 256);
+}
+
+template <int S>
+static cudaError_t launch_tc_bwd23(const CUtensorMap &mdz3, const CUtensorMap &mw3d, const CUtensorMap &mw2d, const Bwd23Params &g, int max_ctas,
+                                   cudaStream_t st) {
+    static bool configured = false;
+    auto kern = tc_bwd23_kernel<S>;
+    constexpr size_t smem = 9 * 64 * 128 + 4 * 128 * 128 + (size_t)S * 144 * 128 + 136 * 128 + 1024;
+    static_assert(smem <= 227 * 1024 && smem > kExclusiveSmem, "shared memory budget");
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int grid = g.n_tiles < max_ctas ? g.n_tiles : max_ctas;
+    return tc::launch_pdl(kern, dim3(grid), dim3(kConvThreads), smem, st, mdz3, mw3d, mw2d, g);
+}
+
+// ------------------------------------------------------------------------------------------------ fused conv2 + conv3 forward
+// conv 4x4 s2 + bias + ReLU -> conv 3x3 s1 + bias + ReLU in ONE kernel, the forward twin of tc_bwd23_kernel: a tile is two
+// samples of the 7-wide grid; the conv2 activations A2 are handed to the second GEMM through a hand-swizzled shared-memory slab
+// (and go to HBM only when a backward pass needs them); A3 leaves in TF flatten order.  One stage less on every forward's
+// critical path; arithmetic and roundings are those of the two separate kernels (bit-identical).
+struct Fwd23Params {
+    int n_tiles, B;
+    const float *bias2, *bias3;
+    bf16 *a2;                   // [B*49][64] or nullptr (acting / target forward: not needed)
+    bf16 *a3;                   // [B][25][64]
+};
+
+template <int S>
+__global__ void __launch_bounds__(kConvThreads, 1) tc_fwd23_kernel(const __grid_constant__ CUtensorMap mapP2, const __grid_constant__ CUtensorMap mapW2,
+                                                                    const __grid_constant__ CUtensorMap mapW3, const Fwd23Params g) {
+    // slab 2 (conv3's input): 8 zero rows + the tile's 98 rows + ...; the 3x3 taps reach 16 rows past an accumulator row, so the
+    // 128-row MMA reads 144 rows (rows 136..143 feed discarded accumulator rows only)
+    constexpr uint32_t W2_BYTES = 8 * 64 * 128, W3_BYTES = 9 * 64 * 128, HALF1 = 136 * 128, SLAB1 = 2 * HALF1, SLAB2 = 144 * 128;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[S], bar_empty[S], bar_b, bar_acc1_full, bar_acc1_empty, bar_acc2_full, bar_acc2_empty, bar_slab2;
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float bias_s[128];
+    uint8_t *smem_gen = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t smem_w2 = tc::smem_u32(smem_gen), smem_w3 = smem_w2 + W2_BYTES, smem_s1 = smem_w3 + W3_BYTES, smem_s2 = smem_s1 + S * SLAB1;
+    uint8_t *slab2_gen = smem_gen + W2_BYTES + W3_BYTES + S * SLAB1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    static_assert(SLAB2 % 1024 == 0 && SLAB1 % 1024 == 0, "swizzle atoms are 1024-byte aligned");
+
+    if (threadIdx.x == 0) {
+        tc::tma_prefetch_desc(&mapP2); tc::tma_prefetch_desc(&mapW2); tc::tma_prefetch_desc(&mapW3);
+        for (int s = 0; s < S; s++) { tc::mbar_init(tc::smem_u32(&bar_full[s]), 1); tc::mbar_init(tc::smem_u32(&bar_empty[s]), 1); }
+        tc::mbar_init(tc::smem_u32(&bar_b), 1);
+        tc::mbar_init(tc::smem_u32(&bar_acc1_full), 1); tc::mbar_init(tc::smem_u32(&bar_acc1_empty), 4);
+        tc::mbar_init(tc::smem_u32(&bar_acc2_full), 1); tc::mbar_init(tc::smem_u32(&bar_acc2_empty), 4);
+        tc::mbar_init(tc::smem_u32(&bar_slab2), 4);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tc::smem_u32(&tmem_slot), 128);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_slot, acc1 = tmem, acc2 = tmem + 64;
+    if (threadIdx.x == 0) {
+        tc::mbar_expect_tx(tc::smem_u32(&bar_b), W2_BYTES + W3_BYTES);
+        for (int kb = 0; kb < 8; kb++) tc::tma_load_2d(smem_w2 + kb * (64 * 128), &mapW2, kb * 64, 0, tc::smem_u32(&bar_b));
+        for (int kb = 0; kb < 9; kb++) tc::tma_load_2d(smem_w3 + kb * (64 * 128), &mapW3, kb * 64, 0, tc::smem_u32(&bar_b));
+    }
+    if (threadIdx.x >= 64) bias_s[threadIdx.x - 64] = threadIdx.x < 128 ? g.bias2[threadIdx.x - 64] : g.bias3[threadIdx.x - 128];
+    tc::pdl_wait();
+    tc::pdl_launch();
+    __syncthreads();
+
+    if (warp == 0) {
+        const bool leader = tc::elect_one();
+        int i = 0;
+        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, i++) {
+            const int s = i % S;
+            tc::mbar_wait(tc::smem_u32(&bar_empty[s]), ((i / S) & 1) ^ 1u);
+            if (leader) {
+                const uint32_t full = tc::smem_u32(&bar_full[s]);
+                tc::mbar_expect_tx(full, SLAB1);
+                tc::tma_load_2d(smem_s1 + s * SLAB1, &mapP2, 0, tile * kBwdRows, full);
+                tc::tma_load_2d(smem_s1 + s * SLAB1 + HALF1, &mapP2, 64, tile * kBwdRows, full);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        const bool leader = tc::elect_one();
+        constexpr uint32_t idesc = tc::instr_desc_bf16(128, 64, 0, 0);
+        constexpr uint32_t dhi = tc::smem_desc_hi(1024, tc::kSwizzle128);
+        const uint32_t w2_lo = tc::smem_desc_lo(smem_w2, 16), w3_lo = tc::smem_desc_lo(smem_w3, 16);
+        const uint32_t s1_lo = tc::smem_desc_lo(smem_s1, 16), s2_lo = tc::smem_desc_lo(smem_s2, 16);
+        tc::mbar_wait(tc::smem_u32(&bar_b), 0);
+        int i = 0;
+        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, i++) {
+            const int s = i % S;
+            // ---- GEMM 1 (conv2): K-block kb = (tap, column half): rows p + (tap >> 1) 7 + (tap & 1), channels 64 half ..
+            tc::mbar_wait(tc::smem_u32(&bar_acc1_empty), (i & 1) ^ 1u);
+            tc::mbar_wait(tc::smem_u32(&bar_full[s]), (i / S) & 1);
+            tc::tc_fence_after();
+            if (leader) {
+#pragma unroll
+                for (int kb = 0; kb < 8; kb++) {
+                    const int tp = kb >> 1;
+                    const uint32_t a_rel = (uint32_t)((kb & 1) * (int)HALF1 + ((tp >> 1) * kG2 + (tp & 1)) * 128) >> 4;
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        tc::umma_bf16_lohi(acc1, s1_lo + s * (SLAB1 >> 4) + a_rel + 2 * k, dhi, w2_lo + ((kb * 64 * 128 + k * 32) >> 4), dhi, idesc, (kb | k) != 0);
+                }
+                tc::umma_commit(tc::smem_u32(&bar_empty[s]));
+                tc::umma_commit(tc::smem_u32(&bar_acc1_full));
+            }
+            __syncwarp();
+            // ---- GEMM 2 (conv3): tap (kh,kw) reads slab-2 rows p + 8 + (kh-1) 7 + (kw-1) = p + kh 7 + kw
+            tc::mbar_wait(tc::smem_u32(&bar_slab2), i & 1);
+            tc::mbar_wait(tc::smem_u32(&bar_acc2_empty), (i & 1) ^ 1u);
+            tc::tc_fence_after();
+            if (leader) {
+#pragma unroll
+                for (int kb = 0; kb < 9; kb++) {
+                    const uint32_t tap = (uint32_t)(((kb / 3) * kG2 + (kb % 3)) * 128) >> 4;
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        tc::umma_bf16_lohi(acc2, s2_lo + tap + 2 * k, dhi, w3_lo + ((kb * 64 * 128 + k * 32) >> 4), dhi, idesc, (kb | k) != 0);
+                }
+                tc::umma_commit(tc::smem_u32(&bar_acc2_full));
+            }
+            __syncwarp();
+        }
+    } else {
+        const int q = warp & 3, r = q * 32 + lane;
+        if (r < 8) {
+#pragma unroll
+            for (int c = 0; c < 8; c++) *reinterpret_cast<uint4 *>(slab2_gen + r * 128 + c * 16) = make_uint4(0, 0, 0, 0);
+        }
+        int i = 0;
+        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, i++) {
+            const long long grow = (long long)tile * kBwdRows + r;
+            const bool in_tile = r < kBwdRows && grow < (long long)g.B * kP2;
+            const int p = r % kP2, oh = p / kG2, ow = p - oh * kG2;
+            const int b = (int)(tile * 2 + (r >= kP2 ? 1 : 0));
+            const bool ok = in_tile && oh < 5 && ow < 5;
+            // ---- epilogue 1: A2 = relu(conv2 + b2), zeros at invalid positions
+            tc::mbar_wait(tc::smem_u32(&bar_acc1_full), i & 1);
+            tc::tc_fence_after();
+            float v[64];
+            tc::tmem_ld32(acc1 + ((uint32_t)(q * 32) << 16), *reinterpret_cast<float(*)[32]>(&v[0]));
+            tc::tmem_ld32(acc1 + ((uint32_t)(q * 32) << 16) + 32, *reinterpret_cast<float(*)[32]>(&v[32]));
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_acc1_empty));
+            const float keep = ok ? 1.f : 0.f;
+            uint4 outw[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const float4 b0 = reinterpret_cast<const float4 *>(bias_s)[2 * c], b1 = reinterpret_cast<const float4 *>(bias_s)[2 * c + 1];
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                uint32_t w[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    __nv_bfloat162 o = __floats2bfloat162_rn(fmaxf(v[c * 8 + 2 * k] + bb[2 * k], 0.f) * keep, fmaxf(v[c * 8 + 2 * k + 1] + bb[2 * k + 1], 0.f) * keep);
+                    w[k] = *reinterpret_cast<uint32_t *>(&o);
+                }
+                outw[c] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            if (in_tile && g.a2 != nullptr) {
+                uint4 *d = reinterpret_cast<uint4 *>(g.a2 + grow * 64);
+#pragma unroll
+                for (int c = 0; c < 8; c++) d[c] = outw[c];
+            }
+            {
+                const int R = r + 8;
+                uint8_t *rowp = slab2_gen + R * 128;
+#pragma unroll
+                for (int c = 0; c < 8; c++) *reinterpret_cast<uint4 *>(rowp + ((c ^ (R & 7)) << 4)) = outw[c];
+            }
+            tc::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_slab2));
+            // ---- epilogue 2: A3 = relu(conv3 + b3), dense [B][25][64]
+            tc::mbar_wait(tc::smem_u32(&bar_acc2_full), i & 1);
+            tc::tc_fence_after();
+            tc::tmem_ld32(acc2 + ((uint32_t)(q * 32) << 16), *reinterpret_cast<float(*)[32]>(&v[0]));
+            tc::tmem_ld32(acc2 + ((uint32_t)(q * 32) << 16) + 32, *reinterpret_cast<float(*)[32]>(&v[32]));
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_acc2_empty));
+            float b3[64];
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                const float4 t4 = reinterpret_cast<const float4 *>(bias_s + 64)[c];
+                b3[4 * c] = t4.x; b3[4 * c + 1] = t4.y; b3[4 * c + 2] = t4.z; b3[4 * c + 3] = t4.w;
+            }
+            if (ok) {
+                uint4 *d = reinterpret_cast<uint4 *>(g.a3 + ((size_t)b * 25 + oh * 5 + ow) * 64);
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        __nv_bfloat162 o = __floats2bfloat162_rn(fmaxf(v[c * 8 + 2 * k] + b3[c * 8 + 2 * k], 0.f), fmaxf(v[c * 8 + 2 * k + 1] + b3[c * 8 + 2 * k + 1], 0.f));
+                        w[k] = *reinterpret_cast<uint32_t *>(&o);
+                    }
+                    d[c] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem, 128);
+}
+
+template <int S>
+static cudaError_t launch_tc_fwd23(const CUtensorMap &mp2, const CUtensorMap &mw2, const CUtensorMap &mw3, const Fwd23Params &g, int max_ctas,
+                                   cudaStream_t st) {
+    static bool configured = false;
+    auto kern = tc_fwd23_kernel<S>;
+    constexpr size_t smem = 8 * 64 * 128 + 9 * 64 * 128 + (size_t)S * 2 * 136 * 128 + 144 * 128 + 1024;
+    static_assert(smem <= 227 * 1024 && smem > kExclusiveSmem, "shared memory budget");
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int grid = g.n_tiles < max_ctas ? g.n_tiles : max_ctas;
+    return tc::launch_pdl(kern, dim3(grid), dim3(kConvThreads), smem, st, mp2, mw2, mw3, g);
+}
+
 // ------------------------------------------------------------------------------------------------ TMA maps
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
@@ -960,6 +1395,8 @@ struct TcState {
     cudaEvent_t ev[16];
     std::vector<GraphEntry> graphs;
     int use_graph;
+    int fuse_fwd;               // 1 (default): conv2 + conv3 forward as one kernel (also FB_TC_FUSE_FWD)
+    int fuse_bwd;               // 1 (default): conv3 / conv2 data gradients and the un-pool as one kernel (also FB_TC_FUSE_BWD)
     int conv1_mode;             // 2 (default): pooled epilogue, slab from u8 when no backward follows; 1: slab always from X2;
                                 // 0: separate pack_x2 / conv1 / pool_pack kernels
 };
@@ -1127,6 +1564,8 @@ int tc_state_create(fb_qnet *n) {
     }
     for (auto &e : t->ev) FB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     t->use_graph = 1;
+    { const char *e = getenv("FB_TC_FUSE_BWD"); t->fuse_bwd = (e && e[0] == '0') ? 0 : 1; }
+    { const char *e = getenv("FB_TC_FUSE_FWD"); t->fuse_fwd = (e && e[0] == '0') ? 0 : 1; }
     { const char *e = getenv("FB_TC_CONV1_MODE"); t->conv1_mode = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }
     n->tc = t;
     return FB_OK;
@@ -1242,8 +1681,13 @@ static int tc_forward_impl(fb_qnet *n, int slot, int w, const float *params_dev,
     } else {
         FB_CUDA_OK((launch_tc_conv1_fused<4, false>(p->x2_s[w], wm.w1p, Conv1FusedParams{fv, B, params_dev + L.b1, nullptr, f.p2}, t->n_sms, st)));
     }
-    FB_CUDA_OK((launch_tc_conv<64, kSlab2, 2, 8, 3, 1>(p->p2_s[w], wm.w2p, p->conv2, t->n_sms, EpiGrid7{f.a2, params_dev + L.b2, P2}, st)));
-    FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4, 1>(p->a2_s[w], wm.w3p, p->conv3, t->n_sms, EpiConv3{f.a3, params_dev + L.b3, P2}, st)));
+    if (t->fuse_fwd) {
+        FB_CUDA_OK((launch_tc_fwd23<2>(p->p2_s[w], wm.w2p, wm.w3p, Fwd23Params{(B + 1) / 2, B, params_dev + L.b2, params_dev + L.b3, keep ? f.a2 : nullptr, f.a3},
+                                       t->n_sms, st)));
+    } else {
+        FB_CUDA_OK((launch_tc_conv<64, kSlab2, 2, 8, 3, 1>(p->p2_s[w], wm.w2p, p->conv2, t->n_sms, EpiGrid7{f.a2, params_dev + L.b2, P2}, st)));
+        FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4, 1>(p->a2_s[w], wm.w3p, p->conv3, t->n_sms, EpiConv3{f.a3, params_dev + L.b3, P2}, st)));
+    }
     FB_CUDA_OK((launch_tc_gemm<128, 2>(p->a3_k[w], wm.wf1n, p->fc1, dim3((B + 127) / 128, L.hidden / 128, p->sf),
                                        EpiStoreF32{f.parth, B, L.hidden, (size_t)n->max_batch * L.hidden}, st)));
     if (join) FB_CUDA_OK(cudaStreamWaitEvent(st, join, 0));
@@ -1349,15 +1793,25 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     FB_CUDA_OK(colsum_on(t->dz3, t->bp3, P2, 64, kChunk23, c23));
     AdamDev ad{a.ad.on, const_cast<float *>(a.params), a.ad.m, a.ad.v, a.ad.beta1, a.ad.beta2, a.ad.eps, a.ad.grad_scale, t->adam_pow + 2};
     FB_CUDA_OK((launch_tc_wgrad<64, 5, kSlabW3, 1, 6>(p->a2_w, p->dz3_b, p->conv3_w, p->s3, EpiStoreF32{t->part3, 640, 64, (size_t)640 * 64}, sx)));
-    FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4, 1>(p->dz3_s, wm.w3d, p->conv3_d, t->n_sms, EpiConv3Dgrad{t->dz2, f.a2, P2}, st)));
-    FB_CUDA_OK(fork(st, sx));
-    FB_CUDA_OK(cudaStreamWaitEvent(sy, t->ev[e - 1], 0));              // sy: after the conv3 data gradient (dz2 complete)
-    FB_CUDA_OK(colsum_on(t->dz2, t->bp2, P2, 64, kChunk23, c23));
-    FB_CUDA_OK((launch_tc_wgrad<64, 4, kSlabW2, 2, 4>(p->p2_w, p->dz2_b, p->conv2_w, p->s2, EpiStoreF32{t->part2, 512, 64, (size_t)512 * 64}, sx)));
-    FB_CUDA_OK((launch_tc_conv<128, kSlab2, 1, 4, 4, 1>(p->dz2_s, wm.w2d, p->conv2_d, t->n_sms, EpiStoreBf16{t->dp2, P2, 128}, st)));
-    FB_CUDA_OK(tc::launch_pdl(unpool_relu_kernel_tc, dim3((unsigned)(((size_t)B * 400 + 255) / 256)), dim3(256), 0, st, f.z1, t->dp2, B, t->dz1));
-    FB_CUDA_OK(fork(st, sy));                                           // sy: after the un-pool (dz1 complete)
-    FB_CUDA_OK(colsum_on(t->dz1, t->bp1, P1, 32, kChunk1, c1));
+    if (t->fuse_bwd) {
+        // conv3 data gradient + ReLU mask + conv2 data gradient + un-pool in one kernel (tc_bwd23_kernel)
+        FB_CUDA_OK((launch_tc_bwd23<2>(p->dz3_s, wm.w3d, wm.w2d, Bwd23Params{(B + 1) / 2, B, f.a2, t->dz2, f.z1, t->dz1}, t->n_sms, st)));
+        FB_CUDA_OK(fork(st, sx));
+        FB_CUDA_OK(cudaStreamWaitEvent(sy, t->ev[e - 1], 0));          // sx, sy: dz2 and dz1 complete
+        FB_CUDA_OK(colsum_on(t->dz1, t->bp1, P1, 32, kChunk1, c1));
+        FB_CUDA_OK(colsum_on(t->dz2, t->bp2, P2, 64, kChunk23, c23));
+        FB_CUDA_OK((launch_tc_wgrad<64, 4, kSlabW2, 2, 4>(p->p2_w, p->dz2_b, p->conv2_w, p->s2, EpiStoreF32{t->part2, 512, 64, (size_t)512 * 64}, sx)));
+    } else {
+        FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4, 1>(p->dz3_s, wm.w3d, p->conv3_d, t->n_sms, EpiConv3Dgrad{t->dz2, f.a2, P2}, st)));
+        FB_CUDA_OK(fork(st, sx));
+        FB_CUDA_OK(cudaStreamWaitEvent(sy, t->ev[e - 1], 0));          // sy: after the conv3 data gradient (dz2 complete)
+        FB_CUDA_OK(colsum_on(t->dz2, t->bp2, P2, 64, kChunk23, c23));
+        FB_CUDA_OK((launch_tc_wgrad<64, 4, kSlabW2, 2, 4>(p->p2_w, p->dz2_b, p->conv2_w, p->s2, EpiStoreF32{t->part2, 512, 64, (size_t)512 * 64}, sx)));
+        FB_CUDA_OK((launch_tc_conv<128, kSlab2, 1, 4, 4, 1>(p->dz2_s, wm.w2d, p->conv2_d, t->n_sms, EpiStoreBf16{t->dp2, P2, 128}, st)));
+        FB_CUDA_OK(tc::launch_pdl(unpool_relu_kernel_tc, dim3((unsigned)(((size_t)B * 400 + 255) / 256)), dim3(256), 0, st, f.z1, t->dp2, B, t->dz1));
+        FB_CUDA_OK(fork(st, sy));                                       // sy: after the un-pool (dz1 complete)
+        FB_CUDA_OK(colsum_on(t->dz1, t->bp1, P1, 32, kChunk1, c1));
+    }
     if (a.ad.on) {                                                      // last on sy: after the fc1 weight gradient (sx) and the fc1 data gradient
         FB_CUDA_OK(cudaStreamWaitEvent(sy, t->ev[e_fc1w], 0));
         adam_wf1_kernel<<<4 * t->n_sms, 256, 0, sy>>>(L, a.grads, ad, t->pw[0]);
@@ -1390,6 +1844,13 @@ extern "C" int fb_qnet_set_conv1_mode(fb_qnet *n, int mode) {
     for (auto &g : n->tc->graphs) destroy_entry(g);
     n->tc->graphs.clear();
     return FB_OK;
+}
+
+extern "C" int fb_qnet_set_fused_backward(fb_qnet *n, int on) {
+    FB_REQUIRE(n != nullptr && n->tc != nullptr, "fb_qnet_set_fused_backward: needs FB_PRECISION_BF16");
+    n->tc->fuse_bwd = (on & 1) ? 1 : 0;
+    n->tc->fuse_fwd = (on & 2) || on == 1 ? 1 : 0;
+    return tc_drop_graphs(n);
 }
 
 extern "C" int fb_qnet_use_graphs(fb_qnet *n, int enable) {

@@ -176,6 +176,9 @@ int fb_qnet_use_graphs(fb_qnet *net, int enable);
  * frames -- neither the bf16 input matrix nor the conv1 activations go through HBM; 1: pooled epilogue, input always via the
  * materialised matrix; 0: three separate kernels (conversion, conv1, pooling).  Results are bit-identical in all modes. */
 int fb_qnet_set_conv1_mode(fb_qnet *net, int mode);
+/* FB_PRECISION_BF16 only: 1 (default, also FB_TC_FUSE_BWD): the conv3 data gradient, its ReLU mask, the conv2 data gradient and the
+ * un-pool run as ONE kernel whose intermediate never leaves the SM; 0: three kernels.  Results are bit-identical. */
+int fb_qnet_set_fused_backward(fb_qnet *net, int on);
 int fb_qnet_param_count(const fb_qnet *net);
 int fb_qnet_layout(const fb_qnet *net, int32_t *out16_host);
 

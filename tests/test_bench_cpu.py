@@ -18,7 +18,11 @@ def test_reference_arm_prints_the_contract_line():
     assert len(r.stdout.strip().splitlines()) == 1          # stdout carries the JSON line and nothing else
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["higher_is_better"] is True
-    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    from oracle import ref_verbatim as rv
+    kind = "reference" if rv.available() else "port"     # baseline/_ref staged by build(): the reference itself, verbatim
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == kind and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["c_port"]["kind"] == "port" and line["cpu_baseline"]["c_port"]["value"] > line["value"] * (1 if kind == "reference" else 0)
+    assert "30 frames/s" in line["cpu_baseline"]["as_shipped"]
     assert line["e2e"] == {"value": line["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     import bench
     assert line["metric"] == bench.METRIC and line["config"]["workload"] == bench.WORKLOAD
@@ -63,3 +67,23 @@ def test_oracle_bf16_emulation_is_close_to_exact_and_rounds_where_the_device_doe
     l1, g1, *_ = qo.loss_and_grads(1, p, p, x[:, 0:4], x[:, 1:5], a, r, term, emulate_bf16=True)
     assert abs(l0 - l1) <= 5e-2 * abs(l0)
     assert np.linalg.norm(g1 - g0) <= 0.2 * np.linalg.norm(g0)
+
+
+def test_reference_runs_verbatim_and_agrees_with_the_port():
+    """baseline/_ref (staged by build() from /root/reference): the reference's env module on the pygame shim, its clock
+    neutralised, gives the same rewards / terminals as the C port driven with the same gaps is checked in test_oracle_env;
+    here: the staging is complete, the worker protocol works, and the reference's PER classes load and sample"""
+    import pytest
+    from oracle import ref_verbatim as rv
+    if not rv.available():
+        if not rv.stage():
+            pytest.skip("no reference checkout and baseline/_ref not staged")
+    assert rv.available()
+    segs = rv.env_segments(2, 12, 2)
+    assert len(segs) == 2 and all(t > 0 for t in segs)
+    SumTree, Memory = rv.load_per_classes()
+    mem = Memory(64)
+    for i in range(64):
+        mem.store((i,))
+    idx, batch, w = mem.sample(8)
+    assert len(idx) == 8 and w.shape == (8, 1) and np.all(w > 0)

@@ -398,3 +398,30 @@ def test_loss_and_gradients_other_hidden_width_bf16(mods):
         o, shp = v
         sz = int(np.prod(shp))
         assert np.linalg.norm(g[o:o + sz] - g_ref[o:o + sz]) <= 1.5e-2 * np.linalg.norm(g_ref[o:o + sz]), name
+
+
+@pytest.mark.parametrize("B,variant,dueling", [(33, "nature", False), (70, "double", True), (300, "nature", False), (700, "vanilla", False)])
+def test_fused_backward_is_bit_identical(mods, B, variant, dueling):
+    """tc_bwd23_kernel (conv3 data gradient + ReLU mask + conv2 data gradient + un-pool in one kernel, dZ2 handed from the
+    first GEMM's epilogue to the second through a hand-swizzled shared-memory slab) against the three separate kernels:
+    identical gradients, bit for bit.  Odd minibatch (last tile = one sample), one tile per CTA, and several tiles per CTA
+    (the slab ring and both accumulators are reused: 350 tiles on 148 CTAs)."""
+    _lib, game, qnet = mods
+    frames = _env_frames(game, B, 23)
+    nets = [qnet.QNetwork(max_batch=B, seed=2, dueling=dueling, precision="bf16") for _ in range(2)]
+    for n in nets:
+        n.params.mul_(4.0); n.target.mul_(4.0)
+    _lib.check(_lib.lib().fb_qnet_set_fused_backward(nets[1]._h, 0), "fb_qnet_set_fused_backward")
+    # (switch 0 also turns off the forward twin, tc_fwd23_kernel: conv2 + conv3 as one kernel)
+    q = [n.forward(qnet.FrameBatch.from_stack(frames, 1)) for n in nets]
+    assert torch.isfinite(q[0]).all() and torch.equal(q[0], q[1])
+    rng = np.random.default_rng(3)
+    a = torch.from_numpy(rng.integers(0, 2, B).astype(np.uint8)).cuda()
+    r = torch.from_numpy(rng.choice(np.array([0.1, 3.0, -3.0], np.float32), B)).cuda()
+    term = (r == -3.0).to(torch.uint8)
+    for rep in range(3):                       # eager, eager, graph replay
+        for n in nets:
+            n.loss_backward(variant, frames, a, r, term, loss_sum=(variant == "vanilla"))
+        assert torch.isfinite(nets[0].grads).all()
+        assert torch.equal(nets[0].grads, nets[1].grads) and nets[0].loss.item() == nets[1].loss.item(), rep
+    assert nets[0].grads.abs().max().item() > 0
