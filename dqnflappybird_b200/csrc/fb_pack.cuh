@@ -3,6 +3,7 @@
 // whoever updates a parameter also refreshes its operand copies and no pack kernel runs in steady state.
 #pragma once
 #include "fb_qnet.cuh"
+#include "fb_tc.cuh"
 
 using bf16 = __nv_bfloat16;
 
@@ -14,10 +15,12 @@ struct PackedWeights {
     bf16 *wf1n;     // [1600][H]   k, n   (as stored)           fc1 forward B (MN-major) and fc1 dgrad Bt
     bf16 *w3d;      // [64][576]   c, (kh, kw, o)               conv3 dgrad    Bt
     bf16 *w2d;      // [128][256]  (r, s, c), (tap, o)          conv2 dgrad    Bt
+    int f16;        // operand format of the copies: 0 bf16, 1 fp16 (the pointers are 16-bit storage either way)
 };
 // parameter i (TF variable order) -> its bf16 operand copies
 __device__ __forceinline__ void scatter_packed(int i, float val, const QnetLayout &L, const PackedWeights &pw, int fwd_only) {
-    const bf16 v = __float2bfloat16(val);
+    const unsigned short bits = tc::pack1(val, pw.f16);
+    const bf16 v = *reinterpret_cast<const bf16 *>(&bits);
     if (i < L.b1) {                         // W1 [kh][kw][c][n]
         int e = i - L.w1, n = e & 31, c = (e >> 5) & 3, kw = (e >> 7) & 7, kh = e >> 10;
         int k = ((kh >> 2) * 2 + (kw >> 2)) * 64 + (kh & 3) * 16 + (kw & 3) * 4 + c;

@@ -422,8 +422,9 @@ extern "C" int fb_qnet_destroy(fb_qnet *n) {
 }
 
 extern "C" int fb_qnet_set_precision(fb_qnet *n, int precision) {
-    FB_REQUIRE(n != nullptr && (precision == FB_PRECISION_FP32 || precision == FB_PRECISION_BF16), "fb_qnet_set_precision: bad argument");
-    if (precision == FB_PRECISION_BF16) { int rc = tc_state_create(n); if (rc) return rc; }
+    FB_REQUIRE(n != nullptr && (precision == FB_PRECISION_FP32 || precision == FB_PRECISION_BF16 || precision == FB_PRECISION_FP16),
+               "fb_qnet_set_precision: bad argument");
+    if (precision != FB_PRECISION_FP32) { int rc = tc_state_create(n); if (rc) return rc; rc = tc_set_format(n, precision == FB_PRECISION_FP16); if (rc) return rc; }
     n->precision = precision;
     n->packed_src[0] = n->packed_src[1] = nullptr;
     return FB_OK;
@@ -469,14 +470,14 @@ extern "C" int fb_qnet_forward(fb_qnet *n, const float *params_dev, const uint8_
     FB_REQUIRE(n && params_dev && frames_dev && chan_off && q_out_dev && batch > 0, "fb_qnet_forward: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     int slot = 0;
-    if (n->precision == FB_PRECISION_BF16) {
+    if (tc_precision(n->precision)) {
         int rc = tc_slot_for(n, params_dev, -1, st, &slot); if (rc) return rc;
         return tc_forward_chunks(n, slot, params_dev, frames_dev, sample_stride, chan_off, batch, q_out_dev, st);
     }
     for (int b0 = 0; b0 < batch; b0 += n->max_batch) {
         int B = min(n->max_batch, batch - b0);
         FrameView fv = make_view(frames_dev + (size_t)b0 * sample_stride, sample_stride, chan_off);
-        int rc = n->precision == FB_PRECISION_BF16 ? tc_forward(n, slot, 0, params_dev, fv, B, q_out_dev + (size_t)b0 * 2, st)
+        int rc = tc_precision(n->precision) ? tc_forward(n, slot, 0, params_dev, fv, B, q_out_dev + (size_t)b0 * 2, st)
                                                    : forward_chunk(n, params_dev, fv, B, q_out_dev + (size_t)b0 * 2, st);
         if (rc) return rc;
     }
@@ -511,7 +512,7 @@ extern "C" int fb_qnet_loss_backward(fb_qnet *n, int variant, const float *param
     if (global_batch <= 0) global_batch = batch;
     FrameView fs = make_view(frames_dev, sample_stride, chan_off_s), fn = make_view(frames_dev, sample_stride, chan_off_next);
     int rc;
-    if (n->precision == FB_PRECISION_BF16) {
+    if (tc_precision(n->precision)) {
         TcTrainArgs ta{variant, params_dev, target_params_dev, fs, fn, actions_dev, rewards_dev, terminals_dev, is_weights_dev, B,
                        global_batch, gamma, loss_sum, grads_dev, loss_out_dev ? loss_out_dev : n->loss_dev, abs_err_out_dev,
                        q_target_out_dev};
@@ -548,7 +549,7 @@ extern "C" int fb_qnet_loss_backward(fb_qnet *n, int variant, const float *param
 extern "C" int fb_qnet_adam(fb_qnet *n, float *params_dev, const float *grads_dev, float *m_dev, float *v_dev, float alpha,
                             float beta1, float beta2, float eps, float grad_scale, void *stream) {
     FB_REQUIRE(n && params_dev && grads_dev && m_dev && v_dev, "fb_qnet_adam: NULL argument");
-    if (n->precision == FB_PRECISION_BF16)    // the same update, plus the bf16 operand copies of what it writes
+    if (tc_precision(n->precision))    // the same update, plus the bf16 operand copies of what it writes
         return tc_adam(n, params_dev, grads_dev, m_dev, v_dev, alpha, beta1, beta2, eps, grad_scale, (cudaStream_t)stream);
     size_t cnt = (size_t)n->L.total;
     adam_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params_dev, grads_dev, m_dev, v_dev, cnt, alpha, beta1, beta2, eps, grad_scale);
@@ -567,7 +568,7 @@ extern "C" int fb_qnet_train_step(fb_qnet *n, int variant, float *params_dev, co
                                   float *loss_out_dev, float *abs_err_out_dev, float *q_target_out_dev, float *m_dev, float *v_dev, float lr,
                                   float beta1, float beta2, float eps, float grad_scale, float beta1_power, float beta2_power, void *stream) {
     FB_REQUIRE(n && params_dev && m_dev && v_dev && grads_dev, "fb_qnet_train_step: NULL argument");
-    if (n->precision == FB_PRECISION_BF16 && n->tc != nullptr) {
+    if (tc_precision(n->precision) && n->tc != nullptr) {
         FB_REQUIRE(frames_dev && chan_off_s && chan_off_next && actions_dev && rewards_dev && terminals_dev, "fb_qnet_train_step: NULL argument");
         FB_REQUIRE(batch > 0 && batch <= n->max_batch, "fb_qnet_train_step: batch exceeds max_batch");
         FB_REQUIRE(variant >= 0 && variant <= 2, "fb_qnet_train_step: variant must be 0 (vanilla), 1 (nature) or 2 (double)");
@@ -598,7 +599,7 @@ extern "C" int fb_qnet_train_step_sampled(fb_qnet *n, const fb_step_sampling *sp
                "fb_qnet_train_step_sampled: NULL argument");
     const bool adam = m_dev != nullptr;            // without Adam slots: gradients only (the caller applies Adam, e.g. fb_dist_adam)
     const int batch = sp->batch;
-    if (n->precision == FB_PRECISION_BF16 && n->tc != nullptr) {
+    if (tc_precision(n->precision) && n->tc != nullptr) {
         FB_REQUIRE(batch > 0 && batch <= n->max_batch, "fb_qnet_train_step_sampled: batch exceeds max_batch");
         FB_REQUIRE(variant >= 0 && variant <= 2, "fb_qnet_train_step_sampled: variant must be 0 (vanilla), 1 (nature) or 2 (double)");
         FB_REQUIRE(variant == 0 || target_params_dev != nullptr, "fb_qnet_train_step_sampled: target parameters required");

@@ -49,7 +49,7 @@ struct TcState;                 // bf16 workspace, packed weights and TMA plans 
 struct fb_qnet {
     QnetLayout L;
     int max_batch;
-    int precision;              // FB_PRECISION_FP32 (CUDA-core FMA) or FB_PRECISION_BF16 (tcgen05, fp32 accumulate)
+    int precision;              // FB_PRECISION_FP32 (CUDA-core FMA), FB_PRECISION_BF16 or FB_PRECISION_FP16 (tcgen05, fp32 accumulate)
     // fp32 activations of the online net on s (kept for backward) and scratch for the other forwards
     float *z1, *p1, *a2, *a3, *h1, *q;          // [max_batch] x {12800, 3200, 1600, 1600, H, 2}
     float *q_next, *q_next_online;
@@ -90,7 +90,9 @@ int replay_launch_per_update(const fb_step_sampling &p, const float *abs_err_dev
 bool replay_is_sampler(const void *func);        // sample_uniform_kernel or per_sample_kernel
 bool replay_is_gather(const void *func);
 int replay_patch_nodes(cudaGraphExec_t exec, cudaGraphNode_t sampler, cudaGraphNode_t gather, const fb_step_sampling &p);
+inline bool tc_precision(int precision) { return precision == FB_PRECISION_BF16 || precision == FB_PRECISION_FP16; }
 int tc_state_create(fb_qnet *n);
+int tc_set_format(fb_qnet *n, int f16);          // operand format of the tensor-core path: 0 bf16, 1 fp16
 int tc_drop_graphs(fb_qnet *n);                 // captured steps embed the net's settings: drop them when one changes
 void tc_state_destroy(fb_qnet *n);
 int tc_pack_weights(fb_qnet *n, const float *params_dev, int slot /* 0 online, 1 target */, cudaStream_t st);

@@ -55,6 +55,7 @@ struct GemmParams {
     int a2_col[16][2];
     // shared-memory descriptor strides (bytes); runtime so that the self-test can probe encodings
     uint32_t lbo_a, sbo_a, kstep_a, lbo_b, sbo_b, kstep_b;
+    int f16;                    // operand format (tc::pack2): 0 bf16, 1 fp16
 };
 
 template <int BN, int MODE, class EP>
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
     } else if (warp == 1) {
         {
             const bool leader = tc::elect_one();
-            constexpr uint32_t idesc = tc::instr_desc_bf16(128, BN, MODE == 1, MODE != 0);
+            const uint32_t idesc = tc::instr_desc_16(128, BN, MODE == 1, MODE != 0, g.f16);
             const uint32_t ahi = tc::smem_desc_hi(g.sbo_a, tc::kSwizzle128), bhi = tc::smem_desc_hi(g.sbo_b, B_LAYOUT);
             const uint32_t a_lo0 = tc::smem_desc_lo(smem, g.lbo_a), b_lo0 = tc::smem_desc_lo(smem + A_BYTES, g.lbo_b);
             const uint32_t ka = g.kstep_a >> 4, kbs = g.kstep_b >> 4;
@@ -182,24 +183,21 @@ static cudaError_t launch_tc_gemm(const CUtensorMap &ma, const CUtensorMap &mb, 
 }
 
 // ------------------------------------------------------------------------------------------------ epilogues
-__device__ __forceinline__ void store_bf16x16(bf16 *dst, const float (&v)[16]) {
+__device__ __forceinline__ void store_bf16x16(bf16 *dst, const float (&v)[16], int f16) {
     uint32_t w[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-        w[i] = *reinterpret_cast<uint32_t *>(&h);
-    }
+    for (int i = 0; i < 8; i++) w[i] = tc::pack2(v[2 * i], v[2 * i + 1], f16);
     uint4 *d = reinterpret_cast<uint4 *>(dst);
     d[0] = make_uint4(w[0], w[1], w[2], w[3]);
     d[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
-__device__ __forceinline__ void load_bf16x16(const bf16 *src, float (&v)[16]) {
+__device__ __forceinline__ void load_bf16x16(const bf16 *src, float (&v)[16], int f16) {
     const uint4 *s = reinterpret_cast<const uint4 *>(src);
     uint4 a = s[0], b = s[1];
     uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&w[i]));
+        float2 f = tc::unpack2(w[i], f16);
         v[2 * i] = f.x; v[2 * i + 1] = f.y;
     }
 }
@@ -216,7 +214,7 @@ __device__ __forceinline__ void load_bias16(const float *bs, int col, float (&b)
     }
 }
 struct EpiConv1 {               // rows on the 21-grid -> Z1 [B*441][32] = relu(conv + b), zeros at invalid positions
-    bf16 *z1; const float *bias; int rows;
+    bf16 *z1; const float *bias; int rows, f16;
     __device__ void operator()(int row, int col, float (&v)[16], int, const float *bs) const {
         float b[16];
         load_bias16(bs, col, b);
@@ -225,11 +223,11 @@ struct EpiConv1 {               // rows on the 21-grid -> Z1 [B*441][32] = relu(
         const float keep = ((p / kG1) < 20 && (p % kG1) < 20) ? 1.f : 0.f;
 #pragma unroll
         for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i] + b[i], 0.f) * keep;
-        store_bf16x16(z1 + (size_t)row * kC1 + col, v);
+        store_bf16x16(z1 + (size_t)row * kC1 + col, v, f16);
     }
 };
 struct EpiGrid7 {               // conv2: rows on the 7-grid -> A2 [B*49][64], zeros at invalid positions
-    bf16 *out; const float *bias; int rows;
+    bf16 *out; const float *bias; int rows, f16;
     __device__ void operator()(int row, int col, float (&v)[16], int, const float *bs) const {
         float b[16];
         load_bias16(bs, col, b);
@@ -238,11 +236,11 @@ struct EpiGrid7 {               // conv2: rows on the 7-grid -> A2 [B*49][64], z
         const float keep = ((p / kG2) < 5 && (p % kG2) < 5) ? 1.f : 0.f;
 #pragma unroll
         for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i] + b[i], 0.f) * keep;
-        store_bf16x16(out + (size_t)row * 64 + col, v);
+        store_bf16x16(out + (size_t)row * 64 + col, v, f16);
     }
 };
 struct EpiConv3 {               // rows on the 7-grid -> dense A3 [B][25][64] (TF flatten order h,w,c)
-    bf16 *a3; const float *bias; int rows;
+    bf16 *a3; const float *bias; int rows, f16;
     __device__ void operator()(int row, int col, float (&v)[16], int, const float *bs) const {
         float bi[16];
         load_bias16(bs, col, bi);
@@ -251,58 +249,59 @@ struct EpiConv3 {               // rows on the 7-grid -> dense A3 [B][25][64] (T
         if (oh >= 5 || ow >= 5) return;
 #pragma unroll
         for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i] + bi[i], 0.f);
-        store_bf16x16(a3 + ((size_t)b * 25 + oh * 5 + ow) * 64 + col, v);
+        store_bf16x16(a3 + ((size_t)b * 25 + oh * 5 + ow) * 64 + col, v, f16);
     }
 };
 struct EpiFc1Dgrad {            // dA3 [B][1600] masked by relu(a3) -> dZ3 on the 7-grid [B*49][64]
-    bf16 *dz3; const bf16 *a3; int B;
+    bf16 *dz3; const bf16 *a3; int B, f16;
     static constexpr const float *bias = nullptr;
     __device__ void operator()(int row, int col, float (&v)[16], int, const float *) const {
         if (row >= B) return;
         float a[16];
-        load_bf16x16(a3 + (size_t)row * kFlat + col, a);
+        load_bf16x16(a3 + (size_t)row * kFlat + col, a, f16);
 #pragma unroll
         for (int i = 0; i < 16; i++) v[i] = a[i] > 0.f ? v[i] : 0.f;
         int pix = col >> 6, oh = pix / 5, ow = pix - oh * 5;
-        store_bf16x16(dz3 + ((size_t)row * kP2 + oh * kG2 + ow) * 64 + (col & 63), v);
+        store_bf16x16(dz3 + ((size_t)row * kP2 + oh * kG2 + ow) * 64 + (col & 63), v, f16);
     }
 };
 struct EpiConv3Dgrad {          // dA2 on the 7-grid masked by relu(a2) -> dZ2 [B*49][64], zeros at invalid positions
-    bf16 *dz2; const bf16 *a2; int rows;
+    bf16 *dz2; const bf16 *a2; int rows, f16;
     static constexpr const float *bias = nullptr;
     __device__ void operator()(int row, int col, float (&v)[16], int, const float *) const {
         if (row >= rows) return;
         int p = row % kP2;
         bool ok = (p / kG2) < 5 && (p % kG2) < 5;
         float a[16];
-        load_bf16x16(a2 + (size_t)row * 64 + col, a);
+        load_bf16x16(a2 + (size_t)row * 64 + col, a, f16);
 #pragma unroll
         for (int i = 0; i < 16; i++) v[i] = (ok && a[i] > 0.f) ? v[i] : 0.f;
-        store_bf16x16(dz2 + (size_t)row * 64 + col, v);
+        store_bf16x16(dz2 + (size_t)row * 64 + col, v, f16);
     }
 };
 struct EpiStoreBf16 {           // conv2 dgrad: dP2 [B*49][128]
-    bf16 *out; int rows, ld;
+    bf16 *out; int rows, ld, f16;
     static constexpr const float *bias = nullptr;
     __device__ void operator()(int row, int col, float (&v)[16], int, const float *) const {
         if (row >= rows) return;
-        store_bf16x16(out + (size_t)row * ld + col, v);
+        store_bf16x16(out + (size_t)row * ld + col, v, f16);
     }
 };
 struct EpiStoreF32 {            // weight-gradient partials [split][rows][ld] and the self-test
     float *out; int rows, ld; size_t split_stride;
+    float scale = 1.f;          // a power of two: un-scales gradients that were scaled for the fp16 operand format
     static constexpr const float *bias = nullptr;
     __device__ void operator()(int row, int col, float (&v)[16], int split, const float *) const {
         if (row >= rows) return;
         float4 *d = reinterpret_cast<float4 *>(out + (size_t)split * split_stride + (size_t)row * ld + col);
 #pragma unroll
-        for (int i = 0; i < 4; i++) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        for (int i = 0; i < 4; i++) d[i] = make_float4(v[4 * i] * scale, v[4 * i + 1] * scale, v[4 * i + 2] * scale, v[4 * i + 3] * scale);
     }
 };
 
 // ------------------------------------------------------------------------------------------------ glue kernels
 // u8 frames (FrameView) -> X2 [B*441][64]: block (bh,bw) of the input padded by 2, channel j = r*16 + s*4 + c
-__global__ void pack_x2_kernel(FrameView fv, int B, bf16 *x2) {
+__global__ void pack_x2_kernel(FrameView fv, int B, bf16 *x2, int f16) {
     tc::pdl_wait();
     tc::pdl_launch();
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -325,23 +324,16 @@ __global__ void pack_x2_kernel(FrameView fv, int B, bf16 *x2) {
 #pragma unroll
     for (int s = 0; s < 2; s++)
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            __nv_bfloat162 v = __floats2bfloat162_rn(px[s][2 * h], px[s][2 * h + 1]);
-            w[s * 2 + h] = *reinterpret_cast<uint32_t *>(&v);
-        }
+        for (int h = 0; h < 2; h++) w[s * 2 + h] = tc::pack2(px[s][2 * h], px[s][2 * h + 1], f16);
     *reinterpret_cast<uint4 *>(x2 + blk * 64 + r * 16 + sp * 8) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-__device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
-    uint4 r;
-    __nv_bfloat162 *pa = reinterpret_cast<__nv_bfloat162 *>(&a), *pb = reinterpret_cast<__nv_bfloat162 *>(&b), *pr = reinterpret_cast<__nv_bfloat162 *>(&r);
-#pragma unroll
-    for (int i = 0; i < 4; i++) pr[i] = __hmax2(pa[i], pb[i]);
-    return r;
+__device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b, int f16) {
+    return make_uint4(tc::max2(a.x, b.x, f16), tc::max2(a.y, b.y, f16), tc::max2(a.z, b.z, f16), tc::max2(a.w, b.w, f16));
 }
 
 // max_pool 2x2 (BrainDQN.py:128) + space-to-depth for conv2: Z1 (21-grid) -> P2 [B*49][128], channel j = r*64 + s*32 + c
-__global__ void pool_pack_kernel(const bf16 *z1, int B, bf16 *p2) {
+__global__ void pool_pack_kernel(const bf16 *z1, int B, bf16 *p2, int f16) {
     tc::pdl_wait();
     tc::pdl_launch();
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -354,14 +346,14 @@ __global__ void pool_pack_kernel(const bf16 *z1, int B, bf16 *p2) {
     uint4 m = make_uint4(0, 0, 0, 0);
     if ((unsigned)ph < 10u && (unsigned)pw < 10u) {
         const uint4 *src = reinterpret_cast<const uint4 *>(z1 + ((size_t)b * kP1 + (2 * ph) * kG1 + 2 * pw) * kC1 + cg * 8);
-        m = bf16x8_max(bf16x8_max(__ldg(src), __ldg(src + 4)), bf16x8_max(__ldg(src + kG1 * 4), __ldg(src + kG1 * 4 + 4)));
+        m = bf16x8_max(bf16x8_max(__ldg(src), __ldg(src + 4), f16), bf16x8_max(__ldg(src + kG1 * 4), __ldg(src + kG1 * 4 + 4), f16), f16);
     }
     *reinterpret_cast<uint4 *>(p2 + ((size_t)b * kP2 + bh * kG2 + bw) * 128 + r * 64 + s * 32 + cg * 8) = m;
 }
 
 // eight channels of one pooling window: g = gradient of the pooled value, z[k] = the window's four activations (k = row-major
 // position); the gradient goes to the FIRST maximum (TF MaxPoolGrad) if it is positive (ReluGrad); bf16 out, 16 bytes a position
-__device__ __forceinline__ void unpool_route8(const float (&g)[8], const float (&z)[4][8], bf16 *dst, const size_t (&off)[4]) {
+__device__ __forceinline__ void unpool_route8(const float (&g)[8], const float (&z)[4][8], bf16 *dst, const size_t (&off)[4], int f16) {
     float o[4][8];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -378,13 +370,13 @@ __device__ __forceinline__ void unpool_route8(const float (&g)[8], const float (
     for (int k = 0; k < 4; k++) {
         uint32_t w[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) { __nv_bfloat162 h = __floats2bfloat162_rn(o[k][2 * i], o[k][2 * i + 1]); w[i] = *reinterpret_cast<uint32_t *>(&h); }
+        for (int i = 0; i < 4; i++) w[i] = tc::pack2(o[k][2 * i], o[k][2 * i + 1], f16);
         *reinterpret_cast<uint4 *>(dst + off[k]) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
 // dZ1 = unpool(dP2) * relu'(z1): the gradient goes to the first maximum of each window (TF MaxPoolGrad)
-__global__ void unpool_relu_kernel_tc(const bf16 *z1, const bf16 *dp2, int B, bf16 *dz1) {
+__global__ void unpool_relu_kernel_tc(const bf16 *z1, const bf16 *dp2, int B, bf16 *dz1, int f16) {
     tc::pdl_wait();
     tc::pdl_launch();
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -396,20 +388,20 @@ __global__ void unpool_relu_kernel_tc(const bf16 *z1, const bf16 *dp2, int B, bf
     float g[8], z[4][8];
     {
         uint4 raw = __ldg(reinterpret_cast<const uint4 *>(dp2 + ((size_t)b * kP2 + bh * kG2 + bw) * 128 + r * 64 + s * 32 + cg * 8));
-        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+        const uint32_t *h = reinterpret_cast<const uint32_t *>(&raw);
 #pragma unroll
-        for (int i = 0; i < 4; i++) { float2 f = __bfloat1622float2(h[i]); g[2 * i] = f.x; g[2 * i + 1] = f.y; }
+        for (int i = 0; i < 4; i++) { float2 f = tc::unpack2(h[i], f16); g[2 * i] = f.x; g[2 * i + 1] = f.y; }
     }
     size_t base = ((size_t)b * kP1 + (2 * ph) * kG1 + 2 * pw) * kC1 + cg * 8;
     const size_t off[4] = {0, (size_t)kC1, (size_t)kG1 * kC1, (size_t)kG1 * kC1 + kC1};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         uint4 raw = __ldg(reinterpret_cast<const uint4 *>(z1 + base + off[k]));
-        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+        const uint32_t *h = reinterpret_cast<const uint32_t *>(&raw);
 #pragma unroll
-        for (int i = 0; i < 4; i++) { float2 f = __bfloat1622float2(h[i]); z[k][2 * i] = f.x; z[k][2 * i + 1] = f.y; }
+        for (int i = 0; i < 4; i++) { float2 f = tc::unpack2(h[i], f16); z[k][2 * i] = f.x; z[k][2 * i + 1] = f.y; }
     }
-    unpool_route8(g, z, dz1 + base, off);
+    unpool_route8(g, z, dz1 + base, off, f16);
 }
 
 // This kernel WRITES the operand copies that its stream successor (a conv kernel) fetches by TMA in its prologue, i.e.
@@ -448,7 +440,7 @@ __global__ void adam_pack_kernel(float *__restrict__ p, const float *__restrict_
 // column sums of bf16 matrices [rows][N] in row chunks -> part[chunk][N] (bias gradients; summed in order by
 // finalize_grads_kernel).  One launch covers all jobs; 16-byte loads, a warp reads whole rows.
 struct ColsumJob { const bf16 *x; float *part; int rows, N, chunk_rows, first_block; };
-struct ColsumJobs { ColsumJob j[3]; int njobs; };
+struct ColsumJobs { ColsumJob j[3]; int njobs, f16; };
 __global__ void __launch_bounds__(256) colsum_kernel(ColsumJobs jobs) {
     tc::pdl_wait();
     tc::pdl_launch();
@@ -467,9 +459,9 @@ __global__ void __launch_bounds__(256) colsum_kernel(ColsumJobs jobs) {
     for (int i = 0; i < 8; i++) acc[i] = 0.f;
     for (int r = r0 + rl; r < r1; r += rows_per_pass) {
         uint4 raw = __ldg(reinterpret_cast<const uint4 *>(jb.x + (size_t)r * jb.N) + v);
-        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+        const uint32_t *h = reinterpret_cast<const uint32_t *>(&raw);
 #pragma unroll
-        for (int i = 0; i < 4; i++) { float2 f = __bfloat1622float2(h[i]); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
+        for (int i = 0; i < 4; i++) { float2 f = tc::unpack2(h[i], jobs.f16); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
     }
     // lanes with equal (lane % vec) hold the same columns: butterfly over the other lane bits, then across warps
 #pragma unroll
@@ -497,10 +489,14 @@ constexpr int kMaxHeadCtas = 160;                   // fused head kernel: at mos
 // turns the beta powers kept in device memory into this step's alpha = lr sqrt(1 - beta2^t) / (1 - beta1^t) (fp32, the
 // host formula) and advances them; the step's last kernel reads alpha.  Nothing about a step is a launch argument.
 struct AdamPow { int on; float *pow /* beta1^t, beta2^t */, *alpha; float lr, beta1, beta2; };
+// operand format of the gradient tensors and the power of two they are scaled by (1 for bf16; fp16's exponent range is narrow:
+// dh1 and everything downstream of it carry the factor, the weight / bias gradients are un-scaled where they are finalised)
+struct GradFmt { int f16; float scale; };
 __global__ void __launch_bounds__(256) head_backward_tc_kernel(const float *__restrict__ h1, const float *__restrict__ dq,
                                                                const float *__restrict__ params, QnetLayout L, int B,
                                                                float *__restrict__ hp /* [G][H][4] */, float *__restrict__ hb /* [G][4] */,
-                                                               const float *__restrict__ loss_terms, bf16 *__restrict__ dh1, const AdamPow ap) {
+                                                               const float *__restrict__ loss_terms, bf16 *__restrict__ dh1, const AdamPow ap,
+                                                               const GradFmt gf) {
     tc::pdl_wait();
     tc::pdl_launch();
     if (ap.on && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
@@ -539,10 +535,10 @@ __global__ void __launch_bounds__(256) head_backward_tc_kernel(const float *__re
             g0 = fmaf(x, d0 - m, g0); g1 = fmaf(x, d1 - m, g1); gv = fmaf(x, d0 + d1, gv);
             g = (d0 - m) * w0 + (d1 - m) * w1 + (d0 + d1) * wv;
         }
-        g = x > 0.f ? g : 0.f;
-        bf16 gr = __float2bfloat16(g);
-        dh1[(size_t)b * H + j] = gr;
-        gb += __bfloat162float(gr);                  // the bias gradient sums what the weight-gradient GEMM sees
+        g = x > 0.f ? g * gf.scale : 0.f;
+        const unsigned short gr = tc::pack1(g, gf.f16);
+        reinterpret_cast<unsigned short *>(dh1)[(size_t)b * H + j] = gr;
+        gb += tc::round1(g, gf.f16);                 // the bias gradient sums what the weight-gradient GEMM sees (scaled)
     }
     red[rl][jl][0] = g0; red[rl][jl][1] = g1; red[rl][jl][2] = gv; red[rl][jl][3] = gb;
     __syncthreads();
@@ -669,7 +665,7 @@ __global__ void __launch_bounds__(128) fc1_head_warp_kernel(const float *__restr
 // gradient; the per-CTA partial sums [G][H][4], [G][4] are what finalize_grads_kernel adds in a fixed order.  Also carries the
 // fused-Adam alpha (AdamPow, as head_backward_tc_kernel did).  Replaces fc1_head_kernel + head_backward_tc_kernel on the
 // step's critical path.
-struct HeadBwd { bf16 *dh1; float *hp /* [G][H][4] */, *hb /* [G][4]: sum dq0, sum dq1, loss */; };
+struct HeadBwd { bf16 *dh1; float *hp /* [G][H][4] */, *hb /* [G][4]: sum dq0, sum dq1, loss */; GradFmt gf; };
 template <int JPL>
 __global__ void __launch_bounds__(128) fc1_head_train_kernel(const float *__restrict__ part, int splits, size_t split_stride,
                                                             const float *__restrict__ params, QnetLayout L, int B, float *__restrict__ q,
@@ -757,10 +753,9 @@ __global__ void __launch_bounds__(128) fc1_head_train_kernel(const float *__rest
                 g0[u] = fmaf(x[u], d0 - m, g0[u]); g1[u] = fmaf(x[u], d1 - m, g1[u]); gv[u] = fmaf(x[u], d0 + d1, gv[u]);
                 gh = (d0 - m) * w0[u] + (d1 - m) * w1[u] + (d0 + d1) * wv[u];
             }
-            gh = x[u] > 0.f ? gh : 0.f;
-            const bf16 gr = __float2bfloat16(gh);
-            o.dh1[(size_t)b * H + lane + 32 * u] = gr;
-            gb[u] += __bfloat162float(gr);            // the bias gradient sums what the weight-gradient GEMM sees
+            gh = x[u] > 0.f ? gh * o.gf.scale : 0.f;
+            reinterpret_cast<unsigned short *>(o.dh1)[(size_t)b * H + lane + 32 * u] = tc::pack1(gh, o.gf.f16);
+            gb[u] += tc::round1(gh, o.gf.f16);        // the bias gradient sums what the weight-gradient GEMM sees (scaled)
         }
     }
 #pragma unroll
@@ -787,6 +782,7 @@ struct FinalizeArgs {
     const float *hp, *hb;                           // head partials [G][H][4], [G][4] (dq sums, loss)
     int G;
     float *loss_out;
+    float inv_scale;                                // un-scales what came through the (scaled) gradient tensors
 };
 // With `ad.on` the same launch also applies Adam (fb_qnet_train_step): the CTA that has just summed 32 gradient elements
 // updates those parameters (W_fc1, whose gradient the fc1 GEMM wrote in place, is updated earlier by adam_wf1_kernel).
@@ -812,7 +808,7 @@ __global__ void __launch_bounds__(256) adam_wf1_kernel(QnetLayout L, const float
         *reinterpret_cast<float4 *>(ad.m + i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
         *reinterpret_cast<float4 *>(ad.v + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
 #pragma unroll
-        for (int k = 0; k < 2; k++) { __nv_bfloat162 h = __floats2bfloat162_rn(pp[2 * k], pp[2 * k + 1]); pk[k] = *reinterpret_cast<uint32_t *>(&h); }
+        for (int k = 0; k < 2; k++) pk[k] = tc::pack2(pp[2 * k], pp[2 * k + 1], pw.f16);
         *reinterpret_cast<uint2 *>(pw.wf1n + 4 * i4) = make_uint2(pk[0], pk[1]);
     }
 }
@@ -867,6 +863,7 @@ __global__ void __launch_bounds__(256) finalize_grads_kernel(const FinalizeArgs 
         float t = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; w++) t += red[w][lane];
+        if (i < L.bf1 + H) t *= a.inv_scale;         // conv / fc1 weights and biases: sums of scaled gradient tensors (the head's are not)
         grads[i] = t;
         if (ad.on) adam_one(i, t, ad.p, ad.m, ad.v, alpha, ad.beta1, ad.beta2, ad.eps, ad.grad_scale, L, pw);
     }
@@ -892,6 +889,7 @@ struct Bwd23Params {
     bf16 *dz2;                  // [B*49][64]   out
     const bf16 *z1;             // [B*441][32]  conv1 activations: pooling argmax + ReLU mask
     bf16 *dz1;                  // [B*441][32]  out (invalid grid positions stay zero)
+    int f16;
 };
 constexpr int kBwdRows = 2 * kP2;           // 98 rows of the 7-grid per tile
 
@@ -945,7 +943,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_bwd23_kernel(const __grid_
         }
     } else if (warp == 1) {
         const bool leader = tc::elect_one();
-        constexpr uint32_t idesc1 = tc::instr_desc_bf16(128, 64, 0, 0), idesc2 = tc::instr_desc_bf16(128, 128, 0, 0);
+        const uint32_t idesc1 = tc::instr_desc_16(128, 64, 0, 0, g.f16), idesc2 = tc::instr_desc_16(128, 128, 0, 0, g.f16);
         constexpr uint32_t dhi = tc::smem_desc_hi(1024, tc::kSwizzle128);
         const uint32_t w3_lo = tc::smem_desc_lo(smem_w3, 16), w2_lo = tc::smem_desc_lo(smem_w2, 16);
         const uint32_t s1_lo = tc::smem_desc_lo(smem_s1, 16), s2_lo = tc::smem_desc_lo(smem_s2, 16);
@@ -1016,13 +1014,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_bwd23_kernel(const __grid_
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
                     const uint4 raw = __ldg(am + c);
-                    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+                    const uint32_t *h = reinterpret_cast<const uint32_t *>(&raw);
                     uint32_t w[4];
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        const float2 a = __bfloat1622float2(h[k]);
-                        __nv_bfloat162 o = __floats2bfloat162_rn(a.x > 0.f ? v[c * 8 + 2 * k] : 0.f, a.y > 0.f ? v[c * 8 + 2 * k + 1] : 0.f);
-                        w[k] = *reinterpret_cast<uint32_t *>(&o);
+                        const float2 a = tc::unpack2(h[k], g.f16);
+                        w[k] = tc::pack2(a.x > 0.f ? v[c * 8 + 2 * k] : 0.f, a.y > 0.f ? v[c * 8 + 2 * k + 1] : 0.f, g.f16);
                     }
                     outw[c] = make_uint4(w[0], w[1], w[2], w[3]);
                 }
@@ -1061,15 +1058,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_bwd23_kernel(const __grid_
                     for (int cg = 0; cg < 4; cg++) {
                         float gg[8], z[4][8];
 #pragma unroll
-                        for (int k = 0; k < 8; k++) gg[k] = __bfloat162float(__float2bfloat16(gq[cg * 8 + k]));      // dP2 was a bf16 tensor
+                        for (int k = 0; k < 8; k++) gg[k] = tc::round1(gq[cg * 8 + k], g.f16);      // dP2 was a 16-bit tensor
 #pragma unroll
                         for (int k = 0; k < 4; k++) {
                             const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(g.z1 + base + off[k] + cg * 8));
-                            const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+                            const uint32_t *h = reinterpret_cast<const uint32_t *>(&raw);
 #pragma unroll
-                            for (int e = 0; e < 4; e++) { const float2 f = __bfloat1622float2(h[e]); z[k][2 * e] = f.x; z[k][2 * e + 1] = f.y; }
+                            for (int e = 0; e < 4; e++) { const float2 f = tc::unpack2(h[e], g.f16); z[k][2 * e] = f.x; z[k][2 * e + 1] = f.y; }
                         }
-                        unpool_route8(gg, z, g.dz1 + base + cg * 8, off);
+                        unpool_route8(gg, z, g.dz1 + base + cg * 8, off, g.f16);
                     }
                 }
                 __syncwarp();
@@ -1107,6 +1104,7 @@ struct Fwd23Params {
     const float *bias2, *bias3;
     bf16 *a2;                   // [B*49][64] or nullptr (acting / target forward: not needed)
     bf16 *a3;                   // [B][25][64]
+    int f16;
 };
 
 template <int S>
@@ -1165,7 +1163,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_fwd23_kernel(const __grid_
         }
     } else if (warp == 1) {
         const bool leader = tc::elect_one();
-        constexpr uint32_t idesc = tc::instr_desc_bf16(128, 64, 0, 0);
+        const uint32_t idesc = tc::instr_desc_16(128, 64, 0, 0, g.f16);
         constexpr uint32_t dhi = tc::smem_desc_hi(1024, tc::kSwizzle128);
         const uint32_t w2_lo = tc::smem_desc_lo(smem_w2, 16), w3_lo = tc::smem_desc_lo(smem_w3, 16);
         const uint32_t s1_lo = tc::smem_desc_lo(smem_s1, 16), s2_lo = tc::smem_desc_lo(smem_s2, 16);
@@ -1237,8 +1235,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_fwd23_kernel(const __grid_
                 uint32_t w[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    __nv_bfloat162 o = __floats2bfloat162_rn(fmaxf(v[c * 8 + 2 * k] + bb[2 * k], 0.f) * keep, fmaxf(v[c * 8 + 2 * k + 1] + bb[2 * k + 1], 0.f) * keep);
-                    w[k] = *reinterpret_cast<uint32_t *>(&o);
+                    w[k] = tc::pack2(fmaxf(v[c * 8 + 2 * k] + bb[2 * k], 0.f) * keep, fmaxf(v[c * 8 + 2 * k + 1] + bb[2 * k + 1], 0.f) * keep, g.f16);
                 }
                 outw[c] = make_uint4(w[0], w[1], w[2], w[3]);
             }
@@ -1277,8 +1274,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_fwd23_kernel(const __grid_
                     uint32_t w[4];
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        __nv_bfloat162 o = __floats2bfloat162_rn(fmaxf(v[c * 8 + 2 * k] + b3[c * 8 + 2 * k], 0.f), fmaxf(v[c * 8 + 2 * k + 1] + b3[c * 8 + 2 * k + 1], 0.f));
-                        w[k] = *reinterpret_cast<uint32_t *>(&o);
+                        w[k] = tc::pack2(fmaxf(v[c * 8 + 2 * k] + b3[c * 8 + 2 * k], 0.f), fmaxf(v[c * 8 + 2 * k + 1] + b3[c * 8 + 2 * k + 1], 0.f), g.f16);
                     }
                     d[c] = make_uint4(w[0], w[1], w[2], w[3]);
                 }
@@ -1395,6 +1391,7 @@ struct TcState {
     cudaEvent_t ev[16];
     std::vector<GraphEntry> graphs;
     int use_graph;
+    int f16;                    // operand format of every 16-bit tensor of this net: 0 bf16, 1 fp16 (FB_PRECISION_FP16)
     int fuse_fwd;               // 1 (default): conv2 + conv3 forward as one kernel (also FB_TC_FUSE_FWD)
     int fuse_bwd;               // 1 (default): conv3 / conv2 data gradients and the un-pool as one kernel (also FB_TC_FUSE_BWD)
     int conv1_mode;             // 2 (default): pooled epilogue, slab from u8 when no backward follows; 1: slab always from X2;
@@ -1405,6 +1402,10 @@ namespace {
 
 constexpr int kChunk1 = 1024, kChunk23 = 256;
 constexpr int kFc1Splits = 5;                    // fc1 forward: 25 K-blocks in 5 K-splits of 5
+// The fused conv2+conv3 forward / conv3+conv2+un-pool backward kernels (two samples = 98 of 128 accumulator rows per tile, the
+// layers of a tile chained inside one CTA) cut launches at minibatch sizes; measured at 4,096 samples they LOSE to the separate,
+// fully pipelined kernels (bwd 172 us against 125 us; whole update 721 against 607 us): above this batch the separate kernels run.
+constexpr int kFuseMaxBatch = 512;
 // the fused head kernel (fc1_head_train_kernel<16>) serves the reference's hidden width; other widths keep the two-kernel form
 bool fused_head_ok(const QnetLayout &L) { return L.hidden == 512; }
 int head_ctas(const TcState *t, int B) { const int c = (B + 3) / 4, m = t->n_sms < kMaxHeadCtas ? t->n_sms : kMaxHeadCtas; return c < m ? c : m; }
@@ -1490,6 +1491,9 @@ int make_plan(fb_qnet *n, int B, TcPlan **out) {
     set_mnmajor(p.fc1_w, 128); p.fc1_w.p_total = B; p.fc1_w.klen = (B + 63) / 64 * 64;
     for (int mt = 0; mt < 13; mt++) for (int i = 0; i < 2; i++) { p.fc1_w.a2_rowoff[mt][i] = 0; p.fc1_w.a2_col[mt][i] = mt * 128 + i * 64; }
     FB_REQUIRE((size_t)p.s1 <= t->cap1 && (size_t)p.s2 <= t->cap2 && (size_t)p.s3 <= t->cap3, "tensor-core path: split-K workspace too small");
+    p.conv1.f16 = p.conv2.f16 = p.conv3.f16 = p.conv3_d.f16 = p.conv2_d.f16 = t->f16;
+    p.conv1_w.f16 = p.conv2_w.f16 = p.conv3_w.f16 = t->f16;
+    p.fc1.f16 = p.fc1_d.f16 = p.fc1_w.f16 = t->f16;
     auto res = t->plans.emplace(B, p);
     *out = &res.first->second;
     return FB_OK;
@@ -1615,7 +1619,7 @@ extern "C" int fb_debug_poison_packed(fb_qnet *n, int slot, void *stream) {
 }
 
 bool tc_online_operands(fb_qnet *n, PackedWeights *out) {
-    if (!n || n->precision != FB_PRECISION_BF16 || !n->tc) return false;
+    if (!n || !tc_precision(n->precision) || !n->tc) return false;
     *out = n->tc->pw[0];
     return true;
 }
@@ -1650,12 +1654,12 @@ static FrameView g_probe_view;                    // frames of the last forward 
 // td != nullptr: the TD target / loss is fused into the head kernel; `join` (if any) is waited for first -- it marks the end
 // of the Q(s') forward on the other stream
 static int tc_forward_impl(fb_qnet *n, int slot, int w, const float *params_dev, FrameView fv, int B, float *q_out, int keep, cudaStream_t st,
-                           const TdFuse *td = nullptr, cudaEvent_t join = nullptr, const AdamPow *ap = nullptr);
+                           const TdFuse *td = nullptr, cudaEvent_t join = nullptr, const AdamPow *ap = nullptr, float gscale = 1.f);
 int tc_forward(fb_qnet *n, int slot, int w, const float *params_dev, FrameView fv, int B, float *q_out, cudaStream_t st) {
     return tc_forward_impl(n, slot, w, params_dev, fv, B, q_out, 0, st);
 }
 static int tc_forward_impl(fb_qnet *n, int slot, int w, const float *params_dev, FrameView fv, int B, float *q_out, int keep, cudaStream_t st,
-                           const TdFuse *td, cudaEvent_t join, const AdamPow *ap) {
+                           const TdFuse *td, cudaEvent_t join, const AdamPow *ap, float gscale) {
     TcState *t = n->tc;
     FB_REQUIRE(t != nullptr && B > 0 && B <= n->max_batch && (w == 0 || w == 1), "tc_forward: bad argument");
     TcPlan *p;
@@ -1671,22 +1675,22 @@ static int tc_forward_impl(fb_qnet *n, int slot, int w, const float *params_dev,
     //   keep != 0: X2 is materialised once (the conv1 weight gradient contracts over it by TMA) and feeds the slab.
     // conv1_mode 0 restores the three separate kernels (pack_x2, conv1, pool_pack).
     if (t->conv1_mode == 0) {
-        FB_CUDA_OK(tc::launch_pdl(pack_x2_kernel, dim3((unsigned)(((size_t)P1 * 8 + 255) / 256)), dim3(256), 0, st, fv, B, f.x2));
-        FB_CUDA_OK((launch_tc_conv<32, kSlab1, 1, 4, 6, 1>(p->x2_s[w], wm.w1p, p->conv1, t->n_sms, EpiConv1{f.z1, params_dev + L.b1, P1}, st)));
-        FB_CUDA_OK(tc::launch_pdl(pool_pack_kernel, dim3((unsigned)(((size_t)B * 36 * 16 + 255) / 256)), dim3(256), 0, st, f.z1, B, f.p2));
+        FB_CUDA_OK(tc::launch_pdl(pack_x2_kernel, dim3((unsigned)(((size_t)P1 * 8 + 255) / 256)), dim3(256), 0, st, fv, B, f.x2, t->f16));
+        FB_CUDA_OK((launch_tc_conv<32, kSlab1, 1, 4, 6, 1>(p->x2_s[w], wm.w1p, p->conv1, t->n_sms, EpiConv1{f.z1, params_dev + L.b1, P1, t->f16}, st)));
+        FB_CUDA_OK(tc::launch_pdl(pool_pack_kernel, dim3((unsigned)(((size_t)B * 36 * 16 + 255) / 256)), dim3(256), 0, st, f.z1, B, f.p2, t->f16));
     } else if (keep || t->conv1_mode == 1) {
-        FB_CUDA_OK(tc::launch_pdl(pack_x2_kernel, dim3((unsigned)(((size_t)P1 * 8 + 255) / 256)), dim3(256), 0, st, fv, B, f.x2));
-        FB_CUDA_OK((launch_tc_conv1_fused<6, true>(p->x2_s[w], wm.w1p, Conv1FusedParams{fv, B, params_dev + L.b1, keep ? f.z1 : nullptr, f.p2},
+        FB_CUDA_OK(tc::launch_pdl(pack_x2_kernel, dim3((unsigned)(((size_t)P1 * 8 + 255) / 256)), dim3(256), 0, st, fv, B, f.x2, t->f16));
+        FB_CUDA_OK((launch_tc_conv1_fused<6, true>(p->x2_s[w], wm.w1p, Conv1FusedParams{fv, B, params_dev + L.b1, keep ? f.z1 : nullptr, f.p2, t->f16},
                                                   t->n_sms, st)));
     } else {
-        FB_CUDA_OK((launch_tc_conv1_fused<4, false>(p->x2_s[w], wm.w1p, Conv1FusedParams{fv, B, params_dev + L.b1, nullptr, f.p2}, t->n_sms, st)));
+        FB_CUDA_OK((launch_tc_conv1_fused<4, false>(p->x2_s[w], wm.w1p, Conv1FusedParams{fv, B, params_dev + L.b1, nullptr, f.p2, t->f16}, t->n_sms, st)));
     }
-    if (t->fuse_fwd) {
-        FB_CUDA_OK((launch_tc_fwd23<2>(p->p2_s[w], wm.w2p, wm.w3p, Fwd23Params{(B + 1) / 2, B, params_dev + L.b2, params_dev + L.b3, keep ? f.a2 : nullptr, f.a3},
+    if (t->fuse_fwd && B <= kFuseMaxBatch) {
+        FB_CUDA_OK((launch_tc_fwd23<2>(p->p2_s[w], wm.w2p, wm.w3p, Fwd23Params{(B + 1) / 2, B, params_dev + L.b2, params_dev + L.b3, keep ? f.a2 : nullptr, f.a3, t->f16},
                                        t->n_sms, st)));
     } else {
-        FB_CUDA_OK((launch_tc_conv<64, kSlab2, 2, 8, 3, 1>(p->p2_s[w], wm.w2p, p->conv2, t->n_sms, EpiGrid7{f.a2, params_dev + L.b2, P2}, st)));
-        FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4, 1>(p->a2_s[w], wm.w3p, p->conv3, t->n_sms, EpiConv3{f.a3, params_dev + L.b3, P2}, st)));
+        FB_CUDA_OK((launch_tc_conv<64, kSlab2, 2, 8, 3, 1>(p->p2_s[w], wm.w2p, p->conv2, t->n_sms, EpiGrid7{f.a2, params_dev + L.b2, P2, t->f16}, st)));
+        FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4, 1>(p->a2_s[w], wm.w3p, p->conv3, t->n_sms, EpiConv3{f.a3, params_dev + L.b3, P2, t->f16}, st)));
     }
     FB_CUDA_OK((launch_tc_gemm<128, 2>(p->a3_k[w], wm.wf1n, p->fc1, dim3((B + 127) / 128, L.hidden / 128, p->sf),
                                        EpiStoreF32{f.parth, B, L.hidden, (size_t)n->max_batch * L.hidden}, st)));
@@ -1694,7 +1698,7 @@ static int tc_forward_impl(fb_qnet *n, int slot, int w, const float *params_dev,
     TdFuse none{};
     if (td != nullptr && ap != nullptr && fused_head_ok(L))      // training step: head forward + TD loss + head backward in one kernel
         FB_CUDA_OK(tc::launch_pdl(fc1_head_train_kernel<16>, dim3(head_ctas(t, B)), dim3(128), 0, st, f.parth, p->sf,
-                                  (size_t)n->max_batch * L.hidden, params_dev, L, B, q_out, *td, HeadBwd{t->dh1, t->hp, t->hb}, *ap));
+                                  (size_t)n->max_batch * L.hidden, params_dev, L, B, q_out, *td, HeadBwd{t->dh1, t->hp, t->hb, GradFmt{t->f16, gscale}}, *ap));
     else if (td == nullptr && fused_head_ok(L)) {
         const int ctas = (B + 3) / 4 < 4 * t->n_sms ? (B + 3) / 4 : 4 * t->n_sms;
         FB_CUDA_OK(tc::launch_pdl(fc1_head_warp_kernel<16>, dim3(ctas), dim3(128), 0, st, f.parth, p->sf, (size_t)n->max_batch * L.hidden,
@@ -1764,7 +1768,11 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     TdFuse td{1, a.variant, a.loss_sum, a.global_batch, n->per_broadcast, a.gamma, n->q_next, n->q_next_online, a.rewards, a.isw, a.actions,
               a.terminals, n->dq, a.abs_err, a.q_target, t->loss_terms};
     const AdamPow apow{a.ad.on, t->adam_pow, t->adam_pow + 2, a.ad.lr, a.ad.beta1, a.ad.beta2};
-    rc = tc_forward_impl(n, 0, 0, a.params, a.fs, B, n->q, 1, st, &td, t->ev[e], &apow); if (rc) return rc;
+    // fp16 operands: gradient tensors carry a power-of-two factor that keeps them in fp16's normal range (dq ~ err / batch for the
+    // mean losses); it is removed exactly where weight / bias gradients are finalised.  bf16: 1.
+    float gscale = 1.f;
+    if (t->f16) { gscale = 8.f; if (!a.loss_sum) { int gb = a.global_batch > 0 ? a.global_batch : B; while (gscale < 8.f * (float)gb) gscale *= 2.f; } }
+    rc = tc_forward_impl(n, 0, 0, a.params, a.fs, B, n->q, 1, st, &td, t->ev[e], &apow, gscale); if (rc) return rc;
     e++;
     // ---- backward.  The head's backward pass rode in the forward's last kernel when hidden = 512 (fc1_head_train_kernel);
     // otherwise: fp32 gradients of the head variables and the fc1 bias straight into partials, dh1 as bf16
@@ -1772,20 +1780,20 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     const int G = fused_head ? head_ctas(t, B) : (B + kHeadRows - 1) / kHeadRows;
     if (!fused_head)
         FB_CUDA_OK(tc::launch_pdl(head_backward_tc_kernel, dim3(H / 32 + 1, G), dim3(256), 0, st, f.h1, n->dq, a.params, L, B, t->hp, t->hb,
-                                  t->loss_terms, t->dh1, apow));
+                                  t->loss_terms, t->dh1, apow, GradFmt{t->f16, gscale}));
     cudaStream_t sy = t->aux2;                  // third stream: bias column sums and the early Adam on W_fc1, all off the critical path
     FB_CUDA_OK(fork(st, sx));
     // fc1: dW = a3^T dh1 (aux, written in place), dz3 = (dh1 Wf1^T) * relu'(a3)
-    FB_CUDA_OK((launch_tc_gemm<128, 1>(p->a3_m, p->dh1_b, p->fc1_w, dim3(13, H / 128, 1), EpiStoreF32{a.grads + L.wf1, kFlat, H, 0}, sx)));
+    FB_CUDA_OK((launch_tc_gemm<128, 1>(p->a3_m, p->dh1_b, p->fc1_w, dim3(13, H / 128, 1), EpiStoreF32{a.grads + L.wf1, kFlat, H, 0, 1.f / gscale}, sx)));
     const int e_fc1w = e++;
     FB_CUDA_OK(cudaEventRecord(t->ev[e_fc1w], sx));                    // W_fc1's gradient is final
-    FB_CUDA_OK((launch_tc_gemm<64, 0>(p->dh1_k, wm.wf1n, p->fc1_d, dim3((B + 127) / 128, kFlat / 64, 1), EpiFc1Dgrad{t->dz3, f.a3, B}, st)));
+    FB_CUDA_OK((launch_tc_gemm<64, 0>(p->dh1_k, wm.wf1n, p->fc1_d, dim3((B + 127) / 128, kFlat / 64, 1), EpiFc1Dgrad{t->dz3, f.a3, B, t->f16}, st)));
     FB_CUDA_OK(fork(st, sx));
     FB_CUDA_OK(cudaStreamWaitEvent(sy, t->ev[e - 1], 0));              // sy: after the fc1 data gradient (dz3 complete, wf1n no longer read)
     const int c1 = (P1 + kChunk1 - 1) / kChunk1, c23 = (P2 + kChunk23 - 1) / kChunk23;
     auto colsum_on = [&](const bf16 *x, float *part, int rows, int N, int chunk_rows, int chunks) -> cudaError_t {
         ColsumJobs cj{};
-        cj.njobs = 1;
+        cj.njobs = 1; cj.f16 = t->f16;
         cj.j[0] = ColsumJob{x, part, rows, N, chunk_rows, 0};
         colsum_kernel<<<chunks, 256, 0, sy>>>(cj);
         return cudaGetLastError();
@@ -1793,22 +1801,22 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     FB_CUDA_OK(colsum_on(t->dz3, t->bp3, P2, 64, kChunk23, c23));
     AdamDev ad{a.ad.on, const_cast<float *>(a.params), a.ad.m, a.ad.v, a.ad.beta1, a.ad.beta2, a.ad.eps, a.ad.grad_scale, t->adam_pow + 2};
     FB_CUDA_OK((launch_tc_wgrad<64, 5, kSlabW3, 1, 6>(p->a2_w, p->dz3_b, p->conv3_w, p->s3, EpiStoreF32{t->part3, 640, 64, (size_t)640 * 64}, sx)));
-    if (t->fuse_bwd) {
+    if (t->fuse_bwd && B <= kFuseMaxBatch) {
         // conv3 data gradient + ReLU mask + conv2 data gradient + un-pool in one kernel (tc_bwd23_kernel)
-        FB_CUDA_OK((launch_tc_bwd23<2>(p->dz3_s, wm.w3d, wm.w2d, Bwd23Params{(B + 1) / 2, B, f.a2, t->dz2, f.z1, t->dz1}, t->n_sms, st)));
+        FB_CUDA_OK((launch_tc_bwd23<2>(p->dz3_s, wm.w3d, wm.w2d, Bwd23Params{(B + 1) / 2, B, f.a2, t->dz2, f.z1, t->dz1, t->f16}, t->n_sms, st)));
         FB_CUDA_OK(fork(st, sx));
         FB_CUDA_OK(cudaStreamWaitEvent(sy, t->ev[e - 1], 0));          // sx, sy: dz2 and dz1 complete
         FB_CUDA_OK(colsum_on(t->dz1, t->bp1, P1, 32, kChunk1, c1));
         FB_CUDA_OK(colsum_on(t->dz2, t->bp2, P2, 64, kChunk23, c23));
         FB_CUDA_OK((launch_tc_wgrad<64, 4, kSlabW2, 2, 4>(p->p2_w, p->dz2_b, p->conv2_w, p->s2, EpiStoreF32{t->part2, 512, 64, (size_t)512 * 64}, sx)));
     } else {
-        FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4, 1>(p->dz3_s, wm.w3d, p->conv3_d, t->n_sms, EpiConv3Dgrad{t->dz2, f.a2, P2}, st)));
+        FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4, 1>(p->dz3_s, wm.w3d, p->conv3_d, t->n_sms, EpiConv3Dgrad{t->dz2, f.a2, P2, t->f16}, st)));
         FB_CUDA_OK(fork(st, sx));
         FB_CUDA_OK(cudaStreamWaitEvent(sy, t->ev[e - 1], 0));          // sy: after the conv3 data gradient (dz2 complete)
         FB_CUDA_OK(colsum_on(t->dz2, t->bp2, P2, 64, kChunk23, c23));
         FB_CUDA_OK((launch_tc_wgrad<64, 4, kSlabW2, 2, 4>(p->p2_w, p->dz2_b, p->conv2_w, p->s2, EpiStoreF32{t->part2, 512, 64, (size_t)512 * 64}, sx)));
-        FB_CUDA_OK((launch_tc_conv<128, kSlab2, 1, 4, 4, 1>(p->dz2_s, wm.w2d, p->conv2_d, t->n_sms, EpiStoreBf16{t->dp2, P2, 128}, st)));
-        FB_CUDA_OK(tc::launch_pdl(unpool_relu_kernel_tc, dim3((unsigned)(((size_t)B * 400 + 255) / 256)), dim3(256), 0, st, f.z1, t->dp2, B, t->dz1));
+        FB_CUDA_OK((launch_tc_conv<128, kSlab2, 1, 4, 4, 1>(p->dz2_s, wm.w2d, p->conv2_d, t->n_sms, EpiStoreBf16{t->dp2, P2, 128, t->f16}, st)));
+        FB_CUDA_OK(tc::launch_pdl(unpool_relu_kernel_tc, dim3((unsigned)(((size_t)B * 400 + 255) / 256)), dim3(256), 0, st, f.z1, t->dp2, B, t->dz1, t->f16));
         FB_CUDA_OK(fork(st, sy));                                       // sy: after the un-pool (dz1 complete)
         FB_CUDA_OK(colsum_on(t->dz1, t->bp1, P1, 32, kChunk1, c1));
     }
@@ -1821,7 +1829,7 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     FB_CUDA_OK((launch_tc_wgrad<32, 2, kSlabW1, 1, 6>(p->x2_w, p->dz1_b, p->conv1_w, p->s1, EpiStoreF32{t->part1, 256, 32, (size_t)256 * 32}, st)));
     FB_CUDA_OK(fork(sx, st));
     FB_CUDA_OK(fork(sy, st));
-    FinalizeArgs fa{t->part1, t->part2, t->part3, p->s1, p->s2, p->s3, t->bp1, t->bp2, t->bp3, c1, c23, c23, t->hp, t->hb, G, a.loss_out};
+    FinalizeArgs fa{t->part1, t->part2, t->part3, p->s1, p->s2, p->s3, t->bp1, t->bp2, t->bp3, c1, c23, c23, t->hp, t->hb, G, a.loss_out, 1.f / gscale};
     const int n_compact = L.wf1 + (L.total - L.bf1);
     const int nb_fin = (n_compact + 31) / 32;
     FB_CUDA_OK(tc::launch_pdl(finalize_grads_kernel, dim3(nb_fin), dim3(256), 0, st, fa, L, a.grads, ad, t->pw[0]));
@@ -1832,6 +1840,20 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
 bool same_key(const GraphKey &x, const GraphKey &y) { return memcmp(&x, &y, sizeof(GraphKey)) == 0; }
 
 }  // namespace
+
+int tc_set_format(fb_qnet *n, int f16) {
+    TcState *t = n->tc;
+    FB_REQUIRE(t != nullptr, "tc_set_format: no tensor-core state");
+    f16 = f16 ? 1 : 0;
+    if (t->f16 != f16) {                         // plans carry the format, graphs the plans, the operand copies the encoding
+        for (auto &g : t->graphs) destroy_entry(g);
+        t->graphs.clear();
+        t->plans.clear();
+        n->packed_src[0] = n->packed_src[1] = nullptr;
+    }
+    t->f16 = f16; t->pw[0].f16 = f16; t->pw[1].f16 = f16;
+    return FB_OK;
+}
 
 int tc_drop_graphs(fb_qnet *n) {
     if (n->tc) { for (auto &g : n->tc->graphs) destroy_entry(g); n->tc->graphs.clear(); }
@@ -1968,19 +1990,19 @@ extern "C" int fb_debug_tc_kernel(fb_qnet *n, int which, int B, int reps, const 
     const int H = L.hidden, P1 = B * kP1, P2 = B * kP2;
     for (int r = 0; r < reps; r++) {
         switch (which) {
-            case 0: FB_CUDA_OK((launch_tc_conv<32, kSlab1, 1, 4, 6, 1>(p->x2_s[0], wm.w1p, p->conv1, t->n_sms, EpiConv1{f.z1, params_dev + L.b1, P1}, st))); break;
-            case 1: FB_CUDA_OK((launch_tc_conv<64, kSlab2, 2, 8, 3, 1>(p->p2_s[0], wm.w2p, p->conv2, t->n_sms, EpiGrid7{f.a2, params_dev + L.b2, P2}, st))); break;
-            case 2: FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4, 1>(p->a2_s[0], wm.w3p, p->conv3, t->n_sms, EpiConv3{f.a3, params_dev + L.b3, P2}, st))); break;
+            case 0: FB_CUDA_OK((launch_tc_conv<32, kSlab1, 1, 4, 6, 1>(p->x2_s[0], wm.w1p, p->conv1, t->n_sms, EpiConv1{f.z1, params_dev + L.b1, P1, t->f16}, st))); break;
+            case 1: FB_CUDA_OK((launch_tc_conv<64, kSlab2, 2, 8, 3, 1>(p->p2_s[0], wm.w2p, p->conv2, t->n_sms, EpiGrid7{f.a2, params_dev + L.b2, P2, t->f16}, st))); break;
+            case 2: FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4, 1>(p->a2_s[0], wm.w3p, p->conv3, t->n_sms, EpiConv3{f.a3, params_dev + L.b3, P2, t->f16}, st))); break;
             case 3: FB_CUDA_OK((launch_tc_gemm<128, 2>(p->a3_k[0], wm.wf1n, p->fc1, dim3((B + 127) / 128, H / 128, p->sf),
                                                        EpiStoreF32{f.parth, B, H, (size_t)n->max_batch * H}, st))); break;
             case 4: FB_CUDA_OK((launch_tc_wgrad<32, 2, kSlabW1, 1, 6>(p->x2_w, p->dz1_b, p->conv1_w, p->s1, EpiStoreF32{t->part1, 256, 32, (size_t)256 * 32}, st))); break;
-            case 5: FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4, 1>(p->dz3_s, wm.w3d, p->conv3_d, t->n_sms, EpiConv3Dgrad{t->dz2, f.a2, P2}, st))); break;
-            case 6: FB_CUDA_OK((launch_tc_gemm<64, 0>(p->dh1_k, wm.wf1n, p->fc1_d, dim3((B + 127) / 128, kFlat / 64, 1), EpiFc1Dgrad{t->dz3, f.a3, B}, st))); break;
-            case 7: FB_CUDA_OK((launch_tc_conv1_fused<4, false>(p->x2_s[0], wm.w1p, Conv1FusedParams{g_probe_view, B, params_dev + L.b1, nullptr, f.p2}, t->n_sms, st))); break;
-            case 8: FB_CUDA_OK((launch_tc_conv1_fused<4, false>(p->x2_s[0], wm.w1p, Conv1FusedParams{g_probe_view, B, params_dev + L.b1, f.z1, f.p2}, t->n_sms, st))); break;
-            case 9: FB_CUDA_OK((launch_tc_conv1_fused<6, true>(p->x2_s[0], wm.w1p, Conv1FusedParams{g_probe_view, B, params_dev + L.b1, nullptr, f.p2}, t->n_sms, st))); break;
-            case 10: FB_CUDA_OK((launch_tc_conv1_fused<6, true>(p->x2_s[0], wm.w1p, Conv1FusedParams{g_probe_view, B, params_dev + L.b1, f.z1, f.p2}, t->n_sms, st))); break;
-            case 11: FB_CUDA_OK((launch_tc_conv1_fused<6, true>(p->x2_s[0], wm.w1p, Conv1FusedParams{g_probe_view, B, params_dev + L.b1, nullptr, nullptr}, t->n_sms, st))); break;
+            case 5: FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4, 1>(p->dz3_s, wm.w3d, p->conv3_d, t->n_sms, EpiConv3Dgrad{t->dz2, f.a2, P2, t->f16}, st))); break;
+            case 6: FB_CUDA_OK((launch_tc_gemm<64, 0>(p->dh1_k, wm.wf1n, p->fc1_d, dim3((B + 127) / 128, kFlat / 64, 1), EpiFc1Dgrad{t->dz3, f.a3, B, t->f16}, st))); break;
+            case 7: FB_CUDA_OK((launch_tc_conv1_fused<4, false>(p->x2_s[0], wm.w1p, Conv1FusedParams{g_probe_view, B, params_dev + L.b1, nullptr, f.p2, t->f16}, t->n_sms, st))); break;
+            case 8: FB_CUDA_OK((launch_tc_conv1_fused<4, false>(p->x2_s[0], wm.w1p, Conv1FusedParams{g_probe_view, B, params_dev + L.b1, f.z1, f.p2, t->f16}, t->n_sms, st))); break;
+            case 9: FB_CUDA_OK((launch_tc_conv1_fused<6, true>(p->x2_s[0], wm.w1p, Conv1FusedParams{g_probe_view, B, params_dev + L.b1, nullptr, f.p2, t->f16}, t->n_sms, st))); break;
+            case 10: FB_CUDA_OK((launch_tc_conv1_fused<6, true>(p->x2_s[0], wm.w1p, Conv1FusedParams{g_probe_view, B, params_dev + L.b1, f.z1, f.p2, t->f16}, t->n_sms, st))); break;
+            case 11: FB_CUDA_OK((launch_tc_conv1_fused<6, true>(p->x2_s[0], wm.w1p, Conv1FusedParams{g_probe_view, B, params_dev + L.b1, nullptr, nullptr, t->f16}, t->n_sms, st))); break;
             default: FB_REQUIRE(false, "fb_debug_tc_kernel: which must be 0..11");
         }
     }

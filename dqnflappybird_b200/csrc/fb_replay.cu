@@ -143,23 +143,22 @@ __global__ void __launch_bounds__(128) gather_kernel(GatherArgs g) {
 
 // ------------------------------------------------------------------------------ SumTree
 // tree: f64[2*cap-1], node 0 the root, leaves [cap-1, 2cap-2] (BrainPrioritizedReplyDQN.py:39-47).
+// Beside it live two more trees of the same shape, maintained by the same kernels along the same leaf-to-root paths:
+//   mn[node] = smallest POSITIVE leaf below it (+inf if none)   -> Memory.sample's get_min_prob (:70-71), an O(capacity) min()
+//   mx[node] = largest leaf below it                             -> Memory.store's np.max over all leaves (:122)
+// so both are read from the root in O(1); round 1 re-scanned every leaf before every sample / store (7.9 MB per update at
+// 983,040 leaves against ~70 KB algorithmic).  min / max are exact, so their order of evaluation is free.
 __device__ __forceinline__ int node_depth(int idx) { return 31 - __clz(idx + 1); }
 __device__ __forceinline__ int ancestor_at(int idx, int depth_idx, int d) { return ((idx + 1) >> (depth_idx - d)) - 1; }
+__device__ __forceinline__ double pos_or_inf(double p) { return p > 0.0 ? p : __longlong_as_double(0x7FF0000000000000ll); }
 
-__global__ void leaf_minmax_kernel(const double *tree, int cap, unsigned long long *out /* [0]=max bits, [1]=min-positive bits */) {
-    unsigned long long mx = 0ull, mn = ~0ull;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
-        double v = tree[cap - 1 + i];
-        unsigned long long b = (unsigned long long)__double_as_longlong(v);     // non-negative doubles order like their bits
-        if (b > mx) mx = b;
-        if (v > 0.0 && b < mn) mn = b;
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        unsigned long long a = __shfl_xor_sync(~0u, mx, o), c = __shfl_xor_sync(~0u, mn, o);
-        mx = a > mx ? a : mx; mn = c < mn ? c : mn;
-    }
-    if ((threadIdx.x & 31) == 0) { atomicMax(&out[0], mx); atomicMin(&out[1], mn); }
+struct Node3 { double s, mn, mx; };
+__device__ __forceinline__ void set_leaf(double *tree, double *mn, double *mx, int leaf, double p) { tree[leaf] = p; mn[leaf] = pos_or_inf(p); mx[leaf] = p; }
+__device__ __forceinline__ void pull_node(double *tree, double *mn, double *mx, int node) {       // parent = f(children), exact
+    const int l = 2 * node + 1;
+    tree[node] = tree[l] + tree[l + 1];
+    mn[node] = fmin(mn[l], mn[l + 1]);
+    mx[node] = fmax(mx[l], mx[l + 1]);
 }
 
 // One CTA applies `count` leaf updates tree[leaf_i] = p_i and repairs the inner nodes.
@@ -169,27 +168,21 @@ __global__ void leaf_minmax_kernel(const double *tree, int cap, unsigned long lo
 //          running node value in a register), so the float64 rounding history equals the reference's.
 //   mode 1 "rebuild": leaves are set, then every touched ancestor is recomputed as left + right,
 //          deepest level first.  Deterministic, parallel, no drift; used for N > 1 at scale.
-// leaves: tree indices.  prio: f64[count] or nullptr -> use *store_prio_bits (max leaf, 1.0 if 0) for all.
+// leaves: tree indices.  prio: f64[count] or nullptr -> Memory.store: the max leaf (root of mx), 1.0 if all zero (:121-125).
 // abs_err (f32, optional): Memory.batch_update's transform (:146-149) p = min(|err| + 0.01, 1)^0.6 in float32, computed
-// here into prio_scratch instead of by a kernel of its own.  store_prio_bits is the leaf scan's result; this kernel, its one
-// consumer on the store path, re-arms it for the next scan.
+// here into prio_scratch instead of by a kernel of its own.
 constexpr int kMaxDupScan = 512;
-constexpr int kTopDepth = 11, kTopNodes = (1 << kTopDepth) - 1;          // depths 0..10 of the tree: 2,047 nodes, 16 KB
-__global__ void __launch_bounds__(1024) tree_update_kernel(double *tree, int cap, const int32_t *leaves, const double *prio,
-                                                           unsigned long long *store_prio_bits, int count, int mode,
-                                                           double *change_scratch, const float *abs_err, double *prio_scratch) {
+constexpr int kTopDepth = 11, kTopNodes = (1 << kTopDepth) - 1;          // depths 0..10 of the tree: 2,047 nodes
+__global__ void __launch_bounds__(1024) tree_update_kernel(double *tree, double *mn, double *mx, int cap, const int32_t *leaves, const double *prio,
+                                                           int count, int mode, double *change_scratch, const float *abs_err,
+                                                           double *prio_scratch) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    Node3 *s_top = reinterpret_cast<Node3 *>(s_raw);                      // depths 0..10 of the three trees (mode 1)
     const int tid = threadIdx.x;
     const int max_depth = node_depth(2 * cap - 2);
     __shared__ double s_store;
-    __shared__ double s_top[kTopNodes];
-    if (tid == 0) {
-        double p = 1.0;
-        if (store_prio_bits) {
-            p = __longlong_as_double((long long)store_prio_bits[0]); if (p == 0.0) p = 1.0;     // Memory.store :121-125
-            store_prio_bits[0] = 0ull; store_prio_bits[1] = ~0ull;
-        }
-        s_store = p;
-    }
+    __shared__ int s_leaf[kMaxDupScan];
+    if (tid == 0) { double p = mx[0]; s_store = p == 0.0 ? 1.0 : p; }     // Memory.store :121-125
     if (abs_err != nullptr) {
         for (int i = tid; i < count; i += blockDim.x) prio_scratch[i] = (double)powf(fminf(abs_err[i] + 0.01f, 1.0f), 0.6f);
         prio = prio_scratch;
@@ -201,10 +194,10 @@ __global__ void __launch_bounds__(1024) tree_update_kernel(double *tree, int cap
                 int leaf = leaves[i];
                 double p = prio ? prio[i] : s_store;
                 change_scratch[i] = p - tree[leaf];
-                tree[leaf] = p;
+                set_leaf(tree, mn, mx, leaf, p);
             }
         __syncthreads();
-        if (tid < max_depth) {              // thread d repairs depth d
+        if (tid < max_depth) {              // thread d repairs depth d of the SUM tree in the reference's order
             int d = tid, cur = -1; double val = 0.0;
             for (int i = 0; i < count; i++) {
                 int leaf = leaves[i], dl = node_depth(leaf);
@@ -215,18 +208,25 @@ __global__ void __launch_bounds__(1024) tree_update_kernel(double *tree, int cap
             }
             if (cur >= 0) tree[cur] = val;
         }
+        __syncthreads();
+        for (int d = max_depth - 1; d >= 0; d--) {                         // min / max trees: exact, level by level
+            for (int i = tid; i < count; i += blockDim.x) {
+                int leaf = leaves[i], dl = node_depth(leaf);
+                if (dl > d) { int node = ancestor_at(leaf, dl, d), l = 2 * node + 1; mn[node] = fmin(mn[l], mn[l + 1]); mx[node] = fmax(mx[l], mx[l + 1]); }
+            }
+            __syncthreads();
+        }
         return;
     }
-    __shared__ int s_leaf[kMaxDupScan];
     const bool in_smem = prio != nullptr && count <= kMaxDupScan;     // a minibatch: scan for duplicates from shared memory
     if (in_smem) { for (int i = tid; i < count; i += blockDim.x) s_leaf[i] = leaves[i]; __syncthreads(); }
     for (int i = tid; i < count; i += blockDim.x) {
-        if (!prio) { tree[leaves[i]] = s_store; continue; }      // stores: distinct leaves, one value
+        if (!prio) { set_leaf(tree, mn, mx, leaves[i], s_store); continue; }      // stores: distinct leaves, one value
         const int mine = leaves[i];
         int later = 0;                                            // duplicates in a minibatch: the last one wins, as in
         if (in_smem) { for (int j = i + 1; j < count; j++) later += (s_leaf[j] == mine); }     // the reference's sequential loop (:150-151)
         else { for (int j = i + 1; j < count; j++) if (leaves[j] == mine) { later = 1; break; } }
-        if (later == 0) tree[mine] = prio[i];
+        if (later == 0) set_leaf(tree, mn, mx, mine, prio[i]);
     }
     __syncthreads();
     // deep levels in global memory (one dependent L2 round trip per level), then depths <= 10 from a shared-memory copy
@@ -234,77 +234,172 @@ __global__ void __launch_bounds__(1024) tree_update_kernel(double *tree, int cap
     for (int d = max_depth - 1; d > top; d--) {
         for (int i = tid; i < count; i += blockDim.x) {
             int leaf = leaves[i], dl = node_depth(leaf);
-            if (dl > d) { int node = ancestor_at(leaf, dl, d); tree[node] = tree[2 * node + 1] + tree[2 * node + 2]; }
+            if (dl > d) pull_node(tree, mn, mx, ancestor_at(leaf, dl, d));
         }
         __syncthreads();
     }
     const int n_top = (2 << top) - 1, n_all = 2 * cap - 1;                         // nodes of depths 0..top
-    for (int j = tid; j < n_top && j < n_all; j += blockDim.x) s_top[j] = tree[j];
+    for (int j = tid; j < n_top && j < n_all; j += blockDim.x) s_top[j] = Node3{tree[j], mn[j], mx[j]};
     __syncthreads();
     for (int d = top; d >= 0; d--) {
         for (int i = tid; i < count; i += blockDim.x) {
             int leaf = leaves[i], dl = node_depth(leaf);
             if (dl > d) {
                 int node = ancestor_at(leaf, dl, d), cl = 2 * node + 1;
-                double v = (cl < n_top ? s_top[cl] : tree[cl]) + (cl + 1 < n_top ? s_top[cl + 1] : tree[cl + 1]);
-                s_top[node] = v; tree[node] = v;
+                const Node3 a = cl < n_top ? s_top[cl] : Node3{tree[cl], mn[cl], mx[cl]};
+                const Node3 b = cl + 1 < n_top ? s_top[cl + 1] : Node3{tree[cl + 1], mn[cl + 1], mx[cl + 1]};
+                const Node3 v{a.s + b.s, fmin(a.mn, b.mn), fmax(a.mx, b.mx)};
+                s_top[node] = v; tree[node] = v.s; mn[node] = v.mn; mx[node] = v.mx;
             }
         }
         __syncthreads();
     }
 }
 
+// Memory.store for one transition of EVERY env (mode "rebuild", N >= kStoreMultiMin): N leaves, one per env, at
+//   leaf(e) = cap - 1 + e C + off.   Round 1 walked them through ONE CTA, level after level.  Here the tree is cut at depth
+// kTopDepth: each of the 2,048 sub-trees below is private to one CTA (CTA b owns sub-trees [b S, (b+1) S)), which finds its envs
+// by arithmetic (a sub-tree's leaves are two contiguous index ranges, one per leaf level), sets their leaves and pulls the
+// touched ancestors level by level with CTA-local barriers only; the CTA that finishes last repairs depths 10..0 in shared memory.
+constexpr int kStoreMultiMin = 2048;
+__global__ void __launch_bounds__(256) per_store_multi_kernel(double *tree, double *mn, double *mx, int cap, int N, int C, int off,
+                                                              unsigned int *done_counter) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    Node3 *s_top = reinterpret_cast<Node3 *>(s_raw);
+    __shared__ double s_store;
+    __shared__ int s_last;
+    const int tid = threadIdx.x, n_all = 2 * cap - 1, max_depth = node_depth(n_all - 1);
+    if (tid == 0) { double p = mx[0]; s_store = p == 0.0 ? 1.0 : p; }     // the max leaf BEFORE this store: read by every CTA before any
+    __syncthreads();                                                      // CTA can have changed the root (only the last CTA writes it)
+    const double p_store = s_store;
+    const int n_sub = 1 << kTopDepth;                                      // sub-trees rooted at depth kTopDepth
+    const int j0 = (int)((long long)blockIdx.x * n_sub / gridDim.x), j1 = (int)((long long)(blockIdx.x + 1) * n_sub / gridDim.x);
+    // envs whose leaf lies below sub-trees [j0, j1): per leaf level dl the node range [(a0+1) 2^k - 1, (a1+1) 2^k - 1), k = dl - kTopDepth
+    int e_lo[2], e_hi[2], dls[2];
+    for (int q = 0; q < 2; q++) {
+        const int dl = max_depth - 1 + q, k = dl - kTopDepth;
+        long long lo = ((long long)(n_sub - 1 + j0 + 1) << k) - 1, hi = ((long long)(n_sub - 1 + j1 + 1) << k) - 1;      // [lo, hi)
+        if (lo < cap - 1) lo = cap - 1;
+        if (hi > n_all) hi = n_all;
+        dls[q] = dl;
+        if (hi <= lo) { e_lo[q] = 0; e_hi[q] = 0; continue; }
+        // leaf(e) in [lo, hi)  <=>  e C + off in [lo - (cap-1), hi - (cap-1))
+        const long long a = lo - (cap - 1) - off, b = hi - (cap - 1) - off;
+        long long el = a <= 0 ? 0 : (a + C - 1) / C, eh = b <= 0 ? 0 : (b + C - 1) / C;
+        if (eh > N) eh = N;
+        if (el > eh) el = eh;
+        e_lo[q] = (int)el; e_hi[q] = (int)eh;
+    }
+    for (int q = 0; q < 2; q++)
+        for (int e = e_lo[q] + tid; e < e_hi[q]; e += blockDim.x) set_leaf(tree, mn, mx, cap - 1 + e * C + off, p_store);
+    __syncthreads();
+    for (int d = max_depth - 1; d >= kTopDepth; d--) {
+        for (int q = 0; q < 2; q++) {
+            const int dl = dls[q];
+            if (dl <= d) continue;
+            for (int e = e_lo[q] + tid; e < e_hi[q]; e += blockDim.x) {
+                const int leaf = cap - 1 + e * C + off, node = ancestor_at(leaf, dl, d);
+                // several envs share an ancestor: the first env below it (in this level's range) pulls it
+                if (e > e_lo[q] && ancestor_at(leaf - C, dl, d) == node) continue;
+                pull_node(tree, mn, mx, node);
+            }
+        }
+        __syncthreads();
+    }
+    // ---- the CTA that finishes last repairs depths kTopDepth-1 .. 0
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int base = n_sub - 1;                                            // first node of depth kTopDepth
+    for (int d = kTopDepth - 1; d >= 0; d--) {
+        const int first = (1 << d) - 1, cnt = 1 << d;
+        for (int i = tid; i < cnt; i += blockDim.x) {
+            const int node = first + i, cl = 2 * node + 1;
+            Node3 a, b;
+            if (d == kTopDepth - 1) { a = Node3{__ldcg(tree + cl), __ldcg(mn + cl), __ldcg(mx + cl)}; b = Node3{__ldcg(tree + cl + 1), __ldcg(mn + cl + 1), __ldcg(mx + cl + 1)}; }
+            else { a = s_top[cl]; b = s_top[cl + 1]; }
+            const Node3 v{a.s + b.s, fmin(a.mn, b.mn), fmax(a.mx, b.mx)};
+            s_top[node] = v; tree[node] = v.s; mn[node] = v.mn; mx[node] = v.mx;
+        }
+        __syncthreads();
+    }
+    (void)base;
+    if (tid == 0) *done_counter = 0u;
+}
+
 // Memory.sample (BrainPrioritizedReplyDQN.py:127-144): stratified v_i = uniform(i seg, (i+1) seg) with
 // np.random.uniform's 53-bit construction from two stream words (purpose 4), SumTree.get_leaf descent
 // (:73-100, "v <= tree[left]" goes left), ISWeights = (p/total / min_prob)^-beta in float64.
-// The top eleven levels of the tree are read once into shared memory; only the deeper ones cost a round trip each.
-__global__ void per_sample_kernel(const double *tree, int cap, int batch, double beta, unsigned long long *minmax,
-                                  uint64_t seed, uint32_t *word_pos, int32_t *tree_idx, int32_t *data_idx, double *isw,
-                                  double *prio_out, float *isw_f32) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per sample.  Depths 0..10 come from a shared-memory copy; below that the warp fetches the next FIVE levels under
+// its current node at once (62 nodes, two per lane, one L2 round trip) and walks them with shuffles -- the comparisons and
+// subtractions are the reference's, in the reference's order, only the loads are batched: 2 round trips instead of 10 at
+// 983,040 leaves.  min_prob comes from the root of the min tree.  The CTA that finishes last advances the stream position.
+constexpr int kSampleWarps = 8;
+__global__ void __launch_bounds__(32 * kSampleWarps) per_sample_kernel(const double *tree, const double *mn, int cap, int batch, double beta,
+                                                                       uint64_t seed, uint32_t *word_pos, unsigned int *done_counter, int32_t *tree_idx,
+                                                                       int32_t *data_idx, double *isw, double *prio_out, float *isw_f32) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * kSampleWarps + warp;
     const int n_nodes = 2 * cap - 1;
     __shared__ double s_top[kTopNodes];                                      // depths 0..10: one round trip instead of eleven
+    __shared__ int s_last;
     const int n_top = n_nodes < kTopNodes ? n_nodes : kTopNodes;
     for (int j = threadIdx.x; j < n_top; j += blockDim.x) s_top[j] = tree[j];
     __syncthreads();
     const double total = s_top[0];
     const uint32_t pos0 = *word_pos;
-    const bool live = i < batch;
-    double v = 0.0;
-    if (live) {
+    if (i < batch) {
         double seg = total / (double)batch, a = seg * (double)i, b = seg * (double)(i + 1);
         uint32_t w0 = stream_word(seed, 4u, 0ull, pos0 + 2 * i) >> 5, w1 = stream_word(seed, 4u, 0ull, pos0 + 2 * i + 1) >> 6;
         double u = ((double)w0 * 67108864.0 + (double)w1) / 9007199254740992.0;
-        v = a + (b - a) * u;
-    }
-    int parent = 0;
-    if (live) {
+        double v = a + (b - a) * u;
+        int parent = 0;
         for (;;) {                                                           // SumTree.get_leaf (:73-100) through the cached levels
             int cl = 2 * parent + 1;
             if (cl + 1 >= n_top) break;
             double left = s_top[cl];
             if (v <= left) parent = cl; else { v -= left; parent = cl + 1; }
         }
-    }
-    if (live) {
-        for (;;) {
-            int cl = 2 * parent + 1;
-            if (cl >= n_nodes) break;
-            double left = tree[cl];
-            if (v <= left) parent = cl; else { v -= left; parent = cl + 1; }
+        while (2 * parent + 1 < n_nodes) {                                   // five levels per round trip
+            // heap position t >= 1 inside the sub-tree of `parent` (t = 1): node(t) = ((parent + 1) << floor(log2 t)) - 1 + (t - 2^floor(log2 t))
+            double val[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int t = lane + 2 + 32 * h;                             // t = 2..33, 34..65 (t <= 63 used)
+                const int lv = 31 - __clz(t);
+                const long long node = (((long long)parent + 1) << lv) - 1 + (t - (1 << lv));
+                val[h] = (t <= 63 && node < n_nodes) ? tree[node] : 0.0;
+            }
+            int t = 1;
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const int cl = 2 * parent + 1;
+                if (cl >= n_nodes) break;                                    // warp-uniform: reached a leaf
+                const int tl = 2 * t;                                        // left child inside the fetched block
+                const double lo = __shfl_sync(0xFFFFFFFFu, val[0], (tl - 2) & 31), hi = __shfl_sync(0xFFFFFFFFu, val[1], (tl - 34) & 31);
+                const double left = tl <= 33 ? lo : hi;
+                if (v <= left) { parent = cl; t = tl; } else { v -= left; parent = cl + 1; t = tl + 1; }
+            }
         }
-        double p = tree[parent];
-        double min_p = __longlong_as_double((long long)minmax[1]);
-        double prob = p / total, min_prob = min_p / total;
-        tree_idx[i] = parent;
-        data_idx[i] = parent - (cap - 1);
-        const double w = pow(prob / min_prob, -beta);
-        isw[i] = w;
-        if (isw_f32) isw_f32[i] = (float)w;             // the ISWeights placeholder is tf.float32 (BrainPrioritizedReplyDQN.py:243)
-        if (prio_out) prio_out[i] = p;
+        if (lane == 0) {
+            const double p = tree[parent];
+            const double min_p = mn[0];
+            const double prob = p / total, min_prob = min_p / total;
+            tree_idx[i] = parent;
+            data_idx[i] = parent - (cap - 1);
+            const double w = pow(prob / min_prob, -beta);
+            isw[i] = w;
+            if (isw_f32) isw_f32[i] = (float)w;             // the ISWeights placeholder is tf.float32 (BrainPrioritizedReplyDQN.py:243)
+            if (prio_out) prio_out[i] = p;
+        }
     }
     __syncthreads();
-    if (i == 0) { *word_pos = pos0 + 2 * (uint32_t)batch; minmax[0] = 0ull; minmax[1] = ~0ull; }     // re-arm the leaf scan
+    if (threadIdx.x == 0) s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) { *word_pos = pos0 + 2 * (uint32_t)batch; *done_counter = 0u; }     // every CTA has read pos0 by now
 }
 
 __global__ void store_leaves_kernel(int N, int C, long long k, int32_t *leaves) {   // leaf of transition k for every env

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -161,6 +162,41 @@ __host__ __device__ constexpr uint32_t smem_desc_hi(uint32_t sbo_bytes, uint32_t
 __host__ __device__ constexpr uint32_t instr_desc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// The same with a run-time operand format: f16 = 0 bf16 x bf16, 1 fp16 x fp16 (kind::f16 serves both; format code 0 = F16, 1 = BF16)
+__host__ __device__ constexpr uint32_t instr_desc_16(int m, int n, int a_mn_major, int b_mn_major, int f16) {
+    const uint32_t fmt = f16 ? 0u : 1u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---- the two 16-bit operand formats of the tensor-core path ------------------------------------------------------------
+// f16 = 0: bf16 (8-bit significand, fp32's exponent range).  f16 = 1: IEEE fp16 (11-bit significand -- exactly TF32's -- at the
+// same tensor rate and the same bytes; its narrow exponent range is handled by scaling the gradients by a power of two, see
+// TcState::gscale).  Every conversion of the path goes through these four helpers; `f16` is uniform over a launch.
+__device__ __forceinline__ uint32_t pack2(float a, float b, int f16) {
+    if (f16) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t *>(&h); }
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+__device__ __forceinline__ float2 unpack2(uint32_t w, int f16) {
+    if (f16) return __half22float2(*reinterpret_cast<__half2 *>(&w));
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&w));
+}
+__device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b, int f16) {
+    if (f16) { __half2 r = __hmax2(*reinterpret_cast<__half2 *>(&a), *reinterpret_cast<__half2 *>(&b)); return *reinterpret_cast<uint32_t *>(&r); }
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162 *>(&a), *reinterpret_cast<__nv_bfloat162 *>(&b));
+    return *reinterpret_cast<uint32_t *>(&r);
+}
+__device__ __forceinline__ unsigned short pack1(float a, int f16) {
+    if (f16) { __half h = __float2half_rn(a); return *reinterpret_cast<unsigned short *>(&h); }
+    __nv_bfloat16 h = __float2bfloat16(a);
+    return *reinterpret_cast<unsigned short *>(&h);
+}
+__device__ __forceinline__ float round1(float a, int f16) {           // the value an operand element holds after the conversion
+    if (f16) return __half2float(__float2half_rn(a));
+    return __bfloat162float(__float2bfloat16(a));
 }
 
 // host: launch with programmatic stream serialization allowed (see pdl_wait)

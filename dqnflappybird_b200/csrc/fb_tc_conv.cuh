@@ -29,6 +29,7 @@ struct ConvParams {
     int slab_row0;                         // the slab of tile t starts at row 128 t + slab_row0 (<= 0)
     int kb_rowoff[16];                     // K-block kb reads slab rows [kb_rowoff, kb_rowoff + 128) ...
     int kb_half[16];                       // ... of column half kb_half (64 channels each)
+    int f16;                               // operand format (tc::pack2): 0 bf16, 1 fp16
 };
 
 // D[p][n] = sum_kb sum_c A[p + tap(kb)][64 half(kb) + c] * Bt[n][64 kb + c], persistent over tiles of 128 positions.
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
     } else if (warp == 1) {
         {
             const bool leader = tc::elect_one();
-            constexpr uint32_t idesc = tc::instr_desc_bf16(128, BN, 0, 0);
+            const uint32_t idesc = tc::instr_desc_16(128, BN, 0, 0, g.f16);
             constexpr uint32_t dhi = tc::smem_desc_hi(1024, tc::kSwizzle128);
             // descriptor start fields, in 16-byte units: per K-block for A (tap row offset, column half), constant for B
             uint32_t a_rel[NKB];
@@ -188,6 +189,7 @@ struct WgradParams {
     int slab_row0;                         // the A slab of K-block p starts at row p + slab_row0
     int acc_rowoff[8];                     // accumulator a: first atom starts acc_rowoff rows into the slab (column half 0),
     uint32_t acc_lbo[8];                   // its second 64-row atom acc_lbo bytes later
+    int f16;
 };
 
 template <int BN, int NACC, int SLAB_ROWS, int NHALF, int S, class EP>
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_wgrad_kernel(const __grid_
     } else if (warp == 1) {
         {
             const bool leader = tc::elect_one();
-            constexpr uint32_t idesc = tc::instr_desc_bf16(128, BN, 1, 1);
+            const uint32_t idesc = tc::instr_desc_16(128, BN, 1, 1, g.f16);
             constexpr uint32_t ahi = tc::smem_desc_hi(1024, tc::kSwizzle128), bhi = tc::smem_desc_hi(B_SBO, B_LAYOUT);
             uint32_t a_lo0[NACC];                 // start (16-byte units) + LBO of each accumulator's A descriptor, stage 0
 #pragma unroll
@@ -336,7 +338,7 @@ constexpr int kRawStages = 4;
 // 1,216 chunks of 16 bytes per slab over the builder threads (every warp equally loaded); r / 21 by multiply-shift;
 // loads unconditional (clamped address) and zeroing by a select, so that no divergent block surrounds the LDS
 template <int NT>
-__device__ __forceinline__ void slab_from_raw(uint8_t *slab, const uint8_t *raw, int tq, int tid) {
+__device__ __forceinline__ void slab_from_raw(uint8_t *slab, const uint8_t *raw, int tq, int tid, int f16) {
     constexpr int K = (kSlabF * 8 + NT - 1) / NT, LAST = kSlabF * 8 - 1;
     // all of a thread's loads first (one warp per scheduler: the conversions of chunk k would otherwise wait out the
     // shared-memory latency of chunk k's own loads, ~350 cycles a chunk), then convert and store
@@ -365,8 +367,7 @@ __device__ __forceinline__ void slab_from_raw(uint8_t *slab, const uint8_t *raw,
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const float lo = (float)((t[k][2 * h] >> (8 * s2)) & 255), hi = (float)((t[k][2 * h + 1] >> (8 * s2)) & 255);
-                __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-                w[s2 * 2 + h] = valid ? *reinterpret_cast<uint32_t *>(&v) : 0u;
+                w[s2 * 2 + h] = valid ? tc::pack2(lo, hi, f16) : 0u;
             }
         if (tid + k * NT <= LAST) *reinterpret_cast<uint4 *>(slab + (dst[k] & 0x7fffffffu)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
@@ -378,6 +379,7 @@ struct Conv1FusedParams {
     const float *bias;
     __nv_bfloat16 *z1;          // [B*441][32] or nullptr (acting / target forward: not needed)
     __nv_bfloat16 *p2;          // [B*49][128]
+    int f16;
 };
 
 // FROM_X2: the slab comes by TMA from a materialised X2 (pack_x2_kernel) instead of the in-kernel builders -- conv1 with
@@ -464,7 +466,7 @@ __global__ void __launch_bounds__(FROM_X2 ? kRoleThreads1 : kFusedThreads, 1) tc
             const int s = i % S, rs = i % kRawStages;
             tc::mbar_wait(tc::smem_u32(&bar_raw_full[rs]), (i / kRawStages) & 1);
             tc::mbar_wait(tc::smem_u32(&bar_empty[s]), ((i / S) & 1) ^ 1u);
-            slab_from_raw<GT>(slab_gen + s * STAGE, raw_gen + rs * kRawBytes, tile & 3, tid);
+            slab_from_raw<GT>(slab_gen + s * STAGE, raw_gen + rs * kRawBytes, tile & 3, tid, g.f16);
             tc::fence_proxy_async();                      // generic-proxy writes -> visible to the tensor core's async proxy
             if (grp == 0) asm volatile("bar.sync 2, %0;" ::"n"(GT) : "memory");
             else asm volatile("bar.sync 3, %0;" ::"n"(GT) : "memory");
@@ -473,7 +475,7 @@ __global__ void __launch_bounds__(FROM_X2 ? kRoleThreads1 : kFusedThreads, 1) tc
     } else if (warp == 1) {
         // ===== MMA issue
         const bool leader = tc::elect_one();
-        constexpr uint32_t idesc = tc::instr_desc_bf16(128, BN, 0, 0);
+        const uint32_t idesc = tc::instr_desc_16(128, BN, 0, 0, g.f16);
         constexpr uint32_t dhi = tc::smem_desc_hi(1024, tc::kSwizzle128);
         const uint32_t a_lo0 = tc::smem_desc_lo(smem_a, 16), b_lo0 = tc::smem_desc_lo(smem_b, 16);
         tc::mbar_wait(tc::smem_u32(&bar_b), 0);
@@ -529,8 +531,7 @@ __global__ void __launch_bounds__(FROM_X2 ? kRoleThreads1 : kFusedThreads, 1) tc
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 const float x0 = fmaxf(v[2 * k] + bia[2 * k], 0.f) * keep, x1 = fmaxf(v[2 * k + 1] + bia[2 * k + 1], 0.f) * keep;
-                __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-                w[k] = *reinterpret_cast<uint32_t *>(&h);
+                w[k] = tc::pack2(x0, x1, g.f16);
             }
             uint4 *zs = reinterpret_cast<uint4 *>(zs_gen + (i & 3) * ZS_BYTES + r * 64);
             if (g.p2 != nullptr)
@@ -551,11 +552,11 @@ __global__ void __launch_bounds__(FROM_X2 ? kRoleThreads1 : kFusedThreads, 1) tc
                     auto ld = [&](int row) { return *reinterpret_cast<const uint4 *>(zb + row * 64 + (((cg + (row >> 1)) & 3) << 4)); };
                     const int r0 = (2 * ph_l) * 21 + 2 * pw;
                     uint4 m = ld(r0), o1 = ld(r0 + 1), o2 = ld(r0 + 21), o3 = ld(r0 + 22);
-                    __nv_bfloat162 *pm = reinterpret_cast<__nv_bfloat162 *>(&m);
-                    const __nv_bfloat162 *p1 = reinterpret_cast<const __nv_bfloat162 *>(&o1), *p2 = reinterpret_cast<const __nv_bfloat162 *>(&o2),
-                                         *p3 = reinterpret_cast<const __nv_bfloat162 *>(&o3);
+                    uint32_t *pm = reinterpret_cast<uint32_t *>(&m);
+                    const uint32_t *p1 = reinterpret_cast<const uint32_t *>(&o1), *p2 = reinterpret_cast<const uint32_t *>(&o2),
+                                   *p3 = reinterpret_cast<const uint32_t *>(&o3);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) pm[k] = __hmax2(__hmax2(pm[k], p1[k]), __hmax2(p2[k], p3[k]));
+                    for (int k = 0; k < 4; k++) pm[k] = tc::max2(tc::max2(pm[k], p1[k], g.f16), tc::max2(p2[k], p3[k], g.f16), g.f16);
                     const int bh = (ph + 1) >> 1, rr = (ph + 1) & 1, bw = (pw + 1) >> 1, ss = (pw + 1) & 1;
                     *reinterpret_cast<uint4 *>(g.p2 + ((size_t)b * 49 + bh * 7 + bw) * 128 + rr * 64 + ss * 32 + cg * 8) = m;
                 }

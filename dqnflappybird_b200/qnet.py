@@ -18,7 +18,7 @@ VARIANTS = {"vanilla": 0, "nature": 1, "double": 2}
 # byte offsets of the four frames of s and of s' inside one minibatch sample u8[5][80][80]
 _OFF_S = (C.c_int32 * 4)(0, 6400, 12800, 19200)
 _OFF_N = (C.c_int32 * 4)(6400, 12800, 19200, 25600)
-PRECISIONS = {"fp32": 0, "bf16": 1}
+PRECISIONS = {"fp32": 0, "bf16": 1, "fp16": 2}
 
 
 def truncated_normal_(t: torch.Tensor, std: float, generator=None):
@@ -65,12 +65,14 @@ class QNetwork:
         _lib.check(self._L.fb_qnet_create(hidden, int(dueling), max_batch, C.byref(h)), "fb_qnet_create")
         self._h = h
         self.hidden, self.dueling, self.max_batch = hidden, bool(dueling), max_batch
-        # "bf16": tcgen05 tensor cores (bf16 operands, fp32 accumulation); "fp32": strict CUDA-core FMA
+        # "bf16" / "fp16": tcgen05 tensor cores (16-bit operands, fp32 accumulation; fp16 has TF32's significand); "fp32": strict CUDA-core FMA
         self.precision = precision
         _lib.check(self._L.fb_qnet_set_precision(self._h, PRECISIONS[precision]), "fb_qnet_set_precision")
         self._seen_versions = None
-        self.compute_path = ("TMA + tcgen05 implicit GEMM (bf16 operands, fp32 accumulate in TMEM)" if precision == "bf16"
-                             else "fp32 CUDA-core implicit GEMM")
+        self.compute_path = {"bf16": "TMA + tcgen05 implicit GEMM (bf16 operands, fp32 accumulate in TMEM)",
+                             "fp16": "TMA + tcgen05 implicit GEMM (fp16 operands = TF32's 11-bit significand, fp32 accumulate in TMEM, "
+                                     "power-of-two gradient scaling)",
+                             "fp32": "fp32 CUDA-core implicit GEMM"}[precision]
         lay = (C.c_int32 * 16)()
         _lib.check(self._L.fb_qnet_layout(self._h, lay), "fb_qnet_layout")
         names = ["w1", "b1", "w2", "b2", "w3", "b3", "wf1", "bf1", "wf2", "bf2", "wv", "bv", "wa", "ba"]

@@ -158,6 +158,12 @@ int fb_qnet_destroy(fb_qnet *net);
  * are otherwise refreshed after fb_qnet_adam / fb_qnet_sync_target). */
 #define FB_PRECISION_FP32 0
 #define FB_PRECISION_BF16 1
+/* FB_PRECISION_FP16: the same tensor-core kernels with IEEE fp16 operands -- an 11-bit significand, exactly TF32's, at the
+ * bf16 tensor rate and byte count.  fp16's narrow exponent range is handled like mixed-precision training does: the gradient
+ * tensors (dh1 and everything downstream) carry a power-of-two factor (8 for the sum loss, 8 x minibatch rounded up to a power
+ * of two for the mean losses) that is removed exactly where weight / bias gradients are finalised.  The precision north_star
+ * names ("fp32/TF32 tolerance"); the default of the Brain classes. */
+#define FB_PRECISION_FP16 2
 int fb_qnet_set_precision(fb_qnet *net, int precision);
 int fb_qnet_get_precision(const fb_qnet *net);
 int fb_qnet_invalidate(fb_qnet *net);

@@ -74,31 +74,59 @@ def _bf16(t):
     return t.to(torch.float32).to(torch.bfloat16).to(torch.float64)
 
 
-class _RoundFwd(torch.autograd.Function):
-    """value rounded to bf16, gradient passed through (a bf16 operand copy of an fp32 master tensor)"""
-
-    @staticmethod
-    def forward(ctx, t):
-        return _bf16(t)
-
-    @staticmethod
-    def backward(ctx, g):
-        return g
+def _fp16(t):
+    return t.to(torch.float32).to(torch.float16).to(torch.float64)
 
 
-class _RoundBwd(torch.autograd.Function):
-    """identity whose GRADIENT is rounded to bf16 (a gradient tensor stored as bf16 between kernels)"""
-
-    @staticmethod
-    def forward(ctx, t):
-        return t.clone()
-
-    @staticmethod
-    def backward(ctx, g):
-        return _bf16(g)
+def _tf32(t):
+    """round-to-nearest-even to TF32 (10 explicit significand bits, fp32's exponent range): what a kind::tf32 operand keeps"""
+    b = t.to(torch.float32).contiguous().view(torch.int32)
+    b = (b + 0x0FFF + ((b >> 13) & 1)) & ~0x1FFF
+    return b.view(torch.float32).to(torch.float64)
 
 
-def forward(flat: torch.Tensor, x_u8, hidden=512, dueling=False, return_all=False, emulate_bf16=False):
+def _rounders(fmt, grad_scale=1.0):
+    """(round a value to the operand format keeping the gradient, identity whose GRADIENT is rounded at `grad_scale`)"""
+    if not fmt:
+        return (lambda t: t), (lambda t: t)
+    rnd = {"bf16": _bf16, "fp16": _fp16, "tf32": _tf32}[fmt]
+
+    class RoundFwd(torch.autograd.Function):
+        """value rounded to the 16-bit format, gradient passed through (an operand copy of an fp32 master tensor)"""
+
+        @staticmethod
+        def forward(ctx, t):
+            return rnd(t)
+
+        @staticmethod
+        def backward(ctx, g):
+            return g
+
+    class RoundBwd(torch.autograd.Function):
+        """identity whose GRADIENT is rounded (a gradient tensor stored in the 16-bit format between kernels, scaled by the
+        power of two the fp16 path applies so that it stays in the format's normal range)"""
+
+        @staticmethod
+        def forward(ctx, t):
+            return t.clone()
+
+        @staticmethod
+        def backward(ctx, g):
+            return rnd(g * grad_scale) / grad_scale
+
+    return RoundFwd.apply, RoundBwd.apply
+
+
+def fp16_grad_scale(batch, loss_sum):
+    """the power of two csrc/fb_qnet_tc.cu (train_step_launch) scales the gradient tensors by under FB_PRECISION_FP16"""
+    s = 8.0
+    if not loss_sum:
+        while s < 8.0 * batch:
+            s *= 2.0
+    return s
+
+
+def forward(flat: torch.Tensor, x_u8, hidden=512, dueling=False, return_all=False, emulate_bf16=False, emulate=None, grad_scale=1.0):
     """x_u8: [B,4,80,80] (channel = frame, oldest first; H = obs axis 0, W = obs axis 1) -> Q [B,2] float64.
 
     emulate_bf16: the same graph with the roundings of the tensor-core path (csrc/fb_qnet_tc.cu) put where that
@@ -106,8 +134,7 @@ def forward(flat: torch.Tensor, x_u8, hidden=512, dueling=False, return_all=Fals
     gradients dz1, dp1, dz2, dz3, dh1 rounded to bf16; sums stay exact.  Separates implementation errors
     (must be ~1e-3) from the precision of the format (a few percent)."""
     p = _unpack(flat, hidden, dueling)
-    rw = _RoundFwd.apply if emulate_bf16 else (lambda t: t)
-    rb = _RoundBwd.apply if emulate_bf16 else (lambda t: t)
+    rw, rb = _rounders("bf16" if emulate_bf16 else emulate, grad_scale)     # emulate: None | "bf16" | "fp16"
     x = torch.as_tensor(np.asarray(x_u8)).to(torch.float64)                      # values 0.0 / 255.0, no normalisation
     z1 = rw(F.relu(rb(F.conv2d(x, rw(p["w1"]).permute(3, 2, 0, 1), p["b1"], stride=4, padding=2))))     # SAME: pad 2/2
     p1 = rb(F.max_pool2d(z1, 2, 2))
@@ -127,7 +154,7 @@ def forward(flat: torch.Tensor, x_u8, hidden=512, dueling=False, return_all=Fals
 
 
 def loss_and_grads(variant, params32, target32, s, s2, actions, rewards, terminals, isw=None, gamma=0.99, loss_sum=False,
-                   global_batch=None, hidden=512, dueling=False, emulate_bf16=False, isw_broadcast=False):
+                   global_batch=None, hidden=512, dueling=False, emulate_bf16=False, isw_broadcast=False, emulate=None):
     """variant 0 vanilla / 1 nature / 2 double.  Returns loss, grads (float64 flat), abs_err, y (fp32 as fed), q(s).
 
     ``isw_broadcast``: the PER cost exactly as the reference's graph evaluates it -- ``ISWeights`` is a [B,1] placeholder and
@@ -137,20 +164,22 @@ def loss_and_grads(variant, params32, target32, s, s2, actions, rewards, termina
     T = torch.tensor((target32 if target32 is not None else params32).astype(np.float64))
     B = len(actions)
     gb = global_batch or B
+    fmt = "bf16" if emulate_bf16 else emulate
+    gs = fp16_grad_scale(gb, loss_sum) if fmt == "fp16" else 1.0
     with torch.no_grad():
         if variant == 0:
-            x = forward(P.detach(), s2, hidden, dueling, emulate_bf16=emulate_bf16).max(dim=1).values
+            x = forward(P.detach(), s2, hidden, dueling, emulate=fmt, grad_scale=gs).max(dim=1).values
         elif variant == 1:
-            x = forward(T, s2, hidden, dueling, emulate_bf16=emulate_bf16).max(dim=1).values
+            x = forward(T, s2, hidden, dueling, emulate=fmt, grad_scale=gs).max(dim=1).values
         else:
-            qt = forward(T, s2, hidden, dueling, emulate_bf16=emulate_bf16)
-            am = forward(P.detach(), s2, hidden, dueling, emulate_bf16=emulate_bf16).argmax(dim=1)
+            qt = forward(T, s2, hidden, dueling, emulate=fmt, grad_scale=gs)
+            am = forward(P.detach(), s2, hidden, dueling, emulate=fmt, grad_scale=gs).argmax(dim=1)
             x = qt[torch.arange(B), am]
         # the reference feeds fp32 Q-values into a Python float64 loop and feeds y back as fp32
         x32 = x.numpy().astype(np.float32).astype(np.float64)
         r = np.array([0.1 if abs(float(v) - 0.1) < 1e-6 else float(v) for v in rewards], np.float64)
         y = np.where(np.asarray(terminals).astype(bool), r, r + gamma * x32).astype(np.float32)
-    q = forward(P, s, hidden, dueling, emulate_bf16=emulate_bf16)
+    q = forward(P, s, hidden, dueling, emulate=fmt, grad_scale=gs)
     onehot = F.one_hot(torch.as_tensor(np.asarray(actions).astype(np.int64)), 2).to(torch.float64)
     q_eval = (q * onehot).sum(dim=1)
     err = torch.as_tensor(y.astype(np.float64)) - q_eval

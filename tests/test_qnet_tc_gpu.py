@@ -425,3 +425,88 @@ def test_fused_backward_is_bit_identical(mods, B, variant, dueling):
         assert torch.isfinite(nets[0].grads).all()
         assert torch.equal(nets[0].grads, nets[1].grads) and nets[0].loss.item() == nets[1].loss.item(), rep
     assert nets[0].grads.abs().max().item() > 0
+
+
+FP16_CASES = [("vanilla", False, True, False, 32), ("nature", False, False, False, 32), ("double", True, False, True, 32),
+              ("nature", False, False, False, 256), ("nature", True, False, False, 100)]
+
+
+@pytest.mark.parametrize("variant,dueling,loss_sum,per,B", FP16_CASES)
+def test_loss_and_gradients_match_oracle_fp16(mods, variant, dueling, loss_sum, per, B):
+    """precision="fp16": the same tcgen05 kernels with IEEE fp16 operands -- an 11-bit significand, exactly TF32's -- and the
+    gradient tensors scaled by a power of two (removed where weight / bias gradients are finalised).  Two tiers as for bf16:
+      (A) against the oracle with the same roundings emulated (emulate="fp16", gradient scale included):
+            Q 5e-4 of max|q|, loss 5e-4, gradients per tensor 1.5e-3 (measured 1e-4 .. 4e-4)
+      (B) against the exact float64 oracle: Q 3e-3, loss 4e-3, gradients per tensor 4.5e-2 (measured 1-3 %: the error of a
+          per-tensor gradient is dominated by the rare ReLU / max-pool decisions that flip under rounding, ~ sqrt(unit
+          round-off); the oracle's emulate="tf32" gives the same figures, so a kind::tf32 path would not do better)."""
+    _lib, game, qnet = mods
+    frames = _env_frames(game, B, 11)
+    net = qnet.QNetwork(hidden=512, dueling=dueling, max_batch=256, precision="fp16")
+    p = qo.init_params(512, dueling, seed=1) * np.float32(3.0)
+    t = qo.init_params(512, dueling, seed=2) * np.float32(3.0)
+    _set_params(net, p, t)
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 2, B).astype(np.uint8)
+    r = rng.choice(np.array([0.1, 3.0, -3.0], np.float32), B, p=[0.8, 0.1, 0.1])
+    term = (r == -3.0).astype(np.uint8)
+    isw = rng.random(B).astype(np.float32) if per else None
+    abs_err = torch.zeros(B, device="cuda"); y = torch.zeros(B, device="cuda")
+    for rep in range(3):                                                  # eager, eager, graph replay
+        net.loss_backward(variant, frames, torch.from_numpy(a).cuda(), torch.from_numpy(r).cuda(), torch.from_numpy(term).cuda(),
+                          torch.from_numpy(isw).cuda() if per else None, 0.99, loss_sum, None, abs_err, y)
+    x = frames.cpu().numpy()
+    g = net.grads.cpu().numpy().astype(np.float64)
+    assert np.isfinite(g).all()
+    L = qo.layout(512, dueling)
+    worst = {}
+    for emulate, tol_loss, tol_y, tol_g in (("fp16", 5e-4, 5e-4, 1.5e-3), (None, 4e-3, 3e-3, 4.5e-2)):
+        loss, g_ref, ae_ref, y_ref, _ = qo.loss_and_grads(qnet.VARIANTS[variant], p, t, x[:, 0:4], x[:, 1:5], a, r, term, isw, 0.99,
+                                                          loss_sum, None, 512, dueling, emulate=emulate)
+        assert abs(net.loss.item() - loss) <= tol_loss * abs(loss), (emulate, net.loss.item(), loss)
+        assert np.abs(y.cpu().numpy() - y_ref).max() <= tol_y * np.abs(y_ref).max(), emulate
+        report = {}
+        for name, v in L.items():
+            if name == "total":
+                continue
+            o, shp = v
+            sz = int(np.prod(shp))
+            report[name] = float(np.linalg.norm(g[o:o + sz] - g_ref[o:o + sz]) / np.linalg.norm(g_ref[o:o + sz]))
+        worst[emulate] = max(report.values())
+        assert all(v <= tol_g for v in report.values()), (emulate, report)
+    print("fp16 worst per-tensor gradient error: emulated %.2e, exact %.2e" % (worst["fp16"], worst[None]))
+
+
+def test_fp16_forward_and_training_step(mods):
+    """fp16 operands: Q-values against the exact oracle to 3e-3 (bf16: 2e-2), acting from the ring, and ten training steps that
+    stay with the strict fp32 path (direction of the Adam update, loss)"""
+    _lib, game, qnet = mods
+    B = 64
+    frames = _env_frames(game, B, 7)
+    flat = qo.init_params(512, False, seed=5) * np.float32(4.0)
+    net = qnet.QNetwork(max_batch=16, precision="fp16")
+    _set_params(net, flat)
+    x = frames.cpu().numpy()
+    q = net.forward(qnet.FrameBatch.from_stack(frames, 0)).cpu().numpy()
+    ref = qo.forward(torch.tensor(flat.astype(np.float64)), x[:, 0:4]).numpy()
+    emu = qo.forward(torch.tensor(flat.astype(np.float64)), x[:, 0:4], emulate="fp16").numpy()
+    assert np.abs(q - emu).max() <= 5e-4 * np.abs(emu).max(), np.abs(q - emu).max() / np.abs(emu).max()
+    assert np.abs(q - ref).max() <= 3e-3 * np.abs(ref).max(), np.abs(q - ref).max() / np.abs(ref).max()
+    nets = [qnet.QNetwork(max_batch=B, seed=3, precision=pr) for pr in ("fp16", "fp32")]
+    for n in nets:
+        n.params.mul_(3.0); n.target.mul_(3.0)
+    rng = np.random.default_rng(4)
+    p0 = nets[0].params.clone()
+    for step in range(10):
+        a = torch.from_numpy(rng.integers(0, 2, B).astype(np.uint8)).cuda()
+        r = torch.from_numpy(rng.choice(np.array([0.1, 3.0, -3.0], np.float32), B)).cuda()
+        term = (r == -3.0).to(torch.uint8)
+        nets[0].train_step("nature", frames, a, r, term)                  # one graph launch, Adam inside
+        nets[1].loss_backward("nature", frames, a, r, term); nets[1].adam_step()
+        if step == 4:
+            for n in nets:
+                n.sync_target()
+    u0, u1 = (nets[0].params - p0).double(), (nets[1].params - p0).double()
+    cos = (u0 @ u1 / (u0.norm() * u1.norm())).item()
+    assert u1.abs().max().item() > 5e-6 and cos > 0.995, cos
+    assert abs(nets[0].loss.item() - nets[1].loss.item()) <= 4e-3 * abs(nets[1].loss.item())
