@@ -530,7 +530,7 @@ def bench_learner(args, rank, world, dev):
     # workspace contents.  At the update's own batch its operands are L2-resident by construction; at the acting chunk
     # (2048 samples: 116 MB of operands + 58 MB of output > L2) they stream from HBM.
     kern = None
-    if args.learner_precision == "bf16":
+    if args.learner_precision in ("bf16", "fp16"):
         from dqnflappybird_b200 import _lib
         L = _lib.lib()
         st = torch.cuda.current_stream().cuda_stream
@@ -575,6 +575,28 @@ def bench_learner(args, rank, world, dev):
                 dist.all_reduce(tv, op=dist.ReduceOp.MAX)
             variants[name] = {"updates_per_s": 1e3 / float(tv[0]), "ms_per_update": float(tv[0])}
             del vb
+    # ---- the same update at the three precisions of the library, side by side (fixed minibatch of the configured size; one
+    # graph launch each on the tensor-core paths): fp32 = CUDA-core FMA (the strict anchor), bf16 = 8-bit significand, fp16 =
+    # 11-bit significand (TF32's), the default
+    by_precision = {}
+    if not args.no_learner_variants and world == 1:
+        from dqnflappybird_b200.qnet import QNetwork
+        mbp = brain.replayMemory.sample(brain.local_batch)
+        fr, ac, rw, tm = mbp.frames.clone(), mbp.actions.clone(), mbp.rewards.clone(), mbp.terminals.clone()
+        for prec in ("fp32", "bf16", "fp16"):
+            netp = QNetwork(device=dev, max_batch=brain.local_batch, precision=prec, seed=0)
+            for _ in range(4):
+                netp.train_step("nature", fr, ac, rw, tm)
+            sync()
+            Kp = K if prec != "fp32" else max(5, K // 5)
+            e0.record()
+            for _ in range(Kp):
+                netp.train_step("nature", fr, ac, rw, tm)
+            e1.record(); sync()
+            msp = e0.elapsed_time(e1) / Kp
+            by_precision[prec] = {"updates_per_s": 1e3 / msp, "ms_per_update": msp, "compute_path": netp.compute_path,
+                                  "includes": "update on a fixed minibatch (no sampling / gather)"}
+            del netp
     # ---- minibatch sweep (BrainDQNNature): the 256 of configs[2] is launch/latency-bound on a B200; the same step at
     # larger minibatches shows what the kernels sustain
     sweep = {str(B): {"updates_per_s": 1e3 / ms_upd, "transitions_per_s": B * 1e3 / ms_upd, "includes": "sample + gather + update"}}
@@ -621,6 +643,7 @@ def bench_learner(args, rank, world, dev):
             "act_envs_per_s": N * world / (ms_act * 1e-3), "ms_per_act": ms_act,
             "act_tflops_per_gpu": N * FLOP_FWD / (ms_act * 1e-3) / 1e12,
             "transitions_per_s": B * 1e3 / ms_upd, "scaling": args.learner_scaling, "cpu_baseline": cpu_upd, "variants": variants, "minibatch_sweep": sweep,
+            "by_precision": by_precision, "precision": args.learner_precision,
             "ms_per_update_without_exchange": ms_local,
             "exchange_us": None if ms_local is None else (ms_upd - ms_local) * 1e3,
             "weak_efficiency_in_run": None if ms_local is None else ms_local / ms_upd,
@@ -654,7 +677,7 @@ def main():
     ap.add_argument("--learner-envs", type=int, default=16384)
     ap.add_argument("--learner-batch", type=int, default=256)
     ap.add_argument("--learner-updates", type=int, default=50)
-    ap.add_argument("--learner-precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--learner-precision", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--learner-scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-learner-variants", action="store_true")
     ap.add_argument("--reference-budget-s", type=float, default=120.0, help="--impl reference: CPU seconds for warm-up + all steps")

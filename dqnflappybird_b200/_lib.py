@@ -150,6 +150,7 @@ _SIGNATURES = {
     "fb_per_sample": ([_vp, C.c_int, C.c_double, C.c_uint64, _i32p, _i32p, _vp, _vp, _f32p, _vp], C.c_int),
     "fb_per_update": ([_vp, _i32p, _f32p, _vp, C.c_int, C.c_int, _vp], C.c_int),
     "fb_per_tree_copy": ([_vp, _vp, C.c_int, _vp], C.c_int),
+    "fb_per_aux_tree_copy": ([_vp, C.c_int, _vp, C.c_int, _vp], C.c_int),
     "fb_replay_rng_pos": ([_vp, _vp, C.c_int, _vp], C.c_int),
     "fb_debug_assets_load_host": ([C.c_char_p, C.c_size_t], C.c_int),
     "fb_debug_host_reset": ([_i32p, _u8p, C.c_int, C.c_uint64, C.c_uint64], C.c_int),

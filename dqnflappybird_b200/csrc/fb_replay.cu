@@ -408,11 +408,19 @@ __global__ void store_leaves_kernel(int N, int C, long long k, int32_t *leaves) 
     leaves[e] = (N * C - 1) + e * C + (int)((k - 1) % C);
 }
 
+__global__ void fill_inf_kernel(double *p, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = __longlong_as_double(0x7FF0000000000000ll);
+}
+constexpr size_t kTopSmem = sizeof(Node3) * kTopNodes;          // 49,128 bytes: depths 0..10 of the three trees
+static int node_depth_host(int idx) { int d = 0; for (unsigned v = (unsigned)idx + 1; v > 1; v >>= 1) d++; return d; }
+
 // ------------------------------------------------------------------------------ C ABI
 struct fb_replay {
     int N, L, C, cap;
     double *tree;                    // PER only
-    unsigned long long *minmax;      // [0] max leaf bits, [1] min positive leaf bits
+    double *mn, *mx;                 // min-positive / max trees of the same shape (see the SumTree section)
+    unsigned int *counters;          // [0] per_store_multi_kernel, [1] per_sample_kernel: "last CTA" counters, self-resetting
     int32_t *leaves; double *prio; double *change;   // scratch, max(N, max_batch)
     uint32_t *word_pos;              // [0] uniform stream, [1] PER stream
     int scratch_n;
@@ -428,14 +436,24 @@ extern "C" int fb_replay_create(int n_envs, int ring_len, int capacity_per_env, 
     r->scratch_n = n_envs > max_batch ? n_envs : max_batch;
     FB_CUDA_OK(cudaMalloc(&r->word_pos, 2 * sizeof(uint32_t)));
     FB_CUDA_OK(cudaMemset(r->word_pos, 0, 2 * sizeof(uint32_t)));
-    FB_CUDA_OK(cudaMalloc(&r->minmax, 2 * sizeof(unsigned long long)));
-    { const unsigned long long armed[2] = {0ull, ~0ull}; FB_CUDA_OK(cudaMemcpy(r->minmax, armed, sizeof(armed), cudaMemcpyHostToDevice)); }
+    r->mn = r->mx = nullptr;
+    FB_CUDA_OK(cudaMalloc(&r->counters, 2 * sizeof(unsigned int)));
+    FB_CUDA_OK(cudaMemset(r->counters, 0, 2 * sizeof(unsigned int)));
     FB_CUDA_OK(cudaMalloc(&r->leaves, sizeof(int32_t) * r->scratch_n));
     FB_CUDA_OK(cudaMalloc(&r->prio, sizeof(double) * r->scratch_n));
     FB_CUDA_OK(cudaMalloc(&r->change, sizeof(double) * r->scratch_n));
     if (prioritized) {
-        FB_CUDA_OK(cudaMalloc(&r->tree, sizeof(double) * (2 * (size_t)r->cap - 1)));
-        FB_CUDA_OK(cudaMemset(r->tree, 0, sizeof(double) * (2 * (size_t)r->cap - 1)));
+        const size_t nn = 2 * (size_t)r->cap - 1;
+        FB_CUDA_OK(cudaMalloc(&r->tree, sizeof(double) * nn));
+        FB_CUDA_OK(cudaMemset(r->tree, 0, sizeof(double) * nn));
+        FB_CUDA_OK(cudaMalloc(&r->mn, sizeof(double) * nn));
+        FB_CUDA_OK(cudaMalloc(&r->mx, sizeof(double) * nn));
+        FB_CUDA_OK(cudaMemset(r->mx, 0, sizeof(double) * nn));
+        fill_inf_kernel<<<(unsigned)((nn + 255) / 256), 256>>>(r->mn, nn);
+        FB_CUDA_OK(cudaGetLastError());
+        FB_CUDA_OK(cudaFuncSetAttribute(tree_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTopSmem));
+        FB_CUDA_OK(cudaFuncSetAttribute(per_store_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTopSmem));
+        FB_CUDA_OK(cudaDeviceSynchronize());
     }
     *out = r;
     return FB_OK;
@@ -443,7 +461,7 @@ extern "C" int fb_replay_create(int n_envs, int ring_len, int capacity_per_env, 
 
 extern "C" int fb_replay_destroy(fb_replay *r) {
     if (!r) return FB_OK;
-    cudaFree(r->tree); cudaFree(r->minmax); cudaFree(r->leaves); cudaFree(r->prio); cudaFree(r->change); cudaFree(r->word_pos);
+    cudaFree(r->tree); cudaFree(r->mn); cudaFree(r->mx); cudaFree(r->counters); cudaFree(r->leaves); cudaFree(r->prio); cudaFree(r->change); cudaFree(r->word_pos);
     delete r;
     return FB_OK;
 }
@@ -473,13 +491,10 @@ extern "C" int fb_replay_gather(fb_replay *r, const uint8_t *ring_dev, const uin
     return FB_OK;
 }
 
-// leaf scan into r->minmax, which is armed ({0, ~0}) at create and re-armed by the scan's one consumer
-// (tree_update_kernel on the store path, per_sample_kernel on the sample path)
-static int refresh_minmax(fb_replay *r, cudaStream_t st) {
-    int blocks = (r->cap + 255) / 256; if (blocks > 592) blocks = 592;
-    leaf_minmax_kernel<<<blocks, 256, 0, st>>>(r->tree, r->cap, r->minmax);
-    FB_CUDA_OK(cudaGetLastError());
-    return FB_OK;
+static void launch_per_sample(fb_replay *r, int batch, double beta, uint64_t seed, int32_t *tree_idx, int32_t *data_idx, double *isw, double *prio,
+                              float *isw32, cudaStream_t st) {
+    per_sample_kernel<<<(batch + kSampleWarps - 1) / kSampleWarps, 32 * kSampleWarps, 0, st>>>(r->tree, r->mn, r->cap, batch, beta, seed, r->word_pos + 1,
+                                                                                               r->counters + 1, tree_idx, data_idx, isw, prio, isw32);
 }
 
 // ---- sampling + gather as the head of a captured training step (fb_qnet_train_step_sampled) -------------------------
@@ -501,10 +516,7 @@ int replay_launch_sample_gather(const fb_step_sampling &p, cudaStream_t st) {
     if (p.prioritized) {
         FB_REQUIRE(r->tree && p.tree_idx_out_dev && p.is_weights_out_dev && p.is_weights_f32_out_dev && (p.per_mode == 0 || p.per_mode == 1) &&
                    p.batch <= r->scratch_n, "step sampling: prioritized replay arguments");
-        int rc = refresh_minmax(r, st); if (rc) return rc;
-        per_sample_kernel<<<1, ((p.batch + 31) / 32) * 32, 0, st>>>(r->tree, r->cap, p.batch, p.beta, r->minmax, p.seed, r->word_pos + 1,
-                                                                    p.tree_idx_out_dev, p.idx_out_dev, p.is_weights_out_dev, p.prio_out_dev,
-                                                                    p.is_weights_f32_out_dev);
+        launch_per_sample(r, p.batch, p.beta, p.seed, p.tree_idx_out_dev, p.idx_out_dev, p.is_weights_out_dev, p.prio_out_dev, p.is_weights_f32_out_dev, st);
     } else {
         FB_REQUIRE(p.setsize <= 2u * kHashSize, "step sampling: setsize too large");
         uint32_t n;
@@ -518,7 +530,7 @@ int replay_launch_sample_gather(const fb_step_sampling &p, cudaStream_t st) {
 int replay_launch_per_update(const fb_step_sampling &p, const float *abs_err_dev, cudaStream_t st) {
     FB_REQUIRE(p.prioritized && abs_err_dev, "step sampling: Memory.batch_update needs the step's |TD errors| (abs_err_out_dev)");
     fb_replay *r = p.replay;
-    tree_update_kernel<<<1, 1024, 0, st>>>(r->tree, r->cap, p.tree_idx_out_dev, nullptr, nullptr, p.batch, p.per_mode, r->change, abs_err_dev, r->prio);
+    tree_update_kernel<<<1, 1024, kTopSmem, st>>>(r->tree, r->mn, r->mx, r->cap, p.tree_idx_out_dev, nullptr, p.batch, p.per_mode, r->change, abs_err_dev, r->prio);
     FB_CUDA_OK(cudaGetLastError());
     return FB_OK;
 }
@@ -529,10 +541,11 @@ int replay_patch_nodes(cudaGraphExec_t exec, cudaGraphNode_t sampler, cudaGraphN
     cudaKernelNodeParams kp{};
     int batch = p.batch; uint64_t seed = p.seed; int32_t *idx = p.idx_out_dev;
     if (p.prioritized) {
-        const double *tree = r->tree; int cap = r->cap; double beta = p.beta; unsigned long long *minmax = r->minmax; uint32_t *word_pos = r->word_pos + 1;
+        const double *tree = r->tree, *mn = r->mn; int cap = r->cap; double beta = p.beta; uint32_t *word_pos = r->word_pos + 1;
+        unsigned int *done = r->counters + 1;
         int32_t *tree_idx = p.tree_idx_out_dev; double *isw = p.is_weights_out_dev, *prio = p.prio_out_dev; float *isw32 = p.is_weights_f32_out_dev;
-        void *sargs[] = {&tree, &cap, &batch, &beta, &minmax, &seed, &word_pos, &tree_idx, &idx, &isw, &prio, &isw32};
-        kp.func = (void *)per_sample_kernel; kp.gridDim = dim3(1); kp.blockDim = dim3(((p.batch + 31) / 32) * 32); kp.kernelParams = sargs;
+        void *sargs[] = {&tree, &mn, &cap, &batch, &beta, &seed, &word_pos, &done, &tree_idx, &idx, &isw, &prio, &isw32};
+        kp.func = (void *)per_sample_kernel; kp.gridDim = dim3((p.batch + kSampleWarps - 1) / kSampleWarps); kp.blockDim = dim3(32 * kSampleWarps); kp.kernelParams = sargs;
         FB_CUDA_OK(cudaGraphExecKernelNodeSetParams(exec, sampler, &kp));
     } else {
         uint32_t n;
@@ -554,9 +567,16 @@ int replay_patch_nodes(cudaGraphExec_t exec, cudaGraphNode_t sampler, cudaGraphN
 extern "C" int fb_per_store(fb_replay *r, long long k, int mode, void *stream) {
     FB_REQUIRE(r && r->tree && k >= 1 && (mode == 0 || mode == 1), "fb_per_store: bad argument (is the replay prioritized?)");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = refresh_minmax(r, st); if (rc) return rc;
+    if (mode == 1 && r->N >= kStoreMultiMin && node_depth_host(2 * r->cap - 2) > kTopDepth + 1) {      // one CTA per group of sub-trees
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        per_store_multi_kernel<<<sms, 256, kTopSmem, st>>>(r->tree, r->mn, r->mx, r->cap, r->N, r->C, (int)((k - 1) % r->C), r->counters);
+        FB_CUDA_OK(cudaGetLastError());
+        return FB_OK;
+    }
     store_leaves_kernel<<<(r->N + 255) / 256, 256, 0, st>>>(r->N, r->C, k, r->leaves);
-    tree_update_kernel<<<1, 1024, 0, st>>>(r->tree, r->cap, r->leaves, nullptr, r->minmax, r->N, mode, r->change, nullptr, nullptr);
+    tree_update_kernel<<<1, 1024, kTopSmem, st>>>(r->tree, r->mn, r->mx, r->cap, r->leaves, nullptr, r->N, mode, r->change, nullptr, nullptr);
     FB_CUDA_OK(cudaGetLastError());
     return FB_OK;
 }
@@ -565,9 +585,7 @@ extern "C" int fb_per_sample(fb_replay *r, int batch, double beta, uint64_t seed
                              double *is_weights_dev, double *prio_out_dev, float *is_weights_f32_dev, void *stream) {
     FB_REQUIRE(r && r->tree && batch > 0 && batch <= 512 && tree_idx_dev && data_idx_dev && is_weights_dev, "fb_per_sample: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = refresh_minmax(r, st); if (rc) return rc;
-    per_sample_kernel<<<1, ((batch + 31) / 32) * 32, 0, st>>>(r->tree, r->cap, batch, beta, r->minmax, seed, r->word_pos + 1,
-                                                            tree_idx_dev, data_idx_dev, is_weights_dev, prio_out_dev, is_weights_f32_dev);
+    launch_per_sample(r, batch, beta, seed, tree_idx_dev, data_idx_dev, is_weights_dev, prio_out_dev, is_weights_f32_dev, st);
     FB_CUDA_OK(cudaGetLastError());
     return FB_OK;
 }
@@ -578,8 +596,8 @@ extern "C" int fb_per_update(fb_replay *r, const int32_t *tree_idx_dev, const fl
     FB_REQUIRE(r && r->tree && tree_idx_dev && (abs_err_dev || prio_dev) && batch > 0 && batch <= r->scratch_n && (mode == 0 || mode == 1),
                "fb_per_update: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    tree_update_kernel<<<1, 1024, 0, st>>>(r->tree, r->cap, tree_idx_dev, prio_dev, nullptr, batch, mode, r->change,
-                                           prio_dev ? nullptr : abs_err_dev, r->prio);
+    tree_update_kernel<<<1, 1024, kTopSmem, st>>>(r->tree, r->mn, r->mx, r->cap, tree_idx_dev, prio_dev, batch, mode, r->change,
+                                                  prio_dev ? nullptr : abs_err_dev, r->prio);
     FB_CUDA_OK(cudaGetLastError());
     return FB_OK;
 }
@@ -587,6 +605,13 @@ extern "C" int fb_per_update(fb_replay *r, const int32_t *tree_idx_dev, const fl
 extern "C" int fb_per_tree_copy(fb_replay *r, double *out_dev, int n_nodes, void *stream) {
     FB_REQUIRE(r && r->tree && out_dev && n_nodes == 2 * r->cap - 1, "fb_per_tree_copy: bad argument");
     FB_CUDA_OK(cudaMemcpyAsync(out_dev, r->tree, sizeof(double) * (size_t)n_nodes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return FB_OK;
+}
+
+// which = 1: the min-positive tree, 2: the max tree (same shape as the SumTree; test hook for their invariants)
+extern "C" int fb_per_aux_tree_copy(fb_replay *r, int which, double *out_dev, int n_nodes, void *stream) {
+    FB_REQUIRE(r && r->tree && out_dev && n_nodes == 2 * r->cap - 1 && (which == 1 || which == 2), "fb_per_aux_tree_copy: bad argument");
+    FB_CUDA_OK(cudaMemcpyAsync(out_dev, which == 1 ? r->mn : r->mx, sizeof(double) * (size_t)n_nodes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return FB_OK;
 }
 

@@ -55,7 +55,7 @@ class FrameBatch:
 class QNetwork:
     def __init__(self, device="cuda:0", hidden: int = 512, dueling: bool = False, max_batch: int = 256, seed: int = 0,
                  lr: float = 1e-6, beta1: float = 0.9, beta2: float = 0.999, adam_eps: float = 1e-8,
-                 copy_target_at_init: bool = False, precision: str = "bf16"):
+                 copy_target_at_init: bool = False, precision: str = "fp16"):
         if not torch.cuda.is_available():
             raise _lib.FlappyError("QNetwork needs a CUDA device (B200); there is no CPU path")
         self.device = torch.device(device)

@@ -190,6 +190,14 @@ class PrioritizedMemory(ReplayMemory):
         _lib.check(self._L.fb_per_tree_copy(self._h, out.data_ptr(), n, self._stream()), "fb_per_tree_copy")
         return out
 
+    def aux_tree(self, which: str) -> torch.Tensor:
+        """copy of the min-positive-leaf ("min") or max-leaf ("max") tree kept beside the SumTree (same shape): the device
+        reads Memory.sample's min_prob and Memory.store's max priority from their roots instead of scanning the leaves"""
+        n = 2 * self.N * self.C - 1
+        out = torch.empty(n, dtype=torch.float64, device=self.device)
+        _lib.check(self._L.fb_per_aux_tree_copy(self._h, {"min": 1, "max": 2}[which], out.data_ptr(), n, self._stream()), "fb_per_aux_tree_copy")
+        return out
+
     @property
     def total_p(self) -> float:
         return float(self.tree()[0].item())

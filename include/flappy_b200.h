@@ -297,6 +297,8 @@ int fb_per_sample(fb_replay *r, int batch, double beta, uint64_t seed, int32_t *
 int fb_per_update(fb_replay *r, const int32_t *tree_idx_dev, const float *abs_err_dev, const double *prio_dev, int batch, int mode, void *stream);
 /* copy of the SumTree array (f64[2*N*C-1]) for inspection / checkpoints */
 int fb_per_tree_copy(fb_replay *r, double *out_dev, int n_nodes, void *stream);
+/* test hook: the min-positive-leaf tree (which = 1) or the max-leaf tree (2) kept beside the SumTree, same shape */
+int fb_per_aux_tree_copy(fb_replay *r, int which, double *out_dev, int n_nodes, void *stream);
 int fb_replay_rng_pos(fb_replay *r, uint32_t *pos_host2, int set, void *stream);
 
 /* The minibatch of fb_qnet_train_step drawn INSIDE the step: random.sample + the list comprehensions of BrainDQN.py:197-201

@@ -96,7 +96,25 @@ def test_gather_returns_the_right_transitions(mods, T):
         _check_minibatch(mb, hf, ha, hr, ht)
 
 
-@pytest.mark.parametrize("N,C,mode", [(1, 50, "reference"), (1, 1000, "reference"), (4, 64, "rebuild"), (4, 64, "reference")])
+def _check_aux_trees(mem, cap):
+    """the min-positive-leaf and max-leaf trees kept beside the SumTree (what replaced round 1's full leaf scans): leaves mirror
+    the SumTree's, every inner node is the exact min / max of its children, so the roots are min_p / max_p over all leaves"""
+    tree, mn, mx = mem.tree(), mem.aux_tree("min"), mem.aux_tree("max")
+    leaves = tree[cap - 1:]
+    inf = torch.tensor(float("inf"), dtype=torch.float64, device=tree.device)
+    assert torch.equal(mx[cap - 1:], leaves) and torch.equal(mn[cap - 1:], torch.where(leaves > 0, leaves, inf))
+    inner = torch.arange(cap - 1, device=tree.device)
+    assert torch.equal(mn[inner], torch.minimum(mn[2 * inner + 1], mn[2 * inner + 2]))
+    assert torch.equal(mx[inner], torch.maximum(mx[2 * inner + 1], mx[2 * inner + 2]))
+    assert mx[0].item() == leaves.max().item()
+    if bool((leaves > 0).any()):
+        assert mn[0].item() == leaves[leaves > 0].min().item()
+
+
+# (4096, 8, "rebuild"): 4,096 stores per step take the multi-CTA store kernel (one CTA per group of depth-11 sub-trees); the
+# capacity 32,768 is a power of two, (3000, 11) is not (leaves on two levels)
+@pytest.mark.parametrize("N,C,mode", [(1, 50, "reference"), (1, 1000, "reference"), (4, 64, "rebuild"), (4, 64, "reference"),
+                                      (4096, 8, "rebuild"), (3000, 11, "rebuild")])
 def test_sumtree_matches_reference_semantics(mods, N, C, mode):
     """store / sample / batch_update sequence: tree array bit-identical to the oracle (itself pinned to the
     reference classes), sampled tree indices identical, IS weights to 1e-12."""
@@ -107,7 +125,7 @@ def test_sumtree_matches_reference_semantics(mods, N, C, mode):
     orc = ro.Memory(N, C, seed=31, mode=mode)
     rng = np.random.default_rng(3)
     B = 32 if N * C >= 64 else 8
-    for k in range(1, 3 * C + 7):
+    for k in range(1, (3 * C + 7) if N <= 1000 else (2 * C + 6)):
         mem.appended(k); orc.store_step(k)
         if k >= 12 and k % 2 == 0:
             mb = mem.sample(B)
@@ -121,9 +139,11 @@ def test_sumtree_matches_reference_semantics(mods, N, C, mode):
             ps = ro.Memory.priorities(rng.random(B) * rng.choice([0.02, 0.7, 3.0])).astype(np.float64)
             mem.batch_update(mb.tree_idx, priorities=torch.from_numpy(ps).cuda())
             orc.batch_update(idx, ps)
-        if k % 25 == 0:
+        if k % 25 == 0 or (N > 1000 and k % 5 == 0):
             np.testing.assert_array_equal(mem.tree().cpu().numpy(), orc.sum_tree.tree, err_msg=f"tree k={k}")
+            _check_aux_trees(mem, N * C)
     np.testing.assert_array_equal(mem.tree().cpu().numpy(), orc.sum_tree.tree)
+    _check_aux_trees(mem, N * C)
     assert mem.rng_positions()[1] == orc.pos
 
 
@@ -190,8 +210,37 @@ def test_full_size_sumtree_properties(mods):
             assert float(mb.is_weights.max()) <= 1.0 + 1e-12
             err = torch.rand(B, device="cuda", generator=g) * 2.0
             mem.batch_update(mb.tree_idx, abs_errors=err)
+    _check_aux_trees(mem, cap)
     tree = mem.tree()
     inner = torch.arange(cap - 1, device="cuda")
     assert torch.equal(tree[inner], tree[2 * inner + 1] + tree[2 * inner + 2])       # exact: parents are recomputed, never drifted
     torch.testing.assert_close(tree[0], tree[cap - 1:].sum(), rtol=1e-9, atol=0)
     assert int((tree[cap - 1:] > 0).sum()) == cap                                     # the memory wrapped: every leaf was stored
+
+
+def test_configs3_shard_size_prioritized_memory(mods):
+    """BASELINE configs[3]: 65,536 envs over 8 GPUs = 8,192 envs per rank.  One rank's prioritized memory at that size (8,192 x
+    28 = 229,376 leaves, not a power of two): stores through the multi-CTA kernel, samples through the warp-cooperative descent,
+    priority updates; the SumTree stays exactly parents = left + right, the min / max trees stay exact, sampled leaves are live
+    and the IS weights follow (p / min_p)^-beta with min_p over ALL leaves"""
+    game, replay = mods
+    N, C, B = 8192, 28, 32
+    ring = torch.zeros((N, C + 4, 80, 80), dtype=torch.uint8, device="cuda")
+    mem = replay.PrioritizedMemory(ring, C, seed=9, max_batch=B)
+    cap = N * C
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for k in range(1, C + 9):
+        mem.appended(k)
+        if k % 4 == 0:
+            mb = mem.sample(B)
+            tree = mem.tree()
+            leaves = tree[cap - 1:]
+            d = mb.tree_idx.long() - (cap - 1)
+            assert bool((leaves[d] > 0).all())
+            want_w = (leaves[d] / leaves[leaves > 0].min()) ** (-mem.beta)
+            torch.testing.assert_close(mb.is_weights, want_w, rtol=1e-12, atol=0)
+            mem.batch_update(mb.tree_idx, abs_errors=torch.rand(B, device="cuda", generator=g) * 2.0)
+    _check_aux_trees(mem, cap)
+    tree = mem.tree()
+    inner = torch.arange(cap - 1, device="cuda")
+    assert torch.equal(tree[inner], tree[2 * inner + 1] + tree[2 * inner + 2])
