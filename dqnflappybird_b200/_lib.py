@@ -114,6 +114,7 @@ _SIGNATURES = {
     "fb_qnet_invalidate": ([_vp], C.c_int),
     "fb_qnet_set_per_broadcast": ([_vp, C.c_int], C.c_int),
     "fb_debug_poison_packed": ([_vp, C.c_int, _vp], C.c_int),
+    "fb_debug_write_probe": ([_vp, C.c_int, C.c_longlong, C.c_int, C.c_int, _vp], C.c_int),
     "fb_qnet_use_graphs": ([_vp, C.c_int], C.c_int),
     "fb_qnet_set_conv1_mode": ([_vp, C.c_int], C.c_int),
     "fb_qnet_set_fused_backward": ([_vp, C.c_int], C.c_int),

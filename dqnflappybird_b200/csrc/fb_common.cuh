@@ -68,7 +68,14 @@ struct ObsTables {                           // copied to shared memory by the s
 
 static_assert(sizeof(ObsTables) % 16 == 0, "ObsTables is copied with 16-byte loads");
 
-struct ExactTables {                         // global memory; rare exact path + collision + full render
+struct HitTables {                           // HITMASKS of flappy_bird_utils.getHitmask as bit rows: 5,696 bytes, copied to shared memory
+    unsigned long long birdRow[3][kBirdH];   // hitmask bit rows: bit x of row r  (getHitmask)
+    unsigned long long pipeRowLo[kPipeH];    // lower-pipe hitmask bit rows
+    unsigned long long pipeRowUp[kPipeH];    // upper (rotated 180) pipe
+};
+static_assert(sizeof(HitTables) % 16 == 0, "HitTables is copied with 16-byte loads");
+
+struct ExactTables {                         // global memory; rare exact path + full render; begins with the HitTables members
     unsigned long long birdRow[3][kBirdH];   // hitmask bit rows: bit x of row r  (getHitmask)
     unsigned long long pipeRowLo[kPipeH];    // lower-pipe hitmask bit rows
     unsigned long long pipeRowUp[kPipeH];    // upper (rotated 180) pipe

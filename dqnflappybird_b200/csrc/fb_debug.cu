@@ -90,3 +90,42 @@ extern "C" int fb_debug_step_sampling_layout(int32_t *out, int capacity) {
     for (int i = 0; i < n; i++) out[i] = v[i];
     return n;
 }
+
+// ---- write-pattern probe (tools/write_bw_probe.py): how fast can the device absorb the env kernel's output pattern? ---------
+// n_chunks chunks of 6,400 bytes, chunk k at dst + k * stride_bytes.  mode 0: one warp per chunk, 16-byte streaming stores
+// straight from registers; mode 1: one warp per chunk through a shared-memory staging frame and cp.async.bulk (the step
+// kernel's path).  No computation: whatever this reaches is the ceiling of a frame-writing kernel for that layout.
+__global__ void __launch_bounds__(256) write_probe_kernel(uint8_t *dst, int n_chunks, long long stride_bytes, int mode) {
+    extern __shared__ __align__(128) uint8_t stage_all[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *stage = stage_all + warp * 6400;
+    const long long W = (long long)gridDim.x * 8, w = (long long)blockIdx.x * 8 + warp;
+    const int lo = (int)((long long)n_chunks * w / W), hi = (int)((long long)n_chunks * (w + 1) / W);
+    if (mode == 1) {
+        for (int i = lane; i < 400; i += 32) reinterpret_cast<uint4 *>(stage)[i] = make_uint4(i, lane, 0xFFFFFFFFu, 0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+    }
+    for (int k = lo; k < hi; k++) {
+        uint8_t *out = dst + (long long)k * stride_bytes;
+        if (mode == 0) {
+            const uint4 v = make_uint4(k, lane, 0xFFFFFFFFu, 0);
+#pragma unroll
+            for (int it = 0; it < 13; it++) { int c = lane + 32 * it; if (c < 400) __stcs(reinterpret_cast<uint4 *>(out) + c, v); }
+        } else if (lane == 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 6400;" ::"l"(reinterpret_cast<uint64_t>(out)),
+                         "r"((uint32_t)__cvta_generic_to_shared(stage)) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (mode == 1 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+extern "C" int fb_debug_write_probe(uint8_t *dst_dev, int n_chunks, long long stride_bytes, int mode, int ctas, void *stream) {
+    FB_REQUIRE(dst_dev && n_chunks > 0 && stride_bytes >= 6400 && (mode == 0 || mode == 1) && ctas > 0, "fb_debug_write_probe: bad argument");
+    FB_CUDA_OK(cudaFuncSetAttribute(write_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 6400));
+    write_probe_kernel<<<ctas, 256, 8 * 6400, (cudaStream_t)stream>>>(dst_dev, n_chunks, stride_bytes, mode);
+    FB_CUDA_OK(cudaGetLastError());
+    return FB_OK;
+}

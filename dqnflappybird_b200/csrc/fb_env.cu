@@ -5,13 +5,12 @@
 //   game/wrapped_flappy_bird.py:165-177  the pygame blits and surfarray.array3d
 //   FlappyBirdDQN.py:31-34               cv2.resize(80x80) / cvtColor / threshold
 //
-// Kernel shape.  A CTA owns EPC envs for the whole launch (state stays in registers across the
-// n_steps of one launch).  Per step: (1) one thread per env runs the integer physics and posts a
-// 16-byte draw list to shared memory; (2) one warp per env builds the 80 observation rows as
-// 64-bit masks (pipe rows and bird windows come from tables derived from the sprites with cv2's
-// exact fixed-point arithmetic; the rare rows where bird and pipe pixels share a 2x2 tap
-// footprint are evaluated per pixel) and streams the 6400-byte frame into the ring with 16-byte
-// stores, 512 contiguous bytes per warp instruction.  No full-resolution frame exists anywhere.
+// Kernel shape.  Persistent and warp-centric (see env_step_kernel): every resident warp owns an equal, contiguous share of
+// the envs; 32 envs at a time, each lane runs one env's integer physics (collision against the hitmask bit rows held in shared
+// memory) and posts a 16-byte draw list; the warp then draws those envs one after another: 80 observation rows as 64-bit masks
+// (pipe rows and bird windows come from tables derived from the sprites with cv2's exact fixed-point arithmetic; the rare rows
+// where bird and pipe pixels share a 2x2 tap footprint are evaluated per pixel), expanded to bytes through a 256-entry table
+// and streamed into the ring with 16-byte stores, 512 contiguous bytes per warp instruction.  No full-resolution frame exists.
 #include <new>
 
 #include "fb_env_logic.cuh"
@@ -32,6 +31,7 @@ struct fb_env {
     cudaEvent_t ev_in[2], ev_step[2], ev_out[2];
     unsigned long long submitted, waited;   // host-step tickets
     int num_sms;
+    int step_slots;                         // resident CTAs of env_step_kernel on this device (0 until the first launch)
 };
 
 struct StepArgs {
@@ -60,17 +60,42 @@ __device__ __forceinline__ uint32_t expand4(uint32_t nib) {      // 4 bits -> 4 
     return ((nib * 0x00204081u) & 0x01010101u) * 255u;
 }
 
-// One warp draws one env's 80x80 observation.
-__device__ __forceinline__ void render_env(const ObsTables &T, const ExactTables *ex, const DrawList d,
+// One warp draws one env's 80x80 observation.  Measured on the B200 (tools/write_bw_probe.py, fb_debug_write_probe): a kernel
+// that only WRITES 131,072 frames of 6,400 bytes reaches 5.75 TB/s with 16 resident warps per SM and 6.3 TB/s with 32 --
+// whether the bytes leave as 16-byte streaming stores or as cp.async.bulk copies from shared memory, whether the frames are
+// contiguous or 25,600 bytes apart.  What a frame-writing kernel needs is stores IN FLIGHT (~200 KB per SM); staging frames in
+// shared memory caps the resident warps at 16 beside the 37 KB of tables (measured: 0.79 of the copy peak, below round 1's
+// register-store kernel).  So: stores straight from registers, 32 warps per SM (<= 64 registers), and fewer instructions per
+// frame than round 1 (~730 issued per frame at 20 warps per SM):
+//   * lane l computes the masks of rows l, l + 32, l + 64; what depends only on the row (first source column, phase in cv2's
+//     5-row coefficient cycle) is computed once per kernel (RowConst);
+//   * bits -> bytes through a 256-entry table (8 bits -> 8 bytes, 2 KB of shared memory) instead of multiply-and-mask;
+//   * 16-byte chunk c = lane + 32 it of the frame (row c / 5, columns 16 (c % 5) ..): one warp instruction writes 512 contiguous bytes.
+struct RowConst { int sx[3], ph5[3]; };
+
+__device__ __forceinline__ unsigned long long row_mask_fast(const ObsTables &T, const DrawList &d, int i, int sx, int ph5, int j0) {
+    const int np = d.np_mixed & 15;
+    unsigned long long m = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        unsigned c = (unsigned)(sx - d.px[k] + 1);
+        if (k < np && c < 54u) m |= T.pipeObs[c][ph5][d.gap[k]];
+    }
+    unsigned r = (unsigned)(i - 16);
+    if (r < (unsigned)kBirdRows) m |= (unsigned long long)T.birdObs[d.pidx][d.y][r] << j0;
+    return m | (1ull << 63);
+}
+
+__device__ __forceinline__ void render_env(const ObsTables &T, const uint2 *lut8, const ExactTables *ex, const DrawList d, const RowConst &rc,
                                            unsigned long long *rowmask, uint8_t *out, int lane) {
     const int j0 = T.birdJ0[d.y];
 #pragma unroll
     for (int it = 0; it < 3; it++) {
-        int i = lane + 32 * it;
-        if (i < kObs) rowmask[i] = obs_row_mask(T, d, i);
+        const int i = lane + 32 * it;
+        if (i < kObs) rowmask[i] = row_mask_fast(T, d, i, rc.sx[it], rc.ph5[it], j0);
     }
     __syncwarp();
-    if (d.np_mixed & 16) {                           // rare: evaluate the bird window per pixel
+    if (d.np_mixed & 16) {                           // rare (warp-uniform): evaluate the bird window per pixel
 #pragma unroll 1
         for (int q = 0; q < 3; q++) {
             int idx = q * 32 + lane, r = idx >> 3, j = j0 + (idx & 7);
@@ -78,64 +103,78 @@ __device__ __forceinline__ void render_env(const ObsTables &T, const ExactTables
             if (r < kBirdRows && j < kBaseJ) bit = exact_obs_bit(ex, d, 0, false, 16 + r, j);
             unsigned bal = __ballot_sync(0xFFFFFFFFu, bit);
             int rr = 4 * q + lane;
-            if (lane < 4 && rr < kBirdRows) {
-                rowmask[16 + rr] = obs_row_fix(rowmask[16 + rr], (bal >> (8 * lane)) & 0xFFu, j0);
-            }
+            if (lane < 4 && rr < kBirdRows) rowmask[16 + rr] = obs_row_fix(rowmask[16 + rr], (bal >> (8 * lane)) & 0xFFu, j0);
         }
         __syncwarp();
     }
     uint4 *dst = reinterpret_cast<uint4 *>(out);
 #pragma unroll
     for (int it = 0; it < 13; it++) {
-        int c = lane + 32 * it;                      // 16-byte chunk: row c / 5, columns 16 * (c % 5) ..
+        const int c = lane + 32 * it;                // 16-byte chunk: row c / 5, columns 16 * (c % 5) ..
         if (c < 400) {
-            int i = (c * 205) >> 10, part = c - 5 * i;
-            uint32_t bits = part == 4 ? 0xFFFFu : (uint32_t)(rowmask[i] >> (16 * part)) & 0xFFFFu;
-            uint4 v;
-            v.x = expand4(bits & 15u); v.y = expand4((bits >> 4) & 15u);
-            v.z = expand4((bits >> 8) & 15u); v.w = expand4(bits >> 12);
-            __stcs(dst + c, v);
+            const int i = (c * 205) >> 10, part = c - 5 * i;
+            const uint32_t bits = part == 4 ? 0xFFFFu : (uint32_t)(rowmask[i] >> (16 * part)) & 0xFFFFu;
+            const uint2 a = lut8[bits & 255u], b = lut8[bits >> 8];
+            __stcs(dst + c, make_uint4(a.x, a.y, b.x, b.y));
         }
     }
     __syncwarp();
 }
 
 // ------------------------------------------------------------------------------- the step kernel
+// Persistent and warp-centric: the launch has one CTA slot's worth of warps per SM (occupancy query), warp w of W owns the
+// contiguous envs [n w / W, n (w+1) / W) -- equal shares, no tail wave, no inter-warp synchronisation after the tables are
+// loaded.  A warp walks its range 32 envs at a time: every lane steps one env (integer physics, collision against the
+// hitmask bit rows in shared memory) and posts a 16-byte draw list; the warp then draws those envs one after another
+// (render_env).  State stays in registers across the n_steps of one launch.
+constexpr int kStepThreads = 256, kStepWarps = kStepThreads / 32;
 
-template <int THREADS, int EPC>
-__global__ void __launch_bounds__(THREADS) env_step_kernel(const StepArgs a) {
-    constexpr int WARPS = THREADS / 32;
+__global__ void __launch_bounds__(kStepThreads, 4) env_step_kernel(const StepArgs a) {
     __shared__ __align__(16) ObsTables T;
-    __shared__ DrawList dl[EPC];
-    __shared__ unsigned long long rowmask[WARPS][kObs];
+    __shared__ __align__(16) HitTables H;                           // flappy_bird_utils hitmasks as bit rows (checkCrash)
+    __shared__ DrawList dl[kStepWarps][32];
+    __shared__ unsigned long long rowmask[kStepWarps][kObs];
+    __shared__ uint2 lut8[256];                                     // 8 bits -> 8 bytes of 0x00 / 0xFF
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    lut8[tid] = make_uint2(expand4(tid & 15u), expand4(tid >> 4));
 
+    {
+        const uint4 *srcH = reinterpret_cast<const uint4 *>(a.ex);                       // ExactTables begins with the HitTables members
+        uint4 *dstH = reinterpret_cast<uint4 *>(&H);
+        for (int k = tid; k < (int)(sizeof(HitTables) / 16); k += kStepThreads) dstH[k] = __ldg(srcH + k);
+    }
     if (a.ring) {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.obs_tab);
         uint4 *dstT = reinterpret_cast<uint4 *>(&T);
-        for (int k = tid; k < (int)(sizeof(ObsTables) / 16); k += THREADS) dstT[k] = __ldg(src + k);
+        for (int k = tid; k < (int)(sizeof(ObsTables) / 16); k += kStepThreads) dstT[k] = __ldg(src + k);
     }
     __syncthreads();
 
-    const int n_groups = (a.n + EPC - 1) / EPC;
-    for (int group = blockIdx.x; group < n_groups; group += gridDim.x) {
-        const int env0 = group * EPC;
-        const int e_mine = env0 + tid;
-        const bool have = tid < EPC && e_mine < a.n;
+    RowConst rc;
+#pragma unroll
+    for (int it = 0; it < 3; it++) {
+        const int i = min(lane + 32 * it, kObs - 1);
+        rc.sx[it] = T.sx[i]; rc.ph5[it] = i - 5 * ((i * 205) >> 10);
+    }
+    const long long W = (long long)gridDim.x * kStepWarps, w = (long long)blockIdx.x * kStepWarps + warp;
+    const int lo = (int)((long long)a.n * w / W), hi = (int)((long long)a.n * (w + 1) / W);
+    for (int base = lo; base < hi; base += 32) {
+        const int e_mine = base + lane;
+        const bool have = e_mine < hi;
+        const int n_here = min(32, hi - base);
         EnvState s;
         GapSource gs;
         if (have) {
             const uint4 *sp = reinterpret_cast<const uint4 *>(a.state + e_mine);
-            uint4 lo = sp[0], hi = sp[1];
-            *reinterpret_cast<uint4 *>(&s) = lo;
-            *(reinterpret_cast<uint4 *>(&s) + 1) = hi;
+            uint4 v0 = sp[0], v1 = sp[1];
+            *reinterpret_cast<uint4 *>(&s) = v0;
+            *(reinterpret_cast<uint4 *>(&s) + 1) = v1;
             gs.script = a.gaps ? a.gaps + (size_t)e_mine * a.gaps_len : nullptr;
             gs.script_len = a.gaps_len;
             gs.seed = a.seed; gs.env_id = a.first_id + (uint64_t)e_mine;
         }
-        const int n_here = min(EPC, a.n - env0);
         for (int step = 0; step < a.n_steps; step++) {
-            if (have && a.draw_only) dl[tid] = make_draw_list(s);
+            if (have && a.draw_only) dl[warp][lane] = make_draw_list(s);
             if (have && !a.draw_only) {
                 int act;
                 const size_t o = (size_t)step * a.n + e_mine;
@@ -147,31 +186,20 @@ __global__ void __launch_bounds__(THREADS) env_step_kernel(const StepArgs a) {
                     if (a.actions_out) a.actions_out[o] = (uint8_t)act;
                 }
                 float rew; uint8_t term; int32_t sc;
-                env_step(s, act, gs, a.ex, rew, term, sc);
+                env_step(s, act, gs, &H, rew, term, sc);
                 if (a.reward) a.reward[o] = rew;
                 if (a.terminal) a.terminal[o] = term;
                 if (a.score) a.score[o] = sc;
-                if (a.ring) dl[tid] = make_draw_list(s);
+                if (a.ring) dl[warp][lane] = make_draw_list(s);
             }
             if (a.ring) {
                 const int slot = (a.ring_slot + step) % a.ring_len;
-                if (EPC == THREADS) {
-                    // each warp draws the 32 envs its own lanes have just stepped: only warp-level synchronisation, so the
-                    // warps of a CTA drift apart and one warp's physics overlaps another's stores
-                    __syncwarp();
-                    for (int e = warp * 32; e < min(n_here, warp * 32 + 32); e++) {
-                        uint8_t *out = a.ring + ((size_t)(env0 + e) * a.ring_len + slot) * (size_t)FB_FRAME_BYTES;
-                        render_env(T, a.ex, dl[e], rowmask[warp], out, lane);
-                    }
-                    __syncwarp();
-                } else {
-                    __syncthreads();
-                    for (int e = warp; e < n_here; e += WARPS) {
-                        uint8_t *out = a.ring + ((size_t)(env0 + e) * a.ring_len + slot) * (size_t)FB_FRAME_BYTES;
-                        render_env(T, a.ex, dl[e], rowmask[warp], out, lane);
-                    }
-                    __syncthreads();
+                __syncwarp();
+                for (int e = 0; e < n_here; e++) {
+                    uint8_t *out = a.ring + ((size_t)(base + e) * a.ring_len + slot) * (size_t)FB_FRAME_BYTES;
+                    render_env(T, lut8, a.ex, dl[warp][e], rc, rowmask[warp], out, lane);
                 }
+                __syncwarp();
             }
         }
         if (have) {
@@ -266,6 +294,7 @@ extern "C" int fb_env_create(int n_envs, uint64_t seed, uint64_t first_env_id, f
     FB_CUDA_OK(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
     FB_CUDA_OK(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
     e->submitted = e->waited = 0;
+    e->step_slots = 0;
     *out = e;
     return fb_env_reset(e, nullptr);
 }
@@ -306,13 +335,17 @@ static int launch_step(fb_env *e, StepArgs &a, cudaStream_t st) {
     a.gaps = e->gaps; a.gaps_len = e->gaps_len; a.err_flag = e->err_flag;
     a.obs_tab = fb_tables().obs_dev; a.ex = fb_tables().exact_dev;
     // Few envs: 32 per CTA so that every SM gets work; many envs: 128 per CTA (4 full physics warps).
-    if (e->n < 128 * e->num_sms) {
-        int groups = (e->n + 31) / 32;
-        env_step_kernel<128, 32><<<groups, 128, 0, st>>>(a);
-    } else {
-        int groups = (e->n + 127) / 128;
-        env_step_kernel<128, 128><<<groups, 128, 0, st>>>(a);
+    if (e->step_slots == 0) {                      // CTAs that fit the device at once (4 per SM: 46 KB of shared memory, 64 registers)
+        int per_sm = 0;
+        FB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, env_step_kernel, kStepThreads, 0));
+        FB_REQUIRE(per_sm >= 1, "env_step_kernel does not fit an SM");
+        e->step_slots = per_sm * e->num_sms;
     }
+    // one env per warp while there are fewer envs than resident warps (every SM draws); equal contiguous shares beyond that
+    long long warps = (long long)e->step_slots * kStepWarps;
+    if (warps > e->n) warps = e->n;
+    const int grid = (int)((warps + kStepWarps - 1) / kStepWarps);
+    env_step_kernel<<<grid, kStepThreads, 0, st>>>(a);
     FB_CUDA_OK(cudaGetLastError());
     return FB_OK;
 }

@@ -58,7 +58,9 @@ FB_HD void env_reset(EnvState &s, const GapSource &g) {
 }
 
 // checkCrash's pipe part (wrapped_flappy_bird.py:254-275) + pixelCollision (:278-300) on bit rows.
-FB_HD bool hits_pipe(const EnvState &s, const ExactTables *ex) {
+// TB: HitTables in shared memory (the step kernel) or ExactTables in global / host memory (debug entry points): plain loads
+template <class TB>
+FB_HD bool hits_pipe(const EnvState &s, const TB *ex) {
     bool hit = false;
     for (int k = 0; k < s.npipes; k++) {
         int x = s.px[k];
@@ -66,13 +68,13 @@ FB_HD bool hits_pipe(const EnvState &s, const ExactTables *ex) {
         int gapY = 100 + 10 * s.gap[k], y = s.y, sh = kPlayerX - x;          // pipe column = bird column + sh
         int y_end = fb_min(y + kBirdH, gapY);                                   // upper pipe rows [gapY-320, gapY)
         for (int Y = y; Y < y_end; Y++) {
-            unsigned long long b = FB_LDG(&ex->birdRow[s.pidx][Y - y]), p = FB_LDG(&ex->pipeRowUp[Y - (gapY - kPipeH)]);
+            unsigned long long b = ex->birdRow[s.pidx][Y - y], p = ex->pipeRowUp[Y - (gapY - kPipeH)];
             p = sh >= 0 ? p >> sh : p << (-sh);
             hit |= (b & p) != 0;
         }
         int ly = gapY + kGapSize;                                            // lower pipe rows [gapY+100, ...)
         for (int Y = fb_max(y, ly); Y < y + kBirdH; Y++) {
-            unsigned long long b = FB_LDG(&ex->birdRow[s.pidx][Y - y]), p = FB_LDG(&ex->pipeRowLo[Y - ly]);
+            unsigned long long b = ex->birdRow[s.pidx][Y - y], p = ex->pipeRowLo[Y - ly];
             p = sh >= 0 ? p >> sh : p << (-sh);
             hit |= (b & p) != 0;
         }
@@ -81,7 +83,8 @@ FB_HD bool hits_pipe(const EnvState &s, const ExactTables *ex) {
 }
 
 // one frame_step (wrapped_flappy_bird.py:95-162), integer restatement of SURVEY appendix A
-FB_HD void env_step(EnvState &s, int action, const GapSource &g, const ExactTables *ex,
+template <class TB>
+FB_HD void env_step(EnvState &s, int action, const GapSource &g, const TB *ex,
                                          float &reward, uint8_t &terminal, int32_t &score_out) {
     reward = 0.1f;
     int vel = s.vel;

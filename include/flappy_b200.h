@@ -174,6 +174,9 @@ int fb_qnet_set_per_broadcast(fb_qnet *net, int on);
 /* test hook: overwrite the bf16 operand copies of slot 0 (online) / 1 (target) with NaNs WITHOUT marking them stale --
  * whoever reads them before the next pack kernel has finished shows up as NaN Q-values */
 int fb_debug_poison_packed(fb_qnet *net, int slot, void *stream);
+/* measurement hook (tools/write_bw_probe.py): n_chunks chunks of 6,400 bytes at dst + k * stride_bytes, written by one warp each
+ * with 16-byte streaming stores (mode 0) or through shared memory + cp.async.bulk (mode 1); no computation */
+int fb_debug_write_probe(uint8_t *dst_dev, int n_chunks, long long stride_bytes, int mode, int ctas, void *stream);
 /* FB_PRECISION_BF16 only: replay fb_qnet_loss_backward as a CUDA graph once the same arguments were seen twice
  * (default on; the eager two-stream path is identical work). */
 int fb_qnet_use_graphs(fb_qnet *net, int enable);

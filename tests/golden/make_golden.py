@@ -159,6 +159,53 @@ def gen_env_trajectories():
     print("frames kept:", n_frames_kept)
 
 
+def gen_env_long():
+    """ONE long reference trajectory with a competent (and occasionally lapsing) controller: >= 1,000 scoring events, pipes
+    spawned / popped hundreds of times, crashes into LOWER pipes, upper pipes and the ground -- the reference's own
+    game/wrapped_flappy_bird.py on the shim, real cv2 preprocess.  Stored per step: action, reward, terminal, score, state;
+    the 80x80 observation (bit-packed) for every 5th step and every step with a score or a crash."""
+    rng = np.random.default_rng(20261019)
+    T = 42000
+    gaps = rng.integers(0, 8, 1021).astype(np.uint8)          # prime length
+    game = fresh_reference_game(gaps)
+    gs = game.GameState()
+    acts = np.zeros(T, np.uint8); rew = np.zeros(T, np.float32); term = np.zeros(T, np.uint8)
+    score = np.zeros(T, np.int32); st = np.zeros((T, 16), np.int32)
+    obs_idx, obs_bits, crash_kind = [], [], []
+    lapse = 0
+    for t in range(T):
+        if t == 0:
+            a = 0
+        else:
+            nxt = None
+            for up in gs.upperPipes:
+                if up["x"] + game.PIPE_WIDTH > gs.playerx:
+                    nxt = up; break
+            centre = (nxt["y"] + game.PIPE_HEIGHT + game.PIPEGAPSIZE / 2) if nxt else 256
+            if lapse > 0:
+                lapse -= 1
+                a = int(rng.random() < (0.0 if lapse % 2 else 0.6))      # erratic: falls or climbs into a pipe
+            else:
+                a = int((gs.playery + 12) - centre > 14)
+                if rng.random() < 0.0012:
+                    lapse = int(rng.integers(12, 40))
+        y_before = gs.playery
+        onehot = np.array([1, 0]) if a == 0 else np.array([0, 1])
+        image, r, done, sc = gs.frame_step(onehot)
+        o = preprocess(image)[:, :, 0]
+        acts[t] = a; rew[t] = r; term[t] = done; score[t] = sc; st[t] = state_of(game, gs)
+        if t % 5 == 0 or done or r == 3:
+            obs_idx.append(t); obs_bits.append(np.packbits(o > 0))
+        if done:
+            crash_kind.append(int(y_before))
+    out = {"gaps": gaps, "actions": acts, "reward": rew, "terminal": term, "score": score, "state": st,
+           "obs_idx": np.array(obs_idx, np.int32), "obsbits": np.stack(obs_bits), "crash_y_before": np.array(crash_kind, np.int32),
+           "cv2_version": np.array(cv2.__version__)}
+    np.savez_compressed(os.path.join(HERE, "ref_env_long.npz"), **out)
+    print(f"long trajectory: T={T} scores={int((rew == 3).sum())} crashes={int(term.sum())} max_score={int(score.max())} "
+          f"frames kept={len(obs_idx)} gaps_used={game.random.used}")
+
+
 def gen_logs():
     out = {}
     pat = re.compile(r"TIMESTEP (\d+) / STATE (\w+) / ACTION ([\d.]+) / EPSILON (\S+) / REWARD (\S+)(?: / SCORE (\d+))?")
@@ -257,6 +304,7 @@ def gen_graphs():
 if __name__ == "__main__":
     which = sys.argv[1:] or ["env", "logs", "per", "cv2", "graphs"]
     if "graphs" in which: gen_graphs()
+    if "envlong" in which: gen_env_long()
     if "env" in which: gen_env_trajectories()
     if "logs" in which: gen_logs()
     if "per" in which: gen_per()

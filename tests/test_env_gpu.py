@@ -104,6 +104,94 @@ def test_4096_envs_vs_oracle(game):
     np.testing.assert_array_equal(gs.obs_exact().cpu().numpy(), obs[-1])
 
 
+def test_4096_envs_10000_steps_vs_oracle(game):
+    """SURVEY 4 layer 2 depth: 4,096 envs x 10,000 steps (4.1e7 frame_steps) against the oracle under replayed gaps and a
+    policy mix with competent controllers (long episodes: thousands of scores, spawns, pops, 3-pipe windows) -- reward, terminal
+    and score of EVERY env at EVERY step, the packed state at the end of every 500-step chunk, and the drawn observation of
+    every env at those points (against the oracle's full-frame render + cv2 arithmetic, and against the library's own per-pixel
+    path)."""
+    from dqnflappybird_b200 import _lib
+    N, T, CH = 4096, 10000, 500
+    rng = np.random.default_rng(11)
+    gaps = rng.integers(0, 8, (N, 127)).astype(np.uint8)
+    oracle = fo.OracleEnvs(N, gaps=gaps)
+    gs = game.GameState(num_envs=N, replay_gaps=gaps, history=4)
+    kind = rng.integers(0, 5, N)                  # 0-2 controller (p_flap when below 0.9 / 0.97 / 0.8), 3 random .5, 4 sparse
+    p_below = np.choose(np.minimum(kind, 2), [0.9, 0.97, 0.8])
+    rew = torch.empty((CH, N), dtype=torch.float32, device="cuda"); term = torch.empty((CH, N), dtype=torch.uint8, device="cuda")
+    score = torch.empty((CH, N), dtype=torch.int32, device="cuda")
+    obs_ring = torch.zeros((N, 1, 80, 80), dtype=torch.uint8, device="cuda")
+    n_scores = n_crashes = 0
+    for c0 in range(0, T, CH):
+        actions = np.zeros((CH, N), np.uint8)
+        o_rew = np.zeros((CH, N), np.float32); o_term = np.zeros((CH, N), np.uint8); o_score = np.zeros((CH, N), np.int32)
+        for t in range(CH):
+            u = rng.random(N)
+            st = oracle.export_state()
+            y, np_, px, gp = st[:, 0], st[:, 7], st[:, 8:11], st[:, 11:14]
+            nxt = np.zeros(N, np.int64)
+            for k in (2, 1, 0):
+                nxt = np.where((k < np_) & (px[:, k] + 52 > 57), k, nxt)
+            below = (y + 12) - (100 + 10 * gp[np.arange(N), nxt] + 50) > 8
+            a = u < np.where(below, p_below, 0.01)
+            a = np.where(kind == 3, u < 0.5, a)
+            a = np.where(kind == 4, u < 0.08, a).astype(np.uint8)
+            if c0 == 0 and t == 0:
+                a[:] = 0
+            actions[t] = a
+            _, o_rew[t], o_term[t], o_score[t] = oracle.step(a, want_obs=False, threads=8)
+        a_dev = torch.from_numpy(actions).cuda()
+        _lib.check(gs._L.fb_env_step(gs._h, CH, a_dev.data_ptr(), None, 0, 0, rew.data_ptr(), term.data_ptr(), score.data_ptr(),
+                                     game._stream_ptr(gs.device)), "fb_env_step")
+        _lib.check(gs._L.fb_env_draw(gs._h, obs_ring.data_ptr(), 1, 0, game._stream_ptr(gs.device)), "fb_env_draw")
+        torch.cuda.synchronize()
+        gs.check_errors()
+        np.testing.assert_array_equal(rew.cpu().numpy(), o_rew, err_msg=f"chunk {c0}")
+        np.testing.assert_array_equal(term.cpu().numpy(), o_term, err_msg=f"chunk {c0}")
+        np.testing.assert_array_equal(score.cpu().numpy(), o_score, err_msg=f"chunk {c0}")
+        np.testing.assert_array_equal(gs.export_state().cpu().numpy(), oracle.export_state(), err_msg=f"chunk {c0}")
+        drawn = obs_ring[:, 0].cpu().numpy()
+        pick = np.arange((c0 // CH) % 4, N, 4)
+        np.testing.assert_array_equal(drawn[pick], np.stack([oracle.obs(int(k)) for k in pick]), err_msg=f"chunk {c0}")
+        np.testing.assert_array_equal(gs.obs_exact().cpu().numpy(), drawn)
+        n_scores += int((o_rew == 3).sum()); n_crashes += int(o_term.sum())
+    assert n_scores > 300000 and n_crashes > 100000, (n_scores, n_crashes)      # the controllers really do fly
+
+
+def test_golden_long_reference_trajectory(game, golden_dir):
+    """42,000 steps of the reference itself (game/wrapped_flappy_bird.py on the shim, real cv2) with a competent, occasionally
+    lapsing controller: > 1,000 scoring events, crashes into lower pipes, upper pipes and the ground -- replayed on the device"""
+    path = os.path.join(golden_dir, "ref_env_long.npz")
+    g = np.load(path)
+    acts = g["actions"]
+    T = len(acts)
+    assert int((g["reward"] == 3).sum()) >= 1000
+    from dqnflappybird_b200 import _lib
+    gs = game.GameState(num_envs=1, replay_gaps=g["gaps"][None, :], history=4)
+    a = torch.from_numpy(np.ascontiguousarray(acts[:, None])).cuda()
+    rew = torch.empty((T, 1), dtype=torch.float32, device="cuda"); term = torch.empty((T, 1), dtype=torch.uint8, device="cuda")
+    score = torch.empty((T, 1), dtype=torch.int32, device="cuda")
+    ring = torch.zeros((1, 1, 80, 80), dtype=torch.uint8, device="cuda")
+    idx = g["obs_idx"]
+    want = np.unpackbits(g["obsbits"], axis=1).reshape(-1, 80, 80) * 255
+    done = 0
+    for k, t_obs in enumerate(idx):                       # step up to each kept frame, draw, compare
+        n = int(t_obs) + 1 - done
+        _lib.check(gs._L.fb_env_step(gs._h, n, a[done:].data_ptr(), None, 0, 0, rew[done:].data_ptr(), term[done:].data_ptr(),
+                                     score[done:].data_ptr(), game._stream_ptr(gs.device)), "fb_env_step")
+        done += n
+        if k % 4 == 0 or g["terminal"][t_obs] or g["reward"][t_obs] == 3:
+            _lib.check(gs._L.fb_env_draw(gs._h, ring.data_ptr(), 1, 0, game._stream_ptr(gs.device)), "fb_env_draw")
+            np.testing.assert_array_equal(ring[0, 0].cpu().numpy(), want[k], err_msg=f"obs at step {t_obs}")
+            st = gs.export_state().cpu().numpy()[0]
+            ref = g["state"][t_obs].copy(); ref[4] = st[4]
+            np.testing.assert_array_equal(st, ref, err_msg=f"state at step {t_obs}")
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(rew.cpu().numpy()[:done, 0], g["reward"][:done])
+    np.testing.assert_array_equal(term.cpu().numpy()[:done, 0], g["terminal"][:done])
+    np.testing.assert_array_equal(score.cpu().numpy()[:done, 0], g["score"][:done])
+
+
 def test_random_action_mode_and_philox_gaps(game):
     """fb_env_step_random: device-drawn Bernoulli(0.5) actions + Philox gap streams, vs the oracle
     fed the same streams (fo_stream_word)."""

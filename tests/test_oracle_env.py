@@ -48,6 +48,28 @@ def test_oracle_matches_reference_trajectories(golden_dir):
                 np.testing.assert_array_equal(env.render_full(0), frames[t], err_msg=f"frame traj {ti} step {t}")
 
 
+def test_oracle_matches_long_reference_trajectory(golden_dir):
+    """42,000 steps of the reference itself with a competent controller (tests/golden/make_golden.py envlong): 1,063 scoring
+    events, 56 crashes into lower pipes / upper pipes / the ground, hundreds of spawns and pops -- every step's reward, terminal,
+    score and state, and the 9,314 kept observations"""
+    g = np.load(os.path.join(golden_dir, "ref_env_long.npz"))
+    acts = g["actions"]
+    assert int((g["reward"] == 3).sum()) >= 1000 and int(g["terminal"].sum()) >= 50
+    env = fo.OracleEnvs(1, gaps=g["gaps"][None, :])
+    keep = {int(t): k for k, t in enumerate(g["obs_idx"])}
+    for t in range(len(acts)):
+        obs, r, term, sc = env.step(acts[t:t + 1], want_obs=t in keep)
+        assert (r[0], term[0], sc[0]) == (g["reward"][t], g["terminal"][t], g["score"][t]), t
+        st = env.export_state()[0]
+        ref = g["state"][t].copy(); ref[4] = st[4]
+        np.testing.assert_array_equal(st, ref, err_msg=f"step {t}")
+        if t in keep:
+            np.testing.assert_array_equal(np.packbits(obs[0] > 0), g["obsbits"][keep[t]], err_msg=f"obs step {t}")
+    # crash kinds: the bird's y before the fatal step separates ground hits (y near 380) from pipe hits in the air
+    yb = g["crash_y_before"]
+    assert (yb >= 360).sum() > 0 and (yb < 300).sum() > 10
+
+
 def test_known_episode_lengths():
     # SURVEY appendix A: all-no-op dies on step 19, all-flap on step 50, for any gaps
     for gap in range(8):

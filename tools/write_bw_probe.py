@@ -29,4 +29,15 @@ ms = t(lambda: y.copy_(x)); out["copy_gbs_read_plus_write"] = 2 * n / ms / 1e6
 # strided like the ring: one 6,400-byte frame of every 25,600
 xr = x.view(131072, 4, 6400)
 ms = t(lambda: xr[:, 1].fill_(255)); out["fill_one_slot_of_four_gbs"] = 131072 * 6400 / ms / 1e6
+# the env kernel's own pattern without its computation (fb_debug_write_probe): 131,072 frames of 6,400 bytes
+import os
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from dqnflappybird_b200 import _lib
+L = _lib.lib()
+st = torch.cuda.current_stream().cuda_stream
+for name, stride in (("ring_env_major_stride_25600", 25600), ("contiguous_stride_6400", 6400)):
+    for mode, mname in ((0, "stg128"), (1, "bulk")):
+        for ctas in (296, 592, 1184):
+            ms = t(lambda: _lib.check(L.fb_debug_write_probe(x.data_ptr(), 131072, stride, mode, ctas, st), "probe"))
+            out[f"{name}_{mname}_{ctas}ctas_gbs"] = 131072 * 6400 / ms / 1e6
 print(json.dumps(out))
