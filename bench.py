@@ -324,6 +324,23 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     learner = None
     if not args.no_learner:
         learner = bench_learner(args, rank, world, dev)
+    # ---- BASELINE.json configs as written, through the reference's own loop (act -> frame_step -> setPerception + update)
+    loops = None
+    if not args.no_learner and not args.no_closed_loop:
+        del gs
+        torch.cuda.empty_cache()
+        loops = {}
+        # configs[4]: BrainDoubleDQN + BrainDuelingDQN acting on 1,048,576 envs over 8 GPUs = 131,072 per GPU (weak scaling)
+        for m in ("ddqn", "duelingdqn"):
+            loops[f"configs4_{m}"] = closed_loop(m, E, args.learner_batch * world, 1, 8, dev, rank, world)
+        if world == 1:
+            # configs[4] on ONE GPU (strong-scaling anchor): all 1,048,576 envs, ring u8[1048576][5][80][80] = 33.6 GB
+            loops["configs4_ddqn_1M_envs_one_gpu"] = closed_loop("ddqn", 1048576, args.learner_batch, 1, 3, dev, rank, world)
+            # configs[2] closed loop: BrainDQNNature, 16,384 envs, minibatch 256
+            loops["configs2_dqnnature"] = closed_loop("dqnnature", args.learner_envs, args.learner_batch, 28, 40, dev, rank, world)
+            # configs[0]: the reference's own case -- 1 env, BrainDQN, minibatch 32, replay 50,000 (BrainDQN.py:19-28; OBSERVE as
+            # shipped is 1000, BASELINE.json says 10000: neither matters for a rate, the loop is timed past it)
+            loops["configs0_dqn_1_env"] = closed_loop("dqn", 1, 32, 50000, 300, dev, rank, world, observe_steps=40)
     if rank != 0:
         return
     total_envs = E * world
@@ -380,6 +397,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "exchange_us": learner and learner["exchange_us"],
         "learner_checks": learner and learner["checks"],
         "learner": learner,
+        "closed_loop": loops,
     }
     emit(line)
 
@@ -446,6 +464,8 @@ def verify_and_time_exchange(brain, dev, world, K, sync):
     # ---- the same update without the exchange, on scratch state (replicas must not diverge)
     saved = (net.params.clone(), net.adam_m.clone(), net.adam_v.clone(), net.beta1_power, net.beta2_power, net.adam_steps)
     ex, net.exchange = net.exchange, None
+    in_step, net.exchange_in_step = net.exchange_in_step, False
+    _lib.check(L.fb_qnet_attach_exchange(net._h, None), "fb_qnet_attach_exchange")
     grads_saved = net.grads
     net.grads = torch.zeros_like(saved[0])
     world_saved, brain.world = brain.world, 1
@@ -460,7 +480,8 @@ def verify_and_time_exchange(brain, dev, world, K, sync):
     e1.record(); sync()
     ms_local = e0.elapsed_time(e1) / K
     brain.world = world_saved
-    net.exchange, net.grads = ex, grads_saved
+    net.exchange, net.grads, net.exchange_in_step = ex, grads_saved, in_step
+    _lib.check(L.fb_qnet_attach_exchange(net._h, ex._h if (ex is not None and in_step) else None), "fb_qnet_attach_exchange")
     net.params.copy_(saved[0]); net.adam_m.copy_(saved[1]); net.adam_v.copy_(saved[2])
     net.beta1_power, net.beta2_power, net.adam_steps = saved[3], saved[4], saved[5]
     _lib.check(L.fb_qnet_invalidate(net._h), "fb_qnet_invalidate")
@@ -468,6 +489,49 @@ def verify_and_time_exchange(brain, dev, world, K, sync):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     assert checksums(), "replicas diverged after restoring the state"
     return res, float(t[0])
+
+
+def closed_loop(model, n_envs, batch, replay_per_env, steps, dev, rank, world, observe_steps=4, max_act_batch=4096):
+    """The reference's own loop (FlappyBirdDQN.py:72-76) on the device: getAction -> frame_step -> setPerception with one
+    minibatch update per step once past OBSERVE -- acting with the Q-network, stepping every env, appending to replay (no copy:
+    the env draws into the Brain's ring) and training.  Returns env frames/s and updates/s of this rank."""
+    import torch
+    from dqnflappybird_b200.brains import MODELS
+    from dqnflappybird_b200.game import GameState
+    brain = MODELS[model](2, "bird", num_envs=n_envs, device=dev, seed=0, first_env_id=rank * n_envs, replay_memory_per_env=replay_per_env,
+                          batch_size=batch, observe=observe_steps, max_act_batch=max_act_batch)
+    gs = GameState(num_envs=n_envs, device=dev, seed=17, first_env_id=rank * n_envs, history=brain.ring.shape[1], ring=brain.ring)
+    a0 = torch.zeros(n_envs, dtype=torch.uint8, device=dev) if n_envs > 1 else [1, 0]
+    obs, *_ = gs.frame_step(a0)
+    brain.setInitState(obs)
+
+    def one():
+        action = brain.getAction()
+        out = brain.next_rows()[1:] if n_envs > 1 else None
+        nxt, reward, terminal, score = gs.frame_step(action, out=out)
+        brain.setPerception(nxt, action, reward, terminal, score)
+    for _ in range(observe_steps + 8):
+        one()
+    torch.cuda.synchronize()
+    upd0 = brain.net.adam_steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    gs.check_errors()
+    res = {"model": model, "envs_per_gpu": n_envs, "envs_total": n_envs * world, "minibatch": batch, "steps": steps,
+           "env_frames_per_s": n_envs * world * steps / (ms * 1e-3), "updates_per_s": (brain.net.adam_steps - upd0) / (ms * 1e-3),
+           "ms_per_loop_step": ms / steps, "precision": brain.net.precision}
+    del brain, gs
+    torch.cuda.empty_cache()
+    return res
 
 
 def bench_learner(args, rank, world, dev):
@@ -649,6 +713,8 @@ def bench_learner(args, rank, world, dev):
             "weak_efficiency_in_run": None if ms_local is None else ms_local / ms_upd,
             "checks": checks,
             "gradient_exchange": ("none (1 GPU)" if world == 1 else
+                                  "inside the step's graph: NVLink peer-memory sum fused with Adam, W_fc1's bucket beside the conv gradients "
+                                  "(adam_xbucket_kernel)" if brain.net.exchange_in_step else
                                   "fused into Adam over NVLink peer memory (fb_dist_adam)" if brain.net.exchange is not None else "NCCL all-reduce"),
             "roofline": None if not kern else {
                 "bound": "tensor", "kernel": "tc_conv1_fused_kernel<6,true> (conv1 forward of the training step: TMA slab + tcgen05.mma, N = 32, "
@@ -680,6 +746,7 @@ def main():
     ap.add_argument("--learner-precision", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--learner-scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-learner-variants", action="store_true")
+    ap.add_argument("--no-closed-loop", action="store_true")
     ap.add_argument("--reference-budget-s", type=float, default=120.0, help="--impl reference: CPU seconds for warm-up + all steps")
     args = ap.parse_args()
 

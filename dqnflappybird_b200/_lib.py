@@ -142,6 +142,8 @@ _SIGNATURES = {
     "fb_dist_connect_local": ([_vp, C.c_int, _vp], C.c_int),
     "fb_dist_grads": ([_vp, C.c_int, C.POINTER(C.c_void_p)], C.c_int),
     "fb_dist_parity": ([_vp], C.c_int),
+    "fb_dist_advance": ([_vp], C.c_int),
+    "fb_qnet_attach_exchange": ([_vp, _vp], C.c_int),
     "fb_dist_adam": ([_vp, _vp, _f32p, _f32p, _f32p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _f32p, C.c_int, _vp], C.c_int),
     "fb_replay_create": ([C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)], C.c_int),
     "fb_replay_destroy": ([_vp], C.c_int),

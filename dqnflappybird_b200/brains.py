@@ -243,8 +243,10 @@ class BrainDQN:
         isw = mb.is_weights_f32 if mb.is_weights is not None else None   # the placeholder is tf.float32 (BrainPrioritizedReplyDQN.py:243)
         args = (variant, mb.frames, mb.actions, mb.rewards, mb.terminals, isw, self.gamma, self.loss_sum, self.local_batch * self.world,
                 self._abs_err[:self.local_batch], self._q_target[:self.local_batch])
-        if self.world == 1:
-            self.net.train_step(*args, sampling=sampling)         # one call: on the tensor-core path one CUDA graph, Adam included
+        if self.world == 1 or self.net.exchange_in_step:
+            # one call: on the tensor-core path one CUDA graph, Adam included -- and, on several GPUs, the gradient exchange too
+            # (W_fc1's 91 % of the vector beside the convolution gradients, the rest at the tail: csrc/fb_dist.cu)
+            self.net.train_step(*args, sampling=sampling)
         else:
             self.net.loss_backward(*args, sampling=sampling)
             if self.net.exchange is None:

@@ -22,6 +22,8 @@
 #include "fb_pack.cuh"
 
 constexpr int kMaxRanks = 8;
+constexpr int kBuckets = 2;                  // 0: W_fc1 (its gradient is final early in the backward pass), 1: everything else
+constexpr int kBucketFlag0 = 64;             // flags[kBucketFlag0 + 16 b + q] = newest step rank q has published for bucket b
 
 struct fb_dist {
     int rank, world;
@@ -39,6 +41,10 @@ struct fb_dist {
     int n_opened;
     uint32_t step;
     unsigned long long *stamps;              // debug: %globaltimer at the phase boundaries of the last exchange (block 0)
+    // exchange INSIDE the training step's graph (dist_launch_bucket): the step number lives in device memory, one counter
+    // per bucket, so that a captured step replays without per-step arguments
+    uint32_t *dev_steps;                     // [kBuckets] exchanges completed, per bucket
+    unsigned int *dev_done;                  // [kBuckets] CTAs of the running bucket kernel that have finished (self-resetting)
 };
 
 namespace {
@@ -84,7 +90,7 @@ __device__ __forceinline__ float adam_x(float &p, float g, float &m, float &v, f
     return p;
 }
 
-__global__ void __launch_bounds__(256) adam_xreduce_kernel(float *__restrict__ params, float *__restrict__ am, float *__restrict__ av, size_t n,
+__global__ void __launch_bounds__(256, 2) adam_xreduce_kernel(float *__restrict__ params, float *__restrict__ am, float *__restrict__ av, size_t n,
                                                            const XArgs x, float alpha, float beta1, float beta2, float eps, float grad_scale,
                                                            float *__restrict__ reduced_out, int repack, const QnetLayout L,
                                                            const PackedWeights pw) {
@@ -190,7 +196,120 @@ __global__ void __launch_bounds__(256) adam_xreduce_kernel(float *__restrict__ p
         }
 }
 
+// ---- the exchange as a node of the training step's graph --------------------------------------------------------------
+// One kernel per BUCKET of the parameter vector: publish "my gradients of this bucket for step s are final" into every peer
+// (system-scope release), wait until every peer has published the same, then for each parameter of the bucket sum the ranks'
+// gradients in rank order straight from peer memory and apply TF-1 Adam (bitwise identical replicas).  One-shot only: every
+// CTA depends on the peers' flags and on nothing else of its own grid -- no grid barrier, no co-residency requirement (round 1's
+// two-shot form needed all 296 CTAs resident).  Nothing about a step is a launch argument: the step number is a device
+// counter advanced by the CTA that finishes last, alpha was left in device memory by the step's head kernel, so the captured
+// step replays as is.  Bucket 0 (W_fc1: 91 % of the vector, final ~50 us before the step ends) runs beside the convolution
+// gradients; bucket 1 (79,522 parameters, 2.2 MB over NVLink at eight ranks) is all that is left at the tail.
+struct BucketArgs {
+    const float *g[kMaxRanks];
+    uint32_t *peer_flags[kMaxRanks];         // each rank's flag block for this bucket
+    const uint32_t *my_flags;
+    uint32_t *dev_step;
+    unsigned int *dev_done;
+    int rank, world;
+    int lo4, hi4;                            // float4 range of the bucket ...
+    int skip_lo4, skip4;                     // ... from which [skip_lo4, skip_lo4 + skip4) is left out (bucket 1 = everything but W_fc1)
+    int tail_lo, tail_hi;                    // scalar tail (total % 4 parameters), bucket 1 only
+};
+
+__global__ void __launch_bounds__(256) adam_xbucket_kernel(float *__restrict__ params, float *__restrict__ am, float *__restrict__ av, const BucketArgs x,
+                                                           const float *__restrict__ alpha_dev, float beta1, float beta2, float eps, float grad_scale,
+                                                           int repack, const QnetLayout L, const PackedWeights pw) {
+    const uint32_t step = *x.dev_step + 1u;
+    if (blockIdx.x == 0 && (int)threadIdx.x < x.world) {
+        __threadfence_system();
+        st_release_sys(x.peer_flags[threadIdx.x] + x.rank, step);
+    }
+    if ((int)threadIdx.x < x.world) {
+        uint32_t spins = 0;
+        while ((int32_t)(ld_acquire_sys(x.my_flags + threadIdx.x) - step) < 0)
+            if (++spins > (1u << 26)) __trap();
+    }
+    __syncthreads();
+    const float alpha = *alpha_dev;
+    constexpr int U = 4;
+    const int stride = gridDim.x * blockDim.x;
+    const int n4 = x.hi4 - x.lo4 - x.skip4;                            // compact index k -> i = lo4 + k (+ skip4 past the hole)
+    for (int base = blockIdx.x * blockDim.x + threadIdx.x; base < n4; base += U * stride) {
+        float4 gs[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {                                  // every remote load first, then the updates
+            const int k = base + u * stride;
+            const int i = x.lo4 + k + (x.lo4 + k >= x.skip_lo4 ? x.skip4 : 0);
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < n4) {
+                g = ld_peer(x.g[0] + 4 * (size_t)i);
+                for (int q = 1; q < x.world; q++) {
+                    float4 h = ld_peer(x.g[q] + 4 * (size_t)i);
+                    g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
+                }
+            }
+            gs[u] = g;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int k = base + u * stride;
+            if (k >= n4) break;
+            const int i = x.lo4 + k + (x.lo4 + k >= x.skip_lo4 ? x.skip4 : 0);
+            float4 g = gs[u];
+            g.x *= grad_scale; g.y *= grad_scale; g.z *= grad_scale; g.w *= grad_scale;
+            float4 p = reinterpret_cast<float4 *>(params)[i], m = reinterpret_cast<float4 *>(am)[i], v = reinterpret_cast<float4 *>(av)[i];
+            adam_x(p.x, g.x, m.x, v.x, alpha, beta1, beta2, eps); adam_x(p.y, g.y, m.y, v.y, alpha, beta1, beta2, eps);
+            adam_x(p.z, g.z, m.z, v.z, alpha, beta1, beta2, eps); adam_x(p.w, g.w, m.w, v.w, alpha, beta1, beta2, eps);
+            reinterpret_cast<float4 *>(params)[i] = p; reinterpret_cast<float4 *>(am)[i] = m; reinterpret_cast<float4 *>(av)[i] = v;
+            if (repack) {
+                const int e = 4 * i;
+                scatter_packed(e, p.x, L, pw, 0); scatter_packed(e + 1, p.y, L, pw, 0); scatter_packed(e + 2, p.z, L, pw, 0); scatter_packed(e + 3, p.w, L, pw, 0);
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int i = x.tail_lo; i < x.tail_hi; i++) {
+            float g = 0.f;
+            for (int q = 0; q < x.world; q++) g += __ldcv(x.g[q] + i);
+            g *= grad_scale;
+            adam_x(params[i], g, am[i], av[i], alpha, beta1, beta2, eps);
+            if (repack) scatter_packed(i, params[i], L, pw, 0);
+        }
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(x.dev_done, 1u) == gridDim.x - 1) { *x.dev_step = step; *x.dev_done = 0u; }   // every CTA has read the step
+}
+
 }  // namespace
+
+// bucket 0: W_fc1 [L.wf1, L.bf1); bucket 1: [0, L.wf1) and [L.bf1, total).  Called by the tensor-core training step
+// (fb_qnet_tc.cu) for the exchange buffer of the CURRENT parity; fb_dist_advance flips it once the step has been enqueued.
+int dist_launch_bucket(fb_dist *d, fb_qnet *net, int bucket, float *params_dev, float *m_dev, float *v_dev, const float *alpha_dev, float beta1,
+                       float beta2, float eps, float grad_scale, cudaStream_t st) {
+    FB_REQUIRE(d && net && (bucket == 0 || bucket == 1) && (size_t)net->L.total == d->n, "dist_launch_bucket: bad argument");
+    const QnetLayout &L = net->L;
+    FB_REQUIRE(L.wf1 % 4 == 0 && L.bf1 % 4 == 0, "dist_launch_bucket: bucket boundaries must be 16-byte aligned");
+    const int par = (int)(d->step & 1);
+    PackedWeights pw{};
+    const int repack = tc_online_operands(net, &pw) ? 1 : 0;
+    auto launch = [&](int lo4, int hi4, int skip_lo4, int skip4, int tail_lo, int tail_hi, int b, int ctas) -> int {
+        BucketArgs x{};
+        for (int q = 0; q < d->world; q++) {
+            FB_REQUIRE(d->peer_grads[par][q] != nullptr && d->peer_flags[q] != nullptr, "dist_launch_bucket: call fb_dist_connect first");
+            x.g[q] = d->peer_grads[par][q]; x.peer_flags[q] = d->peer_flags[q] + kBucketFlag0 + 16 * b;
+        }
+        x.my_flags = d->flags + kBucketFlag0 + 16 * b; x.dev_step = d->dev_steps + b; x.dev_done = d->dev_done + b;
+        x.rank = d->rank; x.world = d->world; x.lo4 = lo4; x.hi4 = hi4; x.skip_lo4 = skip_lo4; x.skip4 = skip4; x.tail_lo = tail_lo; x.tail_hi = tail_hi;
+        adam_xbucket_kernel<<<ctas, 256, 0, st>>>(params_dev, m_dev, v_dev, x, alpha_dev, beta1, beta2, eps, grad_scale, repack, L, pw);
+        FB_CUDA_OK(cudaGetLastError());
+        return FB_OK;
+    };
+    if (bucket == 0) return launch(L.wf1 / 4, L.bf1 / 4, L.bf1 / 4, 0, 0, 0, 0, 200);
+    // bucket 1: [0, total) without W_fc1, one kernel (one handshake)
+    return launch(0, L.total / 4, L.wf1 / 4, (L.bf1 - L.wf1) / 4, (L.total / 4) * 4, L.total, 1, 78);
+}
+
+const float *dist_current_grads(const fb_dist *d) { return d ? d->xgrads[d->step & 1] : nullptr; }
 
 extern "C" int fb_dist_create(int rank, int world, long long n_floats, fb_dist **out) {
     FB_REQUIRE(out != nullptr && world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world && n_floats > 0, "fb_dist_create: bad argument");
@@ -205,6 +324,9 @@ extern "C" int fb_dist_create(int rank, int world, long long n_floats, fb_dist *
     FB_CUDA_OK(cudaMemset(d->red, 0, bytes));
     FB_CUDA_OK(cudaMalloc(&d->grid_count, 256));
     FB_CUDA_OK(cudaMemset(d->grid_count, 0, 256));
+    FB_CUDA_OK(cudaMalloc(&d->dev_steps, 256));
+    FB_CUDA_OK(cudaMemset(d->dev_steps, 0, 256));
+    d->dev_done = reinterpret_cast<unsigned int *>(d->dev_steps) + 16;
     d->stamps = nullptr;
     d->two_shot = world >= 4; d->ts_steps = 0;
     for (int q = 0; q < kMaxRanks; q++) { d->peer_grads[0][q] = d->peer_grads[1][q] = nullptr; d->peer_flags[q] = nullptr; d->peer_red[q] = nullptr; }
@@ -216,7 +338,7 @@ extern "C" int fb_dist_create(int rank, int world, long long n_floats, fb_dist *
 extern "C" int fb_dist_destroy(fb_dist *d) {
     if (!d) return FB_OK;
     for (int k = 0; k < d->n_opened; k++) cudaIpcCloseMemHandle(d->opened[k]);
-    cudaFree(d->xgrads[0]); cudaFree(d->xgrads[1]); cudaFree(d->flags); cudaFree(d->red); cudaFree(d->grid_count); cudaFree(d->stamps);
+    cudaFree(d->xgrads[0]); cudaFree(d->xgrads[1]); cudaFree(d->flags); cudaFree(d->red); cudaFree(d->grid_count); cudaFree(d->stamps); cudaFree(d->dev_steps);
     delete d;
     return FB_OK;
 }
@@ -274,6 +396,12 @@ extern "C" int fb_dist_grads(fb_dist *d, int parity, float **out) {
     return FB_OK;
 }
 extern "C" int fb_dist_parity(const fb_dist *d) { return d ? (int)(d->step & 1) : -1; }
+// the training step that carried this exchange in its graph has been enqueued: the next step writes the other buffer
+extern "C" int fb_dist_advance(fb_dist *d) {
+    FB_REQUIRE(d != nullptr, "fb_dist_advance: NULL argument");
+    d->step++;
+    return FB_OK;
+}
 
 // debug: nanosecond %globaltimer stamps of block 0 at the phase boundaries of the most recent exchange (start, peers'
 // gradients published, own slice reduced, slices published, Adam done); the first call switches the stamping on
@@ -309,7 +437,12 @@ extern "C" int fb_dist_adam(fb_dist *d, fb_qnet *net, float *params_dev, float *
     if (x.two_shot) x.ts_step = ++d->ts_steps;
     PackedWeights pw{};
     const int repack = tc_online_operands(net, &pw) ? 1 : 0;
-    adam_xreduce_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(params_dev, m_dev, v_dev, d->n, x, alpha, beta1, beta2, eps, grad_scale, reduced_out_dev,
+    // the two-shot form has a grid barrier: every CTA must be resident.  Two CTAs per SM fit (launch bounds); the grid is sized from
+    // the device, not hard-coded (the graph-resident bucket kernels, adam_xbucket_kernel, have no barrier at all)
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    adam_xreduce_kernel<<<2 * sms, 256, 0, (cudaStream_t)stream>>>(params_dev, m_dev, v_dev, d->n, x, alpha, beta1, beta2, eps, grad_scale, reduced_out_dev,
                                                                repack, net->L, pw);
     FB_CUDA_OK(cudaGetLastError());
     d->step++;

@@ -11,6 +11,8 @@
 // (pipe rows and bird windows come from tables derived from the sprites with cv2's exact fixed-point arithmetic; the rare rows
 // where bird and pipe pixels share a 2x2 tap footprint are evaluated per pixel), expanded to bytes through a 256-entry table
 // and streamed into the ring with 16-byte stores, 512 contiguous bytes per warp instruction.  No full-resolution frame exists.
+#include <stdlib.h>
+
 #include <new>
 
 #include "fb_env_logic.cuh"
@@ -71,31 +73,54 @@ __device__ __forceinline__ uint32_t expand4(uint32_t nib) {      // 4 bits -> 4 
 //     5-row coefficient cycle) is computed once per kernel (RowConst);
 //   * bits -> bytes through a 256-entry table (8 bits -> 8 bytes, 2 KB of shared memory) instead of multiply-and-mask;
 //   * 16-byte chunk c = lane + 32 it of the frame (row c / 5, columns 16 (c % 5) ..): one warp instruction writes 512 contiguous bytes.
-struct RowConst { int sx[3], ph5[3]; };
+struct RowConst { int sx[3], tab[3]; };      // per lane: first source column and byte offset of the phase block inside pipeObs, rows l, l+32, l+64
 
-__device__ __forceinline__ unsigned long long row_mask_fast(const ObsTables &T, const DrawList &d, int i, int sx, int ph5, int j0) {
+// what the drawing warp needs, as whole words (no byte extraction in the inner loops): 32 bytes, read as two broadcast LDS.128
+struct __align__(16) DrawWords {
+    int px[3];          // pipe x; 9999 for an absent pipe (fails the window test)
+    int flags;          // bit 0: bird and pipe pixels can share a 2x2 tap footprint -> per-pixel detour; bits 1-7: first obs column of the
+                        // bird window (birdJ0[y]); bits 8-19: y; bits 20-21: pidx; bits 24-27: number of pipes
+    int goff[3];        // gap index * 8: byte offset of the gap's mask inside a pipeObs phase block
+    int bird;           // (pidx * 380 + y) * 12: byte offset of the bird window rows in birdObs
+};
+__device__ __forceinline__ DrawWords to_words(const ObsTables &T, const DrawList &d) {
+    DrawWords w;
     const int np = d.np_mixed & 15;
-    unsigned long long m = 0;
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-        unsigned c = (unsigned)(sx - d.px[k] + 1);
-        if (k < np && c < 54u) m |= T.pipeObs[c][ph5][d.gap[k]];
-    }
-    unsigned r = (unsigned)(i - 16);
-    if (r < (unsigned)kBirdRows) m |= (unsigned long long)T.birdObs[d.pidx][d.y][r] << j0;
-    return m | (1ull << 63);
+    for (int k = 0; k < 3; k++) { w.px[k] = k < np ? (int)d.px[k] : 9999; w.goff[k] = (int)d.gap[k] * 8; }
+    w.flags = ((d.np_mixed & 16) ? 1 : 0) | ((int)T.birdJ0[d.y] << 1) | ((int)d.y << 8) | ((int)d.pidx << 20) | (np << 24);
+    w.bird = ((int)d.pidx * (kMaxY + 1) + (int)d.y) * (kBirdRows + 3);
+    return w;
 }
 
-__device__ __forceinline__ void render_env(const ObsTables &T, const uint2 *lut8, const ExactTables *ex, const DrawList d, const RowConst &rc,
-                                           unsigned long long *rowmask, uint8_t *out, int lane) {
-    const int j0 = T.birdJ0[d.y];
+// rows of the frame as 16-bit pieces: chunk c = 5 i + part of the frame (16 bytes: row i, columns 16 part ..) has its bits at m16[c];
+// part 4 (columns 64..79, the base strip) is 0xFFFF.  The store loop then needs no index arithmetic at all: lane l reads m16[l + 32 it].
+constexpr int kChunks = kObs * 5;
+
+__device__ __forceinline__ void render_env(const ObsTables &T, const uint2 *lut8, const ExactTables *ex, const DrawWords w,
+                                           const RowConst &rc, unsigned short *m16, unsigned long long *fixrows, uint8_t *out, int lane) {
+    const int j0 = (w.flags >> 1) & 127;
+    const unsigned char *pipe_bytes = reinterpret_cast<const unsigned char *>(&T.pipeObs[0][0][0]);
+    const unsigned char *bird_bytes = reinterpret_cast<const unsigned char *>(&T.birdObs[0][0][0]) + w.bird;
+    unsigned long long m[3];
 #pragma unroll
     for (int it = 0; it < 3; it++) {
-        const int i = lane + 32 * it;
-        if (i < kObs) rowmask[i] = row_mask_fast(T, d, i, rc.sx[it], rc.ph5[it], j0);
+        unsigned long long v = 1ull << 63;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const unsigned c = (unsigned)(rc.sx[it] - w.px[k] + 1);
+            if (c < 54u) v |= *reinterpret_cast<const unsigned long long *>(pipe_bytes + c * 320u + rc.tab[it] + w.goff[k]);
+        }
+        m[it] = v;
     }
-    __syncwarp();
-    if (d.np_mixed & 16) {                           // rare (warp-uniform): evaluate the bird window per pixel
+    if (lane >= 16 && lane < 16 + kBirdRows) m[0] |= (unsigned long long)bird_bytes[lane - 16] << j0;     // rows 16..24 are lanes 16..24, first pass
+    if (w.flags & 1) {                               // rare (warp-uniform): evaluate the bird window per pixel
+        DrawList d;                                  // (the byte-packed form the per-pixel scene code reads)
+        d.y = (int16_t)((w.flags >> 8) & 4095); d.pidx = (uint8_t)((w.flags >> 20) & 3); d.np_mixed = (uint8_t)(((w.flags >> 24) & 15) | 16);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { d.px[k] = (int16_t)(w.px[k] == 9999 ? 0 : w.px[k]); d.gap[k] = (uint8_t)(w.goff[k] >> 3); d.pad[k] = 0; }
+        if (lane >= 16 && lane < 16 + kBirdRows) fixrows[lane - 16] = m[0];
+        __syncwarp();
 #pragma unroll 1
         for (int q = 0; q < 3; q++) {
             int idx = q * 32 + lane, r = idx >> 3, j = j0 + (idx & 7);
@@ -103,19 +128,29 @@ __device__ __forceinline__ void render_env(const ObsTables &T, const uint2 *lut8
             if (r < kBirdRows && j < kBaseJ) bit = exact_obs_bit(ex, d, 0, false, 16 + r, j);
             unsigned bal = __ballot_sync(0xFFFFFFFFu, bit);
             int rr = 4 * q + lane;
-            if (lane < 4 && rr < kBirdRows) rowmask[16 + rr] = obs_row_fix(rowmask[16 + rr], (bal >> (8 * lane)) & 0xFFu, j0);
+            if (lane < 4 && rr < kBirdRows) fixrows[rr] = obs_row_fix(fixrows[rr], (bal >> (8 * lane)) & 0xFFu, j0);
         }
         __syncwarp();
+        if (lane >= 16 && lane < 16 + kBirdRows) m[0] = fixrows[lane - 16];
     }
-    uint4 *dst = reinterpret_cast<uint4 *>(out);
+#pragma unroll
+    for (int it = 0; it < 3; it++) {
+        const int i = lane + 32 * it;
+        if (i < kObs) {
+            unsigned short *row = m16 + 5 * i;
+            row[0] = (unsigned short)m[it]; row[1] = (unsigned short)(m[it] >> 16);
+            row[2] = (unsigned short)(m[it] >> 32); row[3] = (unsigned short)(m[it] >> 48);
+        }
+    }
+    __syncwarp();
+    const unsigned short *mine = m16 + lane;
+    uint4 *dst = reinterpret_cast<uint4 *>(out) + lane;
 #pragma unroll
     for (int it = 0; it < 13; it++) {
-        const int c = lane + 32 * it;                // 16-byte chunk: row c / 5, columns 16 * (c % 5) ..
-        if (c < 400) {
-            const int i = (c * 205) >> 10, part = c - 5 * i;
-            const uint32_t bits = part == 4 ? 0xFFFFu : (uint32_t)(rowmask[i] >> (16 * part)) & 0xFFFFu;
+        if (it < 12 || lane < kChunks - 32 * 12) {
+            const uint32_t bits = mine[32 * it];
             const uint2 a = lut8[bits & 255u], b = lut8[bits >> 8];
-            __stcs(dst + c, make_uint4(a.x, a.y, b.x, b.y));
+            __stcs(dst + 32 * it, make_uint4(a.x, a.y, b.x, b.y));
         }
     }
     __syncwarp();
@@ -130,10 +165,12 @@ __device__ __forceinline__ void render_env(const ObsTables &T, const uint2 *lut8
 constexpr int kStepThreads = 256, kStepWarps = kStepThreads / 32;
 
 __global__ void __launch_bounds__(kStepThreads, 4) env_step_kernel(const StepArgs a) {
-    __shared__ __align__(16) ObsTables T;
+    extern __shared__ __align__(16) unsigned char t_raw[];           // ObsTables (31.5 KB; with the rest 54.7 KB a CTA: four per SM)
+    ObsTables &T = *reinterpret_cast<ObsTables *>(t_raw);
     __shared__ __align__(16) HitTables H;                           // flappy_bird_utils hitmasks as bit rows (checkCrash)
-    __shared__ DrawList dl[kStepWarps][32];
-    __shared__ unsigned long long rowmask[kStepWarps][kObs];
+    __shared__ DrawWords dw[kStepWarps][32];
+    __shared__ __align__(16) unsigned short m16[kStepWarps][kChunks + 8];
+    __shared__ unsigned long long fixrows[kStepWarps][kBirdRows + 1];
     __shared__ uint2 lut8[256];                                     // 8 bits -> 8 bytes of 0x00 / 0xFF
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     lut8[tid] = make_uint2(expand4(tid & 15u), expand4(tid >> 4));
@@ -154,8 +191,10 @@ __global__ void __launch_bounds__(kStepThreads, 4) env_step_kernel(const StepArg
 #pragma unroll
     for (int it = 0; it < 3; it++) {
         const int i = min(lane + 32 * it, kObs - 1);
-        rc.sx[it] = T.sx[i]; rc.ph5[it] = i - 5 * ((i * 205) >> 10);
+        rc.sx[it] = T.sx[i]; rc.tab[it] = (i - 5 * ((i * 205) >> 10)) * 64;
     }
+    for (int i = lane; i < kObs; i += 32) m16[warp][5 * i + 4] = 0xFFFFu;        // the base strip: written once
+    __syncwarp();
     const long long W = (long long)gridDim.x * kStepWarps, w = (long long)blockIdx.x * kStepWarps + warp;
     const int lo = (int)((long long)a.n * w / W), hi = (int)((long long)a.n * (w + 1) / W);
     for (int base = lo; base < hi; base += 32) {
@@ -174,7 +213,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) env_step_kernel(const StepArg
             gs.seed = a.seed; gs.env_id = a.first_id + (uint64_t)e_mine;
         }
         for (int step = 0; step < a.n_steps; step++) {
-            if (have && a.draw_only) dl[warp][lane] = make_draw_list(s);
+            if (have && a.draw_only) dw[warp][lane] = to_words(T, make_draw_list(s));
             if (have && !a.draw_only) {
                 int act;
                 const size_t o = (size_t)step * a.n + e_mine;
@@ -190,14 +229,14 @@ __global__ void __launch_bounds__(kStepThreads, 4) env_step_kernel(const StepArg
                 if (a.reward) a.reward[o] = rew;
                 if (a.terminal) a.terminal[o] = term;
                 if (a.score) a.score[o] = sc;
-                if (a.ring) dl[warp][lane] = make_draw_list(s);
+                if (a.ring) dw[warp][lane] = to_words(T, make_draw_list(s));
             }
             if (a.ring) {
                 const int slot = (a.ring_slot + step) % a.ring_len;
                 __syncwarp();
                 for (int e = 0; e < n_here; e++) {
                     uint8_t *out = a.ring + ((size_t)(base + e) * a.ring_len + slot) * (size_t)FB_FRAME_BYTES;
-                    render_env(T, lut8, a.ex, dl[warp][e], rc, rowmask[warp], out, lane);
+                    render_env(T, lut8, a.ex, dw[warp][e], rc, m16[warp], fixrows[warp], out, lane);
                 }
                 __syncwarp();
             }
@@ -335,17 +374,20 @@ static int launch_step(fb_env *e, StepArgs &a, cudaStream_t st) {
     a.gaps = e->gaps; a.gaps_len = e->gaps_len; a.err_flag = e->err_flag;
     a.obs_tab = fb_tables().obs_dev; a.ex = fb_tables().exact_dev;
     // Few envs: 32 per CTA so that every SM gets work; many envs: 128 per CTA (4 full physics warps).
-    if (e->step_slots == 0) {                      // CTAs that fit the device at once (4 per SM: 46 KB of shared memory, 64 registers)
+    if (e->step_slots == 0) {                      // CTAs that fit the device at once (4 per SM: 54.7 KB of shared memory, 64 registers)
+        FB_CUDA_OK(cudaFuncSetAttribute(env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ObsTables)));
         int per_sm = 0;
-        FB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, env_step_kernel, kStepThreads, 0));
+        FB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, env_step_kernel, kStepThreads, sizeof(ObsTables)));
         FB_REQUIRE(per_sm >= 1, "env_step_kernel does not fit an SM");
         e->step_slots = per_sm * e->num_sms;
     }
     // one env per warp while there are fewer envs than resident warps (every SM draws); equal contiguous shares beyond that
-    long long warps = (long long)e->step_slots * kStepWarps;
+    static int oversub = 0;                        // CTAs per resident slot (FB_ENV_OVERSUB, default 1): > 1 lets the hardware scheduler balance SMs
+    if (oversub == 0) { const char *v = getenv("FB_ENV_OVERSUB"); oversub = (v && v[0] >= '1' && v[0] <= '8') ? v[0] - '0' : 1; }
+    long long warps = (long long)e->step_slots * kStepWarps * oversub;
     if (warps > e->n) warps = e->n;
     const int grid = (int)((warps + kStepWarps - 1) / kStepWarps);
-    env_step_kernel<<<grid, kStepThreads, 0, st>>>(a);
+    env_step_kernel<<<grid, kStepThreads, sizeof(ObsTables), st>>>(a);
     FB_CUDA_OK(cudaGetLastError());
     return FB_OK;
 }

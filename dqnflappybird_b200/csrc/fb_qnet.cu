@@ -393,6 +393,7 @@ extern "C" int fb_qnet_create(int hidden, int dueling, int max_batch, fb_qnet **
     n->precision = FB_PRECISION_FP32;
     n->tc = nullptr;
     n->per_broadcast = 0;
+    n->xch = nullptr;
     size_t B = (size_t)max_batch;
     auto alloc = [](float **p, size_t floats) { return cudaMalloc(p, floats * sizeof(float)); };
     FB_CUDA_OK(alloc(&n->z1, B * 12800)); FB_CUDA_OK(alloc(&n->p1, B * 3200)); FB_CUDA_OK(alloc(&n->a2, B * 1600));
@@ -431,6 +432,15 @@ extern "C" int fb_qnet_set_precision(fb_qnet *n, int precision) {
 }
 
 extern "C" int fb_qnet_get_precision(const fb_qnet *n) { return n ? n->precision : -1; }
+
+// Several GPUs, tensor-core path: fb_qnet_train_step / _sampled then sum every rank's gradients inside their own graph (the
+// exchange's two buckets are kernels of the step, fb_dist.cu) and apply Adam to the sum; `grads_dev` must be the exchange's
+// current buffer (fb_dist_grads / fb_dist_parity) and the caller calls fb_dist_advance after each step.  NULL detaches.
+extern "C" int fb_qnet_attach_exchange(fb_qnet *n, fb_dist *d) {
+    FB_REQUIRE(n != nullptr, "fb_qnet_attach_exchange: NULL argument");
+    n->xch = d;
+    return tc_drop_graphs(n);
+}
 
 // PER loss as the reference's graph computes it (BrainPrioritizedReplyDQN.py:243-251): ISWeights [B,1] * square(...) [B] is
 // broadcast to [B,B] by TensorFlow, so reduce_mean gives mean(w) * mean(err^2) and every sample's gradient is scaled by
@@ -577,7 +587,7 @@ extern "C" int fb_qnet_train_step(fb_qnet *n, int variant, float *params_dev, co
         FrameView fs = make_view(frames_dev, sample_stride, chan_off_s), fn = make_view(frames_dev, sample_stride, chan_off_next);
         TcTrainArgs ta{variant, params_dev, target_params_dev, fs, fn, actions_dev, rewards_dev, terminals_dev, is_weights_dev, batch,
                        global_batch, gamma, loss_sum, grads_dev, loss_out_dev ? loss_out_dev : n->loss_dev, abs_err_out_dev,
-                       q_target_out_dev, AdamFuse{1, m_dev, v_dev, lr, beta1, beta2, eps, grad_scale}};
+                       q_target_out_dev, AdamFuse{1, m_dev, v_dev, lr, beta1, beta2, eps, grad_scale}, n->xch};
         return tc_train_step(n, ta, beta1_power, beta2_power, (cudaStream_t)stream);
     }
     int rc = fb_qnet_loss_backward(n, variant, params_dev, target_params_dev, frames_dev, sample_stride, chan_off_s, chan_off_next, actions_dev,
@@ -609,7 +619,7 @@ extern "C" int fb_qnet_train_step_sampled(fb_qnet *n, const fb_step_sampling *sp
         TcTrainArgs ta{variant, params_dev, target_params_dev, fs, fn, sp->act_out_dev, sp->rew_out_dev, sp->term_out_dev,
                        sp->prioritized ? sp->is_weights_f32_out_dev : nullptr, batch,
                        global_batch, gamma, loss_sum, grads_dev, loss_out_dev ? loss_out_dev : n->loss_dev, abs_err_out_dev,
-                       q_target_out_dev, AdamFuse{adam ? 1 : 0, m_dev, v_dev, lr, beta1, beta2, eps, grad_scale}, *sp};
+                       q_target_out_dev, AdamFuse{adam ? 1 : 0, m_dev, v_dev, lr, beta1, beta2, eps, grad_scale}, adam ? n->xch : nullptr, *sp};
         return adam ? tc_train_step(n, ta, beta1_power, beta2_power, (cudaStream_t)stream) : tc_loss_backward(n, ta, (cudaStream_t)stream);
     }
     FB_REQUIRE(!sp->prioritized || abs_err_out_dev != nullptr, "fb_qnet_train_step_sampled: prioritized replay needs abs_err_out_dev");

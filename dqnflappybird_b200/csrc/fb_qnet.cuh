@@ -45,6 +45,7 @@ struct FrameView {              // where the 4 input channels of each sample liv
 };
 
 // ---- handle shared by the strict-fp32 path (fb_qnet.cu) and the tcgen05 path (fb_qnet_tc.cu) ------------
+struct fb_dist;                 // multi-GPU gradient exchange (fb_dist.cu)
 struct TcState;                 // bf16 workspace, packed weights and TMA plans (fb_qnet_tc.cu)
 struct fb_qnet {
     QnetLayout L;
@@ -57,6 +58,7 @@ struct fb_qnet {
     float *partial; size_t partial_floats;
     float *loss_dev;
     TcState *tc;
+    fb_dist *xch;                 // attached exchange: the training step sums every rank's gradients inside its own graph (or NULL)
     int per_broadcast;            // PER loss as the reference's graph really computes it: every sample weighted by mean(ISWeights)
     const float *packed_src[2];   // parameter vectors the bf16 operand copies (slot 0 online, 1 target) were made from
 };
@@ -81,6 +83,7 @@ struct TcTrainArgs {
     int B, global_batch; double gamma; int loss_sum;
     float *grads, *loss_out, *abs_err, *q_target;
     AdamFuse ad;                            // ad.on: params is updated in place at the end of the step
+    fb_dist *xch;                           // with ad.on: Adam over the SUM of all ranks' gradients (buckets of fb_dist.cu inside the graph)
     fb_step_sampling pro;                   // pro.replay != nullptr: the minibatch is drawn by the step's first two kernels
 };
 // fb_replay.cu: the two kernels of fb_replay_sample_uniform + fb_replay_gather on `st`; and the per-step patch of their
@@ -91,6 +94,11 @@ bool replay_is_sampler(const void *func);        // sample_uniform_kernel or per
 bool replay_is_gather(const void *func);
 int replay_patch_nodes(cudaGraphExec_t exec, cudaGraphNode_t sampler, cudaGraphNode_t gather, const fb_step_sampling &p);
 inline bool tc_precision(int precision) { return precision == FB_PRECISION_BF16 || precision == FB_PRECISION_FP16; }
+// fb_dist.cu: one bucket of the exchange + Adam as a kernel on `st` (bucket 0 = W_fc1, 1 = the rest), for the exchange buffer of
+// the current parity; the buffer the step's gradients must have been written to
+int dist_launch_bucket(fb_dist *d, fb_qnet *net, int bucket, float *params_dev, float *m_dev, float *v_dev, const float *alpha_dev, float beta1,
+                       float beta2, float eps, float grad_scale, cudaStream_t st);
+const float *dist_current_grads(const fb_dist *d);
 int tc_state_create(fb_qnet *n);
 int tc_set_format(fb_qnet *n, int f16);          // operand format of the tensor-core path: 0 bf16, 1 fp16
 int tc_drop_graphs(fb_qnet *n);                 // captured steps embed the net's settings: drop them when one changes

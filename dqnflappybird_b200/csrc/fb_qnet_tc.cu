@@ -1799,8 +1799,20 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
         return cudaGetLastError();
     };
     FB_CUDA_OK(colsum_on(t->dz3, t->bp3, P2, 64, kChunk23, c23));
-    AdamDev ad{a.ad.on, const_cast<float *>(a.params), a.ad.m, a.ad.v, a.ad.beta1, a.ad.beta2, a.ad.eps, a.ad.grad_scale, t->adam_pow + 2};
+    FB_REQUIRE(a.xch == nullptr || !a.ad.on || a.grads == dist_current_grads(a.xch), "training step with an exchange: gradients must go to its current buffer");
+    AdamDev ad{a.ad.on && a.xch == nullptr, const_cast<float *>(a.params), a.ad.m, a.ad.v, a.ad.beta1, a.ad.beta2, a.ad.eps, a.ad.grad_scale, t->adam_pow + 2};
     FB_CUDA_OK((launch_tc_wgrad<64, 5, kSlabW3, 1, 6>(p->a2_w, p->dz3_b, p->conv3_w, p->s3, EpiStoreF32{t->part3, 640, 64, (size_t)640 * 64}, sx)));
+    if (a.ad.on) {                                                      // on sy, early: after the fc1 weight gradient (sx) and the fc1 data gradient (the last reader of wf1n)
+        FB_CUDA_OK(cudaStreamWaitEvent(sy, t->ev[e_fc1w], 0));
+        if (a.xch != nullptr) {     // several GPUs: W_fc1's share of the gradient exchange + Adam, beside the convolution gradients
+            rc = dist_launch_bucket(a.xch, n, 0, const_cast<float *>(a.params), a.ad.m, a.ad.v, t->adam_pow + 2, a.ad.beta1, a.ad.beta2, a.ad.eps,
+                                    a.ad.grad_scale, sy);
+            if (rc) return rc;
+        } else {
+            adam_wf1_kernel<<<4 * t->n_sms, 256, 0, sy>>>(L, a.grads, ad, t->pw[0]);
+            FB_CUDA_OK(cudaGetLastError());
+        }
+    }
     if (t->fuse_bwd && B <= kFuseMaxBatch) {
         // conv3 data gradient + ReLU mask + conv2 data gradient + un-pool in one kernel (tc_bwd23_kernel)
         FB_CUDA_OK((launch_tc_bwd23<2>(p->dz3_s, wm.w3d, wm.w2d, Bwd23Params{(B + 1) / 2, B, f.a2, t->dz2, f.z1, t->dz1, t->f16}, t->n_sms, st)));
@@ -1820,11 +1832,6 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
         FB_CUDA_OK(fork(st, sy));                                       // sy: after the un-pool (dz1 complete)
         FB_CUDA_OK(colsum_on(t->dz1, t->bp1, P1, 32, kChunk1, c1));
     }
-    if (a.ad.on) {                                                      // last on sy: after the fc1 weight gradient (sx) and the fc1 data gradient
-        FB_CUDA_OK(cudaStreamWaitEvent(sy, t->ev[e_fc1w], 0));
-        adam_wf1_kernel<<<4 * t->n_sms, 256, 0, sy>>>(L, a.grads, ad, t->pw[0]);
-        FB_CUDA_OK(cudaGetLastError());
-    }
     // conv1 weight gradient (no input gradient there); the bias gradients = column sums of the dZ tensors ran beside it
     FB_CUDA_OK((launch_tc_wgrad<32, 2, kSlabW1, 1, 6>(p->x2_w, p->dz1_b, p->conv1_w, p->s1, EpiStoreF32{t->part1, 256, 32, (size_t)256 * 32}, st)));
     FB_CUDA_OK(fork(sx, st));
@@ -1833,6 +1840,11 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     const int n_compact = L.wf1 + (L.total - L.bf1);
     const int nb_fin = (n_compact + 31) / 32;
     FB_CUDA_OK(tc::launch_pdl(finalize_grads_kernel, dim3(nb_fin), dim3(256), 0, st, fa, L, a.grads, ad, t->pw[0]));
+    if (a.ad.on && a.xch != nullptr) {          // the rest of the vector (79,522 parameters): the only exchange left at the tail
+        rc = dist_launch_bucket(a.xch, n, 1, const_cast<float *>(a.params), a.ad.m, a.ad.v, t->adam_pow + 2, a.ad.beta1, a.ad.beta2, a.ad.eps,
+                                a.ad.grad_scale, st);
+        if (rc) return rc;
+    }
     if (a.pro.replay != nullptr && a.pro.prioritized) { rc = replay_launch_per_update(a.pro, a.abs_err, st); if (rc) return rc; }   // Memory.batch_update
     return FB_OK;
 }
@@ -1894,6 +1906,7 @@ int tc_loss_backward(fb_qnet *n, const TcTrainArgs &a, cudaStream_t st) {
     key.a.grads = a.grads; key.a.loss_out = a.loss_out; key.a.abs_err = a.abs_err; key.a.q_target = a.q_target;
     key.a.ad.on = a.ad.on; key.a.ad.m = a.ad.m; key.a.ad.v = a.ad.v; key.a.ad.lr = a.ad.lr; key.a.ad.beta1 = a.ad.beta1; key.a.ad.beta2 = a.ad.beta2;
     key.a.ad.eps = a.ad.eps; key.a.ad.grad_scale = a.ad.grad_scale;
+    key.a.xch = a.xch;
     {   // the sampling head: everything but `t`, which is patched into the two nodes before every launch
         const fb_step_sampling &q = a.pro; fb_step_sampling &k = key.a.pro;
         k.replay = q.replay; k.ring_dev = q.ring_dev; k.act_dev = q.act_dev; k.rew_dev = q.rew_dev; k.term_dev = q.term_dev;

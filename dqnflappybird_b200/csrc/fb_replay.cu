@@ -30,22 +30,26 @@ constexpr int kSampThreads = 256, kCandPerThread = 4, kCandPerRound = kSampThrea
 constexpr int kHashSize = 4096;            // distinct keys ever inserted < max batch 512 + one round (1024)
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 
-__device__ __forceinline__ uint32_t sample_word(uint64_t seed, uint32_t pos) { return stream_word(seed, 3u, 0ull, pos); }
+// The stream position is 64 bits: its low word indexes the Philox block / lane as before, its high word goes into the counter
+// lanes that carry the env id for the per-env streams (these two streams have none), so the sequence never repeats -- a 32-bit
+// position wrapped after 2^32 words, ~8 M updates of minibatch 256.  Below 2^32 words the stream is the one the oracle draws.
+__device__ __forceinline__ uint32_t sample_word(uint64_t seed, unsigned long long pos) { return stream_word(seed, 3u, pos >> 32, (uint32_t)pos); }
+__device__ __forceinline__ uint32_t per_word(uint64_t seed, unsigned long long pos) { return stream_word(seed, 4u, pos >> 32, (uint32_t)pos); }
 
 __global__ void __launch_bounds__(kSampThreads) sample_uniform_kernel(uint32_t n, int batch, uint32_t setsize, uint64_t seed,
-                                                                      uint32_t *word_pos, int32_t *out) {
+                                                                      unsigned long long *word_pos, int32_t *out) {
     __shared__ uint32_t hbuf[2 * kHashSize];
     uint32_t *hkey = hbuf, *hidx = hbuf + kHashSize;
     __shared__ uint32_t warp_tot[kSampThreads / 32];
     __shared__ uint32_t s_taken, s_consumed;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t pos0 = *word_pos;
+    const unsigned long long pos0 = *word_pos;
     if (n <= setsize) {                    // pool branch (Lib/random.py: "An n-length list is smaller than a k-length set")
         uint32_t *pool = hbuf;             // n <= setsize <= 2 * kHashSize
         for (uint32_t i = tid; i < n; i += kSampThreads) pool[i] = i;
         __syncthreads();
         if (tid == 0) {
-            uint32_t pos = pos0;
+            unsigned long long pos = pos0;
             for (int i = 0; i < batch; i++) {
                 uint32_t m = n - (uint32_t)i, bits = 32 - __clz(m), j;
                 do { j = sample_word(seed, pos++) >> (32 - bits); } while (j >= m);
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(256) per_store_multi_kernel(double *tree, doub
 // 983,040 leaves.  min_prob comes from the root of the min tree.  The CTA that finishes last advances the stream position.
 constexpr int kSampleWarps = 8;
 __global__ void __launch_bounds__(32 * kSampleWarps) per_sample_kernel(const double *tree, const double *mn, int cap, int batch, double beta,
-                                                                       uint64_t seed, uint32_t *word_pos, unsigned int *done_counter, int32_t *tree_idx,
+                                                                       uint64_t seed, unsigned long long *word_pos, unsigned int *done_counter, int32_t *tree_idx,
                                                                        int32_t *data_idx, double *isw, double *prio_out, float *isw_f32) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * kSampleWarps + warp;
@@ -350,10 +354,10 @@ __global__ void __launch_bounds__(32 * kSampleWarps) per_sample_kernel(const dou
     for (int j = threadIdx.x; j < n_top; j += blockDim.x) s_top[j] = tree[j];
     __syncthreads();
     const double total = s_top[0];
-    const uint32_t pos0 = *word_pos;
+    const unsigned long long pos0 = *word_pos;
     if (i < batch) {
         double seg = total / (double)batch, a = seg * (double)i, b = seg * (double)(i + 1);
-        uint32_t w0 = stream_word(seed, 4u, 0ull, pos0 + 2 * i) >> 5, w1 = stream_word(seed, 4u, 0ull, pos0 + 2 * i + 1) >> 6;
+        uint32_t w0 = per_word(seed, pos0 + 2 * i) >> 5, w1 = per_word(seed, pos0 + 2 * i + 1) >> 6;
         double u = ((double)w0 * 67108864.0 + (double)w1) / 9007199254740992.0;
         double v = a + (b - a) * u;
         int parent = 0;
@@ -399,7 +403,7 @@ __global__ void __launch_bounds__(32 * kSampleWarps) per_sample_kernel(const dou
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
     __syncthreads();
-    if (s_last && threadIdx.x == 0) { *word_pos = pos0 + 2 * (uint32_t)batch; *done_counter = 0u; }     // every CTA has read pos0 by now
+    if (s_last && threadIdx.x == 0) { *word_pos = pos0 + 2ull * (unsigned long long)batch; *done_counter = 0u; }     // every CTA has read pos0 by now
 }
 
 __global__ void store_leaves_kernel(int N, int C, long long k, int32_t *leaves) {   // leaf of transition k for every env
@@ -422,7 +426,7 @@ struct fb_replay {
     double *mn, *mx;                 // min-positive / max trees of the same shape (see the SumTree section)
     unsigned int *counters;          // [0] per_store_multi_kernel, [1] per_sample_kernel: "last CTA" counters, self-resetting
     int32_t *leaves; double *prio; double *change;   // scratch, max(N, max_batch)
-    uint32_t *word_pos;              // [0] uniform stream, [1] PER stream
+    unsigned long long *word_pos;    // [0] uniform stream, [1] PER stream (64-bit word positions)
     int scratch_n;
 };
 
@@ -434,8 +438,8 @@ extern "C" int fb_replay_create(int n_envs, int ring_len, int capacity_per_env, 
     FB_REQUIRE(r != nullptr, "fb_replay_create: out of host memory");
     r->N = n_envs; r->L = ring_len; r->C = capacity_per_env; r->cap = n_envs * capacity_per_env; r->tree = nullptr;
     r->scratch_n = n_envs > max_batch ? n_envs : max_batch;
-    FB_CUDA_OK(cudaMalloc(&r->word_pos, 2 * sizeof(uint32_t)));
-    FB_CUDA_OK(cudaMemset(r->word_pos, 0, 2 * sizeof(uint32_t)));
+    FB_CUDA_OK(cudaMalloc(&r->word_pos, 2 * sizeof(unsigned long long)));
+    FB_CUDA_OK(cudaMemset(r->word_pos, 0, 2 * sizeof(unsigned long long)));
     r->mn = r->mx = nullptr;
     FB_CUDA_OK(cudaMalloc(&r->counters, 2 * sizeof(unsigned int)));
     FB_CUDA_OK(cudaMemset(r->counters, 0, 2 * sizeof(unsigned int)));
@@ -541,7 +545,7 @@ int replay_patch_nodes(cudaGraphExec_t exec, cudaGraphNode_t sampler, cudaGraphN
     cudaKernelNodeParams kp{};
     int batch = p.batch; uint64_t seed = p.seed; int32_t *idx = p.idx_out_dev;
     if (p.prioritized) {
-        const double *tree = r->tree, *mn = r->mn; int cap = r->cap; double beta = p.beta; uint32_t *word_pos = r->word_pos + 1;
+        const double *tree = r->tree, *mn = r->mn; int cap = r->cap; double beta = p.beta; unsigned long long *word_pos = r->word_pos + 1;
         unsigned int *done = r->counters + 1;
         int32_t *tree_idx = p.tree_idx_out_dev; double *isw = p.is_weights_out_dev, *prio = p.prio_out_dev; float *isw32 = p.is_weights_f32_out_dev;
         void *sargs[] = {&tree, &mn, &cap, &batch, &beta, &seed, &word_pos, &done, &tree_idx, &idx, &isw, &prio, &isw32};
@@ -550,7 +554,7 @@ int replay_patch_nodes(cudaGraphExec_t exec, cudaGraphNode_t sampler, cudaGraphN
     } else {
         uint32_t n;
         if (!sampling_population(p, &n)) { fb_set_error("Sample larger than population or is negative"); return FB_ERR_INVALID; }
-        uint32_t setsize = p.setsize; uint32_t *word_pos = r->word_pos;
+        uint32_t setsize = p.setsize; unsigned long long *word_pos = r->word_pos;
         void *sargs[] = {&n, &batch, &setsize, &seed, &word_pos, &idx};
         kp.func = (void *)sample_uniform_kernel; kp.gridDim = dim3(1); kp.blockDim = dim3(kSampThreads); kp.kernelParams = sargs;
         FB_CUDA_OK(cudaGraphExecKernelNodeSetParams(exec, sampler, &kp));
@@ -615,11 +619,11 @@ extern "C" int fb_per_aux_tree_copy(fb_replay *r, int which, double *out_dev, in
     return FB_OK;
 }
 
-extern "C" int fb_replay_rng_pos(fb_replay *r, uint32_t *pos_host2, int set, void *stream) {
+extern "C" int fb_replay_rng_pos(fb_replay *r, uint64_t *pos_host2, int set, void *stream) {
     FB_REQUIRE(r && pos_host2, "fb_replay_rng_pos: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    if (set) FB_CUDA_OK(cudaMemcpyAsync(r->word_pos, pos_host2, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    else FB_CUDA_OK(cudaMemcpyAsync(pos_host2, r->word_pos, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (set) FB_CUDA_OK(cudaMemcpyAsync(r->word_pos, pos_host2, 2 * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    else FB_CUDA_OK(cudaMemcpyAsync(pos_host2, r->word_pos, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     FB_CUDA_OK(cudaStreamSynchronize(st));
     return FB_OK;
 }

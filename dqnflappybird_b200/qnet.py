@@ -90,6 +90,7 @@ class QNetwork:
         self.beta1_power, self.beta2_power = np.float32(beta1), np.float32(beta2)      # TF keeps these as fp32 variables
         self.adam_steps = 0
         self.exchange = None                    # dist.PeerGradExchange once enable_peer_exchange() was called
+        self.exchange_in_step = False
 
     def set_per_broadcast(self, on: bool):
         """PER loss exactly as the reference's graph evaluates it (BrainPrioritizedReplyDQN.py:243-251): the [B,1] ISWeights
@@ -102,6 +103,9 @@ class QNetwork:
         from .dist import PeerGradExchange
         self.exchange = exchange if exchange is not None else PeerGradExchange(self.n_params, self.device)
         self.grads = self.exchange.grads
+        # tensor-core path: the exchange rides INSIDE the training step's graph (fb_dist.cu buckets) instead of after it
+        self.exchange_in_step = self.precision != "fp32" and self.exchange.world > 1 and not getattr(self.exchange, "no_wait", False)
+        _lib.check(self._L.fb_qnet_attach_exchange(self._h, self.exchange._h if self.exchange_in_step else None), "fb_qnet_attach_exchange")
         return self.exchange
 
     def __del__(self):
@@ -202,7 +206,8 @@ class QNetwork:
         ``sampling`` (``ReplayMemory.step_sampling(batch)[0]``): the minibatch is drawn and gathered by the step's first two
         kernels -- ``random.sample`` and the list comprehensions of BrainDQN.py:197-201 ride in the same graph; ``frames`` /
         ``actions`` / ``rewards`` / ``terminals`` must then be the replay's own minibatch buffers."""
-        if sampling is not None and self.exchange is None:
+        in_step = self.exchange is None or self.exchange_in_step
+        if sampling is not None and in_step:
             assert frames.data_ptr() == sampling.frames_out_dev and frames.shape[0] == sampling.batch
             assert (is_weights is None) == (not sampling.prioritized)
             off_s, off_n = _OFF_S, _OFF_N
@@ -214,7 +219,7 @@ class QNetwork:
                 ptr(q_target), self.adam_m.data_ptr(), self.adam_v.data_ptr(), float(self.lr), float(self.beta1), float(self.beta2),
                 float(self.adam_eps), float(grad_scale), float(self.beta1_power), float(self.beta2_power), self._stream()),
                 "fb_qnet_train_step_sampled")
-            self._advance_powers()
+            self._after_fused_step()
             return self.loss
         if sampling is not None:                 # not fusable here: draw the minibatch with its own two launches
             assert not sampling.prioritized, "with a peer exchange call PrioritizedMemory.sample / batch_update yourself"
@@ -224,7 +229,7 @@ class QNetwork:
                                                 sampling.t, 0, sampling.idx_out_dev, sampling.batch, sampling.frames_out_dev,
                                                 sampling.act_out_dev, sampling.rew_out_dev, sampling.term_out_dev, sampling.env_out_dev,
                                                 sampling.k_out_dev, self._stream()), "fb_replay_gather")
-        if self.exchange is not None:
+        if self.exchange is not None and not self.exchange_in_step:
             self.loss_backward(variant, frames, actions, rewards, terminals, is_weights, gamma, loss_sum, global_batch, abs_err, q_target)
             self.adam_step(grad_scale)
             return self.loss
@@ -240,8 +245,14 @@ class QNetwork:
             ptr(q_target), self.adam_m.data_ptr(), self.adam_v.data_ptr(), float(self.lr), float(self.beta1), float(self.beta2),
             float(self.adam_eps), float(grad_scale), float(self.beta1_power), float(self.beta2_power), self._stream()),
             "fb_qnet_train_step")
-        self._advance_powers()
+        self._after_fused_step()
         return self.loss
+
+    def _after_fused_step(self):
+        self._advance_powers()
+        if self.exchange_in_step:                # the step's graph carried the exchange: switch to the other exchange buffer
+            _lib.check(self._L.fb_dist_advance(self.exchange._h), "fb_dist_advance")
+            self.grads = self.exchange.grads
 
     def _advance_powers(self):
         """beta1_power *= beta1, beta2_power *= beta2 in fp32, like the update ops TF-1's Adam runs after every step"""

@@ -120,7 +120,7 @@ class ReplayMemory:
         return self._gather(self._idx, batch, per=False)
 
     def rng_positions(self):
-        pos = (C.c_uint32 * 2)()
+        pos = (C.c_uint64 * 2)()
         _lib.check(self._L.fb_replay_rng_pos(self._h, pos, 0, self._stream()), "fb_replay_rng_pos")
         return int(pos[0]), int(pos[1])
 

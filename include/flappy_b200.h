@@ -250,6 +250,12 @@ int fb_dist_connect(fb_dist *d, const uint8_t *all_handles_host);   /* world x f
 int fb_dist_connect_local(fb_dist *d, int q, fb_dist *peer);        /* test hook: "ranks" inside one process */
 int fb_dist_grads(fb_dist *d, int parity, float **out_dev_ptr);
 int fb_dist_parity(const fb_dist *d);
+/* With an exchange attached to a net on the tensor-core path (fb_qnet_attach_exchange) the training step carries the exchange
+ * inside its own CUDA graph: W_fc1's 91 % of the gradient vector is summed over NVLink peer memory and Adam-updated beside the
+ * convolution gradients, the remaining 79,522 parameters at the tail; step number and alpha live in device memory.
+ * fb_dist_advance: that step has been enqueued, the next one writes the other exchange buffer. */
+int fb_dist_advance(fb_dist *d);
+int fb_qnet_attach_exchange(fb_qnet *net, fb_dist *d);
 int fb_dist_adam(fb_dist *d, fb_qnet *net, float *params_dev, float *m_dev, float *v_dev, float alpha, float beta1, float beta2,
                  float eps, float grad_scale, float *reduced_out_dev /* may be NULL */, int wait, void *stream);
 /* debug: %globaltimer (ns) of the last exchange's phase boundaries on this rank: start, all gradients published, own slice
@@ -302,7 +308,7 @@ int fb_per_update(fb_replay *r, const int32_t *tree_idx_dev, const float *abs_er
 int fb_per_tree_copy(fb_replay *r, double *out_dev, int n_nodes, void *stream);
 /* test hook: the min-positive-leaf tree (which = 1) or the max-leaf tree (2) kept beside the SumTree, same shape */
 int fb_per_aux_tree_copy(fb_replay *r, int which, double *out_dev, int n_nodes, void *stream);
-int fb_replay_rng_pos(fb_replay *r, uint32_t *pos_host2, int set, void *stream);
+int fb_replay_rng_pos(fb_replay *r, uint64_t *pos_host2, int set, void *stream);
 
 /* The minibatch of fb_qnet_train_step drawn INSIDE the step: random.sample + the list comprehensions of BrainDQN.py:197-201
  * (fb_replay_sample_uniform + fb_replay_gather with these arguments) run as the first two kernels of the step, so that on

@@ -411,6 +411,22 @@ static void *batch_worker(void *arg) {
     return NULL;
 }
 
+/* T consecutive frame_steps of ONE env (long golden trajectories): per-step reward / terminal / score / exported state, and the
+ * preprocessed observation after every step whose want_obs flag is set (packed in order into obs_out) */
+int fo_env_run(fo_env *e, int T, const uint8_t *actions, const uint8_t *want_obs, float *reward, uint8_t *terminal, int32_t *score,
+               int32_t *state16 /* [T][16] */, uint8_t *obs_out /* [n_wanted][80][80] */) {
+    uint8_t *frame = (uint8_t *)malloc((size_t)SCREENWIDTH * SCREENHEIGHT * 3);
+    size_t k = 0;
+    int rc = 0;
+    for (int t = 0; t < T; t++) {
+        if (fo_env_step(e, actions[t], &reward[t], &terminal[t], &score[t]) != 0) { rc = -1; break; }
+        fo_env_export_state(e, state16 + (size_t)t * 16);
+        if (want_obs && want_obs[t]) fo_env_obs(e, frame, obs_out + (k++) * OBS * OBS);
+    }
+    free(frame);
+    return rc;
+}
+
 int fo_batch_step(fo_env **envs, int n, const uint8_t *actions, float *reward, uint8_t *terminal,
                   int32_t *score, uint8_t *obs /* [n][80][80] or NULL */, int n_threads) {
     if (n_threads < 1) n_threads = 1;

@@ -135,6 +135,21 @@ class OracleEnvs:
             raise ValueError("Multiple input actions!")
         return obs, r, t, s
 
+    def run(self, k: int, actions, want_obs=None):
+        """T consecutive steps of env k in one C call: (reward[T], terminal[T], score[T], state[T][16], obs[n_wanted][80][80])"""
+        a = np.ascontiguousarray(actions, np.uint8)
+        T = len(a)
+        w = np.ascontiguousarray(want_obs, np.uint8) if want_obs is not None else np.zeros(T, np.uint8)
+        r = np.empty(T, np.float32); t = np.empty(T, np.uint8); s = np.empty(T, np.int32); st = np.empty((T, 16), np.int32)
+        obs = np.empty((int(w.sum()), 80, 80), np.uint8)
+        L = lib()
+        L.fo_env_run.argtypes = [C.c_void_p] + [C.c_int] + [C.c_void_p] * 7
+        rc = L.fo_env_run(self._h[k], T, a.ctypes.data, w.ctypes.data, r.ctypes.data, t.ctypes.data, s.ctypes.data, st.ctypes.data,
+                          obs.ctypes.data)
+        if rc != 0:
+            raise ValueError("Multiple input actions!")
+        return r, t, s, st, obs
+
     def export_state(self) -> np.ndarray:
         out = np.zeros((self.n, 16), np.int32)
         for k, h in enumerate(self._h):

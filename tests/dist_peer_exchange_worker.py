@@ -34,6 +34,44 @@ def main():
     dist.all_gather(everyone, net.params)
     assert all(torch.equal(everyone[0], e) for e in everyone), "parameters differ between ranks"
 
+    # ---- the exchange INSIDE the training step's graph (tensor-core path): per-rank minibatches, W_fc1's bucket summed and
+    # Adam-updated beside the convolution gradients, the rest at the tail -- against loss_backward + NCCL all-reduce + Adam
+    B = 32
+    gsx = GameState(num_envs=B, device=dev, seed=50 + rank, history=5)
+    gsx.step_random(45, 0.3, 11 + rank)
+    order = [(gsx.slot - 4 + k) % 5 for k in range(5)]
+    frames = gsx.ring[:, order].contiguous()
+    gr = torch.Generator(device=dev).manual_seed(7 + rank)
+    for precision in ("fp16", "bf16"):
+        fused = qnet.QNetwork(device=dev, max_batch=B, seed=5, precision=precision, lr=1e-3)
+        plain = qnet.QNetwork(device=dev, max_batch=B, seed=5, precision=precision, lr=1e-3)
+        for nn in (fused, plain):
+            nn.params.mul_(4.0); nn.target.mul_(4.0)
+        fused.enable_peer_exchange()
+        assert fused.exchange_in_step
+        for step in range(6):                          # eager, eager, then graph replays (two graphs: one per exchange buffer)
+            a = (torch.rand(B, device=dev, generator=gr) < 0.5).to(torch.uint8)
+            r = torch.where(torch.rand(B, device=dev, generator=gr) < 0.2, torch.tensor(3.0, device=dev), torch.tensor(0.1, device=dev))
+            term = torch.zeros(B, dtype=torch.uint8, device=dev)
+            fused.train_step("nature", frames, a, r, term, global_batch=B * world)
+            plain.loss_backward("nature", frames, a, r, term, global_batch=B * world)
+            dist.all_reduce(plain.grads)
+            plain.adam_step()
+            assert torch.allclose(fused.params, plain.params, rtol=0, atol=2e-6), (precision, step, (fused.params - plain.params).abs().max().item())
+            assert fused.beta1_power == plain.beta1_power and fused.adam_steps == step + 1
+            if step == 3:
+                fused.sync_target(); plain.sync_target()
+        ps = [torch.empty_like(fused.params) for _ in range(world)]
+        dist.all_gather(ps, fused.params)
+        assert all(torch.equal(ps[0], e) for e in ps), "in-step exchange: replicas diverged"
+        moved = (fused.params - plain.params).abs().max().item()
+        upd = (fused.params.mean() * 0 + (plain.adam_m.abs().max())).item()
+        assert upd > 0, "no update happened"
+        # the next forward uses the operand copies the bucket kernels rewrote
+        qf = fused.forward(qnet.FrameBatch.from_stack(frames, 0)); qp = plain.forward(qnet.FrameBatch.from_stack(frames, 0))
+        assert torch.allclose(qf, qp, rtol=0, atol=2e-2 * qp.abs().max().item()), moved
+        del fused, plain
+
     # data-parallel training: envs / replay sharded, per-rank minibatch, gradients summed inside the Adam kernel
     N = 64
     brain = BrainDQNNature(2, "bird", num_envs=N, device=dev, replay_memory_per_env=12, observe=6., batch_size=32 * world, seed=1,

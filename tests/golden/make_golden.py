@@ -172,7 +172,7 @@ def gen_env_long():
     acts = np.zeros(T, np.uint8); rew = np.zeros(T, np.float32); term = np.zeros(T, np.uint8)
     score = np.zeros(T, np.int32); st = np.zeros((T, 16), np.int32)
     obs_idx, obs_bits, crash_kind = [], [], []
-    lapse = 0
+    lapse, lapse_p = 0, 0.0
     for t in range(T):
         if t == 0:
             a = 0
@@ -184,11 +184,13 @@ def gen_env_long():
             centre = (nxt["y"] + game.PIPE_HEIGHT + game.PIPEGAPSIZE / 2) if nxt else 256
             if lapse > 0:
                 lapse -= 1
-                a = int(rng.random() < (0.0 if lapse % 2 else 0.6))      # erratic: falls or climbs into a pipe
+                a = int(rng.random() < lapse_p)                         # a lapse either stops flapping (falls into a lower pipe
+                                                                         # or the ground) or flaps wildly (climbs into an upper pipe)
             else:
                 a = int((gs.playery + 12) - centre > 14)
-                if rng.random() < 0.0012:
+                if rng.random() < 0.0016:
                     lapse = int(rng.integers(12, 40))
+                    lapse_p = 0.0 if rng.random() < 0.6 else 0.6
         y_before = gs.playery
         onehot = np.array([1, 0]) if a == 0 else np.array([0, 1])
         image, r, done, sc = gs.frame_step(onehot)
