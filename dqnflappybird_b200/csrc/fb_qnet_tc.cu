@@ -1387,6 +1387,7 @@ struct TcState {
     int n_sms;
     cudaStream_t aux;           // second stream: target forward / weight gradients run beside the critical path
     cudaStream_t aux2;          // third stream: bias column sums and the early Adam on W_fc1
+    cudaStream_t aux3;          // fourth stream (several GPUs): W_fc1's bucket of the gradient exchange, joined only at the step's end
     cudaStream_t cap;           // capture origin (the caller's stream may be the legacy default stream, which cannot capture)
     cudaEvent_t ev[16];
     std::vector<GraphEntry> graphs;
@@ -1564,6 +1565,7 @@ int tc_state_create(fb_qnet *n) {
         FB_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         FB_CUDA_OK(cudaStreamCreateWithPriority(&t->aux, cudaStreamNonBlocking, lo));
         FB_CUDA_OK(cudaStreamCreateWithPriority(&t->aux2, cudaStreamNonBlocking, hi));     // short kernels finalize waits for
+        FB_CUDA_OK(cudaStreamCreateWithPriority(&t->aux3, cudaStreamNonBlocking, hi));
         FB_CUDA_OK(cudaStreamCreateWithPriority(&t->cap, cudaStreamNonBlocking, hi));
     }
     for (auto &e : t->ev) FB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1596,6 +1598,7 @@ void tc_state_destroy(fb_qnet *n) {
     for (auto &e : t->ev) if (e) cudaEventDestroy(e);
     if (t->aux) cudaStreamDestroy(t->aux);
     if (t->aux2) cudaStreamDestroy(t->aux2);
+    if (t->aux3) cudaStreamDestroy(t->aux3);
     if (t->cap) cudaStreamDestroy(t->cap);
     delete t;
     n->tc = nullptr;
@@ -1774,6 +1777,13 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     if (t->f16) { gscale = 8.f; if (!a.loss_sum) { int gb = a.global_batch > 0 ? a.global_batch : B; while (gscale < 8.f * (float)gb) gscale *= 2.f; } }
     rc = tc_forward_impl(n, 0, 0, a.params, a.fs, B, n->q, 1, st, &td, t->ev[e], &apow, gscale); if (rc) return rc;
     e++;
+    // Memory.batch_update (BrainPrioritizedReplyDQN.py:316) needs only |TD error|, which the head kernel has just written: it runs on
+    // a stream of its own beside the whole backward pass (measured: 26 us at the step's tail otherwise) and joins at the end
+    const bool per_on_side = a.pro.replay != nullptr && a.pro.prioritized;
+    if (per_on_side) {
+        FB_CUDA_OK(fork(st, t->aux3));
+        rc = replay_launch_per_update(a.pro, a.abs_err, t->aux3); if (rc) return rc;
+    }
     // ---- backward.  The head's backward pass rode in the forward's last kernel when hidden = 512 (fc1_head_train_kernel);
     // otherwise: fp32 gradients of the head variables and the fc1 bias straight into partials, dh1 as bf16
     const bool fused_head = fused_head_ok(L);
@@ -1789,7 +1799,8 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     FB_CUDA_OK(cudaEventRecord(t->ev[e_fc1w], sx));                    // W_fc1's gradient is final
     FB_CUDA_OK((launch_tc_gemm<64, 0>(p->dh1_k, wm.wf1n, p->fc1_d, dim3((B + 127) / 128, kFlat / 64, 1), EpiFc1Dgrad{t->dz3, f.a3, B, t->f16}, st)));
     FB_CUDA_OK(fork(st, sx));
-    FB_CUDA_OK(cudaStreamWaitEvent(sy, t->ev[e - 1], 0));              // sy: after the fc1 data gradient (dz3 complete, wf1n no longer read)
+    const int e_fc1d = e - 1;
+    FB_CUDA_OK(cudaStreamWaitEvent(sy, t->ev[e_fc1d], 0));              // sy: after the fc1 data gradient (dz3 complete, wf1n no longer read)
     const int c1 = (P1 + kChunk1 - 1) / kChunk1, c23 = (P2 + kChunk23 - 1) / kChunk23;
     auto colsum_on = [&](const bf16 *x, float *part, int rows, int N, int chunk_rows, int chunks) -> cudaError_t {
         ColsumJobs cj{};
@@ -1802,14 +1813,19 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     FB_REQUIRE(a.xch == nullptr || !a.ad.on || a.grads == dist_current_grads(a.xch), "training step with an exchange: gradients must go to its current buffer");
     AdamDev ad{a.ad.on && a.xch == nullptr, const_cast<float *>(a.params), a.ad.m, a.ad.v, a.ad.beta1, a.ad.beta2, a.ad.eps, a.ad.grad_scale, t->adam_pow + 2};
     FB_CUDA_OK((launch_tc_wgrad<64, 5, kSlabW3, 1, 6>(p->a2_w, p->dz3_b, p->conv3_w, p->s3, EpiStoreF32{t->part3, 640, 64, (size_t)640 * 64}, sx)));
-    if (a.ad.on) {                                                      // on sy, early: after the fc1 weight gradient (sx) and the fc1 data gradient (the last reader of wf1n)
-        FB_CUDA_OK(cudaStreamWaitEvent(sy, t->ev[e_fc1w], 0));
-        if (a.xch != nullptr) {     // several GPUs: W_fc1's share of the gradient exchange + Adam, beside the convolution gradients
+    if (a.ad.on) {
+        // Adam on W_fc1 (91 % of the parameters) on a stream of its own, as soon as its gradient is final (fc1 weight-gradient GEMM,
+        // sx) and its bf16 / fp16 copy has been read for the last time (fc1 data-gradient GEMM): beside everything that is left of
+        // the step -- nothing downstream reads W_fc1 or its gradient again; it joins at the step's end.  On several GPUs the same
+        // slot holds W_fc1's bucket of the gradient exchange (sum over NVLink peer memory + Adam).
+        FB_CUDA_OK(cudaStreamWaitEvent(t->aux3, t->ev[e_fc1d], 0));
+        FB_CUDA_OK(cudaStreamWaitEvent(t->aux3, t->ev[e_fc1w], 0));
+        if (a.xch != nullptr) {
             rc = dist_launch_bucket(a.xch, n, 0, const_cast<float *>(a.params), a.ad.m, a.ad.v, t->adam_pow + 2, a.ad.beta1, a.ad.beta2, a.ad.eps,
-                                    a.ad.grad_scale, sy);
+                                    a.ad.grad_scale, t->aux3);
             if (rc) return rc;
         } else {
-            adam_wf1_kernel<<<4 * t->n_sms, 256, 0, sy>>>(L, a.grads, ad, t->pw[0]);
+            adam_wf1_kernel<<<4 * t->n_sms, 256, 0, t->aux3>>>(L, a.grads, ad, t->pw[0]);
             FB_CUDA_OK(cudaGetLastError());
         }
     }
@@ -1845,7 +1861,8 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
                                 a.ad.grad_scale, st);
         if (rc) return rc;
     }
-    if (a.pro.replay != nullptr && a.pro.prioritized) { rc = replay_launch_per_update(a.pro, a.abs_err, st); if (rc) return rc; }   // Memory.batch_update
+    if (a.ad.on) FB_CUDA_OK(fork(t->aux3, st));  // W_fc1's Adam / exchange bucket joins here, at the very end
+    if (per_on_side) FB_CUDA_OK(fork(t->aux3, st));          // Memory.batch_update (started right after the head) joins here
     return FB_OK;
 }
 
