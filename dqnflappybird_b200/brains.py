@@ -15,10 +15,13 @@ Same surface as the reference (BrainDQN.py:32-239): ``Brain(actionNum, gameName)
 
 Reference quirks are switchable: ``reference_quirks=True`` reproduces what the shipped code
 really executes (Q1: ``--model ddqn`` runs the Nature update; Q2: ``--model duelingdqn`` builds the plain
-head; Q3: the PER brain never syncs its target net); the default runs the intended algorithm.
+head; Q3: the PER brain never syncs its target net; and the PER cost as TensorFlow evaluates
+``ISWeights[B,1] * squared_difference[B]`` -- broadcast to [B,B], i.e. mean(w) * mean(err^2),
+BrainPrioritizedReplyDQN.py:243-251); the default runs the intended algorithm (mean of w_i * err_i^2).
 
-All math runs in libflappy_b200.so; with torch.distributed initialised the replicated learner all-reduces
-its flat gradient vector (NCCL) before the Adam step, every rank training on its own env/replay shard.
+All math runs in libflappy_b200.so; with torch.distributed initialised every rank trains on its own env /
+replay shard and the replicated learner sums the ranks' gradients inside the update's CUDA graph over NVLink
+peer memory (fb_dist.cu), or with an NCCL all-reduce before the Adam step when ``peer_exchange=False``.
 """
 from __future__ import annotations
 

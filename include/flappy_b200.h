@@ -177,16 +177,18 @@ int fb_debug_poison_packed(fb_qnet *net, int slot, void *stream);
 /* measurement hook (tools/write_bw_probe.py): n_chunks chunks of 6,400 bytes at dst + k * stride_bytes, written by one warp each
  * with 16-byte streaming stores (mode 0) or through shared memory + cp.async.bulk (mode 1); no computation */
 int fb_debug_write_probe(uint8_t *dst_dev, int n_chunks, long long stride_bytes, int mode, int ctas, void *stream);
-/* FB_PRECISION_BF16 only: replay fb_qnet_loss_backward as a CUDA graph once the same arguments were seen twice
+/* Tensor-core precisions (FB_PRECISION_BF16 / _FP16) only: replay fb_qnet_loss_backward as a CUDA graph once the same arguments were seen twice
  * (default on; the eager two-stream path is identical work). */
 int fb_qnet_use_graphs(fb_qnet *net, int enable);
-/* FB_PRECISION_BF16 only: how conv1 is run (also FB_TC_CONV1_MODE).  2 (default): the 2x2 max-pool is fused into conv1's
+/* Tensor-core precisions only: how conv1 is run (also FB_TC_CONV1_MODE).  2 (default): the 2x2 max-pool is fused into conv1's
  * epilogue, and when no backward pass follows (acting, Q(s')) its input tile is built in the kernel straight from the u8
  * frames -- neither the bf16 input matrix nor the conv1 activations go through HBM; 1: pooled epilogue, input always via the
  * materialised matrix; 0: three separate kernels (conversion, conv1, pooling).  Results are bit-identical in all modes. */
 int fb_qnet_set_conv1_mode(fb_qnet *net, int mode);
-/* FB_PRECISION_BF16 only: 1 (default, also FB_TC_FUSE_BWD): the conv3 data gradient, its ReLU mask, the conv2 data gradient and the
- * un-pool run as ONE kernel whose intermediate never leaves the SM; 0: three kernels.  Results are bit-identical. */
+/* Tensor-core precisions only.  Which fused kernels the update uses at minibatch <= 512 (also FB_TC_FUSE_FWD / FB_TC_FUSE_BWD):
+ * 0: none (conv2, conv3, conv3 data gradient, conv2 data gradient, un-pool are separate kernels); 2: the forward pair only
+ * (conv2 + conv3 as one kernel); 1 or 3 (default): forward pair and backward triple (conv3 data gradient, its ReLU mask, conv2
+ * data gradient and the un-pool as ONE kernel whose intermediate never leaves the SM).  Results are bit-identical. */
 int fb_qnet_set_fused_backward(fb_qnet *net, int on);
 int fb_qnet_param_count(const fb_qnet *net);
 int fb_qnet_layout(const fb_qnet *net, int32_t *out16_host);

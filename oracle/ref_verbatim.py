@@ -132,7 +132,10 @@ def load_per_classes(dst: str = DST):
     """SumTree and Memory of BrainPrioritizedReplyDQN.py:32-151, executed verbatim (the module's top imports TensorFlow)"""
     import numpy as np
     src = open(os.path.join(dst, "BrainPrioritizedReplyDQN.py")).read()
-    tree = ast.parse(src)
+    import warnings
+    with warnings.catch_warnings():          # the reference's docstrings hold '\\ ' escapes: its text, not ours to edit
+        warnings.simplefilter("ignore", SyntaxWarning)
+        tree = ast.parse(src)
     ns = {"np": np}
     for node in tree.body:
         if isinstance(node, ast.ClassDef) and node.name in ("SumTree", "Memory"):
