@@ -154,6 +154,8 @@ _SIGNATURES = {
     "fb_per_update": ([_vp, _i32p, _f32p, _vp, C.c_int, C.c_int, _vp], C.c_int),
     "fb_per_tree_copy": ([_vp, _vp, C.c_int, _vp], C.c_int),
     "fb_per_aux_tree_copy": ([_vp, C.c_int, _vp, C.c_int, _vp], C.c_int),
+    "fb_per_min_root": ([_vp, _vp, _vp], C.c_int),
+    "fb_per_set_global_min": ([_vp, _vp], C.c_int),
     "fb_replay_rng_pos": ([_vp, _vp, C.c_int, _vp], C.c_int),
     "fb_debug_assets_load_host": ([C.c_char_p, C.c_size_t], C.c_int),
     "fb_debug_host_reset": ([_i32p, _u8p, C.c_int, C.c_uint64, C.c_uint64], C.c_int),

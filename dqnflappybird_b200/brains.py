@@ -108,6 +108,8 @@ class BrainDQN:
             peer_exchange = self.world > 1 and torch.distributed.get_backend() == "nccl"
         if peer_exchange and self.world > 1:
             self.net.enable_peer_exchange()
+        if self.prioritized and self.world > 1:
+            self.replayMemory.use_global_min()     # min_prob of Memory.sample over every shard's leaves (one scalar, MIN all-reduce)
         self._k = 0                               # time index of the newest frame in the ring
         self._rng_pos = torch.zeros(N, dtype=torch.int32, device=self.device)
         self._actions = torch.zeros(N, dtype=torch.uint8, device=self.device)
@@ -239,7 +241,7 @@ class BrainDQN:
     def _update(self, variant: str):
         mem = self.replayMemory
         sampling = None
-        if self.fuse_sampling and (self.world == 1 or not self.prioritized):
+        if self.fuse_sampling and (self.world == 1 or not self.prioritized or self.net.exchange_in_step):
             sampling, mb = mem.step_sampling(self.local_batch)    # random.sample + gather ride at the head of the step's graph
         else:
             mb = mem.sample(self.local_batch)

@@ -772,8 +772,11 @@ __global__ void __launch_bounds__(128) fc1_head_train_kernel(const float *__rest
 }
 
 // split-K partials, bias partials and head partials -> the flat gradient vector in TF variable order (HWIO).  One CTA
-// sums 32 consecutive gradient elements: lane = element (coalesced across the partial buffers), the 8 warps take every
-// 8th term, and the 8 sub-sums are added in a fixed order (deterministic for a given batch size).
+// sums 32 consecutive gradient elements: lane = element (coalesced across the partial buffers), the kFinWarps warps take every
+// kFinWarps-th term, and the sub-sums are added in a fixed order (deterministic for a given batch size).  Two warps of 32
+// loads in flight each: the whole grid (2,486 CTAs at hidden 512) is resident at once, so the kernel costs one CTA's chain of
+// round trips (partials -> Adam state -> stores), not two waves of it -- it is the last stage of every update.
+constexpr int kFinWarps = 2, kFinInflight = 32;
 struct FinalizeArgs {
     const float *part1, *part2, *part3;             // [splits][rows][N]
     int s1, s2, s3;                                  // number of splits (fc1's weight gradient is written in place)
@@ -812,49 +815,60 @@ __global__ void __launch_bounds__(256) adam_wf1_kernel(QnetLayout L, const float
         *reinterpret_cast<uint2 *>(pw.wf1n + 4 * i4) = make_uint2(pk[0], pk[1]);
     }
 }
-__global__ void __launch_bounds__(256) finalize_grads_kernel(const FinalizeArgs a, QnetLayout L, float *__restrict__ grads, const AdamDev ad,
-                                                            const PackedWeights pw) {
+__global__ void __launch_bounds__(32 * kFinWarps) finalize_grads_kernel(const FinalizeArgs a, QnetLayout L, float *__restrict__ grads, const AdamDev ad,
+                                                                       const PackedWeights pw) {
     tc::pdl_wait();
     if (!ad.on) tc::pdl_launch();
-    __shared__ float red[8][32];
+    __shared__ float red[kFinWarps][32];
     const float alpha = ad.on ? *ad.alpha : 0.f;
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5, H = L.hidden;
     const int k = blockIdx.x * 32 + lane;            // compact index: [0, wf1) then [bf1, total)
     const int n_compact = L.wf1 + (L.total - L.bf1);
     const int i = k < L.wf1 ? k : k - L.wf1 + L.bf1;
     float s = 0.f;
+    // terms z = g, g + kFinWarps, ... of one element, added in that order; kFinInflight loads are issued before the first add
+    // (the sums over 49 .. 147 split-K partials were a chain of dependent L2 round trips)
+    auto strided_sum = [&](int count, auto &&term) {
+        for (int z = g; z < count; z += kFinWarps * kFinInflight) {
+            float v[kFinInflight];
+#pragma unroll
+            for (int u = 0; u < kFinInflight; u++) v[u] = z + kFinWarps * u < count ? term(z + kFinWarps * u) : 0.f;
+#pragma unroll
+            for (int u = 0; u < kFinInflight; u++) if (z + kFinWarps * u < count) s += v[u];
+        }
+    };
     if (k < n_compact) {
         if (i < L.b1) {                     // W1 [kh][kw][c][n]
             int e = i - L.w1, n = e & 31, c = (e >> 5) & 3, kw = (e >> 7) & 7, kh = e >> 10;
             int row = ((kh >> 2) * 2 + (kw >> 2)) * 64 + (kh & 3) * 16 + (kw & 3) * 4 + c;
-            for (int z = g; z < a.s1; z += 8) s += a.part1[((size_t)z * 256 + row) * 32 + n];
+            strided_sum(a.s1, [&](int z) { return a.part1[((size_t)z * 256 + row) * 32 + n]; });
         } else if (i < L.w2) {
             int n = i - L.b1;
-            for (int z = g; z < a.c1; z += 8) s += a.bp1[z * 32 + n];
+            strided_sum(a.c1, [&](int z) { return a.bp1[z * 32 + n]; });
         } else if (i < L.b2) {              // W2 [kh][kw][c][n]
             int e = i - L.w2, n = e & 63, c = (e >> 6) & 31, kw = (e >> 11) & 3, kh = e >> 13;
             int row = ((kh >> 1) * 2 + (kw >> 1)) * 128 + (kh & 1) * 64 + (kw & 1) * 32 + c;
-            for (int z = g; z < a.s2; z += 8) s += a.part2[((size_t)z * 512 + row) * 64 + n];
+            strided_sum(a.s2, [&](int z) { return a.part2[((size_t)z * 512 + row) * 64 + n]; });
         } else if (i < L.w3) {
             int n = i - L.b2;
-            for (int z = g; z < a.c2; z += 8) s += a.bp2[z * 64 + n];
+            strided_sum(a.c2, [&](int z) { return a.bp2[z * 64 + n]; });
         } else if (i < L.b3) {              // W3 [k][n], k natural
             int e = i - L.w3;
-            for (int z = g; z < a.s3; z += 8) s += a.part3[(size_t)z * 640 * 64 + e];
+            strided_sum(a.s3, [&](int z) { return a.part3[(size_t)z * 640 * 64 + e]; });
         } else if (i < L.wf1) {
             int n = i - L.b3;
-            for (int z = g; z < a.c3; z += 8) s += a.bp3[z * 64 + n];
+            strided_sum(a.c3, [&](int z) { return a.bp3[z * 64 + n]; });
         } else if (i < L.bf1 + H) {         // fc1 bias
             int j = i - L.bf1;
-            for (int z = g; z < a.G; z += 8) s += a.hp[((size_t)z * H + j) * 4 + 3];
+            strided_sum(a.G, [&](int z) { return a.hp[((size_t)z * H + j) * 4 + 3]; });
         } else if (!L.dueling) {
-            if (i < L.bf2) { int e = i - L.wf2; for (int z = g; z < a.G; z += 8) s += a.hp[((size_t)z * H + (e >> 1)) * 4 + (e & 1)]; }
-            else { int e = i - L.bf2; for (int z = g; z < a.G; z += 8) s += a.hb[z * 4 + e]; }
+            if (i < L.bf2) { int e = i - L.wf2; strided_sum(a.G, [&](int z) { return a.hp[((size_t)z * H + (e >> 1)) * 4 + (e & 1)]; }); }
+            else { int e = i - L.bf2; strided_sum(a.G, [&](int z) { return a.hb[z * 4 + e]; }); }
         } else {
-            if (i < L.bv) { int j = i - L.wv; for (int z = g; z < a.G; z += 8) s += a.hp[((size_t)z * H + j) * 4 + 2]; }
-            else if (i < L.wa) { for (int z = g; z < a.G; z += 8) s += a.hb[z * 4] + a.hb[z * 4 + 1]; }
-            else if (i < L.ba) { int e = i - L.wa; for (int z = g; z < a.G; z += 8) s += a.hp[((size_t)z * H + (e >> 1)) * 4 + (e & 1)]; }
-            else { int e = i - L.ba; for (int z = g; z < a.G; z += 8) s += (e == 0 ? 0.5f : -0.5f) * (a.hb[z * 4] - a.hb[z * 4 + 1]); }
+            if (i < L.bv) { int j = i - L.wv; strided_sum(a.G, [&](int z) { return a.hp[((size_t)z * H + j) * 4 + 2]; }); }
+            else if (i < L.wa) { strided_sum(a.G, [&](int z) { return a.hb[z * 4] + a.hb[z * 4 + 1]; }); }
+            else if (i < L.ba) { int e = i - L.wa; strided_sum(a.G, [&](int z) { return a.hp[((size_t)z * H + (e >> 1)) * 4 + (e & 1)]; }); }
+            else { int e = i - L.ba; strided_sum(a.G, [&](int z) { return (e == 0 ? 0.5f : -0.5f) * (a.hb[z * 4] - a.hb[z * 4 + 1]); }); }
         }
     }
     red[g][lane] = s;
@@ -862,7 +876,7 @@ __global__ void __launch_bounds__(256) finalize_grads_kernel(const FinalizeArgs 
     if (g == 0 && k < n_compact) {
         float t = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; w++) t += red[w][lane];
+        for (int w = 0; w < kFinWarps; w++) t += red[w][lane];
         if (i < L.bf1 + H) t *= a.inv_scale;         // conv / fc1 weights and biases: sums of scaled gradient tensors (the head's are not)
         grads[i] = t;
         if (ad.on) adam_one(i, t, ad.p, ad.m, ad.v, alpha, ad.beta1, ad.beta2, ad.eps, ad.grad_scale, L, pw);
@@ -1394,6 +1408,10 @@ struct TcState {
     int use_graph;
     int f16;                    // operand format of every 16-bit tensor of this net: 0 bf16, 1 fp16 (FB_PRECISION_FP16)
     int fuse_fwd;               // 1 (default): conv2 + conv3 forward as one kernel (also FB_TC_FUSE_FWD)
+    int nopdl;                  // mask (FB_TC_NOPDL) of update kernels launched WITHOUT the early (programmatic) launch.  Default 1: the conv1
+                                // weight gradient -- launched early, its 147 CTAs sat on SMs waiting for the fused data-gradient kernel while
+                                // the conv3 weight gradient, which was ready, queued behind them (121 -> 114.5 us per update, measured).
+                                // 2: fused backward, 4 / 8: conv3 / conv2 weight gradient, 16: finalize -- all measured slower or equal
     int fuse_bwd;               // 1 (default): conv3 / conv2 data gradients and the un-pool as one kernel (also FB_TC_FUSE_BWD)
     int conv1_mode;             // 2 (default): pooled epilogue, slab from u8 when no backward follows; 1: slab always from X2;
                                 // 0: separate pack_x2 / conv1 / pool_pack kernels
@@ -1477,7 +1495,10 @@ int make_plan(fb_qnet *n, int B, TcPlan **out) {
     p.conv1_w.p_total = (int)P1; p.conv1_w.slab_row0 = 0;
     // split-K: about 24 (conv1) / 4 (conv2, conv3) K-blocks of 64 positions per CTA, one wave of CTAs at most
     auto splits_for = [](long long P, int kb_per_cta) { long long s = (P / 64 + kb_per_cta - 1) / kb_per_cta; return (int)(s < 1 ? 1 : s > 148 ? 148 : s); };
-    p.s1 = plan_splits(P1, splits_for(P1, 8), &p.conv1_w.klen);            // at minibatch sizes: every SM takes <= 12 K-blocks
+    // conv1: <= 24 K-blocks per CTA once that still gives 64 CTAs (74 at minibatch 256: it runs beside the conv2 / conv3 weight
+    // gradients, 49 CTAs each, and every one of these CTAs owns an SM -- 147 + 49 + 49 queued for 148), else <= 8 per CTA
+    { int s24 = splits_for(P1, 24), s8 = splits_for(P1, 8);
+      p.s1 = plan_splits(P1, s24 >= 64 ? s24 : (s8 < 64 ? s8 : 64), &p.conv1_w.klen); }
     p.conv1_w.acc_rowoff[0] = 0; p.conv1_w.acc_lbo[0] = 128; p.conv1_w.acc_rowoff[1] = kG1; p.conv1_w.acc_lbo[1] = 128;
     p.conv2_w.p_total = (int)P2; p.conv2_w.slab_row0 = 0;
     p.s2 = plan_splits(P2, splits_for(P2, 4), &p.conv2_w.klen);
@@ -1572,7 +1593,8 @@ int tc_state_create(fb_qnet *n) {
     t->use_graph = 1;
     { const char *e = getenv("FB_TC_FUSE_BWD"); t->fuse_bwd = (e && e[0] == '0') ? 0 : 1; }
     { const char *e = getenv("FB_TC_FUSE_FWD"); t->fuse_fwd = (e && e[0] == '0') ? 0 : 1; }
-    { const char *e = getenv("FB_TC_CONV1_MODE"); t->conv1_mode = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }
+    { const char *e = getenv("FB_TC_CONV1_MODE"); t->conv1_mode = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 2; }
+    { const char *e = getenv("FB_TC_NOPDL"); t->nopdl = e ? atoi(e) : 1; }
     n->tc = t;
     return FB_OK;
 }
@@ -1681,12 +1703,13 @@ static int tc_forward_impl(fb_qnet *n, int slot, int w, const float *params_dev,
         FB_CUDA_OK(tc::launch_pdl(pack_x2_kernel, dim3((unsigned)(((size_t)P1 * 8 + 255) / 256)), dim3(256), 0, st, fv, B, f.x2, t->f16));
         FB_CUDA_OK((launch_tc_conv<32, kSlab1, 1, 4, 6, 1>(p->x2_s[w], wm.w1p, p->conv1, t->n_sms, EpiConv1{f.z1, params_dev + L.b1, P1, t->f16}, st)));
         FB_CUDA_OK(tc::launch_pdl(pool_pack_kernel, dim3((unsigned)(((size_t)B * 36 * 16 + 255) / 256)), dim3(256), 0, st, f.z1, B, f.p2, t->f16));
-    } else if (keep || t->conv1_mode == 1) {
+    } else if ((keep && t->conv1_mode != 3) || t->conv1_mode == 1) {
         FB_CUDA_OK(tc::launch_pdl(pack_x2_kernel, dim3((unsigned)(((size_t)P1 * 8 + 255) / 256)), dim3(256), 0, st, fv, B, f.x2, t->f16));
         FB_CUDA_OK((launch_tc_conv1_fused<6, true>(p->x2_s[w], wm.w1p, Conv1FusedParams{fv, B, params_dev + L.b1, keep ? f.z1 : nullptr, f.p2, t->f16},
                                                   t->n_sms, st)));
     } else {
-        FB_CUDA_OK((launch_tc_conv1_fused<4, false>(p->x2_s[w], wm.w1p, Conv1FusedParams{fv, B, params_dev + L.b1, nullptr, f.p2, t->f16}, t->n_sms, st)));
+        // (mode 3 with keep: Z1 is written here too; X2, which only the conv1 weight gradient reads, is packed off the critical path)
+        FB_CUDA_OK((launch_tc_conv1_fused<4, false>(p->x2_s[w], wm.w1p, Conv1FusedParams{fv, B, params_dev + L.b1, keep ? f.z1 : nullptr, f.p2, t->f16}, t->n_sms, st)));
     }
     if (t->fuse_fwd && B <= kFuseMaxBatch) {
         FB_CUDA_OK((launch_tc_fwd23<2>(p->p2_s[w], wm.w2p, wm.w3p, Fwd23Params{(B + 1) / 2, B, params_dev + L.b2, params_dev + L.b3, keep ? f.a2 : nullptr, f.a3, t->f16},
@@ -1768,6 +1791,11 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     // ---- main: Q(s) with the online net; its activations stay in workspace 0 for the backward pass
     // the TD target, loss and dLoss/dQ come out of its head kernel, which first waits for Q(s') from the other stream
     FB_CUDA_OK(cudaEventRecord(t->ev[e], sx));
+    const int e_x2 = 13;
+    if (t->conv1_mode == 3) {                  // X2 of s for the conv1 weight gradient: behind Q(s') on the side stream
+        FB_CUDA_OK(tc::launch_pdl(pack_x2_kernel, dim3((unsigned)(((size_t)P1 * 8 + 255) / 256)), dim3(256), 0, sx, a.fs, B, f.x2, t->f16));
+        FB_CUDA_OK(cudaEventRecord(t->ev[e_x2], sx));
+    }
     TdFuse td{1, a.variant, a.loss_sum, a.global_batch, n->per_broadcast, a.gamma, n->q_next, n->q_next_online, a.rewards, a.isw, a.actions,
               a.terminals, n->dq, a.abs_err, a.q_target, t->loss_terms};
     const AdamPow apow{a.ad.on, t->adam_pow, t->adam_pow + 2, a.ad.lr, a.ad.beta1, a.ad.beta2};
@@ -1812,6 +1840,7 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     FB_CUDA_OK(colsum_on(t->dz3, t->bp3, P2, 64, kChunk23, c23));
     FB_REQUIRE(a.xch == nullptr || !a.ad.on || a.grads == dist_current_grads(a.xch), "training step with an exchange: gradients must go to its current buffer");
     AdamDev ad{a.ad.on && a.xch == nullptr, const_cast<float *>(a.params), a.ad.m, a.ad.v, a.ad.beta1, a.ad.beta2, a.ad.eps, a.ad.grad_scale, t->adam_pow + 2};
+    tc::pdl_next_launch_plain(t->nopdl & 4);
     FB_CUDA_OK((launch_tc_wgrad<64, 5, kSlabW3, 1, 6>(p->a2_w, p->dz3_b, p->conv3_w, p->s3, EpiStoreF32{t->part3, 640, 64, (size_t)640 * 64}, sx)));
     if (a.ad.on) {
         // Adam on W_fc1 (91 % of the parameters) on a stream of its own, as soon as its gradient is final (fc1 weight-gradient GEMM,
@@ -1831,11 +1860,13 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     }
     if (t->fuse_bwd && B <= kFuseMaxBatch) {
         // conv3 data gradient + ReLU mask + conv2 data gradient + un-pool in one kernel (tc_bwd23_kernel)
+        tc::pdl_next_launch_plain(t->nopdl & 2);
         FB_CUDA_OK((launch_tc_bwd23<2>(p->dz3_s, wm.w3d, wm.w2d, Bwd23Params{(B + 1) / 2, B, f.a2, t->dz2, f.z1, t->dz1, t->f16}, t->n_sms, st)));
         FB_CUDA_OK(fork(st, sx));
         FB_CUDA_OK(cudaStreamWaitEvent(sy, t->ev[e - 1], 0));          // sx, sy: dz2 and dz1 complete
         FB_CUDA_OK(colsum_on(t->dz1, t->bp1, P1, 32, kChunk1, c1));
         FB_CUDA_OK(colsum_on(t->dz2, t->bp2, P2, 64, kChunk23, c23));
+        tc::pdl_next_launch_plain(t->nopdl & 8);
         FB_CUDA_OK((launch_tc_wgrad<64, 4, kSlabW2, 2, 4>(p->p2_w, p->dz2_b, p->conv2_w, p->s2, EpiStoreF32{t->part2, 512, 64, (size_t)512 * 64}, sx)));
     } else {
         FB_CUDA_OK((launch_tc_conv<64, kSlab3, 1, 9, 4, 1>(p->dz3_s, wm.w3d, p->conv3_d, t->n_sms, EpiConv3Dgrad{t->dz2, f.a2, P2, t->f16}, st)));
@@ -1849,13 +1880,16 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
         FB_CUDA_OK(colsum_on(t->dz1, t->bp1, P1, 32, kChunk1, c1));
     }
     // conv1 weight gradient (no input gradient there); the bias gradients = column sums of the dZ tensors ran beside it
+    if (t->conv1_mode == 3) FB_CUDA_OK(cudaStreamWaitEvent(st, t->ev[e_x2], 0));
+    tc::pdl_next_launch_plain(t->nopdl & 1);
     FB_CUDA_OK((launch_tc_wgrad<32, 2, kSlabW1, 1, 6>(p->x2_w, p->dz1_b, p->conv1_w, p->s1, EpiStoreF32{t->part1, 256, 32, (size_t)256 * 32}, st)));
     FB_CUDA_OK(fork(sx, st));
     FB_CUDA_OK(fork(sy, st));
     FinalizeArgs fa{t->part1, t->part2, t->part3, p->s1, p->s2, p->s3, t->bp1, t->bp2, t->bp3, c1, c23, c23, t->hp, t->hb, G, a.loss_out, 1.f / gscale};
     const int n_compact = L.wf1 + (L.total - L.bf1);
     const int nb_fin = (n_compact + 31) / 32;
-    FB_CUDA_OK(tc::launch_pdl(finalize_grads_kernel, dim3(nb_fin), dim3(256), 0, st, fa, L, a.grads, ad, t->pw[0]));
+    tc::pdl_next_launch_plain(t->nopdl & 16);
+    FB_CUDA_OK(tc::launch_pdl(finalize_grads_kernel, dim3(nb_fin), dim3(32 * kFinWarps), 0, st, fa, L, a.grads, ad, t->pw[0]));
     if (a.ad.on && a.xch != nullptr) {          // the rest of the vector (79,522 parameters): the only exchange left at the tail
         rc = dist_launch_bucket(a.xch, n, 1, const_cast<float *>(a.params), a.ad.m, a.ad.v, t->adam_pow + 2, a.ad.beta1, a.ad.beta2, a.ad.eps,
                                 a.ad.grad_scale, st);
@@ -1890,7 +1924,7 @@ int tc_drop_graphs(fb_qnet *n) {
 }
 
 extern "C" int fb_qnet_set_conv1_mode(fb_qnet *n, int mode) {
-    FB_REQUIRE(n != nullptr && n->tc != nullptr && mode >= 0 && mode <= 2, "fb_qnet_set_conv1_mode: needs FB_PRECISION_BF16 and mode 0..2");
+    FB_REQUIRE(n != nullptr && n->tc != nullptr && mode >= 0 && mode <= 3, "fb_qnet_set_conv1_mode: needs a tensor-core precision and mode 0..3");
     n->tc->conv1_mode = mode;
     for (auto &g : n->tc->graphs) destroy_entry(g);
     n->tc->graphs.clear();

@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(256) per_store_multi_kernel(double *tree, doub
 // subtractions are the reference's, in the reference's order, only the loads are batched: 2 round trips instead of 10 at
 // 983,040 leaves.  min_prob comes from the root of the min tree.  The CTA that finishes last advances the stream position.
 constexpr int kSampleWarps = 8;
-__global__ void __launch_bounds__(32 * kSampleWarps) per_sample_kernel(const double *tree, const double *mn, int cap, int batch, double beta,
+__global__ void __launch_bounds__(32 * kSampleWarps) per_sample_kernel(const double *tree, const double *min_p_src, int cap, int batch, double beta,
                                                                        uint64_t seed, unsigned long long *word_pos, unsigned int *done_counter, int32_t *tree_idx,
                                                                        int32_t *data_idx, double *isw, double *prio_out, float *isw_f32) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(32 * kSampleWarps) per_sample_kernel(const dou
         }
         if (lane == 0) {
             const double p = tree[parent];
-            const double min_p = mn[0];
+            const double min_p = *min_p_src;               // root of this shard's min tree, or the min over all shards (fb_per_set_global_min)
             const double prob = p / total, min_prob = min_p / total;
             tree_idx[i] = parent;
             data_idx[i] = parent - (cap - 1);
@@ -424,6 +424,7 @@ struct fb_replay {
     int N, L, C, cap;
     double *tree;                    // PER only
     double *mn, *mx;                 // min-positive / max trees of the same shape (see the SumTree section)
+    const double *gmin;              // nullptr, or the caller's device scalar: smallest positive leaf over ALL shards (several GPUs)
     unsigned int *counters;          // [0] per_store_multi_kernel, [1] per_sample_kernel: "last CTA" counters, self-resetting
     int32_t *leaves; double *prio; double *change;   // scratch, max(N, max_batch)
     unsigned long long *word_pos;    // [0] uniform stream, [1] PER stream (64-bit word positions)
@@ -440,7 +441,7 @@ extern "C" int fb_replay_create(int n_envs, int ring_len, int capacity_per_env, 
     r->scratch_n = n_envs > max_batch ? n_envs : max_batch;
     FB_CUDA_OK(cudaMalloc(&r->word_pos, 2 * sizeof(unsigned long long)));
     FB_CUDA_OK(cudaMemset(r->word_pos, 0, 2 * sizeof(unsigned long long)));
-    r->mn = r->mx = nullptr;
+    r->mn = r->mx = nullptr; r->gmin = nullptr;
     FB_CUDA_OK(cudaMalloc(&r->counters, 2 * sizeof(unsigned int)));
     FB_CUDA_OK(cudaMemset(r->counters, 0, 2 * sizeof(unsigned int)));
     FB_CUDA_OK(cudaMalloc(&r->leaves, sizeof(int32_t) * r->scratch_n));
@@ -497,7 +498,7 @@ extern "C" int fb_replay_gather(fb_replay *r, const uint8_t *ring_dev, const uin
 
 static void launch_per_sample(fb_replay *r, int batch, double beta, uint64_t seed, int32_t *tree_idx, int32_t *data_idx, double *isw, double *prio,
                               float *isw32, cudaStream_t st) {
-    per_sample_kernel<<<(batch + kSampleWarps - 1) / kSampleWarps, 32 * kSampleWarps, 0, st>>>(r->tree, r->mn, r->cap, batch, beta, seed, r->word_pos + 1,
+    per_sample_kernel<<<(batch + kSampleWarps - 1) / kSampleWarps, 32 * kSampleWarps, 0, st>>>(r->tree, r->gmin ? r->gmin : r->mn, r->cap, batch, beta, seed, r->word_pos + 1,
                                                                                                r->counters + 1, tree_idx, data_idx, isw, prio, isw32);
 }
 
@@ -545,7 +546,7 @@ int replay_patch_nodes(cudaGraphExec_t exec, cudaGraphNode_t sampler, cudaGraphN
     cudaKernelNodeParams kp{};
     int batch = p.batch; uint64_t seed = p.seed; int32_t *idx = p.idx_out_dev;
     if (p.prioritized) {
-        const double *tree = r->tree, *mn = r->mn; int cap = r->cap; double beta = p.beta; unsigned long long *word_pos = r->word_pos + 1;
+        const double *tree = r->tree, *mn = r->gmin ? r->gmin : r->mn; int cap = r->cap; double beta = p.beta; unsigned long long *word_pos = r->word_pos + 1;
         unsigned int *done = r->counters + 1;
         int32_t *tree_idx = p.tree_idx_out_dev; double *isw = p.is_weights_out_dev, *prio = p.prio_out_dev; float *isw32 = p.is_weights_f32_out_dev;
         void *sargs[] = {&tree, &mn, &cap, &batch, &beta, &seed, &word_pos, &done, &tree_idx, &idx, &isw, &prio, &isw32};
@@ -616,6 +617,22 @@ extern "C" int fb_per_tree_copy(fb_replay *r, double *out_dev, int n_nodes, void
 extern "C" int fb_per_aux_tree_copy(fb_replay *r, int which, double *out_dev, int n_nodes, void *stream) {
     FB_REQUIRE(r && r->tree && out_dev && n_nodes == 2 * r->cap - 1 && (which == 1 || which == 2), "fb_per_aux_tree_copy: bad argument");
     FB_CUDA_OK(cudaMemcpyAsync(out_dev, which == 1 ? r->mn : r->mx, sizeof(double) * (size_t)n_nodes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return FB_OK;
+}
+
+// Several GPUs: Memory.sample's min_prob is a property of the WHOLE memory (BrainPrioritizedReplyDQN.py:131 takes the min over every
+// leaf), and ISWeights = (p_i / min_p)^-beta does not depend on total_p, so one scalar makes the shards' weights those of one
+// global memory.  fb_per_min_root copies this shard's min (the root of its min tree; +inf if it holds no positive leaf) to a
+// caller-owned device scalar; the caller reduces it over the ranks (MIN) and hands the result to fb_per_set_global_min, whose
+// pointer every later sample reads instead of the local root (nullptr: back to the local root).
+extern "C" int fb_per_min_root(fb_replay *r, double *out_dev, void *stream) {
+    FB_REQUIRE(r && r->tree && out_dev, "fb_per_min_root: bad argument");
+    FB_CUDA_OK(cudaMemcpyAsync(out_dev, r->mn, sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return FB_OK;
+}
+extern "C" int fb_per_set_global_min(fb_replay *r, const double *global_min_dev) {
+    FB_REQUIRE(r && r->tree, "fb_per_set_global_min: bad argument");
+    r->gmin = global_min_dev;
     return FB_OK;
 }
 

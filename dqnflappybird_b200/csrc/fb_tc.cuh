@@ -199,14 +199,19 @@ __device__ __forceinline__ float round1(float a, int f16) {           // the val
     return __bfloat162float(__float2bfloat16(a));
 }
 
-// host: launch with programmatic stream serialization allowed (see pdl_wait)
+// host: launch with programmatic stream serialization allowed (see pdl_wait).  An early-launched CTA that asked for an SM's
+// whole shared memory holds that SM while it waits in griddepcontrol.wait: where independent kernels of other streams could
+// have used it, the caller switches the early launch off for that one kernel (pdl_next_launch_plain).
+inline int &pdl_plain_flag() { static thread_local int f = 0; return f; }
+inline void pdl_next_launch_plain(bool plain) { pdl_plain_flag() = plain ? 1 : 0; }
 template <class... KArgs, class... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const Args &...args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_plain_flag() ? 0 : 1;
+    pdl_plain_flag() = 0;
     cfg.attrs = at; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }

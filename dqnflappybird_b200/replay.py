@@ -145,6 +145,24 @@ class PrioritizedMemory(ReplayMemory):
         self._isw = torch.empty(max_batch, dtype=torch.float64, device=dev)
         self._isw32 = torch.empty(max_batch, dtype=torch.float32, device=dev)     # what the tf.float32 placeholder receives (:243)
         self._prio = torch.empty(max_batch, dtype=torch.float64, device=dev)
+        self._gmin = None
+
+    def use_global_min(self, on: bool = True):
+        """Several ranks, one memory sharded over them: ``min_prob`` of Memory.sample (:131) is the minimum over EVERY leaf, so the
+        shards agree on it with one MIN all-reduce of a scalar before each sample (ISWeights = (p_i / min_p)^-beta needs nothing
+        else that is global).  Needs an initialised process group; off: each shard normalises by its own minimum."""
+        if on:
+            if self._gmin is None:
+                self._gmin = torch.empty(1, dtype=torch.float64, device=self.device)
+            _lib.check(self._L.fb_per_set_global_min(self._h, self._gmin.data_ptr()), "fb_per_set_global_min")
+        else:
+            _lib.check(self._L.fb_per_set_global_min(self._h, None), "fb_per_set_global_min")
+            self._gmin = None
+
+    def _reduce_min(self):
+        if self._gmin is not None:
+            _lib.check(self._L.fb_per_min_root(self._h, self._gmin.data_ptr(), self._stream()), "fb_per_min_root")
+            torch.distributed.all_reduce(self._gmin, op=torch.distributed.ReduceOp.MIN)
 
     def appended(self, k: int):
         """Memory.store(transition) for step k of every env (:121-125): new leaves get the max priority"""
@@ -154,6 +172,7 @@ class PrioritizedMemory(ReplayMemory):
     def sample(self, batch: int) -> Minibatch:
         """Memory.sample(n) (:127-144) -> tree_idx, minibatch, ISWeights"""
         self.beta = min(1.0, self.beta + self.beta_increment_per_sampling)
+        self._reduce_min()
         _lib.check(self._L.fb_per_sample(self._h, batch, self.beta, self.seed, self._tree_idx.data_ptr(), self._idx.data_ptr(),
                                          self._isw.data_ptr(), self._prio.data_ptr(), self._isw32.data_ptr(), self._stream()),
                    "fb_per_sample")
@@ -167,6 +186,7 @@ class PrioritizedMemory(ReplayMemory):
         """``sample(batch)`` (and the ``batch_update`` that follows the update) as a descriptor: Memory.sample rides at the head
         of ``QNetwork.train_step(..., sampling=...)``'s graph, Memory.batch_update at its tail"""
         self.beta = min(1.0, self.beta + self.beta_increment_per_sampling)
+        self._reduce_min()                       # enqueued ahead of the step's graph on the same stream
         sp = _lib.StepSampling(self._h.value, self.ring.data_ptr(), self.act.data_ptr(), self.rew.data_ptr(), self.term.data_ptr(), self.t,
                                batch, 0, self.seed, self._idx.data_ptr(), self._frames.data_ptr(), self._a.data_ptr(),
                                self._r.data_ptr(), self._t.data_ptr(), self._env.data_ptr(), self._k.data_ptr(),

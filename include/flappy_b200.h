@@ -310,6 +310,12 @@ int fb_per_update(fb_replay *r, const int32_t *tree_idx_dev, const float *abs_er
 int fb_per_tree_copy(fb_replay *r, double *out_dev, int n_nodes, void *stream);
 /* test hook: the min-positive-leaf tree (which = 1) or the max-leaf tree (2) kept beside the SumTree, same shape */
 int fb_per_aux_tree_copy(fb_replay *r, int which, double *out_dev, int n_nodes, void *stream);
+/* Several GPUs, one memory sharded over the ranks: Memory.sample's min_prob (BrainPrioritizedReplyDQN.py:131, the min over every leaf)
+ * is global, and ISWeights = (p_i / min_p)^-beta needs nothing else that is.  fb_per_min_root: this shard's smallest positive leaf
+ * (+inf if none) into a device scalar; reduce it over the ranks (MIN) and register the scalar with fb_per_set_global_min: every
+ * later fb_per_sample / sampled training step reads it instead of the local root (NULL: local again). */
+int fb_per_min_root(fb_replay *r, double *out_dev, void *stream);
+int fb_per_set_global_min(fb_replay *r, const double *global_min_dev);
 int fb_replay_rng_pos(fb_replay *r, uint64_t *pos_host2, int set, void *stream);
 
 /* The minibatch of fb_qnet_train_step drawn INSIDE the step: random.sample + the list comprehensions of BrainDQN.py:197-201

@@ -9,7 +9,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 from dqnflappybird_b200 import dist as fdist, qnet  # noqa: E402
-from dqnflappybird_b200.brains import BrainDQNNature  # noqa: E402
+from dqnflappybird_b200.brains import BrainDQNNature, BrainPrioritizedReplyDQN  # noqa: E402
 from dqnflappybird_b200.game import GameState  # noqa: E402
 
 
@@ -91,6 +91,44 @@ def main():
     dist.all_gather(ps, brain.net.params)
     assert all(torch.equal(ps[0], e) for e in ps), "replicated learners diverged"
     assert torch.isfinite(brain.net.params).all()
+
+    # ---- prioritized replay sharded over the ranks: Memory.sample's min_prob is the minimum over EVERY shard's leaves (one MIN
+    # all-reduce of a scalar), so ISWeights are those of one global memory: (p_i / min_p_global)^-beta
+    pb = BrainPrioritizedReplyDQN(2, "bird", num_envs=N, device=dev, replay_memory_per_env=12, observe=6., batch_size=32 * world, seed=4,
+                                  first_env_id=rank * N, replace_target_iter=4)
+    mem = pb.replayMemory
+    assert mem._gmin is not None
+    gs2 = GameState(num_envs=N, device=dev, seed=6, history=16, first_env_id=rank * N, ring=pb.ring)
+    obs, *_ = gs2.frame_step(torch.zeros(N, dtype=torch.uint8, device=dev))
+    pb.setInitState(obs)
+    for _ in range(16):
+        a = pb.getAction()
+        obs, r, t, s = gs2.frame_step(a)
+        pb.setPerception(obs, a, r, t, s)
+    assert pb.net.adam_steps == 16 - 7
+    ps = [torch.empty_like(pb.net.params) for _ in range(world)]
+    dist.all_gather(ps, pb.net.params)
+    assert all(torch.equal(ps[0], e) for e in ps), "prioritized learners diverged"
+    # ranks hold different priorities by now; make the minimum live on the LAST rank only, then sample
+    cap = mem.N * mem.C
+    leaves = mem.tree()[cap - 1:]
+    local_min = leaves[leaves > 0].min()
+    mins = [torch.empty_like(local_min) for _ in range(world)]
+    dist.all_gather(mins, local_min)
+    if rank == world - 1:
+        idx = torch.tensor([cap - 1 + 5], dtype=torch.int32, device=dev)
+        mem.batch_update(idx, priorities=torch.tensor([float(min(m.item() for m in mins)) * 0.25], dtype=torch.float64, device=dev))
+    leaves = mem.tree()[cap - 1:]
+    local_min = leaves[leaves > 0].min()
+    dist.all_gather(mins, local_min)
+    gmin = min(m.item() for m in mins)
+    assert (rank == world - 1) == (local_min.item() == gmin)
+    mb = mem.sample(32)
+    p = mem.tree()[mb.tree_idx.long()]
+    want = (p / gmin) ** (-mem.beta)
+    assert torch.allclose(mb.is_weights, want, rtol=1e-12, atol=0), (mb.is_weights - want).abs().max().item()
+    if rank != world - 1:
+        assert (mb.is_weights < (p / local_min.item()) ** (-mem.beta)).all()       # the local minimum would have given larger weights
     dist.barrier()
     if rank == 0:
         print("PEER_EXCHANGE_OK", flush=True)
