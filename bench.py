@@ -41,7 +41,7 @@ def emit(line: dict):
 def recorded_traffic(envs_per_gpu: int):
     """dram read+write bytes per launch of the step kernel from the committed ncu --set full capture."""
     try:
-        with open(os.path.join(ROOT, "profiles", "ncu_env_step_kernel_summary.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_env_step_kernel_summary.json")) as f:
             d = json.load(f)
         if int(d["envs"]) == envs_per_gpu:
             return float(d["traffic_bytes_per_launch"])
@@ -376,8 +376,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                    "l2": "inputs larger than L2 (ring >> 126 MB; every frame is written once and not re-read)",
                    "parallelism": f"env-sharded x{world}, no collective"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": recorded_traffic(E), "traffic_source": "profiles/ncu_env_step_kernel_summary.json (bytes per launch)",
-                     "achieved_bytes_per_launch": BYTES_PER_FRAME * E, "peak_source": peak_src, "kernel": "env_step_kernel<128,128>",
+                     "traffic": recorded_traffic(E), "traffic_source": "profiles/r02_ncu_env_step_kernel_summary.json (dram read + write bytes per launch, ncu --set full of this round's kernel)",
+                     "achieved_bytes_per_launch": BYTES_PER_FRAME * E, "peak_source": peak_src, "kernel": "env_step_kernel",
                      "algorithmic_bytes_per_frame": BYTES_PER_FRAME},
         "cpu_baseline": cpu,
         "e2e": {"value": total_envs * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": E * 1, "d2h_bytes_per_step": E * 9,
