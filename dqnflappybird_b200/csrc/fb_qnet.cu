@@ -470,7 +470,7 @@ extern "C" int fb_qnet_layout(const fb_qnet *n, int32_t *o) {
 }
 
 static FrameView make_view(const uint8_t *frames, long long stride, const int32_t *chan_off) {
-    FrameView fv; fv.base = frames; fv.sample_stride = stride;
+    FrameView fv; fv.base = frames; fv.sample_stride = stride; fv.tab = nullptr;
     for (int c = 0; c < 4; c++) fv.chan_off[c] = chan_off[c];
     return fv;
 }
@@ -615,6 +615,15 @@ extern "C" int fb_qnet_train_step_sampled(fb_qnet *n, const fb_step_sampling *sp
         FB_REQUIRE(variant == 0 || target_params_dev != nullptr, "fb_qnet_train_step_sampled: target parameters required");
         if (global_batch <= 0) global_batch = batch;
         FrameView fs = make_view(sp->frames_out_dev, 5 * 6400, chan_off_s), fn = make_view(sp->frames_out_dev, 5 * 6400, chan_off_next);
+        // channels that are whole frames of the minibatch buffer (the usual 0..3 / 1..4): the convolutions read them in place from
+        // the ring through the offsets the sampler leaves behind; the gather into frames_out_dev runs beside the forward passes
+        bool in_place = sp->ring_dev != nullptr;
+        for (int c = 0; c < 4; c++) in_place = in_place && chan_off_s[c] % 6400 == 0 && chan_off_s[c] / 6400 <= 4 && chan_off_s[c] >= 0 &&
+                                               chan_off_next[c] % 6400 == 0 && chan_off_next[c] / 6400 <= 4 && chan_off_next[c] >= 0;
+        if (in_place) {
+            fs.base = fn.base = sp->ring_dev; fs.sample_stride = fn.sample_stride = 0; fs.tab = fn.tab = replay_frame_tab(sp->replay);
+            for (int c = 0; c < 4; c++) { fs.chan_off[c] = chan_off_s[c] / 6400; fn.chan_off[c] = chan_off_next[c] / 6400; }
+        }
         FB_REQUIRE(!sp->prioritized || abs_err_out_dev != nullptr, "fb_qnet_train_step_sampled: prioritized replay needs abs_err_out_dev");
         TcTrainArgs ta{variant, params_dev, target_params_dev, fs, fn, sp->act_out_dev, sp->rew_out_dev, sp->term_out_dev,
                        sp->prioritized ? sp->is_weights_f32_out_dev : nullptr, batch,

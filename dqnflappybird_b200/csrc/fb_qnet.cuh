@@ -42,6 +42,11 @@ struct FrameView {              // where the 4 input channels of each sample liv
     const uint8_t *base;
     long long sample_stride;    // bytes between consecutive samples
     int chan_off[4];            // byte offset of channel c (oldest frame first, newest last: BrainDQN.py:68)
+    const long long *tab;       // nullptr, or [sample][5] byte offsets from `base` (replay samples read in place from the frame ring:
+                                // the sampler wrote them); chan_off[c] is then the FRAME (0..4) channel c is, sample_stride unused
+    __host__ __device__ const uint8_t *chan(int b, int c) const {
+        return tab ? base + tab[b * 5 + chan_off[c]] : base + (size_t)b * sample_stride + chan_off[c];
+    }
 };
 
 // ---- handle shared by the strict-fp32 path (fb_qnet.cu) and the tcgen05 path (fb_qnet_tc.cu) ------------
@@ -89,10 +94,13 @@ struct TcTrainArgs {
 // fb_replay.cu: the two kernels of fb_replay_sample_uniform + fb_replay_gather on `st`; and the per-step patch of their
 // nodes in an instantiated graph (`t` is the only argument that changes)
 int replay_launch_sample_gather(const fb_step_sampling &p, cudaStream_t st);
+int replay_launch_sample(const fb_step_sampling &p, bool with_tab, cudaStream_t st);   // with_tab: ring offsets of the drawn frames -> replay_frame_tab
+int replay_launch_gather(const fb_step_sampling &p, cudaStream_t st);
+const long long *replay_frame_tab(const fb_replay *r);                                   // [batch][5] byte offsets into the frame ring
 int replay_launch_per_update(const fb_step_sampling &p, const float *abs_err_dev, cudaStream_t st);     // Memory.batch_update, prioritized only
 bool replay_is_sampler(const void *func);        // sample_uniform_kernel or per_sample_kernel
 bool replay_is_gather(const void *func);
-int replay_patch_nodes(cudaGraphExec_t exec, cudaGraphNode_t sampler, cudaGraphNode_t gather, const fb_step_sampling &p);
+int replay_patch_nodes(cudaGraphExec_t exec, cudaGraphNode_t sampler, cudaGraphNode_t gather, const fb_step_sampling &p, bool with_tab);
 inline bool tc_precision(int precision) { return precision == FB_PRECISION_BF16 || precision == FB_PRECISION_FP16; }
 // fb_dist.cu: one bucket of the exchange + Adam as a kernel on `st` (bucket 0 = W_fc1, 1 = the rest), for the exchange buffer of
 // the current parity; the buffer the step's gradients must have been written to

@@ -316,7 +316,7 @@ __global__ void pack_x2_kernel(FrameView fv, int B, bf16 *x2, int f16) {
 #pragma unroll
     for (int c = 0; c < 4; c++) {
         unsigned short two = 0;
-        if (in) two = __ldg(reinterpret_cast<const unsigned short *>(fv.base + (size_t)b * fv.sample_stride + fv.chan_off[c] + ih * 80 + iw));
+        if (in) two = __ldg(reinterpret_cast<const unsigned short *>(fv.chan(b, c) + ih * 80 + iw));
         px[0][c] = (float)(two & 255);
         px[1][c] = (float)(two >> 8);
     }
@@ -1401,6 +1401,7 @@ struct TcState {
     int n_sms;
     cudaStream_t aux;           // second stream: target forward / weight gradients run beside the critical path
     cudaStream_t aux2;          // third stream: bias column sums and the early Adam on W_fc1
+    cudaStream_t aux4;          // fifth stream: Memory.batch_update (prioritized replay) beside the whole backward pass
     cudaStream_t aux3;          // fourth stream (several GPUs): W_fc1's bucket of the gradient exchange, joined only at the step's end
     cudaStream_t cap;           // capture origin (the caller's stream may be the legacy default stream, which cannot capture)
     cudaEvent_t ev[16];
@@ -1587,6 +1588,7 @@ int tc_state_create(fb_qnet *n) {
         FB_CUDA_OK(cudaStreamCreateWithPriority(&t->aux, cudaStreamNonBlocking, lo));
         FB_CUDA_OK(cudaStreamCreateWithPriority(&t->aux2, cudaStreamNonBlocking, hi));     // short kernels finalize waits for
         FB_CUDA_OK(cudaStreamCreateWithPriority(&t->aux3, cudaStreamNonBlocking, hi));
+        FB_CUDA_OK(cudaStreamCreateWithPriority(&t->aux4, cudaStreamNonBlocking, lo));
         FB_CUDA_OK(cudaStreamCreateWithPriority(&t->cap, cudaStreamNonBlocking, hi));
     }
     for (auto &e : t->ev) FB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1621,6 +1623,7 @@ void tc_state_destroy(fb_qnet *n) {
     if (t->aux) cudaStreamDestroy(t->aux);
     if (t->aux2) cudaStreamDestroy(t->aux2);
     if (t->aux3) cudaStreamDestroy(t->aux3);
+    if (t->aux4) cudaStreamDestroy(t->aux4);
     if (t->cap) cudaStreamDestroy(t->cap);
     delete t;
     n->tc = nullptr;
@@ -1748,7 +1751,7 @@ int tc_forward_chunks(fb_qnet *n, int slot, const float *params_dev, const uint8
     for (int b0 = 0; b0 < batch; b0 += n->max_batch, c++) {
         const int B = min(n->max_batch, batch - b0), w = two ? (c & 1) : 0;
         FrameView fv;
-        fv.base = frames_dev + (size_t)b0 * sample_stride; fv.sample_stride = sample_stride;
+        fv.base = frames_dev + (size_t)b0 * sample_stride; fv.sample_stride = sample_stride; fv.tab = nullptr;
         for (int k = 0; k < 4; k++) fv.chan_off[k] = chan_off[k];
         int rc = tc_forward(n, slot, w, params_dev, fv, B, q_out_dev + (size_t)b0 * 2, w ? t->aux : st);
         if (rc) return rc;
@@ -1780,7 +1783,20 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
         e++;
         return r;
     };
-    if (a.pro.replay != nullptr) { rc = replay_launch_sample_gather(a.pro, st); if (rc) return rc; }     // the minibatch itself
+    // the minibatch itself.  The sampler leaves the ring offsets of the drawn frames behind (a.fs.tab): the convolutions read the
+    // frames in place, and the gather into the caller-visible minibatch buffers (frames, actions, rewards, terminals -- the head
+    // kernel needs the last three) runs on a side stream beside the forward passes: one dependent stage less (5.5 us)
+    const bool in_place = a.pro.replay != nullptr && a.fs.tab != nullptr;
+    const int e_gather = 12;
+    if (a.pro.replay != nullptr) {
+        rc = replay_launch_sample(a.pro, in_place, st); if (rc) return rc;
+        if (in_place) {
+            FB_CUDA_OK(cudaEventRecord(t->ev[e_gather], st));
+            FB_CUDA_OK(cudaStreamWaitEvent(t->aux4, t->ev[e_gather], 0));
+            rc = replay_launch_gather(a.pro, t->aux4); if (rc) return rc;
+            FB_CUDA_OK(cudaEventRecord(t->ev[e_gather], t->aux4));
+        } else { rc = replay_launch_gather(a.pro, st); if (rc) return rc; }
+    }
     if (pack_online) { rc = tc_pack_weights(n, a.params, 0, st); if (rc) return rc; }
     FB_CUDA_OK(fork(st, sx));
     // ---- aux: Q(s') with the net the variant names (and the online net too for Double)
@@ -1788,6 +1804,7 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     if (a.variant == 2) { rc = tc_forward(n, 0, 1, a.params, a.fn, B, n->q_next_online, sx); if (rc) return rc; }
     rc = a.variant == 0 ? tc_forward(n, 0, 1, a.params, a.fn, B, n->q_next, sx) : tc_forward(n, 1, 1, a.target, a.fn, B, n->q_next, sx);
     if (rc) return rc;
+    if (in_place) FB_CUDA_OK(cudaStreamWaitEvent(sx, t->ev[e_gather], 0));    // the event below then also says: minibatch buffers complete
     // ---- main: Q(s) with the online net; its activations stay in workspace 0 for the backward pass
     // the TD target, loss and dLoss/dQ come out of its head kernel, which first waits for Q(s') from the other stream
     FB_CUDA_OK(cudaEventRecord(t->ev[e], sx));
@@ -1808,10 +1825,8 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     // Memory.batch_update (BrainPrioritizedReplyDQN.py:316) needs only |TD error|, which the head kernel has just written: it runs on
     // a stream of its own beside the whole backward pass (measured: 26 us at the step's tail otherwise) and joins at the end
     const bool per_on_side = a.pro.replay != nullptr && a.pro.prioritized;
-    if (per_on_side) {
-        FB_CUDA_OK(fork(st, t->aux3));
-        rc = replay_launch_per_update(a.pro, a.abs_err, t->aux3); if (rc) return rc;
-    }
+    int e_head = -1;
+    if (per_on_side) { e_head = e++; FB_CUDA_OK(cudaEventRecord(t->ev[e_head], st)); }       // launched below, after the fc1 gradient GEMMs
     // ---- backward.  The head's backward pass rode in the forward's last kernel when hidden = 512 (fc1_head_train_kernel);
     // otherwise: fp32 gradients of the head variables and the fc1 bias straight into partials, dh1 as bf16
     const bool fused_head = fused_head_ok(L);
@@ -1828,6 +1843,12 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     FB_CUDA_OK((launch_tc_gemm<64, 0>(p->dh1_k, wm.wf1n, p->fc1_d, dim3((B + 127) / 128, kFlat / 64, 1), EpiFc1Dgrad{t->dz3, f.a3, B, t->f16}, st)));
     FB_CUDA_OK(fork(st, sx));
     const int e_fc1d = e - 1;
+    if (per_on_side) {
+        // (captured AFTER the two fc1 GEMMs: its one 1,024-thread CTA fits only on the SMs the fused backward kernel leaves free,
+        // and a kernel that cannot be placed held back the launches captured behind it -- the fc1 weight gradient started 5 us late)
+        FB_CUDA_OK(cudaStreamWaitEvent(t->aux4, t->ev[e_head], 0));
+        rc = replay_launch_per_update(a.pro, a.abs_err, t->aux4); if (rc) return rc;
+    }
     FB_CUDA_OK(cudaStreamWaitEvent(sy, t->ev[e_fc1d], 0));              // sy: after the fc1 data gradient (dz3 complete, wf1n no longer read)
     const int c1 = (P1 + kChunk1 - 1) / kChunk1, c23 = (P2 + kChunk23 - 1) / kChunk23;
     auto colsum_on = [&](const bf16 *x, float *part, int rows, int N, int chunk_rows, int chunks) -> cudaError_t {
@@ -1896,7 +1917,7 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
         if (rc) return rc;
     }
     if (a.ad.on) FB_CUDA_OK(fork(t->aux3, st));  // W_fc1's Adam / exchange bucket joins here, at the very end
-    if (per_on_side) FB_CUDA_OK(fork(t->aux3, st));          // Memory.batch_update (started right after the head) joins here
+    if (per_on_side) FB_CUDA_OK(fork(t->aux4, st));          // Memory.batch_update (started right after the head) joins here
     return FB_OK;
 }
 
@@ -1952,6 +1973,7 @@ int tc_loss_backward(fb_qnet *n, const TcTrainArgs &a, cudaStream_t st) {
     key.a.variant = a.variant; key.a.params = a.params; key.a.target = a.target;
     key.a.fs.base = a.fs.base; key.a.fs.sample_stride = a.fs.sample_stride; key.a.fn.base = a.fn.base; key.a.fn.sample_stride = a.fn.sample_stride;
     for (int c = 0; c < 4; c++) { key.a.fs.chan_off[c] = a.fs.chan_off[c]; key.a.fn.chan_off[c] = a.fn.chan_off[c]; }
+    key.a.fs.tab = a.fs.tab; key.a.fn.tab = a.fn.tab;
     key.a.actions = a.actions; key.a.rewards = a.rewards; key.a.terminals = a.terminals; key.a.isw = a.isw;
     key.a.B = a.B; key.a.global_batch = a.global_batch; key.a.gamma = a.gamma; key.a.loss_sum = a.loss_sum;
     key.a.grads = a.grads; key.a.loss_out = a.loss_out; key.a.abs_err = a.abs_err; key.a.q_target = a.q_target;
@@ -1980,7 +2002,7 @@ int tc_loss_backward(fb_qnet *n, const TcTrainArgs &a, cudaStream_t st) {
         }
     }
     if (ge && ge->exec) {
-        if (a.pro.replay != nullptr) { rc = replay_patch_nodes(ge->exec, ge->n_sampler, ge->n_gather, a.pro); if (rc) return rc; }
+        if (a.pro.replay != nullptr) { rc = replay_patch_nodes(ge->exec, ge->n_sampler, ge->n_gather, a.pro, a.fs.tab != nullptr); if (rc) return rc; }
         FB_CUDA_OK(cudaGraphLaunch(ge->exec, st));
     } else if (ge && ge->seen >= 1) {            // second identical call: capture (everything lazy was initialised by the first)
         cudaGraph_t graph = nullptr;

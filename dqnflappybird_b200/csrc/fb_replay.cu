@@ -36,8 +36,44 @@ constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 __device__ __forceinline__ uint32_t sample_word(uint64_t seed, unsigned long long pos) { return stream_word(seed, 3u, pos >> 32, (uint32_t)pos); }
 __device__ __forceinline__ uint32_t per_word(uint64_t seed, unsigned long long pos) { return stream_word(seed, 4u, pos >> 32, (uint32_t)pos); }
 
+// index -> (env, time): a population index of random.sample over the deque (per == 0), or a SumTree data index (per == 1)
+__device__ __forceinline__ void decode_transition(int per, long long t, int cap, long long j, int *e, long long *k) {
+    const uint32_t ju = (uint32_t)j;                      // indices are int32 (capacity < 2^30): 32-bit divisions
+    if (!per) {
+        long long k_lo = t - cap + 1; if (k_lo < 1) k_lo = 1;
+        const uint32_t cnt = (uint32_t)(t - k_lo + 1);
+        *e = (int)(ju / cnt); *k = k_lo + (long long)(ju % cnt);
+    } else {
+        *e = (int)(ju / (uint32_t)cap);
+        const long long p = (long long)(ju % (uint32_t)cap), back = (t - 1 - p) % cap;
+        *k = t - back;
+    }
+}
+// Where the five frames of each drawn transition live in the ring (byte offsets), written by the sampler itself: the training
+// step's first convolution reads them in place, so the gather that fills the caller-visible minibatch buffers runs beside the
+// forward passes instead of ahead of them.  tab == nullptr: not wanted.
+struct FrameTabArgs { long long *tab; long long t; int cap, L, per; };
+__device__ __forceinline__ void write_frame_tab(const FrameTabArgs &ft, int b, long long j) {
+    int e; long long k;
+    decode_transition(ft.per, ft.t, ft.cap, j, &e, &k);
+    if (k >= 4) {
+        int slot = (int)((k - 4) % ft.L);                 // one 64-bit remainder, then the ring is walked
+#pragma unroll
+        for (int f = 0; f < 5; f++) {
+            ft.tab[b * 5 + f] = ((long long)e * ft.L + slot) * 6400;
+            if (++slot == ft.L) slot = 0;
+        }
+    } else {
+#pragma unroll
+        for (int f = 0; f < 5; f++) {
+            long long tf = k - 4 + f; if (tf < 0) tf = 0;             // setInitState replication of frame 0
+            ft.tab[b * 5 + f] = ((long long)e * ft.L + tf % ft.L) * 6400;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kSampThreads) sample_uniform_kernel(uint32_t n, int batch, uint32_t setsize, uint64_t seed,
-                                                                      unsigned long long *word_pos, int32_t *out) {
+                                                                      unsigned long long *word_pos, int32_t *out, FrameTabArgs ft) {
     __shared__ uint32_t hbuf[2 * kHashSize];
     uint32_t *hkey = hbuf, *hidx = hbuf + kHashSize;
     __shared__ uint32_t warp_tot[kSampThreads / 32];
@@ -58,6 +94,8 @@ __global__ void __launch_bounds__(kSampThreads) sample_uniform_kernel(uint32_t n
             }
             *word_pos = pos;
         }
+        __syncthreads();
+        if (ft.tab) for (int b = tid; b < batch; b += kSampThreads) write_frame_tab(ft, b, out[b]);
         return;
     }
     const uint32_t bits = 32 - __clz(n);
@@ -105,6 +143,7 @@ __global__ void __launch_bounds__(kSampThreads) sample_uniform_kernel(uint32_t n
         if (s_taken >= (uint32_t)batch) break;
     }
     if (tid == 0) *word_pos = pos0 + s_consumed;
+    if (ft.tab) for (int b = tid; b < batch; b += kSampThreads) write_frame_tab(ft, b, out[b]);      // out[] is complete: last barrier above
 }
 
 // ------------------------------------------------------------------------------ gather
@@ -124,11 +163,8 @@ struct GatherArgs {
 __global__ void __launch_bounds__(128) gather_kernel(GatherArgs g) {
     const int b = blockIdx.x, f = blockIdx.y;
     if (b >= g.batch) return;
-    long long k_lo = g.t - g.cap + 1; if (k_lo < 1) k_lo = 1;
-    long long cnt = g.t - k_lo + 1;
-    long long j = g.idx[b], k; int e;
-    if (!g.per) { e = (int)(j / cnt); k = k_lo + j % cnt; }
-    else { e = (int)(j / g.cap); long long p = j % g.cap; long long back = (g.t - 1 - p) % g.cap; k = g.t - back; }
+    long long k; int e;
+    decode_transition(g.per, g.t, g.cap, g.idx[b], &e, &k);
     long long tf = k - 4 + f; if (tf < 0) tf = 0;                     // setInitState replication of frame 0
     const uint4 *src = reinterpret_cast<const uint4 *>(g.ring) + ((size_t)e * g.L + (size_t)(tf % g.L)) * 400;
     uint4 *dst = reinterpret_cast<uint4 *>(g.frames) + (size_t)b * 2000 + f * 400;
@@ -344,7 +380,7 @@ __global__ void __launch_bounds__(256) per_store_multi_kernel(double *tree, doub
 constexpr int kSampleWarps = 8;
 __global__ void __launch_bounds__(32 * kSampleWarps) per_sample_kernel(const double *tree, const double *min_p_src, int cap, int batch, double beta,
                                                                        uint64_t seed, unsigned long long *word_pos, unsigned int *done_counter, int32_t *tree_idx,
-                                                                       int32_t *data_idx, double *isw, double *prio_out, float *isw_f32) {
+                                                                       int32_t *data_idx, double *isw, double *prio_out, float *isw_f32, FrameTabArgs ft) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * kSampleWarps + warp;
     const int n_nodes = 2 * cap - 1;
@@ -394,6 +430,7 @@ __global__ void __launch_bounds__(32 * kSampleWarps) per_sample_kernel(const dou
             const double prob = p / total, min_prob = min_p / total;
             tree_idx[i] = parent;
             data_idx[i] = parent - (cap - 1);
+            if (ft.tab) write_frame_tab(ft, i, parent - (cap - 1));
             const double w = pow(prob / min_prob, -beta);
             isw[i] = w;
             if (isw_f32) isw_f32[i] = (float)w;             // the ISWeights placeholder is tf.float32 (BrainPrioritizedReplyDQN.py:243)
@@ -424,6 +461,7 @@ struct fb_replay {
     int N, L, C, cap;
     double *tree;                    // PER only
     double *mn, *mx;                 // min-positive / max trees of the same shape (see the SumTree section)
+    long long *frame_tab;            // [512][5] ring offsets of the drawn transitions' frames (see FrameTabArgs)
     const double *gmin;              // nullptr, or the caller's device scalar: smallest positive leaf over ALL shards (several GPUs)
     unsigned int *counters;          // [0] per_store_multi_kernel, [1] per_sample_kernel: "last CTA" counters, self-resetting
     int32_t *leaves; double *prio; double *change;   // scratch, max(N, max_batch)
@@ -442,6 +480,8 @@ extern "C" int fb_replay_create(int n_envs, int ring_len, int capacity_per_env, 
     FB_CUDA_OK(cudaMalloc(&r->word_pos, 2 * sizeof(unsigned long long)));
     FB_CUDA_OK(cudaMemset(r->word_pos, 0, 2 * sizeof(unsigned long long)));
     r->mn = r->mx = nullptr; r->gmin = nullptr;
+    FB_CUDA_OK(cudaMalloc(&r->frame_tab, 512 * 5 * sizeof(long long)));
+    FB_CUDA_OK(cudaMemset(r->frame_tab, 0, 512 * 5 * sizeof(long long)));
     FB_CUDA_OK(cudaMalloc(&r->counters, 2 * sizeof(unsigned int)));
     FB_CUDA_OK(cudaMemset(r->counters, 0, 2 * sizeof(unsigned int)));
     FB_CUDA_OK(cudaMalloc(&r->leaves, sizeof(int32_t) * r->scratch_n));
@@ -466,7 +506,7 @@ extern "C" int fb_replay_create(int n_envs, int ring_len, int capacity_per_env, 
 
 extern "C" int fb_replay_destroy(fb_replay *r) {
     if (!r) return FB_OK;
-    cudaFree(r->tree); cudaFree(r->mn); cudaFree(r->mx); cudaFree(r->counters); cudaFree(r->leaves); cudaFree(r->prio); cudaFree(r->change); cudaFree(r->word_pos);
+    cudaFree(r->frame_tab); cudaFree(r->tree); cudaFree(r->mn); cudaFree(r->mx); cudaFree(r->counters); cudaFree(r->leaves); cudaFree(r->prio); cudaFree(r->change); cudaFree(r->word_pos);
     delete r;
     return FB_OK;
 }
@@ -478,7 +518,7 @@ extern "C" int fb_replay_sample_uniform(fb_replay *r, long long t, int batch, ui
     long long n = (t - k_lo + 1) * r->N;
     if (t < 1 || n < batch) { fb_set_error("Sample larger than population or is negative"); return FB_ERR_INVALID; }   // random.sample's ValueError
     FB_REQUIRE(setsize <= 2u * kHashSize, "fb_replay_sample_uniform: setsize too large");
-    sample_uniform_kernel<<<1, kSampThreads, 0, (cudaStream_t)stream>>>((uint32_t)n, batch, setsize, seed, r->word_pos, idx_out_dev);
+    sample_uniform_kernel<<<1, kSampThreads, 0, (cudaStream_t)stream>>>((uint32_t)n, batch, setsize, seed, r->word_pos, idx_out_dev, FrameTabArgs{nullptr, 0, 0, 0, 0});
     FB_CUDA_OK(cudaGetLastError());
     return FB_OK;
 }
@@ -497,9 +537,9 @@ extern "C" int fb_replay_gather(fb_replay *r, const uint8_t *ring_dev, const uin
 }
 
 static void launch_per_sample(fb_replay *r, int batch, double beta, uint64_t seed, int32_t *tree_idx, int32_t *data_idx, double *isw, double *prio,
-                              float *isw32, cudaStream_t st) {
+                              float *isw32, cudaStream_t st, FrameTabArgs ft = FrameTabArgs{nullptr, 0, 0, 0, 0}) {
     per_sample_kernel<<<(batch + kSampleWarps - 1) / kSampleWarps, 32 * kSampleWarps, 0, st>>>(r->tree, r->gmin ? r->gmin : r->mn, r->cap, batch, beta, seed, r->word_pos + 1,
-                                                                                               r->counters + 1, tree_idx, data_idx, isw, prio, isw32);
+                                                                                               r->counters + 1, tree_idx, data_idx, isw, prio, isw32, ft);
 }
 
 // ---- sampling + gather as the head of a captured training step (fb_qnet_train_step_sampled) -------------------------
@@ -514,24 +554,39 @@ static GatherArgs sampling_gather_args(const fb_step_sampling &p) {
     return GatherArgs{p.ring_dev, r->N, r->L, p.act_dev, p.rew_dev, p.term_dev, p.t, r->C, p.prioritized ? 1 : 0, p.idx_out_dev, p.batch,
                       p.frames_out_dev, p.act_out_dev, p.rew_out_dev, p.term_out_dev, p.env_out_dev, p.k_out_dev};
 }
-int replay_launch_sample_gather(const fb_step_sampling &p, cudaStream_t st) {
+static FrameTabArgs sampling_frame_tab(const fb_step_sampling &p, bool want) {
+    const fb_replay *r = p.replay;
+    return FrameTabArgs{want ? r->frame_tab : nullptr, p.t, r->C, r->L, p.prioritized ? 1 : 0};
+}
+// the sampler alone; with_tab: it also leaves the ring offsets of the drawn frames in replay_frame_tab()
+int replay_launch_sample(const fb_step_sampling &p, bool with_tab, cudaStream_t st) {
     FB_REQUIRE(p.replay && p.ring_dev && p.act_dev && p.rew_dev && p.term_dev && p.idx_out_dev && p.frames_out_dev && p.act_out_dev &&
                p.rew_out_dev && p.term_out_dev && p.batch > 0 && p.batch <= 512, "step sampling: bad argument");
     fb_replay *r = p.replay;
     if (p.prioritized) {
         FB_REQUIRE(r->tree && p.tree_idx_out_dev && p.is_weights_out_dev && p.is_weights_f32_out_dev && (p.per_mode == 0 || p.per_mode == 1) &&
                    p.batch <= r->scratch_n, "step sampling: prioritized replay arguments");
-        launch_per_sample(r, p.batch, p.beta, p.seed, p.tree_idx_out_dev, p.idx_out_dev, p.is_weights_out_dev, p.prio_out_dev, p.is_weights_f32_out_dev, st);
+        launch_per_sample(r, p.batch, p.beta, p.seed, p.tree_idx_out_dev, p.idx_out_dev, p.is_weights_out_dev, p.prio_out_dev, p.is_weights_f32_out_dev, st,
+                          sampling_frame_tab(p, with_tab));
     } else {
         FB_REQUIRE(p.setsize <= 2u * kHashSize, "step sampling: setsize too large");
         uint32_t n;
         if (!sampling_population(p, &n)) { fb_set_error("Sample larger than population or is negative"); return FB_ERR_INVALID; }
-        sample_uniform_kernel<<<1, kSampThreads, 0, st>>>(n, p.batch, p.setsize, p.seed, r->word_pos, p.idx_out_dev);
+        sample_uniform_kernel<<<1, kSampThreads, 0, st>>>(n, p.batch, p.setsize, p.seed, r->word_pos, p.idx_out_dev, sampling_frame_tab(p, with_tab));
     }
+    FB_CUDA_OK(cudaGetLastError());
+    return FB_OK;
+}
+int replay_launch_gather(const fb_step_sampling &p, cudaStream_t st) {
     gather_kernel<<<dim3(p.batch, 5), 128, 0, st>>>(sampling_gather_args(p));
     FB_CUDA_OK(cudaGetLastError());
     return FB_OK;
 }
+int replay_launch_sample_gather(const fb_step_sampling &p, cudaStream_t st) {
+    int rc = replay_launch_sample(p, false, st);
+    return rc ? rc : replay_launch_gather(p, st);
+}
+const long long *replay_frame_tab(const fb_replay *r) { return r->frame_tab; }
 int replay_launch_per_update(const fb_step_sampling &p, const float *abs_err_dev, cudaStream_t st) {
     FB_REQUIRE(p.prioritized && abs_err_dev, "step sampling: Memory.batch_update needs the step's |TD errors| (abs_err_out_dev)");
     fb_replay *r = p.replay;
@@ -541,22 +596,23 @@ int replay_launch_per_update(const fb_step_sampling &p, const float *abs_err_dev
 }
 bool replay_is_sampler(const void *func) { return func == (const void *)sample_uniform_kernel || func == (const void *)per_sample_kernel; }
 bool replay_is_gather(const void *func) { return func == (const void *)gather_kernel; }
-int replay_patch_nodes(cudaGraphExec_t exec, cudaGraphNode_t sampler, cudaGraphNode_t gather, const fb_step_sampling &p) {
+int replay_patch_nodes(cudaGraphExec_t exec, cudaGraphNode_t sampler, cudaGraphNode_t gather, const fb_step_sampling &p, bool with_tab) {
     fb_replay *r = p.replay;
     cudaKernelNodeParams kp{};
     int batch = p.batch; uint64_t seed = p.seed; int32_t *idx = p.idx_out_dev;
+    FrameTabArgs ft = sampling_frame_tab(p, with_tab);
     if (p.prioritized) {
         const double *tree = r->tree, *mn = r->gmin ? r->gmin : r->mn; int cap = r->cap; double beta = p.beta; unsigned long long *word_pos = r->word_pos + 1;
         unsigned int *done = r->counters + 1;
         int32_t *tree_idx = p.tree_idx_out_dev; double *isw = p.is_weights_out_dev, *prio = p.prio_out_dev; float *isw32 = p.is_weights_f32_out_dev;
-        void *sargs[] = {&tree, &mn, &cap, &batch, &beta, &seed, &word_pos, &done, &tree_idx, &idx, &isw, &prio, &isw32};
+        void *sargs[] = {&tree, &mn, &cap, &batch, &beta, &seed, &word_pos, &done, &tree_idx, &idx, &isw, &prio, &isw32, &ft};
         kp.func = (void *)per_sample_kernel; kp.gridDim = dim3((p.batch + kSampleWarps - 1) / kSampleWarps); kp.blockDim = dim3(32 * kSampleWarps); kp.kernelParams = sargs;
         FB_CUDA_OK(cudaGraphExecKernelNodeSetParams(exec, sampler, &kp));
     } else {
         uint32_t n;
         if (!sampling_population(p, &n)) { fb_set_error("Sample larger than population or is negative"); return FB_ERR_INVALID; }
         uint32_t setsize = p.setsize; unsigned long long *word_pos = r->word_pos;
-        void *sargs[] = {&n, &batch, &setsize, &seed, &word_pos, &idx};
+        void *sargs[] = {&n, &batch, &setsize, &seed, &word_pos, &idx, &ft};
         kp.func = (void *)sample_uniform_kernel; kp.gridDim = dim3(1); kp.blockDim = dim3(kSampThreads); kp.kernelParams = sargs;
         FB_CUDA_OK(cudaGraphExecKernelNodeSetParams(exec, sampler, &kp));
     }

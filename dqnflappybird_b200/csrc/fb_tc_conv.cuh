@@ -449,10 +449,9 @@ __global__ void __launch_bounds__(FROM_X2 ? kRoleThreads1 : kFusedThreads, 1) tc
                 const int ih0 = 24 * tq - 2, lo = ih0 < 0 ? 0 : ih0, hi = ih0 + kRawRows > 80 ? 80 : ih0 + kRawRows;       // valid rows [lo, hi)
                 const uint32_t bytes = (uint32_t)(hi - lo) * 80u, full = tc::smem_u32(&bar_raw_full[rs]);
                 const uint32_t dst = tc::smem_u32(raw_gen) + rs * kRawBytes + (uint32_t)(lo - ih0) * 80u;
-                const uint8_t *src = g.fv.base + (size_t)b * g.fv.sample_stride + lo * 80;
                 tc::mbar_expect_tx(full, 4 * bytes);
 #pragma unroll
-                for (int c = 0; c < 4; c++) tc::bulk_load_1d(dst + c * (kRawRows * 80), src + g.fv.chan_off[c], bytes, full);
+                for (int c = 0; c < 4; c++) tc::bulk_load_1d(dst + c * (kRawRows * 80), g.fv.chan(b, c) + lo * 80, bytes, full);
             }
             __syncwarp();
         }
