@@ -137,6 +137,7 @@ _SIGNATURES = {
     "fb_dist_destroy": ([_vp], C.c_int),
     "fb_dist_handle_bytes": ([], C.c_int),
     "fb_dist_set_two_shot": ([_vp, C.c_int], C.c_int),
+    "fb_dist_debug_mask": ([_vp, C.c_int], C.c_int),
     "fb_dist_handles": ([_vp, C.c_char_p], C.c_int),
     "fb_dist_connect": ([_vp, C.c_char_p], C.c_int),
     "fb_dist_connect_local": ([_vp, C.c_int, _vp], C.c_int),

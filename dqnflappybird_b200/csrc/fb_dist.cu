@@ -26,6 +26,8 @@ constexpr int kBuckets = 2;                  // 0: W_fc1 (its gradient is final 
 constexpr int kBucketFlag0 = 64;             // flags[kBucketFlag0 + 16 b + q] = newest step rank q has published for bucket b
 
 struct fb_dist {
+    int debug_mask;                          // timing experiments only (fb_dist_debug_mask): bit b: bucket b sums its own gradient alone,
+                                             // bit 2 + b: bucket b skips the publish / wait handshake -- the results are then WRONG
     int rank, world;
     size_t n;
     float *xgrads[2];
@@ -215,17 +217,18 @@ struct BucketArgs {
     int lo4, hi4;                            // float4 range of the bucket ...
     int skip_lo4, skip4;                     // ... from which [skip_lo4, skip_lo4 + skip4) is left out (bucket 1 = everything but W_fc1)
     int tail_lo, tail_hi;                    // scalar tail (total % 4 parameters), bucket 1 only
+    int sum_world, handshake;                // = world, 1 -- except under fb_dist_debug_mask (timing experiments, wrong sums)
 };
 
 __global__ void __launch_bounds__(256) adam_xbucket_kernel(float *__restrict__ params, float *__restrict__ am, float *__restrict__ av, const BucketArgs x,
                                                            const float *__restrict__ alpha_dev, float beta1, float beta2, float eps, float grad_scale,
                                                            int repack, const QnetLayout L, const PackedWeights pw) {
     const uint32_t step = *x.dev_step + 1u;
-    if (blockIdx.x == 0 && (int)threadIdx.x < x.world) {
+    if (x.handshake && blockIdx.x == 0 && (int)threadIdx.x < x.world) {
         __threadfence_system();
         st_release_sys(x.peer_flags[threadIdx.x] + x.rank, step);
     }
-    if ((int)threadIdx.x < x.world) {
+    if (x.handshake && (int)threadIdx.x < x.world) {
         uint32_t spins = 0;
         while ((int32_t)(ld_acquire_sys(x.my_flags + threadIdx.x) - step) < 0)
             if (++spins > (1u << 26)) __trap();
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(256) adam_xbucket_kernel(float *__restrict__ p
             float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
             if (k < n4) {
                 g = ld_peer(x.g[0] + 4 * (size_t)i);
-                for (int q = 1; q < x.world; q++) {
+                for (int q = 1; q < x.sum_world; q++) {
                     float4 h = ld_peer(x.g[q] + 4 * (size_t)i);
                     g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
                 }
@@ -299,6 +302,7 @@ int dist_launch_bucket(fb_dist *d, fb_qnet *net, int bucket, float *params_dev, 
             x.g[q] = d->peer_grads[par][q]; x.peer_flags[q] = d->peer_flags[q] + kBucketFlag0 + 16 * b;
         }
         x.my_flags = d->flags + kBucketFlag0 + 16 * b; x.dev_step = d->dev_steps + b; x.dev_done = d->dev_done + b;
+        x.sum_world = (d->debug_mask >> b) & 1 ? 1 : d->world; x.handshake = (d->debug_mask >> (2 + b)) & 1 ? 0 : 1;
         x.rank = d->rank; x.world = d->world; x.lo4 = lo4; x.hi4 = hi4; x.skip_lo4 = skip_lo4; x.skip4 = skip4; x.tail_lo = tail_lo; x.tail_hi = tail_hi;
         adam_xbucket_kernel<<<ctas, 256, 0, st>>>(params_dev, m_dev, v_dev, x, alpha_dev, beta1, beta2, eps, grad_scale, repack, L, pw);
         FB_CUDA_OK(cudaGetLastError());
@@ -315,7 +319,7 @@ extern "C" int fb_dist_create(int rank, int world, long long n_floats, fb_dist *
     FB_REQUIRE(out != nullptr && world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world && n_floats > 0, "fb_dist_create: bad argument");
     fb_dist *d = new (std::nothrow) fb_dist();
     FB_REQUIRE(d != nullptr, "fb_dist_create: out of host memory");
-    d->rank = rank; d->world = world; d->n = (size_t)n_floats; d->n_opened = 0; d->step = 0;
+    d->rank = rank; d->world = world; d->n = (size_t)n_floats; d->n_opened = 0; d->step = 0; d->debug_mask = 0;
     const size_t bytes = ((size_t)n_floats * sizeof(float) + 255) / 256 * 256;
     for (int k = 0; k < 2; k++) { FB_CUDA_OK(cudaMalloc(&d->xgrads[k], bytes)); FB_CUDA_OK(cudaMemset(d->xgrads[k], 0, bytes)); }
     FB_CUDA_OK(cudaMalloc(&d->flags, 512));
@@ -344,6 +348,13 @@ extern "C" int fb_dist_destroy(fb_dist *d) {
 }
 
 extern "C" int fb_dist_handle_bytes(void) { return 4 * (int)sizeof(cudaIpcMemHandle_t); }
+
+// timing experiments: see fb_dist::debug_mask.  Takes effect for steps captured / launched afterwards.
+extern "C" int fb_dist_debug_mask(fb_dist *d, int mask) {
+    FB_REQUIRE(d != nullptr, "fb_dist_debug_mask: NULL argument");
+    d->debug_mask = mask;
+    return FB_OK;
+}
 
 // force the one-shot (0) or two-shot (1) exchange (default: two-shot from four ranks up)
 extern "C" int fb_dist_set_two_shot(fb_dist *d, int on) {

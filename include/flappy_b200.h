@@ -257,6 +257,9 @@ int fb_dist_parity(const fb_dist *d);
  * convolution gradients, the remaining 79,522 parameters at the tail; step number and alpha live in device memory.
  * fb_dist_advance: that step has been enqueued, the next one writes the other exchange buffer. */
 int fb_dist_advance(fb_dist *d);
+/* timing experiments only (tools/dist_probe.py): bit b: bucket b of the in-step exchange sums its own gradient alone, bit 2+b: it skips
+ * the publish / wait handshake.  Results are WRONG while a bit is set. */
+int fb_dist_debug_mask(fb_dist *d, int mask);
 int fb_qnet_attach_exchange(fb_qnet *net, fb_dist *d);
 int fb_dist_adam(fb_dist *d, fb_qnet *net, float *params_dev, float *m_dev, float *v_dev, float alpha, float beta1, float beta2,
                  float eps, float grad_scale, float *reduced_out_dev /* may be NULL */, int wait, void *stream);
