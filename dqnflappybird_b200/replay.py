@@ -124,6 +124,11 @@ class ReplayMemory:
         _lib.check(self._L.fb_replay_rng_pos(self._h, pos, 0, self._stream()), "fb_replay_rng_pos")
         return int(pos[0]), int(pos[1])
 
+    def set_rng_positions(self, pos):
+        """restore the (uniform, prioritized) word-stream positions ``rng_positions()`` returned (resume / replay of a draw)"""
+        arr = (C.c_uint64 * 2)(int(pos[0]), int(pos[1]))
+        _lib.check(self._L.fb_replay_rng_pos(self._h, arr, 1, self._stream()), "fb_replay_rng_pos")
+
 
 class PrioritizedMemory(ReplayMemory):
     """``Memory`` (BrainPrioritizedReplyDQN.py:107-151) on a device SumTree.

@@ -217,6 +217,11 @@ def test_sampling_inside_the_step_is_identical_to_separate_launches(mods, model)
     assert torch.equal(b1.net.params, b0.net.params) and torch.equal(b1.net.adam_v, b0.net.adam_v)
     assert b1.replayMemory.rng_positions() == b0.replayMemory.rng_positions()
     assert torch.equal(b1.net.loss, b0.net.loss)
+    # inside the step the convolutions read the drawn frames in place from the ring (offsets left by the sampler) and the gather
+    # runs beside them: the caller-visible minibatch buffers are filled all the same
+    m1, m0 = b1.replayMemory, b0.replayMemory
+    assert torch.equal(m1._frames[:32], m0._frames[:32]) and torch.equal(m1._a[:32], m0._a[:32])
+    assert torch.equal(m1._r[:32], m0._r[:32]) and torch.equal(m1._t[:32], m0._t[:32])
     if model == "prioritydqn":                    # Memory.sample at the head, Memory.batch_update at the tail of the same graph
         assert torch.equal(b1.replayMemory.tree(), b0.replayMemory.tree()) and b1.replayMemory.beta == b0.replayMemory.beta
         assert torch.equal(b1.replayMemory._isw[:32], b0.replayMemory._isw[:32])

@@ -129,25 +129,27 @@ def test_forward_matches_oracle_bf16(mods, dueling):
 
 
 def test_conv1_modes_are_bit_identical(mods):
-    """conv1 as three kernels (mode 0), with the max-pool in its epilogue (1), and built straight from the u8 frames when
-    no backward follows (2, default): the same arithmetic on different data paths -- identical Q-values and gradients"""
+    """conv1 as three kernels (mode 0), with the max-pool in its epilogue (1), built straight from the u8 frames when no
+    backward follows (2, default), and from the u8 frames in the training forward too, X2 packed beside it for the weight
+    gradient (3): the same arithmetic on different data paths -- identical Q-values and gradients"""
     _lib, game, qnet = mods
     B = 70
     frames = _env_frames(game, B, 9)
-    nets = [qnet.QNetwork(max_batch=128, seed=2, precision="bf16") for _ in range(3)]
+    nets = [qnet.QNetwork(max_batch=128, seed=2, precision="bf16") for _ in range(4)]
     for mode, n in enumerate(nets):
         n.params.mul_(4.0); n.target.mul_(4.0)
         _lib.check(_lib.lib().fb_qnet_set_conv1_mode(n._h, mode), "fb_qnet_set_conv1_mode")
     q = [n.forward(qnet.FrameBatch.from_stack(frames, 1)) for n in nets]
-    assert torch.equal(q[0], q[1]) and torch.equal(q[0], q[2])
+    assert all(torch.equal(q[0], x) for x in q[1:])
     rng = np.random.default_rng(3)
     a = torch.from_numpy(rng.integers(0, 2, B).astype(np.uint8)).cuda()
     r = torch.from_numpy(rng.choice(np.array([0.1, 3.0, -3.0], np.float32), B)).cuda()
     term = (r == -3.0).to(torch.uint8)
-    for n in nets:
-        n.loss_backward("double", frames, a, r, term)
-    for n in nets[1:]:
-        assert torch.equal(nets[0].grads, n.grads) and nets[0].loss.item() == n.loss.item()
+    for _ in range(3):                              # eager, eager, graph replay
+        for n in nets:
+            n.loss_backward("double", frames, a, r, term)
+        for n in nets[1:]:
+            assert torch.equal(nets[0].grads, n.grads) and nets[0].loss.item() == n.loss.item()
 
 
 def test_forward_from_ring_view_bf16(mods):

@@ -244,3 +244,37 @@ def test_configs3_shard_size_prioritized_memory(mods):
     tree = mem.tree()
     inner = torch.arange(cap - 1, device="cuda")
     assert torch.equal(tree[inner], tree[2 * inner + 1] + tree[2 * inner + 2])
+
+
+def test_prioritized_sample_with_a_global_minimum(mods):
+    """several ranks, one memory (fb_per_min_root / fb_per_set_global_min): ISWeights = (p_i / min_p)^-beta with min_p the
+    minimum over ALL shards, handed in as a device scalar (the ranks MIN-reduce it; here: set by hand)"""
+    game, replay = mods
+    N, C = 16, 8
+    ring = torch.zeros((N, C + 4, 80, 80), dtype=torch.uint8, device="cuda")
+    mem = replay.PrioritizedMemory(ring, C, seed=3, max_batch=32)
+    for k in range(1, C + 3):
+        mem.appended(k)
+    cap = N * C
+    idx = torch.arange(cap - 1, cap - 1 + 32, dtype=torch.int32, device="cuda")
+    pr = torch.linspace(0.05, 2.0, 32, dtype=torch.float64, device="cuda")
+    mem.batch_update(idx, priorities=pr)
+    L = replay._lib.lib()
+    root = torch.empty(1, dtype=torch.float64, device="cuda")
+    replay._lib.check(L.fb_per_min_root(mem._h, root.data_ptr(), torch.cuda.current_stream().cuda_stream), "fb_per_min_root")
+    leaves = mem.tree()[cap - 1:]
+    assert root.item() == leaves[leaves > 0].min().item() == 0.05
+    pos = mem.rng_positions()
+    mb = mem.sample(32)
+    w_local = mb.is_weights.clone(); picked = mb.tree_idx.clone()
+    gmin = torch.tensor([0.0125], dtype=torch.float64, device="cuda")                 # another shard holds a smaller leaf
+    replay._lib.check(L.fb_per_set_global_min(mem._h, gmin.data_ptr()), "fb_per_set_global_min")
+    mem.set_rng_positions(pos); mem.beta -= mem.beta_increment_per_sampling           # the same draw again
+    mb = mem.sample(32)
+    assert torch.equal(mb.tree_idx, picked)
+    p = mem.tree()[picked.long()]
+    assert torch.allclose(mb.is_weights, (p / 0.0125) ** (-mem.beta), rtol=1e-12, atol=0)
+    assert torch.allclose(mb.is_weights, w_local * 4.0 ** (-mem.beta), rtol=1e-12, atol=0)
+    replay._lib.check(L.fb_per_set_global_min(mem._h, None), "fb_per_set_global_min")
+    mem.set_rng_positions(pos); mem.beta -= mem.beta_increment_per_sampling
+    assert torch.equal(mem.sample(32).is_weights, w_local)
