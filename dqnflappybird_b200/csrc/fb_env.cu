@@ -452,8 +452,12 @@ extern "C" int fb_env_step_random(fb_env *e, int n_steps, uint64_t action_seed, 
 // actions, the step kernel and the D2H copies of reward / terminal / score run on three streams chained by events,
 // and the copies of step t overlap the kernel of step t+1.  The reference raises ValueError for a non one-hot action
 // BEFORE touching the state (wrapped_flappy_bird.py:99-100): the actions are checked on the host first.
-extern "C" int fb_env_step_host_submit(fb_env *e, const uint8_t *actions_host, uint8_t *obs_ring_dev, int ring_len, int ring_slot,
-                                       float *reward_host, uint8_t *terminal_host, int32_t *score_host, void *stream) {
+// split: physics first (12 us at 131,072 envs: new state, reward / terminal / score), then the drawing as a second launch of the
+// same kernel -- the D2H copies (1.2 MB, ~45 us over PCIe) run beside the 150 us of drawing instead of after it.  Used by the
+// strictly synchronous fb_env_step_host; with two steps in flight (submit / wait) the copies already overlap the NEXT step's
+// kernel and the one fused launch is cheaper.
+static int host_submit(fb_env *e, const uint8_t *actions_host, uint8_t *obs_ring_dev, int ring_len, int ring_slot,
+                       float *reward_host, uint8_t *terminal_host, int32_t *score_host, void *stream, bool split) {
     int rc = check_ring(e, obs_ring_dev, ring_len, ring_slot, 1);
     if (rc) return rc;
     FB_REQUIRE(actions_host != nullptr, "fb_env_step_host: actions_host is NULL");
@@ -474,16 +478,31 @@ extern "C" int fb_env_step_host_submit(fb_env *e, const uint8_t *actions_host, u
     StepArgs a{};
     a.actions = e->stage_act[sl]; a.ring = obs_ring_dev; a.ring_len = ring_len; a.ring_slot = ring_slot;
     a.reward = e->stage_rew[sl]; a.terminal = e->stage_term[sl]; a.score = e->stage_score[sl]; a.n_steps = 1;
+    split = split && obs_ring_dev != nullptr;
+    if (split) a.ring = nullptr;                                   // physics only
     rc = launch_step(e, a, st, false);
     if (rc) return rc;
     FB_CUDA_OK(cudaEventRecord(e->ev_step[sl], st));
+    if (split) {
+        StepArgs d{};
+        d.ring = obs_ring_dev; d.ring_len = ring_len; d.ring_slot = ring_slot; d.n_steps = 1; d.draw_only = 1;
+        rc = launch_step(e, d, st);
+        if (rc) return rc;
+        FB_CUDA_OK(cudaEventRecord(e->ev_in[sl], st));             // (ev_in[sl] has done its job above: reused for "frames drawn")
+    }
     FB_CUDA_OK(cudaStreamWaitEvent(e->s_out, e->ev_step[sl], 0));
     if (reward_host) FB_CUDA_OK(cudaMemcpyAsync(reward_host, e->stage_rew[sl], sizeof(float) * (size_t)e->n, cudaMemcpyDeviceToHost, e->s_out));
     if (terminal_host) FB_CUDA_OK(cudaMemcpyAsync(terminal_host, e->stage_term[sl], (size_t)e->n, cudaMemcpyDeviceToHost, e->s_out));
     if (score_host) FB_CUDA_OK(cudaMemcpyAsync(score_host, e->stage_score[sl], sizeof(int32_t) * (size_t)e->n, cudaMemcpyDeviceToHost, e->s_out));
+    if (split) FB_CUDA_OK(cudaStreamWaitEvent(e->s_out, e->ev_in[sl], 0));   // the step is over when the frames are in the ring, too
     FB_CUDA_OK(cudaEventRecord(e->ev_out[sl], e->s_out));
     e->submitted++;
     return FB_OK;
+}
+
+extern "C" int fb_env_step_host_submit(fb_env *e, const uint8_t *actions_host, uint8_t *obs_ring_dev, int ring_len, int ring_slot,
+                                       float *reward_host, uint8_t *terminal_host, int32_t *score_host, void *stream) {
+    return host_submit(e, actions_host, obs_ring_dev, ring_len, ring_slot, reward_host, terminal_host, score_host, stream, false);
 }
 
 // Blocks until the OLDEST submitted step has delivered its reward / terminal / score to the host buffers.
@@ -499,7 +518,7 @@ extern "C" int fb_env_step_host(fb_env *e, const uint8_t *actions_host, uint8_t 
                                 float *reward_host, uint8_t *terminal_host, int32_t *score_host, void *stream) {
     FB_REQUIRE(e != nullptr, "fb_env_step_host: env is NULL");
     while (e->submitted > e->waited) { int rc = fb_env_step_host_wait(e); if (rc) return rc; }
-    int rc = fb_env_step_host_submit(e, actions_host, obs_ring_dev, ring_len, ring_slot, reward_host, terminal_host, score_host, stream);
+    int rc = host_submit(e, actions_host, obs_ring_dev, ring_len, ring_slot, reward_host, terminal_host, score_host, stream, e->n >= 8192);
     if (rc) return rc;
     return fb_env_step_host_wait(e);
 }

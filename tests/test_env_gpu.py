@@ -262,9 +262,10 @@ def test_frame_step_api_forms(game):
     assert torch.equal(st[..., 3], gb.ring[:, gb.slot])
 
 
-def test_step_host_entry_point(game):
-    """fb_env_step_host: pinned host actions in, reward/terminal/score out, obs stays on device"""
-    N = 512
+@pytest.mark.parametrize("N", [512, 8229])
+def test_step_host_entry_point(game, N):
+    """fb_env_step_host: pinned host actions in, reward/terminal/score out, obs stays on device.  From 8,192 envs up the call
+    runs the physics and the drawing as two launches, so that the copies back to the host overlap the drawing"""
     gaps = np.random.default_rng(1).integers(0, 8, (N, 17)).astype(np.uint8)
     gs = game.GameState(num_envs=N, replay_gaps=gaps)
     oracle = fo.OracleEnvs(N, gaps=gaps)
@@ -275,10 +276,11 @@ def test_step_host_entry_point(game):
     for k in range(80):
         a.copy_(torch.from_numpy((rng.random(N) < 0.3).astype(np.uint8)))
         obs = gs.frame_step_host(a, r, t, s)
-        _, rr, tt, ss = oracle.step(a.numpy(), want_obs=False)
+        o_obs, rr, tt, ss = oracle.step(a.numpy(), want_obs=(k == 79))
         np.testing.assert_array_equal(r.numpy(), rr); np.testing.assert_array_equal(t.numpy(), tt)
         np.testing.assert_array_equal(s.numpy(), ss)
-    np.testing.assert_array_equal(obs[7].cpu().numpy(), oracle.obs(7))
+    np.testing.assert_array_equal(obs.cpu().numpy(), o_obs)
+    np.testing.assert_array_equal(gs.export_state().cpu().numpy(), oracle.export_state())
     a[3] = 2
     with pytest.raises(ValueError, match="Multiple input actions"):
         gs.frame_step_host(a, r, t, s)
