@@ -721,8 +721,13 @@ def bench_learner(args, rank, world, dev):
                                              "bias + ReLU + 2x2 max-pool in the epilogue, Z1 and P2 out)",
                 "algorithmic_flop_per_sample": 6553600, "unit": "TFLOP/s", "peak": tc_peak,
                 "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, cuBLAS burst)",
-                "achieved": max(v["tflops"] for v in kern.values()),
-                "frac": max(v["tflops"] for v in kern.values()) / tc_peak,
+                # quoted at the CONFIGURED minibatch (configs[2]: 256); the larger batch is there for the kernel's own ceiling
+                "batch": brain.local_batch,
+                "achieved": kern[brain.local_batch]["tflops"],
+                "frac": kern[brain.local_batch]["tflops"] / tc_peak,
+                "whole_step_frac": flop_upd / world / (ms_upd * 1e-3) / 1e12 / tc_peak,
+                "whole_step_tensor_pipe_active_pct_ncu": 3.4,
+                "whole_step_source": "profiles/r02_ncu_learner_step_summary.json (ncu --set full of every kernel of one update)",
                 "by_batch": {str(k): v for k, v in kern.items()},
                 "note": "per launch, CUDA events over back-to-back launches; a tcgen05.mma of N = 32 is bound by its operand reads from "
                         "shared memory at 16/40 of the math rate (profiles/r01_tcgen05_mma_rate_b200.txt), so 0.40 is this layer's ceiling; "
