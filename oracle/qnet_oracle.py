@@ -1,9 +1,17 @@
 """Q-network oracle -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
-float64 torch-CPU restatement of the TensorFlow-1.12 graph the reference builds.  PARITY UNPINNED:
-the arithmetic lives in TensorFlow 1.12.0 (third-party, not vendored, not installable here; version
-from train_history/*/bird-*.meta) and the reference ships neither tests nor weights for it, so this
-restatement is anchored on the reference's call sites only:
+float64 torch-CPU restatement of the TensorFlow-1.12 graph the reference builds.
+
+What IS pinned (round 2): the graph itself.  Every checkpoint under train_history/ carries the serialized GraphDef that
+_createQNetwork built (forward ops with their attributes, the loss, the complete tf.gradients sub-graph, the ApplyAdam ops
+with their constants).  oracle/tf_graph.py parses it (fixtures tests/golden/ref_graph_*.json) and executes it op by op in
+NumPy float64; tests/test_oracle_qnet_graph.py holds this file to it: op sequence, strides, paddings, variable shapes in
+creation order, Adam constants -- and Q(s), Q_target(s'), the cost, every gradient tensor and two optimizer steps to 1e-9.
+
+What stays PARITY UNPINNED: TensorFlow 1.12.0's own floating-point kernels (cuDNN / Eigen summation order; third-party, not
+vendored, not installable here; version from train_history/*/bird-*.meta).  The reference ships neither tests, weights nor
+recorded outputs for them, so the per-op arithmetic is restated from TF 1.12's published semantics and anchored on the
+reference's call sites:
 
   BrainDQN.py:119-163        graph: NHWC, HWIO weights, SAME padding (symmetric 2 / 1 / 1 here),
                              one 2x2 max-pool, flatten (h,w,c), fc 1600->512->2, sum-of-squares loss
