@@ -1011,6 +1011,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_bwd23_kernel(const __grid_
             const int p = r % kP2, bh = p / kG2, bw = p - bh * kG2;
             const int b = (int)(tile * 2 + (r >= kP2 ? 1 : 0));
             // ---- epilogue 1: dZ2 = dA2 * relu'(a2), zeros at invalid positions -> HBM and the second slab
+            const bool ok = in_tile && bh < 5 && bw < 5;
+            uint4 araw[8];                                   // the ReLU mask does not depend on the accumulator: fetched while the MMAs run
+            if (ok) {
+                const uint4 *am = reinterpret_cast<const uint4 *>(g.a2 + grow * 64);
+#pragma unroll
+                for (int c = 0; c < 8; c++) araw[c] = __ldg(am + c);
+            }
             tc::mbar_wait(tc::smem_u32(&bar_acc1_full), i & 1);
             tc::tc_fence_after();
             float v[64];
@@ -1019,16 +1026,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_bwd23_kernel(const __grid_
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_acc1_empty));
-            const bool ok = in_tile && bh < 5 && bw < 5;
             uint4 outw[8];
 #pragma unroll
             for (int c = 0; c < 8; c++) outw[c] = make_uint4(0, 0, 0, 0);
             if (ok) {
-                const uint4 *am = reinterpret_cast<const uint4 *>(g.a2 + grow * 64);
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
-                    const uint4 raw = __ldg(am + c);
-                    const uint32_t *h = reinterpret_cast<const uint32_t *>(&raw);
+                    const uint32_t *h = reinterpret_cast<const uint32_t *>(&araw[c]);
                     uint32_t w[4];
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
@@ -1053,10 +1057,29 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_bwd23_kernel(const __grid_
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_slab2));
             // ---- epilogue 2: dZ1 = unpool(dP2) * relu'(z1); row (b, bh, bw) holds the 2x2 block of pooled positions (2bh-1+rr, 2bw-1+ss)
+            // the window activations of all four channel groups of one pooled position: 16 independent 16-byte loads in flight (they
+            // were four dependent rounds of four -- 16 L2 round trips per thread and tile); the first position's before the wait
+            const size_t off[4] = {0, (size_t)kC1, (size_t)kG1 * kC1, (size_t)kG1 * kC1 + kC1};
+            uint4 zr[4][4];
+            bool valid = false;
+            size_t base = 0;
+            auto issue = [&](int rs) {
+                const int ph = 2 * bh - 1 + (rs >> 1), pw = 2 * bw - 1 + (rs & 1);
+                valid = in_tile && (unsigned)ph < 10u && (unsigned)pw < 10u;
+                base = valid ? ((size_t)b * kP1 + (2 * ph) * kG1 + 2 * pw) * kC1 : 0;
+                if (valid) {
+#pragma unroll
+                    for (int cg = 0; cg < 4; cg++)
+#pragma unroll
+                        for (int k = 0; k < 4; k++) zr[cg][k] = __ldg(reinterpret_cast<const uint4 *>(g.z1 + base + off[k] + cg * 8));
+                }
+            };
+            issue(0);
             tc::mbar_wait(tc::smem_u32(&bar_acc2_full), i & 1);
             tc::tc_fence_after();
 #pragma unroll 1
             for (int rs = 0; rs < 4; rs++) {
+                if (rs > 0) issue(rs);
                 float gq[32];
                 tc::tmem_ld32(acc2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(rs * 32), gq);
                 if (rs == 3) {                             // accumulator drained: hand it back before the stores
@@ -1064,10 +1087,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_bwd23_kernel(const __grid_
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_acc2_empty));
                 }
-                const int ph = 2 * bh - 1 + (rs >> 1), pw = 2 * bw - 1 + (rs & 1);
-                if (in_tile && (unsigned)ph < 10u && (unsigned)pw < 10u) {
-                    const size_t base = ((size_t)b * kP1 + (2 * ph) * kG1 + 2 * pw) * kC1;
-                    const size_t off[4] = {0, (size_t)kC1, (size_t)kG1 * kC1, (size_t)kG1 * kC1 + kC1};
+                if (valid) {
 #pragma unroll
                     for (int cg = 0; cg < 4; cg++) {
                         float gg[8], z[4][8];
@@ -1075,8 +1095,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_bwd23_kernel(const __grid_
                         for (int k = 0; k < 8; k++) gg[k] = tc::round1(gq[cg * 8 + k], g.f16);      // dP2 was a 16-bit tensor
 #pragma unroll
                         for (int k = 0; k < 4; k++) {
-                            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(g.z1 + base + off[k] + cg * 8));
-                            const uint32_t *h = reinterpret_cast<const uint32_t *>(&raw);
+                            const uint32_t *h = reinterpret_cast<const uint32_t *>(&zr[cg][k]);
 #pragma unroll
                             for (int e = 0; e < 4; e++) { const float2 f = tc::unpack2(h[e], g.f16); z[k][2 * e] = f.x; z[k][2 * e + 1] = f.y; }
                         }
