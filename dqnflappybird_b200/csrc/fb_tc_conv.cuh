@@ -272,17 +272,34 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_wgrad_kernel(const __grid_
         const int q = warp & 3;
         tc::mbar_wait(tc::smem_u32(&bar_acc), 0);
         tc::tc_fence_after();
+        // The partial sums go out as whole 128-byte lines: a lane holds 32 columns of ITS row, the warp transposes them through
+        // shared memory (the operand stages are free by now; 16-byte pieces XOR-swizzled by row, conflict-free both ways) so that
+        // eight lanes store one row's 128 bytes.  Straight from the registers every store instruction touched 32 rows with 16
+        // bytes each -- 17 MB of half-sector writes per update from the three weight-gradient kernels, at the update's very end.
+        // (EP must have EpiStoreF32's fields: out, rows, ld, split_stride, scale.)
+        float4 *stage = reinterpret_cast<float4 *>(smem_raw + (smem - tc::smem_u32(smem_raw))) + q * 256;      // 4 KB per warp
+        float *outp = ep.out + (size_t)blockIdx.x * ep.split_stride;
 #pragma unroll 1
         for (int a = 0; a < NACC; a++)
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                float v[16];
-                if (nkb > 0) tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c0), v);
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                float v[32];
+                if (nkb > 0) tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c0), v);
                 else {
 #pragma unroll
-                    for (int i = 0; i < 16; i++) v[i] = 0.f;
+                    for (int i = 0; i < 32; i++) v[i] = 0.f;
                 }
-                ep(a * 128 + q * 32 + lane, c0, v, (int)blockIdx.x, nullptr);
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    stage[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j] * ep.scale, v[4 * j + 1] * ep.scale, v[4 * j + 2] * ep.scale, v[4 * j + 3] * ep.scale);
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int r = (lane >> 3) + 4 * j, c4 = lane & 7, row = a * 128 + q * 32 + r;
+                    const float4 x = stage[r * 8 + (c4 ^ (r & 7))];
+                    if (row < ep.rows) *reinterpret_cast<float4 *>(outp + (size_t)row * ep.ld + c0 + 4 * c4) = x;
+                }
+                __syncwarp();
             }
     }
     tc::tc_fence_before();
