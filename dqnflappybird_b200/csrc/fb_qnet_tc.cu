@@ -151,15 +151,42 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
         tc::mbar_wait(tc::smem_u32(&bar_accum), 0);
         tc::tc_fence_after();
         const int row = mt * 128 + q * 32 + lane;
+        if constexpr (EP::kRowMajorF32) {
+            // fp32 rows out as whole 128-byte lines: the warp transposes 32 columns of its 32 rows through shared memory (the
+            // operand stages are free by now), eight lanes store one row's 128 bytes -- see tc_wgrad_kernel
+            float4 *stage = reinterpret_cast<float4 *>(smem_raw + (smem - tc::smem_u32(smem_raw))) + q * 256;
+            float *outp = ep.out + (size_t)blockIdx.z * ep.split_stride;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-            float v[16];
-            if (nkb > 0) tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            else {
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                float v[32];
+                if (nkb > 0) tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                else {
 #pragma unroll
-                for (int i = 0; i < 16; i++) v[i] = 0.f;
+                    for (int i = 0; i < 32; i++) v[i] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    stage[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j] * ep.scale, v[4 * j + 1] * ep.scale, v[4 * j + 2] * ep.scale, v[4 * j + 3] * ep.scale);
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int r = (lane >> 3) + 4 * j, c4 = lane & 7, orow = mt * 128 + q * 32 + r;
+                    const float4 x = stage[r * 8 + (c4 ^ (r & 7))];
+                    if (orow < ep.rows) *reinterpret_cast<float4 *>(outp + (size_t)orow * ep.ld + n0 + c0 + 4 * c4) = x;
+                }
+                __syncwarp();
             }
-            ep(row, n0 + c0, v, (int)blockIdx.z, nullptr);
+        } else {
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                float v[16];
+                if (nkb > 0) tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] = 0.f;
+                }
+                ep(row, n0 + c0, v, (int)blockIdx.z, nullptr);
+            }
         }
     }
     tc::tc_fence_before();
@@ -255,6 +282,7 @@ struct EpiConv3 {               // rows on the 7-grid -> dense A3 [B][25][64] (T
 struct EpiFc1Dgrad {            // dA3 [B][1600] masked by relu(a3) -> dZ3 on the 7-grid [B*49][64]
     bf16 *dz3; const bf16 *a3; int B, f16;
     static constexpr const float *bias = nullptr;
+    static constexpr bool kRowMajorF32 = false;
     __device__ void operator()(int row, int col, float (&v)[16], int, const float *) const {
         if (row >= B) return;
         float a[16];
@@ -291,6 +319,7 @@ struct EpiStoreF32 {            // weight-gradient partials [split][rows][ld] an
     float *out; int rows, ld; size_t split_stride;
     float scale = 1.f;          // a power of two: un-scales gradients that were scaled for the fp16 operand format
     static constexpr const float *bias = nullptr;
+    static constexpr bool kRowMajorF32 = true;     // tc_gemm_kernel / tc_wgrad_kernel store it as whole lines (warp transpose)
     __device__ void operator()(int row, int col, float (&v)[16], int split, const float *) const {
         if (row >= rows) return;
         float4 *d = reinterpret_cast<float4 *>(out + (size_t)split * split_stride + (size_t)row * ld + col);
