@@ -214,9 +214,7 @@ __device__ __forceinline__ void store_bf16x16(bf16 *dst, const float (&v)[16], i
     uint32_t w[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) w[i] = tc::pack2(v[2 * i], v[2 * i + 1], f16);
-    uint4 *d = reinterpret_cast<uint4 *>(dst);
-    d[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    d[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    tc::st_global_256(dst, make_uint4(w[0], w[1], w[2], w[3]), make_uint4(w[4], w[5], w[6], w[7]));      // every caller's dst is 32-byte aligned
 }
 __device__ __forceinline__ void load_bf16x16(const bf16 *src, float (&v)[16], int f16) {
     const uint4 *s = reinterpret_cast<const uint4 *>(src);
@@ -382,7 +380,7 @@ __global__ void pool_pack_kernel(const bf16 *z1, int B, bf16 *p2, int f16) {
 
 // eight channels of one pooling window: g = gradient of the pooled value, z[k] = the window's four activations (k = row-major
 // position); the gradient goes to the FIRST maximum (TF MaxPoolGrad) if it is positive (ReluGrad); bf16 out, 16 bytes a position
-__device__ __forceinline__ void unpool_route8(const float (&g)[8], const float (&z)[4][8], bf16 *dst, const size_t (&off)[4], int f16) {
+__device__ __forceinline__ void unpool_pack8(const float (&g)[8], const float (&z)[4][8], uint4 (&out)[4], int f16) {
     float o[4][8];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -400,8 +398,14 @@ __device__ __forceinline__ void unpool_route8(const float (&g)[8], const float (
         uint32_t w[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) w[i] = tc::pack2(o[k][2 * i], o[k][2 * i + 1], f16);
-        *reinterpret_cast<uint4 *>(dst + off[k]) = make_uint4(w[0], w[1], w[2], w[3]);
+        out[k] = make_uint4(w[0], w[1], w[2], w[3]);
     }
+}
+__device__ __forceinline__ void unpool_route8(const float (&g)[8], const float (&z)[4][8], bf16 *dst, const size_t (&off)[4], int f16) {
+    uint4 out[4];
+    unpool_pack8(g, z, out, f16);
+#pragma unroll
+    for (int k = 0; k < 4; k++) *reinterpret_cast<uint4 *>(dst + off[k]) = out[k];
 }
 
 // dZ1 = unpool(dP2) * relu'(z1): the gradient goes to the first maximum of each window (TF MaxPoolGrad)
@@ -1074,7 +1078,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_bwd23_kernel(const __grid_
             if (in_tile) {
                 uint4 *d = reinterpret_cast<uint4 *>(g.dz2 + grow * 64);
 #pragma unroll
-                for (int c = 0; c < 8; c++) d[c] = outw[c];
+                for (int c = 0; c < 8; c += 2) tc::st_global_256(d + c, outw[c], outw[c + 1]);
             }
             {   // slab-2 row r + 8, 16-byte chunk c at ((c ^ (row & 7)) << 4): the layout a TMA SWIZZLE_128B load would have produced
                 const int R = r + 8;
@@ -1118,17 +1122,24 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_bwd23_kernel(const __grid_
                 }
                 if (valid) {
 #pragma unroll
-                    for (int cg = 0; cg < 4; cg++) {
-                        float gg[8], z[4][8];
+                    for (int cp = 0; cp < 2; cp++) {                      // two channel groups = 32 bytes of a position: one store
+                        uint4 outp[2][4];
 #pragma unroll
-                        for (int k = 0; k < 8; k++) gg[k] = tc::round1(gq[cg * 8 + k], g.f16);      // dP2 was a 16-bit tensor
+                        for (int hh = 0; hh < 2; hh++) {
+                            const int cg = 2 * cp + hh;
+                            float gg[8], z[4][8];
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const uint32_t *h = reinterpret_cast<const uint32_t *>(&zr[cg][k]);
+                            for (int k = 0; k < 8; k++) gg[k] = tc::round1(gq[cg * 8 + k], g.f16);      // dP2 was a 16-bit tensor
 #pragma unroll
-                            for (int e = 0; e < 4; e++) { const float2 f = tc::unpack2(h[e], g.f16); z[k][2 * e] = f.x; z[k][2 * e + 1] = f.y; }
+                            for (int k = 0; k < 4; k++) {
+                                const uint32_t *h = reinterpret_cast<const uint32_t *>(&zr[cg][k]);
+#pragma unroll
+                                for (int e = 0; e < 4; e++) { const float2 f = tc::unpack2(h[e], g.f16); z[k][2 * e] = f.x; z[k][2 * e + 1] = f.y; }
+                            }
+                            unpool_pack8(gg, z, outp[hh], g.f16);
                         }
-                        unpool_route8(gg, z, g.dz1 + base + cg * 8, off, g.f16);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) tc::st_global_256(g.dz1 + base + off[k] + cp * 16, outp[0][k], outp[1][k]);
                     }
                 }
                 __syncwarp();
@@ -1304,7 +1315,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_fwd23_kernel(const __grid_
             if (in_tile && g.a2 != nullptr) {
                 uint4 *d = reinterpret_cast<uint4 *>(g.a2 + grow * 64);
 #pragma unroll
-                for (int c = 0; c < 8; c++) d[c] = outw[c];
+                for (int c = 0; c < 8; c += 2) tc::st_global_256(d + c, outw[c], outw[c + 1]);
             }
             {
                 const int R = r + 8;
@@ -1332,13 +1343,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_fwd23_kernel(const __grid_
             if (ok) {
                 uint4 *d = reinterpret_cast<uint4 *>(g.a3 + ((size_t)b * 25 + oh * 5 + ow) * 64);
 #pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    uint32_t w[4];
+                for (int c = 0; c < 8; c += 2) {
+                    uint32_t w[8];
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
+                    for (int k = 0; k < 8; k++) {
                         w[k] = tc::pack2(fmaxf(v[c * 8 + 2 * k] + b3[c * 8 + 2 * k], 0.f), fmaxf(v[c * 8 + 2 * k + 1] + b3[c * 8 + 2 * k + 1], 0.f), g.f16);
                     }
-                    d[c] = make_uint4(w[0], w[1], w[2], w[3]);
+                    tc::st_global_256(d + c, make_uint4(w[0], w[1], w[2], w[3]), make_uint4(w[4], w[5], w[6], w[7]));
                 }
             }
         }

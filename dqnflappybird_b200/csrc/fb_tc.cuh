@@ -199,6 +199,14 @@ __device__ __forceinline__ float round1(float a, int f16) {           // the val
     return __bfloat162float(__float2bfloat16(a));
 }
 
+// 32 bytes from one lane in one instruction (STG.256, sm_100): epilogues whose lanes own different ROWS used to write 16 bytes of
+// 32 different lines per store -- half sectors; two pieces of a row together are one whole sector.  p must be 32-byte aligned.
+__device__ __forceinline__ void st_global_256(void *p, const uint4 &a, const uint4 &b) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z),
+                 "r"(b.w)
+                 : "memory");
+}
+
 // host: launch with programmatic stream serialization allowed (see pdl_wait).  An early-launched CTA that asked for an SM's
 // whole shared memory holds that SM while it waits in griddepcontrol.wait: where independent kernels of other streams could
 // have used it, the caller switches the early launch off for that one kernel (pdl_next_launch_plain).

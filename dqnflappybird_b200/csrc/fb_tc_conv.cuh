@@ -556,7 +556,8 @@ __global__ void __launch_bounds__(FROM_X2 ? kRoleThreads1 : kFusedThreads, 1) tc
             if (ok && g.z1 != nullptr) {
                 uint4 *d = reinterpret_cast<uint4 *>(g.z1 + ((size_t)b * 441 + oh * 21 + ow) * BN);
 #pragma unroll
-                for (int k = 0; k < 4; k++) d[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+                for (int k = 0; k < 4; k += 2)
+                    tc::st_global_256(d + k, make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]), make_uint4(w[4 * k + 4], w[4 * k + 5], w[4 * k + 6], w[4 * k + 7]));
             }
             if (g.p2 == nullptr) continue;               // (measurement only: no pooling, no output)
             if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
