@@ -217,8 +217,8 @@ __device__ __forceinline__ void store_bf16x16(bf16 *dst, const float (&v)[16], i
     tc::st_global_256(dst, make_uint4(w[0], w[1], w[2], w[3]), make_uint4(w[4], w[5], w[6], w[7]));      // every caller's dst is 32-byte aligned
 }
 __device__ __forceinline__ void load_bf16x16(const bf16 *src, float (&v)[16], int f16) {
-    const uint4 *s = reinterpret_cast<const uint4 *>(src);
-    uint4 a = s[0], b = s[1];
+    uint4 a, b;
+    tc::ld_global_nc_256(src, a, b);                 // (activations of an earlier kernel: read-only here; 32-byte aligned at every caller)
     uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -1049,7 +1049,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_bwd23_kernel(const __grid_
             if (ok) {
                 const uint4 *am = reinterpret_cast<const uint4 *>(g.a2 + grow * 64);
 #pragma unroll
-                for (int c = 0; c < 8; c++) araw[c] = __ldg(am + c);
+                for (int c = 0; c < 8; c += 2) tc::ld_global_nc_256(am + c, araw[c], araw[c + 1]);
             }
             tc::mbar_wait(tc::smem_u32(&bar_acc1_full), i & 1);
             tc::tc_fence_after();
@@ -1102,9 +1102,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_bwd23_kernel(const __grid_
                 base = valid ? ((size_t)b * kP1 + (2 * ph) * kG1 + 2 * pw) * kC1 : 0;
                 if (valid) {
 #pragma unroll
-                    for (int cg = 0; cg < 4; cg++)
+                    for (int cp = 0; cp < 2; cp++)
 #pragma unroll
-                        for (int k = 0; k < 4; k++) zr[cg][k] = __ldg(reinterpret_cast<const uint4 *>(g.z1 + base + off[k] + cg * 8));
+                        for (int k = 0; k < 4; k++) tc::ld_global_nc_256(g.z1 + base + off[k] + cp * 16, zr[2 * cp][k], zr[2 * cp + 1][k]);
                 }
             };
             issue(0);

@@ -207,6 +207,12 @@ __device__ __forceinline__ void st_global_256(void *p, const uint4 &a, const uin
                  : "memory");
 }
 
+__device__ __forceinline__ void ld_global_nc_256(const void *p, uint4 &a, uint4 &b) {          // read-only data, 32-byte aligned
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
+
 // host: launch with programmatic stream serialization allowed (see pdl_wait).  An early-launched CTA that asked for an SM's
 // whole shared memory holds that SM while it waits in griddepcontrol.wait: where independent kernels of other streams could
 // have used it, the caller switches the early launch off for that one kernel (pdl_next_launch_plain).
