@@ -809,7 +809,7 @@ __global__ void __launch_bounds__(128) fc1_head_train_kernel(const float *__rest
 // kFinWarps-th term, and the sub-sums are added in a fixed order (deterministic for a given batch size).  Two warps of 32
 // loads in flight each: the whole grid (2,486 CTAs at hidden 512) is resident at once, so the kernel costs one CTA's chain of
 // round trips (partials -> Adam state -> stores), not two waves of it -- it is the last stage of every update.
-constexpr int kFinWarps = 2, kFinInflight = 32;
+constexpr int kFinWarps = 2, kFinInflight = 40;      // 74 conv1 splits at minibatch 256: one batch of loads per warp
 struct FinalizeArgs {
     const float *part1, *part2, *part3;             // [splits][rows][N]
     int s1, s2, s3;                                  // number of splits (fc1's weight gradient is written in place)
@@ -850,14 +850,18 @@ __global__ void __launch_bounds__(256) adam_wf1_kernel(QnetLayout L, const float
 }
 __global__ void __launch_bounds__(32 * kFinWarps) finalize_grads_kernel(const FinalizeArgs a, QnetLayout L, float *__restrict__ grads, const AdamDev ad,
                                                                        const PackedWeights pw) {
-    tc::pdl_wait();
-    if (!ad.on) tc::pdl_launch();
     __shared__ float red[kFinWarps][32];
-    const float alpha = ad.on ? *ad.alpha : 0.f;
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5, H = L.hidden;
     const int k = blockIdx.x * 32 + lane;            // compact index: [0, wf1) then [bf1, total)
     const int n_compact = L.wf1 + (L.total - L.bf1);
     const int i = k < L.wf1 ? k : k - L.wf1 + L.bf1;
+    // the Adam state of these parameters was last written by the PREVIOUS step's launch of this kernel: fetched while this
+    // step's weight gradients still run (one round trip off the update's tail)
+    float p0 = 0.f, m0 = 0.f, v0 = 0.f;
+    if (ad.on && g == 0 && k < n_compact) { p0 = ad.p[i]; m0 = ad.m[i]; v0 = ad.v[i]; }
+    tc::pdl_wait();
+    if (!ad.on) tc::pdl_launch();
+    const float alpha = ad.on ? *ad.alpha : 0.f;
     float s = 0.f;
     // terms z = g, g + kFinWarps, ... of one element, added in that order; kFinInflight loads are issued before the first add
     // (the sums over 49 .. 147 split-K partials were a chain of dependent L2 round trips)
@@ -912,7 +916,11 @@ __global__ void __launch_bounds__(32 * kFinWarps) finalize_grads_kernel(const Fi
         for (int w = 0; w < kFinWarps; w++) t += red[w][lane];
         if (i < L.bf1 + H) t *= a.inv_scale;         // conv / fc1 weights and biases: sums of scaled gradient tensors (the head's are not)
         grads[i] = t;
-        if (ad.on) adam_one(i, t, ad.p, ad.m, ad.v, alpha, ad.beta1, ad.beta2, ad.eps, ad.grad_scale, L, pw);
+        if (ad.on) {
+            const float pi = adam_math(t, p0, m0, v0, alpha, ad.beta1, ad.beta2, ad.eps, ad.grad_scale);
+            ad.m[i] = m0; ad.v[i] = v0; ad.p[i] = pi;
+            scatter_packed(i, pi, L, pw, 0);
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.loss_out) {       // the loss: row-group sums in order
         float t = 0.f;
