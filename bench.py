@@ -726,7 +726,7 @@ def bench_learner(args, rank, world, dev):
                 "achieved": kern[brain.local_batch]["tflops"],
                 "frac": kern[brain.local_batch]["tflops"] / tc_peak,
                 "whole_step_frac": flop_upd / world / (ms_upd * 1e-3) / 1e12 / tc_peak,
-                "whole_step_tensor_pipe_active_pct_ncu": 3.4,
+                "whole_step_tensor_pipe_active_pct_ncu": 3.1,
                 "whole_step_source": "profiles/r02_ncu_learner_step_summary.json (ncu --set full of every kernel of one update)",
                 "by_batch": {str(k): v for k, v in kern.items()},
                 "note": "per launch, CUDA events over back-to-back launches; a tcgen05.mma of N = 32 is bound by its operand reads from "
