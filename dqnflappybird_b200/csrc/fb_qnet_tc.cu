@@ -490,11 +490,20 @@ __global__ void __launch_bounds__(256) colsum_kernel(ColsumJobs jobs) {
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) acc[i] = 0.f;
-    for (int r = r0 + rl; r < r1; r += rows_per_pass) {
-        uint4 raw = __ldg(reinterpret_cast<const uint4 *>(jb.x + (size_t)r * jb.N) + v);
-        const uint32_t *h = reinterpret_cast<const uint32_t *>(&raw);
+    for (int r = r0 + rl; r < r1; r += 8 * rows_per_pass) {        // eight rows in flight per thread, added in row order as before
+        uint4 raw[8];
 #pragma unroll
-        for (int i = 0; i < 4; i++) { float2 f = tc::unpack2(h[i], jobs.f16); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
+        for (int u = 0; u < 8; u++) {
+            const int rr = r + u * rows_per_pass;
+            raw[u] = rr < r1 ? __ldg(reinterpret_cast<const uint4 *>(jb.x + (size_t)rr * jb.N) + v) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (r + u * rows_per_pass >= r1) break;
+            const uint32_t *h = reinterpret_cast<const uint32_t *>(&raw[u]);
+#pragma unroll
+            for (int i = 0; i < 4; i++) { float2 f = tc::unpack2(h[i], jobs.f16); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
+        }
     }
     // lanes with equal (lane % vec) hold the same columns: butterfly over the other lane bits, then across warps
 #pragma unroll
