@@ -1490,8 +1490,9 @@ struct TcState {
                                 // the conv3 weight gradient, which was ready, queued behind them (121 -> 114.5 us per update, measured).
                                 // 2: fused backward, 4 / 8: conv3 / conv2 weight gradient, 16: finalize -- all measured slower or equal
     int fuse_bwd;               // 1 (default): conv3 / conv2 data gradients and the un-pool as one kernel (also FB_TC_FUSE_BWD)
-    int conv1_mode;             // 2 (default): pooled epilogue, slab from u8 when no backward follows; 1: slab always from X2;
-                                // 0: separate pack_x2 / conv1 / pool_pack kernels
+    int conv1_mode;             // 4 (default): 3 up to minibatch 512, 2 above.  3: conv1 from the u8 frames in the training forward too, X2
+                                // (only the conv1 weight gradient reads it) packed beside the forwards; 2: pooled epilogue, slab from u8
+                                // when no backward follows; 1: slab always from X2; 0: separate pack_x2 / conv1 / pool_pack kernels
 };
 
 namespace {
@@ -1671,7 +1672,7 @@ int tc_state_create(fb_qnet *n) {
     t->use_graph = 1;
     { const char *e = getenv("FB_TC_FUSE_BWD"); t->fuse_bwd = (e && e[0] == '0') ? 0 : 1; }
     { const char *e = getenv("FB_TC_FUSE_FWD"); t->fuse_fwd = (e && e[0] == '0') ? 0 : 1; }
-    { const char *e = getenv("FB_TC_CONV1_MODE"); t->conv1_mode = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 2; }
+    { const char *e = getenv("FB_TC_CONV1_MODE"); t->conv1_mode = (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 4; }
     { const char *e = getenv("FB_TC_NOPDL"); t->nopdl = e ? atoi(e) : 1; }
     n->tc = t;
     return FB_OK;
@@ -1753,6 +1754,9 @@ int tc_slot_for(fb_qnet *n, const float *params_dev, int want_slot, cudaStream_t
     return FB_OK;
 }
 
+// the conv1 path in effect at this minibatch: measured, mode 3 wins up to 512 samples (100.9 vs 102.9 us per update at 256) and
+// loses above (1,024: 235 vs 213 us; 4,096: 689 vs 635 us -- the u8 path is bound by shared memory, the X2 path by HBM)
+static inline int conv1_mode_at(const TcState *t, int B) { return t->conv1_mode == 4 ? (B <= kFuseMaxBatch ? 3 : 2) : t->conv1_mode; }
 static FrameView g_probe_view;                    // frames of the last forward (the fused conv1 probe re-reads them)
 // keep != 0: this forward's activations feed a backward pass (Z1 and, for the conv1 weight gradient, X2 are written)
 // td != nullptr: the TD target / loss is fused into the head kernel; `join` (if any) is waited for first -- it marks the end
@@ -1778,11 +1782,12 @@ static int tc_forward_impl(fb_qnet *n, int slot, int w, const float *params_dev,
     //   keep == 0 (acting, Q(s') forwards): slab built in the kernel straight from the u8 frames -- no X2 either;
     //   keep != 0: X2 is materialised once (the conv1 weight gradient contracts over it by TMA) and feeds the slab.
     // conv1_mode 0 restores the three separate kernels (pack_x2, conv1, pool_pack).
-    if (t->conv1_mode == 0) {
+    const int c1mode = conv1_mode_at(t, B);
+    if (c1mode == 0) {
         FB_CUDA_OK(tc::launch_pdl(pack_x2_kernel, dim3((unsigned)(((size_t)P1 * 8 + 255) / 256)), dim3(256), 0, st, fv, B, f.x2, t->f16));
         FB_CUDA_OK((launch_tc_conv<32, kSlab1, 1, 4, 6, 1>(p->x2_s[w], wm.w1p, p->conv1, t->n_sms, EpiConv1{f.z1, params_dev + L.b1, P1, t->f16}, st)));
         FB_CUDA_OK(tc::launch_pdl(pool_pack_kernel, dim3((unsigned)(((size_t)B * 36 * 16 + 255) / 256)), dim3(256), 0, st, f.z1, B, f.p2, t->f16));
-    } else if ((keep && t->conv1_mode != 3) || t->conv1_mode == 1) {
+    } else if ((keep && c1mode != 3) || c1mode == 1) {
         FB_CUDA_OK(tc::launch_pdl(pack_x2_kernel, dim3((unsigned)(((size_t)P1 * 8 + 255) / 256)), dim3(256), 0, st, fv, B, f.x2, t->f16));
         FB_CUDA_OK((launch_tc_conv1_fused<6, true>(p->x2_s[w], wm.w1p, Conv1FusedParams{fv, B, params_dev + L.b1, keep ? f.z1 : nullptr, f.p2, t->f16},
                                                   t->n_sms, st)));
@@ -1885,9 +1890,13 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     // the TD target, loss and dLoss/dQ come out of its head kernel, which first waits for Q(s') from the other stream
     FB_CUDA_OK(cudaEventRecord(t->ev[e], sx));
     const int e_x2 = 13;
-    if (t->conv1_mode == 3) {                  // X2 of s for the conv1 weight gradient: behind Q(s') on the side stream
-        FB_CUDA_OK(tc::launch_pdl(pack_x2_kernel, dim3((unsigned)(((size_t)P1 * 8 + 255) / 256)), dim3(256), 0, sx, a.fs, B, f.x2, t->f16));
-        FB_CUDA_OK(cudaEventRecord(t->ev[e_x2], sx));
+    const int c1mode = conv1_mode_at(t, B);
+    if (c1mode == 3) {                         // X2 of s for the conv1 weight gradient: early, on the stream of the replay gather
+        FB_CUDA_OK(cudaEventRecord(t->ev[e_x2], st));          // (st has seen the sampler; nothing else of this step yet)
+        FB_CUDA_OK(cudaStreamWaitEvent(t->aux4, t->ev[e_x2], 0));
+        pack_x2_kernel<<<dim3((unsigned)(((size_t)P1 * 8 + 255) / 256)), dim3(256), 0, t->aux4>>>(a.fs, B, f.x2, t->f16);
+        FB_CUDA_OK(cudaGetLastError());
+        FB_CUDA_OK(cudaEventRecord(t->ev[e_x2], t->aux4));
     }
     TdFuse td{1, a.variant, a.loss_sum, a.global_batch, n->per_broadcast, a.gamma, n->q_next, n->q_next_online, a.rewards, a.isw, a.actions,
               a.terminals, n->dq, a.abs_err, a.q_target, t->loss_terms};
@@ -1977,7 +1986,7 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
         FB_CUDA_OK(colsum_on(t->dz1, t->bp1, P1, 32, kChunk1, c1));
     }
     // conv1 weight gradient (no input gradient there); the bias gradients = column sums of the dZ tensors ran beside it
-    if (t->conv1_mode == 3) FB_CUDA_OK(cudaStreamWaitEvent(st, t->ev[e_x2], 0));
+    if (c1mode == 3) FB_CUDA_OK(cudaStreamWaitEvent(st, t->ev[e_x2], 0));
     tc::pdl_next_launch_plain((t->nopdl & 1) && B <= kFuseMaxBatch);      // (large minibatches fill the GPU by themselves: early launch pays there)
     FB_CUDA_OK((launch_tc_wgrad<32, 2, kSlabW1, 1, 6>(p->x2_w, p->dz1_b, p->conv1_w, p->s1, EpiStoreF32{t->part1, 256, 32, (size_t)256 * 32}, st)));
     FB_CUDA_OK(fork(sx, st));
@@ -2021,7 +2030,7 @@ int tc_drop_graphs(fb_qnet *n) {
 }
 
 extern "C" int fb_qnet_set_conv1_mode(fb_qnet *n, int mode) {
-    FB_REQUIRE(n != nullptr && n->tc != nullptr && mode >= 0 && mode <= 3, "fb_qnet_set_conv1_mode: needs a tensor-core precision and mode 0..3");
+    FB_REQUIRE(n != nullptr && n->tc != nullptr && mode >= 0 && mode <= 4, "fb_qnet_set_conv1_mode: needs a tensor-core precision and mode 0..4");
     n->tc->conv1_mode = mode;
     for (auto &g : n->tc->graphs) destroy_entry(g);
     n->tc->graphs.clear();

@@ -135,7 +135,7 @@ def test_conv1_modes_are_bit_identical(mods):
     _lib, game, qnet = mods
     B = 70
     frames = _env_frames(game, B, 9)
-    nets = [qnet.QNetwork(max_batch=128, seed=2, precision="bf16") for _ in range(4)]
+    nets = [qnet.QNetwork(max_batch=128, seed=2, precision="bf16") for _ in range(5)]      # modes 0..3 and 4 = the default choice by minibatch
     for mode, n in enumerate(nets):
         n.params.mul_(4.0); n.target.mul_(4.0)
         _lib.check(_lib.lib().fb_qnet_set_conv1_mode(n._h, mode), "fb_qnet_set_conv1_mode")
