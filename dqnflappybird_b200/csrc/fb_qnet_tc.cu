@@ -1490,7 +1490,8 @@ struct TcState {
                                 // the conv3 weight gradient, which was ready, queued behind them (121 -> 114.5 us per update, measured).
                                 // 2: fused backward, 4 / 8: conv3 / conv2 weight gradient, 16: finalize -- all measured slower or equal
     int fuse_bwd;               // 1 (default): conv3 / conv2 data gradients and the un-pool as one kernel (also FB_TC_FUSE_BWD)
-    int conv1_mode;             // 4 (default): 3 up to minibatch 512, 2 above.  3: conv1 from the u8 frames in the training forward too, X2
+    int step_samples;           // set by train_step_launch around its forwards: the step draws its own minibatch (replay sampling inside)
+    int conv1_mode;             // 4 (default): 3 up to minibatch 512 when the step samples its own minibatch, else 2.  3: conv1 from the u8 frames in the training forward too, X2
                                 // (only the conv1 weight gradient reads it) packed beside the forwards; 2: pooled epilogue, slab from u8
                                 // when no backward follows; 1: slab always from X2; 0: separate pack_x2 / conv1 / pool_pack kernels
 };
@@ -1756,7 +1757,11 @@ int tc_slot_for(fb_qnet *n, const float *params_dev, int want_slot, cudaStream_t
 
 // the conv1 path in effect at this minibatch: measured, mode 3 wins up to 512 samples (100.9 vs 102.9 us per update at 256) and
 // loses above (1,024: 235 vs 213 us; 4,096: 689 vs 635 us -- the u8 path is bound by shared memory, the X2 path by HBM)
-static inline int conv1_mode_at(const TcState *t, int B) { return t->conv1_mode == 4 ? (B <= kFuseMaxBatch ? 3 : 2) : t->conv1_mode; }
+// (and only when the step draws its own minibatch: the replay gather ahead of the X2 conversion on their side stream keeps the
+// conversion's 3,528 CTAs out of the way of the two conv1 launches; on a caller-supplied minibatch 3 costs 105 vs 98 us)
+static inline int conv1_mode_at(const TcState *t, int B) {
+    return t->conv1_mode == 4 ? (B <= kFuseMaxBatch && t->step_samples ? 3 : 2) : t->conv1_mode;
+}
 static FrameView g_probe_view;                    // frames of the last forward (the fused conv1 probe re-reads them)
 // keep != 0: this forward's activations feed a backward pass (Z1 and, for the conv1 weight gradient, X2 are written)
 // td != nullptr: the TD target / loss is fused into the head kernel; `join` (if any) is waited for first -- it marks the end
@@ -1868,6 +1873,7 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
     // frames in place, and the gather into the caller-visible minibatch buffers (frames, actions, rewards, terminals -- the head
     // kernel needs the last three) runs on a side stream beside the forward passes: one dependent stage less (5.5 us)
     const bool in_place = a.pro.replay != nullptr && a.fs.tab != nullptr;
+    t->step_samples = a.pro.replay != nullptr ? 1 : 0;            // (read by conv1_mode_at; reset below, after the step's conv1 launches)
     const int e_gather = 12;
     if (a.pro.replay != nullptr) {
         rc = replay_launch_sample(a.pro, in_place, st); if (rc) return rc;
@@ -1986,6 +1992,7 @@ int train_step_launch(fb_qnet *n, const TcTrainArgs &a, int pack_online, int pac
         FB_CUDA_OK(colsum_on(t->dz1, t->bp1, P1, 32, kChunk1, c1));
     }
     // conv1 weight gradient (no input gradient there); the bias gradients = column sums of the dZ tensors ran beside it
+    t->step_samples = 0;
     if (c1mode == 3) FB_CUDA_OK(cudaStreamWaitEvent(st, t->ev[e_x2], 0));
     tc::pdl_next_launch_plain((t->nopdl & 1) && B <= kFuseMaxBatch);      // (large minibatches fill the GPU by themselves: early launch pays there)
     FB_CUDA_OK((launch_tc_wgrad<32, 2, kSlabW1, 1, 6>(p->x2_w, p->dz1_b, p->conv1_w, p->s1, EpiStoreF32{t->part1, 256, 32, (size_t)256 * 32}, st)));

@@ -180,7 +180,8 @@ int fb_debug_write_probe(uint8_t *dst_dev, int n_chunks, long long stride_bytes,
 /* Tensor-core precisions (FB_PRECISION_BF16 / _FP16) only: replay fb_qnet_loss_backward as a CUDA graph once the same arguments were seen twice
  * (default on; the eager two-stream path is identical work). */
 int fb_qnet_use_graphs(fb_qnet *net, int enable);
-/* Tensor-core precisions only: how conv1 is run (also FB_TC_CONV1_MODE).  4 (default): 3 up to minibatch 512, 2 above (measured).
+/* Tensor-core precisions only: how conv1 is run (also FB_TC_CONV1_MODE).  4 (default): 3 up to minibatch 512 when the step draws its own
+ * minibatch (fb_qnet_train_step_sampled), 2 otherwise (measured).
  * 3: the 2x2 max-pool is fused into conv1's epilogue and its input tile is ALWAYS built in the kernel straight from the u8 frames;
  * the 16-bit input matrix X2, which then only the conv1 weight gradient reads, is packed on a side stream beside the forwards.
  * 2: as 3 when no backward pass follows (acting, Q(s')); the training forward materialises X2 first and reads it by TMA.
